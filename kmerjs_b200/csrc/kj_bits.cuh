@@ -1,0 +1,89 @@
+// kj_bits.cuh -- SIMD-in-register primitives shared by the extraction kernels.
+// All functions are pure integer code, usable on host and device (the host build is what
+// tests/test_bits_host.py exercises exhaustively before any GPU time is spent).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KJ_HD __host__ __device__ __forceinline__
+#else
+#define KJ_HD static inline
+#endif
+
+// 2-bit code of a base byte: (b >> 1) & 3  ->  A=0 C=1 T=2 G=3 (upper and lower case alike).
+// It is a function of the byte, so "codes equal" is a necessary condition for "bytes equal":
+// matching in code space is an exact superset filter, verified on the bytes afterwards.
+KJ_HD uint32_t kj_code(uint32_t b) { return (b >> 1) & 3u; }
+
+// complement in code space: A<->T, C<->G  ==  code ^ 2
+KJ_HD bool kj_is_acgt(uint32_t b) { return b == 'A' || b == 'C' || b == 'G' || b == 'T'; }
+
+// reference complement (lib/kmers.js:12-17,31-38): only upper-case ACGT are mapped
+KJ_HD uint8_t kj_comp_byte(uint8_t b) {
+    switch (b) {
+        case 'A': return 'T';
+        case 'T': return 'A';
+        case 'G': return 'C';
+        case 'C': return 'G';
+        default: return b;
+    }
+}
+
+// 4 bytes (little-endian word) -> 8 bits: code of byte i at bits 2i..2i+1.
+// t keeps bits 1..2 of every byte; one multiply gathers the four 2-bit fields into the top byte
+// (the partial products never overlap, so there are no carries).
+KJ_HD uint32_t kj_pack4(uint32_t w) {
+    return ((w & 0x06060606u) * 0x00820820u) >> 24;
+}
+
+// 16 bytes -> 32 bits: code of byte p at bits 2p..2p+1
+KJ_HD uint32_t kj_pack16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    return kj_pack4(w0) | (kj_pack4(w1) << 8) | (kj_pack4(w2) << 16) | (kj_pack4(w3) << 24);
+}
+
+// 4 bytes -> 4 bits: bit i set iff byte i == '\n'
+KJ_HD uint32_t kj_nl4(uint32_t w) {
+    uint32_t t = ((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;   // msb set iff low 7 bits differ
+    uint32_t z = ~(t | w) & 0x80808080u;                            // msb set iff byte == 0x0A
+    return (z * 0x00204081u) >> 28;                                 // gather the 4 msbs
+}
+
+// 16 bytes -> 16 bits
+KJ_HD uint32_t kj_nl16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    return kj_nl4(w0) | (kj_nl4(w1) << 4) | (kj_nl4(w2) << 8) | (kj_nl4(w3) << 12);
+}
+
+// low 32 bits of (hi:lo) >> s, 0 <= s < 32
+KJ_HD uint32_t kj_funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+
+// 16 code lanes starting `d` lanes (0..31) after the first lane of c0; c0,c1,c2 consecutive words
+KJ_HD uint32_t kj_lanes(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t d) {
+    uint32_t r = (d & 15u) * 2u;
+    return (d & 16u) ? kj_funnel_r(c1, c2, r) : kj_funnel_r(c0, c1, r);
+}
+
+// lanes (bit 2p) whose 2-bit field in acc is zero
+KJ_HD uint32_t kj_zero_lanes(uint32_t acc) {
+    return ~(acc | (acc >> 1)) & 0x55555555u;
+}
+
+// 64-bit finalizer (splitmix64): slot hash and owner hash of 2-bit keys
+KJ_HD uint64_t kj_mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+
+// ordinal = read index (36 bits) | strand (1 bit) | position (27 bits); see DESIGN.md "first-seen order"
+#define KJ_POS_BITS 27
+#define KJ_POS_MAX ((1ull << KJ_POS_BITS) - 1)
+KJ_HD uint64_t kj_ordinal(uint64_t read_idx, uint32_t strand, uint64_t pos) {
+    return (read_idx << (KJ_POS_BITS + 1)) | ((uint64_t)strand << KJ_POS_BITS) | pos;
+}

@@ -1,0 +1,967 @@
+// kj_count.cu -- host side of the extraction + count path (kj_counts_* of include/kmerjs_b200.h)
+// and the small maintenance kernels around the table (rehash, replay, compaction, exchange).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include "kj_internal.hpp"
+#include "kj_scan.cuh"
+
+// ------------------------------------------------------------------------------------ kernels
+
+__global__ void kj_rehash_kernel(KjTable oldt, uint64_t old_cap, KjTable newt, KjCounters *ctr) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_cap;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t key = oldt.keys[i];
+        if (key == KJ_EMPTY) continue;
+        uint64_t ord = oldt.ords ? oldt.ords[i] : ~0ull;
+        if (!kj_insert(newt, ctr, key, ord, oldt.counts[i])) atomicOr(&ctr->error_flags, 0x80000000u);
+    }
+}
+
+__global__ void kj_rehash_irr_kernel(KjIrrTable oldt, uint64_t old_cap, KjIrrTable newt,
+                                     KjCounters *ctr) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_cap;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t st = oldt.state[i];
+        if (st < 2) continue;
+        __align__(8) uint8_t key32[32];
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(oldt.keys + i * 32);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(key32);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        if (!kj_insert_irr(newt, ctr, key32, st - 2, oldt.ords[i], oldt.counts[i]))
+            atomicOr(&ctr->error_flags, 0x80000000u);
+    }
+}
+
+// re-insert spilled regular emissions {key, ord}
+__global__ void kj_replay_kernel(KjTable t, KjCounters *ctr, const uint64_t *rec, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        if (!kj_insert(t, ctr, rec[2 * i], rec[2 * i + 1], 1)) atomicOr(&ctr->error_flags, 0x80000000u);
+}
+
+// re-insert spilled irregular emissions {buffer offset, len<<1|strand, ord}
+__global__ void kj_replay_irr_kernel(KjIrrTable t, KjCounters *ctr, const uint8_t *buf,
+                                     const uint64_t *rec, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        __align__(8) uint8_t key32[32];
+        uint32_t len = (uint32_t)(rec[3 * i + 1] >> 1), strand = (uint32_t)(rec[3 * i + 1] & 1);
+        kj_window_bytes(buf, rec[3 * i], len, strand, key32);
+        if (!kj_insert_irr(t, ctr, key32, len, rec[3 * i + 2], 1))
+            atomicOr(&ctr->error_flags, 0x80000000u);
+    }
+}
+
+// one atomic per warp: ballot the occupied slots, lane 0 claims a run of output positions
+__global__ void kj_compact_kernel(KjTable t, uint64_t cap, KjCounters *ctr, uint64_t *keys,
+                                  uint64_t *counts, uint64_t *ords) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (cap + stride - 1) / stride;       // same trip count for every thread
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint64_t r = 0; r < rounds; ++r, i += stride) {
+        uint64_t key = (i < cap) ? t.keys[i] : KJ_EMPTY;
+        bool have = key != KJ_EMPTY;
+        uint32_t b = __ballot_sync(0xFFFFFFFFu, have);
+        if (!b) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->n_compact, (unsigned long long)__popc(b));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (have) {
+            uint64_t o = base + __popc(b & ((1u << lane) - 1u));
+            keys[o] = key;
+            counts[o] = t.counts[i];
+            ords[o] = t.ords ? t.ords[i] : ~0ull;
+        }
+    }
+}
+
+__global__ void kj_compact_irr_kernel(KjIrrTable t, uint64_t cap, KjCounters *ctr,
+                                      KjIrrRecord *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t st = t.state[i];
+        if (st < 2) continue;
+        unsigned long long o = atomicAdd(&ctr->n_irr_compact, 1ull);
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(t.keys + i * 32);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(out[o].key);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        out[o].len = st - 2;
+        out[o].count = t.counts[i];
+        out[o].ord = t.ords[i];
+    }
+}
+
+// newline statistics of a byte range (sharded ingest: a rank needs the number of '\n' before its
+// range, lib/kmers.js:151-163 is "line index mod 4")
+__global__ void kj_newline_kernel(const uint8_t *buf, uint64_t n, unsigned long long *out /* count, last+1 */) {
+    unsigned long long cnt = 0, last = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 16;
+    for (uint64_t off = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 16; off < n; off += stride) {
+        uint4 v = kj_load_chunk(buf, off, n);
+        uint32_t m = kj_nl16(v.x, v.y, v.z, v.w);
+        if (off + 16 > n) m &= (1u << (uint32_t)(n - off)) - 1u;
+        if (m) { cnt += __popc(m); last = off + (31 - __clz(m)) + 1; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, last, d);
+        last = o > last ? o : last;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (cnt) atomicAdd(&out[0], cnt);
+        if (last) atomicMax(&out[1], last);
+    }
+}
+
+__global__ void kj_merge_records_kernel(KjTable t, KjCounters *ctr, const KjRecord *rec, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        if (!kj_insert(t, ctr, rec[i].key, rec[i].ord, rec[i].count))
+            atomicOr(&ctr->error_flags, 0x80000000u);
+}
+
+__global__ void kj_merge_irr_kernel(KjIrrTable t, KjCounters *ctr, const KjIrrRecord *rec, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        __align__(8) uint8_t key32[32];
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(rec[i].key);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(key32);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        if (!kj_insert_irr(t, ctr, key32, (uint32_t)rec[i].len, rec[i].ord, rec[i].count))
+            atomicOr(&ctr->error_flags, 0x80000000u);
+    }
+}
+
+// exchange: histogram of owners, then scatter into owner-grouped records
+__global__ void kj_part_hist_kernel(const uint64_t *keys, uint64_t n, uint32_t n_parts,
+                                    unsigned long long *hist) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&hist[kj_owner_key(keys[i], n_parts)], 1ull);
+}
+__global__ void kj_part_scatter_kernel(const uint64_t *keys, const uint64_t *counts,
+                                       const uint64_t *ords, uint64_t n, uint32_t n_parts,
+                                       unsigned long long *cursor, KjRecord *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long o = atomicAdd(&cursor[kj_owner_key(keys[i], n_parts)], 1ull);
+        out[o].key = keys[i];
+        out[o].count = counts[i];
+        out[o].ord = ords[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------ helpers
+
+static uint64_t next_pow2(uint64_t x) {
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+int kj_grid_for(const kj_ctx *ctx, uint64_t n, int threads) {
+    uint64_t g = (n + threads - 1) / threads;
+    uint64_t mx = (uint64_t)ctx->sm_count * 8;
+    return (int)std::max<uint64_t>(1, std::min(g, mx));
+}
+static int grid_for(const kj_ctx *ctx, uint64_t n, int threads = 256) { return kj_grid_for(ctx, n, threads); }
+
+static void free_table(kj_ctx *ctx, KjTable &t) {
+    kj_dfree(ctx, t.keys); kj_dfree(ctx, t.counts); kj_dfree(ctx, t.ords);
+    t = KjTable{};
+}
+static void free_irr(kj_ctx *ctx, KjIrrTable &t) {
+    kj_dfree(ctx, t.state); kj_dfree(ctx, t.keys); kj_dfree(ctx, t.counts); kj_dfree(ctx, t.ords);
+    t = KjIrrTable{};
+}
+
+static int alloc_table(kj_counts *c, uint64_t cap, KjTable *out) {
+    kj_ctx *ctx = c->ctx;
+    KjTable t{};
+    cudaError_t e = kj_dmalloc(ctx, &t.keys, cap * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &t.counts, cap * 8);
+    if (e == cudaSuccess && c->order) e = kj_dmalloc(ctx, &t.ords, cap * 8);
+    if (e != cudaSuccess) {
+        free_table(ctx, t);
+        cudaGetLastError();
+        return kj_fail(ctx, KJ_E_TABLE_FULL, "k-mer table of " + std::to_string(cap) +
+                                                 " slots does not fit in device memory");
+    }
+    t.mask = cap - 1;
+    KJ_CUDA(ctx, cudaMemsetAsync(t.keys, 0xFF, cap * 8, ctx->stream));
+    KJ_CUDA(ctx, cudaMemsetAsync(t.counts, 0, cap * 8, ctx->stream));
+    if (t.ords) KJ_CUDA(ctx, cudaMemsetAsync(t.ords, 0xFF, cap * 8, ctx->stream));
+    *out = t;
+    return KJ_OK;
+}
+static int alloc_irr(kj_counts *c, uint64_t cap, KjIrrTable *out) {
+    kj_ctx *ctx = c->ctx;
+    KjIrrTable t{};
+    KJ_CUDA(ctx, kj_dmalloc(ctx, &t.state, cap * 4));
+    KJ_CUDA(ctx, kj_dmalloc(ctx, &t.keys, cap * 32));
+    KJ_CUDA(ctx, kj_dmalloc(ctx, &t.counts, cap * 8));
+    KJ_CUDA(ctx, kj_dmalloc(ctx, &t.ords, cap * 8));
+    t.mask = cap - 1;
+    KJ_CUDA(ctx, cudaMemsetAsync(t.state, 0, cap * 4, ctx->stream));
+    KJ_CUDA(ctx, cudaMemsetAsync(t.counts, 0, cap * 8, ctx->stream));
+    KJ_CUDA(ctx, cudaMemsetAsync(t.ords, 0xFF, cap * 8, ctx->stream));
+    *out = t;
+    return KJ_OK;
+}
+
+static int pull_counters(kj_counts *c) {
+    kj_ctx *ctx = c->ctx;
+    KJ_CUDA(ctx, cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(KjCounters), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KJ_OK;
+}
+
+// make the regular table hold at least `want` slots (power of two); rehash when it exists
+static int grow_table(kj_counts *c, uint64_t want) {
+    kj_ctx *ctx = c->ctx;
+    want = next_pow2(std::max<uint64_t>(want, 1ull << 12));
+    if (want <= c->cap) return KJ_OK;
+    KjTable nt{};
+    int rc = alloc_table(c, want, &nt);
+    if (rc) return rc;
+    if (c->cap) {
+        KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_unique, 0, sizeof(unsigned long long), ctx->stream));
+        KJ_LAUNCH(kj_rehash_kernel, grid_for(ctx, c->cap), 256, 0, ctx->stream, c->tab, c->cap, nt, c->ctr);
+        ctx->launches++;
+        free_table(ctx, c->tab);
+    }
+    c->tab = nt;
+    c->cap = want;
+    return KJ_OK;
+}
+
+static int grow_irr(kj_counts *c, uint64_t want) {
+    kj_ctx *ctx = c->ctx;
+    want = next_pow2(std::max<uint64_t>(want, 1ull << 10));
+    if (want <= c->irr_cap) return KJ_OK;
+    KjIrrTable nt{};
+    int rc = alloc_irr(c, want, &nt);
+    if (rc) return rc;
+    if (c->irr_cap) {
+        KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_irr_unique, 0, sizeof(unsigned long long), ctx->stream));
+        KJ_LAUNCH(kj_rehash_irr_kernel, grid_for(ctx, c->irr_cap), 256, 0, ctx->stream, c->irr, c->irr_cap,
+                  nt, c->ctr);
+        ctx->launches++;
+        free_irr(ctx, c->irr);
+    }
+    c->irr = nt;
+    c->irr_cap = want;
+    return KJ_OK;
+}
+
+static int ensure_overflow(kj_counts *c, uint64_t reg_cap, uint64_t irr_cap) {
+    kj_ctx *ctx = c->ctx;
+    if (reg_cap > c->ovf.cap) {
+        kj_dfree(ctx, c->ovf.rec);
+        c->ovf.rec = nullptr; c->ovf.cap = 0;
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->ovf.rec, reg_cap * 16));
+        c->ovf.cap = reg_cap;
+    }
+    if (irr_cap > c->ovf.irr_cap) {
+        kj_dfree(ctx, c->ovf.irr_rec);
+        c->ovf.irr_rec = nullptr; c->ovf.irr_cap = 0;
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->ovf.irr_rec, irr_cap * 24));
+        c->ovf.irr_cap = irr_cap;
+    }
+    return KJ_OK;
+}
+
+static int check_device_errors(kj_counts *c) {
+    uint32_t f = c->h_ctr->error_flags;
+    if (!f) return KJ_OK;
+    if (f & 0x80000000u) return kj_fail(c->ctx, KJ_E_TABLE_FULL, "k-mer table probe limit reached while rehashing/merging");
+    if (f & KJ_DEV_E_LINE_EXCEEDS_HALO)
+        return kj_fail(c->ctx, KJ_E_RANGE, "a sequence line extends beyond the halo of its buffer (the line-oriented kernel needs whole lines; give a larger halo)");
+    if (f & KJ_DEV_E_LINE_TOO_LONG)
+        return kj_fail(c->ctx, KJ_E_RANGE, "a sequence line is longer than 2^27 bytes (first-seen position field); use KJ_F_NO_ORDER");
+    if (f & KJ_DEV_E_READS_OVERFLOW)
+        return kj_fail(c->ctx, KJ_E_RANGE, "more than 2^36 reads (first-seen read field); use KJ_F_NO_ORDER");
+    return kj_fail(c->ctx, KJ_E_CUDA, "unknown device error flag");
+}
+
+// expected number of emissions of `bytes` input bytes (i.i.d. bases): both strands, every
+// position, times 4^-m
+static double expected_emissions(const kj_counts *c, uint64_t bytes) {
+    double e = (double)bytes;   // ~ half the bytes are bases, two strands
+    const uint32_t m = (uint32_t)c->prefix.size();
+    for (uint32_t i = 0; i < std::min<uint32_t>(m, 16); ++i) e *= 0.25;
+    return e;
+}
+
+// One kernel launch over a device-resident piece.  Synchronises, handles spills and growth.
+static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t own_n, int final_) {
+    kj_ctx *ctx = c->ctx;
+    if (own_n == 0) return KJ_OK;
+    const uint32_t m = (uint32_t)c->prefix.size();
+    const uint64_t n_tiles64 = (own_n + KJ_TILE_BYTES - 1) / KJ_TILE_BYTES;
+    if (n_tiles64 > 0xFFFFFFF0ull) return kj_fail(ctx, KJ_E_RANGE, "piece too large");
+    const uint32_t n_tiles = (uint32_t)n_tiles64;
+
+    // table capacity: the caller's hint, else what this piece is expected to add (it grows by
+    // rehash between pieces, and emissions that find no slot are spilled and replayed)
+    const uint64_t hard_bound = 2 * own_n + 16;                 // emissions this launch can produce
+    uint64_t expect = c->use_filter ? (uint64_t)(4.0 * expected_emissions(c, own_n)) + 65536 : hard_bound;
+    expect = std::min(expect, hard_bound);
+    uint64_t known = c->h_ctr->n_unique;
+    uint64_t want = c->capacity_hint ? std::max<uint64_t>(2 * c->capacity_hint, 2 * known)
+                                     : std::min<uint64_t>(2 * (known + expect), std::max<uint64_t>(1ull << 24, 4 * known));
+    int rc = grow_table(c, want);
+    if (rc) return rc;
+    rc = grow_irr(c, std::max<uint64_t>(1ull << 12, 4 * c->h_ctr->n_irr_unique));
+    if (rc) return rc;
+    rc = ensure_overflow(c, std::min<uint64_t>(hard_bound, std::max<uint64_t>(1ull << 16, expect)),
+                         std::min<uint64_t>(hard_bound, c->use_filter ? (1ull << 16) : expect));
+    if (rc) return rc;
+
+    // tile state
+    if (n_tiles > c->tile_cap) {
+        kj_dfree(ctx, c->tile_mem);
+        c->tile_mem = nullptr; c->tile_cap = 0;
+        uint64_t tc = std::max<uint64_t>(n_tiles, 4096);
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->tile_mem, tc * 3 * 8));
+        c->tile_cap = tc;
+    }
+    KJ_CUDA(ctx, cudaMemsetAsync(c->tile_mem, 0, (uint64_t)n_tiles * 8, ctx->stream));  // status only
+    KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->ticket, 0, sizeof(unsigned int), ctx->stream));
+
+    KjScanArgs a{};
+    a.buf = dbuf; a.n = n; a.own_n = own_n; a.voff = c->voff;
+    a.n_tiles = n_tiles; a.parity = c->parity; a.final_ = final_ ? 1u : 0u;
+    a.k = c->k; a.step = c->step; a.m = m; a.order = c->order ? 1u : 0u;
+    a.n_strands = (c->flags & KJ_F_FORWARD_ONLY) ? 1u : 2u;
+    a.line_gate = (c->flags & KJ_F_NO_LINE_GATE) ? 0u : 1u;
+    a.mp = std::min<uint32_t>(m, KJ_MAX_MP);
+    a.rc_shift = (m <= c->k) ? c->k - m : 0;
+    for (uint32_t i = 0; i < a.mp; ++i) {
+        a.pat_f[i] = kj_code(c->prefix[i]) * 0x55555555u;
+        a.pat_r[i] = kj_code(c->rprefix[i]) * 0x55555555u;
+    }
+    memset(a.prefix, 0, 32); memset(a.rprefix, 0, 32);
+    memcpy(a.prefix, c->prefix.data(), std::min<size_t>(32, m));
+    memcpy(a.rprefix, c->rprefix.data(), std::min<size_t>(32, m));
+    a.tab = c->tab; a.irr = c->irr; a.ovf = c->ovf; a.ctr = c->ctr;
+    a.ts.status = c->tile_mem;
+    a.ts.agg_last = c->tile_mem + c->tile_cap;
+    a.ts.inc_last = c->tile_mem + 2 * c->tile_cap;
+
+    void (*fn)(const KjScanArgs) = kj_scan_lines_kernel;
+    if (c->use_filter) {
+        switch (a.mp) {
+            case 1: fn = kj_scan_filter_kernel<1>; break;
+            case 2: fn = kj_scan_filter_kernel<2>; break;
+            case 3: fn = kj_scan_filter_kernel<3>; break;
+            case 4: fn = kj_scan_filter_kernel<4>; break;
+            case 5: fn = kj_scan_filter_kernel<5>; break;
+            case 6: fn = kj_scan_filter_kernel<6>; break;
+            case 7: fn = kj_scan_filter_kernel<7>; break;
+            default: fn = kj_scan_filter_kernel<8>; break;
+        }
+    }
+    int occ = 0;
+    KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KJ_THREADS, 0));
+    // persistent CTAs: a whole number of CTAs per SM, tiles handed out by ticket
+    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * std::max(occ, 1));
+    if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    KJ_LAUNCH(fn, grid, KJ_THREADS, 0, ctx->stream, a);
+    if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches++;
+    KJ_CUDA(ctx, cudaGetLastError());
+    rc = pull_counters(c);
+    if (rc) return rc;
+    if (ctx->timers_on) {
+        float ms = 0.f;
+        KJ_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->scan_ms += ms;
+        ctx->scan_launches++;
+        ctx->scan_bytes += own_n;
+    }
+    rc = check_device_errors(c);
+    if (rc) return rc;
+
+    // spills: grow and replay until clean
+    for (int round = 0; round < 8 && (c->h_ctr->n_overflow || c->h_ctr->n_irr_overflow); ++round) {
+        uint64_t nov = c->h_ctr->n_overflow, niov = c->h_ctr->n_irr_overflow;
+        if (nov > c->ovf.cap || niov > c->ovf.irr_cap)
+            return kj_fail(ctx, KJ_E_TABLE_FULL,
+                           "k-mer table overflowed beyond the spill buffer (" + std::to_string(nov) +
+                               " regular, " + std::to_string(niov) +
+                               " irregular spills); raise capacity_hint");
+        if (nov) { rc = grow_table(c, std::max<uint64_t>(c->cap * 4, 4 * (c->h_ctr->n_unique + nov))); if (rc) return rc; }
+        if (niov) { rc = grow_irr(c, std::max<uint64_t>(c->irr_cap * 4, 4 * (c->h_ctr->n_irr_unique + niov))); if (rc) return rc; }
+        KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_overflow, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        // after growing 4x a spill during the replay means a broken hash: the replay kernels raise
+        // the error flag instead of appending to the list they are reading
+        if (nov) {
+            KJ_LAUNCH(kj_replay_kernel, grid_for(ctx, nov), 256, 0, ctx->stream, c->tab, c->ctr, c->ovf.rec, nov);
+            ctx->launches++;
+        }
+        if (niov) {
+            KJ_LAUNCH(kj_replay_irr_kernel, grid_for(ctx, niov), 256, 0, ctx->stream, c->irr, c->ctr, dbuf,
+                      c->ovf.irr_rec, niov);
+            ctx->launches++;
+        }
+        rc = pull_counters(c);
+        if (rc) return rc;
+        rc = check_device_errors(c);
+        if (rc) return rc;
+    }
+    // keep the load factor at or below one half between launches
+    if (c->h_ctr->n_unique * 2 > c->cap) { rc = grow_table(c, c->cap * 4); if (rc) return rc; }
+    if (c->h_ctr->n_irr_unique * 2 > c->irr_cap) { rc = grow_irr(c, c->irr_cap * 4); if (rc) return rc; }
+
+    c->voff += own_n;
+    c->consumed += own_n;
+    c->parity ^= 1u;
+    return KJ_OK;
+}
+
+// device-resident buffer.  The filter kernel takes it in one launch when the caller sized the
+// table (capacity_hint), else in 512 MiB pieces so the table can grow in between; the line
+// kernel (whose spill lists are sized for the worst case) in 4 MiB pieces.
+static int scan_device(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t own_n, int final_) {
+    const uint64_t piece = c->use_filter ? (c->capacity_hint ? (1ull << 40) : (512ull << 20)) : (4ull << 20);
+    uint64_t lo = 0;
+    while (lo < own_n) {
+        uint64_t len = std::min(piece, own_n - lo);
+        int rc = scan_piece(c, dbuf + lo, n - lo, len, (final_ && lo + len == own_n) ? 1 : 0);
+        if (rc) return rc;
+        lo += len;
+    }
+    return KJ_OK;
+}
+
+// ------------------------------------------------------------------------------------ API
+
+extern "C" int kj_counts_create(kj_ctx *ctx, const kj_count_params *p, kj_counts **out) {
+    if (!ctx || !p || !out) return kj_fail(ctx, KJ_E_INVALID, "kj_counts_create: null argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (p->k < 1 || p->k > 32) return kj_fail(ctx, KJ_E_RANGE, "k must be in 1..32");
+    if (p->step < 1) return kj_fail(ctx, KJ_E_INVALID, "step must be >= 1");
+    if (p->prefix_len && !p->prefix) return kj_fail(ctx, KJ_E_INVALID, "prefix is null");
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    kj_counts *c = new kj_counts();
+    c->ctx = ctx;
+    c->prefix.assign(p->prefix, p->prefix + p->prefix_len);
+    c->rprefix.resize(p->prefix_len);
+    for (uint32_t i = 0; i < p->prefix_len; ++i)
+        c->rprefix[i] = kj_comp_byte(p->prefix[p->prefix_len - 1 - i]);
+    c->k = p->k; c->step = p->step; c->flags = p->flags;
+    c->order = !(p->flags & KJ_F_NO_ORDER);
+    c->use_filter = p->step == 1 && p->prefix_len >= 1 && p->prefix_len <= p->k &&
+                    !(p->flags & KJ_F_FORCE_GENERIC);
+    c->capacity_hint = p->capacity_hint;
+    c->voff = p->base_col;
+    cudaError_t e = kj_dmalloc(ctx, &c->ctr, sizeof(KjCounters));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_ctr, sizeof(KjCounters));
+    if (e != cudaSuccess) {
+        kj_counts_free(c);
+        return kj_fail(ctx, KJ_E_CUDA, std::string("kj_counts_create: ") + cudaGetErrorString(e));
+    }
+    memset(c->h_ctr, 0, sizeof(KjCounters));
+    c->h_ctr->special_ord = ~0ull;
+    c->h_ctr->carry_lines[0] = p->base_line;
+    c->h_ctr->carry_last[0] = 0;
+    e = cudaMemcpyAsync(c->ctr, c->h_ctr, sizeof(KjCounters), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        kj_counts_free(c);
+        return kj_fail(ctx, KJ_E_CUDA, std::string("kj_counts_create: ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return KJ_OK;
+}
+
+static const uint64_t KJ_STAGE_CHUNK = 64ull << 20;
+static const uint64_t KJ_STAGE_HALO_LINES = 1ull << 20;   // line kernel: longest line it can finish
+
+static int ensure_staging(kj_ctx *ctx, bool need_host) {
+    const uint64_t cap = KJ_STAGE_CHUNK + KJ_STAGE_HALO_LINES;
+    if (!ctx->d_stage[0]) {
+        for (int i = 0; i < 2; ++i) {
+            KJ_CUDA(ctx, cudaMalloc(&ctx->d_stage[i], cap + 64));
+            KJ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+        }
+        ctx->stage_cap = cap;
+    }
+    if (need_host && !ctx->h_stage[0])
+        for (int i = 0; i < 2; ++i) KJ_CUDA(ctx, cudaMallocHost(&ctx->h_stage[i], cap));
+    return KJ_OK;
+}
+
+static int add_host(kj_counts *c, const uint8_t *buf, uint64_t n, uint64_t own_n, int final_) {
+    kj_ctx *ctx = c->ctx;
+    const uint64_t halo = c->use_filter ? 64 : KJ_STAGE_HALO_LINES;
+    const uint64_t chunk = KJ_STAGE_CHUNK;
+    cudaPointerAttributes attr{};
+    bool pinned = cudaPointerGetAttributes(&attr, buf) == cudaSuccess &&
+                  (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    int rc = ensure_staging(ctx, !pinned);
+    if (rc) return rc;
+
+    const uint64_t n_chunks = (own_n + chunk - 1) / chunk;
+    auto issue_copy = [&](uint64_t ci) -> int {
+        uint64_t lo = ci * chunk;
+        uint64_t hi = std::min(own_n, lo + chunk);
+        uint64_t rd = std::min(n, hi + halo) - lo;          // bytes readable by this piece
+        int s = (int)(ci & 1);
+        const uint8_t *src = buf + lo;
+        if (!pinned) { memcpy(ctx->h_stage[s], src, rd); src = ctx->h_stage[s]; }
+        KJ_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage[s], src, rd, cudaMemcpyHostToDevice, ctx->copy_stream));
+        KJ_CUDA(ctx, cudaEventRecord(ctx->ev_copy[s], ctx->copy_stream));
+        return KJ_OK;
+    };
+    // the launch stream is idle here (every scan_piece ends synchronised), so both slots are free
+    rc = n_chunks ? issue_copy(0) : KJ_OK;
+    if (rc) return rc;
+    for (uint64_t ci = 0; ci < n_chunks; ++ci) {
+        uint64_t lo = ci * chunk;
+        uint64_t hi = std::min(own_n, lo + chunk);
+        uint64_t rd = std::min(n, hi + halo) - lo;
+        int s = (int)(ci & 1);
+        KJ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[s], 0));
+        // the other slot's kernel was synchronised by the previous iteration: start the next copy
+        if (ci + 1 < n_chunks) { rc = issue_copy(ci + 1); if (rc) return rc; }
+        rc = scan_device(c, ctx->d_stage[s], rd, hi - lo, (final_ && lo + rd == n) ? 1 : 0);
+        if (rc) return rc;
+    }
+    return KJ_OK;
+}
+
+extern "C" int kj_counts_add_buffer(kj_counts *c, const uint8_t *buf, uint64_t n, uint64_t own_n,
+                                    int mem_kind, int final_) {
+    if (!c) return KJ_E_INVALID;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (c->finished || c->saw_final) return kj_fail(ctx, KJ_E_STATE, "kj_counts_add_buffer after the final buffer / finish");
+    if (own_n > n) return kj_fail(ctx, KJ_E_INVALID, "own_n > n");
+    if (n && !buf) return kj_fail(ctx, KJ_E_INVALID, "buf is null");
+    if (final_ && own_n != n) return kj_fail(ctx, KJ_E_INVALID, "final buffer must own all its bytes");
+    if (!final_ && n - own_n < 32) return kj_fail(ctx, KJ_E_INVALID, "non-final buffer needs a halo of at least 32 bytes");
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (mem_kind == KJ_MEM_DEVICE) {
+        if ((uintptr_t)buf & 15) return kj_fail(ctx, KJ_E_INVALID, "device buffers must be 16-byte aligned");
+        rc = scan_device(c, buf, n, own_n, final_);
+    } else if (mem_kind == KJ_MEM_HOST) {
+        rc = add_host(c, buf, n, own_n, final_);
+    } else {
+        return kj_fail(ctx, KJ_E_INVALID, "mem_kind");
+    }
+    if (rc) return rc;
+    if (final_) c->saw_final = true;
+    return KJ_OK;
+}
+
+extern "C" int kj_counts_add_file(kj_counts *c, const char *path) {
+    if (!c || !path) return KJ_E_INVALID;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return kj_fail(ctx, KJ_E_IO, std::string("cannot open ") + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return kj_fail(ctx, KJ_E_IO, std::string("cannot stat ") + path); }
+    const uint64_t size = (uint64_t)st.st_size;
+    const uint64_t halo = c->use_filter ? 64 : KJ_STAGE_HALO_LINES;
+    const uint64_t chunk = KJ_STAGE_CHUNK;
+    // read each piece (chunk + halo) into pinned memory and hand it over as a host buffer;
+    // the halo bytes are read again by the next piece
+    uint8_t *pin = nullptr;
+    if (cudaMallocHost(&pin, chunk + halo) != cudaSuccess) { close(fd); return kj_fail(ctx, KJ_E_NOMEM, "pinned staging"); }
+    int rc = KJ_OK;
+    uint64_t lo = 0;
+    if (size == 0) rc = kj_counts_add_buffer(c, pin, 0, 0, KJ_MEM_HOST, 1);
+    while (lo < size && rc == KJ_OK) {
+        uint64_t hi = std::min(size, lo + chunk);
+        uint64_t rd_end = std::min(size, hi + halo);
+        uint64_t got = 0;
+        while (got < rd_end - lo) {
+            ssize_t r = pread(fd, pin + got, rd_end - lo - got, (off_t)(lo + got));
+            if (r <= 0) { rc = kj_fail(ctx, KJ_E_IO, std::string("read error on ") + path); break; }
+            got += (uint64_t)r;
+        }
+        if (rc) break;
+        int fin = hi == size;
+        rc = kj_counts_add_buffer(c, pin, fin ? hi - lo : rd_end - lo, hi - lo, KJ_MEM_HOST, fin);
+        lo = hi;
+    }
+    cudaFreeHost(pin);
+    close(fd);
+    if (rc == KJ_OK) c->bytes_read = size;
+    return rc;
+}
+
+static void drop_compact(kj_counts *c) {
+    kj_ctx *ctx = c->ctx;
+    kj_dfree(ctx, c->reg.keys); kj_dfree(ctx, c->reg.counts); kj_dfree(ctx, c->reg.ords); kj_dfree(ctx, c->reg.alive);
+    c->reg = KjCompact{};
+    c->irr_host.clear();
+    c->export_perm.clear();
+}
+
+extern "C" int kj_counts_finish(kj_counts *c) {
+    if (!c) return KJ_E_INVALID;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = pull_counters(c);
+    if (rc) return rc;
+    rc = check_device_errors(c);
+    if (rc) return rc;
+    drop_compact(c);   // finish may be called again after merges
+    const uint64_t n_tab = c->h_ctr->n_unique;
+    const uint64_t n_reg = n_tab + (c->h_ctr->special_count ? 1 : 0);
+    const uint64_t n_irr = c->h_ctr->n_irr_unique;
+    const uint64_t q = n_reg + n_irr;
+    if (q > 0xFFFFFFF0ull) return kj_fail(ctx, KJ_E_RANGE, "more than 2^32 distinct k-mers on one GPU");
+    KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_compact, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    std::vector<uint64_t> tail_counts, tail_ords;   // special + irregular entries, host side
+    if (c->h_ctr->special_count) {
+        tail_counts.push_back(c->h_ctr->special_count);
+        tail_ords.push_back(c->h_ctr->special_ord);
+    }
+    if (n_irr) {
+        KjIrrRecord *d_irr = nullptr;
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &d_irr, n_irr * sizeof(KjIrrRecord)));
+        KJ_LAUNCH(kj_compact_irr_kernel, grid_for(ctx, c->irr_cap), 256, 0, ctx->stream, c->irr, c->irr_cap,
+                  c->ctr, d_irr);
+        ctx->launches++;
+        c->irr_host.resize(n_irr * sizeof(KjIrrRecord));
+        cudaError_t e = cudaMemcpyAsync(c->irr_host.data(), d_irr, n_irr * sizeof(KjIrrRecord),
+                                        cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        kj_dfree(ctx, d_irr);
+        if (e != cudaSuccess) return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e));
+        // deterministic order of the irregular entries (slot order depends on the table size)
+        KjIrrRecord *ir = reinterpret_cast<KjIrrRecord *>(c->irr_host.data());
+        std::sort(ir, ir + n_irr, [](const KjIrrRecord &x, const KjIrrRecord &y) {
+            if (x.ord != y.ord) return x.ord < y.ord;
+            int d = memcmp(x.key, y.key, 32);
+            return d ? d < 0 : x.len < y.len;
+        });
+        for (uint64_t i = 0; i < n_irr; ++i) { tail_counts.push_back(ir[i].count); tail_ords.push_back(ir[i].ord); }
+    }
+    if (q) {
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.keys, q * 8));
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.counts, q * 8));
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.ords, q * 8));
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.alive, q));
+        KJ_CUDA(ctx, cudaMemsetAsync(c->reg.alive, 1, q, ctx->stream));
+        if (n_tab) {
+            KJ_LAUNCH(kj_compact_kernel, grid_for(ctx, c->cap), 256, 0, ctx->stream, c->tab, c->cap, c->ctr,
+                      c->reg.keys, c->reg.counts, c->reg.ords);
+            ctx->launches++;
+        }
+        if (!tail_counts.empty()) {
+            // keys of the tail entries: KJ_EMPTY for the special key, unused (KJ_EMPTY) for irregular ones
+            KJ_CUDA(ctx, cudaMemsetAsync(c->reg.keys + n_tab, 0xFF, tail_counts.size() * 8, ctx->stream));
+            KJ_CUDA(ctx, cudaMemcpyAsync(c->reg.counts + n_tab, tail_counts.data(), tail_counts.size() * 8,
+                                         cudaMemcpyHostToDevice, ctx->stream));
+            KJ_CUDA(ctx, cudaMemcpyAsync(c->reg.ords + n_tab, tail_ords.data(), tail_ords.size() * 8,
+                                         cudaMemcpyHostToDevice, ctx->stream));
+            KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // tail_* are pageable host vectors
+        }
+    }
+    c->reg.n = q;
+    c->reg.n_reg = n_reg;
+    c->reg.n_tab = n_tab;
+    rc = pull_counters(c);
+    if (rc) return rc;
+    if (c->h_ctr->n_compact != n_tab) return kj_fail(ctx, KJ_E_CUDA, "internal: compaction count mismatch");
+    c->lines = c->h_ctr->carry_lines[c->parity];
+    c->bases = c->h_ctr->n_bases;
+    // a non-empty unterminated tail is one more line (lib/kmers.js:130-136)
+    const uint64_t tail_start = c->h_ctr->carry_last[c->parity];
+    if (c->consumed && tail_start != c->voff) {
+        const uint64_t tail_len = c->voff - tail_start;
+        // the filter kernel counts a sequence line when it meets its '\n'; the line kernel when it starts
+        if (c->use_filter && (c->lines & 3ull) == 1ull && tail_len > 1) c->bases += tail_len;
+        c->lines += 1;
+    }
+    c->occurrences = c->h_ctr->n_occ;
+    c->finished = true;
+    return KJ_OK;
+}
+
+int kj_counts_check_finished(const kj_counts *c) {
+    if (!c) return KJ_E_INVALID;
+    if (!c->finished) return kj_fail(c->ctx, KJ_E_STATE, "kj_counts_finish has not been called");
+    return KJ_OK;
+}
+
+extern "C" uint64_t kj_counts_size(const kj_counts *c) { return c ? c->reg.n : 0; }
+extern "C" uint64_t kj_counts_lines(const kj_counts *c) { return c ? c->lines : 0; }
+extern "C" uint64_t kj_counts_bases(const kj_counts *c) { return c ? c->bases : 0; }
+extern "C" uint64_t kj_counts_bytes_read(const kj_counts *c) { return c ? (c->bytes_read ? c->bytes_read : c->consumed) : 0; }
+extern "C" uint64_t kj_counts_occurrences(const kj_counts *c) { return c ? c->occurrences : 0; }
+extern "C" uint64_t kj_counts_irregular_size(const kj_counts *c) {
+    return c ? c->irr_host.size() / sizeof(KjIrrRecord) : 0;
+}
+
+void kj_decode_key(uint64_t key, uint32_t k, uint8_t *out) {
+    static const char L[4] = {'A', 'C', 'T', 'G'};   // code = (byte >> 1) & 3
+    for (uint32_t i = 0; i < k; ++i) out[i] = (uint8_t)L[(key >> (2 * (k - 1 - i))) & 3];
+}
+
+// export_perm[o] = query index (position in the compact arrays) of the o-th key in
+// first-insertion order = ascending first-seen ordinal (lib/kmers.js:46-54,95)
+static int build_export_perm(kj_counts *c, std::vector<uint64_t> &hk) {
+    kj_ctx *ctx = c->ctx;
+    const uint64_t q = c->reg.n, n_reg = c->reg.n_reg;
+    std::vector<uint64_t> ho(q);
+    hk.resize(q);
+    if (q) {
+        KJ_CUDA(ctx, cudaMemcpyAsync(hk.data(), c->reg.keys, q * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KJ_CUDA(ctx, cudaMemcpyAsync(ho.data(), c->reg.ords, q * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    const KjIrrRecord *ir = reinterpret_cast<const KjIrrRecord *>(c->irr_host.data());
+    c->export_perm.resize(q);
+    for (uint64_t i = 0; i < q; ++i) c->export_perm[i] = i;
+    std::sort(c->export_perm.begin(), c->export_perm.end(), [&](uint64_t x, uint64_t y) {
+        if (ho[x] != ho[y]) return ho[x] < ho[y];
+        // KJ_F_NO_ORDER: every ordinal is ~0; fall back to the key so the export is deterministic
+        bool xr = x < n_reg, yr = y < n_reg;
+        if (xr && yr) return hk[x] < hk[y];
+        if (xr != yr) return xr;
+        return memcmp(ir[x - n_reg].key, ir[y - n_reg].key, 32) < 0;
+    });
+    return KJ_OK;
+}
+
+extern "C" int kj_counts_export(kj_counts *c, uint8_t *keys, uint32_t *key_len, uint64_t *counts) {
+    int rc = kj_counts_check_finished(c);
+    if (rc) return rc;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t q = c->reg.n, n_reg = c->reg.n_reg;
+    std::vector<uint64_t> hk, hc(q);
+    rc = build_export_perm(c, hk);
+    if (rc) return rc;
+    if (q) {
+        KJ_CUDA(ctx, cudaMemcpyAsync(hc.data(), c->reg.counts, q * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    const KjIrrRecord *ir = reinterpret_cast<const KjIrrRecord *>(c->irr_host.data());
+    for (uint64_t o = 0; o < q; ++o) {
+        uint64_t i = c->export_perm[o];
+        uint8_t *dst = keys + 32 * o;
+        memset(dst, 0, 32);
+        if (i < n_reg) {
+            kj_decode_key(hk[i], c->k, dst);
+            key_len[o] = c->k;
+        } else {
+            const KjIrrRecord &r = ir[i - n_reg];
+            memcpy(dst, r.key, 32);
+            key_len[o] = (uint32_t)r.len;
+        }
+        counts[o] = hc[i];
+    }
+    return KJ_OK;
+}
+
+// alive flags in export order (1 = still in the map; kj_wta_next clears the winner's k-mers,
+// mirroring kmerMap.delete of lib/kmerFinderClient.js:220-230)
+extern "C" int kj_counts_alive(kj_counts *c, uint8_t *alive) {
+    int rc = kj_counts_check_finished(c);
+    if (rc) return rc;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t q = c->reg.n;
+    if (c->export_perm.size() != q) {
+        std::vector<uint64_t> hk;
+        rc = build_export_perm(c, hk);
+        if (rc) return rc;
+    }
+    std::vector<uint8_t> ha(q);
+    if (q) {
+        KJ_CUDA(ctx, cudaMemcpyAsync(ha.data(), c->reg.alive, q, cudaMemcpyDeviceToHost, ctx->stream));
+        KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    for (uint64_t o = 0; o < q; ++o) alive[o] = ha[c->export_perm[o]];
+    return KJ_OK;
+}
+
+extern "C" void kj_counts_free(kj_counts *c) {
+    if (!c) return;
+    kj_ctx *ctx = c->ctx;
+    if (ctx) {
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        cudaSetDevice(ctx->device);
+        free_table(ctx, c->tab);
+        free_irr(ctx, c->irr);
+        kj_dfree(ctx, c->ovf.rec); kj_dfree(ctx, c->ovf.irr_rec);
+        kj_dfree(ctx, c->ctr);
+        if (c->h_ctr) cudaFreeHost(c->h_ctr);
+        kj_dfree(ctx, c->tile_mem);
+        drop_compact(c);
+        kj_dfree(ctx, c->part_rec);
+    }
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------ exchange
+
+extern "C" int kj_counts_partition(kj_counts *c, uint32_t n_parts, const void **dev_records,
+                                   uint64_t *part_sizes) {
+    int rc = kj_counts_check_finished(c);
+    if (rc) return rc;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (!n_parts || n_parts > 1024 || !dev_records || !part_sizes)
+        return kj_fail(ctx, KJ_E_INVALID, "kj_counts_partition arguments");
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = c->reg.n_reg;   // regular entries only; irregular ones travel as host records
+    unsigned long long *d_hist = nullptr;
+    KJ_CUDA(ctx, kj_dmalloc(ctx, &d_hist, n_parts * 8));
+    KJ_CUDA(ctx, cudaMemsetAsync(d_hist, 0, n_parts * 8, ctx->stream));
+    std::vector<unsigned long long> hist(n_parts, 0);
+    if (n) {
+        KJ_LAUNCH(kj_part_hist_kernel, grid_for(ctx, n), 256, 0, ctx->stream, c->reg.keys, n, n_parts, d_hist);
+        ctx->launches++;
+    }
+    cudaError_t e = cudaMemcpyAsync(hist.data(), d_hist, n_parts * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { kj_dfree(ctx, d_hist); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
+    std::vector<unsigned long long> cursor(n_parts, 0);
+    unsigned long long run = 0;
+    for (uint32_t p = 0; p < n_parts; ++p) { cursor[p] = run; run += hist[p]; part_sizes[p] = hist[p]; }
+    if (n > c->part_cap || !c->part_rec) {
+        kj_dfree(ctx, c->part_rec);
+        c->part_rec = nullptr; c->part_cap = 0;
+        e = kj_dmalloc(ctx, &c->part_rec, std::max<uint64_t>(n, 1) * sizeof(KjRecord));
+        if (e != cudaSuccess) { kj_dfree(ctx, d_hist); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
+        c->part_cap = std::max<uint64_t>(n, 1);
+    }
+    if (n) {
+        e = cudaMemcpyAsync(d_hist, cursor.data(), n_parts * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            KJ_LAUNCH(kj_part_scatter_kernel, grid_for(ctx, n), 256, 0, ctx->stream, c->reg.keys, c->reg.counts,
+                      c->reg.ords, n, n_parts, d_hist, reinterpret_cast<KjRecord *>(c->part_rec));
+            ctx->launches++;
+            e = cudaStreamSynchronize(ctx->stream);
+        }
+    }
+    kj_dfree(ctx, d_hist);
+    if (e != cudaSuccess) return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e));
+    *dev_records = c->part_rec;
+    return KJ_OK;
+}
+
+extern "C" int kj_counts_merge_records(kj_counts *c, const void *dev_records, uint64_t n) {
+    if (!c) return KJ_E_INVALID;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (!n) return KJ_OK;
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = pull_counters(c);
+    if (rc) return rc;
+    rc = grow_table(c, std::max<uint64_t>(2 * (c->h_ctr->n_unique + n), c->capacity_hint * 2));
+    if (rc) return rc;
+    KJ_LAUNCH(kj_merge_records_kernel, grid_for(ctx, n), 256, 0, ctx->stream, c->tab, c->ctr,
+              reinterpret_cast<const KjRecord *>(dev_records), n);
+    ctx->launches++;
+    rc = pull_counters(c);
+    if (rc) return rc;
+    c->finished = false;
+    return check_device_errors(c);
+}
+
+extern "C" int kj_counts_irregular_export(kj_counts *c, void *host_records) {
+    int rc = kj_counts_check_finished(c);
+    if (rc) return rc;
+    if (!c->irr_host.empty()) memcpy(host_records, c->irr_host.data(), c->irr_host.size());
+    return KJ_OK;
+}
+
+extern "C" int kj_counts_irregular_merge(kj_counts *c, const void *host_records, uint64_t n) {
+    if (!c) return KJ_E_INVALID;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (!n) return KJ_OK;
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = pull_counters(c);
+    if (rc) return rc;
+    rc = grow_irr(c, 2 * (c->h_ctr->n_irr_unique + n));
+    if (rc) return rc;
+    KjIrrRecord *d = nullptr;
+    KJ_CUDA(ctx, kj_dmalloc(ctx, &d, n * sizeof(KjIrrRecord)));
+    cudaError_t e = cudaMemcpyAsync(d, host_records, n * sizeof(KjIrrRecord), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        KJ_LAUNCH(kj_merge_irr_kernel, grid_for(ctx, n), 256, 0, ctx->stream, c->irr, c->ctr, d, n);
+        ctx->launches++;
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    kj_dfree(ctx, d);
+    if (e != cudaSuccess) return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e));
+    rc = pull_counters(c);
+    if (rc) return rc;
+    c->finished = false;
+    return check_device_errors(c);
+}
+
+// set totals that the exchange cannot reconstruct (lines / bases / occurrences / bytes of the
+// whole job when this handle holds only the k-mers one rank owns)
+extern "C" int kj_counts_set_totals(kj_counts *c, uint64_t lines, uint64_t bases, uint64_t occurrences,
+                                    uint64_t bytes_read) {
+    if (!c) return KJ_E_INVALID;
+    c->lines = lines; c->bases = bases; c->occurrences = occurrences; c->bytes_read = bytes_read;
+    return KJ_OK;
+}
+
+extern "C" int kj_count_newlines(kj_ctx *ctx, const uint8_t *buf, uint64_t n, int mem_kind,
+                                 uint64_t *n_newlines, uint64_t *last_newline_plus1) {
+    if (!ctx || (n && !buf)) return kj_fail(ctx, KJ_E_INVALID, "kj_count_newlines arguments");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d_out = nullptr;
+    KJ_CUDA(ctx, kj_dmalloc(ctx, &d_out, 16));
+    KJ_CUDA(ctx, cudaMemsetAsync(d_out, 0, 16, ctx->stream));
+    unsigned long long total[2] = {0, 0};
+    int rc = KJ_OK;
+    if (mem_kind == KJ_MEM_DEVICE) {
+        if ((uintptr_t)buf & 15) rc = kj_fail(ctx, KJ_E_INVALID, "device buffers must be 16-byte aligned");
+        else if (n) {
+            KJ_LAUNCH(kj_newline_kernel, grid_for(ctx, (n + 15) / 16), 256, 0, ctx->stream, buf, n, d_out);
+            ctx->launches++;
+        }
+        if (rc == KJ_OK) {
+            cudaError_t e = cudaMemcpyAsync(total, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e));
+        }
+    } else {
+        rc = kj_fail(ctx, KJ_E_INVALID, "kj_count_newlines takes device buffers (stage the range first)");
+    }
+    kj_dfree(ctx, d_out);
+    if (rc) return rc;
+    if (n_newlines) *n_newlines = total[0];
+    if (last_newline_plus1) *last_newline_plus1 = total[1];
+    return KJ_OK;
+}
+
+static bool ascii_regular(const uint8_t *kmer, uint32_t len) {
+    for (uint32_t i = 0; i < len; ++i) if (!kj_is_acgt(kmer[i])) return false;
+    return len >= 1 && len <= 32;
+}
+
+extern "C" uint32_t kj_owner(const uint8_t *kmer, uint32_t len, uint32_t n_parts) {
+    if (!kmer || !n_parts) return 0;
+    if (!ascii_regular(kmer, len)) return 0;       // irregular k-mers are gathered on part 0
+    uint64_t key = 0;
+    for (uint32_t i = 0; i < len; ++i) key = (key << 2) | kj_code(kmer[i]);
+    return kj_owner_key(key, n_parts);
+}

@@ -1,0 +1,122 @@
+// kj_internal.hpp -- host-side structures behind the opaque handles of include/kmerjs_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/kmerjs_b200.h"
+#include "kj_device.cuh"
+
+// Kernel launch.  The second definition belongs to tools/cuemu (a developer-only harness that
+// compiles these sources with g++ to run them under AddressSanitizer on a box without a GPU);
+// the shipped library is always built by nvcc and takes the first one.
+#ifndef KJ_CPU_EMU
+#define KJ_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define KJ_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#endif
+
+struct kj_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;      // launch stream
+    bool own_stream = false;
+    cudaStream_t copy_stream = nullptr; // H2D staging
+    std::recursive_mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    int rounding_mode = 4;              // bignumber.js ROUND_HALF_UP
+    // scan-kernel timing (CUDA events on `stream`)
+    bool timers_on = false;
+    double scan_ms = 0.0;
+    uint64_t scan_launches = 0;
+    uint64_t scan_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // host -> device staging (KJ_MEM_HOST buffers), double buffered, owned by the context so that
+    // repeated count jobs do not re-allocate
+    uint8_t *d_stage[2] = {nullptr, nullptr};
+    uint8_t *h_stage[2] = {nullptr, nullptr};
+    uint64_t stage_cap = 0;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+};
+
+// stream-ordered device memory from the default pool (release threshold = keep everything), so
+// that per-job tables are recycled without cudaMalloc/cudaFree round trips
+template <class T>
+static inline cudaError_t kj_dmalloc(kj_ctx *ctx, T **p, uint64_t bytes) {
+    return cudaMallocAsync((void **)p, bytes ? bytes : 1, ctx->stream);
+}
+static inline void kj_dfree(kj_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+extern thread_local std::string kj_tls_error;
+
+int kj_fail(kj_ctx *ctx, int code, const std::string &msg);
+
+#define KJ_CUDA(ctx, call)                                                              \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return kj_fail((ctx), KJ_E_CUDA,                                            \
+                           std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+struct KjCompact {        // built by kj_counts_finish: dense list of the regular entries
+    uint64_t *keys = nullptr;
+    uint64_t *counts = nullptr;
+    uint64_t *ords = nullptr;
+    uint8_t *alive = nullptr;   // WTA alive mask (1 = still in the query map)
+    uint64_t n = 0;             // all entries: [0,n_tab) table entries, then the special key (k = 32,
+    uint64_t n_reg = 0;         // all G) if present -> n_reg, then the irregular entries (byte keys on
+    uint64_t n_tab = 0;         // the host, irr_host, same order)
+};
+
+struct kj_counts {
+    kj_ctx *ctx = nullptr;
+    // parameters
+    std::vector<uint8_t> prefix, rprefix;
+    uint32_t k = 16, step = 1, flags = 0;
+    bool order = true;
+    bool use_filter = true;      // filter kernel (step == 1, 1 <= m <= k) or line kernel
+    uint64_t capacity_hint = 0;
+    // stream position
+    uint64_t voff = 0;           // virtual offset of the next byte (starts at base_col)
+    uint64_t consumed = 0;       // stream bytes consumed
+    uint32_t parity = 0;
+    bool finished = false;
+    bool saw_final = false;
+    // device state
+    KjTable tab{};
+    uint64_t cap = 0;
+    KjIrrTable irr{};
+    uint64_t irr_cap = 0;
+    KjOverflow ovf{};
+    KjCounters *ctr = nullptr;        // device
+    KjCounters *h_ctr = nullptr;      // pinned mirror
+    uint64_t *tile_mem = nullptr;     // 3 * tile_cap u64
+    uint64_t tile_cap = 0;
+    // results
+    KjCompact reg{};
+    // irregular entries, host side after finish: 56-byte records
+    std::vector<uint8_t> irr_host;   // {u8 key[32], u64 len, u64 count, u64 ord} * n
+    std::vector<uint64_t> export_perm;   // export position -> query index (built on first export)
+    uint64_t bytes_read = 0;
+    uint64_t lines = 0;
+    uint64_t occurrences = 0;
+    uint64_t bases = 0;
+    uint64_t special_count = 0, special_ord = 0;
+    // partition scratch
+    uint64_t *part_rec = nullptr;
+    uint64_t part_cap = 0;
+};
+
+// records used by the exchange and by export: {key, count, ord}
+struct KjRecord { uint64_t key, count, ord; };
+struct KjIrrRecord { uint8_t key[32]; uint64_t len, count, ord; };
+
+// kj_count.cu internals used by kj_score.cu
+int kj_counts_check_finished(const kj_counts *c);
+int kj_grid_for(const kj_ctx *ctx, uint64_t n, int threads = 256);
+void kj_decode_key(uint64_t key, uint32_t k, uint8_t *out);

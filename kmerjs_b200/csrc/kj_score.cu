@@ -1,0 +1,853 @@
+// kj_score.cu -- template scoring on the GPU (K4-K6 of SURVEY.md appendix B):
+//
+//   kj_db_*         k-mer -> ordered template list as a device hash index + CSR lists; replaces the
+//                   Redis LRANGE store of lib/kmerFinderServer.js:171-226 (schema :68-92,184-199)
+//   kj_first_match  per-template uScore / tScore / hits over the query (lib/kmerFinderServer.js:180-201)
+//   kj_wta_next     one round of the findMatches generator (lib/kmerFinderClient.js:174-290):
+//                   argmax over uScore (ties: first-encounter order), gate, removal of the winner's
+//                   k-mers with incremental score decrements
+//
+// Layout in HBM.  DB: keys[cap] u64 + vals[cap] u32 (open addressing, linear probing), list_off
+// [n_kmers+1] u64, tmpl[pairs] u32 (DB list order), ulen[T] u64.  Match: score vector
+// S = {u[T], tau[T], H} u64 (partial sums of this rank) and G (global sums; G == S on one GPU),
+// first-encounter keys first_ord[T], first_idx[T] u64, rank[T] u32, the per-template CSR of
+// matched query entries toff[T+1] u64 / tq[hits] u32, qkmer[Q] u32 (DB k-mer id per query entry).
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+#include "kj_internal.hpp"
+#include "kj_stats.hpp"
+
+#define KJ_NONE32 0xFFFFFFFFu
+#define KJ_SCORE_THREADS 256
+#define KJ_SMEM_T_MAX 8192u     // templates whose u (u32) and tau (u64) are privatised in shared memory
+
+struct KjDbDev {
+    const uint64_t *keys;
+    const uint32_t *vals;
+    uint64_t mask;
+    const uint64_t *list_off;
+    const uint32_t *tmpl;
+};
+
+struct kj_db {
+    kj_ctx *ctx = nullptr;
+    uint32_t k = 0;                 // length of the regular (ACGT-only) k-mers in the device index
+    uint64_t n_kmers = 0, n_pairs = 0;
+    uint32_t n_templates = 0;
+    uint64_t *d_keys = nullptr;
+    uint32_t *d_vals = nullptr;
+    uint64_t cap = 0;
+    uint64_t *d_list_off = nullptr;
+    uint32_t *d_tmpl = nullptr;
+    uint64_t *d_ulen = nullptr;
+    std::vector<uint64_t> lengths, ulengths;
+    std::unordered_map<std::string, uint32_t> other;   // k-mers that are not regular: bytes -> k-mer id
+    uint32_t special_id = KJ_NONE32;                   // k-mer whose key equals KJ_EMPTY (k = 32, all G)
+    uint64_t s_templates = 0, s_unique_lens = 0, s_total_len = 0;
+    KjDbDev dev() const { return KjDbDev{d_keys, d_vals, cap - 1, d_list_off, d_tmpl}; }
+};
+
+struct KjWtaResult {        // written by the argmax kernel, copied to the host every round
+    uint32_t winner;        // template id, KJ_NONE32 when every uScore is zero
+    uint32_t pad;
+    uint64_t u, tau, hits;
+    double z, p;            // double-precision zScore / fastp * templates (the device gate)
+};
+
+struct kj_match {
+    kj_ctx *ctx = nullptr;
+    kj_counts *q = nullptr;
+    const kj_db *db = nullptr;
+    uint32_t T = 0;
+    uint64_t Q = 0;
+    uint32_t *d_qkmer = nullptr;
+    uint64_t *d_part = nullptr;      // {u[T], tau[T], H}: this rank's sums
+    uint64_t *d_glob = nullptr;      // global sums (== d_part unless the host layer reduces over ranks)
+    uint64_t *d_first_ord = nullptr, *d_first_idx = nullptr;
+    uint32_t *d_rank = nullptr;
+    uint64_t *d_toff = nullptr;
+    unsigned long long *d_tcur = nullptr;
+    uint32_t *d_tq = nullptr;
+    KjWtaResult *d_res = nullptr, *h_res = nullptr;
+    bool committed = false;
+    bool distributed = false;        // d_glob is separate and maintained by the host layer
+    std::vector<uint64_t> u0, t0;    // first-round scores (lib/kmerFinderClient.js:44-46)
+    std::vector<uint32_t> order;     // matched templates in first-encounter order
+    uint64_t hits0 = 0;
+    uint64_t kmer_map_size = 0;
+    uint32_t max_hits = 100, hit_counter = 0;
+    bool ended = false;
+};
+
+// ------------------------------------------------------------------------------------ kernels
+
+__device__ __forceinline__ uint32_t kj_db_lookup(const KjDbDev &d, uint64_t key) {
+    uint64_t slot = kj_mix64(key) & d.mask;
+    for (;;) {
+        uint64_t cur = d.keys[slot];
+        if (cur == key) return d.vals[slot];
+        if (cur == KJ_EMPTY) return KJ_NONE32;
+        slot = (slot + 1) & d.mask;
+    }
+}
+
+__global__ void kj_db_build_kernel(uint64_t *keys, uint32_t *vals, uint64_t mask, const uint64_t *in_keys,
+                                   const uint32_t *in_ids, uint64_t n, unsigned int *dup_flag) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t key = in_keys[i];
+        uint64_t slot = kj_mix64(key) & mask;
+        for (;;) {
+            uint64_t cur = atomicCAS((unsigned long long *)&keys[slot], (unsigned long long)KJ_EMPTY,
+                                     (unsigned long long)key);
+            if (cur == KJ_EMPTY) { vals[slot] = in_ids[i]; break; }
+            if (cur == key) { atomicOr(dup_flag, 1u); break; }     // duplicate k-mer in the DB
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+
+// query entry -> DB k-mer id (table entries only; the special and irregular ones are resolved on the host)
+__global__ void kj_probe_kernel(KjDbDev d, const uint64_t *qkeys, uint64_t n_tab, uint32_t *qkmer) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_tab;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        qkmer[i] = kj_db_lookup(d, qkeys[i]);
+}
+
+struct KjWalkArgs {
+    KjDbDev d;
+    const uint32_t *qkmer;
+    const uint64_t *qcount, *qord;
+    const uint8_t *alive;
+    uint64_t Q;
+    uint32_t T;
+    uint64_t *part;              // u[T], tau[T], H
+    uint64_t *first_ord, *first_idx;
+    const uint64_t *toff;
+    unsigned long long *tcur;
+    uint32_t *tq;
+};
+
+enum { KJ_WALK_ACCUM = 0, KJ_WALK_FIRST = 1, KJ_WALK_FILL = 2 };
+
+// Every warp takes 32 consecutive query entries; entries that hit the DB are walked one after the
+// other by the whole warp (lanes stride over the template list: coalesced reads of tmpl[]).
+//   ACCUM: u[t] += 1, tau[t] += count, first_ord[t] = min(ord), H += list length.  With SMEM the
+//          block keeps u (u32) / tau (u64) in shared memory and flushes once.
+//   FIRST: first_idx[t] = min(list index) over the entries whose ord equals first_ord[t].
+//   FILL : tq[toff[t] + cursor[t]++] = q  (per-template list of matched query entries).
+template <int MODE, bool SMEM>
+__global__ void __launch_bounds__(KJ_SCORE_THREADS) kj_walk_kernel(const KjWalkArgs a) {
+    KJ_DYN_SMEM(dyn);
+    unsigned long long *s_tau = reinterpret_cast<unsigned long long *>(dyn);
+    uint32_t *s_u = reinterpret_cast<uint32_t *>(dyn + (size_t)a.T * 8);
+    const uint32_t lane = threadIdx.x & 31;
+    if (MODE == KJ_WALK_ACCUM && SMEM) {
+        for (uint32_t t = threadIdx.x; t < a.T; t += blockDim.x) { s_tau[t] = 0; s_u[t] = 0; }
+        __syncthreads();
+    }
+    unsigned long long my_hits = 0;
+    const uint64_t n_groups = (a.Q + 31) / 32;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
+        const uint64_t q = g * 32 + lane;
+        uint32_t id = KJ_NONE32;
+        uint64_t cnt = 0, ord = 0;
+        if (q < a.Q && a.alive[q]) {
+            id = a.qkmer[q];
+            if (id != KJ_NONE32) { cnt = a.qcount[q]; ord = a.qord[q]; }
+        }
+        uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, id != KJ_NONE32);
+        while (hitmask) {
+            const int src = __ffs(hitmask) - 1;
+            hitmask &= hitmask - 1;
+            const uint32_t kid = __shfl_sync(0xFFFFFFFFu, id, src);
+            const uint64_t c = __shfl_sync(0xFFFFFFFFu, cnt, src);
+            const uint64_t o = __shfl_sync(0xFFFFFFFFu, ord, src);
+            const uint64_t lo = a.d.list_off[kid], hi = a.d.list_off[kid + 1];
+            if (MODE == KJ_WALK_ACCUM && lane == 0) my_hits += hi - lo;
+            for (uint64_t i = lo + lane; i < hi; i += 32) {
+                const uint32_t t = a.d.tmpl[i];
+                if (MODE == KJ_WALK_ACCUM) {
+                    if (SMEM) {
+                        atomicAdd(&s_u[t], 1u);
+                        atomicAdd(&s_tau[t], (unsigned long long)c);
+                    } else {
+                        atomicAdd((unsigned long long *)&a.part[t], 1ull);
+                        atomicAdd((unsigned long long *)&a.part[a.T + t], (unsigned long long)c);
+                    }
+                    if (a.first_ord[t] > o) atomicMin((unsigned long long *)&a.first_ord[t], (unsigned long long)o);
+                } else if (MODE == KJ_WALK_FIRST) {
+                    if (a.first_ord[t] == o)
+                        atomicMin((unsigned long long *)&a.first_idx[t], (unsigned long long)(i - lo));
+                } else {
+                    unsigned long long pos = atomicAdd(&a.tcur[t], 1ull);
+                    a.tq[a.toff[t] + pos] = (uint32_t)(g * 32 + src);
+                }
+            }
+        }
+    }
+    if (MODE == KJ_WALK_ACCUM) {
+        for (int d = 16; d > 0; d >>= 1) my_hits += __shfl_xor_sync(0xFFFFFFFFu, my_hits, d);
+        if (lane == 0 && my_hits) atomicAdd((unsigned long long *)&a.part[2 * (uint64_t)a.T], my_hits);
+        if (SMEM) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < a.T; t += blockDim.x) {
+                uint32_t u = s_u[t];
+                if (u) {
+                    atomicAdd((unsigned long long *)&a.part[t], (unsigned long long)u);
+                    atomicAdd((unsigned long long *)&a.part[a.T + t], s_tau[t]);
+                }
+            }
+        }
+    }
+}
+
+// double-precision restatement of lib/stats.js:19-45 (the device gate; rows are finished exactly on the host)
+__device__ __forceinline__ double kj_zscore_f64(double r1, double n1, double r2, double n2) {
+    const double eta = 1.0e-8;
+    double p1 = r1 / n1 + eta, p2 = r2 / n2 + eta;
+    double p = (r1 + r2) / (n1 + n2 + eta);
+    double q = 1.0 - p;
+    double s = sqrt(p * q * (1.0 / (n1 + eta) + 1.0 / (n2 + eta)) + eta);
+    return (p1 - p2) / s;
+}
+__device__ __forceinline__ double kj_fastp_f64(double z) {
+    const double thr[27] = {10.7016, 10.4862, 10.2663, 10.0416, 9.81197, 9.5769, 9.33604, 9.08895, 8.83511,
+                            8.57394, 8.30479, 8.02686, 7.73926, 7.4409,  7.13051, 6.8065,  6.46695, 6.10941,
+                            5.73073, 5.32672, 4.89164, 4.41717, 3.89059, 3.29053, 2.57583, 1.95996, 1.64485};
+    const double pv[27] = {1e-26, 1e-25, 1e-24, 1e-23, 1e-22, 1e-21, 1e-20, 1e-19, 1e-18,
+                           1e-17, 1e-16, 1e-15, 1e-14, 1e-13, 1e-12, 1e-11, 1e-10, 1e-9,
+                           1e-8,  1e-7,  1e-6,  1e-5,  1e-4,  1e-3,  0.01,  0.05,  0.1};
+    for (int i = 0; i < 27; ++i)
+        if (z > thr[i]) return pv[i];
+    return 1.0;
+}
+
+__global__ void kj_stats_kernel(uint64_t n, const uint64_t *r1, const uint64_t *n1, const uint64_t *r2,
+                                const uint64_t *n2, double *z, double *p) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        double zz = kj_zscore_f64((double)r1[i], (double)n1[i], (double)r2[i], (double)n2[i]);
+        z[i] = zz;
+        p[i] = kj_fastp_f64(zz);
+    }
+}
+
+// winner = argmax over (uScore desc, first-encounter rank asc)  (lib/kmerFinderClient.js:100-109,181;
+// the stable-sort tie rule of SURVEY.md 7.5).  One block.
+__global__ void __launch_bounds__(1024) kj_argmax_kernel(const uint64_t *glob, const uint32_t *rank, uint32_t T,
+                                                         const uint64_t *ulen, double unique_lens,
+                                                         double n_templates, KjWtaResult *res) {
+    __shared__ unsigned long long s_best[32];
+    __shared__ uint32_t s_who[32];
+    // key = u << 32 | ~rank  (u < 2^32: a template has fewer than 2^32 k-mers in one query)
+    unsigned long long best = 0;
+    uint32_t who = KJ_NONE32;
+    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+        uint64_t u = glob[t];
+        if (!u) continue;
+        unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(~rank[t]);
+        if (key > best) { best = key; who = t; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
+        uint32_t ow = __shfl_xor_sync(0xFFFFFFFFu, who, d);
+        if (ob > best) { best = ob; who = ow; }
+    }
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_best[warp] = best; s_who[warp] = who; }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t nw = (blockDim.x + 31) >> 5;
+        best = lane < nw ? s_best[lane] : 0ull;
+        who = lane < nw ? s_who[lane] : KJ_NONE32;
+        for (int d = 16; d > 0; d >>= 1) {
+            unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
+            uint32_t ow = __shfl_xor_sync(0xFFFFFFFFu, who, d);
+            if (ob > best) { best = ob; who = ow; }
+        }
+        if (lane == 0) {
+            KjWtaResult r;
+            r.winner = who; r.pad = 0;
+            r.hits = glob[2 * (uint64_t)T];
+            r.u = 0; r.tau = 0; r.z = 0.0; r.p = 1.0;
+            if (who != KJ_NONE32) {
+                r.u = glob[who];
+                r.tau = glob[(uint64_t)T + who];
+                r.z = kj_zscore_f64((double)r.u, (double)ulen[who], (double)r.hits, unique_lens);
+                r.p = kj_fastp_f64(r.z) * n_templates;
+            }
+            *res = r;
+        }
+    }
+}
+
+// Remove the winner's k-mers from the query (kmerMap.delete, lib/kmerFinderClient.js:220-230) and
+// take their contribution out of every template that shares them.  One warp per matched entry.
+__global__ void kj_remove_kernel(KjDbDev d, const uint32_t *tq, uint64_t lo, uint64_t hi, const uint32_t *qkmer,
+                                 const uint64_t *qcount, uint8_t *alive, uint64_t *part, uint32_t T) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long gone = 0;
+    for (uint64_t i = lo + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < hi; i += warps) {
+        const uint32_t q = tq[i];
+        const uint8_t was = alive[q];          // each q occurs once in a template's list (DB lists are deduplicated)
+        __syncwarp();
+        if (!was) continue;
+        if (lane == 0) alive[q] = 0;
+        const uint32_t kid = qkmer[q];
+        const unsigned long long c = qcount[q];
+        const uint64_t l0 = d.list_off[kid], l1 = d.list_off[kid + 1];
+        if (lane == 0) gone += l1 - l0;
+        for (uint64_t j = l0 + lane; j < l1; j += 32) {
+            const uint32_t t = d.tmpl[j];
+            atomicAdd((unsigned long long *)&part[t], ~0ull);                    // u[t] -= 1
+            atomicAdd((unsigned long long *)&part[(uint64_t)T + t], 0ull - c);    // tau[t] -= count
+        }
+    }
+    if (lane == 0 && gone) atomicAdd((unsigned long long *)&part[2 * (uint64_t)T], 0ull - gone);
+}
+
+// ------------------------------------------------------------------------------------ database
+
+static bool all_acgt(const uint8_t *p, uint32_t n) {
+    for (uint32_t i = 0; i < n; ++i) if (!kj_is_acgt(p[i])) return false;
+    return true;
+}
+static uint64_t pack_key(const uint8_t *p, uint32_t n) {
+    uint64_t key = 0;
+    for (uint32_t i = 0; i < n; ++i) key = (key << 2) | kj_code(p[i]);
+    return key;
+}
+static uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+
+extern "C" void kj_db_free(kj_db *db) {
+    if (!db) return;
+    kj_ctx *ctx = db->ctx;
+    if (ctx) {
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        cudaSetDevice(ctx->device);
+        kj_dfree(ctx, db->d_keys); kj_dfree(ctx, db->d_vals); kj_dfree(ctx, db->d_list_off);
+        kj_dfree(ctx, db->d_tmpl); kj_dfree(ctx, db->d_ulen);
+    }
+    delete db;
+}
+
+extern "C" int kj_db_create(kj_ctx *ctx, const kj_db_desc *d, kj_db **out) {
+    if (!ctx || !d || !out) return kj_fail(ctx, KJ_E_INVALID, "kj_db_create: null argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (d->n_kmers && (!d->kmer_bytes || !d->kmer_len || !d->list_off || !d->tmpl_ids))
+        return kj_fail(ctx, KJ_E_INVALID, "kj_db_create: null k-mer arrays");
+    if (d->n_templates && (!d->lengths || !d->ulengths))
+        return kj_fail(ctx, KJ_E_INVALID, "kj_db_create: null template arrays");
+    if (d->n_kmers > 0xFFFFFFF0ull) return kj_fail(ctx, KJ_E_RANGE, "more than 2^32 DB k-mers on one GPU");
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    kj_db *db = new kj_db();
+    db->ctx = ctx;
+    db->n_templates = d->n_templates;
+    db->lengths.assign(d->lengths, d->lengths + d->n_templates);
+    db->ulengths.assign(d->ulengths, d->ulengths + d->n_templates);
+    db->s_templates = d->summary_templates;
+    db->s_unique_lens = d->summary_unique_lens;
+    db->s_total_len = d->summary_total_len;
+    const uint32_t n_parts = d->n_parts ? d->n_parts : 1;
+
+    // regular k-mer length = length of the first ACGT-only k-mer
+    uint64_t boff = 0;
+    for (uint64_t i = 0; i < d->n_kmers && !db->k; ++i) {
+        if (d->kmer_len[i] >= 1 && d->kmer_len[i] <= 32 && all_acgt(d->kmer_bytes + boff, d->kmer_len[i]))
+            db->k = d->kmer_len[i];
+        boff += d->kmer_len[i];
+    }
+    // keep the k-mers this part owns; rebuild the CSR with duplicate templates removed
+    // (getMatches counts Set members, lib/kmerFinderClient.js:238-259: a template counts once per k-mer)
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> ids;
+    std::vector<uint64_t> off(1, 0);
+    std::vector<uint32_t> tm;
+    std::vector<uint32_t> seen_stamp(d->n_templates, KJ_NONE32);
+    boff = 0;
+    uint32_t next_id = 0;
+    for (uint64_t i = 0; i < d->n_kmers; ++i) {
+        const uint8_t *kb = d->kmer_bytes + boff;
+        const uint32_t len = d->kmer_len[i];
+        boff += len;
+        if (len > 32) { delete db; return kj_fail(ctx, KJ_E_RANGE, "DB k-mer longer than 32 bytes"); }
+        const bool regular = db->k && len == db->k && all_acgt(kb, len);
+        const uint32_t owner = regular ? kj_owner_key(pack_key(kb, len), n_parts) : 0;
+        if (owner != d->part % n_parts) continue;
+        const uint32_t id = next_id;
+        if (regular) {
+            uint64_t key = pack_key(kb, len);
+            if (key == KJ_EMPTY) {
+                if (db->special_id != KJ_NONE32) continue;      // duplicate k-mer: the first list wins
+                db->special_id = id;
+            } else { keys.push_back(key); ids.push_back(id); }
+        } else {
+            if (!db->other.emplace(std::string((const char *)kb, len), id).second) continue;
+        }
+        for (uint64_t j = d->list_off[i]; j < d->list_off[i + 1]; ++j) {
+            uint32_t t = d->tmpl_ids[j];
+            if (t >= d->n_templates) { delete db; return kj_fail(ctx, KJ_E_INVALID, "template id out of range"); }
+            if (seen_stamp[t] == id) continue;
+            seen_stamp[t] = id;
+            tm.push_back(t);
+        }
+        off.push_back(tm.size());
+        ++next_id;
+    }
+    db->n_kmers = next_id;
+    db->n_pairs = tm.size();
+    db->cap = pow2_at_least(std::max<uint64_t>(2 * keys.size(), 1024));
+
+    cudaError_t e = kj_dmalloc(ctx, &db->d_keys, db->cap * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &db->d_vals, db->cap * 4);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &db->d_list_off, off.size() * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &db->d_tmpl, std::max<size_t>(tm.size(), 1) * 4);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &db->d_ulen, std::max<uint32_t>(d->n_templates, 1) * 8);
+    uint64_t *d_in_keys = nullptr;
+    uint32_t *d_in_ids = nullptr;
+    unsigned int *d_dup = nullptr;
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_in_keys, std::max<size_t>(keys.size(), 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_in_ids, std::max<size_t>(ids.size(), 1) * 4);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_dup, 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(db->d_keys, 0xFF, db->cap * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(db->d_vals, 0xFF, db->cap * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_dup, 0, 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(db->d_list_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && !tm.empty()) e = cudaMemcpyAsync(db->d_tmpl, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && d->n_templates) e = cudaMemcpyAsync(db->d_ulen, d->ulengths, (size_t)d->n_templates * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && !keys.empty()) e = cudaMemcpyAsync(d_in_keys, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && !ids.empty()) e = cudaMemcpyAsync(d_in_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    unsigned int dup = 0;
+    if (e == cudaSuccess && !keys.empty()) {
+        KJ_LAUNCH(kj_db_build_kernel, kj_grid_for(ctx, keys.size()), 256, 0, ctx->stream, db->d_keys, db->d_vals,
+                  db->cap - 1, d_in_keys, d_in_ids, (uint64_t)keys.size(), d_dup);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&dup, d_dup, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // host vectors go out of scope
+    kj_dfree(ctx, d_in_keys); kj_dfree(ctx, d_in_ids); kj_dfree(ctx, d_dup);
+    if (e != cudaSuccess) {
+        kj_db_free(db);
+        return kj_fail(ctx, KJ_E_CUDA, std::string("kj_db_create: ") + cudaGetErrorString(e));
+    }
+    if (dup) {
+        kj_db_free(db);
+        return kj_fail(ctx, KJ_E_INVALID, "kj_db_create: the same k-mer appears more than once in the DB");
+    }
+    *out = db;
+    return KJ_OK;
+}
+
+extern "C" uint64_t kj_db_n_kmers(const kj_db *db) { return db ? db->n_kmers : 0; }
+extern "C" uint64_t kj_db_n_pairs(const kj_db *db) { return db ? db->n_pairs : 0; }
+extern "C" uint32_t kj_db_n_templates(const kj_db *db) { return db ? db->n_templates : 0; }
+
+// ------------------------------------------------------------------------------------ first match
+
+extern "C" void kj_match_free(kj_match *m) {
+    if (!m) return;
+    kj_ctx *ctx = m->ctx;
+    if (ctx) {
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        cudaSetDevice(ctx->device);
+        kj_dfree(ctx, m->d_qkmer);
+        if (m->d_glob != m->d_part) kj_dfree(ctx, m->d_glob);
+        kj_dfree(ctx, m->d_part);
+        kj_dfree(ctx, m->d_first_ord); kj_dfree(ctx, m->d_first_idx); kj_dfree(ctx, m->d_rank);
+        kj_dfree(ctx, m->d_toff); kj_dfree(ctx, m->d_tcur); kj_dfree(ctx, m->d_tq); kj_dfree(ctx, m->d_res);
+        if (m->h_res) cudaFreeHost(m->h_res);
+    }
+    delete m;
+}
+
+static KjWalkArgs walk_args(const kj_match *m) {
+    KjWalkArgs a{};
+    a.d = m->db->dev();
+    a.qkmer = m->d_qkmer;
+    a.qcount = m->q->reg.counts;
+    a.qord = m->q->reg.ords;
+    a.alive = m->q->reg.alive;
+    a.Q = m->Q;
+    a.T = m->T;
+    a.part = m->d_part;
+    a.first_ord = m->d_first_ord;
+    a.first_idx = m->d_first_idx;
+    a.toff = m->d_toff;
+    a.tcur = m->d_tcur;
+    a.tq = m->d_tq;
+    return a;
+}
+
+template <int MODE>
+static int launch_walk(kj_match *m) {
+    kj_ctx *ctx = m->ctx;
+    if (!m->Q) return KJ_OK;
+    KjWalkArgs a = walk_args(m);
+    const uint64_t groups = (m->Q + 31) / 32;
+    const int warps_per_block = KJ_SCORE_THREADS / 32;
+    int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((groups + warps_per_block - 1) / warps_per_block,
+                                                               (uint64_t)ctx->sm_count * 4));
+    const bool smem = MODE == KJ_WALK_ACCUM && m->T <= KJ_SMEM_T_MAX && m->T > 0;
+    if (smem) {
+        // privatised histograms: fewer, fatter blocks (one flush of T atomics per block)
+        grid = std::min(grid, ctx->sm_count * 2);
+        const size_t bytes = (size_t)m->T * 12 + 16;
+        KJ_CUDA(ctx, cudaFuncSetAttribute(kj_walk_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        KJ_LAUNCH((kj_walk_kernel<MODE, true>), grid, KJ_SCORE_THREADS, bytes, ctx->stream, a);
+    } else {
+        KJ_LAUNCH((kj_walk_kernel<MODE, false>), grid, KJ_SCORE_THREADS, 0, ctx->stream, a);
+    }
+    ctx->launches++;
+    KJ_CUDA(ctx, cudaGetLastError());
+    return KJ_OK;
+}
+
+// resolve the query entries, accumulate this rank's partial scores and first-encounter ordinals
+extern "C" int kj_first_match_local(kj_ctx *ctx, kj_counts *q, const kj_db *db, kj_match **out) {
+    if (!ctx || !q || !db || !out) return kj_fail(ctx, KJ_E_INVALID, "kj_first_match: null argument");
+    int rc = kj_counts_check_finished(q);
+    if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    kj_match *m = new kj_match();
+    m->ctx = ctx; m->q = q; m->db = db;
+    m->T = db->n_templates;
+    m->Q = q->reg.n;
+    m->kmer_map_size = q->reg.n;
+    const uint64_t T = m->T;
+    cudaError_t e = kj_dmalloc(ctx, &m->d_qkmer, std::max<uint64_t>(m->Q, 1) * 4);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_part, (2 * T + 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_ord, std::max<uint64_t>(T, 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_idx, std::max<uint64_t>(T, 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_rank, std::max<uint64_t>(T, 1) * 4);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_toff, (T + 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_tcur, std::max<uint64_t>(T, 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_res, sizeof(KjWtaResult));
+    if (e == cudaSuccess) e = cudaMallocHost(&m->h_res, sizeof(KjWtaResult));
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_qkmer, 0xFF, std::max<uint64_t>(m->Q, 1) * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_part, 0, (2 * T + 1) * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_first_ord, 0xFF, std::max<uint64_t>(T, 1) * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_first_idx, 0xFF, std::max<uint64_t>(T, 1) * 8, ctx->stream);
+    if (e != cudaSuccess) {
+        kj_match_free(m);
+        return kj_fail(ctx, KJ_E_CUDA, std::string("kj_first_match: ") + cudaGetErrorString(e));
+    }
+    m->d_glob = m->d_part;
+
+    // query entry -> DB k-mer id
+    const uint64_t n_tab = q->reg.n_tab, n_reg = q->reg.n_reg;
+    if (q->k == db->k) {
+        if (n_tab) {
+            KJ_LAUNCH(kj_probe_kernel, kj_grid_for(ctx, n_tab), 256, 0, ctx->stream, db->dev(), q->reg.keys, n_tab,
+                      m->d_qkmer);
+            ctx->launches++;
+        }
+        if (n_reg > n_tab && db->special_id != KJ_NONE32)
+            e = cudaMemcpyAsync(m->d_qkmer + n_tab, &db->special_id, 4, cudaMemcpyHostToDevice, ctx->stream);
+    } else if (!db->other.empty() && n_reg) {
+        // query k differs from the DB's regular length: only byte-string DB entries can match
+        std::vector<uint64_t> hk(n_reg);
+        std::vector<uint32_t> ids(n_reg, KJ_NONE32);
+        e = cudaMemcpyAsync(hk.data(), q->reg.keys, n_reg * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        uint8_t buf[32];
+        for (uint64_t i = 0; i < n_reg && e == cudaSuccess; ++i) {
+            kj_decode_key(hk[i], q->k, buf);
+            auto it = db->other.find(std::string((const char *)buf, q->k));
+            if (it != db->other.end()) ids[i] = it->second;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_qkmer, ids.data(), n_reg * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    const uint64_t n_irr = m->Q - n_reg;
+    if (e == cudaSuccess && n_irr && !db->other.empty()) {
+        const KjIrrRecord *ir = reinterpret_cast<const KjIrrRecord *>(q->irr_host.data());
+        std::vector<uint32_t> ids(n_irr, KJ_NONE32);
+        for (uint64_t i = 0; i < n_irr; ++i) {
+            auto it = db->other.find(std::string((const char *)ir[i].key, (size_t)ir[i].len));
+            if (it != db->other.end()) ids[i] = it->second;
+        }
+        e = cudaMemcpyAsync(m->d_qkmer + n_reg, ids.data(), n_irr * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e != cudaSuccess) {
+        kj_match_free(m);
+        return kj_fail(ctx, KJ_E_CUDA, std::string("kj_first_match: ") + cudaGetErrorString(e));
+    }
+    rc = launch_walk<KJ_WALK_ACCUM>(m);
+    if (rc) { kj_match_free(m); return rc; }
+    *out = m;
+    return KJ_OK;
+}
+
+// vectors the host layer reduces over ranks (device memory, caller-provided buffers)
+static int vec_info(kj_match *m, int which, uint64_t **ptr, uint64_t *n) {
+    switch (which) {
+        case KJ_VEC_SCORES: *ptr = m->d_part; *n = 2 * (uint64_t)m->T + 1; return KJ_OK;
+        case KJ_VEC_FIRST_ORD: *ptr = m->d_first_ord; *n = m->T; return KJ_OK;
+        case KJ_VEC_FIRST_IDX: *ptr = m->d_first_idx; *n = m->T; return KJ_OK;
+        default: return kj_fail(m->ctx, KJ_E_INVALID, "unknown vector id");
+    }
+}
+
+extern "C" uint64_t kj_match_vec_len(kj_match *m, int which) {
+    uint64_t *p = nullptr, n = 0;
+    if (!m || vec_info(m, which, &p, &n)) return 0;
+    return n;
+}
+
+extern "C" int kj_match_get(kj_match *m, int which, void *dev_out) {
+    if (!m || !dev_out) return KJ_E_INVALID;
+    kj_ctx *ctx = m->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t *p = nullptr, n = 0;
+    int rc = vec_info(m, which, &p, &n);
+    if (rc) return rc;
+    if (which == KJ_VEC_FIRST_IDX) {
+        // second stage of the (ordinal, list index) minimum: only entries whose ordinal equals the
+        // (by now global) first_ord contribute
+        KJ_CUDA(ctx, cudaMemsetAsync(m->d_first_idx, 0xFF, std::max<uint64_t>(m->T, 1) * 8, ctx->stream));
+        rc = launch_walk<KJ_WALK_FIRST>(m);
+        if (rc) return rc;
+    }
+    if (n) KJ_CUDA(ctx, cudaMemcpyAsync(dev_out, p, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KJ_OK;
+}
+
+extern "C" int kj_match_set(kj_match *m, int which, const void *dev_in) {
+    if (!m || !dev_in) return KJ_E_INVALID;
+    kj_ctx *ctx = m->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t *p = nullptr, n = 0;
+    int rc = vec_info(m, which, &p, &n);
+    if (rc) return rc;
+    if (which == KJ_VEC_SCORES) {
+        // global sums live beside the partial ones from now on
+        if (m->d_glob == m->d_part) {
+            uint64_t *g = nullptr;
+            KJ_CUDA(ctx, kj_dmalloc(ctx, &g, n * 8));
+            m->d_glob = g;
+            m->distributed = true;
+        }
+        p = m->d_glob;
+    }
+    if (n) KJ_CUDA(ctx, cudaMemcpyAsync(p, dev_in, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KJ_OK;
+}
+
+extern "C" int kj_match_set_query_size(kj_match *m, uint64_t kmer_map_size) {
+    if (!m) return KJ_E_INVALID;
+    m->kmer_map_size = kmer_map_size;
+    return KJ_OK;
+}
+
+// first-encounter order, first-round scores, per-template lists of matched query entries
+extern "C" int kj_match_commit(kj_match *m) {
+    if (!m) return KJ_E_INVALID;
+    kj_ctx *ctx = m->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (m->committed) return kj_fail(ctx, KJ_E_STATE, "kj_match_commit called twice");
+    const uint64_t T = m->T;
+    int rc;
+    if (!m->distributed) {
+        // single GPU: first_ord is already global; compute the list indices now
+        rc = launch_walk<KJ_WALK_FIRST>(m);
+        if (rc) return rc;
+    }
+    std::vector<uint64_t> glob(2 * T + 1), part_u(T), ford(T), fidx(T);
+    KJ_CUDA(ctx, cudaMemcpyAsync(glob.data(), m->d_glob, (2 * T + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (T) {
+        KJ_CUDA(ctx, cudaMemcpyAsync(part_u.data(), m->d_part, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KJ_CUDA(ctx, cudaMemcpyAsync(ford.data(), m->d_first_ord, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KJ_CUDA(ctx, cudaMemcpyAsync(fidx.data(), m->d_first_idx, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    m->u0.assign(glob.begin(), glob.begin() + T);
+    m->t0.assign(glob.begin() + T, glob.begin() + 2 * T);
+    m->hits0 = glob[2 * T];
+    // templates in order of first encounter (lib/kmerFinderServer.js:180-201: query k-mers in Map
+    // order, each list in DB order) = ascending (first ordinal, list index)
+    m->order.clear();
+    for (uint32_t t = 0; t < T; ++t) if (m->u0[t]) m->order.push_back(t);
+    std::sort(m->order.begin(), m->order.end(), [&](uint32_t a, uint32_t b) {
+        if (ford[a] != ford[b]) return ford[a] < ford[b];
+        if (fidx[a] != fidx[b]) return fidx[a] < fidx[b];
+        return a < b;
+    });
+    std::vector<uint32_t> rank(T, KJ_NONE32 - 1);
+    for (uint32_t i = 0; i < m->order.size(); ++i) rank[m->order[i]] = i;
+    // CSR of this rank's matched entries per template (sized by the partial uScores)
+    std::vector<uint64_t> toff(T + 1, 0);
+    for (uint64_t t = 0; t < T; ++t) toff[t + 1] = toff[t] + part_u[t];
+    const uint64_t local_pairs = toff[T];
+    if (local_pairs > 0xFFFFFFF0ull * 16) return kj_fail(ctx, KJ_E_RANGE, "too many matched pairs");
+    kj_dfree(ctx, m->d_tq);
+    m->d_tq = nullptr;
+    KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_tq, std::max<uint64_t>(local_pairs, 1) * 4));
+    if (T) {
+        KJ_CUDA(ctx, cudaMemcpyAsync(m->d_rank, rank.data(), T * 4, cudaMemcpyHostToDevice, ctx->stream));
+        KJ_CUDA(ctx, cudaMemsetAsync(m->d_tcur, 0, T * 8, ctx->stream));
+    }
+    KJ_CUDA(ctx, cudaMemcpyAsync(m->d_toff, toff.data(), (T + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_walk<KJ_WALK_FILL>(m);
+    if (rc) return rc;
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // rank/toff are host vectors
+    m->committed = true;
+    return KJ_OK;
+}
+
+extern "C" int kj_first_match(kj_ctx *ctx, kj_counts *q, const kj_db *db, kj_match **out) {
+    kj_match *m = nullptr;
+    int rc = kj_first_match_local(ctx, q, db, &m);
+    if (rc) return rc;
+    rc = kj_match_commit(m);
+    if (rc) { kj_match_free(m); return rc; }
+    if (m->hits0 == 0) {
+        // lib/kmerFinderServer.js:219-221; the client rejects with the same text (:159-161)
+        kj_match_free(m);
+        return kj_fail(ctx, KJ_E_NO_HITS, "No hits were found!");
+    }
+    *out = m;
+    return KJ_OK;
+}
+
+extern "C" uint64_t kj_match_hits(const kj_match *m) { return m ? m->hits0 : 0; }
+extern "C" uint32_t kj_match_n_matched(const kj_match *m) { return m ? (uint32_t)m->order.size() : 0; }
+
+extern "C" int kj_match_scores(kj_match *m, uint64_t *uscore, uint64_t *tscore, uint32_t *order) {
+    if (!m) return KJ_E_INVALID;
+    if (!m->committed) return kj_fail(m->ctx, KJ_E_STATE, "kj_match_commit has not run");
+    if (uscore) memcpy(uscore, m->u0.data(), m->u0.size() * 8);
+    if (tscore) memcpy(tscore, m->t0.data(), m->t0.size() * 8);
+    if (order) memcpy(order, m->order.data(), m->order.size() * 4);
+    return KJ_OK;
+}
+
+extern "C" int kj_match_set_max_hits(kj_match *m, uint32_t max_hits) {
+    if (!m) return KJ_E_INVALID;
+    m->max_hits = max_hits;
+    return KJ_OK;
+}
+
+// ------------------------------------------------------------------------------------ winner takes all
+
+extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
+    if (!m || !out) return KJ_E_INVALID;
+    kj_ctx *ctx = m->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (!m->committed) return kj_fail(ctx, KJ_E_STATE, "kj_match_commit has not run");
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    // while (notFound && hitCounter < maxHits)   lib/kmerFinderClient.js:274
+    if (m->ended || m->hit_counter >= m->max_hits) {
+        m->ended = true;
+        if (m->hit_counter == 0)
+            return kj_fail(ctx, KJ_E_NO_WINNER, "No hits were found! (kmerResults.length === 0)");
+        return 0;
+    }
+    KJ_LAUNCH(kj_argmax_kernel, 1, 1024, 0, ctx->stream, m->d_glob, m->d_rank, m->T, m->db->d_ulen,
+              (double)m->db->s_unique_lens, (double)m->db->s_templates, m->d_res);
+    ctx->launches++;
+    KJ_CUDA(ctx, cudaMemcpyAsync(m->h_res, m->d_res, sizeof(KjWtaResult), cudaMemcpyDeviceToHost, ctx->stream));
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const KjWtaResult r = *m->h_res;
+    // getMatches: nHits === 0 throws (lib/kmerFinderClient.js:264-266), also after earlier winners
+    if (r.hits == 0 || r.winner == KJ_NONE32) {
+        m->ended = true;
+        return kj_fail(ctx, KJ_E_NO_HITS, "No hits were found! (nHits === 0)");
+    }
+    const uint32_t w = r.winner;
+    int accepted = 0;
+    if (!kj_exact_row(ctx->rounding_mode, r.u, r.tau, m->u0[w], m->t0[w], m->db->lengths[w], m->db->ulengths[w],
+                      r.hits, m->kmer_map_size, m->db->s_templates, m->db->s_unique_lens, out, &accepted))
+        return kj_fail(ctx, KJ_E_INVALID, "template with zero length / ulength or zero Summary.uniqueLens");
+    out->template_id = w;
+    out->z_device = r.z;
+    out->probability_device = r.p;
+    if (!accepted) {
+        // findWinner returned undefined: notFound = false (lib/kmerFinderClient.js:214-217)
+        m->ended = true;
+        if (m->hit_counter == 0)
+            return kj_fail(ctx, KJ_E_NO_WINNER, "No hits were found! (kmerResults.length === 0)");
+        return 0;
+    }
+    m->hit_counter++;
+    // removeWinnerKmers (lib/kmerFinderClient.js:220-230) on this rank's share of K_w
+    std::vector<uint64_t> range(2);
+    KJ_CUDA(ctx, cudaMemcpyAsync(range.data(), m->d_toff + w, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (range[1] > range[0]) {
+        const uint64_t n = range[1] - range[0];
+        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8));
+        KJ_LAUNCH(kj_remove_kernel, grid, 256, 0, ctx->stream, m->db->dev(), m->d_tq, range[0], range[1], m->d_qkmer,
+                  m->q->reg.counts, m->q->reg.alive, m->d_part, m->T);
+        ctx->launches++;
+        KJ_CUDA(ctx, cudaGetLastError());
+    }
+    return 1;
+}
+
+// standardScoring (lib/kmerFinderServer.js:857-874): matchSummary of every matched template against
+// the first-match result, sorted by score (descending, stable); templates the evalue gate rejects
+// produce no row.
+extern "C" int kj_standard_scoring(kj_match *m, kj_row *rows, uint32_t n_rows_cap, uint32_t *n_rows) {
+    if (!m || !n_rows) return KJ_E_INVALID;
+    kj_ctx *ctx = m->ctx;
+    if (!m->committed) return kj_fail(ctx, KJ_E_STATE, "kj_match_commit has not run");
+    std::vector<kj_row> all;
+    for (uint32_t t : m->order) {
+        kj_row r;
+        memset(&r, 0, sizeof(r));
+        int accepted = 0;
+        if (!kj_exact_row(ctx->rounding_mode, m->u0[t], m->t0[t], m->u0[t], m->t0[t], m->db->lengths[t],
+                          m->db->ulengths[t], m->hits0, m->kmer_map_size, m->db->s_templates,
+                          m->db->s_unique_lens, &r, &accepted))
+            return kj_fail(ctx, KJ_E_INVALID, "template with zero length / ulength or zero Summary.uniqueLens");
+        if (!accepted) continue;
+        r.template_id = t;
+        all.push_back(r);
+    }
+    std::stable_sort(all.begin(), all.end(), [](const kj_row &a, const kj_row &b) { return a.score > b.score; });
+    *n_rows = (uint32_t)all.size();
+    if (rows) {
+        if (all.size() > n_rows_cap) return kj_fail(ctx, KJ_E_RANGE, "row buffer too small");
+        if (!all.empty()) memcpy(rows, all.data(), all.size() * sizeof(kj_row));
+    }
+    return KJ_OK;
+}
+
+extern "C" int kj_stats_zscore_device(kj_ctx *ctx, uint64_t n, const uint64_t *r1, const uint64_t *n1,
+                                      const uint64_t *r2, const uint64_t *n2, double *z, double *p) {
+    if (!ctx || (n && (!r1 || !n1 || !r2 || !n2 || !z || !p))) return kj_fail(ctx, KJ_E_INVALID, "null argument");
+    if (!n) return KJ_OK;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t *d_in = nullptr;
+    double *d_out = nullptr;
+    KJ_CUDA(ctx, kj_dmalloc(ctx, &d_in, 4 * n * 8));
+    cudaError_t e = kj_dmalloc(ctx, &d_out, 2 * n * 8);
+    const uint64_t *src[4] = {r1, n1, r2, n2};
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+        e = cudaMemcpyAsync(d_in + i * n, src[i], n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        KJ_LAUNCH(kj_stats_kernel, kj_grid_for(ctx, n), 256, 0, ctx->stream, n, d_in, d_in + n, d_in + 2 * n,
+                  d_in + 3 * n, d_out, d_out + n);
+        ctx->launches++;
+        e = cudaMemcpyAsync(z, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p, d_out + n, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    kj_dfree(ctx, d_in); kj_dfree(ctx, d_out);
+    if (e != cudaSuccess) return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e));
+    return KJ_OK;
+}

@@ -348,8 +348,10 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
         a.pat_r[i] = kj_code(c->rprefix[i]) * 0x55555555u;
     }
     memset(a.prefix, 0, 32); memset(a.rprefix, 0, 32);
-    memcpy(a.prefix, c->prefix.data(), std::min<size_t>(32, m));
-    memcpy(a.rprefix, c->rprefix.data(), std::min<size_t>(32, m));
+    if (m) {
+        memcpy(a.prefix, c->prefix.data(), std::min<size_t>(32, m));
+        memcpy(a.rprefix, c->rprefix.data(), std::min<size_t>(32, m));
+    }
     a.tab = c->tab; a.irr = c->irr; a.ovf = c->ovf; a.ctr = c->ctr;
     a.ts.status = c->tile_mem;
     a.ts.agg_last = c->tile_mem + c->tile_cap;

@@ -128,16 +128,25 @@ class KmerJS:
 
     def kmersInLine(self, line: str) -> None:
         """lib/kmers.js:88-100: count the windows of ``line`` (this strand only) into kmerMap."""
-        data = line.encode("latin-1")
-        if "\n" in line:
-            raise ValueError("kmersInLine takes one line")
+        prefix = self.preffix
+        sentinel = None
+        if "\n" in line or "\n" in prefix:
+            # a JS string may hold '\n' as an ordinary character (test/kmers.js:14-15 does); the byte
+            # stream API splits on it, so it travels as a byte that occurs nowhere else
+            used = set(line) | set(prefix)
+            sentinel = next(chr(i) for i in range(1, 256) if chr(i) not in used and chr(i) not in "ATGC\n")
+            line = line.replace("\n", sentinel)
+            prefix = prefix.replace("\n", sentinel)
         # base_line=1: the buffer starts on line index 1, i.e. it is a sequence line of the FSM;
         # the length > 1 gate belongs to readFile (lib/kmers.js:151), not to kmersInLine
-        c = Counts(flags=_abi.KJ_F_FORWARD_ONLY | _abi.KJ_F_NO_LINE_GATE, base_line=1, **self._params())
+        c = Counts(prefix.encode("latin-1"), int(self.kmerLength), int(self.step),
+                   flags=_abi.KJ_F_FORWARD_ONLY | _abi.KJ_F_NO_LINE_GATE, base_line=1)
         try:
-            c.add_host(data, final=True)
+            c.add_host(line.encode("latin-1"), final=True)
             c.finish()
             for kmer, n in c.to_dict().items():
+                if sentinel is not None:
+                    kmer = kmer.replace(sentinel, "\n")
                 self.kmerMap[kmer] = self.kmerMap.get(kmer, 0) + n
         finally:
             c.free()

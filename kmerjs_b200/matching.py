@@ -1,0 +1,122 @@
+"""Object wrapper over kj_first_match / kj_wta_next / kj_standard_scoring."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .counts import Counts
+from .db import TemplateDB
+
+# lib/kmerFinderClient.js:75-89 -- key order is part of the output JSON layout
+ROW_KEYS = ["template", "score", "expected", "z", "probability", "frac-q", "frac-d", "depth",
+            "kmers-template", "total-frac-q", "total-frac-d", "total-temp-cover", "species"]
+
+
+class NoHitsError(RuntimeError):
+    """'No hits were found!' family (lib/kmerFinderClient.js:161,265,284)."""
+
+
+def row_to_dict(r: _abi.kj_row, db: TemplateDB) -> dict:
+    def num(x):                      # JS numbers: 108 prints as 108, not 108.0
+        return int(x) if float(x).is_integer() and abs(x) < 2 ** 53 else float(x)
+    t = int(r.template_id)
+    return {"template": db.names[t], "score": int(r.score), "expected": num(r.expected), "z": num(r.z),
+            "probability": float(r.probability), "frac-q": num(r.frac_q), "frac-d": num(r.frac_d),
+            "depth": num(r.depth), "kmers-template": int(r.kmers_template),
+            "total-frac-q": num(r.total_frac_q), "total-frac-d": num(r.total_frac_d),
+            "total-temp-cover": num(r.total_temp_cover), "species": db.species[t]}
+
+
+class Match:
+    def __init__(self, counts: Counts, db: TemplateDB, *, local_only: bool = False, part: int = 0,
+                 n_parts: int = 1):
+        self.counts, self.db = counts, db
+        self.ctx = counts.ctx
+        self._L = _abi.lib()
+        self._dbh = db.device(self.ctx, part, n_parts)
+        h = C.c_void_p()
+        fn = self._L.kj_first_match_local if local_only else self._L.kj_first_match
+        rc = fn(self.ctx.handle, counts.handle, self._dbh.handle, C.byref(h))
+        if rc == _abi.KJ_E_NO_HITS:
+            raise NoHitsError("No hits were found!")
+        _abi.check(rc, self.ctx.handle)
+        self.handle = h
+        self.last_row = None
+
+    # -- distributed protocol ---------------------------------------------------------------------
+    def vec_len(self, which: int) -> int:
+        return int(self._L.kj_match_vec_len(self.handle, which))
+
+    def get(self, which: int, dev_ptr: int):
+        _abi.check(self._L.kj_match_get(self.handle, which, C.c_void_p(dev_ptr)), self.ctx.handle)
+
+    def set(self, which: int, dev_ptr: int):
+        _abi.check(self._L.kj_match_set(self.handle, which, C.c_void_p(dev_ptr)), self.ctx.handle)
+
+    def commit(self):
+        _abi.check(self._L.kj_match_commit(self.handle), self.ctx.handle)
+
+    def set_query_size(self, n: int):
+        _abi.check(self._L.kj_match_set_query_size(self.handle, n), self.ctx.handle)
+
+    # -- results ----------------------------------------------------------------------------------
+    @property
+    def hits(self) -> int:
+        return int(self._L.kj_match_hits(self.handle))
+
+    def scores(self):
+        """(uScore[T], tScore[T], order[n_matched]) of the first match."""
+        T = self.db.n_templates
+        u = np.zeros(max(T, 1), dtype=np.uint64)
+        t = np.zeros(max(T, 1), dtype=np.uint64)
+        n = int(self._L.kj_match_n_matched(self.handle))
+        o = np.zeros(max(n, 1), dtype=np.uint32)
+        _abi.check(self._L.kj_match_scores(self.handle, u.ctypes.data, t.ctypes.data, o.ctypes.data),
+                   self.ctx.handle)
+        return u[:T], t[:T], o[:n]
+
+    def templates(self) -> dict:
+        """name -> {tScore,uScore,lengths,ulength,species} in first-encounter order: the
+        ``templates`` Map of the findFirstMatch reply (lib/kmerFinderClient.js:150-157)."""
+        u, t, order = self.scores()
+        out = {}
+        for i in order.tolist():
+            out[self.db.names[i]] = {"tScore": int(t[i]), "uScore": int(u[i]),
+                                     "lengths": int(self.db.lengths[i]), "ulength": int(self.db.ulengths[i]),
+                                     "species": self.db.species[i]}
+        return out
+
+    def set_max_hits(self, n: int):
+        _abi.check(self._L.kj_match_set_max_hits(self.handle, int(n)), self.ctx.handle)
+
+    def next_row(self):
+        """One step of the findMatches generator: row dict, or None when the loop ended."""
+        r = _abi.kj_row()
+        rc = self._L.kj_wta_next(self.handle, C.byref(r))
+        if rc == _abi.KJ_E_NO_HITS:
+            raise NoHitsError("No hits were found! (nHits === 0)")
+        if rc == _abi.KJ_E_NO_WINNER:
+            raise NoHitsError("No hits were found! (kmerResults.length === 0)")
+        _abi.check(rc, self.ctx.handle)
+        self.last_row = r
+        return row_to_dict(r, self.db) if rc == 1 else None
+
+    def standard_scoring(self) -> list:
+        n = C.c_uint32()
+        cap = max(self.db.n_templates, 1)
+        rows = (_abi.kj_row * cap)()
+        _abi.check(self._L.kj_standard_scoring(self.handle, rows, cap, C.byref(n)), self.ctx.handle)
+        return [row_to_dict(rows[i], self.db) for i in range(n.value)]
+
+    def free(self):
+        if getattr(self, "handle", None):
+            self._L.kj_match_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

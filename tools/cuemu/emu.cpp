@@ -45,6 +45,7 @@ unsigned g_block_gen = 0;
 int g_nthreads = 0;
 const std::function<void()> *g_body = nullptr;
 long g_idle_spins = 0;
+long g_switches = 0;
 std::recursive_mutex g_launch_mu;
 
 void fiber_main() {
@@ -175,6 +176,7 @@ uint8_t *emu_dyn_smem() { return g_dyn.data(); }
 void emu_launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()> &body) {
     std::lock_guard<std::recursive_mutex> lk(g_launch_mu);
     g_dyn.assign(dyn_smem + 16, 0xCD);
+    g_switches = 0;
     const int nthreads = (int)(block.x * block.y * block.z);
     if ((int)g_fibers.size() < nthreads) {
         size_t old = g_fibers.size();
@@ -212,6 +214,7 @@ void emu_launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void
 #if EMU_ASAN
                 __sanitizer_start_switch_fiber(&g_sched_fake, f.stack, kStack);
 #endif
+                ++g_switches;
                 swapcontext(&g_sched, &f.ctx);
 #if EMU_ASAN
                 __sanitizer_finish_switch_fiber(g_sched_fake, nullptr, nullptr);
@@ -221,6 +224,7 @@ void emu_launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void
         }
     }
     g_body = nullptr;
+    if (getenv("EMU_STATS")) fprintf(stderr, "cuemu: launch grid=%u block=%u switches=%ld\n", grid.x, block.x, g_switches);
 }
 
 // ---- "device" memory -----------------------------------------------------------------------
@@ -230,7 +234,7 @@ std::mutex g_alloc_mu;
 cudaError_t alloc(void **p, size_t n, int kind) {
     void *q = nullptr;
     if (posix_memalign(&q, 256, n ? n : 1)) return cudaErrorMemoryAllocation;
-    memset(q, 0xCD, n);   // poison: uninitialised reads show up as garbage deterministically
+    if (n <= (16u << 20)) memset(q, 0xCD, n);   // poison: uninitialised reads show up as garbage deterministically
     std::lock_guard<std::mutex> lk(g_alloc_mu);
     g_allocs[q] = {n, kind};
     *p = q;

@@ -134,6 +134,8 @@ int kj_counts_partition(kj_counts *c, uint32_t n_parts, const void **dev_records
                         uint64_t *part_sizes /* n_parts entries */);
 /* fold packed records (device memory) into this table: counts add, ordinals min */
 int kj_counts_merge_records(kj_counts *c, const void *dev_records, uint64_t n);
+/* the same for records in host memory (a k-mer map that did not come from kj_counts_add_*: JSON) */
+int kj_counts_merge_host_records(kj_counts *c, const void *host_records, uint64_t n);
 /* irregular (non-ACGT / short) k-mers travel as 56-byte host records {u8 key[32], u64 len, u64 count, u64 ordinal} */
 uint64_t kj_counts_irregular_size(const kj_counts *c);
 int kj_counts_irregular_export(kj_counts *c, void *host_records);

@@ -88,6 +88,7 @@ SIGNATURES = {
     "kj_count_newlines": (C.c_int, [vp, vp, C.c_uint64, C.c_int, u64p, u64p]),
     "kj_counts_partition": (C.c_int, [vp, C.c_uint32, C.POINTER(vp), u64p]),
     "kj_counts_merge_records": (C.c_int, [vp, vp, C.c_uint64]),
+    "kj_counts_merge_host_records": (C.c_int, [vp, vp, C.c_uint64]),
     "kj_counts_irregular_size": (C.c_uint64, [vp]),
     "kj_counts_irregular_export": (C.c_int, [vp, vp]),
     "kj_counts_irregular_merge": (C.c_int, [vp, vp, C.c_uint64]),

@@ -124,6 +124,14 @@ class Counts:
         _abi.check(self._L.kj_counts_merge_records(self.handle, C.c_void_p(dev_ptr), n), self.ctx.handle)
         self.finished = False
 
+    def merge_host_records(self, records: np.ndarray):
+        """records: uint64[n, 3] = (2-bit key, count, ordinal)."""
+        records = np.ascontiguousarray(records, dtype=np.uint64)
+        n = records.size // 3
+        if n:
+            _abi.check(self._L.kj_counts_merge_host_records(self.handle, _ptr(records), n), self.ctx.handle)
+            self.finished = False
+
     def irregular_records(self) -> np.ndarray:
         n = int(self._L.kj_counts_irregular_size(self.handle))
         rec = np.zeros(max(n, 1) * 56, dtype=np.uint8)

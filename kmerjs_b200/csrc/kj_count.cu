@@ -882,6 +882,22 @@ extern "C" int kj_counts_merge_records(kj_counts *c, const void *dev_records, ui
     return check_device_errors(c);
 }
 
+// same as kj_counts_merge_records for records in HOST memory (a k-mer map that arrives as JSON)
+extern "C" int kj_counts_merge_host_records(kj_counts *c, const void *host_records, uint64_t n) {
+    if (!c || (n && !host_records)) return KJ_E_INVALID;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (!n) return KJ_OK;
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    KjRecord *d = nullptr;
+    KJ_CUDA(ctx, kj_dmalloc(ctx, &d, n * sizeof(KjRecord)));
+    cudaError_t e = cudaMemcpyAsync(d, host_records, n * sizeof(KjRecord), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    int rc = e == cudaSuccess ? kj_counts_merge_records(c, d, n) : kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e));
+    kj_dfree(ctx, d);
+    return rc;
+}
+
 extern "C" int kj_counts_irregular_export(kj_counts *c, void *host_records) {
     int rc = kj_counts_check_finished(c);
     if (rc) return rc;

@@ -1,0 +1,205 @@
+"""Multi-GPU partitioning of the path: one process per GPU, torch.distributed for the
+plumbing (NCCL over NVLink on the GPU box; gloo in the CPU tests of this host logic).
+
+  reads      contiguous byte ranges of the FASTQ per rank (+ halo); the record phase of a range is
+             fixed by the number of '\\n' before it (allgather of one integer per rank)
+  k-mers     owner(key) = hash(key) mod world: locally counted (key, count, first-seen ordinal)
+             records are exchanged with ONE all-to-all; owners merge with add / min
+  templates  the DB is sharded by the same owner function; per-template partial vectors are
+             all-reduced (sum for uScore/tScore/hits, min for the first-encounter keys)
+  WTA        every rank holds the global score vector, takes the same argmax and gate, removes the
+             winner's k-mers from its own shard, and the partial sums are all-reduced again.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _abi
+from .counts import Counts, count_newlines_device
+from .matching import Match, NoHitsError
+
+_SIGN = -(2 ** 63)
+
+
+def plan_ranges(n_bytes: int, world: int, halo: int = 64, align: int = 16):
+    """[(lo, own_n, read_n)] per rank: rank r owns window starts in [lo, lo+own_n) and may read
+    read_n >= own_n bytes (halo for windows / lines that cross the cut).  Cuts are 16-byte aligned
+    (device buffers are read with 16-byte vector loads)."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    cuts = [min(n_bytes, (n_bytes * r // world) // align * align) for r in range(world)] + [n_bytes]
+    out = []
+    for r in range(world):
+        lo, hi = cuts[r], cuts[r + 1]
+        out.append((lo, hi - lo, min(n_bytes, hi + halo) - lo if hi < n_bytes else hi - lo))
+    return out
+
+
+def phase_of_ranges(newline_counts, last_newline_plus1, range_lens):
+    """Given per-rank (number of '\\n', offset+1 of the last '\\n' or 0) of the OWNED ranges, return
+    per-rank (base_line, base_col): lines before the range, bytes of the current line before it."""
+    base_line, base_col = [], []
+    lines, col = 0, 0
+    for cnt, last, n in zip(newline_counts, last_newline_plus1, range_lens):
+        base_line.append(lines)
+        base_col.append(col)
+        lines += cnt
+        col = (n - last) if cnt else col + n
+    return base_line, base_col
+
+
+def _to_signed_order(t):
+    """u64 bit patterns held in int64 -> int64 values with the same ORDER (for MIN reductions)."""
+    return t ^ _SIGN
+
+
+def allreduce_u64(t, op: str, group=None):
+    """In-place all-reduce of a tensor of u64 bit patterns stored as int64.  'sum' wraps like u64;
+    'min' compares as unsigned."""
+    import torch.distributed as dist
+    if op == "sum":
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    elif op == "min":
+        t.bitwise_xor_(_SIGN)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        t.bitwise_xor_(_SIGN)
+    else:
+        raise ValueError(op)
+    return t
+
+
+def exchange_records(send, send_sizes, group=None):
+    """All-to-all of owner-grouped records.  send: int64 tensor [n, 3] grouped by destination rank,
+    send_sizes[r] = records for rank r.  Returns the int64 tensor [m, 3] this rank received."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sizes = torch.tensor(send_sizes, dtype=torch.int64, device=send.device)
+    recv_sizes = torch.empty(world, dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(recv_sizes, sizes, group=group)
+    rs = [int(x) for x in recv_sizes.tolist()]
+    recv = torch.empty((sum(rs), 3), dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(recv, send.reshape(-1, 3), output_split_sizes=rs,
+                           input_split_sizes=[int(x) for x in send_sizes], group=group)
+    return recv
+
+
+class _CudaView:
+    """Zero-copy torch view of device memory owned by libkmerjs_b200 (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, n_i64: int):
+        self.__cuda_array_interface__ = {"shape": (n_i64,), "typestr": "<i8", "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def exchange_counts(local: Counts, group=None) -> Counts:
+    """Local table -> the table of the k-mers this rank owns (collective)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device(f"cuda:{local.ctx.device}")
+    ptr, sizes = local.partition(world)
+    n = sum(sizes)
+    if n:
+        send = torch.as_tensor(_CudaView(ptr, 3 * n), device=dev).reshape(-1, 3)
+    else:
+        send = torch.empty((0, 3), dtype=torch.int64, device=dev)
+    recv = exchange_records(send, sizes, group)
+    torch.cuda.synchronize(dev)
+    owned = Counts(local.prefix, local.k, local.step, flags=local.flags & ~(_abi.KJ_F_FORWARD_ONLY),
+                   capacity_hint=max(int(recv.shape[0]), 1024), ctx=local.ctx)
+    if recv.shape[0]:
+        owned.merge_records(recv.data_ptr(), int(recv.shape[0]))
+    # irregular k-mers (rare) are gathered on rank 0 as host records
+    irr = local.irregular_records()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, irr.tobytes(), group=group)
+    if rank == 0:
+        for blob in gathered:
+            if blob:
+                owned.merge_irregular(np.frombuffer(blob, dtype=np.uint8))
+    owned.finish()
+    tot = torch.tensor([local.lines, local.bases, local.occurrences, local.bytes_read, owned.size],
+                       dtype=torch.int64, device=dev)
+    dist.all_reduce(tot, group=group)
+    lines, bases, occ, nbytes, qsize = [int(x) for x in tot.tolist()]
+    owned.set_totals(lines, bases, occ, nbytes)
+    owned.global_size = qsize
+    return owned
+
+
+def count_sharded(dev_ptr: int, n_own: int, n_read: int, *, prefix=b"ATGAC", k=16, step=1, final: bool,
+                  base_line: int | None = None, base_col: int = 0, capacity_hint: int = 0, flags: int = 0,
+                  group=None, ctx=None) -> Counts:
+    """Count this rank's byte range and exchange.  With base_line None the ranks agree on the record
+    phase first (newline counts of the owned ranges, allgathered)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if base_line is None:
+        cnt, last = count_newlines_device(dev_ptr, n_own, ctx)
+        dev = torch.device(f"cuda:{(ctx.device if ctx else 0)}")
+        mine = torch.tensor([cnt, last, n_own], dtype=torch.int64, device=dev)
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine, group=group)
+        rows = [[int(x) for x in v.tolist()] for v in allv]
+        bl, bc = phase_of_ranges([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows])
+        base_line, base_col = bl[rank], bc[rank]
+    local = Counts(prefix, k, step, flags=flags, base_line=base_line, base_col=base_col,
+                   capacity_hint=capacity_hint, ctx=ctx)
+    local.add_device(dev_ptr, n_read, own_n=n_own, final=final)
+    local.finish()
+    owned = exchange_counts(local, group)
+    local.free()
+    return owned
+
+
+class DistMatch:
+    """findFirstMatch + findMatches over ranks: every rank returns the same rows."""
+
+    def __init__(self, owned: Counts, db, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self.dev = torch.device(f"cuda:{owned.ctx.device}")
+        self.m = Match(owned, db, local_only=True, part=rank, n_parts=world)
+        self._buf = {}
+        self._reduce(_abi.KJ_VEC_SCORES, "sum")
+        self._reduce(_abi.KJ_VEC_FIRST_ORD, "min")
+        self._reduce(_abi.KJ_VEC_FIRST_IDX, "min")
+        self.m.set_query_size(int(getattr(owned, "global_size", owned.size)))
+        self.m.commit()
+        if self.m.hits == 0:
+            raise NoHitsError("No hits were found!")
+
+    def _reduce(self, which: int, op: str):
+        import torch
+        n = self.m.vec_len(which)
+        t = self._buf.get(which)
+        if t is None:
+            t = torch.empty(max(n, 1), dtype=torch.int64, device=self.dev)
+            self._buf[which] = t
+        self.m.get(which, t.data_ptr())
+        allreduce_u64(t[:n], op, self.group)
+        torch.cuda.synchronize(self.dev)
+        self.m.set(which, t.data_ptr())
+
+    @property
+    def hits(self):
+        return self.m.hits
+
+    def templates(self):
+        return self.m.templates()
+
+    def rows(self, max_hits: int = 100):
+        self.m.set_max_hits(max_hits)
+        while True:
+            row = self.m.next_row()
+            if row is None:
+                return
+            self._reduce(_abi.KJ_VEC_SCORES, "sum")
+            yield row
+
+    def free(self):
+        self.m.free()

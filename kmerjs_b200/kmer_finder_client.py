@@ -23,7 +23,6 @@ TSV_HEADER = ("Template\tScore\tExpected\tz\tp_value\tquery\tcoverage [%]\ttempl
 def counts_from_map(kmerMap: dict, preffix: str, length: int, step: int) -> Counts:
     """Device table for a k-mer map that did not come from findKmers (e.g. parsed from JSON):
     keys in Map order get ordinals 0..n-1."""
-    import torch
     c = Counts(preffix.encode("latin-1"), length, step)
     regular, irregular = [], []
     code = np.full(256, 255, dtype=np.uint8)
@@ -44,9 +43,7 @@ def counts_from_map(kmerMap: dict, preffix: str, length: int, step: int) -> Coun
                 raise ValueError("k-mers longer than 32 bytes are not supported")
             irregular.append((b, int(v), i))
     if regular:
-        rec = torch.tensor(np.array(regular, dtype=np.uint64).view(np.int64).reshape(-1, 3))
-        rec = rec.to(f"cuda:{c.ctx.device}")
-        c.merge_records(rec.data_ptr(), rec.shape[0])
+        c.merge_host_records(np.array(regular, dtype=np.uint64).reshape(-1, 3))
     if irregular:
         raw = np.zeros((len(irregular), 56), dtype=np.uint8)
         for j, (b, v, i) in enumerate(irregular):

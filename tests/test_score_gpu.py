@@ -1,0 +1,247 @@
+"""Parity of template scoring on the GPU (kj_first_match / kj_wta_next / kj_standard_scoring)
+with the CPU oracle: per-template uScore/tScore, hits, first-encounter order and winner order are
+bit-exact; rounded row fields are identical; 'probability' within 1e-9 relative."""
+import copy
+import json
+import random
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+import kmer_oracle as ko
+from conftest import read_golden
+from util import random_fastq, synthetic_db
+
+import kmerjs_b200
+from kmerjs_b200 import _abi
+from kmerjs_b200.counts import Counts
+from kmerjs_b200.db import TemplateDB
+from kmerjs_b200.kmer_finder_client import counts_from_map
+from kmerjs_b200.matching import Match, NoHitsError
+
+pytestmark = pytest.mark.gpu
+REL = 1e-9      # tolerance of the one unrounded float field (north star: 1e-9 relative)
+
+
+def oracle_rows(qmap, kmer_lists, attrs, summary, max_hits=100):
+    """(first-match templates, hits, rows, error text or None) from the CPU oracle."""
+    db = ko.TemplateDB(kmer_lists, attrs, summary)
+    q = OrderedDict(qmap)
+    templates, hits = ko.first_match(q, db)
+    first = OrderedDict((n, dict(uScore=t["uScore"], tScore=t["tScore"])) for n, t in templates.items())
+    rows, err = [], None
+    try:
+        for r in ko.find_matches(templates, summary, q, len(qmap), max_hits):
+            rows.append(r)
+    except RuntimeError as exc:
+        err = str(exc)
+    return first, hits, rows, err, q
+
+
+def gpu_rows(counts, tdb, max_hits=100):
+    m = Match(counts, tdb)
+    first = m.templates()
+    hits = m.hits
+    m.set_max_hits(max_hits)
+    rows, err = [], None
+    try:
+        while True:
+            r = m.next_row()
+            if r is None:
+                break
+            rows.append(r)
+            assert m.last_row.z_device == pytest.approx(float(ko.z_score(
+                r["score"], r["kmers-template"], int(m.last_row.hits), tdb.summary["uniqueLens"]).toNumber()), rel=REL)
+    except NoHitsError as exc:
+        err = str(exc)
+    return first, hits, rows, err, m
+
+
+def check_rows(got, exp):
+    assert [r["template"] for r in got] == [r["template"] for r in exp]        # winner order
+    for g, e in zip(got, exp):
+        assert list(g.keys()) == ko.ROW_KEYS                                     # JSON key order
+        for f in ko.ROW_KEYS:
+            if f == "probability":
+                assert g[f] == pytest.approx(e[f], rel=REL)
+            else:
+                assert g[f] == e[f], (g["template"], f)
+
+
+def test_c2_golden_query_vs_seeded_db():
+    """BASELINE config 2 as re-stated in SURVEY.md 8c: query = kmers_long.json (the golden
+    findKmers output of test_long.fastq), DB = seeded synthetic templates over those keys."""
+    golden = json.loads(read_golden("kmers_long.json"))
+    qmap = OrderedDict((k.encode("latin-1"), v) for k, v in golden.items())
+    rng = random.Random(2026)
+    lists, attrs, summary = synthetic_db(list(qmap.keys()), rng, n_templates=60, decoys=500)
+    tdb = TemplateDB.from_lists(lists, attrs, summary)
+    counts = counts_from_map(golden, "ATGAC", 16, 1)
+    assert counts.size == 6191 and counts.to_dict() == golden and list(counts.to_dict()) == list(golden)
+    e_first, e_hits, e_rows, e_err, e_q = oracle_rows(qmap, lists, attrs, summary)
+    g_first, g_hits, g_rows, g_err, m = gpu_rows(counts, tdb)
+    assert g_hits == e_hits == sum(t["uScore"] for t in e_first.values())      # KA8 invariant
+    assert list(g_first.keys()) == list(e_first.keys())                          # first-encounter order
+    for n in e_first:
+        assert (g_first[n]["uScore"], g_first[n]["tScore"]) == (e_first[n]["uScore"], e_first[n]["tScore"]), n
+    assert len(e_rows) >= 3
+    check_rows(g_rows, e_rows)
+    assert g_err == e_err
+    # the query after the loop: exactly the winner k-mers are gone (kmerMap.delete)
+    alive = counts.alive()
+    keys = list(golden.keys())
+    assert [k.encode("latin-1") for k, a in zip(keys, alive) if a] == list(e_q.keys())
+    # standard scoring (lib/kmerFinderServer.js:857-874) on a fresh match
+    m.free(); counts.free()
+
+
+def test_ka7_reference_row(known):
+    """The only stats known-answer in the reference (test/kmerFinderServer.js:70-82), through the
+    exact-decimal routine kj_wta_next uses; both bignumber rounding modes."""
+    import ctypes as C
+    ka = known["KA7_best_match"]
+    summary = json.loads(read_golden("summary.json"))
+    for mode in (4, 2):
+        r, ok = _abi.kj_row(), C.c_int()
+        _abi.check(_abi.lib().kj_stats_row(mode, ka["score"], ka["tScore"], ka["score"], ka["tScore"], 10000,
+                                           ka["kmers-template"], ka["hits"], ka["kmerMapSize"],
+                                           summary["templates"], summary["uniqueLens"], C.byref(r), C.byref(ok)))
+        assert ok.value == 1
+        assert (r.score, r.expected, r.z, r.frac_q, r.frac_d, r.depth, r.kmers_template) == \
+            (ka["score"], ka["expected"], ka["z"], ka["frac-q"], ka["frac-d"], ka["depth"], ka["kmers-template"])
+        assert (r.total_frac_q, r.total_frac_d, r.total_temp_cover) == (ka["total-frac-q"], ka["total-frac-d"], 0.36)
+        assert r.probability == pytest.approx(ka["probability"], rel=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_fastq_to_rows_end_to_end(seed, tmp_path):
+    """FASTQ -> counts on the GPU -> scoring on the GPU, against oracle count -> oracle scoring;
+    irregular (N) k-mers take part in the DB."""
+    rng = random.Random(400 + seed)
+    data = random_fastq(rng, 250, p_n=0.03 if seed % 2 else 0.0, plant=(b"ATGAC", 0.8), min_len=40)
+    qmap, _ = ko.count_fastq(data)
+    assert len(qmap) > 50
+    lists, attrs, summary = synthetic_db(list(qmap.keys()), rng, n_templates=12 + 7 * seed, decoys=50,
+                                         share=0.6)
+    tdb = TemplateDB.from_lists(lists, attrs, summary)
+    path = tmp_path / "reads.fastq"
+    path.write_bytes(data)
+    client = kmerjs_b200.KmerFinderClient(str(path), "node", "ATGAC", 16, 1, 1, False, tdb)
+    kmap = client.findKmers().promise.result(timeout=300)
+    assert {k.encode("latin-1"): v for k, v in kmap.items()} == dict(qmap) and \
+        [k.encode("latin-1") for k in kmap] == list(qmap)
+    e_first, e_hits, e_rows, e_err, e_q = oracle_rows(qmap, lists, attrs, summary)
+    winner = client.findFirstMatch(kmap).result(timeout=300)
+    assert winner["hits"] == e_hits and list(winner["templates"]) == list(e_first)
+    assert winner["summary"] == summary
+    got, err = [], None
+    try:
+        for row in client.findMatches(winner, kmap):
+            got.append(row)
+    except NoHitsError as exc:
+        err = str(exc)
+    check_rows(got, e_rows)
+    assert err == e_err
+    # the caller's map lost the winner k-mers, like the reference's Map
+    assert [k.encode("latin-1") for k in kmap if k not in ("db", "collection")] == list(e_q.keys())
+    client.close()
+
+
+def test_no_hits_errors():
+    qmap = {"ATGACAAAAAAAAAAA": 3, "ATGACCCCCCCCCCCC": 1}
+    lists = {b"ATGACGGGGGGGGGGG": ["T1"]}
+    attrs = {"T1": {"lengths": 1000, "ulength": 10, "species": "s"}}
+    summary = {"templates": 1, "uniqueLens": 10, "totalLen": 1000}
+    tdb = TemplateDB.from_lists(lists, attrs, summary)
+    c = counts_from_map(qmap, "ATGAC", 16, 1)
+    with pytest.raises(NoHitsError, match=r"^No hits were found!$"):           # lib/kmerFinderClient.js:161
+        Match(c, tdb)
+    # a match whose best template fails the evalue gate: zero rows -> the second error text
+    lists = {b"ATGACAAAAAAAAAAA": ["T1"]}
+    attrs = {"T1": {"lengths": 1000, "ulength": 100000, "species": "s"}}
+    summary = {"templates": 5000, "uniqueLens": 100000, "totalLen": 1000}
+    tdb = TemplateDB.from_lists(lists, attrs, summary)
+    e = oracle_rows(OrderedDict((k.encode(), v) for k, v in qmap.items()), lists, attrs, summary)
+    assert e[2] == [] and "kmerResults.length === 0" in e[3]
+    m = Match(c, tdb)
+    with pytest.raises(NoHitsError, match=r"kmerResults\.length === 0"):       # lib/kmerFinderClient.js:284
+        m.next_row()
+    m.free(); c.free()
+
+
+def test_max_hits_and_ties():
+    rng = random.Random(77)
+    keys = [bytes(b"ATGAC") + bytes(rng.choice(b"ACGT") for _ in range(11)) for _ in range(400)]
+    qmap = OrderedDict((k, rng.randint(1, 9)) for k in dict.fromkeys(keys))
+    lists, attrs, summary = synthetic_db(list(qmap.keys()), rng, n_templates=30, decoys=10, share=0.9)
+    tdb = TemplateDB.from_lists(lists, attrs, summary)
+    for max_hits in (1, 3, 100):
+        c = counts_from_map({k.decode(): v for k, v in qmap.items()}, "ATGAC", 16, 1)
+        e_first, e_hits, e_rows, e_err, _ = oracle_rows(qmap, lists, attrs, summary, max_hits)
+        g_first, g_hits, g_rows, g_err, m = gpu_rows(c, tdb, max_hits)
+        assert list(g_first) == list(e_first) and g_hits == e_hits
+        check_rows(g_rows, e_rows)
+        assert g_err == e_err and len(g_rows) <= max_hits
+        m.free(); c.free()
+
+
+def test_standard_scoring():
+    golden = json.loads(read_golden("test_long.json"))          # 6045-key sorted subset of the golden map
+    qmap = OrderedDict((k.encode("latin-1"), v) for k, v in golden.items())
+    rng = random.Random(9)
+    lists, attrs, summary = synthetic_db(list(qmap.keys()), rng, n_templates=25, decoys=100)
+    tdb = TemplateDB.from_lists(lists, attrs, summary)
+    c = counts_from_map(golden, "ATGAC", 16, 1)
+    m = Match(c, tdb)
+    got = m.standard_scoring()
+    # oracle: matchSummary of every first-match template, stable sort by score desc
+    # (lib/kmerFinderServer.js:857-874,684-693)
+    db = ko.TemplateDB(lists, attrs, summary)
+    templates, hits = ko.first_match(OrderedDict(qmap), db)
+    exp = []
+    for name, t in templates.items():
+        r = ko.match_summary(len(qmap), templates, name, t, hits, summary)
+        if r is not None:
+            exp.append(r)
+    exp.sort(key=lambda r: -r["score"])
+    check_rows(got, exp)
+    m.free(); c.free()
+
+
+def test_device_stats_match_exact_decimal(ctx):
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    n = 512
+    n1 = rng.integers(1, 2_000_000, n).astype(np.uint64)
+    r1 = (rng.random(n) * n1).astype(np.uint64)
+    n2 = rng.integers(1_000, 50_000_000, n).astype(np.uint64)
+    r2 = (rng.random(n) * np.minimum(n2, 500_000)).astype(np.uint64)
+    z = np.zeros(n); p = np.zeros(n)
+    _abi.check(_abi.lib().kj_stats_zscore_device(ctx.handle, n, r1.ctypes.data, n1.ctypes.data, r2.ctypes.data,
+                                                 n2.ctypes.data, z.ctypes.data, p.ctypes.data), ctx.handle)
+    for i in range(n):
+        ez = ko.z_score(int(r1[i]), int(n1[i]), int(r2[i]), int(n2[i]))
+        assert z[i] == pytest.approx(ez.toNumber(), rel=REL, abs=1e-12)
+        # the step function may only differ when z sits within the tolerance of a threshold
+        if all(abs(z[i] - thr) > 1e-6 for thr, _ in ko._FASTP_TABLE):
+            assert p[i] == ko.fastp(ez).toNumber()
+
+
+def test_exact_decimal_host_functions():
+    """kj_stats_zscore / kj_stats_fastp_text (host-only entry points) against the oracle's BN."""
+    rng = random.Random(1)
+    for mode in (4, 2, 6):
+        ko.BNConfig.rounding_mode = mode
+        kmerjs_b200.stats.set_rounding_mode(mode)
+        try:
+            for _ in range(60):
+                n1 = rng.randint(1, 10**6); r1 = rng.randint(0, n1)
+                n2 = rng.randint(1, 10**8); r2 = rng.randint(0, min(n2, 10**6))
+                ez = ko.z_score(r1, n1, r2, n2)
+                gz = kmerjs_b200.zScore(r1, n1, r2, n2)
+                assert gz == __import__("decimal").Decimal(ez.n).scaleb(-ez.e)
+                assert float(kmerjs_b200.fastp(gz)) == ko.fastp(ez).toNumber()
+        finally:
+            ko.BNConfig.rounding_mode = 4
+            kmerjs_b200.stats.set_rounding_mode(4)

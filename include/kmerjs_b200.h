@@ -52,7 +52,9 @@ enum {
     KJ_F_NO_ORDER = 1u << 0,     /* do not track first-seen ordinals (export order undefined) */
     KJ_F_FORCE_GENERIC = 1u << 1,/* use the line-oriented kernel even where the filter kernel applies (tests) */
     KJ_F_FORWARD_ONLY = 1u << 2, /* scan the line only, not complement(line): one KmerJS#kmersInLine call (lib/kmers.js:88-100) */
-    KJ_F_NO_LINE_GATE = 1u << 3  /* drop readFile's `line.length > 1` gate (lib/kmers.js:151); kmersInLine has none */
+    KJ_F_NO_LINE_GATE = 1u << 3, /* drop readFile's `line.length > 1` gate (lib/kmers.js:151); kmersInLine has none */
+    KJ_F_COUNT_BASES = 1u << 4   /* also sum the sequence-line lengths (kj_counts_bases); off by default: a statistic the
+                                    reference does not have, and it costs the scan kernel about 20 % */
 };
 
 typedef struct kj_ctx kj_ctx;
@@ -110,7 +112,7 @@ int kj_counts_finish(kj_counts *c);
 
 uint64_t kj_counts_size(const kj_counts *c);        /* kmerMapSize  lib/kmers.js:177 */
 uint64_t kj_counts_lines(const kj_counts *c);       /* KmerJS#lines lib/kmers.js:164-165 */
-uint64_t kj_counts_bases(const kj_counts *c);       /* sum of processed sequence-line lengths */
+uint64_t kj_counts_bases(const kj_counts *c);       /* sum of the lengths of the sequence lines (line index 1 mod 4); needs KJ_F_COUNT_BASES */
 uint64_t kj_counts_bytes_read(const kj_counts *c);  /* KmerJS#bytesRead lib/kmers.js:146 */
 uint64_t kj_counts_occurrences(const kj_counts *c); /* sum of all counts */
 /* Export in first-insertion order (the order of JS Map iteration / mapToJSON, lib/kmers.js:46-54).

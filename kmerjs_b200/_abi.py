@@ -14,7 +14,7 @@ KJ_OK = 0
 KJ_E_INVALID, KJ_E_NO_SM100, KJ_E_CUDA, KJ_E_NOMEM, KJ_E_IO = -1, -2, -3, -4, -5
 KJ_E_TABLE_FULL, KJ_E_NO_HITS, KJ_E_NO_WINNER, KJ_E_RANGE, KJ_E_STATE = -6, -7, -8, -9, -10
 KJ_MEM_HOST, KJ_MEM_DEVICE = 0, 1
-KJ_F_NO_ORDER, KJ_F_FORCE_GENERIC, KJ_F_FORWARD_ONLY, KJ_F_NO_LINE_GATE = 1, 2, 4, 8
+KJ_F_NO_ORDER, KJ_F_FORCE_GENERIC, KJ_F_FORWARD_ONLY, KJ_F_NO_LINE_GATE, KJ_F_COUNT_BASES = 1, 2, 4, 8, 16
 KJ_VEC_SCORES, KJ_VEC_FIRST_ORD, KJ_VEC_FIRST_IDX = 0, 1, 2
 KJ_ABI_VERSION = 1
 

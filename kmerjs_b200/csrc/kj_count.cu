@@ -320,8 +320,10 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
     if (rc) return rc;
     rc = grow_irr(c, std::max<uint64_t>(1ull << 12, 4 * c->h_ctr->n_irr_unique));
     if (rc) return rc;
-    rc = ensure_overflow(c, std::min<uint64_t>(hard_bound, std::max<uint64_t>(1ull << 16, expect)),
-                         std::min<uint64_t>(hard_bound, c->use_filter ? (1ull << 16) : expect));
+    // spill lists: the table is sized for the expected load, so spills are the exception; the line
+    // kernel (every window is an emission) gets the worst case of its 4 MiB pieces
+    rc = ensure_overflow(c, c->use_filter ? std::min<uint64_t>(hard_bound, 1ull << 20) : hard_bound,
+                         c->use_filter ? std::min<uint64_t>(hard_bound, 1ull << 16) : hard_bound);
     if (rc) return rc;
 
     // tile state
@@ -329,7 +331,7 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
         kj_dfree(ctx, c->tile_mem);
         c->tile_mem = nullptr; c->tile_cap = 0;
         uint64_t tc = std::max<uint64_t>(n_tiles, 4096);
-        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->tile_mem, tc * 3 * 8));
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->tile_mem, tc * 8));
         c->tile_cap = tc;
     }
     KJ_CUDA(ctx, cudaMemsetAsync(c->tile_mem, 0, (uint64_t)n_tiles * 8, ctx->stream));  // status only
@@ -341,6 +343,7 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
     a.k = c->k; a.step = c->step; a.m = m; a.order = c->order ? 1u : 0u;
     a.n_strands = (c->flags & KJ_F_FORWARD_ONLY) ? 1u : 2u;
     a.line_gate = (c->flags & KJ_F_NO_LINE_GATE) ? 0u : 1u;
+    a.count_bases = (c->flags & KJ_F_COUNT_BASES) ? 1u : 0u;
     a.mp = std::min<uint32_t>(m, KJ_MAX_MP);
     a.rc_shift = (m <= c->k) ? c->k - m : 0;
     for (uint32_t i = 0; i < a.mp; ++i) {
@@ -353,22 +356,26 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
         memcpy(a.rprefix, c->rprefix.data(), std::min<size_t>(32, m));
     }
     a.tab = c->tab; a.irr = c->irr; a.ovf = c->ovf; a.ctr = c->ctr;
-    a.ts.status = c->tile_mem;
-    a.ts.agg_last = c->tile_mem + c->tile_cap;
-    a.ts.inc_last = c->tile_mem + 2 * c->tile_cap;
+    a.status = c->tile_mem;
 
     void (*fn)(const KjScanArgs) = kj_scan_lines_kernel;
     if (c->use_filter) {
+        // where the filter symbols of complement(prefix) sit relative to the window start
+        const uint32_t d_lo = a.rc_shift, d_hi = a.rc_shift + a.mp - 1;
+        const int rc = d_hi < 16 ? KJ_RC_LOW : (d_lo >= 16 ? KJ_RC_HIGH : KJ_RC_MIXED);
+#define KJ_PICK(MP)                                                                          \
+    case MP:                                                                                 \
+        fn = rc == KJ_RC_LOW ? kj_scan_filter_kernel<MP, KJ_RC_LOW>                          \
+                             : rc == KJ_RC_HIGH ? kj_scan_filter_kernel<MP, KJ_RC_HIGH>      \
+                                                : kj_scan_filter_kernel<MP, KJ_RC_MIXED>;    \
+        break;
         switch (a.mp) {
-            case 1: fn = kj_scan_filter_kernel<1>; break;
-            case 2: fn = kj_scan_filter_kernel<2>; break;
-            case 3: fn = kj_scan_filter_kernel<3>; break;
-            case 4: fn = kj_scan_filter_kernel<4>; break;
-            case 5: fn = kj_scan_filter_kernel<5>; break;
-            case 6: fn = kj_scan_filter_kernel<6>; break;
-            case 7: fn = kj_scan_filter_kernel<7>; break;
-            default: fn = kj_scan_filter_kernel<8>; break;
+            KJ_PICK(1) KJ_PICK(2) KJ_PICK(3) KJ_PICK(4) KJ_PICK(5) KJ_PICK(6) KJ_PICK(7)
+            default: fn = rc == KJ_RC_LOW ? kj_scan_filter_kernel<8, KJ_RC_LOW>
+                                          : rc == KJ_RC_HIGH ? kj_scan_filter_kernel<8, KJ_RC_HIGH>
+                                                             : kj_scan_filter_kernel<8, KJ_RC_MIXED>;
         }
+#undef KJ_PICK
     }
     int occ = 0;
     KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KJ_THREADS, 0));
@@ -464,9 +471,13 @@ extern "C" int kj_counts_create(kj_ctx *ctx, const kj_count_params *p, kj_counts
                     !(p->flags & KJ_F_FORCE_GENERIC);
     c->capacity_hint = p->capacity_hint;
     c->voff = p->base_col;
+    c->base_line = p->base_line;
+    c->base_col = p->base_col;
     cudaError_t e = kj_dmalloc(ctx, &c->ctr, sizeof(KjCounters));
-    if (e == cudaSuccess) e = cudaMallocHost(&c->h_ctr, sizeof(KjCounters));
-    if (e != cudaSuccess) {
+    static_assert(sizeof(KjCounters) <= 512, "pinned block size");
+    if (e == cudaSuccess) c->h_ctr = (KjCounters *)kj_pinned_get(ctx);
+    if (e != cudaSuccess || !c->h_ctr) {
+        if (e == cudaSuccess) e = cudaErrorMemoryAllocation;
         kj_counts_free(c);
         return kj_fail(ctx, KJ_E_CUDA, std::string("kj_counts_create: ") + cudaGetErrorString(e));
     }
@@ -682,15 +693,18 @@ extern "C" int kj_counts_finish(kj_counts *c) {
     if (rc) return rc;
     if (c->h_ctr->n_compact != n_tab) return kj_fail(ctx, KJ_E_CUDA, "internal: compaction count mismatch");
     c->lines = c->h_ctr->carry_lines[c->parity];
-    c->bases = c->h_ctr->n_bases;
-    // a non-empty unterminated tail is one more line (lib/kmers.js:130-136)
-    const uint64_t tail_start = c->h_ctr->carry_last[c->parity];
-    if (c->consumed && tail_start != c->voff) {
-        const uint64_t tail_len = c->voff - tail_start;
-        // the filter kernel counts a sequence line when it meets its '\n'; the line kernel when it starts
-        if (c->use_filter && (c->lines & 3ull) == 1ull && tail_len > 1) c->bases += tail_len;
-        c->lines += 1;
+    // sum of the sequence-line lengths (lines with index 1 mod 4).  The filter kernel accumulates
+    // signed newline offsets that telescope; the two ends of this handle's byte range close the sum:
+    // a range that starts inside a sequence line does not own the bytes before it, a range that ends
+    // inside one (unterminated last line, or a shard cut) owns the bytes up to its end.
+    long long bases = (long long)c->h_ctr->n_bases;
+    if (c->use_filter && c->consumed && (c->flags & KJ_F_COUNT_BASES)) {
+        if ((c->base_line & 3ull) == 1ull) bases -= (long long)c->base_col;
+        if ((c->lines & 3ull) == 1ull) bases += (long long)c->voff;
     }
+    c->bases = (c->flags & KJ_F_COUNT_BASES) ? (uint64_t)bases : 0;
+    // a non-empty unterminated tail is one more line (lib/kmers.js:130-136)
+    if (c->consumed && c->h_ctr->carry_last[c->parity] != c->voff) c->lines += 1;
     c->occurrences = c->h_ctr->n_occ;
     c->finished = true;
     return KJ_OK;
@@ -807,7 +821,7 @@ extern "C" void kj_counts_free(kj_counts *c) {
         free_irr(ctx, c->irr);
         kj_dfree(ctx, c->ovf.rec); kj_dfree(ctx, c->ovf.irr_rec);
         kj_dfree(ctx, c->ctr);
-        if (c->h_ctr) cudaFreeHost(c->h_ctr);
+        kj_pinned_put(ctx, c->h_ctr);
         kj_dfree(ctx, c->tile_mem);
         drop_compact(c);
         kj_dfree(ctx, c->part_rec);

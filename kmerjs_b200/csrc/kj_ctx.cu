@@ -9,6 +9,32 @@ int kj_fail(kj_ctx *ctx, int code, const std::string &msg) {
     return code;
 }
 
+static const size_t KJ_PIN_BLOCK = 512, KJ_PIN_BLOCKS = 256;
+
+void *kj_pinned_get(kj_ctx *ctx) {
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (!ctx->pin_slab) {
+        if (cudaMallocHost(&ctx->pin_slab, KJ_PIN_BLOCK * KJ_PIN_BLOCKS) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        for (size_t i = 0; i < KJ_PIN_BLOCKS; ++i) ctx->pin_free.push_back(ctx->pin_slab + i * KJ_PIN_BLOCK);
+    }
+    if (ctx->pin_free.empty()) {          // more live handles than blocks: a block of its own
+        void *p = nullptr;
+        if (cudaMallocHost(&p, KJ_PIN_BLOCK) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return p;
+    }
+    void *p = ctx->pin_free.back();
+    ctx->pin_free.pop_back();
+    return p;
+}
+
+void kj_pinned_put(kj_ctx *ctx, void *p) {
+    if (!p) return;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    uint8_t *q = (uint8_t *)p;
+    if (ctx->pin_slab && q >= ctx->pin_slab && q < ctx->pin_slab + KJ_PIN_BLOCK * KJ_PIN_BLOCKS) ctx->pin_free.push_back(p);
+    else cudaFreeHost(p);
+}
+
 extern "C" int kj_abi_version(void) { return KJ_ABI_VERSION; }
 
 extern "C" int kj_init(int device, void *stream, kj_ctx **out) {
@@ -68,6 +94,7 @@ extern "C" void kj_destroy(kj_ctx *ctx) {
         if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
     }
+    if (ctx->pin_slab) cudaFreeHost(ctx->pin_slab);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -39,7 +39,14 @@ struct kj_ctx {
     uint8_t *h_stage[2] = {nullptr, nullptr};
     uint64_t stage_cap = 0;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    // small pinned blocks (device counters mirrored to the host, WTA results): cudaMallocHost costs
+    // milliseconds, so handles borrow 512-byte blocks from a slab owned by the context
+    uint8_t *pin_slab = nullptr;
+    std::vector<void *> pin_free;
 };
+
+void *kj_pinned_get(kj_ctx *ctx);              // 512 bytes, nullptr when out of memory
+void kj_pinned_put(kj_ctx *ctx, void *p);
 
 // stream-ordered device memory from the default pool (release threshold = keep everything), so
 // that per-job tables are recycled without cudaMalloc/cudaFree round trips
@@ -83,6 +90,7 @@ struct kj_counts {
     uint64_t capacity_hint = 0;
     // stream position
     uint64_t voff = 0;           // virtual offset of the next byte (starts at base_col)
+    uint64_t base_line = 0, base_col = 0;
     uint64_t consumed = 0;       // stream bytes consumed
     uint32_t parity = 0;
     bool finished = false;

@@ -4,10 +4,10 @@
 //
 //   P1  coalesced 16-byte loads -> per 16-byte chunk: a 32-bit word of 2-bit base codes and a
 //       16-bit newline mask, both kept in shared memory (the raw bytes are never staged);
-//       per-tile newline count and last-newline position.
+//       newline counts per 512-byte row (one warp-wide load) and per tile.
 //   LB  decoupled look-back over tiles (dynamic tile tickets) gives every tile the number of
 //       '\n' before it -- the reference's record FSM is "line index mod 4" (lib/kmers.js:151-163),
-//       which is global state -- and the position of the last '\n' (column of a window).
+//       which is global state.
 //   P2  (filter kernel) bit-parallel search of the prefix and of complement(prefix) in code
 //       space, 16 window positions per 32-bit operation.  Codes are a function of the byte, so
 //       this is an exact superset filter; candidates go to a shared-memory queue.
@@ -25,7 +25,7 @@
 #define KJ_THREADS 256
 #define KJ_TILE_CHUNKS (KJ_TILE_BYTES / 16)              // 2048 16-byte chunks
 #define KJ_CPT (KJ_TILE_CHUNKS / KJ_THREADS)             // 8 chunks per thread
-#define KJ_ROWS (KJ_TILE_CHUNKS / 32)                    // 64 rows of 512 bytes
+#define KJ_ROWS (KJ_TILE_CHUNKS / 32)                    // 64 rows of 512 bytes (one warp-wide load)
 #define KJ_QCAP 1536                                     // candidate / line queue entries
 #define KJ_MAX_MP 8                                      // filter symbols used in code space
 
@@ -33,11 +33,10 @@
 #define KJ_ST_INC 2ull
 #define KJ_ST_MASK 0x3FFFFFFFFFFFFFFFull
 
-struct KjTileState {      // SoA, n_tiles entries each; zeroed before every launch
-    uint64_t *status;     // flag << 62 | newline count
-    uint64_t *agg_last;   // virtual offset + 1 of the last '\n' inside the tile (0 = none)
-    uint64_t *inc_last;   // same, over the whole stream up to the end of the tile
-};
+// where complement(prefix) sits inside the 48 code lanes a chunk looks at (c0,c1,c2)
+#define KJ_RC_LOW 0      // every filter symbol within 16 lanes of the window start: (c0,c1)
+#define KJ_RC_HIGH 1     // every one at 16 or more: (c1,c2)
+#define KJ_RC_MIXED 2
 
 struct KjScanArgs {
     const uint8_t *buf;   // 16-byte aligned
@@ -51,6 +50,7 @@ struct KjScanArgs {
     uint32_t order;       // track first-seen ordinals
     uint32_t n_strands;   // 2, or 1 with KJ_F_FORWARD_ONLY
     uint32_t line_gate;   // 1: lines of length <= 1 are not processed (lib/kmers.js:151)
+    uint32_t count_bases; // KJ_F_COUNT_BASES
     uint32_t mp;          // number of filter symbols (<= min(m, KJ_MAX_MP))
     uint32_t rc_shift;    // k - m: lane offset of complement(prefix) inside a window
     uint32_t pat_f[KJ_MAX_MP];   // code of prefix[i] replicated to all 16 lanes
@@ -60,7 +60,7 @@ struct KjScanArgs {
     KjTable tab;
     KjIrrTable irr;
     KjOverflow ovf;
-    KjTileState ts;
+    uint64_t *status;     // per tile: flag << 62 | newline count; zeroed before every launch
     KjCounters *ctr;
 };
 
@@ -88,185 +88,174 @@ __device__ __forceinline__ uint4 kj_load_chunk(const uint8_t *buf, uint64_t off,
 
 struct KjTileSmem {
     uint32_t codes[KJ_TILE_CHUNKS + 2];   // +2 halo words: windows reach k-1 bytes past the tile
-    uint16_t nl[KJ_TILE_CHUNKS];
-    uint32_t row_pre[KJ_ROWS];            // row counts, then exclusive prefix
+    uint16_t nl[KJ_TILE_CHUNKS];          // '\n' mask of the chunk
+    uint32_t row_pre[KJ_ROWS];            // row counts, then exclusive prefix over the tile
     uint32_t queue[KJ_QCAP];
     uint32_t q_n;
-    uint32_t tile;
+    uint32_t tile;                        // ticket of the tile being processed
+    uint32_t tile_next;                   // ticket fetched ahead for the next round
     uint32_t tile_count;                  // '\n' in the tile
-    uint32_t tile_last_p1;                // tile-relative position + 1 of the last '\n' (0 none)
     unsigned long long excl_count;        // '\n' before the tile (whole stream)
-    unsigned long long excl_last;         // virtual offset + 1 of the last '\n' before the tile
 };
 
-// number of '\n' in the tile strictly before tile-relative position jt (jt <= KJ_TILE_BYTES)
+// number of '\n' in the tile strictly before tile-relative position jt (jt <= KJ_TILE_BYTES).
+// Only the rare consumers (candidates, line starts) need it, so the prefix inside the 32-chunk row
+// is summed on demand instead of being scanned for every chunk in P1.
 __device__ __forceinline__ uint32_t kj_count_before(const KjTileSmem &s, uint32_t jt) {
-    uint32_t row = jt >> 9;
-    uint32_t c = jt >> 4;
-    uint32_t cnt = (row < KJ_ROWS) ? s.row_pre[row] : s.tile_count;
-    if (row >= KJ_ROWS) return cnt;
-    for (uint32_t i = row * 32; i < c; ++i) cnt += __popc((uint32_t)s.nl[i]);
-    cnt += __popc((uint32_t)s.nl[c] & ((1u << (jt & 15)) - 1u));
+    const uint32_t c = jt >> 4;
+    if (c >= KJ_TILE_CHUNKS) return s.tile_count;
+    uint32_t cnt = s.row_pre[c >> 5] + __popc((uint32_t)s.nl[c] & ((1u << (jt & 15)) - 1u));
+    for (uint32_t i = c & ~31u; i < c; ++i) cnt += __popc((uint32_t)s.nl[i]);
     return cnt;
 }
 
-// virtual offset + 1 of the last '\n' strictly before tile-relative jt (0 = none in the stream)
-__device__ __forceinline__ unsigned long long kj_last_nl_before(const KjTileSmem &s, uint32_t jt,
-                                                                uint64_t tile_voff) {
+// virtual offset of the first byte of the line that holds buffer position p (= offset + 1 of the
+// last '\n' in [0, p)), searched backwards in global memory; falls back to the stream carry
+static __device__ __noinline__ unsigned long long kj_line_start_global(const KjScanArgs &a, uint64_t p) {
+    while (p > 0) {
+        const uint64_t b = (p - 1) & ~15ull;
+        const uint4 v = kj_load_chunk(a.buf, b, a.n);
+        uint32_t m = kj_nl16(v.x, v.y, v.z, v.w);
+        if (p - b < 16) m &= (1u << (uint32_t)(p - b)) - 1u;
+        if (m) return a.voff + b + (31u - __clz(m)) + 1ull;
+        p = b;
+    }
+    return a.ctr->carry_last[a.parity];
+}
+
+// same for tile-relative position jt, first in the tile's newline masks
+__device__ __forceinline__ unsigned long long kj_line_start(const KjScanArgs &a, const KjTileSmem &s, uint32_t jt,
+                                                            uint64_t tile_off, uint64_t tile_voff) {
     int c = (int)(jt >> 4);
     uint32_t m = (c < KJ_TILE_CHUNKS) ? ((uint32_t)s.nl[c] & ((1u << (jt & 15)) - 1u)) : 0u;
-    if (c >= KJ_TILE_CHUNKS) c = KJ_TILE_CHUNKS;   // jt == tile end
+    if (c >= KJ_TILE_CHUNKS) c = KJ_TILE_CHUNKS;
     while (m == 0 && c > 0) { --c; m = s.nl[c]; }
-    if (m == 0) return s.excl_last;
-    uint32_t pos = (uint32_t)c * 16u + (31u - __clz(m));
-    return tile_voff + pos + 1ull;
+    if (m) return tile_voff + (uint32_t)c * 16u + (31u - __clz(m)) + 1ull;
+    return kj_line_start_global(a, tile_off);
 }
 
 // ----------------------------------------------------------------------------- P1 + look-back
 
-// Fills codes / nl / row_pre / tile_count / tile_last_p1 for tile `tile`.  Ends with a barrier.
+// Fills codes / nlp / row_pre / tile_count for tile `tile`.  INTERIOR: the tile and its 32-byte
+// code halo lie inside the owned range, no per-chunk bounds work.  Ends with a barrier.
+template <bool INTERIOR>
 __device__ __forceinline__ void kj_tile_p1(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
-    uint4 v[KJ_CPT];
+    const uint8_t *tbase = a.buf + tile_off;
 #pragma unroll
-    for (int it = 0; it < KJ_CPT; ++it) {
-        uint64_t off = tile_off + (uint64_t)(it * KJ_THREADS + tid) * 16u;
-        v[it] = (off < a.n) ? kj_load_chunk(a.buf, off, a.n) : make_uint4(0, 0, 0, 0);
-    }
+    for (int half = 0; half < 2; ++half) {
+        uint4 v[KJ_CPT / 2];
 #pragma unroll
-    for (int it = 0; it < KJ_CPT; ++it) {
-        uint32_t c = it * KJ_THREADS + tid;
-        uint64_t off = tile_off + (uint64_t)c * 16u;
-        s.codes[c] = kj_pack16(v[it].x, v[it].y, v[it].z, v[it].w);
-        uint32_t nl = kj_nl16(v[it].x, v[it].y, v[it].z, v[it].w);
-        // newlines are counted only inside the owned range
-        if (off >= a.own_n) nl = 0;
-        else if (off + 16 > a.own_n) nl &= (1u << (uint32_t)(a.own_n - off)) - 1u;
-        s.nl[c] = (uint16_t)nl;
-        uint32_t rc = __reduce_add_sync(0xFFFFFFFFu, __popc(nl));
-        if (lane == 0) s.row_pre[it * (KJ_THREADS / 32) + warp] = rc;
+        for (int j = 0; j < KJ_CPT / 2; ++j) {
+            const uint32_t c = (half * (KJ_CPT / 2) + j) * KJ_THREADS + tid;
+            if (INTERIOR) {
+                v[j] = kj_ldg16(tbase + c * 16u);
+            } else {
+                const uint64_t off = tile_off + (uint64_t)c * 16u;
+                v[j] = (off < a.n) ? kj_load_chunk(a.buf, off, a.n) : make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KJ_CPT / 2; ++j) {
+            const int it = half * (KJ_CPT / 2) + j;
+            const uint32_t c = it * KJ_THREADS + tid;
+            s.codes[c] = kj_pack16(v[j].x, v[j].y, v[j].z, v[j].w);
+            uint32_t nl = kj_nl16(v[j].x, v[j].y, v[j].z, v[j].w);
+            if (!INTERIOR) {   // newlines are counted only inside the owned range
+                const uint64_t off = tile_off + (uint64_t)c * 16u;
+                if (off >= a.own_n) nl = 0;
+                else if (off + 16 > a.own_n) nl &= (1u << (uint32_t)(a.own_n - off)) - 1u;
+            }
+            s.nl[c] = (uint16_t)nl;
+            const uint32_t rc = __reduce_add_sync(0xFFFFFFFFu, __popc(nl));
+            if (lane == 0) s.row_pre[it * (KJ_THREADS / 32) + warp] = rc;       // row = chunk >> 5
+        }
     }
     if (tid < 2) {   // halo code words
-        uint64_t off = tile_off + (uint64_t)(KJ_TILE_CHUNKS + tid) * 16u;
-        uint4 h = (off < a.n) ? kj_load_chunk(a.buf, off, a.n) : make_uint4(0, 0, 0, 0);
+        const uint64_t off = tile_off + (uint64_t)(KJ_TILE_CHUNKS + tid) * 16u;
+        const uint4 h = (off < a.n) ? kj_load_chunk(a.buf, off, a.n) : make_uint4(0, 0, 0, 0);
         s.codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
     }
     __syncthreads();
     if (warp == 0) {
-        // exclusive scan of the 64 row counts, 2 per lane
-        uint32_t c0 = s.row_pre[2 * lane], c1 = s.row_pre[2 * lane + 1];
-        uint32_t sum = c0 + c1, incl = sum;
+        // exclusive scan of the 64 row counts, 2 per lane; the tile's aggregate is published at once
+        const uint32_t c0 = s.row_pre[2 * lane], c1 = s.row_pre[2 * lane + 1];
+        const uint32_t sum = c0 + c1;
+        uint32_t incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if ((int)lane >= d) incl += o;
         }
-        uint32_t excl = incl - sum;
+        const uint32_t excl = incl - sum;
         s.row_pre[2 * lane] = excl;
         s.row_pre[2 * lane + 1] = excl + c0;
-        uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        // last newline: highest non-empty row, then highest non-empty chunk in it
-        uint32_t rows_hi = __ballot_sync(0xFFFFFFFFu, c1 != 0);
-        uint32_t rows_lo = __ballot_sync(0xFFFFFFFFu, c0 != 0);
-        uint32_t last_p1 = 0;
-        if (total) {
-            int hl = rows_hi ? 31 - __clz(rows_hi) : -1;
-            int ll = rows_lo ? 31 - __clz(rows_lo) : -1;
-            int row = (hl >= ll) ? 2 * hl + 1 : 2 * ll;     // hl == ll -> the odd row is later
-            uint32_t mk = s.nl[row * 32 + lane];
-            uint32_t chunks = __ballot_sync(0xFFFFFFFFu, mk != 0);
-            int cl = 31 - __clz(chunks);
-            uint32_t mm = __shfl_sync(0xFFFFFFFFu, mk, cl);
-            last_p1 = (uint32_t)(row * 32 + cl) * 16u + (31u - __clz(mm)) + 1u;
+        if (lane == 31) {
+            s.tile_count = incl;
+            *reinterpret_cast<volatile uint64_t *>(&a.status[tile]) = (KJ_ST_AGG << 62) | (uint64_t)incl;
         }
-        if (lane == 0) { s.tile_count = total; s.tile_last_p1 = last_p1; }
     }
     __syncthreads();
 }
 
-// Publish this tile's aggregate (thread 0).  Tile 0's predecessor is the stream carry.
-__device__ __forceinline__ void kj_publish_aggregate(const KjScanArgs &a, const KjTileSmem &s,
-                                                     uint32_t tile, uint64_t tile_voff) {
-    if (threadIdx.x == 0) {
-        a.ts.agg_last[tile] = s.tile_last_p1 ? tile_voff + s.tile_last_p1 : 0ull;
-        __threadfence();
-        *reinterpret_cast<volatile uint64_t *>(&a.ts.status[tile]) =
-            (KJ_ST_AGG << 62) | (uint64_t)s.tile_count;
-    }
-}
-
-// Warp 0: decoupled look-back.  Writes excl_count/excl_last, publishes the inclusive state and,
-// for the last tile, the stream carry of the next launch.
-__device__ __forceinline__ void kj_lookback(const KjScanArgs &a, KjTileSmem &s, uint32_t tile,
-                                            uint64_t tile_voff) {
+// Warp 0: decoupled look-back.  Writes excl_count, publishes the inclusive state and, for the last
+// tile, the stream carry of the next launch.
+__device__ __forceinline__ void kj_lookback(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
     const uint32_t lane = threadIdx.x & 31;
-    unsigned long long ex_count = 0, ex_last = 0;
+    unsigned long long ex_count = 0;
     int base = (int)tile - 1;
     bool done = false;
     while (!done) {
-        int idx = base - (int)lane;          // idx == -1 is the stream carry, below that: nothing
-        uint64_t st = 0, last = 0;
+        const int idx = base - (int)lane;    // idx == -1 is the stream carry, below that: nothing
+        uint64_t st;
         if (idx >= 0) {
             do {
-                st = kj_ld_volatile(&a.ts.status[idx]);
+                st = kj_ld_volatile(&a.status[idx]);
             } while ((st >> 62) == 0);
-            __threadfence();
-            last = ((st >> 62) == KJ_ST_INC) ? kj_ld_volatile(&a.ts.inc_last[idx])
-                                             : kj_ld_volatile(&a.ts.agg_last[idx]);
         } else if (idx == -1) {
             st = (KJ_ST_INC << 62) | (uint64_t)a.ctr->carry_lines[a.parity];
-            last = a.ctr->carry_last[a.parity];
         } else {
             st = (KJ_ST_AGG << 62);          // neutral element
         }
-        uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (st >> 62) == KJ_ST_INC);
-        uint32_t upto = inc_mask ? (uint32_t)(__ffs(inc_mask) - 1) : 31u;   // lanes <= upto count
+        const uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (st >> 62) == KJ_ST_INC);
+        const uint32_t upto = inc_mask ? (uint32_t)(__ffs(inc_mask) - 1) : 31u;   // lanes <= upto count
         unsigned long long cnt = (lane <= upto) ? (st & KJ_ST_MASK) : 0ull;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
         ex_count += cnt;
-        uint32_t has_last = __ballot_sync(0xFFFFFFFFu, lane <= upto && last != 0);
-        if (ex_last == 0 && has_last) {
-            int src = __ffs(has_last) - 1;    // nearest predecessor that contains a '\n'
-            ex_last = __shfl_sync(0xFFFFFFFFu, last, src);
-        } else {
-            (void)__shfl_sync(0xFFFFFFFFu, last, 0);
-        }
         if (inc_mask) done = true; else base -= 32;
     }
     if (lane == 0) {
         s.excl_count = ex_count;
-        s.excl_last = ex_last;
-        unsigned long long inc_count = ex_count + s.tile_count;
-        unsigned long long inc_last = s.tile_last_p1 ? tile_voff + s.tile_last_p1 : ex_last;
-        a.ts.inc_last[tile] = inc_last;
-        __threadfence();
-        *reinterpret_cast<volatile uint64_t *>(&a.ts.status[tile]) = (KJ_ST_INC << 62) | inc_count;
+        const unsigned long long inc_count = ex_count + s.tile_count;
+        *reinterpret_cast<volatile uint64_t *>(&a.status[tile]) = (KJ_ST_INC << 62) | inc_count;
         if (tile == a.n_tiles - 1) {
             a.ctr->carry_lines[a.parity ^ 1] = inc_count;
-            a.ctr->carry_last[a.parity ^ 1] = inc_last;
+            a.ctr->carry_last[a.parity ^ 1] = kj_line_start_global(a, a.own_n);
         }
     }
 }
 
-// Sum of the lengths of the processed sequence lines (line index mod 4 == 1, length > 1,
-// lib/kmers.js:151) that END with a '\n' of this tile.  Called by all threads after the look-back.
-__device__ __forceinline__ unsigned long long kj_tile_bases(const KjTileSmem &s, uint64_t tile_voff) {
-    unsigned long long sum = 0;
+// Contribution of this tile's '\n' to the sum of sequence-line lengths (lines with index 1 mod 4):
+// a '\n' that ends such a line adds its offset, one that ends the line before (index 0 mod 4)
+// subtracts offset + 1.  The sums telescope over tiles and launches; the host adds the two ends
+// of the stream (kj_counts_finish).  Optional (KJ_F_COUNT_BASES): it is a statistic the reference
+// does not have, and it costs about as much as the prefix search itself.
+__device__ __forceinline__ long long kj_tile_bases(const KjTileSmem &s, uint64_t tile_voff) {
+    long long sum = 0;
 #pragma unroll 1
     for (int it = 0; it < KJ_CPT; ++it) {
         const uint32_t c = it * KJ_THREADS + threadIdx.x;
         uint32_t mk = s.nl[c];
         if (!mk) continue;
-        unsigned long long line = s.excl_count + kj_count_before(s, c * 16u);   // line ended by the first '\n' of the chunk
+        uint32_t line = (uint32_t)s.excl_count + kj_count_before(s, c * 16u);    // mod 4 is all that matters
+        const long long at = (long long)(tile_voff + (uint64_t)c * 16u);
         while (mk) {
-            uint32_t bit = __ffs(mk) - 1; mk &= mk - 1;
-            if ((line & 3ull) == 1ull) {
-                uint32_t e = c * 16u + bit;
-                unsigned long long len = tile_voff + e - kj_last_nl_before(s, e, tile_voff);
-                if (len > 1) sum += len;
-            }
+            const uint32_t bit = __ffs(mk) - 1; mk &= mk - 1;
+            const uint32_t ph = line & 3u;
+            if (ph == 1u) sum += at + bit;
+            else if (ph == 0u) sum -= at + bit + 1;
             ++line;
         }
     }
@@ -300,7 +289,7 @@ __device__ __forceinline__ void kj_window_bytes(const uint8_t *buf, uint64_t off
 }
 
 static __device__ __noinline__ void kj_emit_irregular(const KjScanArgs &a, uint64_t off, uint32_t len,
-                                               uint32_t strand, uint64_t ord) {
+                                                      uint32_t strand, uint64_t ord) {
     __align__(8) uint8_t key32[32];
     kj_window_bytes(a.buf, off, len, strand, key32);
     if (!kj_insert_irr(a.irr, a.ctr, key32, len, ord, 1)) kj_spill_irr(a, off, len, strand, ord);
@@ -316,36 +305,48 @@ __device__ __forceinline__ void kj_verify_candidate(const KjScanArgs &a, const K
     if (j + k > a.n) return;                              // window must lie inside the stream
     const uint64_t line = s.excl_count + kj_count_before(s, jt);
     if ((line & 3ull) != 1ull) return;                    // lib/kmers.js:151  i === 1
+    // the window's bytes: at most three aligned 16-byte chunks, fetched together (they were read
+    // a moment ago, so these are L2 hits) instead of k dependent byte loads
+    const uint32_t o = (uint32_t)(j & 15u);
+    const uint64_t base = j - o;
+    uint32_t w[12];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (base + 16u * t < j + k) v = kj_load_chunk(a.buf, base + 16u * t, a.n);
+        w[4 * t] = v.x; w[4 * t + 1] = v.y; w[4 * t + 2] = v.z; w[4 * t + 3] = v.w;
+    }
     uint64_t fk = 0, rk = 0;
     bool regular = true;
     const uint32_t rc0 = k - m;
     for (uint32_t i = 0; i < k; ++i) {
-        uint32_t c = a.buf[j + i];
+        const uint32_t p = o + i;
+        const uint32_t c = (w[p >> 2] >> (8u * (p & 3u))) & 0xFFu;
         if (c == '\n') return;                            // window crosses the end of the line
         if (strand == 0) { if (i < m && c != a.prefix[i]) return; }
         else             { if (i >= rc0 && c != a.rprefix[i - rc0]) return; }
         regular = regular && kj_is_acgt(c);
-        uint64_t code = (c >> 1) & 3u;
+        const uint64_t code = (c >> 1) & 3u;
         fk = (fk << 2) | code;
         rk = (rk >> 2) | ((code ^ 2ull) << (2 * (k - 1)));
     }
     uint64_t ord = 0;
     if (a.order || k == 1) {
-        unsigned long long last_p1 = kj_last_nl_before(s, jt, tile_voff);
-        uint64_t col = tile_voff + jt - last_p1;
+        const unsigned long long start = kj_line_start(a, s, jt, tile_off, tile_voff);
+        const uint64_t col = tile_voff + jt - start;
         if (k == 1 && col == 0 && a.line_gate) {          // lib/kmers.js:151  line.length > 1
-            bool more = (j + 1 < a.n) && a.buf[j + 1] != '\n';
+            const bool more = (j + 1 < a.n) && a.buf[j + 1] != '\n';
             if (!more) return;
         }
         if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); return; }
-        uint64_t read_idx = line >> 2;
+        const uint64_t read_idx = line >> 2;
         if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); return; }
         // forward emissions in ascending column, then reverse emissions in descending column
         ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
     }
     ++n_emit;
     if (regular) {
-        uint64_t key = strand ? rk : fk;
+        const uint64_t key = strand ? rk : fk;
         if (!kj_insert(a.tab, a.ctr, key, ord, 1)) kj_spill(a, key, ord);
     } else {
         kj_emit_irregular(a, j, k, strand, ord);
@@ -354,24 +355,50 @@ __device__ __forceinline__ void kj_verify_candidate(const KjScanArgs &a, const K
 
 // ----------------------------------------------------------------------------- filter kernel
 
-template <int MP>
+// 16 code lanes holding symbol i of complement(prefix) for the 16 windows of a chunk
+template <int RC>
+__device__ __forceinline__ uint32_t kj_rc_lanes(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t d) {
+    if (RC == KJ_RC_LOW) return kj_funnel_r(c0, c1, 2u * d);
+    if (RC == KJ_RC_HIGH) return kj_funnel_r(c1, c2, 2u * (d - 16u));
+    return kj_lanes(c0, c1, c2, d);
+}
+
+// candidate lanes (bit 2p set: window at chunk position p passes the code-space filter)
+template <int MP, int RC>
+__device__ __forceinline__ void kj_chunk_filter(const KjScanArgs &a, const KjTileSmem &s, uint32_t c,
+                                                uint32_t &zf, uint32_t &zr) {
+    const uint32_t c0 = s.codes[c], c1 = s.codes[c + 1], c2 = s.codes[c + 2];
+    uint32_t accf = 0, accr = 0;
+#pragma unroll
+    for (int i = 0; i < MP; ++i) {
+        accf |= kj_funnel_r(c0, c1, 2u * i) ^ a.pat_f[i];
+        accr |= kj_rc_lanes<RC>(c0, c1, c2, a.rc_shift + i) ^ a.pat_r[i];
+    }
+    zf = kj_zero_lanes(accf);
+    zr = a.n_strands > 1 ? kj_zero_lanes(accr) : 0u;
+}
+
+template <int MP, int RC>
 __global__ void __launch_bounds__(KJ_THREADS)
 kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ KjTileSmem s;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     uint32_t n_emit = 0;
-    unsigned long long n_bases = 0;
+    long long n_bases = 0;
+    if (tid == 0) s.tile_next = atomicAdd(&a.ctr->ticket, 1u);
     for (;;) {
-        __syncthreads();
-        if (tid == 0) { s.tile = atomicAdd(&a.ctr->ticket, 1u); s.q_n = 0; }
-        __syncthreads();
-        const uint32_t tile = s.tile;
+        __syncthreads();                                   // previous tile fully consumed; ticket visible
+        const uint32_t tile = s.tile_next;
         if (tile >= a.n_tiles) break;
         const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
         const uint64_t tile_voff = a.voff + tile_off;
+        const bool interior = tile_off + KJ_TILE_BYTES + 32u <= a.own_n;
+        if (tid == 0) s.q_n = 0;
 
-        kj_tile_p1(a, s, tile);
-        kj_publish_aggregate(a, s, tile, tile_voff);
+        if (interior) kj_tile_p1<true>(a, s, tile); else kj_tile_p1<false>(a, s, tile);
+
+        // the scan state of this tile goes out first: later tiles wait on it
+        if (warp == 0) kj_lookback(a, s, tile);
 
         // P2: bit-parallel prefix search in code space
         const uint32_t own_in_tile =
@@ -381,39 +408,32 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
             const uint32_t c = it * KJ_THREADS + tid;
             const uint32_t pos0 = c * 16u;
             if (pos0 >= own_in_tile) continue;
-            const uint32_t c0 = s.codes[c], c1 = s.codes[c + 1], c2 = s.codes[c + 2];
-            uint32_t accf = 0, accr = 0;
-#pragma unroll
-            for (int i = 0; i < MP; ++i) {
-                accf |= kj_funnel_r(c0, c1, 2u * i) ^ a.pat_f[i];
-                accr |= kj_lanes(c0, c1, c2, a.rc_shift + i) ^ a.pat_r[i];
-            }
-            uint32_t zf = kj_zero_lanes(accf), zr = a.n_strands > 1 ? kj_zero_lanes(accr) : 0u;
+            uint32_t zf, zr;
+            kj_chunk_filter<MP, RC>(a, s, c, zf, zr);
             if (own_in_tile - pos0 < 16u) {
-                uint32_t keep = (1u << (2u * (own_in_tile - pos0))) - 1u;
+                const uint32_t keep = (1u << (2u * (own_in_tile - pos0))) - 1u;
                 zf &= keep; zr &= keep;
             }
             while (zf | zr) {
-                uint32_t strand = zf ? 0u : 1u;
+                const uint32_t strand = zf ? 0u : 1u;
                 uint32_t &z = zf ? zf : zr;
-                uint32_t bit = __ffs(z) - 1;
+                const uint32_t bit = __ffs(z) - 1;
                 z &= z - 1;
-                uint32_t jt = pos0 + (bit >> 1);
-                uint32_t q = atomicAdd(&s.q_n, 1u);
+                const uint32_t jt = pos0 + (bit >> 1);
+                const uint32_t q = atomicAdd(&s.q_n, 1u);
                 if (q < KJ_QCAP) s.queue[q] = (jt << 1) | strand;
-                else s.queue[KJ_QCAP - 1] = 0xFFFFFFFFu;   // overflow marker, handled below
             }
         }
-        if (warp == 0) kj_lookback(a, s, tile, tile_voff);
         __syncthreads();
 
-        n_bases += kj_tile_bases(s, tile_voff);
+        if (a.count_bases) n_bases += kj_tile_bases(s, tile_voff);
 
-        // P3: verify + insert
+        // P3: verify + insert.  Candidates sit densely in the first warps: the kernel is bound by
+        // instruction issue, and a warp with one busy lane costs as much as a full one.
         const uint32_t qn = s.q_n;
         if (qn <= KJ_QCAP) {
             for (uint32_t q = tid; q < qn; q += KJ_THREADS) {
-                uint32_t e = s.queue[q];
+                const uint32_t e = s.queue[q];
                 kj_verify_candidate(a, s, tile_off, tile_voff, e >> 1, e & 1u, n_emit);
             }
         } else {
@@ -422,32 +442,36 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                 const uint32_t c = it * KJ_THREADS + tid;
                 const uint32_t pos0 = c * 16u;
                 if (pos0 >= own_in_tile) continue;
-                const uint32_t c0 = s.codes[c], c1 = s.codes[c + 1], c2 = s.codes[c + 2];
-                uint32_t accf = 0, accr = 0;
-#pragma unroll
-                for (int i = 0; i < MP; ++i) {
-                    accf |= kj_funnel_r(c0, c1, 2u * i) ^ a.pat_f[i];
-                    accr |= kj_lanes(c0, c1, c2, a.rc_shift + i) ^ a.pat_r[i];
-                }
-                uint32_t zf = kj_zero_lanes(accf), zr = a.n_strands > 1 ? kj_zero_lanes(accr) : 0u;
+                uint32_t zf, zr;
+                kj_chunk_filter<MP, RC>(a, s, c, zf, zr);
                 if (own_in_tile - pos0 < 16u) {
-                    uint32_t keep = (1u << (2u * (own_in_tile - pos0))) - 1u;
+                    const uint32_t keep = (1u << (2u * (own_in_tile - pos0))) - 1u;
                     zf &= keep; zr &= keep;
                 }
                 // insertion order inside a read is carried by the ordinal, not by visit order
                 while (zf) {
-                    uint32_t bit = __ffs(zf) - 1; zf &= zf - 1;
+                    const uint32_t bit = __ffs(zf) - 1; zf &= zf - 1;
                     kj_verify_candidate(a, s, tile_off, tile_voff, pos0 + (bit >> 1), 0u, n_emit);
                 }
                 while (zr) {
-                    uint32_t bit = __ffs(zr) - 1; zr &= zr - 1;
+                    const uint32_t bit = __ffs(zr) - 1; zr &= zr - 1;
                     kj_verify_candidate(a, s, tile_off, tile_voff, pos0 + (bit >> 1), 1u, n_emit);
                 }
             }
         }
+        // the next ticket is taken as late as possible: tiles behind it wait for its aggregate,
+        // which this CTA can only publish after the barrier at the top of the loop
+        if (tid == 0) s.tile_next = atomicAdd(&a.ctr->ticket, 1u);
     }
-    if (n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);
-    if (n_bases) atomicAdd(&a.ctr->n_bases, n_bases);
+    // one atomic per warp
+    for (int d = 16; d > 0; d >>= 1) {
+        n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
+        n_bases += __shfl_xor_sync(0xFFFFFFFFu, n_bases, d);
+    }
+    if ((tid & 31) == 0) {
+        if (n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);
+        if (n_bases) atomicAdd(&a.ctr->n_bases, (unsigned long long)n_bases);
+    }
 }
 
 // ----------------------------------------------------------------------------- line-oriented kernel
@@ -469,9 +493,9 @@ __device__ __forceinline__ void kj_process_line(const KjScanArgs &a, uint64_t ls
         if (lane == 0) atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_EXCEEDS_HALO);
         return;
     }
+    if (lane == 0 && L) atomicAdd(&a.ctr->n_bases, (unsigned long long)L);   // every sequence line counts
     if (L <= 1 && a.line_gate) return;                    // lib/kmers.js:151
     if (L == 0) return;
-    if (lane == 0) atomicAdd(&a.ctr->n_bases, (unsigned long long)L);
     const uint64_t k = a.k, step = a.step, m = a.m;
     if (L < k) return;                                    // stop < 0: no iterations
     const uint64_t stop = L - k;
@@ -525,16 +549,14 @@ kj_scan_lines_kernel(const __grid_constant__ KjScanArgs a) {
         const uint32_t tile = s.tile;
         if (tile >= a.n_tiles) break;
         const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
-        const uint64_t tile_voff = a.voff + tile_off;
 
-        kj_tile_p1(a, s, tile);
-        kj_publish_aggregate(a, s, tile, tile_voff);
-        if (warp == 0) kj_lookback(a, s, tile, tile_voff);
+        kj_tile_p1<false>(a, s, tile);
+        if (warp == 0) kj_lookback(a, s, tile);
         __syncthreads();
 
         // the line that starts exactly at the first byte of the stream piece: owned iff the
         // previous stream byte was a '\n' (or there is no previous byte at all)
-        if (tile == 0 && tid == 0 && s.excl_last == a.voff && (s.excl_count & 3ull) == 1ull &&
+        if (tile == 0 && tid == 0 && a.ctr->carry_last[a.parity] == a.voff && (s.excl_count & 3ull) == 1ull &&
             a.own_n > 0)
             s.queue[s.q_n++] = 0;
         // P2': every '\n' at e starts a line at e+1 (owned by the tile that holds the '\n')
@@ -551,7 +573,7 @@ kj_scan_lines_kernel(const __grid_constant__ KjScanArgs a) {
                     uint64_t start = tile_off + c * 16u + bit + 1u;
                     if ((line & 3ull) == 1ull && start < a.n) {
                         uint32_t q = atomicAdd(&s.q_n, 1u);
-                        s.queue[q] = c * 16u + bit + 1u;       // <= KJ_CPT*... entries per round
+                        s.queue[q] = c * 16u + bit + 1u;       // at most 4096 / 4 entries per round
                     }
                 }
             }

@@ -460,7 +460,7 @@ extern "C" void kj_match_free(kj_match *m) {
         kj_dfree(ctx, m->d_part);
         kj_dfree(ctx, m->d_first_ord); kj_dfree(ctx, m->d_first_idx); kj_dfree(ctx, m->d_rank);
         kj_dfree(ctx, m->d_toff); kj_dfree(ctx, m->d_tcur); kj_dfree(ctx, m->d_tq); kj_dfree(ctx, m->d_res);
-        if (m->h_res) cudaFreeHost(m->h_res);
+        kj_pinned_put(ctx, m->h_res);
     }
     delete m;
 }
@@ -528,7 +528,10 @@ extern "C" int kj_first_match_local(kj_ctx *ctx, kj_counts *q, const kj_db *db, 
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_toff, (T + 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_tcur, std::max<uint64_t>(T, 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_res, sizeof(KjWtaResult));
-    if (e == cudaSuccess) e = cudaMallocHost(&m->h_res, sizeof(KjWtaResult));
+    if (e == cudaSuccess) {
+        m->h_res = (KjWtaResult *)kj_pinned_get(ctx);
+        if (!m->h_res) e = cudaErrorMemoryAllocation;
+    }
     if (e == cudaSuccess) e = cudaMemsetAsync(m->d_qkmer, 0xFF, std::max<uint64_t>(m->Q, 1) * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->d_part, 0, (2 * T + 1) * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->d_first_ord, 0xFF, std::max<uint64_t>(T, 1) * 8, ctx->stream);

@@ -119,11 +119,14 @@ def exchange_counts(local: Counts, group=None) -> Counts:
             if blob:
                 owned.merge_irregular(np.frombuffer(blob, dtype=np.uint8))
     owned.finish()
-    tot = torch.tensor([local.lines, local.bases, local.occurrences, local.bytes_read, owned.size],
+    tot = torch.tensor([local.bases, local.occurrences, local.bytes_read, owned.size],
                        dtype=torch.int64, device=dev)
     dist.all_reduce(tot, group=group)
-    lines, bases, occ, nbytes, qsize = [int(x) for x in tot.tolist()]
-    owned.set_totals(lines, bases, occ, nbytes)
+    bases, occ, nbytes, qsize = [int(x) for x in tot.tolist()]
+    # a rank's line count already includes the lines before its range (base_line): the last rank's is the file's
+    ln = torch.tensor([local.lines], dtype=torch.int64, device=dev)
+    dist.all_reduce(ln, op=dist.ReduceOp.MAX, group=group)
+    owned.set_totals(int(ln.item()), bases, occ, nbytes)
     owned.global_size = qsize
     return owned
 

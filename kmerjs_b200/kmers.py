@@ -175,7 +175,6 @@ class KmerJS:
                 self.kmerMapSize = len(m)              # lib/kmers.js:177
                 self.lines = c.lines                   # lib/kmers.js:164-165
                 self.bytesRead = c.bytes_read
-                self.bases = c.bases
                 if self.env == "node" and self.progress:
                     # one line instead of one write per FASTQ line (lib/kmers.js:166-169,174-176)
                     print(f"Lines: {self.lines} / Kmers: {len(m)}\r\n                               ")

@@ -24,7 +24,7 @@ def oracle(data, prefix=b"ATGAC", k=16, step=1):
 
 
 def gpu(data, prefix=b"ATGAC", k=16, step=1, flags=0, device=False, pieces=None, halo=64, **kw):
-    c = Counts(prefix, k, step, flags=flags, **kw)
+    c = Counts(prefix, k, step, flags=flags | _abi.KJ_F_COUNT_BASES, **kw)
     if pieces is None:
         if device:
             b = DevBuf(data)
@@ -58,7 +58,7 @@ def gpu(data, prefix=b"ATGAC", k=16, step=1, flags=0, device=False, pieces=None,
 
 def seq_bases(data):
     lines = ko_py.split_lines(data)
-    return sum(len(l) for i, l in enumerate(lines) if i % 4 == 1 and len(l) > 1)
+    return sum(len(l) for i, l in enumerate(lines) if i % 4 == 1)      # every sequence line, gated or not
 
 
 @pytest.mark.parametrize("name", ["test_short.fastq", "test_long.kmer.fastq", "test_kmers.fastq"])
@@ -175,11 +175,11 @@ def test_sharded_base_line():
     for cut in (1, len(data) // 3, len(data) // 2 + 7):
         nl = data[:cut].count(b"\n")
         col = cut - (data[:cut].rfind(b"\n") + 1)
-        a = Counts(b"ATGAC", 16, 1)
+        a = Counts(b"ATGAC", 16, 1, flags=_abi.KJ_F_COUNT_BASES)
         a.add_host(data[:cut + 64], own_n=cut, final=False)     # left rank: halo of 64 bytes, not final
         # a left rank never sees the end of stream; finish() is still valid
         a.finish()
-        b = Counts(b"ATGAC", 16, 1, base_line=nl, base_col=col)
+        b = Counts(b"ATGAC", 16, 1, flags=_abi.KJ_F_COUNT_BASES, base_line=nl, base_col=col)
         b.add_host(data[cut:], final=True)
         b.finish()
         merged = {}
@@ -187,6 +187,8 @@ def test_sharded_base_line():
             for kk, v in d.items():
                 merged[kk] = merged.get(kk, 0) + v
         assert merged == whole, cut
+        assert a.bases + b.bases == seq_bases(data), cut      # the cut may fall inside a sequence line
+        assert b.lines == oracle(data)[1]
         a.free(); b.free()
 
 
@@ -247,7 +249,7 @@ def test_size_independent_properties():
     from kmerjs_b200 import synth
     n_reads = 4000 if os.environ.get("KMERJS_B200_EMU") == "1" else 400000
     w = synth.Workload(n_reads=n_reads, genome_len=200000, seed=99)
-    c = Counts(b"ATGAC", 16, 1)
+    c = Counts(b"ATGAC", 16, 1, flags=_abi.KJ_F_COUNT_BASES)
     c.add_device(w.fastq_ptr, w.n_bytes, final=True).finish()
     m = c.to_dict()
     assert c.lines == 4 * n_reads and c.bases == 150 * n_reads

@@ -1,0 +1,160 @@
+"""The multi-GPU protocol of the C ABI, with the ranks emulated one after the other on one device
+(no collectives here: the reductions NCCL would do are done with numpy): byte-range sharding with
+newline phase, owner partition + merge, sharded DB, reduced score vectors, replicated WTA.
+The result must equal the single-device run and the oracle."""
+import ctypes as C
+import json
+import random
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+import kmer_oracle as ko
+import ko as ko_c
+from conftest import read_golden
+from util import DevBuf, dev_u64, emulated, random_fastq, synthetic_db
+
+from kmerjs_b200 import _abi
+from kmerjs_b200 import dist as kdist
+from kmerjs_b200.counts import Counts, count_newlines_device
+from kmerjs_b200.db import TemplateDB
+from kmerjs_b200.matching import Match, NoHitsError
+
+pytestmark = pytest.mark.gpu
+
+
+def read_device(ptr, n_bytes):
+    if emulated():
+        return np.frombuffer(C.string_at(ptr, n_bytes), dtype=np.uint8).copy()
+    import torch
+    out = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    C.cdll.LoadLibrary  # noqa: B018
+    # copy through torch: build a view with the CUDA array interface
+    view = torch.as_tensor(kdist._CudaView(ptr, n_bytes // 8), device="cuda")
+    return view.cpu().numpy().view(np.uint8).copy()
+
+
+def sharded_counts(data, world, prefix=b"ATGAC", k=16, step=1, halo=64):
+    """count every rank's range, partition by owner, merge per owner -> list of owned Counts."""
+    ranges = kdist.plan_ranges(len(data), world, halo=halo)
+    whole = DevBuf(data)
+    stats = [count_newlines_device(whole.ptr + lo, own) for lo, own, _ in ranges]
+    for (lo, own, _), (cnt, last) in zip(ranges, stats):
+        seg = data[lo:lo + own]
+        assert cnt == seg.count(b"\n") and last == seg.rfind(b"\n") + 1
+    bl, bc = kdist.phase_of_ranges([s[0] for s in stats], [s[1] for s in stats], [r[1] for r in ranges])
+    locals_ = []
+    for r, (lo, own, rd) in enumerate(ranges):
+        c = Counts(prefix, k, step, flags=_abi.KJ_F_COUNT_BASES, base_line=bl[r], base_col=bc[r])
+        c.add_device(whole.ptr + lo, rd, own_n=own, final=(r == world - 1))
+        c.finish()
+        locals_.append(c)
+    parts = [c.partition(world) for c in locals_]
+    owned = []
+    for o in range(world):
+        oc = Counts(prefix, k, step)
+        for r, (ptr, sizes) in enumerate(parts):
+            off = sum(sizes[:o])
+            if sizes[o]:
+                oc.merge_records(ptr + 24 * off, sizes[o])
+        if o == 0:
+            for c in locals_:
+                oc.merge_irregular(c.irregular_records())
+        oc.finish()
+        owned.append(oc)
+    totals = (max(c.lines for c in locals_), sum(c.bases for c in locals_), sum(c.occurrences for c in locals_))
+    for c in locals_:
+        c.free()
+    return owned, totals, whole
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_count_equals_whole(world):
+    rng = random.Random(50 + world)
+    data = random_fastq(rng, 500, p_n=0.02, blank_lines=0.03)
+    exp, lines = ko_c.count_fastq(data)
+    owned, totals, _keep = sharded_counts(data, world)
+    merged = {}
+    for o, oc in enumerate(owned):
+        d = oc.to_dict()
+        assert not (set(d) & set(merged))                         # every key has one owner
+        for kk in d:
+            assert _abi.lib().kj_owner(kk.encode("latin-1"), len(kk), world) == o
+        merged.update(d)
+    assert {k.encode("latin-1"): v for k, v in merged.items()} == dict(exp)
+    assert totals[0] == lines                        # the last rank's count includes the lines before it
+    assert totals[1] == sum(len(l) for i, l in enumerate(ko.split_lines(data)) if i % 4 == 1)
+    assert totals[2] == sum(exp.values())
+    for oc in owned:
+        oc.free()
+
+
+def test_sharded_scoring_equals_single_device():
+    golden_reads = read_golden("test_long.kmer.fastq")
+    world = 2
+    exp_counts, _ = ko_c.count_fastq(golden_reads)
+    rng = random.Random(314)
+    lists, attrs, summary = synthetic_db(list(exp_counts.keys()), rng, n_templates=20, decoys=80, share=0.7)
+    tdb = TemplateDB.from_lists(lists, attrs, summary)
+    # oracle
+    db = ko.TemplateDB(lists, attrs, summary)
+    q = OrderedDict(exp_counts)
+    templates, hits = ko.first_match(q, db)
+    e_order = list(templates.keys())
+    e_rows, e_err = [], None
+    try:
+        for r in ko.find_matches(templates, summary, q, len(exp_counts)):
+            e_rows.append(r)
+    except RuntimeError as exc:
+        e_err = str(exc)
+    # sharded run
+    owned, totals, _keep = sharded_counts(golden_reads, world)
+    qsize = sum(oc.size for oc in owned)
+    assert qsize == len(exp_counts)
+    ms = [Match(oc, tdb, local_only=True, part=r, n_parts=world) for r, oc in enumerate(owned)]
+
+    def reduce(which, op):
+        n = ms[0].vec_len(which)
+        vals = []
+        for m in ms:
+            ptr, keep, back = dev_u64(np.zeros(max(n, 1), dtype=np.uint64))
+            m.get(which, ptr)
+            vals.append(back()[:n])
+        red = np.sum(vals, axis=0, dtype=np.uint64) if op == "sum" else np.min(vals, axis=0)
+        for m in ms:
+            ptr, keep, _ = dev_u64(red if n else np.zeros(1, dtype=np.uint64))
+            m.set(which, ptr)
+
+    reduce(_abi.KJ_VEC_SCORES, "sum")
+    reduce(_abi.KJ_VEC_FIRST_ORD, "min")
+    reduce(_abi.KJ_VEC_FIRST_IDX, "min")
+    for m in ms:
+        m.set_query_size(qsize)
+        m.commit()
+        assert m.hits == hits and list(m.templates().keys()) == e_order
+        assert {n: (t["uScore"], t["tScore"]) for n, t in m.templates().items()} == \
+            {n: (t["uScore"], t["tScore"]) for n, t in templates.items()}
+    g_rows, g_err = [], None
+    try:
+        while True:
+            rows = [m.next_row() for m in ms]                   # every rank takes the same decision
+            assert all(r == rows[0] for r in rows)
+            if rows[0] is None:
+                break
+            g_rows.append(rows[0])
+            reduce(_abi.KJ_VEC_SCORES, "sum")
+    except NoHitsError as exc:
+        g_err = str(exc)
+    assert [r["template"] for r in g_rows] == [r["template"] for r in e_rows]
+    for g, e in zip(g_rows, e_rows):
+        for f in ko.ROW_KEYS:
+            if f == "probability":
+                assert g[f] == pytest.approx(e[f], rel=1e-9)
+            else:
+                assert g[f] == e[f], f
+    assert g_err == e_err
+    for m in ms:
+        m.free()
+    for oc in owned:
+        oc.free()

@@ -26,7 +26,9 @@
 #define KJ_TILE_CHUNKS (KJ_TILE_BYTES / 16)              // 2048 16-byte chunks
 #define KJ_CPT (KJ_TILE_CHUNKS / KJ_THREADS)             // 8 chunks per thread
 #define KJ_ROWS (KJ_TILE_CHUNKS / 32)                    // 64 rows of 512 bytes (one warp-wide load)
-#define KJ_QCAP 1536                                     // candidate / line queue entries
+#define KJ_QCAP 1536                                     // line queue entries (line kernel: <= 1024 per round)
+#define KJ_FQCAP 512                                     // candidate queue entries (filter kernel: ~64 per tile)
+#define KJ_STAGE_BYTES (KJ_TILE_BYTES + 32)              // a tile and the 32 bytes its last windows reach into
 #define KJ_MAX_MP 8                                      // filter symbols used in code space
 
 #define KJ_ST_AGG 1ull
@@ -90,8 +92,7 @@ struct KjTileSmem {
     uint32_t codes[KJ_TILE_CHUNKS + 2];   // +2 halo words: windows reach k-1 bytes past the tile
     uint16_t nl[KJ_TILE_CHUNKS];          // '\n' mask of the chunk
     uint32_t row_pre[KJ_ROWS];            // row counts, then exclusive prefix over the tile
-    uint32_t queue[KJ_QCAP];
-    uint32_t q_n;
+    uint32_t q_n;                         // entries in the kernel's candidate / line queue
     uint32_t tile;                        // ticket of the tile being processed
     uint32_t tile_next;                   // ticket fetched ahead for the next round
     uint32_t tile_count;                  // '\n' in the tile
@@ -136,10 +137,62 @@ __device__ __forceinline__ unsigned long long kj_line_start(const KjScanArgs &a,
 
 // ----------------------------------------------------------------------------- P1 + look-back
 
-// Fills codes / nlp / row_pre / tile_count for tile `tile`.  INTERIOR: the tile and its 32-byte
-// code halo lie inside the owned range, no per-chunk bounds work.  Ends with a barrier.
+// ---- asynchronous bulk copy global -> shared (TMA engine; SASS UBLKCP) completing on an mbarrier
+#ifdef KJ_CPU_EMU   // tools/cuemu: the copy happens at issue time
+__device__ __forceinline__ void kj_bar_init(uint64_t *, uint32_t) {}
+__device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void kj_bar_wait(uint64_t *, uint32_t) {}
+#else
+__device__ __forceinline__ uint32_t kj_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void kj_bar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kj_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// one thread: announce `bytes` on the barrier, then start the copy (src, dst 16-byte aligned, bytes % 16 == 0)
+__device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(kj_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(kj_smem_u32(dst)), "l"(src), "r"(bytes), "r"(kj_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void kj_bar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t addr = kj_smem_u32(bar);
+    while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+}
+#endif
+
+// one 16-byte chunk -> code word, newline mask, row count (warp = 32 consecutive chunks = one row)
+__device__ __forceinline__ void kj_p1_chunk(KjTileSmem &s, uint32_t c, uint32_t row, const uint4 v, uint32_t nl_keep) {
+    s.codes[c] = kj_pack16(v.x, v.y, v.z, v.w);
+    const uint32_t nl = kj_nl16(v.x, v.y, v.z, v.w) & nl_keep;
+    s.nl[c] = (uint16_t)nl;
+    const uint32_t rc = __reduce_add_sync(0xFFFFFFFFu, __popc(nl));
+    if ((threadIdx.x & 31) == 0) s.row_pre[row] = rc;
+}
+
+// P1 from the staged tile (interior tiles: every byte owned, halo readable).  Ends with a barrier.
+__device__ __forceinline__ void kj_tile_p1_stage(KjTileSmem &s, const uint8_t *stage) {
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+#pragma unroll
+    for (int it = 0; it < KJ_CPT; ++it) {
+        const uint32_t c = it * KJ_THREADS + tid;
+        const uint4 v = *reinterpret_cast<const uint4 *>(stage + c * 16u);
+        kj_p1_chunk(s, c, it * (KJ_THREADS / 32) + warp, v, 0xFFFFu);
+    }
+    if (tid < 2) {
+        const uint4 h = *reinterpret_cast<const uint4 *>(stage + (KJ_TILE_CHUNKS + tid) * 16u);
+        s.codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
+    }
+    __syncthreads();
+}
+
+// P1 straight from global memory.  INTERIOR: the tile and its 32-byte code halo lie inside the
+// owned range, no per-chunk bounds work.  Ends with a barrier.
 template <bool INTERIOR>
-__device__ __forceinline__ void kj_tile_p1(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
+__device__ __forceinline__ void kj_tile_p1_global(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
     const uint8_t *tbase = a.buf + tile_off;
@@ -160,16 +213,13 @@ __device__ __forceinline__ void kj_tile_p1(const KjScanArgs &a, KjTileSmem &s, u
         for (int j = 0; j < KJ_CPT / 2; ++j) {
             const int it = half * (KJ_CPT / 2) + j;
             const uint32_t c = it * KJ_THREADS + tid;
-            s.codes[c] = kj_pack16(v[j].x, v[j].y, v[j].z, v[j].w);
-            uint32_t nl = kj_nl16(v[j].x, v[j].y, v[j].z, v[j].w);
+            uint32_t keep = 0xFFFFu;
             if (!INTERIOR) {   // newlines are counted only inside the owned range
                 const uint64_t off = tile_off + (uint64_t)c * 16u;
-                if (off >= a.own_n) nl = 0;
-                else if (off + 16 > a.own_n) nl &= (1u << (uint32_t)(a.own_n - off)) - 1u;
+                if (off >= a.own_n) keep = 0;
+                else if (off + 16 > a.own_n) keep = (1u << (uint32_t)(a.own_n - off)) - 1u;
             }
-            s.nl[c] = (uint16_t)nl;
-            const uint32_t rc = __reduce_add_sync(0xFFFFFFFFu, __popc(nl));
-            if (lane == 0) s.row_pre[it * (KJ_THREADS / 32) + warp] = rc;       // row = chunk >> 5
+            kj_p1_chunk(s, c, it * (KJ_THREADS / 32) + warp, v[j], keep);
         }
     }
     if (tid < 2) {   // halo code words
@@ -178,6 +228,11 @@ __device__ __forceinline__ void kj_tile_p1(const KjScanArgs &a, KjTileSmem &s, u
         s.codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
     }
     __syncthreads();
+}
+
+// Warp 0 turns the row counts into exclusive prefixes and publishes the tile's aggregate.  Ends with a barrier.
+__device__ __forceinline__ void kj_tile_rowscan(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (warp == 0) {
         // exclusive scan of the 64 row counts, 2 per lane; the tile's aggregate is published at once
         const uint32_t c0 = s.row_pre[2 * lane], c1 = s.row_pre[2 * lane + 1];
@@ -382,23 +437,49 @@ template <int MP, int RC>
 __global__ void __launch_bounds__(KJ_THREADS)
 kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ KjTileSmem s;
+    __shared__ uint32_t queue[KJ_FQCAP];
+    __shared__ __align__(128) uint8_t stage[KJ_STAGE_BYTES];    // raw bytes of the tile in flight (TMA bulk copy)
+    __shared__ __align__(8) uint64_t bar;                       // its completion barrier
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    uint32_t n_emit = 0;
+    uint32_t n_emit = 0, ph = 0;
     long long n_bases = 0;
-    if (tid == 0) s.tile_next = atomicAdd(&a.ctr->ticket, 1u);
+    // a tile travels through `stage` when it and the 32 bytes behind it are owned and readable
+    const uint64_t staged_end = a.own_n >= KJ_STAGE_BYTES ? a.own_n - KJ_STAGE_BYTES : 0;   // tile_off <= staged_end
+    const bool any_staged = a.own_n >= KJ_STAGE_BYTES;
+    if (tid == 0) {
+        kj_bar_init(&bar, 1);
+        const uint32_t t = atomicAdd(&a.ctr->ticket, 1u);
+        s.tile_next = t;
+        const uint64_t off = (uint64_t)t * KJ_TILE_BYTES;
+        if (t < a.n_tiles && any_staged && off <= staged_end) kj_bulk_g2s(stage, a.buf + off, KJ_STAGE_BYTES, &bar);
+    }
     for (;;) {
         __syncthreads();                                   // previous tile fully consumed; ticket visible
         const uint32_t tile = s.tile_next;
         if (tile >= a.n_tiles) break;
         const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
         const uint64_t tile_voff = a.voff + tile_off;
-        const bool interior = tile_off + KJ_TILE_BYTES + 32u <= a.own_n;
+        const bool staged = any_staged && tile_off <= staged_end;
         if (tid == 0) s.q_n = 0;
 
-        if (interior) kj_tile_p1<true>(a, s, tile); else kj_tile_p1<false>(a, s, tile);
-
-        // the scan state of this tile goes out first: later tiles wait on it
-        if (warp == 0) kj_lookback(a, s, tile);
+        // P1: bytes -> code words + newline masks
+        if (staged) {
+            kj_bar_wait(&bar, ph);
+            ph ^= 1u;
+            kj_tile_p1_stage(s, stage);
+        } else {
+            kj_tile_p1_global<false>(a, s, tile);
+        }
+        // `stage` is free again: take the next ticket and start its copy, so that the bytes of the
+        // next tile stream in while this one is searched.  (A warp other than warp 0, which is busy
+        // publishing this tile's aggregate for the tiles behind it.)
+        if (tid == 32) {
+            const uint32_t t = atomicAdd(&a.ctr->ticket, 1u);
+            s.tile_next = t;
+            const uint64_t off = (uint64_t)t * KJ_TILE_BYTES;
+            if (t < a.n_tiles && any_staged && off <= staged_end) kj_bulk_g2s(stage, a.buf + off, KJ_STAGE_BYTES, &bar);
+        }
+        kj_tile_rowscan(a, s, tile);
 
         // P2: bit-parallel prefix search in code space
         const uint32_t own_in_tile =
@@ -421,9 +502,11 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                 z &= z - 1;
                 const uint32_t jt = pos0 + (bit >> 1);
                 const uint32_t q = atomicAdd(&s.q_n, 1u);
-                if (q < KJ_QCAP) s.queue[q] = (jt << 1) | strand;
+                if (q < KJ_FQCAP) queue[q] = (jt << 1) | strand;
             }
         }
+        // the line phase is needed from here on; by now the tiles in front have published
+        if (warp == 0) kj_lookback(a, s, tile);
         __syncthreads();
 
         if (a.count_bases) n_bases += kj_tile_bases(s, tile_voff);
@@ -431,9 +514,9 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
         // P3: verify + insert.  Candidates sit densely in the first warps: the kernel is bound by
         // instruction issue, and a warp with one busy lane costs as much as a full one.
         const uint32_t qn = s.q_n;
-        if (qn <= KJ_QCAP) {
+        if (qn <= KJ_FQCAP) {
             for (uint32_t q = tid; q < qn; q += KJ_THREADS) {
-                const uint32_t e = s.queue[q];
+                const uint32_t e = queue[q];
                 kj_verify_candidate(a, s, tile_off, tile_voff, e >> 1, e & 1u, n_emit);
             }
         } else {
@@ -459,9 +542,6 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                 }
             }
         }
-        // the next ticket is taken as late as possible: tiles behind it wait for its aggregate,
-        // which this CTA can only publish after the barrier at the top of the loop
-        if (tid == 0) s.tile_next = atomicAdd(&a.ctr->ticket, 1u);
     }
     // one atomic per warp
     for (int d = 16; d > 0; d >>= 1) {
@@ -540,6 +620,7 @@ __device__ __forceinline__ void kj_process_line(const KjScanArgs &a, uint64_t ls
 __global__ void __launch_bounds__(KJ_THREADS)
 kj_scan_lines_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ KjTileSmem s;
+    __shared__ uint32_t queue[KJ_QCAP];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t n_emit = 0;
     for (;;) {
@@ -550,7 +631,8 @@ kj_scan_lines_kernel(const __grid_constant__ KjScanArgs a) {
         if (tile >= a.n_tiles) break;
         const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
 
-        kj_tile_p1<false>(a, s, tile);
+        kj_tile_p1_global<false>(a, s, tile);
+        kj_tile_rowscan(a, s, tile);
         if (warp == 0) kj_lookback(a, s, tile);
         __syncthreads();
 
@@ -558,7 +640,7 @@ kj_scan_lines_kernel(const __grid_constant__ KjScanArgs a) {
         // previous stream byte was a '\n' (or there is no previous byte at all)
         if (tile == 0 && tid == 0 && a.ctr->carry_last[a.parity] == a.voff && (s.excl_count & 3ull) == 1ull &&
             a.own_n > 0)
-            s.queue[s.q_n++] = 0;
+            queue[s.q_n++] = 0;
         // P2': every '\n' at e starts a line at e+1 (owned by the tile that holds the '\n')
         for (int it = 0; it < KJ_CPT; ++it) {
             __syncthreads();
@@ -573,7 +655,7 @@ kj_scan_lines_kernel(const __grid_constant__ KjScanArgs a) {
                     uint64_t start = tile_off + c * 16u + bit + 1u;
                     if ((line & 3ull) == 1ull && start < a.n) {
                         uint32_t q = atomicAdd(&s.q_n, 1u);
-                        s.queue[q] = c * 16u + bit + 1u;       // at most 4096 / 4 entries per round
+                        queue[q] = c * 16u + bit + 1u;       // at most 4096 / 4 entries per round
                     }
                 }
             }
@@ -581,7 +663,7 @@ kj_scan_lines_kernel(const __grid_constant__ KjScanArgs a) {
             // P3': one warp per line
             const uint32_t qn = s.q_n;
             for (uint32_t q = warp; q < qn; q += KJ_THREADS / 32) {
-                uint32_t st = s.queue[q];
+                uint32_t st = queue[q];
                 unsigned long long line = s.excl_count + kj_count_before(s, st);
                 kj_process_line(a, tile_off + st, line, lane, n_emit);
             }

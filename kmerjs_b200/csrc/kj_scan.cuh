@@ -88,13 +88,12 @@ __device__ __forceinline__ uint4 kj_load_chunk(const uint8_t *buf, uint64_t off,
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// per-tile state that outlives the code words: the filter kernel keeps two of these, so that the
+// next tile can be converted (and its aggregate published) before the current one is finished
 struct KjTileSmem {
-    uint32_t codes[KJ_TILE_CHUNKS + 2];   // +2 halo words: windows reach k-1 bytes past the tile
     uint16_t nl[KJ_TILE_CHUNKS];          // '\n' mask of the chunk
     uint32_t row_pre[KJ_ROWS];            // row counts, then exclusive prefix over the tile
     uint32_t q_n;                         // entries in the kernel's candidate / line queue
-    uint32_t tile;                        // ticket of the tile being processed
-    uint32_t tile_next;                   // ticket fetched ahead for the next round
     uint32_t tile_count;                  // '\n' in the tile
     unsigned long long excl_count;        // '\n' before the tile (whole stream)
 };
@@ -165,8 +164,9 @@ __device__ __forceinline__ void kj_bar_wait(uint64_t *bar, uint32_t parity) {
 #endif
 
 // one 16-byte chunk -> code word, newline mask, row count (warp = 32 consecutive chunks = one row)
-__device__ __forceinline__ void kj_p1_chunk(KjTileSmem &s, uint32_t c, uint32_t row, const uint4 v, uint32_t nl_keep) {
-    s.codes[c] = kj_pack16(v.x, v.y, v.z, v.w);
+__device__ __forceinline__ void kj_p1_chunk(uint32_t *codes, KjTileSmem &s, uint32_t c, uint32_t row, const uint4 v,
+                                            uint32_t nl_keep) {
+    codes[c] = kj_pack16(v.x, v.y, v.z, v.w);
     const uint32_t nl = kj_nl16(v.x, v.y, v.z, v.w) & nl_keep;
     s.nl[c] = (uint16_t)nl;
     const uint32_t rc = __reduce_add_sync(0xFFFFFFFFu, __popc(nl));
@@ -174,17 +174,17 @@ __device__ __forceinline__ void kj_p1_chunk(KjTileSmem &s, uint32_t c, uint32_t 
 }
 
 // P1 from the staged tile (interior tiles: every byte owned, halo readable).  Ends with a barrier.
-__device__ __forceinline__ void kj_tile_p1_stage(KjTileSmem &s, const uint8_t *stage) {
+__device__ __forceinline__ void kj_tile_p1_stage(uint32_t *codes, KjTileSmem &s, const uint8_t *stage) {
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
 #pragma unroll
     for (int it = 0; it < KJ_CPT; ++it) {
         const uint32_t c = it * KJ_THREADS + tid;
         const uint4 v = *reinterpret_cast<const uint4 *>(stage + c * 16u);
-        kj_p1_chunk(s, c, it * (KJ_THREADS / 32) + warp, v, 0xFFFFu);
+        kj_p1_chunk(codes, s, c, it * (KJ_THREADS / 32) + warp, v, 0xFFFFu);
     }
     if (tid < 2) {
         const uint4 h = *reinterpret_cast<const uint4 *>(stage + (KJ_TILE_CHUNKS + tid) * 16u);
-        s.codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
+        codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
     }
     __syncthreads();
 }
@@ -192,7 +192,7 @@ __device__ __forceinline__ void kj_tile_p1_stage(KjTileSmem &s, const uint8_t *s
 // P1 straight from global memory.  INTERIOR: the tile and its 32-byte code halo lie inside the
 // owned range, no per-chunk bounds work.  Ends with a barrier.
 template <bool INTERIOR>
-__device__ __forceinline__ void kj_tile_p1_global(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
+__device__ __forceinline__ void kj_tile_p1_global(const KjScanArgs &a, uint32_t *codes, KjTileSmem &s, uint32_t tile) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
     const uint8_t *tbase = a.buf + tile_off;
@@ -219,21 +219,21 @@ __device__ __forceinline__ void kj_tile_p1_global(const KjScanArgs &a, KjTileSme
                 if (off >= a.own_n) keep = 0;
                 else if (off + 16 > a.own_n) keep = (1u << (uint32_t)(a.own_n - off)) - 1u;
             }
-            kj_p1_chunk(s, c, it * (KJ_THREADS / 32) + warp, v[j], keep);
+            kj_p1_chunk(codes, s, c, it * (KJ_THREADS / 32) + warp, v[j], keep);
         }
     }
     if (tid < 2) {   // halo code words
         const uint64_t off = tile_off + (uint64_t)(KJ_TILE_CHUNKS + tid) * 16u;
         const uint4 h = (off < a.n) ? kj_load_chunk(a.buf, off, a.n) : make_uint4(0, 0, 0, 0);
-        s.codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
+        codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
     }
     __syncthreads();
 }
 
-// Warp 0 turns the row counts into exclusive prefixes and publishes the tile's aggregate.  Ends with a barrier.
-__device__ __forceinline__ void kj_tile_rowscan(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp == 0) {
+// Warp 0 turns the row counts into exclusive prefixes and publishes the tile's aggregate.
+__device__ __forceinline__ void kj_tile_rowscan_warp0(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
+    const uint32_t lane = threadIdx.x & 31;
+    {
         // exclusive scan of the 64 row counts, 2 per lane; the tile's aggregate is published at once
         const uint32_t c0 = s.row_pre[2 * lane], c1 = s.row_pre[2 * lane + 1];
         const uint32_t sum = c0 + c1;
@@ -251,7 +251,6 @@ __device__ __forceinline__ void kj_tile_rowscan(const KjScanArgs &a, KjTileSmem 
             *reinterpret_cast<volatile uint64_t *>(&a.status[tile]) = (KJ_ST_AGG << 62) | (uint64_t)incl;
         }
     }
-    __syncthreads();
 }
 
 // Warp 0: decoupled look-back.  Writes excl_count, publishes the inclusive state and, for the last
@@ -420,9 +419,9 @@ __device__ __forceinline__ uint32_t kj_rc_lanes(uint32_t c0, uint32_t c1, uint32
 
 // candidate lanes (bit 2p set: window at chunk position p passes the code-space filter)
 template <int MP, int RC>
-__device__ __forceinline__ void kj_chunk_filter(const KjScanArgs &a, const KjTileSmem &s, uint32_t c,
+__device__ __forceinline__ void kj_chunk_filter(const KjScanArgs &a, const uint32_t *codes, uint32_t c,
                                                 uint32_t &zf, uint32_t &zr) {
-    const uint32_t c0 = s.codes[c], c1 = s.codes[c + 1], c2 = s.codes[c + 2];
+    const uint32_t c0 = codes[c], c1 = codes[c + 1], c2 = codes[c + 2];
     uint32_t accf = 0, accr = 0;
 #pragma unroll
     for (int i = 0; i < MP; ++i) {
@@ -433,114 +432,125 @@ __device__ __forceinline__ void kj_chunk_filter(const KjScanArgs &a, const KjTil
     zr = a.n_strands > 1 ? kj_zero_lanes(accr) : 0u;
 }
 
+// P2 of one tile: bit-parallel prefix search in code space; candidates -> queue
+template <int MP, int RC>
+__device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32_t *codes, KjTileSmem &s, uint32_t *queue,
+                                               uint32_t own_in_tile) {
+    const uint32_t tid = threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < KJ_CPT; ++it) {
+        const uint32_t c = it * KJ_THREADS + tid;
+        const uint32_t pos0 = c * 16u;
+        if (pos0 >= own_in_tile) continue;
+        uint32_t zf, zr;
+        kj_chunk_filter<MP, RC>(a, codes, c, zf, zr);
+        if (own_in_tile - pos0 < 16u) {
+            const uint32_t keep = (1u << (2u * (own_in_tile - pos0))) - 1u;
+            zf &= keep; zr &= keep;
+        }
+        while (zf | zr) {
+            const uint32_t strand = zf ? 0u : 1u;
+            uint32_t &z = zf ? zf : zr;
+            const uint32_t bit = __ffs(z) - 1;
+            z &= z - 1;
+            const uint32_t jt = pos0 + (bit >> 1);
+            const uint32_t q = atomicAdd(&s.q_n, 1u);
+            if (q < KJ_FQCAP) queue[q] = (jt << 1) | strand;
+        }
+    }
+}
+
+// The filter kernel, software-pipelined over tiles.  While tile `cur` is searched, verified and
+// counted, the bytes of tile `nxt` arrive in `stage` through the TMA engine (cp.async.bulk +
+// mbarrier); `nxt` is converted to code words and its newline aggregate is published BEFORE `cur`
+// is finished, so the look-back of the tiles behind it does not wait for this CTA:
+//
+//   search(cur) | convert(nxt), take ticket, start copy(nxt+1) | warp 0: aggregate(nxt), look-back(cur) | verify+count(cur)
+//
+// Shared memory: code words (one tile), two KjTileSmem (cur / nxt), candidate queue, stage (dynamic).
 template <int MP, int RC>
 __global__ void __launch_bounds__(KJ_THREADS)
 kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
-    __shared__ KjTileSmem s;
+    __shared__ uint32_t codes[KJ_TILE_CHUNKS + 2];              // +2 halo words: windows reach k-1 bytes past the tile
+    __shared__ KjTileSmem meta[2];
     __shared__ uint32_t queue[KJ_FQCAP];
-    __shared__ __align__(128) uint8_t stage[KJ_STAGE_BYTES];    // raw bytes of the tile in flight (TMA bulk copy)
-    __shared__ __align__(8) uint64_t bar;                       // its completion barrier
+    __shared__ uint32_t tile_next;                              // ticket fetched ahead
+    __shared__ __align__(8) uint64_t bar;                       // completion barrier of the copy in flight
+    KJ_DYN_SMEM(stage);                                         // KJ_STAGE_BYTES: raw bytes of the tile in flight
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     uint32_t n_emit = 0, ph = 0;
     long long n_bases = 0;
     // a tile travels through `stage` when it and the 32 bytes behind it are owned and readable
-    const uint64_t staged_end = a.own_n >= KJ_STAGE_BYTES ? a.own_n - KJ_STAGE_BYTES : 0;   // tile_off <= staged_end
     const bool any_staged = a.own_n >= KJ_STAGE_BYTES;
-    if (tid == 0) {
-        kj_bar_init(&bar, 1);
+    const uint64_t staged_end = any_staged ? a.own_n - KJ_STAGE_BYTES : 0;      // staged iff tile_off <= staged_end
+
+    auto take_ticket = [&]() {          // one thread: next tile + start of its copy
         const uint32_t t = atomicAdd(&a.ctr->ticket, 1u);
-        s.tile_next = t;
+        tile_next = t;
         const uint64_t off = (uint64_t)t * KJ_TILE_BYTES;
         if (t < a.n_tiles && any_staged && off <= staged_end) kj_bulk_g2s(stage, a.buf + off, KJ_STAGE_BYTES, &bar);
-    }
-    for (;;) {
-        __syncthreads();                                   // previous tile fully consumed; ticket visible
-        const uint32_t tile = s.tile_next;
-        if (tile >= a.n_tiles) break;
-        const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
-        const uint64_t tile_voff = a.voff + tile_off;
-        const bool staged = any_staged && tile_off <= staged_end;
-        if (tid == 0) s.q_n = 0;
-
-        // P1: bytes -> code words + newline masks
-        if (staged) {
+    };
+    auto convert = [&](uint32_t tile, KjTileSmem &m) {   // P1; ends with a barrier
+        if (tid == 0) m.q_n = 0;
+        const uint64_t off = (uint64_t)tile * KJ_TILE_BYTES;
+        if (any_staged && off <= staged_end) {
             kj_bar_wait(&bar, ph);
             ph ^= 1u;
-            kj_tile_p1_stage(s, stage);
+            kj_tile_p1_stage(codes, m, stage);
         } else {
-            kj_tile_p1_global<false>(a, s, tile);
+            kj_tile_p1_global<false>(a, codes, m, tile);
         }
-        // `stage` is free again: take the next ticket and start its copy, so that the bytes of the
-        // next tile stream in while this one is searched.  (A warp other than warp 0, which is busy
-        // publishing this tile's aggregate for the tiles behind it.)
-        if (tid == 32) {
-            const uint32_t t = atomicAdd(&a.ctr->ticket, 1u);
-            s.tile_next = t;
-            const uint64_t off = (uint64_t)t * KJ_TILE_BYTES;
-            if (t < a.n_tiles && any_staged && off <= staged_end) kj_bulk_g2s(stage, a.buf + off, KJ_STAGE_BYTES, &bar);
-        }
-        kj_tile_rowscan(a, s, tile);
+    };
 
-        // P2: bit-parallel prefix search in code space
-        const uint32_t own_in_tile =
-            (a.own_n - tile_off < KJ_TILE_BYTES) ? (uint32_t)(a.own_n - tile_off) : KJ_TILE_BYTES;
-#pragma unroll
-        for (int it = 0; it < KJ_CPT; ++it) {
-            const uint32_t c = it * KJ_THREADS + tid;
-            const uint32_t pos0 = c * 16u;
-            if (pos0 >= own_in_tile) continue;
-            uint32_t zf, zr;
-            kj_chunk_filter<MP, RC>(a, s, c, zf, zr);
-            if (own_in_tile - pos0 < 16u) {
-                const uint32_t keep = (1u << (2u * (own_in_tile - pos0))) - 1u;
-                zf &= keep; zr &= keep;
-            }
-            while (zf | zr) {
-                const uint32_t strand = zf ? 0u : 1u;
-                uint32_t &z = zf ? zf : zr;
-                const uint32_t bit = __ffs(z) - 1;
-                z &= z - 1;
-                const uint32_t jt = pos0 + (bit >> 1);
-                const uint32_t q = atomicAdd(&s.q_n, 1u);
-                if (q < KJ_FQCAP) queue[q] = (jt << 1) | strand;
-            }
-        }
-        // the line phase is needed from here on; by now the tiles in front have published
-        if (warp == 0) kj_lookback(a, s, tile);
-        __syncthreads();
+    if (tid == 0) { kj_bar_init(&bar, 1); take_ticket(); }
+    __syncthreads();
+    uint32_t cur = tile_next, b = 0;
+    if (cur < a.n_tiles) {
+        convert(cur, meta[0]);
+        if (tid == 32) take_ticket();
+        if (warp == 0) kj_tile_rowscan_warp0(a, meta[0], cur);
+        for (;;) {
+            __syncthreads();                               // aggregate of cur, ticket of nxt visible; queue free
+            const uint32_t nxt = tile_next;
+            KjTileSmem &m = meta[b];
+            const uint64_t tile_off = (uint64_t)cur * KJ_TILE_BYTES;
+            const uint64_t tile_voff = a.voff + tile_off;
+            const uint32_t own_in_tile =
+                (a.own_n - tile_off < KJ_TILE_BYTES) ? (uint32_t)(a.own_n - tile_off) : KJ_TILE_BYTES;
 
-        if (a.count_bases) n_bases += kj_tile_bases(s, tile_voff);
-
-        // P3: verify + insert.  Candidates sit densely in the first warps: the kernel is bound by
-        // instruction issue, and a warp with one busy lane costs as much as a full one.
-        const uint32_t qn = s.q_n;
-        if (qn <= KJ_FQCAP) {
-            for (uint32_t q = tid; q < qn; q += KJ_THREADS) {
-                const uint32_t e = queue[q];
-                kj_verify_candidate(a, s, tile_off, tile_voff, e >> 1, e & 1u, n_emit);
+            kj_tile_search<MP, RC>(a, codes, m, queue, own_in_tile);
+            __syncthreads();                               // code words of cur no longer needed
+            if (nxt < a.n_tiles) {
+                convert(nxt, meta[b ^ 1]);
+                if (tid == 32) take_ticket();              // `stage` is free again
             }
-        } else {
-            // dense candidates (e.g. homopolymer input): re-run the search and verify inline
-            for (int it = 0; it < KJ_CPT; ++it) {
-                const uint32_t c = it * KJ_THREADS + tid;
-                const uint32_t pos0 = c * 16u;
-                if (pos0 >= own_in_tile) continue;
-                uint32_t zf, zr;
-                kj_chunk_filter<MP, RC>(a, s, c, zf, zr);
-                if (own_in_tile - pos0 < 16u) {
-                    const uint32_t keep = (1u << (2u * (own_in_tile - pos0))) - 1u;
-                    zf &= keep; zr &= keep;
+            if (warp == 0) {
+                if (nxt < a.n_tiles) kj_tile_rowscan_warp0(a, meta[b ^ 1], nxt);
+                kj_lookback(a, m, cur);                    // the tiles in front published long ago
+            }
+            __syncthreads();
+
+            if (a.count_bases) n_bases += kj_tile_bases(m, tile_voff);
+
+            // verify + insert.  Candidates sit densely in the first warps: the kernel is bound by
+            // instruction issue, and a warp with one busy lane costs as much as a full one.
+            const uint32_t qn = m.q_n;
+            if (qn <= KJ_FQCAP) {
+                for (uint32_t q = tid; q < qn; q += KJ_THREADS) {
+                    const uint32_t e = queue[q];
+                    kj_verify_candidate(a, m, tile_off, tile_voff, e >> 1, e & 1u, n_emit);
                 }
-                // insertion order inside a read is carried by the ordinal, not by visit order
-                while (zf) {
-                    const uint32_t bit = __ffs(zf) - 1; zf &= zf - 1;
-                    kj_verify_candidate(a, s, tile_off, tile_voff, pos0 + (bit >> 1), 0u, n_emit);
-                }
-                while (zr) {
-                    const uint32_t bit = __ffs(zr) - 1; zr &= zr - 1;
-                    kj_verify_candidate(a, s, tile_off, tile_voff, pos0 + (bit >> 1), 1u, n_emit);
+            } else {
+                // dense candidates (e.g. homopolymer input): walk every owned position; the code words are
+                // gone by now, so every position is a candidate for the exact check
+                for (uint32_t jt = tid; jt < own_in_tile; jt += KJ_THREADS) {
+                    kj_verify_candidate(a, m, tile_off, tile_voff, jt, 0u, n_emit);
+                    if (a.n_strands > 1) kj_verify_candidate(a, m, tile_off, tile_voff, jt, 1u, n_emit);
                 }
             }
+            if (nxt >= a.n_tiles) break;
+            cur = nxt;
+            b ^= 1u;
         }
     }
     // one atomic per warp
@@ -620,20 +630,21 @@ __device__ __forceinline__ void kj_process_line(const KjScanArgs &a, uint64_t ls
 __global__ void __launch_bounds__(KJ_THREADS)
 kj_scan_lines_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ KjTileSmem s;
+    __shared__ uint32_t codes[KJ_TILE_CHUNKS + 2];
     __shared__ uint32_t queue[KJ_QCAP];
+    __shared__ uint32_t cur_tile;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t n_emit = 0;
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s.tile = atomicAdd(&a.ctr->ticket, 1u); s.q_n = 0; }
+        if (tid == 0) { cur_tile = atomicAdd(&a.ctr->ticket, 1u); s.q_n = 0; }
         __syncthreads();
-        const uint32_t tile = s.tile;
+        const uint32_t tile = cur_tile;
         if (tile >= a.n_tiles) break;
         const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
 
-        kj_tile_p1_global<false>(a, s, tile);
-        kj_tile_rowscan(a, s, tile);
-        if (warp == 0) kj_lookback(a, s, tile);
+        kj_tile_p1_global<false>(a, codes, s, tile);
+        if (warp == 0) { kj_tile_rowscan_warp0(a, s, tile); kj_lookback(a, s, tile); }
         __syncthreads();
 
         // the line that starts exactly at the first byte of the stream piece: owned iff the

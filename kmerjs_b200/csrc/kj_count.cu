@@ -381,12 +381,13 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
     const size_t dyn_smem = c->use_filter ? (size_t)KJ_STAGE_BYTES : 0;
     if (dyn_smem) KJ_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     int occ = 0;
-    KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KJ_THREADS, dyn_smem));
+    const int threads = c->use_filter ? KJ_FTHREADS : KJ_THREADS;   // filter kernel: 8 stream + 2 emit warps
+    KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, dyn_smem));
     // persistent CTAs: a whole number of CTAs per SM, all resident (tiles are handed out by ticket and
     // a tile waits for the aggregates of the tiles before it)
     const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * std::max(occ, 1));
     if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    KJ_LAUNCH(fn, grid, KJ_THREADS, dyn_smem, ctx->stream, a);
+    KJ_LAUNCH(fn, grid, threads, dyn_smem, ctx->stream, a);
     if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches++;
     KJ_CUDA(ctx, cudaGetLastError());

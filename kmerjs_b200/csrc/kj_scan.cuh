@@ -27,7 +27,10 @@
 #define KJ_CPT (KJ_TILE_CHUNKS / KJ_THREADS)             // 8 chunks per thread
 #define KJ_ROWS (KJ_TILE_CHUNKS / 32)                    // 64 rows of 512 bytes (one warp-wide load)
 #define KJ_QCAP 1536                                     // line queue entries (line kernel: <= 1024 per round)
-#define KJ_FQCAP 512                                     // candidate queue entries (filter kernel: ~64 per tile)
+#define KJ_FQCAP 256                                     // candidate queue entries per slot (filter kernel: ~64 per tile)
+#define KJ_ETHREADS 64                                   // emit warps of the filter kernel (verify + count)
+#define KJ_FTHREADS (KJ_THREADS + KJ_ETHREADS)           // 8 stream warps + 2 emit warps
+#define KJ_NO_TILE 0xFFFFFFFFu
 #define KJ_STAGE_BYTES (KJ_TILE_BYTES + 32)              // a tile and the 32 bytes its last windows reach into
 #define KJ_MAX_MP 8                                      // filter symbols used in code space
 
@@ -137,16 +140,29 @@ __device__ __forceinline__ unsigned long long kj_line_start(const KjScanArgs &a,
 // ----------------------------------------------------------------------------- P1 + look-back
 
 // ---- asynchronous bulk copy global -> shared (TMA engine; SASS UBLKCP) completing on an mbarrier
-#ifdef KJ_CPU_EMU   // tools/cuemu: the copy happens at issue time
-__device__ __forceinline__ void kj_bar_init(uint64_t *, uint32_t) {}
-__device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ void kj_bar_wait(uint64_t *, uint32_t) {}
+#ifdef KJ_CPU_EMU   // tools/cuemu: mbarrier = {pending:16, count:16, phase:1}; the bulk copy happens at issue time
+__device__ __forceinline__ void kj_bar_init(uint64_t *bar, uint32_t count) { *bar = (uint64_t)count | ((uint64_t)count << 16); }
+__device__ __forceinline__ void kj_bar_arrive(uint64_t *bar) {
+    uint64_t v = *bar;
+    uint32_t pending = (uint32_t)(v & 0xFFFF) - 1, count = (uint32_t)((v >> 16) & 0xFFFF), phase = (uint32_t)(v >> 32);
+    if (pending == 0) { pending = count; phase ^= 1u; }
+    *bar = (uint64_t)pending | ((uint64_t)count << 16) | ((uint64_t)phase << 32);
+}
+__device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    memcpy(dst, src, bytes);
+    kj_bar_arrive(bar);
+}
+__device__ __forceinline__ void kj_bar_wait(uint64_t *bar, uint32_t parity) {
+    while ((uint32_t)(*reinterpret_cast<volatile uint64_t *>(bar) >> 32) == parity) emu_yield();
+}
+__device__ __forceinline__ void kj_sync_stream() { emu_named_barrier(1, 256); }
 #else
 __device__ __forceinline__ uint32_t kj_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void kj_bar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kj_smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void kj_bar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(kj_smem_u32(bar)) : "memory");
 }
 // one thread: announce `bytes` on the barrier, then start the copy (src, dst 16-byte aligned, bytes % 16 == 0)
 __device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -154,6 +170,7 @@ __device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(kj_smem_u32(dst)), "l"(src), "r"(bytes), "r"(kj_smem_u32(bar)) : "memory");
 }
+// returns once the phase with parity `parity` has completed
 __device__ __forceinline__ void kj_bar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok = 0;
     const uint32_t addr = kj_smem_u32(bar);
@@ -161,6 +178,8 @@ __device__ __forceinline__ void kj_bar_wait(uint64_t *bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
 }
+// barrier of the 8 stream warps of the filter kernel (the emit warps do not take part)
+__device__ __forceinline__ void kj_sync_stream() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 #endif
 
 // one 16-byte chunk -> code word, newline mask, row count (warp = 32 consecutive chunks = one row)
@@ -173,7 +192,7 @@ __device__ __forceinline__ void kj_p1_chunk(uint32_t *codes, KjTileSmem &s, uint
     if ((threadIdx.x & 31) == 0) s.row_pre[row] = rc;
 }
 
-// P1 from the staged tile (interior tiles: every byte owned, halo readable).  Ends with a barrier.
+// P1 from the staged tile (interior tiles: every byte owned, halo readable).  The caller synchronises.
 __device__ __forceinline__ void kj_tile_p1_stage(uint32_t *codes, KjTileSmem &s, const uint8_t *stage) {
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
 #pragma unroll
@@ -186,11 +205,10 @@ __device__ __forceinline__ void kj_tile_p1_stage(uint32_t *codes, KjTileSmem &s,
         const uint4 h = *reinterpret_cast<const uint4 *>(stage + (KJ_TILE_CHUNKS + tid) * 16u);
         codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
     }
-    __syncthreads();
 }
 
 // P1 straight from global memory.  INTERIOR: the tile and its 32-byte code halo lie inside the
-// owned range, no per-chunk bounds work.  Ends with a barrier.
+// owned range, no per-chunk bounds work.  The caller synchronises.
 template <bool INTERIOR>
 __device__ __forceinline__ void kj_tile_p1_global(const KjScanArgs &a, uint32_t *codes, KjTileSmem &s, uint32_t tile) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -227,7 +245,6 @@ __device__ __forceinline__ void kj_tile_p1_global(const KjScanArgs &a, uint32_t 
         const uint4 h = (off < a.n) ? kj_load_chunk(a.buf, off, a.n) : make_uint4(0, 0, 0, 0);
         codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
     }
-    __syncthreads();
 }
 
 // Warp 0 turns the row counts into exclusive prefixes and publishes the tile's aggregate.
@@ -296,11 +313,10 @@ __device__ __forceinline__ void kj_lookback(const KjScanArgs &a, KjTileSmem &s, 
 // subtracts offset + 1.  The sums telescope over tiles and launches; the host adds the two ends
 // of the stream (kj_counts_finish).  Optional (KJ_F_COUNT_BASES): it is a statistic the reference
 // does not have, and it costs about as much as the prefix search itself.
-__device__ __forceinline__ long long kj_tile_bases(const KjTileSmem &s, uint64_t tile_voff) {
+__device__ __forceinline__ long long kj_tile_bases(const KjTileSmem &s, uint64_t tile_voff, uint32_t t, uint32_t nthreads) {
     long long sum = 0;
 #pragma unroll 1
-    for (int it = 0; it < KJ_CPT; ++it) {
-        const uint32_t c = it * KJ_THREADS + threadIdx.x;
+    for (uint32_t c = t; c < KJ_TILE_CHUNKS; c += nthreads) {
         uint32_t mk = s.nl[c];
         if (!mk) continue;
         uint32_t line = (uint32_t)s.excl_count + kj_count_before(s, c * 16u);    // mod 4 is all that matters
@@ -460,26 +476,28 @@ __device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32
     }
 }
 
-// The filter kernel, software-pipelined over tiles.  While tile `cur` is searched, verified and
-// counted, the bytes of tile `nxt` arrive in `stage` through the TMA engine (cp.async.bulk +
-// mbarrier); `nxt` is converted to code words and its newline aggregate is published BEFORE `cur`
-// is finished, so the look-back of the tiles behind it does not wait for this CTA:
+// The filter kernel: warp-specialised and software-pipelined over tiles.
 //
-//   search(cur) | convert(nxt), take ticket, start copy(nxt+1) | warp 0: aggregate(nxt), look-back(cur) | verify+count(cur)
+//   8 stream warps  search(cur) | convert(nxt), take ticket, start copy(nxt+1) | warp 0: aggregate(nxt), look-back(cur)
+//   2 emit warps    verify + count the candidates of the tile handed over last (latency bound: L2
+//                   round trips of the byte check and of the hash table), overlapped with the above
 //
-// Shared memory: code words (one tile), two KjTileSmem (cur / nxt), candidate queue, stage (dynamic).
+// The bytes of a tile arrive in `stage` through the TMA engine (cp.async.bulk + mbarrier) while the
+// tile before it is searched.  A tile is converted to code words and its newline aggregate is
+// published BEFORE the current one is finished, so the look-back of the tiles behind it does not
+// wait for this CTA.  Stream -> emit hand-over: two slots {KjTileSmem, candidate queue} with a
+// full / empty mbarrier pair each.
 template <int MP, int RC>
-__global__ void __launch_bounds__(KJ_THREADS)
+__global__ void __launch_bounds__(KJ_FTHREADS, 4)
 kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ uint32_t codes[KJ_TILE_CHUNKS + 2];              // +2 halo words: windows reach k-1 bytes past the tile
     __shared__ KjTileSmem meta[2];
-    __shared__ uint32_t queue[KJ_FQCAP];
+    __shared__ uint32_t queue[2][KJ_FQCAP];
+    __shared__ uint32_t tile_of[2];                             // tile in the slot (KJ_NO_TILE: no more work)
     __shared__ uint32_t tile_next;                              // ticket fetched ahead
-    __shared__ __align__(8) uint64_t bar;                       // completion barrier of the copy in flight
+    __shared__ __align__(8) uint64_t bar_load, bar_full[2], bar_empty[2];
     KJ_DYN_SMEM(stage);                                         // KJ_STAGE_BYTES: raw bytes of the tile in flight
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    uint32_t n_emit = 0, ph = 0;
-    long long n_bases = 0;
     // a tile travels through `stage` when it and the 32 bytes behind it are owned and readable
     const bool any_staged = a.own_n >= KJ_STAGE_BYTES;
     const uint64_t staged_end = any_staged ? a.own_n - KJ_STAGE_BYTES : 0;      // staged iff tile_off <= staged_end
@@ -488,80 +506,124 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
         const uint32_t t = atomicAdd(&a.ctr->ticket, 1u);
         tile_next = t;
         const uint64_t off = (uint64_t)t * KJ_TILE_BYTES;
-        if (t < a.n_tiles && any_staged && off <= staged_end) kj_bulk_g2s(stage, a.buf + off, KJ_STAGE_BYTES, &bar);
+        if (t < a.n_tiles && any_staged && off <= staged_end) kj_bulk_g2s(stage, a.buf + off, KJ_STAGE_BYTES, &bar_load);
     };
-    auto convert = [&](uint32_t tile, KjTileSmem &m) {   // P1; ends with a barrier
+
+    if (tid == 0) {
+        kj_bar_init(&bar_load, 1);
+        kj_bar_init(&bar_full[0], 1); kj_bar_init(&bar_full[1], 1);
+        kj_bar_init(&bar_empty[0], KJ_ETHREADS); kj_bar_init(&bar_empty[1], KJ_ETHREADS);
+#if defined(__CUDA_ARCH__)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+        take_ticket();
+    }
+    __syncthreads();
+
+    if (tid >= KJ_THREADS) {
+        // ------------------------------------------------------------------ emit warps
+        const uint32_t et = tid - KJ_THREADS;
+        uint32_t n_emit = 0, phf0 = 0, phf1 = 0, b = 0;
+        long long n_bases = 0;
+        for (;;) {
+            if (b == 0) { kj_bar_wait(&bar_full[0], phf0); phf0 ^= 1u; }
+            else        { kj_bar_wait(&bar_full[1], phf1); phf1 ^= 1u; }
+            const uint32_t tile = tile_of[b];
+            if (tile == KJ_NO_TILE) break;
+            const KjTileSmem &m = meta[b];
+            const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
+            const uint64_t tile_voff = a.voff + tile_off;
+            const uint32_t own_in_tile =
+                (a.own_n - tile_off < KJ_TILE_BYTES) ? (uint32_t)(a.own_n - tile_off) : KJ_TILE_BYTES;
+            if (a.count_bases) n_bases += kj_tile_bases(m, tile_voff, et, KJ_ETHREADS);
+            const uint32_t qn = m.q_n;
+            if (qn <= KJ_FQCAP) {
+                // candidates sit densely in the lanes: a warp with one busy lane costs as much as a full one
+                for (uint32_t q = et; q < qn; q += KJ_ETHREADS) {
+                    const uint32_t e = queue[b][q];
+                    kj_verify_candidate(a, m, tile_off, tile_voff, e >> 1, e & 1u, n_emit);
+                }
+            } else {
+                // dense candidates (e.g. homopolymer input): the code words are gone by now, so every
+                // owned position takes the exact check
+                for (uint32_t jt = et; jt < own_in_tile; jt += KJ_ETHREADS) {
+                    kj_verify_candidate(a, m, tile_off, tile_voff, jt, 0u, n_emit);
+                    if (a.n_strands > 1) kj_verify_candidate(a, m, tile_off, tile_voff, jt, 1u, n_emit);
+                }
+            }
+            kj_bar_arrive(&bar_empty[b]);
+            b ^= 1u;
+        }
+        for (int d = 16; d > 0; d >>= 1) {       // one atomic per warp
+            n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
+            n_bases += __shfl_xor_sync(0xFFFFFFFFu, n_bases, d);
+        }
+        if ((tid & 31) == 0) {
+            if (n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);
+            if (n_bases) atomicAdd(&a.ctr->n_bases, (unsigned long long)n_bases);
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- stream warps
+    uint32_t ph_load = 0, phe0 = 0, phe1 = 0;       // phase parities: copy in flight, slot-empty barriers
+    uint32_t handed = 0;                            // bit s: slot s has been handed to the emit warps before
+    auto wait_slot_free = [&](uint32_t sl) {
+        if (handed & (1u << sl)) {
+            if (sl == 0) { kj_bar_wait(&bar_empty[0], phe0); phe0 ^= 1u; }
+            else         { kj_bar_wait(&bar_empty[1], phe1); phe1 ^= 1u; }
+        }
+    };
+    auto convert = [&](uint32_t tile, KjTileSmem &m) {   // P1 of `tile` into codes / m
         if (tid == 0) m.q_n = 0;
         const uint64_t off = (uint64_t)tile * KJ_TILE_BYTES;
         if (any_staged && off <= staged_end) {
-            kj_bar_wait(&bar, ph);
-            ph ^= 1u;
+            kj_bar_wait(&bar_load, ph_load);
+            ph_load ^= 1u;
             kj_tile_p1_stage(codes, m, stage);
         } else {
             kj_tile_p1_global<false>(a, codes, m, tile);
         }
     };
 
-    if (tid == 0) { kj_bar_init(&bar, 1); take_ticket(); }
-    __syncthreads();
     uint32_t cur = tile_next, b = 0;
     if (cur < a.n_tiles) {
         convert(cur, meta[0]);
+        kj_sync_stream();
         if (tid == 32) take_ticket();
         if (warp == 0) kj_tile_rowscan_warp0(a, meta[0], cur);
         for (;;) {
-            __syncthreads();                               // aggregate of cur, ticket of nxt visible; queue free
+            kj_sync_stream();                              // aggregate of cur and the next ticket are visible
             const uint32_t nxt = tile_next;
             KjTileSmem &m = meta[b];
             const uint64_t tile_off = (uint64_t)cur * KJ_TILE_BYTES;
-            const uint64_t tile_voff = a.voff + tile_off;
             const uint32_t own_in_tile =
                 (a.own_n - tile_off < KJ_TILE_BYTES) ? (uint32_t)(a.own_n - tile_off) : KJ_TILE_BYTES;
 
-            kj_tile_search<MP, RC>(a, codes, m, queue, own_in_tile);
-            __syncthreads();                               // code words of cur no longer needed
+            kj_tile_search<MP, RC>(a, codes, m, queue[b], own_in_tile);
+            kj_sync_stream();                              // code words of cur no longer needed; queue complete
             if (nxt < a.n_tiles) {
-                convert(nxt, meta[b ^ 1]);
+                wait_slot_free(b ^ 1u);                    // the emit warps are done with the tile before cur
+                convert(nxt, meta[b ^ 1u]);
+                kj_sync_stream();
                 if (tid == 32) take_ticket();              // `stage` is free again
             }
             if (warp == 0) {
-                if (nxt < a.n_tiles) kj_tile_rowscan_warp0(a, meta[b ^ 1], nxt);
+                if (nxt < a.n_tiles) kj_tile_rowscan_warp0(a, meta[b ^ 1u], nxt);
                 kj_lookback(a, m, cur);                    // the tiles in front published long ago
+                __syncwarp();
+                if (tid == 0) { tile_of[b] = cur; kj_bar_arrive(&bar_full[b]); }    // hand cur to the emit warps
             }
-            __syncthreads();
-
-            if (a.count_bases) n_bases += kj_tile_bases(m, tile_voff);
-
-            // verify + insert.  Candidates sit densely in the first warps: the kernel is bound by
-            // instruction issue, and a warp with one busy lane costs as much as a full one.
-            const uint32_t qn = m.q_n;
-            if (qn <= KJ_FQCAP) {
-                for (uint32_t q = tid; q < qn; q += KJ_THREADS) {
-                    const uint32_t e = queue[q];
-                    kj_verify_candidate(a, m, tile_off, tile_voff, e >> 1, e & 1u, n_emit);
-                }
-            } else {
-                // dense candidates (e.g. homopolymer input): walk every owned position; the code words are
-                // gone by now, so every position is a candidate for the exact check
-                for (uint32_t jt = tid; jt < own_in_tile; jt += KJ_THREADS) {
-                    kj_verify_candidate(a, m, tile_off, tile_voff, jt, 0u, n_emit);
-                    if (a.n_strands > 1) kj_verify_candidate(a, m, tile_off, tile_voff, jt, 1u, n_emit);
-                }
-            }
+            handed |= 1u << b;
             if (nxt >= a.n_tiles) break;
             cur = nxt;
             b ^= 1u;
         }
+        b ^= 1u;                                           // the slot after the last tile carries the stop mark
     }
-    // one atomic per warp
-    for (int d = 16; d > 0; d >>= 1) {
-        n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
-        n_bases += __shfl_xor_sync(0xFFFFFFFFu, n_bases, d);
-    }
-    if ((tid & 31) == 0) {
-        if (n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);
-        if (n_bases) atomicAdd(&a.ctr->n_bases, (unsigned long long)n_bases);
-    }
+    wait_slot_free(b);
+    if (tid == 0) { tile_of[b] = KJ_NO_TILE; kj_bar_arrive(&bar_full[b]); }
 }
 
 // ----------------------------------------------------------------------------- line-oriented kernel
@@ -644,6 +706,7 @@ kj_scan_lines_kernel(const __grid_constant__ KjScanArgs a) {
         const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
 
         kj_tile_p1_global<false>(a, codes, s, tile);
+        __syncthreads();
         if (warp == 0) { kj_tile_rowscan_warp0(a, s, tile); kj_lookback(a, s, tile); }
         __syncthreads();
 

@@ -92,6 +92,19 @@ void emu_syncthreads() {
     while (g_block_gen == gen) { spin_guard(); emu_yield(); }
 }
 
+namespace { struct NamedBar { int count = 0; unsigned gen = 0; }; NamedBar g_named[16]; }
+void emu_named_barrier(int id, int expected) {
+    NamedBar &b = g_named[id & 15];
+    if (++b.count == expected) {
+        b.count = 0;
+        ++b.gen;
+        g_idle_spins = 0;
+        return;
+    }
+    unsigned gen = b.gen;
+    while (b.gen == gen) { spin_guard(); emu_yield(); }
+}
+
 unsigned emu_lane() { return threadIdx.x & 31u; }
 
 static int warp_size_of(unsigned w) {
@@ -193,6 +206,7 @@ void emu_launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void
     for (unsigned bx = 0; bx < grid.x; ++bx) {
         g_block_count = 0;
         for (auto &w : g_warps) { w.count = 0; }
+        for (auto &nb : g_named) { nb.count = 0; }
         for (int t = 0; t < nthreads; ++t) {
             Fiber &f = g_fibers[t];
             f.done = false;

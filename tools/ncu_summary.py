@@ -31,13 +31,13 @@ cur, h = None, None
 inst, smp, stall = collections.Counter(), collections.Counter(), collections.Counter()
 by_line_i, by_line_s, text = collections.Counter(), collections.Counter(), {}
 kernels = 0
+seen_files = set()
 for r in rows:
-    if len(r) == 2 and r[0] == "Function Name":
-        kernels += 1
-    if kernels > 1:
-        break
     if len(r) == 2 and r[0] == "File Path":
         cur = r[1].split("/")[-1]
+        if cur in seen_files:
+            break               # second kernel instance: same files again
+        seen_files.add(cur)
         continue
     if len(r) > 5 and r[0] == "Line No":
         h = r

@@ -53,6 +53,42 @@ KJ_HD uint32_t kj_nl16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     return kj_nl4(w0) | (kj_nl4(w1) << 4) | (kj_nl4(w2) << 8) | (kj_nl4(w3) << 12);
 }
 
+// 4 bytes -> nonzero iff some byte is not one of 'A','C','G','T' (upper case).  The 2-bit code of
+// every byte selects the letter that has this code from the table word "ACTG" (one PRMT); a byte
+// is a base iff it equals that letter.
+KJ_HD uint32_t kj_not_acgt4(uint32_t w) {
+    const uint32_t c = (w >> 1) & 0x03030303u;            // code of byte i in bits 8i..8i+1
+    const uint32_t t = c | (c >> 4);                      // byte 0: c0 | c1 << 4, byte 2: c2 | c3 << 4
+#if defined(__CUDA_ARCH__)
+    const uint32_t sel = __byte_perm(t, 0u, 0x4420u);     // selector nibbles c0, c1, c2, c3
+    const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);   // table bytes: 'A','C','T','G' for codes 0..3
+#else
+    const uint32_t sel = (t & 0xFFu) | ((t >> 8) & 0xFF00u);
+    const uint32_t tab = 0x47544341u;
+    uint32_t expect = 0;
+    for (int i = 0; i < 4; ++i) expect |= ((tab >> (8u * ((sel >> (4 * i)) & 3u))) & 0xFFu) << (8 * i);
+#endif
+    return w ^ expect;
+}
+
+// 4 bytes -> msb of byte i set iff byte i == '\n'
+KJ_HD uint32_t kj_nl_msb4(uint32_t w) {
+    const uint32_t t = ((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | w) & 0x80808080u;
+}
+
+// reverse the order of the 32 two-bit fields of a 64-bit word
+KJ_HD uint64_t kj_pairrev64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t lo = __brev((uint32_t)(x >> 32)), hi = __brev((uint32_t)x);
+#else
+    uint32_t a = (uint32_t)(x >> 32), b = (uint32_t)x, lo = 0, hi = 0;
+    for (int i = 0; i < 32; ++i) { if (a >> i & 1) lo |= 1u << (31 - i); if (b >> i & 1) hi |= 1u << (31 - i); }
+#endif
+    const uint64_t r = ((uint64_t)hi << 32) | lo;          // all 64 bits reversed: fields reversed, bits inside swapped
+    return ((r & 0x5555555555555555ull) << 1) | ((r >> 1) & 0x5555555555555555ull);
+}
+
 // low 32 bits of (hi:lo) >> s, 0 <= s < 32
 KJ_HD uint32_t kj_funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
 #if defined(__CUDA_ARCH__)

@@ -355,6 +355,18 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
         memcpy(a.prefix, c->prefix.data(), std::min<size_t>(32, m));
         memcpy(a.rprefix, c->rprefix.data(), std::min<size_t>(32, m));
     }
+    {   // byte-exact window check of the filter kernel: wanted bytes and their mask, per strand
+        uint8_t want[2][32], mask[2][32];
+        memset(want, 0, sizeof(want)); memset(mask, 0, sizeof(mask));
+        if (m <= c->k && c->k <= 32) {
+            for (uint32_t i = 0; i < m; ++i) {
+                want[0][i] = c->prefix[i]; mask[0][i] = 0xFF;
+                want[1][c->k - m + i] = c->rprefix[i]; mask[1][c->k - m + i] = 0xFF;
+            }
+        }
+        memcpy(a.want, want, sizeof(want));
+        memcpy(a.wmask, mask, sizeof(mask));
+    }
     a.tab = c->tab; a.irr = c->irr; a.ovf = c->ovf; a.ctr = c->ctr;
     a.status = c->tile_mem;
 

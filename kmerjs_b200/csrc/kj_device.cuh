@@ -83,9 +83,9 @@ __device__ __forceinline__ bool kj_insert(const KjTable &t, KjCounters *ctr, uin
             }
         }
         if (cur == key) {
+            // results unused: both become fire-and-forget reductions (RED), nothing waits on them
             atomicAdd((unsigned long long *)&t.counts[slot], (unsigned long long)add);
-            if (t.ords && kj_ld_volatile(&t.ords[slot]) > ord)
-                atomicMin((unsigned long long *)&t.ords[slot], (unsigned long long)ord);
+            if (t.ords) atomicMin((unsigned long long *)&t.ords[slot], (unsigned long long)ord);
             return true;
         }
         slot = (slot + 1) & t.mask;

@@ -62,6 +62,10 @@ struct KjScanArgs {
     uint32_t pat_r[KJ_MAX_MP];   // code of complement(prefix)[i], replicated
     uint8_t prefix[32];
     uint8_t rprefix[32];  // complement(prefix) (reverse complement as bytes, lib/kmers.js:31-38)
+    // exact byte check of a window held in 8 words: (window ^ want[strand]) & mask[strand] must be 0
+    // (strand 0: prefix at the start of the window, strand 1: complement(prefix) at its end)
+    uint32_t want[2][8];
+    uint32_t wmask[2][8];
     KjTable tab;
     KjIrrTable irr;
     KjOverflow ovf;
@@ -93,8 +97,8 @@ __device__ __forceinline__ uint4 kj_load_chunk(const uint8_t *buf, uint64_t off,
 
 // per-tile state that outlives the code words: the filter kernel keeps two of these, so that the
 // next tile can be converted (and its aggregate published) before the current one is finished
-struct KjTileSmem {
-    uint16_t nl[KJ_TILE_CHUNKS];          // '\n' mask of the chunk
+struct __align__(16) KjTileSmem {
+    uint16_t nl[KJ_TILE_CHUNKS];          // '\n' mask of the chunk: together a bitmap of the tile, bit p = byte p
     uint32_t row_pre[KJ_ROWS];            // row counts, then exclusive prefix over the tile
     uint32_t q_n;                         // entries in the kernel's candidate / line queue
     uint32_t tile_count;                  // '\n' in the tile
@@ -365,44 +369,83 @@ static __device__ __noinline__ void kj_emit_irregular(const KjScanArgs &a, uint6
     if (!kj_insert_irr(a.irr, a.ctr, key32, len, ord, 1)) kj_spill_irr(a, off, len, strand, ord);
 }
 
-// Filter-kernel candidate: window start at tile-relative jt (step == 1, 1 <= m <= k).
+// The 512-bit newline bitmap of the row (32 chunks) that holds tile position jt, as 16 words.
+struct KjRowBits { uint32_t w[16]; };
+__device__ __forceinline__ KjRowBits kj_row_bits(const KjTileSmem &s, uint32_t jt) {
+    const uint4 *rp = reinterpret_cast<const uint4 *>(&s.nl[(jt >> 9) * 32u]);
+    KjRowBits r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 v = rp[i];
+        r.w[4 * i] = v.x; r.w[4 * i + 1] = v.y; r.w[4 * i + 2] = v.z; r.w[4 * i + 3] = v.w;
+    }
+    return r;
+}
+
+// Filter-kernel candidate: window start at tile-relative jt (step == 1, 1 <= m <= k, jt inside the
+// tile).  Straight-line SIMD-in-register code: the emit warps run a chain of dependent work per
+// candidate, so instruction count and round trips on that chain set their pace.
 __device__ __forceinline__ void kj_verify_candidate(const KjScanArgs &a, const KjTileSmem &s,
                                                     uint64_t tile_off, uint64_t tile_voff,
                                                     uint32_t jt, uint32_t strand,
                                                     uint32_t &n_emit) {
     const uint64_t j = tile_off + jt;
-    const uint32_t k = a.k, m = a.m;
+    const uint32_t k = a.k;
     if (j + k > a.n) return;                              // window must lie inside the stream
-    const uint64_t line = s.excl_count + kj_count_before(s, jt);
-    if ((line & 3ull) != 1ull) return;                    // lib/kmers.js:151  i === 1
-    // the window's bytes: at most three aligned 16-byte chunks, fetched together (they were read
-    // a moment ago, so these are L2 hits) instead of k dependent byte loads
+    // the window's bytes: at most three aligned 16-byte chunks, requested together (they were read a
+    // moment ago: L2 hits) before the line phase is worked out from shared memory
     const uint32_t o = (uint32_t)(j & 15u);
     const uint64_t base = j - o;
-    uint32_t w[12];
+    uint4 v0 = kj_load_chunk(a.buf, base, a.n), v1 = make_uint4(0, 0, 0, 0), v2 = make_uint4(0, 0, 0, 0);
+    if (base + 16u < j + k) v1 = kj_load_chunk(a.buf, base + 16u, a.n);
+    if (base + 32u < j + k) v2 = kj_load_chunk(a.buf, base + 32u, a.n);
+
+    // newlines of the tile before jt: prefix of the row + bitmap words of the row below jt
+    const KjRowBits rb = kj_row_bits(s, jt);
+    const uint32_t p = jt & 511u, pw = p >> 5;
+    const uint32_t part = (1u << (p & 31u)) - 1u;
+    uint32_t before = s.row_pre[jt >> 9];
+    uint32_t last_w = 0, last_i = 0;                      // highest bitmap word with a '\n' below jt
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (base + 16u * t < j + k) v = kj_load_chunk(a.buf, base + 16u * t, a.n);
-        w[4 * t] = v.x; w[4 * t + 1] = v.y; w[4 * t + 2] = v.z; w[4 * t + 3] = v.w;
+    for (uint32_t i = 0; i < 16; ++i) {
+        const uint32_t x = rb.w[i] & (i < pw ? 0xFFFFFFFFu : (i == pw ? part : 0u));
+        before += __popc(x);
+        if (x) { last_w = x; last_i = i; }
     }
-    uint64_t fk = 0, rk = 0;
-    bool regular = true;
-    const uint32_t rc0 = k - m;
-    for (uint32_t i = 0; i < k; ++i) {
-        const uint32_t p = o + i;
-        const uint32_t c = (w[p >> 2] >> (8u * (p & 3u))) & 0xFFu;
-        if (c == '\n') return;                            // window crosses the end of the line
-        if (strand == 0) { if (i < m && c != a.prefix[i]) return; }
-        else             { if (i >= rc0 && c != a.rprefix[i - rc0]) return; }
-        regular = regular && kj_is_acgt(c);
-        const uint64_t code = (c >> 1) & 3u;
-        fk = (fk << 2) | code;
-        rk = (rk >> 2) | ((code ^ 2ull) << (2 * (k - 1)));
+    const uint64_t line = s.excl_count + before;
+    if ((line & 3ull) != 1ull) return;                    // lib/kmers.js:151  i === 1
+
+    // window bytes 0..31 in X[0..7]: shift the 48 loaded bytes down by o
+    const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+    const uint32_t q = o >> 2, r8 = (o & 3u) * 8u;
+    uint32_t X[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t lo = q == 0 ? W[i] : q == 1 ? W[i + 1] : q == 2 ? W[i + 2] : W[i + 3];
+        const uint32_t hi = q == 0 ? W[i + 1] : q == 1 ? W[i + 2] : q == 2 ? W[i + 3] : W[i + 4];
+        X[i] = kj_funnel_r(lo, hi, r8);
     }
+    uint32_t bad = 0, nl = 0, irr = 0, p_lo = 0, p_hi = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (4u * i < k) {
+            const uint32_t bm = (4u * i + 4u <= k) ? 0xFFFFFFFFu : ((1u << (8u * (k - 4u * i))) - 1u);   // bytes of the window
+            bad |= (X[i] ^ a.want[strand][i]) & a.wmask[strand][i];
+            nl |= kj_nl_msb4(X[i]) & bm;
+            irr |= kj_not_acgt4(X[i]) & bm;
+            const uint32_t c8 = kj_pack4(X[i] & bm);
+            if (i < 4) p_lo |= c8 << (8 * i); else p_hi |= c8 << (8 * (i - 4));
+        }
+    }
+    if (nl | bad) return;                                 // crosses the end of the line / prefix bytes differ
+    const uint64_t P = ((uint64_t)p_hi << 32) | p_lo;     // code of window byte i at bits 2i
+    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
     uint64_t ord = 0;
     if (a.order || k == 1) {
-        const unsigned long long start = kj_line_start(a, s, jt, tile_off, tile_voff);
+        // first byte of the line: the last '\n' below jt in this row, else further back
+        unsigned long long start;
+        if (last_w) start = tile_voff + (jt & ~511u) + last_i * 32u + (31u - __clz(last_w)) + 1ull;
+        else start = kj_line_start(a, s, jt & ~511u, tile_off, tile_voff);
         const uint64_t col = tile_voff + jt - start;
         if (k == 1 && col == 0 && a.line_gate) {          // lib/kmers.js:151  line.length > 1
             const bool more = (j + 1 < a.n) && a.buf[j + 1] != '\n';
@@ -415,8 +458,9 @@ __device__ __forceinline__ void kj_verify_candidate(const KjScanArgs &a, const K
         ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
     }
     ++n_emit;
-    if (regular) {
-        const uint64_t key = strand ? rk : fk;
+    if (!irr) {
+        // forward key: first base most significant; reverse key: complement codes, last base first
+        const uint64_t key = strand ? ((P ^ 0xAAAAAAAAAAAAAAAAull) & kmask) : (kj_pairrev64(P) >> (64u - 2u * k));
         if (!kj_insert(a.tab, a.ctr, key, ord, 1)) kj_spill(a, key, ord);
     } else {
         kj_emit_irregular(a, j, k, strand, ord);

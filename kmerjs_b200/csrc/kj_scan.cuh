@@ -31,6 +31,7 @@
 #define KJ_ETHREADS 64                                   // emit warps of the filter kernel (verify + count)
 #define KJ_FTHREADS (KJ_THREADS + KJ_ETHREADS)           // 8 stream warps + 2 emit warps
 #define KJ_NO_TILE 0xFFFFFFFFu
+#define KJ_SLOTS 3                                       // stream -> emit hand-over slots
 #define KJ_STAGE_BYTES (KJ_TILE_BYTES + 32)              // a tile and the 32 bytes its last windows reach into
 #define KJ_MAX_MP 8                                      // filter symbols used in code space
 
@@ -494,7 +495,7 @@ __device__ __forceinline__ void kj_chunk_filter(const KjScanArgs &a, const uint3
 
 // P2 of one tile: bit-parallel prefix search in code space; candidates -> queue
 template <int MP, int RC>
-__device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32_t *codes, KjTileSmem &s, uint32_t *queue,
+__device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32_t *codes, KjTileSmem &s, uint16_t *queue,
                                                uint32_t own_in_tile) {
     const uint32_t tid = threadIdx.x;
 #pragma unroll
@@ -515,7 +516,7 @@ __device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32
             z &= z - 1;
             const uint32_t jt = pos0 + (bit >> 1);
             const uint32_t q = atomicAdd(&s.q_n, 1u);
-            if (q < KJ_FQCAP) queue[q] = (jt << 1) | strand;
+            if (q < KJ_FQCAP) queue[q] = (uint16_t)((jt << 1) | strand);
         }
     }
 }
@@ -535,11 +536,11 @@ template <int MP, int RC>
 __global__ void __launch_bounds__(KJ_FTHREADS, 4)
 kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ uint32_t codes[KJ_TILE_CHUNKS + 2];              // +2 halo words: windows reach k-1 bytes past the tile
-    __shared__ KjTileSmem meta[2];
-    __shared__ uint32_t queue[2][KJ_FQCAP];
-    __shared__ uint32_t tile_of[2];                             // tile in the slot (KJ_NO_TILE: no more work)
+    __shared__ KjTileSmem meta[KJ_SLOTS];
+    __shared__ uint16_t queue[KJ_SLOTS][KJ_FQCAP];              // candidates: tile position << 1 | strand
+    __shared__ uint32_t tile_of[KJ_SLOTS];                      // tile in the slot (KJ_NO_TILE: no more work)
     __shared__ uint32_t tile_next;                              // ticket fetched ahead
-    __shared__ __align__(8) uint64_t bar_load, bar_full[2], bar_empty[2];
+    __shared__ __align__(8) uint64_t bar_load, bar_full[KJ_SLOTS], bar_empty[KJ_SLOTS];
     KJ_DYN_SMEM(stage);                                         // KJ_STAGE_BYTES: raw bytes of the tile in flight
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     // a tile travels through `stage` when it and the 32 bytes behind it are owned and readable
@@ -555,8 +556,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
 
     if (tid == 0) {
         kj_bar_init(&bar_load, 1);
-        kj_bar_init(&bar_full[0], 1); kj_bar_init(&bar_full[1], 1);
-        kj_bar_init(&bar_empty[0], KJ_ETHREADS); kj_bar_init(&bar_empty[1], KJ_ETHREADS);
+        for (int i = 0; i < KJ_SLOTS; ++i) { kj_bar_init(&bar_full[i], 1); kj_bar_init(&bar_empty[i], KJ_ETHREADS); }
 #if defined(__CUDA_ARCH__)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -568,11 +568,11 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     if (tid >= KJ_THREADS) {
         // ------------------------------------------------------------------ emit warps
         const uint32_t et = tid - KJ_THREADS;
-        uint32_t n_emit = 0, phf0 = 0, phf1 = 0, b = 0;
+        uint32_t n_emit = 0, phf = 0, b = 0;           // phf bit s: parity of the next full phase of slot s
         long long n_bases = 0;
         for (;;) {
-            if (b == 0) { kj_bar_wait(&bar_full[0], phf0); phf0 ^= 1u; }
-            else        { kj_bar_wait(&bar_full[1], phf1); phf1 ^= 1u; }
+            kj_bar_wait(&bar_full[b], (phf >> b) & 1u);
+            phf ^= 1u << b;
             const uint32_t tile = tile_of[b];
             if (tile == KJ_NO_TILE) break;
             const KjTileSmem &m = meta[b];
@@ -597,7 +597,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                 }
             }
             kj_bar_arrive(&bar_empty[b]);
-            b ^= 1u;
+            b = (b + 1u == KJ_SLOTS) ? 0u : b + 1u;
         }
         for (int d = 16; d > 0; d >>= 1) {       // one atomic per warp
             n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
@@ -611,14 +611,15 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     }
 
     // ---------------------------------------------------------------------- stream warps
-    uint32_t ph_load = 0, phe0 = 0, phe1 = 0;       // phase parities: copy in flight, slot-empty barriers
+    uint32_t ph_load = 0, phe = 0;                  // phase parities: copy in flight, slot-empty barriers (bit s)
     uint32_t handed = 0;                            // bit s: slot s has been handed to the emit warps before
     auto wait_slot_free = [&](uint32_t sl) {
         if (handed & (1u << sl)) {
-            if (sl == 0) { kj_bar_wait(&bar_empty[0], phe0); phe0 ^= 1u; }
-            else         { kj_bar_wait(&bar_empty[1], phe1); phe1 ^= 1u; }
+            kj_bar_wait(&bar_empty[sl], (phe >> sl) & 1u);
+            phe ^= 1u << sl;
         }
     };
+    auto next_slot = [](uint32_t sl) { return (sl + 1u == KJ_SLOTS) ? 0u : sl + 1u; };
     auto convert = [&](uint32_t tile, KjTileSmem &m) {   // P1 of `tile` into codes / m
         if (tid == 0) m.q_n = 0;
         const uint64_t off = (uint64_t)tile * KJ_TILE_BYTES;
@@ -647,14 +648,15 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
 
             kj_tile_search<MP, RC>(a, codes, m, queue[b], own_in_tile);
             kj_sync_stream();                              // code words of cur no longer needed; queue complete
+            const uint32_t nb = next_slot(b);
             if (nxt < a.n_tiles) {
-                wait_slot_free(b ^ 1u);                    // the emit warps are done with the tile before cur
-                convert(nxt, meta[b ^ 1u]);
+                wait_slot_free(nb);                        // the emit warps may lag KJ_SLOTS - 1 tiles behind
+                convert(nxt, meta[nb]);
                 kj_sync_stream();
                 if (tid == 32) take_ticket();              // `stage` is free again
             }
             if (warp == 0) {
-                if (nxt < a.n_tiles) kj_tile_rowscan_warp0(a, meta[b ^ 1u], nxt);
+                if (nxt < a.n_tiles) kj_tile_rowscan_warp0(a, meta[nb], nxt);
                 kj_lookback(a, m, cur);                    // the tiles in front published long ago
                 __syncwarp();
                 if (tid == 0) { tile_of[b] = cur; kj_bar_arrive(&bar_full[b]); }    // hand cur to the emit warps
@@ -662,9 +664,9 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
             handed |= 1u << b;
             if (nxt >= a.n_tiles) break;
             cur = nxt;
-            b ^= 1u;
+            b = nb;
         }
-        b ^= 1u;                                           // the slot after the last tile carries the stop mark
+        b = next_slot(b);                                  // the slot after the last tile carries the stop mark
     }
     wait_slot_free(b);
     if (tid == 0) { tile_of[b] = KJ_NO_TILE; kj_bar_arrive(&bar_full[b]); }

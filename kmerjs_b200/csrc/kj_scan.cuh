@@ -21,19 +21,22 @@
 #include <stdint.h>
 #include "kj_device.cuh"
 
-#define KJ_TILE_BYTES 32768
-#define KJ_THREADS 256
-#define KJ_TILE_CHUNKS (KJ_TILE_BYTES / 16)              // 2048 16-byte chunks
-#define KJ_CPT (KJ_TILE_CHUNKS / KJ_THREADS)             // 8 chunks per thread
-#define KJ_ROWS (KJ_TILE_CHUNKS / 32)                    // 64 rows of 512 bytes (one warp-wide load)
+#define KJ_TILE_BYTES 28672                              // 56 rows of 512 bytes: 8 chunks for each of 224 stream threads,
+#define KJ_TILE_CHUNKS (KJ_TILE_BYTES / 16)              // 7 for each of the 256 threads of the line kernel
+#define KJ_ROWS (KJ_TILE_CHUNKS / 32)                    // a row = 32 chunks = one warp-wide 16-byte load
+#define KJ_THREADS 256                                   // line kernel
 #define KJ_QCAP 1536                                     // line queue entries (line kernel: <= 1024 per round)
-#define KJ_FQCAP 256                                     // candidate queue entries per slot (filter kernel: ~64 per tile)
-#define KJ_ETHREADS 64                                   // emit warps of the filter kernel (verify + count)
-#define KJ_FTHREADS (KJ_THREADS + KJ_ETHREADS)           // 8 stream warps + 2 emit warps
+#define KJ_MAX_MP 8                                      // filter symbols used in code space
+// filter kernel: warp 0 = control (aggregates, look-back, hand-over), warps 1-7 = stream (convert +
+// search), warps 8-9 = emit (verify + count)
+#define KJ_CTHREADS 32
+#define KJ_STHREADS 224
+#define KJ_ETHREADS 64
+#define KJ_FTHREADS (KJ_CTHREADS + KJ_STHREADS + KJ_ETHREADS)
+#define KJ_FQCAP 256                                     // candidate queue entries per slot (~56 per tile)
+#define KJ_STAGE_BYTES (KJ_TILE_BYTES + 32)              // a tile and the 32 bytes its last windows reach into
 #define KJ_NO_TILE 0xFFFFFFFFu
 #define KJ_SLOTS 3                                       // stream -> emit hand-over slots
-#define KJ_STAGE_BYTES (KJ_TILE_BYTES + 32)              // a tile and the 32 bytes its last windows reach into
-#define KJ_MAX_MP 8                                      // filter symbols used in code space
 
 #define KJ_ST_AGG 1ull
 #define KJ_ST_INC 2ull
@@ -87,13 +90,19 @@ __device__ __forceinline__ uint4 kj_ldg16(const uint8_t *p) {
 #endif
 }
 
-// 16 bytes at p, bytes at or beyond `limit` read as 0
-__device__ __forceinline__ uint4 kj_load_chunk(const uint8_t *buf, uint64_t off, uint64_t limit) {
-    if (off + 16 <= limit) return kj_ldg16(buf + off);
+// 16 bytes at p, bytes at or beyond `limit` read as 0.  The byte-wise tail is kept out of line: it
+// runs for the last chunk of a buffer only, and inlining it at every load site bloats the hot loops
+// past the instruction cache.
+static __device__ __noinline__ uint4 kj_load_chunk_tail(const uint8_t *buf, uint64_t off, uint64_t limit) {
     uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll 1
     for (uint32_t i = 0; i < 16; ++i)
         if (off + i < limit) w[i >> 2] |= (uint32_t)buf[off + i] << (8 * (i & 3));
     return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 kj_load_chunk(const uint8_t *buf, uint64_t off, uint64_t limit) {
+    if (off + 16 <= limit) return kj_ldg16(buf + off);
+    return kj_load_chunk_tail(buf, off, limit);
 }
 
 // per-tile state that outlives the code words: the filter kernel keeps two of these, so that the
@@ -160,7 +169,7 @@ __device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t
 __device__ __forceinline__ void kj_bar_wait(uint64_t *bar, uint32_t parity) {
     while ((uint32_t)(*reinterpret_cast<volatile uint64_t *>(bar) >> 32) == parity) emu_yield();
 }
-__device__ __forceinline__ void kj_sync_stream() { emu_named_barrier(1, 256); }
+__device__ __forceinline__ void kj_sync_stream() { emu_named_barrier(1, KJ_STHREADS); }
 #else
 __device__ __forceinline__ uint32_t kj_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void kj_bar_init(uint64_t *bar, uint32_t count) {
@@ -183,8 +192,8 @@ __device__ __forceinline__ void kj_bar_wait(uint64_t *bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
 }
-// barrier of the 8 stream warps of the filter kernel (the emit warps do not take part)
-__device__ __forceinline__ void kj_sync_stream() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// barrier of the 7 stream warps of the filter kernel (control and emit warps do not take part)
+__device__ __forceinline__ void kj_sync_stream() { asm volatile("bar.sync 1, %0;" ::"n"(KJ_STHREADS) : "memory"); }
 #endif
 
 // one 16-byte chunk -> code word, newline mask, row count (warp = 32 consecutive chunks = one row)
@@ -197,85 +206,72 @@ __device__ __forceinline__ void kj_p1_chunk(uint32_t *codes, KjTileSmem &s, uint
     if ((threadIdx.x & 31) == 0) s.row_pre[row] = rc;
 }
 
-// P1 from the staged tile (interior tiles: every byte owned, halo readable).  The caller synchronises.
-__device__ __forceinline__ void kj_tile_p1_stage(uint32_t *codes, KjTileSmem &s, const uint8_t *stage) {
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
-#pragma unroll
-    for (int it = 0; it < KJ_CPT; ++it) {
-        const uint32_t c = it * KJ_THREADS + tid;
+// P1 from the staged tile (interior tiles: every byte owned, halo readable) by a group of NT threads,
+// t = index in the group.  The caller synchronises.
+template <int NT>
+__device__ __forceinline__ void kj_tile_p1_stage(uint32_t *codes, KjTileSmem &s, const uint8_t *stage, uint32_t t) {
+    constexpr int CPT = KJ_TILE_CHUNKS / NT;
+    static_assert(CPT * NT == KJ_TILE_CHUNKS && NT % 32 == 0, "tile must split evenly into warp rows");
+#pragma unroll 4
+    for (int it = 0; it < CPT; ++it) {
+        const uint32_t c = it * NT + t;
         const uint4 v = *reinterpret_cast<const uint4 *>(stage + c * 16u);
-        kj_p1_chunk(codes, s, c, it * (KJ_THREADS / 32) + warp, v, 0xFFFFu);
+        kj_p1_chunk(codes, s, c, c >> 5, v, 0xFFFFu);
     }
-    if (tid < 2) {
-        const uint4 h = *reinterpret_cast<const uint4 *>(stage + (KJ_TILE_CHUNKS + tid) * 16u);
-        codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
+    if (t < 2) {
+        const uint4 h = *reinterpret_cast<const uint4 *>(stage + (KJ_TILE_CHUNKS + t) * 16u);
+        codes[KJ_TILE_CHUNKS + t] = kj_pack16(h.x, h.y, h.z, h.w);
     }
 }
 
-// P1 straight from global memory.  INTERIOR: the tile and its 32-byte code halo lie inside the
-// owned range, no per-chunk bounds work.  The caller synchronises.
-template <bool INTERIOR>
-__device__ __forceinline__ void kj_tile_p1_global(const KjScanArgs &a, uint32_t *codes, KjTileSmem &s, uint32_t tile) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// P1 straight from global memory (edge tiles of the filter kernel, every tile of the line kernel).
+// Newlines are counted only inside the owned range.  The caller synchronises.
+template <int NT>
+static __device__ __noinline__ void kj_tile_p1_global(const KjScanArgs &a, uint32_t *codes, KjTileSmem &s, uint32_t tile,
+                                                      uint32_t t) {
+    constexpr int CPT = KJ_TILE_CHUNKS / NT;
+    static_assert(CPT * NT == KJ_TILE_CHUNKS && NT % 32 == 0, "tile must split evenly into warp rows");
     const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
-    const uint8_t *tbase = a.buf + tile_off;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        uint4 v[KJ_CPT / 2];
-#pragma unroll
-        for (int j = 0; j < KJ_CPT / 2; ++j) {
-            const uint32_t c = (half * (KJ_CPT / 2) + j) * KJ_THREADS + tid;
-            if (INTERIOR) {
-                v[j] = kj_ldg16(tbase + c * 16u);
-            } else {
-                const uint64_t off = tile_off + (uint64_t)c * 16u;
-                v[j] = (off < a.n) ? kj_load_chunk(a.buf, off, a.n) : make_uint4(0, 0, 0, 0);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < KJ_CPT / 2; ++j) {
-            const int it = half * (KJ_CPT / 2) + j;
-            const uint32_t c = it * KJ_THREADS + tid;
-            uint32_t keep = 0xFFFFu;
-            if (!INTERIOR) {   // newlines are counted only inside the owned range
-                const uint64_t off = tile_off + (uint64_t)c * 16u;
-                if (off >= a.own_n) keep = 0;
-                else if (off + 16 > a.own_n) keep = (1u << (uint32_t)(a.own_n - off)) - 1u;
-            }
-            kj_p1_chunk(codes, s, c, it * (KJ_THREADS / 32) + warp, v[j], keep);
-        }
+#pragma unroll 1
+    for (int it = 0; it < CPT; ++it) {
+        const uint32_t c = it * NT + t;
+        const uint64_t off = tile_off + (uint64_t)c * 16u;
+        const uint4 v = (off < a.n) ? kj_load_chunk(a.buf, off, a.n) : make_uint4(0, 0, 0, 0);
+        uint32_t keep = 0xFFFFu;
+        if (off >= a.own_n) keep = 0;
+        else if (off + 16 > a.own_n) keep = (1u << (uint32_t)(a.own_n - off)) - 1u;
+        kj_p1_chunk(codes, s, c, c >> 5, v, keep);
     }
-    if (tid < 2) {   // halo code words
-        const uint64_t off = tile_off + (uint64_t)(KJ_TILE_CHUNKS + tid) * 16u;
+    if (t < 2) {   // halo code words
+        const uint64_t off = tile_off + (uint64_t)(KJ_TILE_CHUNKS + t) * 16u;
         const uint4 h = (off < a.n) ? kj_load_chunk(a.buf, off, a.n) : make_uint4(0, 0, 0, 0);
-        codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
+        codes[KJ_TILE_CHUNKS + t] = kj_pack16(h.x, h.y, h.z, h.w);
     }
 }
 
-// Warp 0 turns the row counts into exclusive prefixes and publishes the tile's aggregate.
-__device__ __forceinline__ void kj_tile_rowscan_warp0(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
+// One warp turns the row counts into exclusive prefixes and publishes the tile's aggregate.
+__device__ __forceinline__ void kj_tile_rowscan_warp(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
     const uint32_t lane = threadIdx.x & 31;
-    {
-        // exclusive scan of the 64 row counts, 2 per lane; the tile's aggregate is published at once
-        const uint32_t c0 = s.row_pre[2 * lane], c1 = s.row_pre[2 * lane + 1];
-        const uint32_t sum = c0 + c1;
-        uint32_t incl = sum;
+    static_assert(KJ_ROWS <= 64, "two rows per lane");
+    const uint32_t c0 = 2 * lane < KJ_ROWS ? s.row_pre[2 * lane] : 0u;
+    const uint32_t c1 = 2 * lane + 1 < KJ_ROWS ? s.row_pre[2 * lane + 1] : 0u;
+    const uint32_t sum = c0 + c1;
+    uint32_t incl = sum;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if ((int)lane >= d) incl += o;
-        }
-        const uint32_t excl = incl - sum;
-        s.row_pre[2 * lane] = excl;
-        s.row_pre[2 * lane + 1] = excl + c0;
-        if (lane == 31) {
-            s.tile_count = incl;
-            *reinterpret_cast<volatile uint64_t *>(&a.status[tile]) = (KJ_ST_AGG << 62) | (uint64_t)incl;
-        }
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += o;
+    }
+    const uint32_t excl = incl - sum;
+    if (2 * lane < KJ_ROWS) s.row_pre[2 * lane] = excl;
+    if (2 * lane + 1 < KJ_ROWS) s.row_pre[2 * lane + 1] = excl + c0;
+    if (lane == 31) {
+        s.tile_count = incl;
+        *reinterpret_cast<volatile uint64_t *>(&a.status[tile]) = (KJ_ST_AGG << 62) | (uint64_t)incl;
     }
 }
 
-// Warp 0: decoupled look-back.  Writes excl_count, publishes the inclusive state and, for the last
+// One warp: decoupled look-back.  Writes excl_count, publishes the inclusive state and, for the last
 // tile, the stream carry of the next launch.
 __device__ __forceinline__ void kj_lookback(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
     const uint32_t lane = threadIdx.x & 31;
@@ -386,7 +382,7 @@ __device__ __forceinline__ KjRowBits kj_row_bits(const KjTileSmem &s, uint32_t j
 // Filter-kernel candidate: window start at tile-relative jt (step == 1, 1 <= m <= k, jt inside the
 // tile).  Straight-line SIMD-in-register code: the emit warps run a chain of dependent work per
 // candidate, so instruction count and round trips on that chain set their pace.
-__device__ __forceinline__ void kj_verify_candidate(const KjScanArgs &a, const KjTileSmem &s,
+static __device__ __noinline__ void kj_verify_candidate(const KjScanArgs &a, const KjTileSmem &s,
                                                     uint64_t tile_off, uint64_t tile_voff,
                                                     uint32_t jt, uint32_t strand,
                                                     uint32_t &n_emit) {
@@ -493,14 +489,14 @@ __device__ __forceinline__ void kj_chunk_filter(const KjScanArgs &a, const uint3
     zr = a.n_strands > 1 ? kj_zero_lanes(accr) : 0u;
 }
 
-// P2 of one tile: bit-parallel prefix search in code space; candidates -> queue
-template <int MP, int RC>
+// P2 of one tile by a group of NT threads: bit-parallel prefix search in code space; candidates -> queue
+template <int MP, int RC, int NT>
 __device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32_t *codes, KjTileSmem &s, uint16_t *queue,
-                                               uint32_t own_in_tile) {
-    const uint32_t tid = threadIdx.x;
-#pragma unroll
-    for (int it = 0; it < KJ_CPT; ++it) {
-        const uint32_t c = it * KJ_THREADS + tid;
+                                               uint32_t own_in_tile, uint32_t t) {
+    constexpr int CPT = KJ_TILE_CHUNKS / NT;
+#pragma unroll 4
+    for (int it = 0; it < CPT; ++it) {
+        const uint32_t c = it * NT + t;
         const uint32_t pos0 = c * 16u;
         if (pos0 >= own_in_tile) continue;
         uint32_t zf, zr;
@@ -523,15 +519,19 @@ __device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32
 
 // The filter kernel: warp-specialised and software-pipelined over tiles.
 //
-//   8 stream warps  search(cur) | convert(nxt), take ticket, start copy(nxt+1) | warp 0: aggregate(nxt), look-back(cur)
-//   2 emit warps    verify + count the candidates of the tile handed over last (latency bound: L2
-//                   round trips of the byte check and of the hash table), overlapped with the above
+//   warps 1-7  stream   search(cur) | convert(nxt) | take ticket, start copy(nxt+1), tell control
+//   warp  0    control  aggregate(nxt) -> published for the tiles behind; look-back(cur); hand cur to emit
+//   warps 8-9  emit     verify + count the candidates of the tiles handed over (latency bound: L2 round
+//                       trips of the byte check and of the hash table), up to KJ_SLOTS - 1 tiles behind
 //
 // The bytes of a tile arrive in `stage` through the TMA engine (cp.async.bulk + mbarrier) while the
 // tile before it is searched.  A tile is converted to code words and its newline aggregate is
 // published BEFORE the current one is finished, so the look-back of the tiles behind it does not
-// wait for this CTA.  Stream -> emit hand-over: two slots {KjTileSmem, candidate queue} with a
-// full / empty mbarrier pair each.
+// wait for this CTA.  Hand-over: KJ_SLOTS slots {KjTileSmem, candidate queue} with a full / empty
+// mbarrier pair each; stream -> control commands alternate between two mbarriers (at most two are
+// outstanding, because the stream warps cannot run further ahead of the emit warps than the slots allow).
+struct KjCtlCmd { uint32_t lb_tile, lb_slot, scan_tile, scan_slot; };
+
 template <int MP, int RC>
 __global__ void __launch_bounds__(KJ_FTHREADS, 4)
 kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
@@ -540,9 +540,10 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ uint16_t queue[KJ_SLOTS][KJ_FQCAP];              // candidates: tile position << 1 | strand
     __shared__ uint32_t tile_of[KJ_SLOTS];                      // tile in the slot (KJ_NO_TILE: no more work)
     __shared__ uint32_t tile_next;                              // ticket fetched ahead
-    __shared__ __align__(8) uint64_t bar_load, bar_full[KJ_SLOTS], bar_empty[KJ_SLOTS];
+    __shared__ KjCtlCmd ctl[2];
+    __shared__ __align__(8) uint64_t bar_load, bar_full[KJ_SLOTS], bar_empty[KJ_SLOTS], bar_ctl[2];
     KJ_DYN_SMEM(stage);                                         // KJ_STAGE_BYTES: raw bytes of the tile in flight
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x;
     // a tile travels through `stage` when it and the 32 bytes behind it are owned and readable
     const bool any_staged = a.own_n >= KJ_STAGE_BYTES;
     const uint64_t staged_end = any_staged ? a.own_n - KJ_STAGE_BYTES : 0;      // staged iff tile_off <= staged_end
@@ -556,6 +557,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
 
     if (tid == 0) {
         kj_bar_init(&bar_load, 1);
+        kj_bar_init(&bar_ctl[0], 1); kj_bar_init(&bar_ctl[1], 1);
         for (int i = 0; i < KJ_SLOTS; ++i) { kj_bar_init(&bar_full[i], 1); kj_bar_init(&bar_empty[i], KJ_ETHREADS); }
 #if defined(__CUDA_ARCH__)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -565,9 +567,29 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     }
     __syncthreads();
 
-    if (tid >= KJ_THREADS) {
+    if (tid < KJ_CTHREADS) {
+        // ------------------------------------------------------------------ control warp
+        uint32_t phc = 0, seq = 0;
+        for (;;) {
+            const uint32_t kk = seq & 1u;
+            kj_bar_wait(&bar_ctl[kk], (phc >> kk) & 1u);
+            phc ^= 1u << kk;
+            ++seq;
+            const KjCtlCmd cmd = ctl[kk];
+            if (cmd.scan_tile != KJ_NO_TILE) kj_tile_rowscan_warp(a, meta[cmd.scan_slot], cmd.scan_tile);
+            if (cmd.lb_tile != KJ_NO_TILE) {
+                kj_lookback(a, meta[cmd.lb_slot], cmd.lb_tile);
+                __syncwarp();
+                if (tid == 0) { tile_of[cmd.lb_slot] = cmd.lb_tile; kj_bar_arrive(&bar_full[cmd.lb_slot]); }
+            }
+            if (cmd.scan_tile == KJ_NO_TILE) break;          // nothing behind it
+        }
+        return;
+    }
+
+    if (tid >= KJ_CTHREADS + KJ_STHREADS) {
         // ------------------------------------------------------------------ emit warps
-        const uint32_t et = tid - KJ_THREADS;
+        const uint32_t et = tid - (KJ_CTHREADS + KJ_STHREADS);
         uint32_t n_emit = 0, phf = 0, b = 0;           // phf bit s: parity of the next full phase of slot s
         long long n_bases = 0;
         for (;;) {
@@ -611,8 +633,10 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     }
 
     // ---------------------------------------------------------------------- stream warps
+    const uint32_t st = tid - KJ_CTHREADS;
     uint32_t ph_load = 0, phe = 0;                  // phase parities: copy in flight, slot-empty barriers (bit s)
-    uint32_t handed = 0;                            // bit s: slot s has been handed to the emit warps before
+    uint32_t handed = 0;                            // bit s: slot s has been handed over before
+    uint32_t cseq = 0;                              // commands sent to the control warp
     auto wait_slot_free = [&](uint32_t sl) {
         if (handed & (1u << sl)) {
             kj_bar_wait(&bar_empty[sl], (phe >> sl) & 1u);
@@ -621,55 +645,58 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     };
     auto next_slot = [](uint32_t sl) { return (sl + 1u == KJ_SLOTS) ? 0u : sl + 1u; };
     auto convert = [&](uint32_t tile, KjTileSmem &m) {   // P1 of `tile` into codes / m
-        if (tid == 0) m.q_n = 0;
+        if (st == 0) m.q_n = 0;
         const uint64_t off = (uint64_t)tile * KJ_TILE_BYTES;
         if (any_staged && off <= staged_end) {
             kj_bar_wait(&bar_load, ph_load);
             ph_load ^= 1u;
-            kj_tile_p1_stage(codes, m, stage);
+            kj_tile_p1_stage<KJ_STHREADS>(codes, m, stage, st);
         } else {
-            kj_tile_p1_global<false>(a, codes, m, tile);
+            kj_tile_p1_global<KJ_STHREADS>(a, codes, m, tile, st);
         }
+    };
+    auto send_cmd = [&](uint32_t lb_tile, uint32_t lb_slot, uint32_t scan_tile, uint32_t scan_slot) {   // thread st == 0
+        const uint32_t kk = cseq & 1u;
+        ctl[kk].lb_tile = lb_tile; ctl[kk].lb_slot = lb_slot;
+        ctl[kk].scan_tile = scan_tile; ctl[kk].scan_slot = scan_slot;
+        kj_bar_arrive(&bar_ctl[kk]);
     };
 
     uint32_t cur = tile_next, b = 0;
     if (cur < a.n_tiles) {
         convert(cur, meta[0]);
         kj_sync_stream();
-        if (tid == 32) take_ticket();
-        if (warp == 0) kj_tile_rowscan_warp0(a, meta[0], cur);
+        if (st == 0) { take_ticket(); send_cmd(KJ_NO_TILE, 0, cur, 0); }
+        ++cseq;
         for (;;) {
-            kj_sync_stream();                              // aggregate of cur and the next ticket are visible
-            const uint32_t nxt = tile_next;
-            KjTileSmem &m = meta[b];
             const uint64_t tile_off = (uint64_t)cur * KJ_TILE_BYTES;
             const uint32_t own_in_tile =
                 (a.own_n - tile_off < KJ_TILE_BYTES) ? (uint32_t)(a.own_n - tile_off) : KJ_TILE_BYTES;
-
-            kj_tile_search<MP, RC>(a, codes, m, queue[b], own_in_tile);
-            kj_sync_stream();                              // code words of cur no longer needed; queue complete
+            kj_tile_search<MP, RC, KJ_STHREADS>(a, codes, meta[b], queue[b], own_in_tile, st);
+            kj_sync_stream();                              // code words of cur no longer needed; queue complete; ticket visible
+            const uint32_t nxt = tile_next;
             const uint32_t nb = next_slot(b);
             if (nxt < a.n_tiles) {
                 wait_slot_free(nb);                        // the emit warps may lag KJ_SLOTS - 1 tiles behind
                 convert(nxt, meta[nb]);
-                kj_sync_stream();
-                if (tid == 32) take_ticket();              // `stage` is free again
+                kj_sync_stream();                          // `stage` is free again
             }
-            if (warp == 0) {
-                if (nxt < a.n_tiles) kj_tile_rowscan_warp0(a, meta[nb], nxt);
-                kj_lookback(a, m, cur);                    // the tiles in front published long ago
-                __syncwarp();
-                if (tid == 0) { tile_of[b] = cur; kj_bar_arrive(&bar_full[b]); }    // hand cur to the emit warps
+            if (st == 0) {
+                if (nxt < a.n_tiles) take_ticket();
+                send_cmd(cur, b, nxt < a.n_tiles ? nxt : KJ_NO_TILE, nb);
             }
+            ++cseq;
             handed |= 1u << b;
             if (nxt >= a.n_tiles) break;
             cur = nxt;
             b = nb;
         }
         b = next_slot(b);                                  // the slot after the last tile carries the stop mark
+    } else {
+        if (st == 0) send_cmd(KJ_NO_TILE, 0, KJ_NO_TILE, 0);
     }
     wait_slot_free(b);
-    if (tid == 0) { tile_of[b] = KJ_NO_TILE; kj_bar_arrive(&bar_full[b]); }
+    if (st == 0) { tile_of[b] = KJ_NO_TILE; kj_bar_arrive(&bar_full[b]); }
 }
 
 // ----------------------------------------------------------------------------- line-oriented kernel
@@ -751,9 +778,9 @@ kj_scan_lines_kernel(const __grid_constant__ KjScanArgs a) {
         if (tile >= a.n_tiles) break;
         const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
 
-        kj_tile_p1_global<false>(a, codes, s, tile);
+        kj_tile_p1_global<KJ_THREADS>(a, codes, s, tile, tid);
         __syncthreads();
-        if (warp == 0) { kj_tile_rowscan_warp0(a, s, tile); kj_lookback(a, s, tile); }
+        if (warp == 0) { kj_tile_rowscan_warp(a, s, tile); kj_lookback(a, s, tile); }
         __syncthreads();
 
         // the line that starts exactly at the first byte of the stream piece: owned iff the
@@ -762,7 +789,7 @@ kj_scan_lines_kernel(const __grid_constant__ KjScanArgs a) {
             a.own_n > 0)
             queue[s.q_n++] = 0;
         // P2': every '\n' at e starts a line at e+1 (owned by the tile that holds the '\n')
-        for (int it = 0; it < KJ_CPT; ++it) {
+        for (int it = 0; it < KJ_TILE_CHUNKS / KJ_THREADS; ++it) {
             __syncthreads();
             const uint32_t c = it * KJ_THREADS + tid;
             uint32_t mk = s.nl[c];

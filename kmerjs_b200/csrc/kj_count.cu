@@ -335,6 +335,19 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
         c->tile_cap = tc;
     }
     KJ_CUDA(ctx, cudaMemsetAsync(c->tile_mem, 0, (uint64_t)n_tiles * 8, ctx->stream));  // status only
+    if (c->use_filter) {
+        // candidate records: code-space matches in sequence lines, about 0.9 * 4^-m of the bytes for
+        // FASTQ of random bases; whatever does not fit is verified in place by the scan kernel
+        uint64_t want_rec = std::min<uint64_t>(hard_bound, (uint64_t)(2.0 * expected_emissions(c, own_n)) + (1ull << 18));
+        want_rec = (want_rec + KJ_REC_BLOCK - 1) / KJ_REC_BLOCK * KJ_REC_BLOCK;
+        if (want_rec > c->cand_cap) {
+            kj_dfree(ctx, c->cand);
+            c->cand = nullptr; c->cand_cap = 0;
+            KJ_CUDA(ctx, kj_dmalloc(ctx, &c->cand, want_rec * 16));
+            c->cand_cap = want_rec;
+        }
+        KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_cand, 0, sizeof(unsigned long long), ctx->stream));
+    }
     KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->ticket, 0, sizeof(unsigned int), ctx->stream));
 
     KjScanArgs a{};
@@ -369,6 +382,8 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
     }
     a.tab = c->tab; a.irr = c->irr; a.ovf = c->ovf; a.ctr = c->ctr;
     a.status = c->tile_mem;
+    a.cand = c->cand;
+    a.cand_cap = c->cand_cap;
 
     void (*fn)(const KjScanArgs) = kj_scan_lines_kernel;
     if (c->use_filter) {
@@ -400,6 +415,11 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
     const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * std::max(occ, 1));
     if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     KJ_LAUNCH(fn, grid, threads, dyn_smem, ctx->stream, a);
+    ctx->launches++;
+    if (c->use_filter) {
+        // part B of the candidates: one thread per record, the whole GPU at once
+        KJ_LAUNCH(kj_verify_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);
+    }
     if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches++;
     KJ_CUDA(ctx, cudaGetLastError());
@@ -840,6 +860,7 @@ extern "C" void kj_counts_free(kj_counts *c) {
         kj_dfree(ctx, c->ctr);
         kj_pinned_put(ctx, c->h_ctr);
         kj_dfree(ctx, c->tile_mem);
+        kj_dfree(ctx, c->cand);
         drop_compact(c);
         kj_dfree(ctx, c->part_rec);
     }

@@ -43,6 +43,7 @@ struct KjCounters {
     unsigned long long n_irr_unique;
     unsigned long long n_overflow;
     unsigned long long n_irr_overflow;
+    unsigned long long n_cand;         // candidate record slots handed out in the current launch (filter kernel)
     unsigned long long n_occ;          // emitted occurrences (regular + irregular)
     unsigned long long n_bases;        // sum of processed sequence-line lengths
     unsigned long long special_count;  // the one key equal to KJ_EMPTY (k = 32, all 'G')

@@ -103,8 +103,10 @@ struct kj_counts {
     KjOverflow ovf{};
     KjCounters *ctr = nullptr;        // device
     KjCounters *h_ctr = nullptr;      // pinned mirror
-    uint64_t *tile_mem = nullptr;     // 3 * tile_cap u64
+    uint64_t *tile_mem = nullptr;     // tile_cap u64 (look-back status words)
     uint64_t tile_cap = 0;
+    uint64_t *cand = nullptr;         // candidate records of the launch in flight (filter kernel), 16 bytes each
+    uint64_t cand_cap = 0;
     // results
     KjCompact reg{};
     // irregular entries, host side after finish: 56-byte records

@@ -37,6 +37,7 @@
 #define KJ_STAGE_BYTES (KJ_TILE_BYTES + 32)              // a tile and the 32 bytes its last windows reach into
 #define KJ_NO_TILE 0xFFFFFFFFu
 #define KJ_SLOTS 3                                       // stream -> emit hand-over slots
+#define KJ_REC_BLOCK 256u                                // candidate records reserved per emit warp at a time
 
 #define KJ_ST_AGG 1ull
 #define KJ_ST_INC 2ull
@@ -74,6 +75,8 @@ struct KjScanArgs {
     KjIrrTable irr;
     KjOverflow ovf;
     uint64_t *status;     // per tile: flag << 62 | newline count; zeroed before every launch
+    uint64_t *cand;       // candidate records {position | strand << 63, ordinal} of this launch (filter kernel)
+    uint64_t cand_cap;    // in records
     KjCounters *ctr;
 };
 
@@ -184,14 +187,19 @@ __device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(kj_smem_u32(dst)), "l"(src), "r"(bytes), "r"(kj_smem_u32(bar)) : "memory");
 }
-// returns once the phase with parity `parity` has completed
-__device__ __forceinline__ void kj_bar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok = 0;
-    const uint32_t addr = kj_smem_u32(bar);
-    while (!ok)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-}
+// returns once the phase with parity `parity` has completed.  try_wait suspends the warp in hardware
+// for up to the hinted time, so waiting warps do not eat issue slots.  (A macro, so that profiles
+// attribute the wait to the call site.)
+#define kj_bar_wait(bar, parity)                                                                              \
+    do {                                                                                                      \
+        uint32_t ok__ = 0;                                                                                    \
+        const uint32_t addr__ = kj_smem_u32(bar);                                                             \
+        const uint32_t par__ = (parity);                                                                      \
+        while (!ok__)                                                                                         \
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t" \
+                         "selp.u32 %0, 1, 0, p;\n\t}"                                                         \
+                         : "=r"(ok__) : "r"(addr__), "r"(par__), "r"(20000u) : "memory");                     \
+    } while (0)
 // barrier of the 7 stream warps of the filter kernel (control and emit warps do not take part)
 __device__ __forceinline__ void kj_sync_stream() { asm volatile("bar.sync 1, %0;" ::"n"(KJ_STHREADS) : "memory"); }
 #endif
@@ -379,24 +387,24 @@ __device__ __forceinline__ KjRowBits kj_row_bits(const KjTileSmem &s, uint32_t j
     return r;
 }
 
-// Filter-kernel candidate: window start at tile-relative jt (step == 1, 1 <= m <= k, jt inside the
-// tile).  Straight-line SIMD-in-register code: the emit warps run a chain of dependent work per
-// candidate, so instruction count and round trips on that chain set their pace.
-static __device__ __noinline__ void kj_verify_candidate(const KjScanArgs &a, const KjTileSmem &s,
-                                                    uint64_t tile_off, uint64_t tile_voff,
-                                                    uint32_t jt, uint32_t strand,
-                                                    uint32_t &n_emit) {
-    const uint64_t j = tile_off + jt;
-    const uint32_t k = a.k;
-    if (j + k > a.n) return;                              // window must lie inside the stream
-    // the window's bytes: at most three aligned 16-byte chunks, requested together (they were read a
-    // moment ago: L2 hits) before the line phase is worked out from shared memory
-    const uint32_t o = (uint32_t)(j & 15u);
-    const uint64_t base = j - o;
-    uint4 v0 = kj_load_chunk(a.buf, base, a.n), v1 = make_uint4(0, 0, 0, 0), v2 = make_uint4(0, 0, 0, 0);
-    if (base + 16u < j + k) v1 = kj_load_chunk(a.buf, base + 16u, a.n);
-    if (base + 32u < j + k) v2 = kj_load_chunk(a.buf, base + 32u, a.n);
+// A candidate of the filter kernel (window start at tile-relative jt; step == 1, 1 <= m <= k) is
+// handled in two parts.
+//
+// Part A, from the tile's newline bitmap in shared memory (emit warps of the scan kernel): is the
+// line a sequence line (index 1 mod 4, lib/kmers.js:151) and, if first-seen order is tracked, the
+// ordinal (read index, strand, column).  Survivors become 16-byte records {position | strand << 63,
+// ordinal} in global memory.
+//
+// Part B, from the window's bytes (kj_verify_kernel, one thread per record, the whole GPU at once):
+// exact prefix / newline / alphabet check and the hash-table update.  It is a chain of L2 round
+// trips per candidate; run per tile inside the scan kernel it set the pace of the whole pipeline,
+// as a separate wide kernel its latency disappears behind parallelism.
+#define KJ_REC_STRAND (1ull << 63)
+#define KJ_REC_NONE 0xFFFFFFFFFFFFFFFFull
 
+// Part A.  false: not in a sequence line (or an error was flagged).
+__device__ __forceinline__ bool kj_candidate_line(const KjScanArgs &a, const KjTileSmem &s, uint64_t tile_off,
+                                                  uint64_t tile_voff, uint32_t jt, uint32_t strand, uint64_t &ord) {
     // newlines of the tile before jt: prefix of the row + bitmap words of the row below jt
     const KjRowBits rb = kj_row_bits(s, jt);
     const uint32_t p = jt & 511u, pw = p >> 5;
@@ -410,8 +418,34 @@ static __device__ __noinline__ void kj_verify_candidate(const KjScanArgs &a, con
         if (x) { last_w = x; last_i = i; }
     }
     const uint64_t line = s.excl_count + before;
-    if ((line & 3ull) != 1ull) return;                    // lib/kmers.js:151  i === 1
+    if ((line & 3ull) != 1ull) return false;              // lib/kmers.js:151  i === 1
+    ord = 0;
+    if (a.order || a.k == 1) {
+        // first byte of the line: the last '\n' below jt in this row, else further back
+        unsigned long long start;
+        if (last_w) start = tile_voff + (jt & ~511u) + last_i * 32u + (31u - __clz(last_w)) + 1ull;
+        else start = kj_line_start(a, s, jt & ~511u, tile_off, tile_voff);
+        const uint64_t col = tile_voff + jt - start;
+        if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); return false; }
+        const uint64_t read_idx = line >> 2;
+        if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); return false; }
+        // forward emissions in ascending column, then reverse emissions in descending column
+        ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
+    }
+    return true;
+}
 
+// Part B: the window at buffer offset j.  Straight-line SIMD-in-register code.
+__device__ __forceinline__ void kj_window_emit(const KjScanArgs &a, uint64_t j, uint32_t strand, uint64_t ord,
+                                               uint32_t &n_emit) {
+    const uint32_t k = a.k;
+    if (j + k > a.n) return;                              // window must lie inside the stream
+    // the window's bytes: at most three aligned 16-byte chunks, requested together
+    const uint32_t o = (uint32_t)(j & 15u);
+    const uint64_t base = j - o;
+    uint4 v0 = kj_load_chunk(a.buf, base, a.n), v1 = make_uint4(0, 0, 0, 0), v2 = make_uint4(0, 0, 0, 0);
+    if (base + 16u < j + k) v1 = kj_load_chunk(a.buf, base + 16u, a.n);
+    if (base + 32u < j + k) v2 = kj_load_chunk(a.buf, base + 32u, a.n);
     // window bytes 0..31 in X[0..7]: shift the 48 loaded bytes down by o
     const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
     const uint32_t q = o >> 2, r8 = (o & 3u) * 8u;
@@ -435,25 +469,13 @@ static __device__ __noinline__ void kj_verify_candidate(const KjScanArgs &a, con
         }
     }
     if (nl | bad) return;                                 // crosses the end of the line / prefix bytes differ
+    if (k == 1 && a.line_gate) {                          // lib/kmers.js:151  line.length > 1: a lone byte is not processed
+        const bool first = j == 0 ? (a.ctr->carry_last[a.parity] == a.voff) : (a.buf[j - 1] == '\n');
+        const bool more = (j + 1 < a.n) && a.buf[j + 1] != '\n';
+        if (first && !more) return;
+    }
     const uint64_t P = ((uint64_t)p_hi << 32) | p_lo;     // code of window byte i at bits 2i
     const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
-    uint64_t ord = 0;
-    if (a.order || k == 1) {
-        // first byte of the line: the last '\n' below jt in this row, else further back
-        unsigned long long start;
-        if (last_w) start = tile_voff + (jt & ~511u) + last_i * 32u + (31u - __clz(last_w)) + 1ull;
-        else start = kj_line_start(a, s, jt & ~511u, tile_off, tile_voff);
-        const uint64_t col = tile_voff + jt - start;
-        if (k == 1 && col == 0 && a.line_gate) {          // lib/kmers.js:151  line.length > 1
-            const bool more = (j + 1 < a.n) && a.buf[j + 1] != '\n';
-            if (!more) return;
-        }
-        if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); return; }
-        const uint64_t read_idx = line >> 2;
-        if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); return; }
-        // forward emissions in ascending column, then reverse emissions in descending column
-        ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
-    }
     ++n_emit;
     if (!irr) {
         // forward key: first base most significant; reverse key: complement codes, last base first
@@ -462,6 +484,29 @@ static __device__ __noinline__ void kj_verify_candidate(const KjScanArgs &a, con
     } else {
         kj_emit_irregular(a, j, k, strand, ord);
     }
+}
+
+// both parts in place: the scan kernel's fallback when the record buffer is full, and dense inputs
+static __device__ __noinline__ void kj_verify_candidate(const KjScanArgs &a, const KjTileSmem &s,
+                                                        uint64_t tile_off, uint64_t tile_voff,
+                                                        uint32_t jt, uint32_t strand, uint32_t &n_emit) {
+    uint64_t ord;
+    if (tile_off + jt + a.k > a.n) return;
+    if (kj_candidate_line(a, s, tile_off, tile_voff, jt, strand, ord)) kj_window_emit(a, tile_off + jt, strand, ord, n_emit);
+}
+
+// Part B over the records of one launch.
+__global__ void __launch_bounds__(256) kj_verify_kernel(const __grid_constant__ KjScanArgs a) {
+    const unsigned long long n_res = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;   // slots handed out
+    uint32_t n_emit = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_res;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(a.cand + 2 * i);
+        if (r.x == KJ_REC_NONE) continue;                  // unused tail of a reserved block
+        kj_window_emit(a, r.x & ~KJ_REC_STRAND, (uint32_t)(r.x >> 63), r.y, n_emit);
+    }
+    for (int d = 16; d > 0; d >>= 1) n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
+    if ((threadIdx.x & 31) == 0 && n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);
 }
 
 // ----------------------------------------------------------------------------- filter kernel
@@ -592,6 +637,8 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
         const uint32_t et = tid - (KJ_CTHREADS + KJ_STHREADS);
         uint32_t n_emit = 0, phf = 0, b = 0;           // phf bit s: parity of the next full phase of slot s
         long long n_bases = 0;
+        unsigned long long blk_base = KJ_REC_NONE;      // this warp's block of record slots
+        uint32_t blk_used = KJ_REC_BLOCK;
         for (;;) {
             kj_bar_wait(&bar_full[b], (phf >> b) & 1u);
             phf ^= 1u << b;
@@ -605,14 +652,46 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
             if (a.count_bases) n_bases += kj_tile_bases(m, tile_voff, et, KJ_ETHREADS);
             const uint32_t qn = m.q_n;
             if (qn <= KJ_FQCAP) {
-                // candidates sit densely in the lanes: a warp with one busy lane costs as much as a full one
-                for (uint32_t q = et; q < qn; q += KJ_ETHREADS) {
-                    const uint32_t e = queue[b][q];
-                    kj_verify_candidate(a, m, tile_off, tile_voff, e >> 1, e & 1u, n_emit);
+                // candidates sit densely in the lanes.  Survivors of the line check are appended to
+                // the record buffer, in blocks of KJ_REC_BLOCK records reserved per warp (one global
+                // atomic per block, off the per-tile path).
+                for (uint32_t q0 = 0; q0 < qn; q0 += KJ_ETHREADS) {
+                    const uint32_t q = q0 + et;
+                    bool keep = false;
+                    uint64_t ord = 0, rec = 0;
+                    uint32_t e = 0;
+                    if (q < qn) {
+                        e = queue[b][q];
+                        if (tile_off + (e >> 1) + a.k <= a.n)
+                            keep = kj_candidate_line(a, m, tile_off, tile_voff, e >> 1, e & 1u, ord);
+                        rec = (tile_off + (e >> 1)) | ((e & 1u) ? KJ_REC_STRAND : 0ull);
+                    }
+                    const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
+                    const uint32_t need = __popc(kb);
+                    if (need == 0) continue;
+                    if (blk_used + need > KJ_REC_BLOCK) {
+                        // retire the block (mark its unused tail), reserve a new one
+                        if (blk_base != KJ_REC_NONE)
+                            for (uint32_t i = blk_used + (tid & 31); i < KJ_REC_BLOCK; i += 32) a.cand[2 * (blk_base + i)] = KJ_REC_NONE;
+                        unsigned long long nb_ = 0;
+                        if ((tid & 31) == 0) nb_ = atomicAdd(&a.ctr->n_cand, (unsigned long long)KJ_REC_BLOCK);
+                        nb_ = __shfl_sync(0xFFFFFFFFu, nb_, 0);
+                        blk_base = nb_ + KJ_REC_BLOCK <= a.cand_cap ? nb_ : KJ_REC_NONE;     // NONE: buffer full
+                        blk_used = blk_base == KJ_REC_NONE ? KJ_REC_BLOCK : 0;              // stay "full"
+                    }
+                    if (blk_base != KJ_REC_NONE) {
+                        if (keep) {
+                            const unsigned long long at = blk_base + blk_used + __popc(kb & ((1u << (tid & 31)) - 1u));
+                            *reinterpret_cast<ulonglong2 *>(a.cand + 2 * at) = make_ulonglong2(rec, ord);
+                        }
+                        blk_used += need;
+                    } else if (keep) {
+                        kj_window_emit(a, rec & ~KJ_REC_STRAND, (uint32_t)(rec >> 63), ord, n_emit);   // buffer full: in place
+                    }
                 }
             } else {
                 // dense candidates (e.g. homopolymer input): the code words are gone by now, so every
-                // owned position takes the exact check
+                // owned position takes the exact check, in place
                 for (uint32_t jt = et; jt < own_in_tile; jt += KJ_ETHREADS) {
                     kj_verify_candidate(a, m, tile_off, tile_voff, jt, 0u, n_emit);
                     if (a.n_strands > 1) kj_verify_candidate(a, m, tile_off, tile_voff, jt, 1u, n_emit);
@@ -621,6 +700,8 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
             kj_bar_arrive(&bar_empty[b]);
             b = (b + 1u == KJ_SLOTS) ? 0u : b + 1u;
         }
+        if (blk_base != KJ_REC_NONE)               // unused tail of the last block
+            for (uint32_t i = blk_used + (tid & 31); i < KJ_REC_BLOCK; i += 32) a.cand[2 * (blk_base + i)] = KJ_REC_NONE;
         for (int d = 16; d > 0; d >>= 1) {       // one atomic per warp
             n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
             n_bases += __shfl_xor_sync(0xFFFFFFFFu, n_bases, d);

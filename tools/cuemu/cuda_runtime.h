@@ -44,6 +44,8 @@ struct uint4 { uint32_t x, y, z, w; };
 struct uint2 { uint32_t x, y; };
 static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }
 static inline uint2 make_uint2(uint32_t a, uint32_t b) { return uint2{a, b}; }
+struct __attribute__((aligned(16))) ulonglong2 { unsigned long long x, y; };
+static inline ulonglong2 make_ulonglong2(unsigned long long a, unsigned long long b) { return ulonglong2{a, b}; }
 
 extern uint3 threadIdx, blockIdx;
 extern dim3 blockDim, gridDim;

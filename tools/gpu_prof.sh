@@ -5,6 +5,6 @@ SHORT="python bench.py --reads ${READS:-2000000} --steps 2 --warmup 3 --e2e-step
 $SHORT --trace > gpurun_out/plain_short.json 2> gpurun_out/plain_short.err; R=$?
 cat gpurun_out/plain_short.json; tail -3 gpurun_out/plain_short.err
 if [ "$R" == "0" ]; then
-  ncu --set full --clock-control none --import-source on -k regex:kj_scan -s ${SKIP:-3} -c ${COUNT:-2} -f -o gpurun_out/prof_scan $SHORT > gpurun_out/ncu_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k "regex:kj_scan|kj_verify" -s ${SKIP:-6} -c ${COUNT:-4} -f -o gpurun_out/prof_scan $SHORT > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
 fi

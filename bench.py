@@ -284,6 +284,7 @@ def run_b200(args):
     ms_total = timed(step_device, args.steps)
     launches = ctx.launches - l0
     scan_ms, scan_n, scan_bytes = ctx.scan_kernel_stats()
+    verify_ms = ctx.verify_kernel_ms()
     ctx.enable_timers(False)
     clocks = sampler.stop() if rank == 0 else None
     bases_per_step = n_reads * 150 * world
@@ -345,7 +346,8 @@ def run_b200(args):
     alg_bytes = scan_bytes / max(scan_n, 1) + 32.0 * per_rank_occ          # F + 32 * N_occ per launch
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "kj_scan_filter_kernel<5>", "kernel_ms": scan_ms,
+                "traffic": None, "kernel": "kj_scan_filter_kernel<5,0> + kj_verify_kernel (extraction + count)",
+                "kernel_ms": scan_ms, "scan_kernel_ms": scan_ms - verify_ms, "verify_kernel_ms": verify_ms,
                 "launches_averaged": scan_n, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": scan_ms * scan_n / max(ms_total, 1e-9)}
 

@@ -75,6 +75,8 @@ uint64_t kj_launch_count(const kj_ctx *ctx);
 /* average device time (ms, CUDA events on the launching stream) of the dominant extraction kernel
  * since the last kj_reset_timers(); n_launches receives the number of launches averaged */
 double kj_scan_kernel_ms(const kj_ctx *ctx, uint64_t *n_launches);
+/* the part of it spent in the candidate check + hash update kernel that follows the scan kernel */
+double kj_verify_kernel_ms(const kj_ctx *ctx);
 /* input bytes those launches owned (the F term of the algorithmic-bytes model) */
 uint64_t kj_scan_kernel_bytes(const kj_ctx *ctx);
 void kj_reset_timers(kj_ctx *ctx);

@@ -70,6 +70,7 @@ SIGNATURES = {
     "kj_abi_version": (C.c_int, []),
     "kj_launch_count": (C.c_uint64, [vp]),
     "kj_scan_kernel_ms": (C.c_double, [vp, u64p]),
+    "kj_verify_kernel_ms": (C.c_double, [vp]),
     "kj_scan_kernel_bytes": (C.c_uint64, [vp]),
     "kj_reset_timers": (None, [vp]),
     "kj_enable_timers": (None, [vp, C.c_int]),

@@ -45,6 +45,9 @@ class Context:
         ms = self._L.kj_scan_kernel_ms(self.handle, C.byref(n))
         return float(ms), int(n.value), int(self._L.kj_scan_kernel_bytes(self.handle))
 
+    def verify_kernel_ms(self) -> float:
+        return float(self._L.kj_verify_kernel_ms(self.handle))
+
 
 def default_context(device: int | None = None) -> Context:
     """The process-wide context of `device` (default: LOCAL_RANK, else 0)."""

@@ -418,6 +418,7 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
     ctx->launches++;
     if (c->use_filter) {
         // part B of the candidates: one thread per record, the whole GPU at once
+        if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
         KJ_LAUNCH(kj_verify_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);
     }
     if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -429,6 +430,11 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
         float ms = 0.f;
         KJ_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->scan_ms += ms;
+        if (c->use_filter) {
+            float vms = 0.f;
+            KJ_CUDA(ctx, cudaEventElapsedTime(&vms, ctx->ev2, ctx->ev1));
+            ctx->verify_ms += vms;
+        }
         ctx->scan_launches++;
         ctx->scan_bytes += own_n;
     }

@@ -77,6 +77,7 @@ extern "C" int kj_init(int device, void *stream, kj_ctx **out) {
     }
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev2);
     if (e != cudaSuccess) {
         int rc = kj_fail(nullptr, KJ_E_CUDA, cudaGetErrorString(e));
         kj_destroy(ctx);
@@ -97,6 +98,7 @@ extern "C" void kj_destroy(kj_ctx *ctx) {
     if (ctx->pin_slab) cudaFreeHost(ctx->pin_slab);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -114,9 +116,12 @@ extern "C" double kj_scan_kernel_ms(const kj_ctx *ctx, uint64_t *n_launches) {
     if (n_launches) *n_launches = ctx->scan_launches;
     return ctx->scan_launches ? ctx->scan_ms / (double)ctx->scan_launches : 0.0;
 }
+extern "C" double kj_verify_kernel_ms(const kj_ctx *ctx) {
+    return ctx && ctx->scan_launches ? ctx->verify_ms / (double)ctx->scan_launches : 0.0;
+}
 extern "C" uint64_t kj_scan_kernel_bytes(const kj_ctx *ctx) { return ctx ? ctx->scan_bytes : 0; }
 extern "C" void kj_reset_timers(kj_ctx *ctx) {
-    if (ctx) { ctx->scan_ms = 0.0; ctx->scan_launches = 0; ctx->scan_bytes = 0; }
+    if (ctx) { ctx->scan_ms = 0.0; ctx->verify_ms = 0.0; ctx->scan_launches = 0; ctx->scan_bytes = 0; }
 }
 extern "C" void kj_enable_timers(kj_ctx *ctx, int on) {
     if (ctx) ctx->timers_on = on != 0;

@@ -32,7 +32,8 @@ struct kj_ctx {
     double scan_ms = 0.0;
     uint64_t scan_launches = 0;
     uint64_t scan_bytes = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    double verify_ms = 0.0;            // part of scan_ms spent in kj_verify_kernel
     // host -> device staging (KJ_MEM_HOST buffers), double buffered, owned by the context so that
     // repeated count jobs do not re-allocate
     uint8_t *d_stage[2] = {nullptr, nullptr};

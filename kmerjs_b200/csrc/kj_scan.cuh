@@ -172,6 +172,7 @@ __device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t
 __device__ __forceinline__ void kj_bar_wait(uint64_t *bar, uint32_t parity) {
     while ((uint32_t)(*reinterpret_cast<volatile uint64_t *>(bar) >> 32) == parity) emu_yield();
 }
+#define kj_bar_wait_idle kj_bar_wait
 __device__ __forceinline__ void kj_sync_stream() { emu_named_barrier(1, KJ_STHREADS); }
 #else
 __device__ __forceinline__ uint32_t kj_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -199,6 +200,21 @@ __device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t" \
                          "selp.u32 %0, 1, 0, p;\n\t}"                                                         \
                          : "=r"(ok__) : "r"(addr__), "r"(par__), "r"(20000u) : "memory");                     \
+    } while (0)
+// the same for warps that are off the critical path (control, emit): sleep between polls, an idle
+// warp must not compete for issue slots with the stream warps
+#define kj_bar_wait_idle(bar, parity)                                                                         \
+    do {                                                                                                      \
+        uint32_t ok__ = 0;                                                                                    \
+        const uint32_t addr__ = kj_smem_u32(bar);                                                             \
+        const uint32_t par__ = (parity);                                                                      \
+        for (;;) {                                                                                            \
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"    \
+                         "selp.u32 %0, 1, 0, p;\n\t}"                                                         \
+                         : "=r"(ok__) : "r"(addr__), "r"(par__) : "memory");                                  \
+            if (ok__) break;                                                                                  \
+            __nanosleep(256);                                                                                 \
+        }                                                                                                     \
     } while (0)
 // barrier of the 7 stream warps of the filter kernel (control and emit warps do not take part)
 __device__ __forceinline__ void kj_sync_stream() { asm volatile("bar.sync 1, %0;" ::"n"(KJ_STHREADS) : "memory"); }
@@ -535,7 +551,7 @@ __device__ __forceinline__ void kj_chunk_filter(const KjScanArgs &a, const uint3
 }
 
 // P2 of one tile by a group of NT threads: bit-parallel prefix search in code space; candidates -> queue
-template <int MP, int RC, int NT>
+template <int MP, int RC, int NT, bool FULL>
 __device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32_t *codes, KjTileSmem &s, uint16_t *queue,
                                                uint32_t own_in_tile, uint32_t t) {
     constexpr int CPT = KJ_TILE_CHUNKS / NT;
@@ -543,10 +559,10 @@ __device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32
     for (int it = 0; it < CPT; ++it) {
         const uint32_t c = it * NT + t;
         const uint32_t pos0 = c * 16u;
-        if (pos0 >= own_in_tile) continue;
+        if (!FULL && pos0 >= own_in_tile) continue;        // FULL: every position of the tile is owned
         uint32_t zf, zr;
         kj_chunk_filter<MP, RC>(a, codes, c, zf, zr);
-        if (own_in_tile - pos0 < 16u) {
+        if (!FULL && own_in_tile - pos0 < 16u) {
             const uint32_t keep = (1u << (2u * (own_in_tile - pos0))) - 1u;
             zf &= keep; zr &= keep;
         }
@@ -617,7 +633,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
         uint32_t phc = 0, seq = 0;
         for (;;) {
             const uint32_t kk = seq & 1u;
-            kj_bar_wait(&bar_ctl[kk], (phc >> kk) & 1u);
+            kj_bar_wait_idle(&bar_ctl[kk], (phc >> kk) & 1u);
             phc ^= 1u << kk;
             ++seq;
             const KjCtlCmd cmd = ctl[kk];
@@ -640,7 +656,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
         unsigned long long blk_base = KJ_REC_NONE;      // this warp's block of record slots
         uint32_t blk_used = KJ_REC_BLOCK;
         for (;;) {
-            kj_bar_wait(&bar_full[b], (phf >> b) & 1u);
+            kj_bar_wait_idle(&bar_full[b], (phf >> b) & 1u);
             phf ^= 1u << b;
             const uint32_t tile = tile_of[b];
             if (tile == KJ_NO_TILE) break;
@@ -753,7 +769,8 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
             const uint64_t tile_off = (uint64_t)cur * KJ_TILE_BYTES;
             const uint32_t own_in_tile =
                 (a.own_n - tile_off < KJ_TILE_BYTES) ? (uint32_t)(a.own_n - tile_off) : KJ_TILE_BYTES;
-            kj_tile_search<MP, RC, KJ_STHREADS>(a, codes, meta[b], queue[b], own_in_tile, st);
+            if (own_in_tile == KJ_TILE_BYTES) kj_tile_search<MP, RC, KJ_STHREADS, true>(a, codes, meta[b], queue[b], own_in_tile, st);
+            else kj_tile_search<MP, RC, KJ_STHREADS, false>(a, codes, meta[b], queue[b], own_in_tile, st);
             kj_sync_stream();                              // code words of cur no longer needed; queue complete; ticket visible
             const uint32_t nxt = tile_next;
             const uint32_t nb = next_slot(b);

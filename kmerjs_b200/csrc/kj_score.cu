@@ -74,6 +74,7 @@ struct kj_match {
     bool distributed = false;        // d_glob is separate and maintained by the host layer
     std::vector<uint64_t> u0, t0;    // first-round scores (lib/kmerFinderClient.js:44-46)
     std::vector<uint32_t> order;     // matched templates in first-encounter order
+    std::vector<uint64_t> toff_h;    // host copy of toff (range of a winner's matched entries)
     uint64_t hits0 = 0;
     uint64_t kmer_map_size = 0;
     uint32_t max_hits = 100, hit_counter = 0;
@@ -693,6 +694,7 @@ extern "C" int kj_match_commit(kj_match *m) {
     std::vector<uint64_t> toff(T + 1, 0);
     for (uint64_t t = 0; t < T; ++t) toff[t + 1] = toff[t] + part_u[t];
     const uint64_t local_pairs = toff[T];
+    m->toff_h = toff;
     if (local_pairs > 0xFFFFFFF0ull * 16) return kj_fail(ctx, KJ_E_RANGE, "too many matched pairs");
     kj_dfree(ctx, m->d_tq);
     m->d_tq = nullptr;
@@ -786,9 +788,7 @@ extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
     }
     m->hit_counter++;
     // removeWinnerKmers (lib/kmerFinderClient.js:220-230) on this rank's share of K_w
-    std::vector<uint64_t> range(2);
-    KJ_CUDA(ctx, cudaMemcpyAsync(range.data(), m->d_toff + w, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t range[2] = {m->toff_h[w], m->toff_h[w + 1]};
     if (range[1] > range[0]) {
         const uint64_t n = range[1] - range[0];
         const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8));

@@ -19,8 +19,27 @@
 namespace kjstats {
 
 // ------------------------------------------------------------------ unsigned big integer
+// fixed-capacity limb array with the few std::vector members the arithmetic below uses: the rows
+// are finished on the critical path of kj_wta_next, so no heap traffic here.  1024 bits are far
+// more than the widest intermediate (a 60-decimal product scaled by 10^40: ~335 bits).
+struct Limbs {
+    enum { CAP = 40 };
+    uint32_t v[CAP];
+    uint32_t n = 0;
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    uint32_t &operator[](size_t i) { return v[i]; }
+    const uint32_t &operator[](size_t i) const { return v[i]; }
+    uint32_t &back() { return v[n - 1]; }
+    const uint32_t &back() const { return v[n - 1]; }
+    void push_back(uint32_t x) { if (n >= CAP) abort(); v[n++] = x; }
+    void pop_back() { --n; }
+    void resize(size_t m) { if (m > CAP) abort(); for (size_t i = n; i < m; ++i) v[i] = 0; n = (uint32_t)m; }
+    void assign(size_t m, uint32_t x) { if (m > CAP) abort(); for (size_t i = 0; i < m; ++i) v[i] = x; n = (uint32_t)m; }
+};
+
 struct Big {
-    std::vector<uint32_t> d;   // little endian, no leading zero limbs; empty = 0
+    Limbs d;   // little endian, no leading zero limbs; empty = 0
     Big() {}
     Big(uint64_t v) { while (v) { d.push_back((uint32_t)v); v >>= 32; } }
     bool zero() const { return d.empty(); }
@@ -121,20 +140,65 @@ static void shl1_or(Big &a, bool b) {   // a = a*2 + b
     }
     if (carry) a.d.push_back(carry);
 }
-// binary long division: q = a / b, r = a % b  (b != 0)
+// q = a / b, r = a % b  (b != 0): schoolbook long division in base 2^32 (Knuth, algorithm D)
 static void divmod(const Big &a, const Big &b, Big &q, Big &r) {
     q = Big();
     r = Big();
-    size_t n = bits(a);
-    q.d.assign((n + 31) / 32, 0);
-    for (size_t i = n; i-- > 0;) {
-        shl1_or(r, bit(a, i));
-        if (cmp(r, b) >= 0) {
-            r = sub(r, b);
-            q.d[i >> 5] |= 1u << (i & 31);
+    const size_t n = b.d.size(), la = a.d.size();
+    if (la < n) { r = a; return; }
+    if (n == 1) {
+        q = a;
+        uint32_t rem = divmod_small(q, b.d[0]);
+        if (rem) r.d.push_back(rem);
+        return;
+    }
+    const int sh = __builtin_clz(b.d[n - 1]);
+    // normalised copies: v = b << sh (n limbs), u = a << sh (la + 1 limbs)
+    uint32_t v[Limbs::CAP], u[Limbs::CAP + 1];
+    for (size_t i = n; i-- > 0;)
+        v[i] = sh ? (b.d[i] << sh) | (i ? b.d[i - 1] >> (32 - sh) : 0) : b.d[i];
+    u[la] = sh ? a.d[la - 1] >> (32 - sh) : 0;
+    for (size_t i = la; i-- > 0;)
+        u[i] = sh ? (a.d[i] << sh) | (i ? a.d[i - 1] >> (32 - sh) : 0) : a.d[i];
+    const size_t m = la - n;
+    q.d.assign(m + 1, 0);
+    for (size_t j = m + 1; j-- > 0;) {
+        const uint64_t num = ((uint64_t)u[j + n] << 32) | u[j + n - 1];
+        uint64_t qhat = num / v[n - 1], rhat = num % v[n - 1];
+        while (qhat >> 32 || qhat * v[n - 2] > ((rhat << 32) | u[j + n - 2])) {
+            --qhat;
+            rhat += v[n - 1];
+            if (rhat >> 32) break;
         }
+        // u[j .. j+n] -= qhat * v
+        int64_t borrow = 0;
+        uint64_t carry = 0;
+        for (size_t i = 0; i < n; ++i) {
+            const uint64_t p = qhat * v[i] + carry;
+            carry = p >> 32;
+            const int64_t t = (int64_t)u[i + j] - borrow - (int64_t)(p & 0xFFFFFFFFull);
+            u[i + j] = (uint32_t)t;
+            borrow = t < 0 ? 1 : 0;
+        }
+        const int64_t t = (int64_t)u[j + n] - borrow - (int64_t)carry;
+        u[j + n] = (uint32_t)t;
+        if (t < 0) {   // qhat was one too large: add v back
+            --qhat;
+            uint64_t c = 0;
+            for (size_t i = 0; i < n; ++i) {
+                const uint64_t sum = (uint64_t)u[i + j] + v[i] + c;
+                u[i + j] = (uint32_t)sum;
+                c = sum >> 32;
+            }
+            u[j + n] += (uint32_t)c;
+        }
+        q.d[j] = (uint32_t)qhat;
     }
     q.trim();
+    r.d.assign(n, 0);
+    for (size_t i = 0; i < n; ++i)
+        r.d[i] = sh ? (u[i] >> sh) | ((uint64_t)u[i + 1] << (32 - sh)) : u[i];
+    r.trim();
 }
 static Big pow10(unsigned e) {
     Big r(1);
@@ -143,20 +207,29 @@ static Big pow10(unsigned e) {
     if (e) r = mul_small(r, p[e]);
     return r;
 }
-// floor(sqrt(a)), bit by bit
+// floor(sqrt(a)): Newton's iteration from above, x <- (x + a / x) / 2 until it stops decreasing
 static Big isqrt(const Big &a) {
-    Big r;
-    size_t n = (bits(a) + 1) / 2;      // the root has at most n bits
-    r.d.assign((n >> 5) + 1, 0);
-    for (size_t i = n; i-- > 0;) {
-        Big t = r;
-        t.d[i >> 5] |= 1u << (i & 31);
-        Big tt = t;
-        tt.trim();
-        if (cmp(mul(tt, tt), a) <= 0) r = t;
+    if (a.zero()) return Big();
+    const size_t nb = (bits(a) + 1) / 2;
+    Big x;                                     // 2^nb >= sqrt(a)
+    x.d.assign(nb / 32 + 1, 0);
+    x.d[nb / 32] = 1u << (nb % 32);
+    x.trim();
+    for (;;) {
+        Big qd, rd;
+        divmod(a, x, qd, rd);
+        Big y = add(x, qd);
+        // y >>= 1
+        uint32_t carry = 0;
+        for (size_t i = y.d.size(); i-- > 0;) {
+            const uint32_t nc = y.d[i] & 1u;
+            y.d[i] = (y.d[i] >> 1) | (carry << 31);
+            carry = nc;
+        }
+        y.trim();
+        if (cmp(y, x) >= 0) return x;
+        x = y;
     }
-    r.trim();
-    return r;
 }
 static std::string to_string(Big a) {
     if (a.zero()) return "0";

@@ -318,7 +318,10 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
                                      : std::min<uint64_t>(2 * (known + expect), std::max<uint64_t>(1ull << 24, 4 * known));
     int rc = grow_table(c, want);
     if (rc) return rc;
-    rc = grow_irr(c, std::max<uint64_t>(1ull << 12, 4 * c->h_ctr->n_irr_unique));
+    // irregular k-mers (an N in the window, short windows of step > 1): a small share of the emissions
+    // for the filter kernel, potentially all of them for the line kernel
+    rc = grow_irr(c, std::max<uint64_t>(std::max<uint64_t>(1ull << 12, 4 * c->h_ctr->n_irr_unique),
+                                        c->use_filter ? expect / 32 : std::min<uint64_t>(expect, 1ull << 22)));
     if (rc) return rc;
     // spill lists: the table is sized for the expected load, so spills are the exception; the line
     // kernel (every window is an emission) gets the worst case of its 4 MiB pieces

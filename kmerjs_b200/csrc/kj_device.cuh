@@ -6,6 +6,7 @@
 
 #define KJ_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define KJ_MAX_PROBE 1024
+#define KJ_MAX_PROBE_IRR 128      // side table: every probe compares 32-byte keys
 
 // error bits raised by kernels (KjCounters::error_flags)
 #define KJ_DEV_E_LINE_TOO_LONG 1u      // position does not fit KJ_POS_BITS
@@ -107,7 +108,7 @@ static __device__ __noinline__ bool kj_insert_irr(const KjIrrTable &t, KjCounter
                                            uint64_t add) {
     uint64_t slot = kj_hash_bytes(key32, len) & t.mask;
     const uint64_t *kw = reinterpret_cast<const uint64_t *>(key32);
-    for (int probe = 0; probe < KJ_MAX_PROBE; ++probe) {
+    for (int probe = 0; probe < KJ_MAX_PROBE_IRR; ++probe) {
         uint32_t st = kj_ld_volatile(&t.state[slot]);
         if (st == 0) {
             st = atomicCAS(&t.state[slot], 0u, 1u);

@@ -38,6 +38,10 @@
 #define KJ_NO_TILE 0xFFFFFFFFu
 #define KJ_SLOTS 3                                       // stream -> emit hand-over slots
 #define KJ_REC_BLOCK 256u                                // candidate records reserved per emit warp at a time
+// named barriers of the filter kernel (0: __syncthreads, 1: stream warps)
+#define KJ_NB_CTL 2                                      // +0/+1: stream warp 0 -> control warp, alternating
+#define KJ_NB_FULL 4                                     // +slot: control warp -> emit warps
+#define KJ_NB_EMPTY 7                                    // +slot: emit warps -> stream warps
 
 #define KJ_ST_AGG 1ull
 #define KJ_ST_INC 2ull
@@ -174,6 +178,8 @@ __device__ __forceinline__ void kj_bar_wait(uint64_t *bar, uint32_t parity) {
 }
 #define kj_bar_wait_idle kj_bar_wait
 __device__ __forceinline__ void kj_sync_stream() { emu_named_barrier(1, KJ_STHREADS); }
+__device__ __forceinline__ void kj_nbar_sync(uint32_t id, uint32_t count) { emu_named_barrier((int)id, (int)count); }
+__device__ __forceinline__ void kj_nbar_arrive(uint32_t id, uint32_t count) { emu_named_arrive((int)id, (int)count); }
 #else
 __device__ __forceinline__ uint32_t kj_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void kj_bar_init(uint64_t *bar, uint32_t count) {
@@ -218,6 +224,15 @@ __device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t
     } while (0)
 // barrier of the 7 stream warps of the filter kernel (control and emit warps do not take part)
 __device__ __forceinline__ void kj_sync_stream() { asm volatile("bar.sync 1, %0;" ::"n"(KJ_STHREADS) : "memory"); }
+// producer / consumer hand-over between warp groups on a hardware named barrier: the producer group
+// arrives and goes on, the consumer group blocks (no polling, no issue slots) until `count` threads
+// of both groups have arrived.  One hand-over may be outstanding per barrier id.
+__device__ __forceinline__ void kj_nbar_sync(uint32_t id, uint32_t count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void kj_nbar_arrive(uint32_t id, uint32_t count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 #endif
 
 // one 16-byte chunk -> code word, newline mask, row count (warp = 32 consecutive chunks = one row)
@@ -602,7 +617,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ uint32_t tile_of[KJ_SLOTS];                      // tile in the slot (KJ_NO_TILE: no more work)
     __shared__ uint32_t tile_next;                              // ticket fetched ahead
     __shared__ KjCtlCmd ctl[2];
-    __shared__ __align__(8) uint64_t bar_load, bar_full[KJ_SLOTS], bar_empty[KJ_SLOTS], bar_ctl[2];
+    __shared__ __align__(8) uint64_t bar_load;                  // completion of the copy in flight
     KJ_DYN_SMEM(stage);                                         // KJ_STAGE_BYTES: raw bytes of the tile in flight
     const uint32_t tid = threadIdx.x;
     // a tile travels through `stage` when it and the 32 bytes behind it are owned and readable
@@ -618,8 +633,6 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
 
     if (tid == 0) {
         kj_bar_init(&bar_load, 1);
-        kj_bar_init(&bar_ctl[0], 1); kj_bar_init(&bar_ctl[1], 1);
-        for (int i = 0; i < KJ_SLOTS; ++i) { kj_bar_init(&bar_full[i], 1); kj_bar_init(&bar_empty[i], KJ_ETHREADS); }
 #if defined(__CUDA_ARCH__)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -630,18 +643,18 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
 
     if (tid < KJ_CTHREADS) {
         // ------------------------------------------------------------------ control warp
-        uint32_t phc = 0, seq = 0;
+        uint32_t seq = 0;
         for (;;) {
             const uint32_t kk = seq & 1u;
-            kj_bar_wait_idle(&bar_ctl[kk], (phc >> kk) & 1u);
-            phc ^= 1u << kk;
+            kj_nbar_sync(KJ_NB_CTL + kk, 32 + KJ_CTHREADS);      // a command from stream warp 0
             ++seq;
             const KjCtlCmd cmd = ctl[kk];
             if (cmd.scan_tile != KJ_NO_TILE) kj_tile_rowscan_warp(a, meta[cmd.scan_slot], cmd.scan_tile);
             if (cmd.lb_tile != KJ_NO_TILE) {
                 kj_lookback(a, meta[cmd.lb_slot], cmd.lb_tile);
+                if (tid == 0) tile_of[cmd.lb_slot] = cmd.lb_tile;
                 __syncwarp();
-                if (tid == 0) { tile_of[cmd.lb_slot] = cmd.lb_tile; kj_bar_arrive(&bar_full[cmd.lb_slot]); }
+                kj_nbar_arrive(KJ_NB_FULL + cmd.lb_slot, KJ_CTHREADS + KJ_ETHREADS);
             }
             if (cmd.scan_tile == KJ_NO_TILE) break;          // nothing behind it
         }
@@ -651,13 +664,12 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     if (tid >= KJ_CTHREADS + KJ_STHREADS) {
         // ------------------------------------------------------------------ emit warps
         const uint32_t et = tid - (KJ_CTHREADS + KJ_STHREADS);
-        uint32_t n_emit = 0, phf = 0, b = 0;           // phf bit s: parity of the next full phase of slot s
+        uint32_t n_emit = 0, b = 0;
         long long n_bases = 0;
         unsigned long long blk_base = KJ_REC_NONE;      // this warp's block of record slots
         uint32_t blk_used = KJ_REC_BLOCK;
         for (;;) {
-            kj_bar_wait_idle(&bar_full[b], (phf >> b) & 1u);
-            phf ^= 1u << b;
+            kj_nbar_sync(KJ_NB_FULL + b, KJ_CTHREADS + KJ_ETHREADS);   // slot b handed over (by the control warp, or the stop mark)
             const uint32_t tile = tile_of[b];
             if (tile == KJ_NO_TILE) break;
             const KjTileSmem &m = meta[b];
@@ -713,7 +725,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                     if (a.n_strands > 1) kj_verify_candidate(a, m, tile_off, tile_voff, jt, 1u, n_emit);
                 }
             }
-            kj_bar_arrive(&bar_empty[b]);
+            kj_nbar_arrive(KJ_NB_EMPTY + b, KJ_ETHREADS + KJ_STHREADS);
             b = (b + 1u == KJ_SLOTS) ? 0u : b + 1u;
         }
         if (blk_base != KJ_REC_NONE)               // unused tail of the last block
@@ -731,13 +743,13 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
 
     // ---------------------------------------------------------------------- stream warps
     const uint32_t st = tid - KJ_CTHREADS;
-    uint32_t ph_load = 0, phe = 0;                  // phase parities: copy in flight, slot-empty barriers (bit s)
-    uint32_t handed = 0;                            // bit s: slot s has been handed over before
+    uint32_t ph_load = 0;                           // phase parity of the copy in flight
+    uint32_t handed = 0;                            // bit s: slot s has been handed over and not waited for yet
     uint32_t cseq = 0;                              // commands sent to the control warp
     auto wait_slot_free = [&](uint32_t sl) {
         if (handed & (1u << sl)) {
-            kj_bar_wait(&bar_empty[sl], (phe >> sl) & 1u);
-            phe ^= 1u << sl;
+            kj_nbar_sync(KJ_NB_EMPTY + sl, KJ_ETHREADS + KJ_STHREADS);
+            handed &= ~(1u << sl);
         }
     };
     auto next_slot = [](uint32_t sl) { return (sl + 1u == KJ_SLOTS) ? 0u : sl + 1u; };
@@ -752,18 +764,22 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
             kj_tile_p1_global<KJ_STHREADS>(a, codes, m, tile, st);
         }
     };
-    auto send_cmd = [&](uint32_t lb_tile, uint32_t lb_slot, uint32_t scan_tile, uint32_t scan_slot) {   // thread st == 0
+    auto send_cmd = [&](uint32_t lb_tile, uint32_t lb_slot, uint32_t scan_tile, uint32_t scan_slot) {   // stream warp 0
         const uint32_t kk = cseq & 1u;
-        ctl[kk].lb_tile = lb_tile; ctl[kk].lb_slot = lb_slot;
-        ctl[kk].scan_tile = scan_tile; ctl[kk].scan_slot = scan_slot;
-        kj_bar_arrive(&bar_ctl[kk]);
+        if (st == 0) {
+            ctl[kk].lb_tile = lb_tile; ctl[kk].lb_slot = lb_slot;
+            ctl[kk].scan_tile = scan_tile; ctl[kk].scan_slot = scan_slot;
+        }
+        __syncwarp();
+        kj_nbar_arrive(KJ_NB_CTL + kk, 32 + KJ_CTHREADS);
     };
 
     uint32_t cur = tile_next, b = 0;
     if (cur < a.n_tiles) {
         convert(cur, meta[0]);
         kj_sync_stream();
-        if (st == 0) { take_ticket(); send_cmd(KJ_NO_TILE, 0, cur, 0); }
+        if (st == 0) take_ticket();
+        if (st < 32) send_cmd(KJ_NO_TILE, 0, cur, 0);
         ++cseq;
         for (;;) {
             const uint64_t tile_off = (uint64_t)cur * KJ_TILE_BYTES;
@@ -779,10 +795,8 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                 convert(nxt, meta[nb]);
                 kj_sync_stream();                          // `stage` is free again
             }
-            if (st == 0) {
-                if (nxt < a.n_tiles) take_ticket();
-                send_cmd(cur, b, nxt < a.n_tiles ? nxt : KJ_NO_TILE, nb);
-            }
+            if (st == 0 && nxt < a.n_tiles) take_ticket();
+            if (st < 32) send_cmd(cur, b, nxt < a.n_tiles ? nxt : KJ_NO_TILE, nb);
             ++cseq;
             handed |= 1u << b;
             if (nxt >= a.n_tiles) break;
@@ -791,10 +805,14 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
         }
         b = next_slot(b);                                  // the slot after the last tile carries the stop mark
     } else {
-        if (st == 0) send_cmd(KJ_NO_TILE, 0, KJ_NO_TILE, 0);
+        if (st < 32) send_cmd(KJ_NO_TILE, 0, KJ_NO_TILE, 0);
     }
     wait_slot_free(b);
-    if (st == 0) { tile_of[b] = KJ_NO_TILE; kj_bar_arrive(&bar_full[b]); }
+    if (st < 32) {       // stop mark for the emit warps, by the warp that would otherwise be the control warp's producer
+        if (st == 0) tile_of[b] = KJ_NO_TILE;
+        __syncwarp();
+        kj_nbar_arrive(KJ_NB_FULL + b, KJ_CTHREADS + KJ_ETHREADS);
+    }
 }
 
 // ----------------------------------------------------------------------------- line-oriented kernel

@@ -112,6 +112,7 @@ uint8_t *emu_dyn_smem();
 void emu_yield();
 void emu_syncthreads();
 void emu_named_barrier(int id, int count);           // bar.sync id, count
+void emu_named_arrive(int id, int count);            // bar.arrive id, count
 uint64_t emu_warp_xchg(uint64_t v, int src_lane);   // every lane deposits v, returns lane src's value
 uint32_t emu_warp_ballot(int pred);
 uint64_t emu_warp_reduce_add(uint64_t v);

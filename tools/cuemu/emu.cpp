@@ -105,6 +105,15 @@ void emu_named_barrier(int id, int expected) {
     while (b.gen == gen) { spin_guard(); emu_yield(); }
 }
 
+void emu_named_arrive(int id, int expected) {
+    NamedBar &b = g_named[id & 15];
+    if (++b.count == expected) {
+        b.count = 0;
+        ++b.gen;
+        g_idle_spins = 0;
+    }
+}
+
 unsigned emu_lane() { return threadIdx.x & 31u; }
 
 static int warp_size_of(unsigned w) {

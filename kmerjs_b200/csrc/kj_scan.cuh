@@ -35,6 +35,7 @@
 #define KJ_FTHREADS (KJ_CTHREADS + KJ_STHREADS + KJ_ETHREADS)
 #define KJ_FQCAP 256                                     // candidate queue entries per slot (~56 per tile)
 #define KJ_STAGE_BYTES (KJ_TILE_BYTES + 32)              // a tile and the 32 bytes its last windows reach into
+#define KJ_HALF_BYTES (KJ_TILE_BYTES / 2)                // the tile is copied and converted in two halves
 #define KJ_NO_TILE 0xFFFFFFFFu
 #define KJ_SLOTS 3                                       // stream -> emit hand-over slots
 #define KJ_REC_BLOCK 256u                                // candidate records reserved per emit warp at a time
@@ -245,19 +246,19 @@ __device__ __forceinline__ void kj_p1_chunk(uint32_t *codes, KjTileSmem &s, uint
     if ((threadIdx.x & 31) == 0) s.row_pre[row] = rc;
 }
 
-// P1 from the staged tile (interior tiles: every byte owned, halo readable) by a group of NT threads,
-// t = index in the group.  The caller synchronises.
-template <int NT>
+// P1 of one half of the staged tile (interior tiles: every byte owned, halo readable) by a group of
+// NT threads, t = index in the group.  The caller synchronises.
+template <int NT, int HALF>
 __device__ __forceinline__ void kj_tile_p1_stage(uint32_t *codes, KjTileSmem &s, const uint8_t *stage, uint32_t t) {
     constexpr int CPT = KJ_TILE_CHUNKS / NT;
-    static_assert(CPT * NT == KJ_TILE_CHUNKS && NT % 32 == 0, "tile must split evenly into warp rows");
+    static_assert(CPT * NT == KJ_TILE_CHUNKS && NT % 32 == 0 && CPT % 2 == 0, "tile must split evenly into warp rows, twice");
 #pragma unroll 4
-    for (int it = 0; it < CPT; ++it) {
+    for (int it = HALF * (CPT / 2); it < (HALF + 1) * (CPT / 2); ++it) {      // the first or the second half of the tile
         const uint32_t c = it * NT + t;
         const uint4 v = *reinterpret_cast<const uint4 *>(stage + c * 16u);
         kj_p1_chunk(codes, s, c, c >> 5, v, 0xFFFFu);
     }
-    if (t < 2) {
+    if (HALF == 1 && t < 2) {
         const uint4 h = *reinterpret_cast<const uint4 *>(stage + (KJ_TILE_CHUNKS + t) * 16u);
         codes[KJ_TILE_CHUNKS + t] = kj_pack16(h.x, h.y, h.z, h.w);
     }
@@ -617,27 +618,37 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ uint32_t tile_of[KJ_SLOTS];                      // tile in the slot (KJ_NO_TILE: no more work)
     __shared__ uint32_t tile_next;                              // ticket fetched ahead
     __shared__ KjCtlCmd ctl[2];
-    __shared__ __align__(8) uint64_t bar_load;                  // completion of the copy in flight
+    __shared__ __align__(8) uint64_t bar_load[2];               // completion of the two half-tile copies in flight
     KJ_DYN_SMEM(stage);                                         // KJ_STAGE_BYTES: raw bytes of the tile in flight
     const uint32_t tid = threadIdx.x;
     // a tile travels through `stage` when it and the 32 bytes behind it are owned and readable
     const bool any_staged = a.own_n >= KJ_STAGE_BYTES;
     const uint64_t staged_end = any_staged ? a.own_n - KJ_STAGE_BYTES : 0;      // staged iff tile_off <= staged_end
 
-    auto take_ticket = [&]() {          // one thread: next tile + start of its copy
+    // The tile in flight is copied in two halves, each re-armed as soon as the stream warps have
+    // converted that half of the tile before it: with one staging buffer a copy can only run while
+    // its target is not being read, and half-tile granularity keeps a copy in flight most of the time.
+    auto start_half = [&](uint32_t t, int half) {   // one thread
+        const uint64_t off = (uint64_t)t * KJ_TILE_BYTES;
+        if (t < a.n_tiles && any_staged && off <= staged_end)
+            kj_bulk_g2s(stage + half * KJ_HALF_BYTES, a.buf + off + half * KJ_HALF_BYTES,
+                        half ? KJ_STAGE_BYTES - KJ_HALF_BYTES : KJ_HALF_BYTES, &bar_load[half]);
+    };
+    auto take_ticket = [&]() {          // one thread: next tile + start of the copy of its first half
         const uint32_t t = atomicAdd(&a.ctr->ticket, 1u);
         tile_next = t;
-        const uint64_t off = (uint64_t)t * KJ_TILE_BYTES;
-        if (t < a.n_tiles && any_staged && off <= staged_end) kj_bulk_g2s(stage, a.buf + off, KJ_STAGE_BYTES, &bar_load);
+        start_half(t, 0);
     };
 
     if (tid == 0) {
-        kj_bar_init(&bar_load, 1);
+        kj_bar_init(&bar_load[0], 1);
+        kj_bar_init(&bar_load[1], 1);
 #if defined(__CUDA_ARCH__)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
         take_ticket();
+        start_half(tile_next, 1);
     }
     __syncthreads();
 
@@ -753,15 +764,24 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
         }
     };
     auto next_slot = [](uint32_t sl) { return (sl + 1u == KJ_SLOTS) ? 0u : sl + 1u; };
-    auto convert = [&](uint32_t tile, KjTileSmem &m) {   // P1 of `tile` into codes / m
+    // P1 of `tile` into codes / m; takes the next ticket and re-arms the copies.  Ends synchronised.
+    auto convert = [&](uint32_t tile, KjTileSmem &m) {
         if (st == 0) m.q_n = 0;
         const uint64_t off = (uint64_t)tile * KJ_TILE_BYTES;
         if (any_staged && off <= staged_end) {
-            kj_bar_wait(&bar_load, ph_load);
+            kj_bar_wait(&bar_load[0], ph_load);
+            kj_tile_p1_stage<KJ_STHREADS, 0>(codes, m, stage, st);
+            kj_sync_stream();                              // first half of `stage` is free
+            if (st == 0) take_ticket();
+            kj_bar_wait(&bar_load[1], ph_load);
             ph_load ^= 1u;
-            kj_tile_p1_stage<KJ_STHREADS>(codes, m, stage, st);
+            kj_tile_p1_stage<KJ_STHREADS, 1>(codes, m, stage, st);
+            kj_sync_stream();                              // second half is free
+            if (st == 0) start_half(tile_next, 1);
         } else {
             kj_tile_p1_global<KJ_STHREADS>(a, codes, m, tile, st);
+            kj_sync_stream();
+            if (st == 0) { take_ticket(); start_half(tile_next, 1); }
         }
     };
     auto send_cmd = [&](uint32_t lb_tile, uint32_t lb_slot, uint32_t scan_tile, uint32_t scan_slot) {   // stream warp 0
@@ -777,8 +797,6 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     uint32_t cur = tile_next, b = 0;
     if (cur < a.n_tiles) {
         convert(cur, meta[0]);
-        kj_sync_stream();
-        if (st == 0) take_ticket();
         if (st < 32) send_cmd(KJ_NO_TILE, 0, cur, 0);
         ++cseq;
         for (;;) {
@@ -793,9 +811,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
             if (nxt < a.n_tiles) {
                 wait_slot_free(nb);                        // the emit warps may lag KJ_SLOTS - 1 tiles behind
                 convert(nxt, meta[nb]);
-                kj_sync_stream();                          // `stage` is free again
             }
-            if (st == 0 && nxt < a.n_tiles) take_ticket();
             if (st < 32) send_cmd(cur, b, nxt < a.n_tiles ? nxt : KJ_NO_TILE, nb);
             ++cseq;
             handed |= 1u << b;

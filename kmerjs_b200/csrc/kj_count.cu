@@ -346,7 +346,7 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
         if (want_rec > c->cand_cap) {
             kj_dfree(ctx, c->cand);
             c->cand = nullptr; c->cand_cap = 0;
-            KJ_CUDA(ctx, kj_dmalloc(ctx, &c->cand, want_rec * 16));
+            KJ_CUDA(ctx, kj_dmalloc(ctx, &c->cand, want_rec * 8 * KJ_REC_WORDS));
             c->cand_cap = want_rec;
         }
         KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_cand, 0, sizeof(unsigned long long), ctx->stream));

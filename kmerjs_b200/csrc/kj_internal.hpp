@@ -106,7 +106,7 @@ struct kj_counts {
     KjCounters *h_ctr = nullptr;      // pinned mirror
     uint64_t *tile_mem = nullptr;     // tile_cap u64 (look-back status words)
     uint64_t tile_cap = 0;
-    uint64_t *cand = nullptr;         // candidate records of the launch in flight (filter kernel), 16 bytes each
+    uint64_t *cand = nullptr;         // candidate records of the launch in flight (filter kernel), 64 bytes each
     uint64_t cand_cap = 0;
     // results
     KjCompact reg{};

@@ -80,7 +80,7 @@ struct KjScanArgs {
     KjIrrTable irr;
     KjOverflow ovf;
     uint64_t *status;     // per tile: flag << 62 | newline count; zeroed before every launch
-    uint64_t *cand;       // candidate records {position | strand << 63, ordinal} of this launch (filter kernel)
+    uint64_t *cand;       // candidate records (KJ_REC_WORDS u64 each) of this launch (filter kernel)
     uint64_t cand_cap;    // in records
     KjCounters *ctr;
 };
@@ -424,8 +424,9 @@ __device__ __forceinline__ KjRowBits kj_row_bits(const KjTileSmem &s, uint32_t j
 //
 // Part A, from the tile's newline bitmap in shared memory (emit warps of the scan kernel): is the
 // line a sequence line (index 1 mod 4, lib/kmers.js:151) and, if first-seen order is tracked, the
-// ordinal (read index, strand, column).  Survivors become 16-byte records {position | strand << 63,
-// ordinal} in global memory.
+// ordinal (read index, strand, column).  Survivors become 64-byte records {position | strand << 63,
+// ordinal, the three 16-byte chunks that hold the window} in global memory: the chunks are L2 hits
+// for the emit warps (the tile was streamed in a moment ago) and part B never touches the input again.
 //
 // Part B, from the window's bytes (kj_verify_kernel, one thread per record, the whole GPU at once):
 // exact prefix / newline / alphabet check and the hash-table update.  It is a chain of L2 round
@@ -433,6 +434,7 @@ __device__ __forceinline__ KjRowBits kj_row_bits(const KjTileSmem &s, uint32_t j
 // as a separate wide kernel its latency disappears behind parallelism.
 #define KJ_REC_STRAND (1ull << 63)
 #define KJ_REC_NONE 0xFFFFFFFFFFFFFFFFull
+#define KJ_REC_WORDS 8      // u64 words per record: position | strand, ordinal, 48 bytes of the window's chunks
 
 // Part A.  false: not in a sequence line (or an error was flagged).
 __device__ __forceinline__ bool kj_candidate_line(const KjScanArgs &a, const KjTileSmem &s, uint64_t tile_off,
@@ -467,17 +469,21 @@ __device__ __forceinline__ bool kj_candidate_line(const KjScanArgs &a, const KjT
     return true;
 }
 
-// Part B: the window at buffer offset j.  Straight-line SIMD-in-register code.
+// the window's bytes: the (at most) three aligned 16-byte chunks that hold buf[j, j + k), requested together
+__device__ __forceinline__ void kj_window_load(const KjScanArgs &a, uint64_t j, uint4 &v0, uint4 &v1, uint4 &v2) {
+    const uint64_t base = j & ~15ull;
+    v0 = kj_load_chunk(a.buf, base, a.n);
+    v1 = make_uint4(0, 0, 0, 0);
+    v2 = make_uint4(0, 0, 0, 0);
+    if (base + 16u < j + a.k) v1 = kj_load_chunk(a.buf, base + 16u, a.n);
+    if (base + 32u < j + a.k) v2 = kj_load_chunk(a.buf, base + 32u, a.n);
+}
+
+// Part B: the window at buffer offset j, its chunks already loaded.  Straight-line SIMD-in-register code.
 __device__ __forceinline__ void kj_window_emit(const KjScanArgs &a, uint64_t j, uint32_t strand, uint64_t ord,
-                                               uint32_t &n_emit) {
+                                               const uint4 v0, const uint4 v1, const uint4 v2, uint32_t &n_emit) {
     const uint32_t k = a.k;
-    if (j + k > a.n) return;                              // window must lie inside the stream
-    // the window's bytes: at most three aligned 16-byte chunks, requested together
     const uint32_t o = (uint32_t)(j & 15u);
-    const uint64_t base = j - o;
-    uint4 v0 = kj_load_chunk(a.buf, base, a.n), v1 = make_uint4(0, 0, 0, 0), v2 = make_uint4(0, 0, 0, 0);
-    if (base + 16u < j + k) v1 = kj_load_chunk(a.buf, base + 16u, a.n);
-    if (base + 32u < j + k) v2 = kj_load_chunk(a.buf, base + 32u, a.n);
     // window bytes 0..31 in X[0..7]: shift the 48 loaded bytes down by o
     const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
     const uint32_t q = o >> 2, r8 = (o & 3u) * 8u;
@@ -523,8 +529,12 @@ static __device__ __noinline__ void kj_verify_candidate(const KjScanArgs &a, con
                                                         uint64_t tile_off, uint64_t tile_voff,
                                                         uint32_t jt, uint32_t strand, uint32_t &n_emit) {
     uint64_t ord;
-    if (tile_off + jt + a.k > a.n) return;
-    if (kj_candidate_line(a, s, tile_off, tile_voff, jt, strand, ord)) kj_window_emit(a, tile_off + jt, strand, ord, n_emit);
+    if (tile_off + jt + a.k > a.n) return;                // window must lie inside the stream
+    if (kj_candidate_line(a, s, tile_off, tile_voff, jt, strand, ord)) {
+        uint4 v0, v1, v2;
+        kj_window_load(a, tile_off + jt, v0, v1, v2);
+        kj_window_emit(a, tile_off + jt, strand, ord, v0, v1, v2, n_emit);
+    }
 }
 
 // Part B over the records of one launch.
@@ -533,9 +543,11 @@ __global__ void __launch_bounds__(256) kj_verify_kernel(const __grid_constant__ 
     uint32_t n_emit = 0;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_res;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(a.cand + 2 * i);
+        const uint4 *rp = reinterpret_cast<const uint4 *>(a.cand + KJ_REC_WORDS * i);
+        const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(rp);
         if (r.x == KJ_REC_NONE) continue;                  // unused tail of a reserved block
-        kj_window_emit(a, r.x & ~KJ_REC_STRAND, (uint32_t)(r.x >> 63), r.y, n_emit);
+        const uint4 v0 = rp[1], v1 = rp[2], v2 = rp[3];    // the window's chunks travel in the record
+        kj_window_emit(a, r.x & ~KJ_REC_STRAND, (uint32_t)(r.x >> 63), r.y, v0, v1, v2, n_emit);
     }
     for (int d = 16; d > 0; d >>= 1) n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
     if ((threadIdx.x & 31) == 0 && n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);
@@ -711,7 +723,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                     if (blk_used + need > KJ_REC_BLOCK) {
                         // retire the block (mark its unused tail), reserve a new one
                         if (blk_base != KJ_REC_NONE)
-                            for (uint32_t i = blk_used + (tid & 31); i < KJ_REC_BLOCK; i += 32) a.cand[2 * (blk_base + i)] = KJ_REC_NONE;
+                            for (uint32_t i = blk_used + (tid & 31); i < KJ_REC_BLOCK; i += 32) a.cand[KJ_REC_WORDS * (blk_base + i)] = KJ_REC_NONE;
                         unsigned long long nb_ = 0;
                         if ((tid & 31) == 0) nb_ = atomicAdd(&a.ctr->n_cand, (unsigned long long)KJ_REC_BLOCK);
                         nb_ = __shfl_sync(0xFFFFFFFFu, nb_, 0);
@@ -721,11 +733,17 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                     if (blk_base != KJ_REC_NONE) {
                         if (keep) {
                             const unsigned long long at = blk_base + blk_used + __popc(kb & ((1u << (tid & 31)) - 1u));
-                            *reinterpret_cast<ulonglong2 *>(a.cand + 2 * at) = make_ulonglong2(rec, ord);
+                            uint4 v0, v1, v2;
+                            kj_window_load(a, rec & ~KJ_REC_STRAND, v0, v1, v2);
+                            uint4 *rp = reinterpret_cast<uint4 *>(a.cand + KJ_REC_WORDS * at);
+                            *reinterpret_cast<ulonglong2 *>(rp) = make_ulonglong2(rec, ord);
+                            rp[1] = v0; rp[2] = v1; rp[3] = v2;
                         }
                         blk_used += need;
                     } else if (keep) {
-                        kj_window_emit(a, rec & ~KJ_REC_STRAND, (uint32_t)(rec >> 63), ord, n_emit);   // buffer full: in place
+                        uint4 v0, v1, v2;                   // buffer full: in place
+                        kj_window_load(a, rec & ~KJ_REC_STRAND, v0, v1, v2);
+                        kj_window_emit(a, rec & ~KJ_REC_STRAND, (uint32_t)(rec >> 63), ord, v0, v1, v2, n_emit);
                     }
                 }
             } else {
@@ -740,7 +758,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
             b = (b + 1u == KJ_SLOTS) ? 0u : b + 1u;
         }
         if (blk_base != KJ_REC_NONE)               // unused tail of the last block
-            for (uint32_t i = blk_used + (tid & 31); i < KJ_REC_BLOCK; i += 32) a.cand[2 * (blk_base + i)] = KJ_REC_NONE;
+            for (uint32_t i = blk_used + (tid & 31); i < KJ_REC_BLOCK; i += 32) a.cand[KJ_REC_WORDS * (blk_base + i)] = KJ_REC_NONE;
         for (int d = 16; d > 0; d >>= 1) {       // one atomic per warp
             n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
             n_bases += __shfl_xor_sync(0xFFFFFFFFu, n_bases, d);
@@ -764,24 +782,25 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
         }
     };
     auto next_slot = [](uint32_t sl) { return (sl + 1u == KJ_SLOTS) ? 0u : sl + 1u; };
-    // P1 of `tile` into codes / m; takes the next ticket and re-arms the copies.  Ends synchronised.
-    auto convert = [&](uint32_t tile, KjTileSmem &m) {
+    // P1 of `tile` into codes / m; publishes the ticket taken ahead (t_ahead, thread st == 0) and
+    // re-arms the copies.  Ends synchronised.
+    auto convert = [&](uint32_t tile, KjTileSmem &m, uint32_t t_ahead) {
         if (st == 0) m.q_n = 0;
         const uint64_t off = (uint64_t)tile * KJ_TILE_BYTES;
         if (any_staged && off <= staged_end) {
             kj_bar_wait(&bar_load[0], ph_load);
             kj_tile_p1_stage<KJ_STHREADS, 0>(codes, m, stage, st);
             kj_sync_stream();                              // first half of `stage` is free
-            if (st == 0) take_ticket();
+            if (st == 0) { tile_next = t_ahead; start_half(t_ahead, 0); }
             kj_bar_wait(&bar_load[1], ph_load);
             ph_load ^= 1u;
             kj_tile_p1_stage<KJ_STHREADS, 1>(codes, m, stage, st);
             kj_sync_stream();                              // second half is free
-            if (st == 0) start_half(tile_next, 1);
+            if (st == 0) start_half(t_ahead, 1);
         } else {
             kj_tile_p1_global<KJ_STHREADS>(a, codes, m, tile, st);
             kj_sync_stream();
-            if (st == 0) { take_ticket(); start_half(tile_next, 1); }
+            if (st == 0) { tile_next = t_ahead; start_half(t_ahead, 0); start_half(t_ahead, 1); }
         }
     };
     auto send_cmd = [&](uint32_t lb_tile, uint32_t lb_slot, uint32_t scan_tile, uint32_t scan_slot) {   // stream warp 0
@@ -796,10 +815,18 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
 
     uint32_t cur = tile_next, b = 0;
     if (cur < a.n_tiles) {
-        convert(cur, meta[0]);
+        {
+            uint32_t t_ahead = 0;
+            if (st == 0) t_ahead = atomicAdd(&a.ctr->ticket, 1u);
+            convert(cur, meta[0], t_ahead);
+        }
         if (st < 32) send_cmd(KJ_NO_TILE, 0, cur, 0);
         ++cseq;
         for (;;) {
+            // the ticket after the next one is requested now: the round trip of the atomic hides behind the
+            // search instead of holding up the barrier in convert()
+            uint32_t t_ahead = 0;
+            if (st == 0) t_ahead = atomicAdd(&a.ctr->ticket, 1u);
             const uint64_t tile_off = (uint64_t)cur * KJ_TILE_BYTES;
             const uint32_t own_in_tile =
                 (a.own_n - tile_off < KJ_TILE_BYTES) ? (uint32_t)(a.own_n - tile_off) : KJ_TILE_BYTES;
@@ -810,7 +837,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
             const uint32_t nb = next_slot(b);
             if (nxt < a.n_tiles) {
                 wait_slot_free(nb);                        // the emit warps may lag KJ_SLOTS - 1 tiles behind
-                convert(nxt, meta[nb]);
+                convert(nxt, meta[nb], t_ahead);
             }
             if (st < 32) send_cmd(cur, b, nxt < a.n_tiles ? nxt : KJ_NO_TILE, nb);
             ++cseq;

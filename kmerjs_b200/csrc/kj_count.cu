@@ -219,6 +219,9 @@ static int pull_counters(kj_counts *c) {
     KJ_CUDA(ctx, cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(KjCounters), cudaMemcpyDeviceToHost,
                                  ctx->stream));
     KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long nu = 0;
+    for (int i = 0; i < 64; ++i) nu += c->h_ctr->n_unique_part[i];
+    c->h_ctr->n_unique = nu;
     return KJ_OK;
 }
 
@@ -231,7 +234,7 @@ static int grow_table(kj_counts *c, uint64_t want) {
     int rc = alloc_table(c, want, &nt);
     if (rc) return rc;
     if (c->cap) {
-        KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_unique, 0, sizeof(unsigned long long), ctx->stream));
+        KJ_CUDA(ctx, cudaMemsetAsync(c->ctr->n_unique_part, 0, sizeof(c->ctr->n_unique_part), ctx->stream));
         KJ_LAUNCH(kj_rehash_kernel, grid_for(ctx, c->cap), 256, 0, ctx->stream, c->tab, c->cap, nt, c->ctr);
         ctx->launches++;
         free_table(ctx, c->tab);
@@ -520,7 +523,7 @@ extern "C" int kj_counts_create(kj_ctx *ctx, const kj_count_params *p, kj_counts
     c->base_line = p->base_line;
     c->base_col = p->base_col;
     cudaError_t e = kj_dmalloc(ctx, &c->ctr, sizeof(KjCounters));
-    static_assert(sizeof(KjCounters) <= 512, "pinned block size");
+    static_assert(sizeof(KjCounters) <= 1024, "pinned block size");
     if (e == cudaSuccess) c->h_ctr = (KjCounters *)kj_pinned_get(ctx);
     if (e != cudaSuccess || !c->h_ctr) {
         if (e == cudaSuccess) e = cudaErrorMemoryAllocation;

@@ -9,7 +9,7 @@ int kj_fail(kj_ctx *ctx, int code, const std::string &msg) {
     return code;
 }
 
-static const size_t KJ_PIN_BLOCK = 512, KJ_PIN_BLOCKS = 256;
+static const size_t KJ_PIN_BLOCK = 1024, KJ_PIN_BLOCKS = 256;
 
 void *kj_pinned_get(kj_ctx *ctx) {
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);

@@ -40,7 +40,7 @@ struct KjOverflow {
 };
 
 struct KjCounters {
-    unsigned long long n_unique;
+    unsigned long long n_unique;       // host view: sum of n_unique_part, filled in by pull_counters
     unsigned long long n_irr_unique;
     unsigned long long n_overflow;
     unsigned long long n_irr_overflow;
@@ -54,6 +54,8 @@ struct KjCounters {
     unsigned int error_flags;
     unsigned int ticket;               // dynamic tile counter
     unsigned int pad_;
+    // new keys are counted in 64 places (same-address atomics serialise in L2; a launch can add 10^5..10^9 keys)
+    unsigned long long n_unique_part[64];
     unsigned long long n_compact;      // compaction cursors
     unsigned long long n_irr_compact;
 };
@@ -80,7 +82,7 @@ __device__ __forceinline__ bool kj_insert(const KjTable &t, KjCounters *ctr, uin
             cur = atomicCAS((unsigned long long *)&t.keys[slot], (unsigned long long)KJ_EMPTY,
                             (unsigned long long)key);
             if (cur == KJ_EMPTY) {
-                atomicAdd(&ctr->n_unique, 1ull);
+                atomicAdd(&ctr->n_unique_part[slot & 63], 1ull);
                 cur = key;
             }
         }

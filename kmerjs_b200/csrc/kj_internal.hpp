@@ -41,12 +41,12 @@ struct kj_ctx {
     uint64_t stage_cap = 0;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     // small pinned blocks (device counters mirrored to the host, WTA results): cudaMallocHost costs
-    // milliseconds, so handles borrow 512-byte blocks from a slab owned by the context
+    // milliseconds, so handles borrow 1024-byte blocks from a slab owned by the context
     uint8_t *pin_slab = nullptr;
     std::vector<void *> pin_free;
 };
 
-void *kj_pinned_get(kj_ctx *ctx);              // 512 bytes, nullptr when out of memory
+void *kj_pinned_get(kj_ctx *ctx);              // 1024 bytes, nullptr when out of memory
 void kj_pinned_put(kj_ctx *ctx, void *p);
 
 // stream-ordered device memory from the default pool (release threshold = keep everything), so

@@ -541,13 +541,22 @@ static __device__ __noinline__ void kj_verify_candidate(const KjScanArgs &a, con
 __global__ void __launch_bounds__(256) kj_verify_kernel(const __grid_constant__ KjScanArgs a) {
     const unsigned long long n_res = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;   // slots handed out
     uint32_t n_emit = 0;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_res;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
+    // two records in flight per thread: the kernel is a chain of round trips (record, key slot), so
+    // its pace is set by how many of them overlap
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_res; i += 2 * stride) {
+        const unsigned long long i2 = i + stride;
         const uint4 *rp = reinterpret_cast<const uint4 *>(a.cand + KJ_REC_WORDS * i);
+        const uint4 *rq = reinterpret_cast<const uint4 *>(a.cand + KJ_REC_WORDS * (i2 < n_res ? i2 : i));
         const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(rp);
-        if (r.x == KJ_REC_NONE) continue;                  // unused tail of a reserved block
         const uint4 v0 = rp[1], v1 = rp[2], v2 = rp[3];    // the window's chunks travel in the record
-        kj_window_emit(a, r.x & ~KJ_REC_STRAND, (uint32_t)(r.x >> 63), r.y, v0, v1, v2, n_emit);
+        ulonglong2 r2 = *reinterpret_cast<const ulonglong2 *>(rq);
+        const uint4 w0 = rq[1], w1 = rq[2], w2 = rq[3];
+        if (i2 >= n_res) r2.x = KJ_REC_NONE;
+        if (r.x != KJ_REC_NONE)                            // KJ_REC_NONE: unused tail of a reserved block
+            kj_window_emit(a, r.x & ~KJ_REC_STRAND, (uint32_t)(r.x >> 63), r.y, v0, v1, v2, n_emit);
+        if (r2.x != KJ_REC_NONE)
+            kj_window_emit(a, r2.x & ~KJ_REC_STRAND, (uint32_t)(r2.x >> 63), r2.y, w0, w1, w2, n_emit);
     }
     for (int d = 16; d > 0; d >>= 1) n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
     if ((threadIdx.x & 31) == 0 && n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);

@@ -235,7 +235,7 @@ def run_b200(args):
             owned = kdist.count_sharded(w.fastq_ptr, w.n_bytes, w.n_bytes, prefix=PREFIX, k=K, step=STEP, final=True,
                                         base_line=rank * n_reads * 4, capacity_hint=hint, flags=state.get("flags", 0),
                                         ctx=ctx)
-            dm = kdist.DistMatch(owned, tdb)
+            dm = kdist.DistMatch(owned, tdb, torch_stream=stream)
             rows = []
             try:
                 rows = list(dm.rows())
@@ -321,7 +321,7 @@ def run_b200(args):
             stream.synchronize()
             owned = kdist.count_sharded(dev_in.data_ptr(), w.n_bytes, w.n_bytes, prefix=PREFIX, k=K, step=STEP,
                                         final=True, base_line=rank * n_reads * 4, ctx=ctx)
-            dm = kdist.DistMatch(owned, tdb)
+            dm = kdist.DistMatch(owned, tdb, torch_stream=stream)
             try:
                 rows = list(dm.rows())
             except NoHitsError:

@@ -205,6 +205,11 @@ int kj_first_match_local(kj_ctx *ctx, kj_counts *q, const kj_db *db, kj_match **
 uint64_t kj_match_vec_len(kj_match *m, int which);          /* in u64 elements */
 int kj_match_get(kj_match *m, int which, void *dev_out);
 int kj_match_set(kj_match *m, int which, const void *dev_in);
+/* the same without waiting for the copy: stream-ordered on the context's stream.  For callers whose
+ * collective runs on (or is ordered against) that stream -- kj_init(device, stream) with the stream the
+ * NCCL calls are issued from -- so that a WTA round costs one host synchronisation instead of four */
+int kj_match_get_async(kj_match *m, int which, void *dev_out);
+int kj_match_set_async(kj_match *m, int which, const void *dev_in);
 int kj_match_commit(kj_match *m);
 /* override kmerMapSize (the global query size when the query is sharded over ranks) */
 int kj_match_set_query_size(kj_match *m, uint64_t kmer_map_size);

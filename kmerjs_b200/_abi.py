@@ -105,6 +105,8 @@ SIGNATURES = {
     "kj_match_vec_len": (C.c_uint64, [vp, C.c_int]),
     "kj_match_get": (C.c_int, [vp, C.c_int, vp]),
     "kj_match_set": (C.c_int, [vp, C.c_int, vp]),
+    "kj_match_get_async": (C.c_int, [vp, C.c_int, vp]),
+    "kj_match_set_async": (C.c_int, [vp, C.c_int, vp]),
     "kj_match_commit": (C.c_int, [vp]),
     "kj_match_set_query_size": (C.c_int, [vp, C.c_uint64]),
     "kj_match_hits": (C.c_uint64, [vp]),

@@ -13,6 +13,7 @@
 // first-encounter keys first_ord[T], first_idx[T] u64, rank[T] u32, the per-template CSR of
 // matched query entries toff[T+1] u64 / tq[hits] u32, qkmer[Q] u32 (DB k-mer id per query entry).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <unordered_map>
 #include "kj_internal.hpp"
@@ -79,6 +80,7 @@ struct kj_match {
     uint64_t kmer_map_size = 0;
     uint32_t max_hits = 100, hit_counter = 0;
     bool ended = false;
+    bool inflight = false;           // the argmax of the next round has been launched ahead
 };
 
 // ------------------------------------------------------------------------------------ kernels
@@ -605,7 +607,7 @@ extern "C" uint64_t kj_match_vec_len(kj_match *m, int which) {
     return n;
 }
 
-extern "C" int kj_match_get(kj_match *m, int which, void *dev_out) {
+static int match_get(kj_match *m, int which, void *dev_out, bool sync) {
     if (!m || !dev_out) return KJ_E_INVALID;
     kj_ctx *ctx = m->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -621,11 +623,13 @@ extern "C" int kj_match_get(kj_match *m, int which, void *dev_out) {
         if (rc) return rc;
     }
     if (n) KJ_CUDA(ctx, cudaMemcpyAsync(dev_out, p, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (sync) KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KJ_OK;
 }
+extern "C" int kj_match_get(kj_match *m, int which, void *dev_out) { return match_get(m, which, dev_out, true); }
+extern "C" int kj_match_get_async(kj_match *m, int which, void *dev_out) { return match_get(m, which, dev_out, false); }
 
-extern "C" int kj_match_set(kj_match *m, int which, const void *dev_in) {
+static int match_set(kj_match *m, int which, const void *dev_in, bool sync) {
     if (!m || !dev_in) return KJ_E_INVALID;
     kj_ctx *ctx = m->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -644,9 +648,11 @@ extern "C" int kj_match_set(kj_match *m, int which, const void *dev_in) {
         p = m->d_glob;
     }
     if (n) KJ_CUDA(ctx, cudaMemcpyAsync(p, dev_in, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (sync) KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KJ_OK;
 }
+extern "C" int kj_match_set(kj_match *m, int which, const void *dev_in) { return match_set(m, which, dev_in, true); }
+extern "C" int kj_match_set_async(kj_match *m, int which, const void *dev_in) { return match_set(m, which, dev_in, false); }
 
 extern "C" int kj_match_set_query_size(kj_match *m, uint64_t kmer_map_size) {
     if (!m) return KJ_E_INVALID;
@@ -760,10 +766,29 @@ extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
             return kj_fail(ctx, KJ_E_NO_WINNER, "No hits were found! (kmerResults.length === 0)");
         return 0;
     }
-    KJ_LAUNCH(kj_argmax_kernel, 1, 1024, 0, ctx->stream, m->d_glob, m->d_rank, m->T, m->db->d_ulen,
-              (double)m->db->s_unique_lens, (double)m->db->s_templates, m->d_res);
-    ctx->launches++;
-    KJ_CUDA(ctx, cudaMemcpyAsync(m->h_res, m->d_res, sizeof(KjWtaResult), cudaMemcpyDeviceToHost, ctx->stream));
+    auto launch_argmax = [&]() -> int {
+        KJ_LAUNCH(kj_argmax_kernel, 1, 1024, 0, ctx->stream, m->d_glob, m->d_rank, m->T, m->db->d_ulen,
+                  (double)m->db->s_unique_lens, (double)m->db->s_templates, m->d_res);
+        ctx->launches++;
+        KJ_CUDA(ctx, cudaMemcpyAsync(m->h_res, m->d_res, sizeof(KjWtaResult), cudaMemcpyDeviceToHost, ctx->stream));
+        return KJ_OK;
+    };
+    // removeWinnerKmers (lib/kmerFinderClient.js:220-230) on this rank's share of K_w
+    auto launch_remove = [&](uint32_t w) -> int {
+        const uint64_t range[2] = {m->toff_h[w], m->toff_h[w + 1]};
+        if (range[1] > range[0]) {
+            const uint64_t n = range[1] - range[0];
+            const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8));
+            KJ_LAUNCH(kj_remove_kernel, grid, 256, 0, ctx->stream, m->db->dev(), m->d_tq, range[0], range[1], m->d_qkmer,
+                      m->q->reg.counts, m->q->reg.alive, m->d_part, m->T);
+            ctx->launches++;
+            KJ_CUDA(ctx, cudaGetLastError());
+        }
+        return KJ_OK;
+    };
+    int rc;
+    if (!m->inflight) { rc = launch_argmax(); if (rc) return rc; }
+    m->inflight = false;
     KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const KjWtaResult r = *m->h_res;
     // getMatches: nHits === 0 throws (lib/kmerFinderClient.js:264-266), also after earlier winners
@@ -772,6 +797,30 @@ extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
         return kj_fail(ctx, KJ_E_NO_HITS, "No hits were found! (nHits === 0)");
     }
     const uint32_t w = r.winner;
+    // The device evaluated the gate in double precision (kj_argmax_kernel).  When its z is nowhere near
+    // a fastp threshold the exact-decimal gate below cannot come out differently, so the removal (and the
+    // argmax of the next round) start now and run while the host finishes the row in exact arithmetic.
+    bool decisive = true;
+    {
+        static const double thr[27] = {10.7016, 10.4862, 10.2663, 10.0416, 9.81197, 9.5769, 9.33604, 9.08895, 8.83511,
+                                       8.57394, 8.30479, 8.02686, 7.73926, 7.4409,  7.13051, 6.8065,  6.46695, 6.10941,
+                                       5.73073, 5.32672, 4.89164, 4.41717, 3.89059, 3.29053, 2.57583, 1.95996, 1.64485};
+        for (double t : thr) if (std::fabs(r.z - t) <= 1e-6) decisive = false;
+        if (!(r.z == r.z)) decisive = false;
+        if (std::fabs(r.p - 0.05) <= 1e-9) decisive = false;      // p * templates on the evalue itself: exact arithmetic decides
+    }
+    const bool dev_accept = r.u > 0 && r.p <= 0.05;
+    bool removed = false;
+    if (decisive && dev_accept) {
+        rc = launch_remove(w);
+        if (rc) return rc;
+        removed = true;
+        if (!m->distributed && m->hit_counter + 1 < m->max_hits) {
+            rc = launch_argmax();
+            if (rc) return rc;
+            m->inflight = true;
+        }
+    }
     int accepted = 0;
     if (!kj_exact_row(ctx->rounding_mode, r.u, r.tau, m->u0[w], m->t0[w], m->db->lengths[w], m->db->ulengths[w],
                       r.hits, m->kmer_map_size, m->db->s_templates, m->db->s_unique_lens, out, &accepted))
@@ -779,6 +828,8 @@ extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
     out->template_id = w;
     out->z_device = r.z;
     out->probability_device = r.p;
+    if (decisive && (accepted != 0) != dev_accept)
+        return kj_fail(ctx, KJ_E_CUDA, "internal: device gate and exact-decimal gate disagree away from a threshold");
     if (!accepted) {
         // findWinner returned undefined: notFound = false (lib/kmerFinderClient.js:214-217)
         m->ended = true;
@@ -787,16 +838,7 @@ extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
         return 0;
     }
     m->hit_counter++;
-    // removeWinnerKmers (lib/kmerFinderClient.js:220-230) on this rank's share of K_w
-    const uint64_t range[2] = {m->toff_h[w], m->toff_h[w + 1]};
-    if (range[1] > range[0]) {
-        const uint64_t n = range[1] - range[0];
-        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8));
-        KJ_LAUNCH(kj_remove_kernel, grid, 256, 0, ctx->stream, m->db->dev(), m->d_tq, range[0], range[1], m->d_qkmer,
-                  m->q->reg.counts, m->q->reg.alive, m->d_part, m->T);
-        ctx->launches++;
-        KJ_CUDA(ctx, cudaGetLastError());
-    }
+    if (!removed) { rc = launch_remove(w); if (rc) return rc; }
     return 1;
 }
 

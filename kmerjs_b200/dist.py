@@ -110,14 +110,24 @@ def exchange_counts(local: Counts, group=None) -> Counts:
                    capacity_hint=max(int(recv.shape[0]), 1024), ctx=local.ctx)
     if recv.shape[0]:
         owned.merge_records(recv.data_ptr(), int(recv.shape[0]))
-    # irregular k-mers (rare) are gathered on rank 0 as host records
+    # irregular k-mers (rare) are gathered on rank 0 as host records: one small all-gather of the
+    # counts; the payload only moves when some rank has any
     irr = local.irregular_records()
-    gathered = [None] * world
-    dist.all_gather_object(gathered, irr.tobytes(), group=group)
-    if rank == 0:
-        for blob in gathered:
-            if blob:
-                owned.merge_irregular(np.frombuffer(blob, dtype=np.uint8))
+    n_irr = torch.tensor([irr.size], dtype=torch.int64, device=dev)
+    all_n = [torch.empty_like(n_irr) for _ in range(world)]
+    dist.all_gather(all_n, n_irr, group=group)
+    sizes_irr = [int(x.item()) for x in all_n]
+    if max(sizes_irr) > 0:
+        pad = max(sizes_irr)
+        mine = torch.zeros(pad, dtype=torch.uint8, device=dev)
+        if irr.size:
+            mine[:irr.size] = torch.from_numpy(irr.copy()).to(dev)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        if rank == 0:
+            for sz, part in zip(sizes_irr, parts):
+                if sz:
+                    owned.merge_irregular(part[:sz].cpu().numpy())
     owned.finish()
     tot = torch.tensor([local.bases, local.occurrences, local.bytes_read, owned.size],
                        dtype=torch.int64, device=dev)
@@ -160,10 +170,13 @@ def count_sharded(dev_ptr: int, n_own: int, n_read: int, *, prefix=b"ATGAC", k=1
 class DistMatch:
     """findFirstMatch + findMatches over ranks: every rank returns the same rows."""
 
-    def __init__(self, owned: Counts, db, group=None):
+    def __init__(self, owned: Counts, db, group=None, torch_stream=None):
+        """torch_stream: the torch.cuda.Stream whose handle the Context was created on.  With it the
+        reductions are stream-ordered (no host synchronisation between copy, all-reduce and copy back)."""
         import torch
         import torch.distributed as dist
         self.group = group
+        self.torch_stream = torch_stream
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         self.dev = torch.device(f"cuda:{owned.ctx.device}")
         self.m = Match(owned, db, local_only=True, part=rank, n_parts=world)
@@ -183,6 +196,12 @@ class DistMatch:
         if t is None:
             t = torch.empty(max(n, 1), dtype=torch.int64, device=self.dev)
             self._buf[which] = t
+        if self.torch_stream is not None:
+            with torch.cuda.stream(self.torch_stream):      # everything below is ordered on the context's stream
+                self.m.get(which, t.data_ptr(), sync=False)
+                allreduce_u64(t[:n], op, self.group)
+                self.m.set(which, t.data_ptr(), sync=False)
+            return
         self.m.get(which, t.data_ptr())
         allreduce_u64(t[:n], op, self.group)
         torch.cuda.synchronize(self.dev)

@@ -49,11 +49,13 @@ class Match:
     def vec_len(self, which: int) -> int:
         return int(self._L.kj_match_vec_len(self.handle, which))
 
-    def get(self, which: int, dev_ptr: int):
-        _abi.check(self._L.kj_match_get(self.handle, which, C.c_void_p(dev_ptr)), self.ctx.handle)
+    def get(self, which: int, dev_ptr: int, sync: bool = True):
+        fn = self._L.kj_match_get if sync else self._L.kj_match_get_async
+        _abi.check(fn(self.handle, which, C.c_void_p(dev_ptr)), self.ctx.handle)
 
-    def set(self, which: int, dev_ptr: int):
-        _abi.check(self._L.kj_match_set(self.handle, which, C.c_void_p(dev_ptr)), self.ctx.handle)
+    def set(self, which: int, dev_ptr: int, sync: bool = True):
+        fn = self._L.kj_match_set if sync else self._L.kj_match_set_async
+        _abi.check(fn(self.handle, which, C.c_void_p(dev_ptr)), self.ctx.handle)
 
     def commit(self):
         _abi.check(self._L.kj_match_commit(self.handle), self.ctx.handle)

@@ -263,6 +263,9 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()        # from the warm-up on: the timed region is tens of milliseconds, nvidia-smi samples every 100 ms
     # the first warm-up step also sums the sequence-line lengths on the device (KJ_F_COUNT_BASES) so that
     # the bases the throughput is quoted on are checked against what the kernel saw
     state["flags"] = _abi.KJ_F_COUNT_BASES
@@ -275,9 +278,6 @@ def run_b200(args):
         trace.clear()
         step_device()
         print("trace (ms, one device-resident step):", json.dumps({k: round(v, 3) for k, v in trace.items()}), file=sys.stderr)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ctx.enable_timers(True)
     ctx.reset_timers()
     l0 = ctx.launches
@@ -345,8 +345,15 @@ def run_b200(args):
     per_rank_uniq = state["uniq"] / world
     alg_bytes = scan_bytes / max(scan_n, 1) + 32.0 * per_rank_occ          # F + 32 * N_occ per launch
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this workload (profiles/), scaled to
+    # the bytes of this launch when the capture was taken at another size
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_per_input_byte"] * (scan_bytes / max(scan_n, 1))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "kj_scan_filter_kernel<5,0> + kj_verify_kernel (extraction + count)",
+                "traffic": traffic, "kernel": "kj_scan_filter_kernel<5,0> + kj_verify_kernel (extraction + count)",
                 "kernel_ms": scan_ms, "scan_kernel_ms": scan_ms - verify_ms, "verify_kernel_ms": verify_ms,
                 "launches_averaged": scan_n, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": scan_ms * scan_n / max(ms_total, 1e-9)}

@@ -238,7 +238,8 @@ def run_b200(args):
             dm = kdist.DistMatch(owned, tdb, torch_stream=stream)
             rows = []
             try:
-                rows = list(dm.rows())
+                for r in dm.rows():      # the generator may end by throwing (query exhausted): keep what it yielded
+                    rows.append(r)
             except NoHitsError:
                 pass
             state.update(occ=owned.occurrences, uniq=getattr(owned, "global_size", owned.size), rows=rows,
@@ -322,10 +323,12 @@ def run_b200(args):
             owned = kdist.count_sharded(dev_in.data_ptr(), w.n_bytes, w.n_bytes, prefix=PREFIX, k=K, step=STEP,
                                         final=True, base_line=rank * n_reads * 4, ctx=ctx)
             dm = kdist.DistMatch(owned, tdb, torch_stream=stream)
+            rows = []
             try:
-                rows = list(dm.rows())
+                for r in dm.rows():
+                    rows.append(r)
             except NoHitsError:
-                rows = []
+                pass
             keys, lens, cnts = owned.export_arrays()
             d2h["bytes"] = keys.nbytes + lens.nbytes + cnts.nbytes + len(rows) * 136
             dm.free(); owned.free()

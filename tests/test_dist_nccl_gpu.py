@@ -1,0 +1,101 @@
+"""The multi-GPU path over real NCCL (needs >= 2 GPUs; skipped otherwise): reads sharded over ranks,
+owner all-to-all, sharded DB, all-reduced score vectors, replicated WTA -- every rank must produce the rows
+of the single-GPU run over all the reads, in both the synchronous and the stream-ordered reduction mode."""
+import os
+import socket
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from kmerjs_b200 import dist as kdist, synth
+    from kmerjs_b200.context import Context
+    from kmerjs_b200.counts import Counts
+    from kmerjs_b200.matching import Match, NoHitsError
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device(f"cuda:{rank}")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        stream = torch.cuda.Stream(device=dev)
+        ctx = Context(rank, stream=stream.cuda_stream)
+        n_reads = 100000
+        w = synth.Workload(n_reads=n_reads, genome_len=1_000_000, seed=5, first_read=rank * n_reads, ctx=ctx)
+        tdb = synth.template_db_from_genome(w.genome_host(), 8, b"ATGAC", 16)
+        out = {}
+        for mode, ts in (("sync", None), ("stream", stream)):
+            owned = kdist.count_sharded(w.fastq_ptr, w.n_bytes, w.n_bytes, prefix=b"ATGAC", k=16, step=1, final=True,
+                                        base_line=rank * n_reads * 4, ctx=ctx)
+            dm = kdist.DistMatch(owned, tdb, torch_stream=ts)
+            rows, err = [], None
+            try:
+                for r in dm.rows():
+                    rows.append(r)
+            except NoHitsError as exc:
+                err = str(exc)
+            out[mode] = dict(size=owned.global_size, lines=owned.lines, hits=dm.hits, order=list(dm.templates()),
+                             rows=rows, err=err, counts=owned.to_dict())
+            dm.free(); owned.free()
+        if rank == 0:      # single-GPU truth over the reads of all ranks
+            w2 = synth.Workload(n_reads=world * n_reads, genome_len=1_000_000, seed=5, first_read=0, ctx=ctx)
+            c = Counts(b"ATGAC", 16, 1, ctx=ctx)
+            c.add_device(w2.fastq_ptr, w2.n_bytes, final=True).finish()
+            counts = c.to_dict()
+            m = Match(c, tdb)
+            rows, err = [], None
+            hits, order = m.hits, list(m.templates())
+            try:
+                while True:
+                    r = m.next_row()
+                    if r is None:
+                        break
+                    rows.append(r)
+            except NoHitsError as exc:
+                err = str(exc)
+            out["single"] = dict(size=c.size, lines=c.lines, hits=hits, order=order, rows=rows, err=err, counts=counts)
+        q.put((rank, out))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_equal_single_gpu():
+    import torch
+    import torch.multiprocessing as mp
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    single = res[0]["single"]
+    assert len(single["rows"]) >= 1
+    merged = {}
+    for rank in range(world):
+        for mode in ("sync", "stream"):
+            o = res[rank][mode]
+            for f in ("size", "lines", "hits", "order", "rows", "err"):
+                assert o[f] == single[f], (rank, mode, f)
+        assert not (set(res[rank]["sync"]["counts"]) & set(merged))       # every k-mer has one owner
+        merged.update(res[rank]["sync"]["counts"])
+    assert merged == single["counts"]

@@ -544,7 +544,17 @@ extern "C" int kj_counts_create(kj_ctx *ctx, const kj_count_params *p, kj_counts
     return KJ_OK;
 }
 
-static const uint64_t KJ_STAGE_CHUNK = 64ull << 20;
+// host -> device staging chunk.  KJ_STAGE_CHUNK_MB overrides it (tuning aid; read once).
+static uint64_t kj_stage_chunk() {
+    static uint64_t v = 0;
+    if (!v) {
+        const char *e = getenv("KJ_STAGE_CHUNK_MB");
+        long mb = e ? atol(e) : 0;
+        v = (mb >= 1 && mb <= 4096) ? ((uint64_t)mb << 20) : (64ull << 20);
+    }
+    return v;
+}
+#define KJ_STAGE_CHUNK kj_stage_chunk()
 static const uint64_t KJ_STAGE_HALO_LINES = 1ull << 20;   // line kernel: longest line it can finish
 
 static int ensure_staging(kj_ctx *ctx, bool need_host) {
@@ -794,14 +804,37 @@ static int build_export_perm(kj_counts *c, std::vector<uint64_t> &hk) {
     const KjIrrRecord *ir = reinterpret_cast<const KjIrrRecord *>(c->irr_host.data());
     c->export_perm.resize(q);
     for (uint64_t i = 0; i < q; ++i) c->export_perm[i] = i;
-    std::sort(c->export_perm.begin(), c->export_perm.end(), [&](uint64_t x, uint64_t y) {
-        if (ho[x] != ho[y]) return ho[x] < ho[y];
-        // KJ_F_NO_ORDER: every ordinal is ~0; fall back to the key so the export is deterministic
-        bool xr = x < n_reg, yr = y < n_reg;
-        if (xr && yr) return hk[x] < hk[y];
-        if (xr != yr) return xr;
-        return memcmp(ir[x - n_reg].key, ir[y - n_reg].key, 32) < 0;
-    });
+    if (c->order) {
+        // first-seen ordinals are distinct: LSD radix sort of (ordinal, index), skipping the byte
+        // positions on which all ordinals agree (the export sits on the end-to-end path)
+        std::vector<uint64_t> k0(ho), k1(q), p1(q);
+        std::vector<uint64_t> *ks = &k0, *kd = &k1, *ps = &c->export_perm, *pd = &p1;
+        for (int pass = 0; pass < 8; ++pass) {
+            size_t hist[257] = {0};
+            const int sh = 8 * pass;
+            for (uint64_t i = 0; i < q; ++i) hist[(((*ks)[i]) >> sh & 0xFF) + 1]++;
+            bool trivial = false;
+            for (int b = 1; b <= 256; ++b) if (hist[b] == q) trivial = true;
+            if (trivial) continue;
+            for (int b = 0; b < 256; ++b) hist[b + 1] += hist[b];
+            for (uint64_t i = 0; i < q; ++i) {
+                const size_t at = hist[((*ks)[i]) >> sh & 0xFF]++;
+                (*kd)[at] = (*ks)[i];
+                (*pd)[at] = (*ps)[i];
+            }
+            std::swap(ks, kd);
+            std::swap(ps, pd);
+        }
+        if (ps != &c->export_perm) c->export_perm = *ps;
+    } else {
+        // KJ_F_NO_ORDER: every ordinal is ~0; order by key so the export is deterministic
+        std::sort(c->export_perm.begin(), c->export_perm.end(), [&](uint64_t x, uint64_t y) {
+            bool xr = x < n_reg, yr = y < n_reg;
+            if (xr && yr) return hk[x] < hk[y];
+            if (xr != yr) return xr;
+            return memcmp(ir[x - n_reg].key, ir[y - n_reg].key, 32) < 0;
+        });
+    }
     return KJ_OK;
 }
 

@@ -186,6 +186,10 @@ uint32_t kj_match_n_matched(const kj_match *m);   /* templates with uScore > 0 *
 /* uscore/tscore: n_templates entries each (0 for unmatched); order: ids of the matched templates
  * in first-encounter order (lib/kmerFinderServer.js:180-201), n_matched entries */
 int kj_match_scores(kj_match *m, uint64_t *uscore, uint64_t *tscore, uint32_t *order);
+/* the `kmers` Set of a template in the findFirstMatch reply (lib/kmerFinderClient.js:150-157): positions, in the
+ * export order of the counts handle, of the query k-mers that list the template; ascending = insertion order.
+ * idx may be NULL to ask for the count. */
+int kj_match_template_kmers(kj_match *m, uint32_t template_id, uint64_t *idx, uint64_t cap, uint64_t *n);
 void kj_match_free(kj_match *m);
 
 /* multi-GPU protocol (SURVEY 8e collectives 3/4).  The query is sharded by k-mer owner and so is

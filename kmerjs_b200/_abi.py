@@ -112,6 +112,7 @@ SIGNATURES = {
     "kj_match_hits": (C.c_uint64, [vp]),
     "kj_match_n_matched": (C.c_uint32, [vp]),
     "kj_match_scores": (C.c_int, [vp, vp, vp, vp]),
+    "kj_match_template_kmers": (C.c_int, [vp, C.c_uint32, vp, C.c_uint64, u64p]),
     "kj_match_free": (None, [vp]),
     "kj_wta_next": (C.c_int, [vp, C.POINTER(kj_row)]),
     "kj_match_set_max_hits": (C.c_int, [vp, C.c_uint32]),

@@ -680,6 +680,7 @@ static void drop_compact(kj_counts *c) {
     c->reg = KjCompact{};
     c->irr_host.clear();
     c->export_perm.clear();
+    c->export_rank.clear();
 }
 
 extern "C" int kj_counts_finish(kj_counts *c) {
@@ -867,6 +868,23 @@ extern "C" int kj_counts_export(kj_counts *c, uint8_t *keys, uint32_t *key_len, 
         }
         counts[o] = hc[i];
     }
+    return KJ_OK;
+}
+
+int kj_counts_export_rank(kj_counts *c, const std::vector<uint64_t> **rank) {
+    int rc = kj_counts_check_finished(c);
+    if (rc) return rc;
+    const uint64_t q = c->reg.n;
+    if (c->export_perm.size() != q) {
+        std::vector<uint64_t> hk;
+        rc = build_export_perm(c, hk);
+        if (rc) return rc;
+    }
+    if (c->export_rank.size() != q) {
+        c->export_rank.resize(q);
+        for (uint64_t o = 0; o < q; ++o) c->export_rank[c->export_perm[o]] = o;
+    }
+    *rank = &c->export_rank;
     return KJ_OK;
 }
 

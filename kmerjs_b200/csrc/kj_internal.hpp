@@ -113,6 +113,7 @@ struct kj_counts {
     // irregular entries, host side after finish: 56-byte records
     std::vector<uint8_t> irr_host;   // {u8 key[32], u64 len, u64 count, u64 ord} * n
     std::vector<uint64_t> export_perm;   // export position -> query index (built on first export)
+    std::vector<uint64_t> export_rank;   // its inverse
     uint64_t bytes_read = 0;
     uint64_t lines = 0;
     uint64_t occurrences = 0;
@@ -131,3 +132,4 @@ struct KjIrrRecord { uint8_t key[32]; uint64_t len, count, ord; };
 int kj_counts_check_finished(const kj_counts *c);
 int kj_grid_for(const kj_ctx *ctx, uint64_t n, int threads = 256);
 void kj_decode_key(uint64_t key, uint32_t k, uint8_t *out);
+int kj_counts_export_rank(kj_counts *c, const std::vector<uint64_t> **rank);   // query index -> export position

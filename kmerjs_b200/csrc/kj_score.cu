@@ -744,6 +744,32 @@ extern "C" int kj_match_scores(kj_match *m, uint64_t *uscore, uint64_t *tscore, 
     return KJ_OK;
 }
 
+// The `kmers` Set of one template in the findFirstMatch reply (lib/kmerFinderClient.js:150-157,
+// lib/kmerFinderServer.js:190-199): the query k-mers that list the template, as positions in the export
+// order of the counts handle (ascending = the Set's insertion order).  Only this rank's share when the
+// query is sharded.
+extern "C" int kj_match_template_kmers(kj_match *m, uint32_t template_id, uint64_t *idx, uint64_t cap, uint64_t *n_out) {
+    if (!m || !n_out) return KJ_E_INVALID;
+    kj_ctx *ctx = m->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (!m->committed) return kj_fail(ctx, KJ_E_STATE, "kj_match_commit has not run");
+    if (template_id >= m->T) return kj_fail(ctx, KJ_E_INVALID, "template id out of range");
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t lo = m->toff_h[template_id], hi = m->toff_h[template_id + 1];
+    *n_out = hi - lo;
+    if (!idx || hi == lo) return KJ_OK;
+    if (cap < hi - lo) return kj_fail(ctx, KJ_E_RANGE, "index buffer too small");
+    std::vector<uint32_t> q(hi - lo);
+    KJ_CUDA(ctx, cudaMemcpyAsync(q.data(), m->d_tq + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const std::vector<uint64_t> *inv = nullptr;
+    int rc = kj_counts_export_rank(m->q, &inv);       // query index -> export position
+    if (rc) return rc;
+    for (uint64_t i = 0; i < hi - lo; ++i) idx[i] = (*inv)[q[i]];
+    std::sort(idx, idx + (hi - lo));
+    return KJ_OK;
+}
+
 extern "C" int kj_match_set_max_hits(kj_match *m, uint32_t max_hits) {
     if (!m) return KJ_E_INVALID;
     m->max_hits = max_hits;

@@ -79,15 +79,29 @@ class Match:
                    self.ctx.handle)
         return u[:T], t[:T], o[:n]
 
-    def templates(self) -> dict:
-        """name -> {tScore,uScore,lengths,ulength,species} in first-encounter order: the
-        ``templates`` Map of the findFirstMatch reply (lib/kmerFinderClient.js:150-157)."""
+    def template_kmers(self, template_id: int) -> np.ndarray:
+        """Export-order positions of the query k-mers that list the template (its ``kmers`` Set)."""
+        n = C.c_uint64()
+        _abi.check(self._L.kj_match_template_kmers(self.handle, template_id, None, 0, C.byref(n)), self.ctx.handle)
+        idx = np.zeros(max(int(n.value), 1), dtype=np.uint64)
+        _abi.check(self._L.kj_match_template_kmers(self.handle, template_id, idx.ctypes.data, idx.size, C.byref(n)),
+                   self.ctx.handle)
+        return idx[:int(n.value)]
+
+    def templates(self, with_kmers: bool = False, keys=None) -> dict:
+        """name -> {tScore,uScore,lengths,ulength,species[,kmers]} in first-encounter order: the
+        ``templates`` Map of the findFirstMatch reply (lib/kmerFinderClient.js:150-157).  ``kmers`` (the
+        Set of matched k-mers, in insertion order) is materialised on request: ``keys`` is the list of
+        query k-mers in Map order."""
         u, t, order = self.scores()
         out = {}
         for i in order.tolist():
             out[self.db.names[i]] = {"tScore": int(t[i]), "uScore": int(u[i]),
                                      "lengths": int(self.db.lengths[i]), "ulength": int(self.db.ulengths[i]),
                                      "species": self.db.species[i]}
+            if with_kmers:
+                idx = self.template_kmers(i).tolist()
+                out[self.db.names[i]]["kmers"] = [keys[j] for j in idx] if keys is not None else idx
         return out
 
     def set_max_hits(self, n: int):

@@ -14,6 +14,7 @@
 //   wtaNext(match) -> row | null        (synchronous, like the generator's .next())
 //   countsAlive(counts) -> Uint8Array   (to mirror kmerMap.delete on the JS Map)
 #include <node_api.h>
+#include <string.h>
 #include <string>
 #include <vector>
 #include "../include/kmerjs_b200.h"
@@ -139,8 +140,167 @@ static napi_value WtaNext(napi_env env, napi_callback_info info) {
     return out;
 }
 
-// countsFromMap, dbCreate, firstMatch, matchScores, countsAlive follow the same pattern (external
-// handles + kj_* calls) and are listed in INTEGRATION.md; omitted here for brevity of the sketch.
+// ---- helpers for array arguments ---------------------------------------------------------------
+static bool get_u64_vec(napi_env env, napi_value arr, std::vector<uint64_t> &out) {
+    uint32_t n = 0;
+    if (napi_get_array_length(env, arr, &n) != napi_ok) return false;
+    out.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        napi_value v; double d = 0;
+        napi_get_element(env, arr, i, &v);
+        napi_get_value_double(env, v, &d);
+        out[i] = (uint64_t)d;
+    }
+    return true;
+}
+
+// countsFromMap(ctx, keys: string[], counts: number[], prefix, k, step) -> counts
+// A k-mer Map that did not come from countFile (e.g. parsed from JSON): keys in Map order get the
+// ordinals 0..n-1.  Regular keys travel as {2-bit key, count, ordinal} records, the others as
+// 56-byte byte-string records (kj_counts_merge_host_records / kj_counts_irregular_merge).
+static napi_value CountsFromMap(napi_env env, napi_callback_info info) {
+    size_t argc = 6; napi_value argv[6];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    kj_ctx *ctx = unwrap<kj_ctx>(env, argv[0]);
+    std::vector<uint64_t> counts;
+    if (!get_u64_vec(env, argv[2], counts)) return throw_kj(env, ctx, KJ_E_INVALID);
+    std::string prefix = get_string(env, argv[3]);
+    uint32_t k = 16, step = 1;
+    napi_get_value_uint32(env, argv[4], &k); napi_get_value_uint32(env, argv[5], &step);
+    kj_count_params p{};
+    p.prefix = (const uint8_t *)prefix.data(); p.prefix_len = (uint32_t)prefix.size(); p.k = k; p.step = step;
+    kj_counts *c = nullptr;
+    int rc = kj_counts_create(ctx, &p, &c);
+    if (rc) return throw_kj(env, ctx, rc);
+    std::vector<uint64_t> reg;            // {key, count, ordinal} triples
+    std::vector<uint8_t> irr;             // 56-byte records {u8 key[32], u64 len, u64 count, u64 ordinal}
+    for (uint32_t i = 0; i < counts.size(); ++i) {
+        napi_value v; napi_get_element(env, argv[1], i, &v);
+        std::string key = get_string(env, v);
+        bool regular = key.size() == k && k <= 32;
+        uint64_t packed = 0;
+        for (char ch : key) {
+            if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { regular = false; break; }
+            packed = (packed << 2) | (uint64_t)(((unsigned char)ch >> 1) & 3);     // A=0 C=1 T=2 G=3
+        }
+        if (regular && packed != ~0ull) { reg.push_back(packed); reg.push_back(counts[i]); reg.push_back(i); }
+        else if (key.size() <= 32) {
+            size_t at = irr.size(); irr.resize(at + 56, 0);
+            memcpy(&irr[at], key.data(), key.size());
+            uint64_t tail[3] = {key.size(), counts[i], i};
+            memcpy(&irr[at + 32], tail, 24);
+        } else { kj_counts_free(c); napi_throw_error(env, nullptr, "k-mers longer than 32 bytes are not supported"); return nullptr; }
+    }
+    if (!rc && !reg.empty()) rc = kj_counts_merge_host_records(c, reg.data(), reg.size() / 3);
+    if (!rc && !irr.empty()) rc = kj_counts_irregular_merge(c, irr.data(), irr.size() / 56);
+    if (!rc) rc = kj_counts_finish(c);
+    if (rc) { kj_counts_free(c); return throw_kj(env, ctx, rc); }
+    napi_value ext;
+    NAPI_OK(napi_create_external(env, c, [](napi_env, void *q, void *) { kj_counts_free((kj_counts *)q); }, nullptr, &ext));
+    return ext;
+}
+
+// dbCreate(ctx, {kmers: string[], lists: number[][], lengths: number[], ulengths: number[],
+//                summary: {templates, uniqueLens, totalLen}}) -> db
+static napi_value DbCreate(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value argv[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    kj_ctx *ctx = unwrap<kj_ctx>(env, argv[0]);
+    napi_value kmers, lists, lengths, ulengths, summary, v;
+    napi_get_named_property(env, argv[1], "kmers", &kmers);
+    napi_get_named_property(env, argv[1], "lists", &lists);
+    napi_get_named_property(env, argv[1], "lengths", &lengths);
+    napi_get_named_property(env, argv[1], "ulengths", &ulengths);
+    napi_get_named_property(env, argv[1], "summary", &summary);
+    uint32_t n = 0; napi_get_array_length(env, kmers, &n);
+    std::vector<uint8_t> bytes; std::vector<uint32_t> klen(n), tm; std::vector<uint64_t> off(1, 0), len, ulen;
+    for (uint32_t i = 0; i < n; ++i) {
+        napi_get_element(env, kmers, i, &v);
+        std::string key = get_string(env, v);
+        bytes.insert(bytes.end(), key.begin(), key.end()); klen[i] = (uint32_t)key.size();
+        napi_get_element(env, lists, i, &v);
+        std::vector<uint64_t> lst; get_u64_vec(env, v, lst);
+        for (uint64_t t : lst) tm.push_back((uint32_t)t);
+        off.push_back(tm.size());
+    }
+    get_u64_vec(env, lengths, len); get_u64_vec(env, ulengths, ulen);
+    auto num = [&](const char *name) { napi_value x; double d = 0; napi_get_named_property(env, summary, name, &x); napi_get_value_double(env, x, &d); return (uint64_t)d; };
+    kj_db_desc d{};
+    d.n_kmers = n; d.kmer_bytes = bytes.data(); d.kmer_len = klen.data(); d.list_off = off.data(); d.tmpl_ids = tm.data();
+    d.n_templates = (uint32_t)len.size(); d.lengths = len.data(); d.ulengths = ulen.data();
+    d.summary_templates = num("templates"); d.summary_unique_lens = num("uniqueLens"); d.summary_total_len = num("totalLen");
+    kj_db *db = nullptr;
+    int rc = kj_db_create(ctx, &d, &db);
+    if (rc) return throw_kj(env, ctx, rc);
+    napi_value ext;
+    NAPI_OK(napi_create_external(env, db, [](napi_env, void *q, void *) { kj_db_free((kj_db *)q); }, nullptr, &ext));
+    return ext;
+}
+
+// firstMatch(ctx, counts, db) -> match   (throws 'No hits were found!', lib/kmerFinderClient.js:159-161)
+static napi_value FirstMatch(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value argv[3];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    kj_ctx *ctx = unwrap<kj_ctx>(env, argv[0]);
+    kj_match *m = nullptr;
+    int rc = kj_first_match(ctx, unwrap<kj_counts>(env, argv[1]), unwrap<kj_db>(env, argv[2]), &m);
+    if (rc) return throw_kj(env, ctx, rc);
+    napi_value ext;
+    NAPI_OK(napi_create_external(env, m, [](napi_env, void *q, void *) { kj_match_free((kj_match *)q); }, nullptr, &ext));
+    return ext;
+}
+
+// matchScores(match, nTemplates) -> {uScore: number[], tScore: number[], order: number[], hits}
+static napi_value MatchScores(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value argv[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    kj_match *m = unwrap<kj_match>(env, argv[0]);
+    uint32_t T = 0; napi_get_value_uint32(env, argv[1], &T);
+    std::vector<uint64_t> u(T + 1), t(T + 1); std::vector<uint32_t> order(kj_match_n_matched(m) + 1);
+    if (int rc = kj_match_scores(m, u.data(), t.data(), order.data())) return throw_kj(env, nullptr, rc);
+    napi_value out, ju, jt, jo, v;
+    napi_create_object(env, &out);
+    napi_create_array_with_length(env, T, &ju); napi_create_array_with_length(env, T, &jt);
+    napi_create_array_with_length(env, kj_match_n_matched(m), &jo);
+    for (uint32_t i = 0; i < T; ++i) {
+        napi_create_double(env, (double)u[i], &v); napi_set_element(env, ju, i, v);
+        napi_create_double(env, (double)t[i], &v); napi_set_element(env, jt, i, v);
+    }
+    for (uint32_t i = 0; i < kj_match_n_matched(m); ++i) { napi_create_uint32(env, order[i], &v); napi_set_element(env, jo, i, v); }
+    napi_set_named_property(env, out, "uScore", ju); napi_set_named_property(env, out, "tScore", jt);
+    napi_set_named_property(env, out, "order", jo);
+    napi_create_double(env, (double)kj_match_hits(m), &v); napi_set_named_property(env, out, "hits", v);
+    return out;
+}
+
+// templateKmers(match, templateId) -> number[]  positions (Map order) of the k-mers in the template's `kmers` Set
+static napi_value TemplateKmers(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value argv[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    kj_match *m = unwrap<kj_match>(env, argv[0]);
+    uint32_t t = 0; napi_get_value_uint32(env, argv[1], &t);
+    uint64_t n = 0;
+    if (int rc = kj_match_template_kmers(m, t, nullptr, 0, &n)) return throw_kj(env, nullptr, rc);
+    std::vector<uint64_t> idx(n + 1);
+    if (int rc = kj_match_template_kmers(m, t, idx.data(), n, &n)) return throw_kj(env, nullptr, rc);
+    napi_value out, v;
+    napi_create_array_with_length(env, n, &out);
+    for (uint64_t i = 0; i < n; ++i) { napi_create_double(env, (double)idx[i], &v); napi_set_element(env, out, (uint32_t)i, v); }
+    return out;
+}
+
+// countsAlive(counts) -> Uint8Array in Map order (0 = deleted by a winner, kmerMap.delete of lib/kmerFinderClient.js:223-225)
+static napi_value CountsAlive(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value argv[1];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    kj_counts *c = unwrap<kj_counts>(env, argv[0]);
+    const uint64_t n = kj_counts_size(c);
+    void *data = nullptr; napi_value buf, out;
+    NAPI_OK(napi_create_arraybuffer(env, n, &data, &buf));
+    if (int rc = kj_counts_alive(c, (uint8_t *)data)) return throw_kj(env, nullptr, rc);
+    NAPI_OK(napi_create_typedarray(env, napi_uint8_array, n, buf, 0, &out));
+    return out;
+}
 
 static napi_value ModuleInit(napi_env env, napi_value exports) {
     napi_property_descriptor props[] = {
@@ -148,6 +308,12 @@ static napi_value ModuleInit(napi_env env, napi_value exports) {
         {"countFile", nullptr, CountFile, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"countsExport", nullptr, CountsExport, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"wtaNext", nullptr, WtaNext, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"countsFromMap", nullptr, CountsFromMap, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"dbCreate", nullptr, DbCreate, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"firstMatch", nullptr, FirstMatch, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"matchScores", nullptr, MatchScores, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"templateKmers", nullptr, TemplateKmers, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"countsAlive", nullptr, CountsAlive, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
     return exports;

@@ -47,4 +47,65 @@ function kmerjs(fastqPath, prefix = 'ATGAC', k = 16, step = 1, output) {        
   });
 }
 
-module.exports = { kmerjs, default: kmerjs, KmerJS, complement, complementMap, mapToJSON, objectToMap };
+// lib/kmerFinderClient.js:111-291.  `db` is {kmers, lists, lengths, ulengths, names, species, summary}
+// (what lib/kmerFinderServer.js keeps in Redis) or a handle from native.dbCreate.
+const ROW_KEYS = ['template', 'score', 'expected', 'z', 'probability', 'frac-q', 'frac-d', 'depth', 'kmers-template',
+  'total-frac-q', 'total-frac-d', 'total-temp-cover', 'species'];                    // lib/kmerFinderClient.js:75-89
+
+class KmerFinderClient extends KmerJS {
+  constructor(fastq, env, preffix = 'ATGAC', length = 16, step = 1, coverage = 1, out = true, db = 'server',
+    url = 'http://localhost:3000/kmers', summary, collection = 'genomes', dbName = 'Kmers') {
+    super(fastq, preffix, length, step, coverage, out, env);
+    Object.assign(this, { dbLocation: db, dbURL: url, collection, dbName, maxHits: 100 });
+  }
+  findKmers() { return this.readFile(); }
+  findFirstMatch(kmerQuery) {
+    return new Promise((resolve, reject) => {
+      try {
+        const db = this.dbLocation;
+        if (!db._handle) db._handle = native.dbCreate(context(), db);
+        kmerQuery.set('db', this.dbName); kmerQuery.set('collection', this.collection);   // :132-133
+        let counts = kmerQuery._counts;
+        if (!counts) {
+          const keys = [], vals = [];
+          for (const [k, v] of kmerQuery) if (typeof v === 'number') { keys.push(k); vals.push(v); }
+          counts = native.countsFromMap(context(), keys, vals, this.preffix, this.kmerLength, this.step);
+          kmerQuery._counts = counts;
+        }
+        this._match = native.firstMatch(context(), counts, db._handle);
+        const s = native.matchScores(this._match, db.names.length);
+        const keys = [...kmerQuery.keys()].filter((k) => k !== 'db' && k !== 'collection');
+        const templates = new Map();
+        for (const t of s.order) {
+          const match = this._match;
+          templates.set(db.names[t], { tScore: s.tScore[t], uScore: s.uScore[t], lengths: db.lengths[t],
+            ulength: db.ulengths[t], species: db.species[t],
+            get kmers() { return new Set(native.templateKmers(match, t).map((i) => keys[i])); } });
+        }
+        resolve({ templates, summary: db.summary, hits: s.hits });
+      } catch (e) {
+        reject(/No hits were found!$/.test(e.message) ? 'No hits were found!' : e);      // :159-161
+      }
+    });
+  }
+  * findMatches(winner, kmerMap) {                                                     // :174-290
+    this.summary = winner.summary; this.firstMatches = winner.templates;
+    const db = this.dbLocation;
+    const keys = [...kmerMap.keys()].filter((k) => k !== 'db' && k !== 'collection');
+    let alivePrev = null;
+    for (;;) {
+      const r = native.wtaNext(this._match);           // throws the two 'No hits were found! (...)' errors
+      if (r === null) return;
+      const row = {};
+      for (const k of ROW_KEYS) {
+        row[k] = k === 'template' ? db.names[r.templateId] : k === 'species' ? db.species[r.templateId] : r[k];
+      }
+      const alive = native.countsAlive(kmerMap._counts);                                 // removeWinnerKmers, :220-230
+      for (let i = 0; i < alive.length; i++) if (!alive[i] && (!alivePrev || alivePrev[i])) kmerMap.delete(keys[i]);
+      alivePrev = alive;
+      yield row;
+    }
+  }
+}
+
+module.exports = { kmerjs, default: kmerjs, KmerJS, KmerFinderClient, complement, complementMap, mapToJSON, objectToMap };

@@ -79,6 +79,13 @@ def test_c2_golden_query_vs_seeded_db():
     tdb = TemplateDB.from_lists(lists, attrs, summary)
     counts = counts_from_map(golden, "ATGAC", 16, 1)
     assert counts.size == 6191 and counts.to_dict() == golden and list(counts.to_dict()) == list(golden)
+    # the `kmers` Set of every template (lib/kmerFinderServer.js:190-199), in insertion order
+    o_templates, _ = ko.first_match(OrderedDict(qmap), ko.TemplateDB(lists, attrs, summary))
+    m0 = Match(counts, tdb)
+    with_sets = m0.templates(with_kmers=True, keys=list(golden.keys()))
+    for name, t in o_templates.items():
+        assert [k.encode("latin-1") for k in with_sets[name]["kmers"]] == list(t["kmers"].keys()), name
+    m0.free()
     e_first, e_hits, e_rows, e_err, e_q = oracle_rows(qmap, lists, attrs, summary)
     g_first, g_hits, g_rows, g_err, m = gpu_rows(counts, tdb)
     assert g_hits == e_hits == sum(t["uScore"] for t in e_first.values())      # KA8 invariant

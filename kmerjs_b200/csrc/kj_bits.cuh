@@ -71,6 +71,18 @@ KJ_HD uint32_t kj_not_acgt4(uint32_t w) {
     return w ^ expect;
 }
 
+// 4 bytes -> 4 bits: bit i set iff byte i != 0
+KJ_HD uint32_t kj_nz4(uint32_t x) {
+    const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    const uint32_t z = (t | x) & 0x80808080u;
+    return (z * 0x00204081u) >> 28;
+}
+// 16 bytes -> 16 bits: bit p set iff byte p is not one of 'A','C','G','T'
+KJ_HD uint32_t kj_bad16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    return kj_nz4(kj_not_acgt4(w0)) | (kj_nz4(kj_not_acgt4(w1)) << 4) | (kj_nz4(kj_not_acgt4(w2)) << 8) |
+           (kj_nz4(kj_not_acgt4(w3)) << 12);
+}
+
 // 4 bytes -> msb of byte i set iff byte i == '\n'
 KJ_HD uint32_t kj_nl_msb4(uint32_t w) {
     const uint32_t t = ((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;

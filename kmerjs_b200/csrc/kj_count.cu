@@ -328,8 +328,9 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
     if (rc) return rc;
     // spill lists: the table is sized for the expected load, so spills are the exception; the line
     // kernel (every window is an emission) gets the worst case of its 4 MiB pieces
-    rc = ensure_overflow(c, c->use_filter ? std::min<uint64_t>(hard_bound, 1ull << 20) : hard_bound,
-                         c->use_filter ? std::min<uint64_t>(hard_bound, 1ull << 16) : hard_bound);
+    rc = ensure_overflow(c, (c->use_filter || c->use_dense) ? std::min<uint64_t>(hard_bound, 1ull << 20) : hard_bound,
+                         c->use_filter ? std::min<uint64_t>(hard_bound, 1ull << 16)
+                                       : (c->use_dense ? std::min<uint64_t>(hard_bound, 1ull << 20) : hard_bound));
     if (rc) return rc;
 
     // tile state
@@ -391,7 +392,7 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
     a.cand = c->cand;
     a.cand_cap = c->cand_cap;
 
-    void (*fn)(const KjScanArgs) = kj_scan_lines_kernel;
+    void (*fn)(const KjScanArgs) = c->use_dense ? kj_scan_dense_kernel : kj_scan_lines_kernel;
     if (c->use_filter) {
         // where the filter symbols of complement(prefix) sit relative to the window start
         const uint32_t d_lo = a.rc_shift, d_hi = a.rc_shift + a.mp - 1;
@@ -488,7 +489,8 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
 // table (capacity_hint), else in 512 MiB pieces so the table can grow in between; the line
 // kernel (whose spill lists are sized for the worst case) in 4 MiB pieces.
 static int scan_device(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t own_n, int final_) {
-    const uint64_t piece = c->use_filter ? (c->capacity_hint ? (1ull << 40) : (512ull << 20)) : (4ull << 20);
+    const uint64_t piece = c->use_filter ? (c->capacity_hint ? (1ull << 40) : (512ull << 20))
+                                         : (c->use_dense ? (16ull << 20) : (4ull << 20));
     uint64_t lo = 0;
     while (lo < own_n) {
         uint64_t len = std::min(piece, own_n - lo);
@@ -518,6 +520,7 @@ extern "C" int kj_counts_create(kj_ctx *ctx, const kj_count_params *p, kj_counts
     c->order = !(p->flags & KJ_F_NO_ORDER);
     c->use_filter = p->step == 1 && p->prefix_len >= 1 && p->prefix_len <= p->k &&
                     !(p->flags & KJ_F_FORCE_GENERIC);
+    c->use_dense = p->step == 1 && p->prefix_len == 0 && p->k >= 2 && !(p->flags & KJ_F_FORCE_GENERIC);
     c->capacity_hint = p->capacity_hint;
     c->voff = p->base_col;
     c->base_line = p->base_line;
@@ -573,7 +576,7 @@ static int ensure_staging(kj_ctx *ctx, bool need_host) {
 
 static int add_host(kj_counts *c, const uint8_t *buf, uint64_t n, uint64_t own_n, int final_) {
     kj_ctx *ctx = c->ctx;
-    const uint64_t halo = c->use_filter ? 64 : KJ_STAGE_HALO_LINES;
+    const uint64_t halo = (c->use_filter || c->use_dense) ? 64 : KJ_STAGE_HALO_LINES;
     const uint64_t chunk = KJ_STAGE_CHUNK;
     cudaPointerAttributes attr{};
     bool pinned = cudaPointerGetAttributes(&attr, buf) == cudaSuccess &&
@@ -645,7 +648,7 @@ extern "C" int kj_counts_add_file(kj_counts *c, const char *path) {
     struct stat st;
     if (fstat(fd, &st) != 0) { close(fd); return kj_fail(ctx, KJ_E_IO, std::string("cannot stat ") + path); }
     const uint64_t size = (uint64_t)st.st_size;
-    const uint64_t halo = c->use_filter ? 64 : KJ_STAGE_HALO_LINES;
+    const uint64_t halo = (c->use_filter || c->use_dense) ? 64 : KJ_STAGE_HALO_LINES;
     const uint64_t chunk = KJ_STAGE_CHUNK;
     // read each piece (chunk + halo) into pinned memory and hand it over as a host buffer;
     // the halo bytes are read again by the next piece
@@ -758,7 +761,7 @@ extern "C" int kj_counts_finish(kj_counts *c) {
     // a range that starts inside a sequence line does not own the bytes before it, a range that ends
     // inside one (unterminated last line, or a shard cut) owns the bytes up to its end.
     long long bases = (long long)c->h_ctr->n_bases;
-    if (c->use_filter && c->consumed && (c->flags & KJ_F_COUNT_BASES)) {
+    if ((c->use_filter || c->use_dense) && c->consumed && (c->flags & KJ_F_COUNT_BASES)) {
         if ((c->base_line & 3ull) == 1ull) bases -= (long long)c->base_col;
         if ((c->lines & 3ull) == 1ull) bases += (long long)c->voff;
     }

@@ -87,7 +87,8 @@ struct kj_counts {
     std::vector<uint8_t> prefix, rprefix;
     uint32_t k = 16, step = 1, flags = 0;
     bool order = true;
-    bool use_filter = true;      // filter kernel (step == 1, 1 <= m <= k) or line kernel
+    bool use_filter = true;      // filter kernel (step == 1, 1 <= m <= k), else dense or line kernel
+    bool use_dense = false;      // dense kernel (step == 1, empty prefix, k >= 2): every window is an emission
     uint64_t capacity_hint = 0;
     // stream position
     uint64_t voff = 0;           // virtual offset of the next byte (starts at base_col)

@@ -867,6 +867,146 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     }
 }
 
+// ----------------------------------------------------------------------------- dense kernel
+
+// Empty prefix, step == 1, k >= 2: every window of a sequence line is an emission on both strands
+// (BASELINE config 5), so there is nothing to filter and the hash table is the bound.  Same tiles,
+// tickets and look-back as the other kernels; per chunk a thread walks its 16 window starts with
+// the 2-bit codes, a newline bitmap and a "not A/C/G/T" bitmap of the chunk and its 32-byte halo in
+// registers: a window is regular iff no bit of either bitmap falls inside it, its key is a shift of
+// the code words away.  Windows with another byte (N, lower case, ...) take the byte-string side path.
+struct KjDenseSmem {
+    uint16_t nlt[KJ_TILE_CHUNKS + 2];     // '\n' bitmap incl. halo, NOT clipped to the owned range (window validity)
+    uint16_t bad[KJ_TILE_CHUNKS + 2];     // bytes that are not A/C/G/T, incl. halo ('\n' is one of them)
+    uint16_t pre[KJ_TILE_CHUNKS];         // counted '\n' before the chunk inside its row
+};
+
+__global__ void __launch_bounds__(KJ_THREADS)
+kj_scan_dense_kernel(const __grid_constant__ KjScanArgs a) {
+    __shared__ KjTileSmem s;
+    __shared__ KjDenseSmem ds;
+    __shared__ uint32_t codes[KJ_TILE_CHUNKS + 2];
+    __shared__ uint32_t cur_tile;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t k = a.k;
+    const uint64_t kbits = k == 32 ? 0xFFFFFFFFull : ((1ull << k) - 1ull);           // k window bytes
+    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);             // 2k key bits
+    uint32_t n_emit = 0;
+    long long n_bases = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) cur_tile = atomicAdd(&a.ctr->ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = cur_tile;
+        if (tile >= a.n_tiles) break;
+        const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
+        const uint64_t tile_voff = a.voff + tile_off;
+        const uint32_t own_in_tile =
+            (a.own_n - tile_off < KJ_TILE_BYTES) ? (uint32_t)(a.own_n - tile_off) : KJ_TILE_BYTES;
+
+        // P1: codes, both bitmaps, counted newlines with their prefix inside the row
+#pragma unroll 1
+        for (int it = 0; it < KJ_TILE_CHUNKS / KJ_THREADS; ++it) {
+            const uint32_t c = it * KJ_THREADS + tid;
+            const uint64_t off = tile_off + (uint64_t)c * 16u;
+            const uint4 v = (off < a.n) ? kj_load_chunk(a.buf, off, a.n) : make_uint4(0, 0, 0, 0);
+            uint32_t keep = 0xFFFFu;
+            if (off >= a.own_n) keep = 0;
+            else if (off + 16 > a.own_n) keep = (1u << (uint32_t)(a.own_n - off)) - 1u;
+            codes[c] = kj_pack16(v.x, v.y, v.z, v.w);
+            const uint32_t nlt = kj_nl16(v.x, v.y, v.z, v.w);
+            ds.nlt[c] = (uint16_t)nlt;
+            ds.bad[c] = (uint16_t)kj_bad16(v.x, v.y, v.z, v.w);
+            const uint32_t nl = nlt & keep;
+            s.nl[c] = (uint16_t)nl;
+            const uint32_t cnt = __popc(nl);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if ((int)lane >= d) incl += o;
+            }
+            ds.pre[c] = (uint16_t)(incl - cnt);
+            if (lane == 31) s.row_pre[c >> 5] = incl;
+        }
+        if (tid < 2) {   // halo
+            const uint64_t off = tile_off + (uint64_t)(KJ_TILE_CHUNKS + tid) * 16u;
+            const uint4 h = (off < a.n) ? kj_load_chunk(a.buf, off, a.n) : make_uint4(0, 0, 0, 0);
+            codes[KJ_TILE_CHUNKS + tid] = kj_pack16(h.x, h.y, h.z, h.w);
+            ds.nlt[KJ_TILE_CHUNKS + tid] = (uint16_t)kj_nl16(h.x, h.y, h.z, h.w);
+            ds.bad[KJ_TILE_CHUNKS + tid] = (uint16_t)kj_bad16(h.x, h.y, h.z, h.w);
+        }
+        __syncthreads();
+        if (warp == 0) { kj_tile_rowscan_warp(a, s, tile); kj_lookback(a, s, tile); }
+        __syncthreads();
+        if (a.count_bases) n_bases += kj_tile_bases(s, tile_voff, tid, KJ_THREADS);
+
+        // P2: every owned window start
+#pragma unroll 1
+        for (int it = 0; it < KJ_TILE_CHUNKS / KJ_THREADS; ++it) {
+            const uint32_t c = it * KJ_THREADS + tid;
+            const uint32_t pos0 = c * 16u;
+            if (pos0 >= own_in_tile) continue;
+            const uint32_t n_own = own_in_tile - pos0 < 16u ? own_in_tile - pos0 : 16u;
+            const uint64_t NLT = (uint64_t)ds.nlt[c] | ((uint64_t)ds.nlt[c + 1] << 16) | ((uint64_t)ds.nlt[c + 2] << 32);
+            const uint64_t BAD = (uint64_t)ds.bad[c] | ((uint64_t)ds.bad[c + 1] << 16) | ((uint64_t)ds.bad[c + 2] << 32);
+            const uint64_t CLO = (uint64_t)codes[c] | ((uint64_t)codes[c + 1] << 32);
+            const uint64_t CHI = codes[c + 2];
+            const uint32_t nlm = s.nl[c];
+            const uint64_t line0 = s.excl_count + s.row_pre[c >> 5] + ds.pre[c];
+            unsigned long long start0 = 0;
+            bool have_start0 = false;
+#pragma unroll 1
+            for (uint32_t p = 0; p < n_own; ++p) {
+                const uint64_t j = tile_off + pos0 + p;
+                if (j + k > a.n) break;                                // window must lie inside the stream
+                const uint32_t below = nlm & ((1u << p) - 1u);
+                const uint64_t line = line0 + __popc(below);
+                if ((line & 3ull) != 1ull) continue;                   // lib/kmers.js:151  i === 1
+                if ((NLT >> p) & kbits) continue;                      // crosses the end of the line
+                uint64_t ord_f = 0, ord_r = 0;
+                if (a.order) {
+                    unsigned long long start;
+                    if (below) start = tile_voff + pos0 + (31u - __clz(below)) + 1ull;
+                    else {
+                        if (!have_start0) { start0 = kj_line_start(a, s, pos0, tile_off, tile_voff); have_start0 = true; }
+                        start = start0;
+                    }
+                    const uint64_t col = tile_voff + pos0 + p - start;
+                    const uint64_t read_idx = line >> 2;
+                    if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); continue; }
+                    if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); continue; }
+                    ord_f = kj_ordinal(read_idx, 0, col);
+                    ord_r = kj_ordinal(read_idx, 1, KJ_POS_MAX - col);
+                }
+                if ((BAD >> p) & kbits) {                              // some other byte inside: byte-string keys
+                    kj_emit_irregular(a, j, k, 0, ord_f);
+                    ++n_emit;
+                    if (a.n_strands > 1) { kj_emit_irregular(a, j, k, 1, ord_r); ++n_emit; }
+                    continue;
+                }
+                const uint64_t P = ((CLO >> (2u * p)) | (p ? CHI << (64u - 2u * p) : 0ull)) & kmask;   // code of window byte i at bits 2i
+                const uint64_t fk = kj_pairrev64(P) >> (64u - 2u * k);
+                if (!kj_insert(a.tab, a.ctr, fk, ord_f, 1)) kj_spill(a, fk, ord_f);
+                ++n_emit;
+                if (a.n_strands > 1) {
+                    const uint64_t rk = (P ^ 0xAAAAAAAAAAAAAAAAull) & kmask;
+                    if (!kj_insert(a.tab, a.ctr, rk, ord_r, 1)) kj_spill(a, rk, ord_r);
+                    ++n_emit;
+                }
+            }
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {       // one atomic per warp
+        n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
+        n_bases += __shfl_xor_sync(0xFFFFFFFFu, n_bases, d);
+    }
+    if ((tid & 31) == 0) {
+        if (n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);
+        if (n_bases) atomicAdd(&a.ctr->n_bases, (unsigned long long)n_bases);
+    }
+}
+
 // ----------------------------------------------------------------------------- line-oriented kernel
 
 // One whole sequence line starting at buffer offset ls with line index `line`; `width` threads

@@ -127,6 +127,24 @@ def test_fuzz(case, flags):
         assert bases == seq_bases(data)
 
 
+@pytest.mark.parametrize("k", [2, 5, 16, 31, 32])
+def test_dense_kernel_empty_prefix(k):
+    """Empty prefix, step 1, k >= 2 runs the dense kernel (every window is an emission, both strands);
+    the line kernel (KJ_F_FORCE_GENERIC) and the oracle must agree with it, irregular bytes included."""
+    rng = random.Random(900 + k)
+    for case in (dict(p_n=0.03, p_lower=0.02), dict(crlf=True), dict(blank_lines=0.1, trailing_newline=False),
+                 dict(min_len=0, max_len=40), dict(alphabet=b"AAAAAAAC", plant=None)):
+        data = random_fastq(rng, 80, **case)
+        exp = oracle(data, b"", k, 1)
+        got, (occ, bases, _) = gpu(data, b"", k, 1)
+        assert got == exp, (k, case)
+        assert occ == sum(v for _, v in exp[0]) and bases == seq_bases(data)
+        assert gpu(data, b"", k, 1, flags=_abi.KJ_F_FORCE_GENERIC, device=True)[0] == exp
+    data = read_golden("test_kmers.fastq")
+    cuts = [1000, 3000, 5555]
+    assert gpu(data, b"", k, 1, pieces=cuts, halo=64)[0] == oracle(data, b"", k, 1)      # window kernel: 64-byte halo
+
+
 def test_empty_and_degenerate_inputs():
     for data in (b"", b"\n", b"\n\n\n\n\n", b"@r\nA\n+\n#\n", b"@r\nATGACATGACATGACAT", b"ATGACATGACATGACATG",
                  b"@r\n\n+\n\n", b"@\nATGACATGACATGACATGAC\n+"):

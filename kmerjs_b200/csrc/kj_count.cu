@@ -719,13 +719,38 @@ extern "C" int kj_counts_finish(kj_counts *c) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         kj_dfree(ctx, d_irr);
         if (e != cudaSuccess) return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e));
-        // deterministic order of the irregular entries (slot order depends on the table size)
+        // order of the irregular entries: by first-seen ordinal (distinct per entry), so that it does not
+        // depend on the table size.  LSD radix sort of (ordinal, index), then one permutation pass: the
+        // stress configs have ~10^6 of these.  Without ordinals (KJ_F_NO_ORDER) they stay in slot order.
         KjIrrRecord *ir = reinterpret_cast<KjIrrRecord *>(c->irr_host.data());
-        std::sort(ir, ir + n_irr, [](const KjIrrRecord &x, const KjIrrRecord &y) {
-            if (x.ord != y.ord) return x.ord < y.ord;
-            int d = memcmp(x.key, y.key, 32);
-            return d ? d < 0 : x.len < y.len;
-        });
+        if (c->order && n_irr > 1) {
+            std::vector<uint64_t> k0(n_irr), k1(n_irr);
+            std::vector<uint32_t> p0(n_irr), p1(n_irr);
+            for (uint64_t i = 0; i < n_irr; ++i) { k0[i] = ir[i].ord; p0[i] = (uint32_t)i; }
+            std::vector<uint64_t> *ks = &k0, *kd = &k1;
+            std::vector<uint32_t> *ps = &p0, *pd = &p1;
+            for (int pass = 0; pass < 8; ++pass) {
+                size_t hist[257] = {0};
+                const int sh = 8 * pass;
+                for (uint64_t i = 0; i < n_irr; ++i) hist[(((*ks)[i]) >> sh & 0xFF) + 1]++;
+                bool trivial = false;
+                for (int b = 1; b <= 256; ++b) if (hist[b] == n_irr) trivial = true;
+                if (trivial) continue;
+                for (int b = 0; b < 256; ++b) hist[b + 1] += hist[b];
+                for (uint64_t i = 0; i < n_irr; ++i) {
+                    const size_t at = hist[((*ks)[i]) >> sh & 0xFF]++;
+                    (*kd)[at] = (*ks)[i];
+                    (*pd)[at] = (*ps)[i];
+                }
+                std::swap(ks, kd);
+                std::swap(ps, pd);
+            }
+            std::vector<uint8_t> sorted(c->irr_host.size());
+            KjIrrRecord *dst = reinterpret_cast<KjIrrRecord *>(sorted.data());
+            for (uint64_t i = 0; i < n_irr; ++i) dst[i] = ir[(*ps)[i]];
+            c->irr_host.swap(sorted);
+            ir = reinterpret_cast<KjIrrRecord *>(c->irr_host.data());
+        }
         for (uint64_t i = 0; i < n_irr; ++i) { tail_counts.push_back(ir[i].count); tail_ords.push_back(ir[i].ord); }
     }
     if (q) {

@@ -232,16 +232,20 @@ def run_b200(args):
             m.free(); c.free()
             t = tick("free", t)
         else:
+            t = time.perf_counter()
             owned = kdist.count_sharded(w.fastq_ptr, w.n_bytes, w.n_bytes, prefix=PREFIX, k=K, step=STEP, final=True,
                                         base_line=rank * n_reads * 4, capacity_hint=hint, flags=state.get("flags", 0),
                                         ctx=ctx)
+            t = tick("count+exchange", t)
             dm = kdist.DistMatch(owned, tdb, torch_stream=stream)
+            t = tick("first_match+reduce", t)
             rows = []
             try:
                 for r in dm.rows():      # the generator may end by throwing (query exhausted): keep what it yielded
                     rows.append(r)
             except NoHitsError:
                 pass
+            t = tick("wta_rows", t)
             state.update(occ=owned.occurrences, uniq=getattr(owned, "global_size", owned.size), rows=rows,
                          lines=owned.lines, bases=owned.bases)
             dm.free(); owned.free()
@@ -275,10 +279,11 @@ def run_b200(args):
     state["flags"] = 0
     for _ in range(max(args.warmup, 3) - 1):
         step_device()
-    if args.trace and rank == 0:
+    if args.trace:            # every rank runs the step (it contains collectives); rank 0 prints
         trace.clear()
         step_device()
-        print("trace (ms, one device-resident step):", json.dumps({k: round(v, 3) for k, v in trace.items()}), file=sys.stderr)
+        if rank == 0:
+            print("trace (ms, one device-resident step):", json.dumps({k: round(v, 3) for k, v in trace.items()}), file=sys.stderr)
     ctx.enable_timers(True)
     ctx.reset_timers()
     l0 = ctx.launches

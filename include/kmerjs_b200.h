@@ -242,6 +242,12 @@ typedef struct kj_row {       /* lib/kmerFinderClient.js:75-89, same order */
 /* One step of the findMatches generator: 1 = row written, 0 = loop ended normally,
  * KJ_E_NO_HITS / KJ_E_NO_WINNER mirror the two throws of lib/kmerFinderClient.js:264-266,283-285. */
 int kj_wta_next(kj_match *m, kj_row *out);
+/* Deferred rows, for callers that issue a collective per round (multi-GPU): with kj_match_defer_rows(m, 1),
+ * kj_wta_next may return 2 = "winner accepted by the device gate (away from every fastp threshold), its k-mers
+ * are being removed, integers in out->score/tscore/hits"; the caller starts its all-reduce and then calls
+ * kj_wta_row, which finishes the row in exact-decimal arithmetic while the GPU works. */
+int kj_match_defer_rows(kj_match *m, int on);
+int kj_wta_row(kj_match *m, kj_row *out);
 /* maxHits (lib/kmerFinderClient.js:123), default 100 */
 int kj_match_set_max_hits(kj_match *m, uint32_t max_hits);
 /* standardScoring (lib/kmerFinderServer.js:857-874): one row per matched template from the first

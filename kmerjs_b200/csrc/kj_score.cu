@@ -81,6 +81,9 @@ struct kj_match {
     uint32_t max_hits = 100, hit_counter = 0;
     bool ended = false;
     bool inflight = false;           // the argmax of the next round has been launched ahead
+    bool defer_rows = false;         // kj_wta_next may return 2: the exact row is finished by kj_wta_row
+    bool row_pending = false;
+    KjWtaResult pending{};           // integers of the row to finish
 };
 
 // ------------------------------------------------------------------------------------ kernels
@@ -847,6 +850,16 @@ extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
             m->inflight = true;
         }
     }
+    if (m->defer_rows && removed) {
+        // the caller wants to issue its collective before the host spends time on the exact row
+        m->pending = r;
+        m->row_pending = true;
+        m->hit_counter++;
+        out->template_id = w;
+        out->score = r.u; out->tscore = r.tau; out->hits = r.hits;
+        out->z_device = r.z; out->probability_device = r.p;
+        return 2;
+    }
     int accepted = 0;
     if (!kj_exact_row(ctx->rounding_mode, r.u, r.tau, m->u0[w], m->t0[w], m->db->lengths[w], m->db->ulengths[w],
                       r.hits, m->kmer_map_size, m->db->s_templates, m->db->s_unique_lens, out, &accepted))
@@ -865,6 +878,35 @@ extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
     }
     m->hit_counter++;
     if (!removed) { rc = launch_remove(w); if (rc) return rc; }
+    return 1;
+}
+
+// Deferred rows (kj_match_defer_rows): kj_wta_next returned 2 after the device gate accepted the winner away
+// from every threshold and the removal was launched; this finishes the row in exact arithmetic.
+extern "C" int kj_match_defer_rows(kj_match *m, int on) {
+    if (!m) return KJ_E_INVALID;
+    m->defer_rows = on != 0;
+    return KJ_OK;
+}
+
+extern "C" int kj_wta_row(kj_match *m, kj_row *out) {
+    if (!m || !out) return KJ_E_INVALID;
+    kj_ctx *ctx = m->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (!m->row_pending) return kj_fail(ctx, KJ_E_STATE, "kj_wta_row without a pending row");
+    m->row_pending = false;
+    const KjWtaResult r = m->pending;
+    const uint32_t w = r.winner;
+    memset(out, 0, sizeof(*out));
+    int accepted = 0;
+    if (!kj_exact_row(ctx->rounding_mode, r.u, r.tau, m->u0[w], m->t0[w], m->db->lengths[w], m->db->ulengths[w],
+                      r.hits, m->kmer_map_size, m->db->s_templates, m->db->s_unique_lens, out, &accepted))
+        return kj_fail(ctx, KJ_E_INVALID, "template with zero length / ulength or zero Summary.uniqueLens");
+    out->template_id = w;
+    out->z_device = r.z;
+    out->probability_device = r.p;
+    if (!accepted)
+        return kj_fail(ctx, KJ_E_CUDA, "internal: device gate and exact-decimal gate disagree away from a threshold");
     return 1;
 }
 

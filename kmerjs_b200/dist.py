@@ -110,33 +110,35 @@ def exchange_counts(local: Counts, group=None) -> Counts:
                    capacity_hint=max(int(recv.shape[0]), 1024), ctx=local.ctx)
     if recv.shape[0]:
         owned.merge_records(recv.data_ptr(), int(recv.shape[0]))
-    # irregular k-mers (rare) are gathered on rank 0 as host records: one small all-gather of the
-    # counts; the payload only moves when some rank has any
+    # one small all-gather carries everything the ranks need from each other besides the records:
+    # irregular-record bytes (rare k-mers, gathered on rank 0), line / base / occurrence / byte totals
     irr = local.irregular_records()
-    n_irr = torch.tensor([irr.size], dtype=torch.int64, device=dev)
-    all_n = [torch.empty_like(n_irr) for _ in range(world)]
-    dist.all_gather(all_n, n_irr, group=group)
-    sizes_irr = [int(x.item()) for x in all_n]
+    mine_v = torch.tensor([irr.size, local.lines, local.bases, local.occurrences, local.bytes_read],
+                          dtype=torch.int64, device=dev)
+    all_v = torch.empty((world, 5), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_v, mine_v, group=group)
+    rows = all_v.tolist()
+    sizes_irr = [int(r[0]) for r in rows]
     if max(sizes_irr) > 0:
         pad = max(sizes_irr)
         mine = torch.zeros(pad, dtype=torch.uint8, device=dev)
         if irr.size:
             mine[:irr.size] = torch.from_numpy(irr.copy()).to(dev)
-        parts = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine, group=group)
+        parts = torch.empty((world, pad), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(parts, mine, group=group)
         if rank == 0:
-            for sz, part in zip(sizes_irr, parts):
+            host = parts.cpu().numpy()
+            for rr, sz in enumerate(sizes_irr):
                 if sz:
-                    owned.merge_irregular(part[:sz].cpu().numpy())
+                    owned.merge_irregular(host[rr, :sz])
     owned.finish()
-    tot = torch.tensor([local.bases, local.occurrences, local.bytes_read, owned.size],
-                       dtype=torch.int64, device=dev)
-    dist.all_reduce(tot, group=group)
-    bases, occ, nbytes, qsize = [int(x) for x in tot.tolist()]
     # a rank's line count already includes the lines before its range (base_line): the last rank's is the file's
-    ln = torch.tensor([local.lines], dtype=torch.int64, device=dev)
-    dist.all_reduce(ln, op=dist.ReduceOp.MAX, group=group)
-    owned.set_totals(int(ln.item()), bases, occ, nbytes)
+    lines = max(int(r[1]) for r in rows)
+    bases, occ, nbytes = (sum(int(r[i]) for r in rows) for i in (2, 3, 4))
+    qs = torch.tensor([owned.size], dtype=torch.int64, device=dev)
+    dist.all_reduce(qs, group=group)
+    qsize = int(qs.item())
+    owned.set_totals(lines, bases, occ, nbytes)
     owned.global_size = qsize
     return owned
 
@@ -216,11 +218,16 @@ class DistMatch:
 
     def rows(self, max_hits: int = 100):
         self.m.set_max_hits(max_hits)
+        self.m.defer_rows(True)
         while True:
-            row = self.m.next_row()
-            if row is None:
+            state, row = self.m.next_row_begin()
+            if state == 0:
                 return
+            # the partial sums changed (the winner's k-mers are being removed): reduce them for the next
+            # round; with a pending row the exact-decimal arithmetic runs on the host while the GPUs reduce
             self._reduce(_abi.KJ_VEC_SCORES, "sum")
+            if state == 2:
+                row = self.m.finish_row()
             yield row
 
     def free(self):

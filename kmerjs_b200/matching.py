@@ -119,6 +119,27 @@ class Match:
         self.last_row = r
         return row_to_dict(r, self.db) if rc == 1 else None
 
+    def defer_rows(self, on: bool = True):
+        _abi.check(self._L.kj_match_defer_rows(self.handle, 1 if on else 0), self.ctx.handle)
+
+    def next_row_begin(self):
+        """(state, row): state 0 = loop ended, 1 = row complete, 2 = winner accepted, row pending (finish_row)."""
+        r = _abi.kj_row()
+        rc = self._L.kj_wta_next(self.handle, C.byref(r))
+        if rc == _abi.KJ_E_NO_HITS:
+            raise NoHitsError("No hits were found! (nHits === 0)")
+        if rc == _abi.KJ_E_NO_WINNER:
+            raise NoHitsError("No hits were found! (kmerResults.length === 0)")
+        _abi.check(rc, self.ctx.handle)
+        self.last_row = r
+        return rc, (row_to_dict(r, self.db) if rc == 1 else None)
+
+    def finish_row(self):
+        r = _abi.kj_row()
+        _abi.check(self._L.kj_wta_row(self.handle, C.byref(r)), self.ctx.handle)
+        self.last_row = r
+        return row_to_dict(r, self.db)
+
     def standard_scoring(self) -> list:
         n = C.c_uint32()
         cap = max(self.db.n_templates, 1)

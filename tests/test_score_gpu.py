@@ -193,6 +193,35 @@ def test_max_hits_and_ties():
         m.free(); c.free()
 
 
+def test_deferred_rows_equal_immediate_rows():
+    """kj_match_defer_rows: kj_wta_next hands back the integers, kj_wta_row finishes the row later (the
+    multi-GPU layer puts its all-reduce in between); the rows must be the same."""
+    rng = random.Random(123)
+    keys = [bytes(b"ATGAC") + bytes(rng.choice(b"ACGT") for _ in range(11)) for _ in range(600)]
+    qmap = OrderedDict((k, rng.randint(1, 5)) for k in dict.fromkeys(keys))
+    lists, attrs, summary = synthetic_db(list(qmap.keys()), rng, n_templates=16, decoys=20, share=0.8)
+    tdb = TemplateDB.from_lists(lists, attrs, summary)
+    _, _, e_rows, e_err, _ = oracle_rows(qmap, lists, attrs, summary)
+    c = counts_from_map({k.decode(): v for k, v in qmap.items()}, "ATGAC", 16, 1)
+    m = Match(c, tdb)
+    m.defer_rows(True)
+    got, err, pending = [], None, 0
+    try:
+        while True:
+            state, row = m.next_row_begin()
+            if state == 0:
+                break
+            if state == 2:
+                pending += 1
+                row = m.finish_row()
+            got.append(row)
+    except NoHitsError as exc:
+        err = str(exc)
+    check_rows(got, e_rows)
+    assert err == e_err and pending >= 1
+    m.free(); c.free()
+
+
 def test_standard_scoring():
     golden = json.loads(read_golden("test_long.json"))          # 6045-key sorted subset of the golden map
     qmap = OrderedDict((k.encode("latin-1"), v) for k, v in golden.items())

@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-reads", type=int, default=1_000_000, help="reads in the CPU-baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--score-mode", default="auto", choices=["auto", "gather", "reduce"],
+                    help="N>1: all-gather the matched set once (gather) or all-reduce the score vector every round (reduce)")
     ap.add_argument("--trace", action="store_true", help="print host-side phase timings of one device step to stderr")
     return ap.parse_args()
 
@@ -61,7 +63,9 @@ def workload_config(args, world):
                         f"template DB of {N_TEMPLATES} synthetic templates over a {GENOME_LEN // 1_000_000} Mbp genome",
             "reads_per_gpu": args.reads, "read_len": 150, "prefix": "ATGAC", "k": K, "step": STEP,
             "templates": N_TEMPLATES, "l2": "inputs larger than L2 (3.46 GB FASTQ per GPU vs 126 MB)",
-            "sharding": "whole records per rank; owner all-to-all + per-template allreduce" if world > 1 else "single GPU"}
+            "sharding": ("whole records per rank; owner all-to-all of counted k-mers; scoring: " +
+                         ("per-round all-reduce of the template sums" if args.score_mode == "reduce" else
+                          "one all-gather of the matched entries, winner-takes-all replicated")) if world > 1 else "single GPU"}
 
 
 # ---------------------------------------------------------------------------------------------- CPU leg
@@ -237,7 +241,7 @@ def run_b200(args):
                                         base_line=rank * n_reads * 4, capacity_hint=hint, flags=state.get("flags", 0),
                                         ctx=ctx)
             t = tick("count+exchange", t)
-            dm = kdist.DistMatch(owned, tdb, torch_stream=stream)
+            dm = kdist.DistMatch(owned, tdb, torch_stream=stream, mode=args.score_mode)
             t = tick("first_match+reduce", t)
             rows = []
             try:
@@ -327,7 +331,7 @@ def run_b200(args):
             stream.synchronize()
             owned = kdist.count_sharded(dev_in.data_ptr(), w.n_bytes, w.n_bytes, prefix=PREFIX, k=K, step=STEP,
                                         final=True, base_line=rank * n_reads * 4, ctx=ctx)
-            dm = kdist.DistMatch(owned, tdb, torch_stream=stream)
+            dm = kdist.DistMatch(owned, tdb, torch_stream=stream, mode=args.score_mode)
             rows = []
             try:
                 for r in dm.rows():

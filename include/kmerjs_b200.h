@@ -248,6 +248,21 @@ int kj_wta_next(kj_match *m, kj_row *out);
  * kj_wta_row, which finishes the row in exact-decimal arithmetic while the GPU works. */
 int kj_match_defer_rows(kj_match *m, int on);
 int kj_wta_row(kj_match *m, kj_row *out);
+/* Gathered matches (multi-GPU): instead of a collective per winner-takes-all round, every rank exports the
+ * query entries that hit its DB shard as self-contained records, the ranks all-gather them (NVLink bandwidth,
+ * one exchange), and each rank runs the loop of lib/kmerFinderClient.js:233-289 on the whole matched set.
+ *   kj_match_matched_size   : entries that hit and the sum of their template-list lengths (synchronises);
+ *   kj_match_export_matched : device buffers, entries = u64[4] {count, ordinal, list begin, list length}
+ *                             per entry (begin relative to dev_tmpl), dev_tmpl = u32 template ids in DB order;
+ *                             stream-ordered on the context's stream;
+ *   kj_match_from_matched   : a match over the segments of all ranks (device addresses as u64), template
+ *                             metadata from db (any shard: lengths / Summary are replicated).  Follow with
+ *                             kj_match_commit.  kj_match_template_kmers is not available on it. */
+int kj_match_matched_size(kj_match *m, uint64_t *n_entries, uint64_t *n_pairs);
+int kj_match_export_matched(kj_match *m, void *dev_entries, uint64_t cap_entries, void *dev_tmpl, uint64_t cap_pairs);
+int kj_match_from_matched(kj_ctx *ctx, const kj_db *db, uint32_t n_segments, const uint64_t *seg_entries,
+                          const uint64_t *seg_n_entries, const uint64_t *seg_tmpl, const uint64_t *seg_n_pairs,
+                          uint64_t kmer_map_size, kj_match **out);
 /* maxHits (lib/kmerFinderClient.js:123), default 100 */
 int kj_match_set_max_hits(kj_match *m, uint32_t max_hits);
 /* standardScoring (lib/kmerFinderServer.js:857-874): one row per matched template from the first

@@ -62,7 +62,16 @@ struct kj_match {
     const kj_db *db = nullptr;
     uint32_t T = 0;
     uint64_t Q = 0;
+    // the query entries and the template lists the kernels read: the counts handle's and the database's
+    // arrays, or (kj_match_from_matched) copies of the matched entries of every rank, owned by the match
+    const uint64_t *qcount = nullptr, *qord = nullptr;
+    uint8_t *alive = nullptr;
+    KjDbDev d{};
+    uint64_t *own_count = nullptr, *own_ord = nullptr, *own_off = nullptr;
+    uint8_t *own_alive = nullptr;
+    uint32_t *own_tmpl = nullptr;
     uint32_t *d_qkmer = nullptr;
+    unsigned long long *d_msize = nullptr;   // {matched entries, template-list pairs} of kj_match_matched_size
     uint64_t *d_part = nullptr;      // {u[T], tau[T], H}: this rank's sums
     uint64_t *d_glob = nullptr;      // global sums (== d_part unless the host layer reduces over ranks)
     uint64_t *d_first_ord = nullptr, *d_first_idx = nullptr;
@@ -207,6 +216,81 @@ __global__ void __launch_bounds__(KJ_SCORE_THREADS) kj_walk_kernel(const KjWalkA
                 }
             }
         }
+    }
+}
+
+// Matched entries of this rank as self-contained records {count, ord, off, len} + their template lists
+// (copied in DB order), for the all-gather that lets every rank run the winner-takes-all loop on the whole
+// matched set without a collective per round.  COUNT only sizes the two outputs.
+template <bool COUNT>
+__global__ void __launch_bounds__(KJ_SCORE_THREADS)
+kj_matched_export_kernel(KjDbDev d, const uint32_t *qkmer, const uint64_t *qcount, const uint64_t *qord,
+                         const uint8_t *alive, uint64_t Q, uint64_t *entries, uint64_t cap_entries,
+                         uint32_t *tmpl_out, uint64_t cap_pairs, unsigned long long *ctr) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n_groups = (Q + 31) / 32;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
+        const uint64_t q = g * 32 + lane;
+        uint32_t id = KJ_NONE32;
+        if (q < Q && alive[q]) id = qkmer[q];
+        const bool hit = id != KJ_NONE32;
+        uint64_t lo = 0, len = 0;
+        if (hit) { lo = d.list_off[id]; len = d.list_off[id + 1] - lo; }
+        uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, hit);
+        if (!hitmask) continue;
+        uint64_t incl = len;
+        for (int s = 1; s < 32; s <<= 1) {
+            uint64_t o = __shfl_up_sync(0xFFFFFFFFu, incl, s);
+            if ((int)lane >= s) incl += o;
+        }
+        const uint64_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        unsigned long long ebase = 0, pbase = 0;
+        if (lane == 0) {
+            ebase = atomicAdd(&ctr[0], (unsigned long long)__popc(hitmask));
+            pbase = atomicAdd(&ctr[1], (unsigned long long)total);
+        }
+        if (COUNT) continue;
+        ebase = __shfl_sync(0xFFFFFFFFu, ebase, 0);
+        pbase = __shfl_sync(0xFFFFFFFFu, pbase, 0);
+        const uint64_t my_off = pbase + incl - len;
+        if (hit) {
+            const uint64_t e = ebase + __popc(hitmask & ((1u << lane) - 1));
+            if (e < cap_entries) {
+                entries[4 * e + 0] = qcount[q];
+                entries[4 * e + 1] = qord[q];
+                entries[4 * e + 2] = my_off;
+                entries[4 * e + 3] = len;
+            }
+        }
+        while (hitmask) {
+            const int src = __ffs(hitmask) - 1;
+            hitmask &= hitmask - 1;
+            const uint64_t slo = __shfl_sync(0xFFFFFFFFu, lo, src);
+            const uint64_t slen = __shfl_sync(0xFFFFFFFFu, len, src);
+            const uint64_t dst = __shfl_sync(0xFFFFFFFFu, my_off, src);
+            for (uint64_t i = lane; i < slen; i += 32)
+                if (dst + i < cap_pairs) tmpl_out[dst + i] = d.tmpl[slo + i];
+        }
+    }
+}
+
+// One gathered segment -> the arrays of a gathered match.  Entry e of the segment becomes query entry
+// e0 + e with "k-mer id" 2 * (e0 + e): list_off[id] / list_off[id + 1] are its own {begin, end}.
+__global__ void kj_matched_import_kernel(const uint64_t *entries, uint64_t n, uint64_t e0, uint64_t p0,
+                                         uint64_t p_end, uint64_t *count, uint64_t *ord, uint8_t *alive,
+                                         uint32_t *qkmer, uint64_t *off, unsigned int *bad) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t e = e0 + i;
+        const uint64_t o = entries[4 * i + 2], l = entries[4 * i + 3];
+        count[e] = entries[4 * i + 0];
+        ord[e] = entries[4 * i + 1];
+        alive[e] = 1;
+        qkmer[e] = (uint32_t)(2 * e);
+        off[2 * e] = p0 + o;
+        off[2 * e + 1] = p0 + o + l;
+        if (p0 + o + l > p_end || o + l < o) atomicOr(bad, 1u);
     }
 }
 
@@ -461,7 +545,9 @@ extern "C" void kj_match_free(kj_match *m) {
     if (ctx) {
         std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         cudaSetDevice(ctx->device);
-        kj_dfree(ctx, m->d_qkmer);
+        kj_dfree(ctx, m->d_qkmer); kj_dfree(ctx, m->d_msize);
+        kj_dfree(ctx, m->own_count); kj_dfree(ctx, m->own_ord); kj_dfree(ctx, m->own_off);
+        kj_dfree(ctx, m->own_alive); kj_dfree(ctx, m->own_tmpl);
         if (m->d_glob != m->d_part) kj_dfree(ctx, m->d_glob);
         kj_dfree(ctx, m->d_part);
         kj_dfree(ctx, m->d_first_ord); kj_dfree(ctx, m->d_first_idx); kj_dfree(ctx, m->d_rank);
@@ -473,11 +559,11 @@ extern "C" void kj_match_free(kj_match *m) {
 
 static KjWalkArgs walk_args(const kj_match *m) {
     KjWalkArgs a{};
-    a.d = m->db->dev();
+    a.d = m->d;
     a.qkmer = m->d_qkmer;
-    a.qcount = m->q->reg.counts;
-    a.qord = m->q->reg.ords;
-    a.alive = m->q->reg.alive;
+    a.qcount = m->qcount;
+    a.qord = m->qord;
+    a.alive = m->alive;
     a.Q = m->Q;
     a.T = m->T;
     a.part = m->d_part;
@@ -522,6 +608,8 @@ extern "C" int kj_first_match_local(kj_ctx *ctx, kj_counts *q, const kj_db *db, 
     KJ_CUDA(ctx, cudaSetDevice(ctx->device));
     kj_match *m = new kj_match();
     m->ctx = ctx; m->q = q; m->db = db;
+    m->qcount = q->reg.counts; m->qord = q->reg.ords; m->alive = q->reg.alive;
+    m->d = db->dev();
     m->T = db->n_templates;
     m->Q = q->reg.n;
     m->kmer_map_size = q->reg.n;
@@ -589,6 +677,122 @@ extern "C" int kj_first_match_local(kj_ctx *ctx, kj_counts *q, const kj_db *db, 
         return kj_fail(ctx, KJ_E_CUDA, std::string("kj_first_match: ") + cudaGetErrorString(e));
     }
     rc = launch_walk<KJ_WALK_ACCUM>(m);
+    if (rc) { kj_match_free(m); return rc; }
+    *out = m;
+    return KJ_OK;
+}
+
+// ------------------------------------------------------------------------------------ gathered matches
+
+static int launch_export(kj_match *m, bool count, void *dev_entries, uint64_t cap_entries, void *dev_tmpl,
+                         uint64_t cap_pairs) {
+    kj_ctx *ctx = m->ctx;
+    if (!m->d_msize) KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_msize, 16));
+    KJ_CUDA(ctx, cudaMemsetAsync(m->d_msize, 0, 16, ctx->stream));
+    if (!m->Q) return KJ_OK;
+    const uint64_t groups = (m->Q + 31) / 32;
+    const int wpb = KJ_SCORE_THREADS / 32;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((groups + wpb - 1) / wpb, (uint64_t)ctx->sm_count * 8));
+    if (count)
+        KJ_LAUNCH((kj_matched_export_kernel<true>), grid, KJ_SCORE_THREADS, 0, ctx->stream, m->d, m->d_qkmer, m->qcount,
+                  m->qord, m->alive, m->Q, (uint64_t *)nullptr, (uint64_t)0, (uint32_t *)nullptr, (uint64_t)0, m->d_msize);
+    else
+        KJ_LAUNCH((kj_matched_export_kernel<false>), grid, KJ_SCORE_THREADS, 0, ctx->stream, m->d, m->d_qkmer, m->qcount,
+                  m->qord, m->alive, m->Q, (uint64_t *)dev_entries, cap_entries, (uint32_t *)dev_tmpl, cap_pairs, m->d_msize);
+    ctx->launches++;
+    KJ_CUDA(ctx, cudaGetLastError());
+    return KJ_OK;
+}
+
+extern "C" int kj_match_matched_size(kj_match *m, uint64_t *n_entries, uint64_t *n_pairs) {
+    if (!m || !n_entries || !n_pairs) return KJ_E_INVALID;
+    kj_ctx *ctx = m->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = launch_export(m, true, nullptr, 0, nullptr, 0);
+    if (rc) return rc;
+    unsigned long long *h = (unsigned long long *)m->h_res;      // pinned scratch of the match
+    KJ_CUDA(ctx, cudaMemcpyAsync(h, m->d_msize, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_entries = h[0];
+    *n_pairs = h[1];
+    return KJ_OK;
+}
+
+extern "C" int kj_match_export_matched(kj_match *m, void *dev_entries, uint64_t cap_entries, void *dev_tmpl,
+                                       uint64_t cap_pairs) {
+    if (!m || !dev_entries || !dev_tmpl) return KJ_E_INVALID;
+    kj_ctx *ctx = m->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_export(m, false, dev_entries, cap_entries, dev_tmpl, cap_pairs);     // stream-ordered, no sync
+}
+
+extern "C" int kj_match_from_matched(kj_ctx *ctx, const kj_db *db, uint32_t n_segments, const uint64_t *seg_entries,
+                                     const uint64_t *seg_n_entries, const uint64_t *seg_tmpl, const uint64_t *seg_n_pairs,
+                                     uint64_t kmer_map_size, kj_match **out) {
+    if (!ctx || !db || !out || (n_segments && (!seg_entries || !seg_n_entries || !seg_tmpl || !seg_n_pairs)))
+        return kj_fail(ctx, KJ_E_INVALID, "kj_match_from_matched: null argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t Q = 0, P = 0;
+    for (uint32_t s = 0; s < n_segments; ++s) { Q += seg_n_entries[s]; P += seg_n_pairs[s]; }
+    if (2 * Q >= KJ_NONE32) return kj_fail(ctx, KJ_E_RANGE, "too many matched entries for a gathered match");
+    kj_match *m = new kj_match();
+    m->ctx = ctx; m->q = nullptr; m->db = db;
+    m->T = db->n_templates;
+    m->Q = Q;
+    m->kmer_map_size = kmer_map_size;
+    const uint64_t T = m->T;
+    unsigned int *d_bad = nullptr;
+    cudaError_t e = kj_dmalloc(ctx, &m->d_qkmer, std::max<uint64_t>(Q, 1) * 4);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->own_count, std::max<uint64_t>(Q, 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->own_ord, std::max<uint64_t>(Q, 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->own_off, std::max<uint64_t>(2 * Q, 2) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->own_alive, std::max<uint64_t>(Q, 1));
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->own_tmpl, std::max<uint64_t>(P, 1) * 4);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_part, (2 * T + 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_ord, std::max<uint64_t>(T, 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_idx, std::max<uint64_t>(T, 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_rank, std::max<uint64_t>(T, 1) * 4);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_toff, (T + 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_tcur, std::max<uint64_t>(T, 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_res, sizeof(KjWtaResult));
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_bad, 4);
+    if (e == cudaSuccess) {
+        m->h_res = (KjWtaResult *)kj_pinned_get(ctx);
+        if (!m->h_res) e = cudaErrorMemoryAllocation;
+    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_part, 0, (2 * T + 1) * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_first_ord, 0xFF, std::max<uint64_t>(T, 1) * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_first_idx, 0xFF, std::max<uint64_t>(T, 1) * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, 4, ctx->stream);
+    uint64_t e0 = 0, p0 = 0;
+    for (uint32_t s = 0; s < n_segments && e == cudaSuccess; ++s) {
+        const uint64_t n = seg_n_entries[s], np = seg_n_pairs[s];
+        if (n) {
+            KJ_LAUNCH(kj_matched_import_kernel, kj_grid_for(ctx, n), 256, 0, ctx->stream,
+                      (const uint64_t *)(uintptr_t)seg_entries[s], n, e0, p0, p0 + np, m->own_count, m->own_ord,
+                      m->own_alive, m->d_qkmer, m->own_off, d_bad);
+            ctx->launches++;
+        }
+        if (np) e = cudaMemcpyAsync(m->own_tmpl + p0, (const void *)(uintptr_t)seg_tmpl[s], np * 4,
+                                    cudaMemcpyDeviceToDevice, ctx->stream);
+        e0 += n; p0 += np;
+    }
+    unsigned int bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    kj_dfree(ctx, d_bad);
+    if (e != cudaSuccess || bad) {
+        kj_match_free(m);
+        if (bad) return kj_fail(ctx, KJ_E_INVALID, "kj_match_from_matched: a record's template list lies outside its segment");
+        return kj_fail(ctx, KJ_E_CUDA, std::string("kj_match_from_matched: ") + cudaGetErrorString(e));
+    }
+    m->d_glob = m->d_part;
+    m->qcount = m->own_count; m->qord = m->own_ord; m->alive = m->own_alive;
+    m->d = KjDbDev{nullptr, nullptr, 0, m->own_off, m->own_tmpl};
+    int rc = launch_walk<KJ_WALK_ACCUM>(m);
     if (rc) { kj_match_free(m); return rc; }
     *out = m;
     return KJ_OK;
@@ -757,6 +961,7 @@ extern "C" int kj_match_template_kmers(kj_match *m, uint32_t template_id, uint64
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (!m->committed) return kj_fail(ctx, KJ_E_STATE, "kj_match_commit has not run");
     if (template_id >= m->T) return kj_fail(ctx, KJ_E_INVALID, "template id out of range");
+    if (!m->q) return kj_fail(ctx, KJ_E_STATE, "a gathered match has no counts handle: ask the local match");
     KJ_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t lo = m->toff_h[template_id], hi = m->toff_h[template_id + 1];
     *n_out = hi - lo;
@@ -808,8 +1013,8 @@ extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
         if (range[1] > range[0]) {
             const uint64_t n = range[1] - range[0];
             const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8));
-            KJ_LAUNCH(kj_remove_kernel, grid, 256, 0, ctx->stream, m->db->dev(), m->d_tq, range[0], range[1], m->d_qkmer,
-                      m->q->reg.counts, m->q->reg.alive, m->d_part, m->T);
+            KJ_LAUNCH(kj_remove_kernel, grid, 256, 0, ctx->stream, m->d, m->d_tq, range[0], range[1], m->d_qkmer,
+                      m->qcount, m->alive, m->d_part, m->T);
             ctx->launches++;
             KJ_CUDA(ctx, cudaGetLastError());
         }

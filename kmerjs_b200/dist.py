@@ -170,26 +170,71 @@ def count_sharded(dev_ptr: int, n_own: int, n_read: int, *, prefix=b"ATGAC", k=1
 
 
 class DistMatch:
-    """findFirstMatch + findMatches over ranks: every rank returns the same rows."""
+    """findFirstMatch + findMatches over ranks: every rank returns the same rows.
 
-    def __init__(self, owned: Counts, db, group=None, torch_stream=None):
+    mode "gather" (the default while the matched set is small enough): the ranks all-gather the query
+    entries that hit their DB shard together with those entries' template lists -- one bandwidth-bound
+    exchange over NVLink -- and each runs the winner-takes-all loop on the whole matched set, so no round
+    of the loop waits on a collective.  mode "reduce": the matched set stays sharded and every round
+    all-reduces the per-template sums ({u, tau, H}); memory per rank stays 1/N, each round pays a
+    collective's latency.  "auto" picks "gather" up to gather_limit_pairs template-list entries."""
+
+    def __init__(self, owned: Counts, db, group=None, torch_stream=None, mode: str = "auto",
+                 gather_limit_pairs: int = 1 << 28):
         """torch_stream: the torch.cuda.Stream whose handle the Context was created on.  With it the
-        reductions are stream-ordered (no host synchronisation between copy, all-reduce and copy back)."""
+        collectives are stream-ordered (no host synchronisation between copy, collective and copy back)."""
         import torch
         import torch.distributed as dist
+        if mode not in ("auto", "gather", "reduce"):
+            raise ValueError(mode)
         self.group = group
         self.torch_stream = torch_stream
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         self.dev = torch.device(f"cuda:{owned.ctx.device}")
-        self.m = Match(owned, db, local_only=True, part=rank, n_parts=world)
+        self.local = Match(owned, db, local_only=True, part=rank, n_parts=world)
+        self.m = self.local
         self._buf = {}
-        self._reduce(_abi.KJ_VEC_SCORES, "sum")
-        self._reduce(_abi.KJ_VEC_FIRST_ORD, "min")
-        self._reduce(_abi.KJ_VEC_FIRST_IDX, "min")
-        self.m.set_query_size(int(getattr(owned, "global_size", owned.size)))
+        qsize = int(getattr(owned, "global_size", owned.size))
+        ne, npairs = self.local.matched_size()
+        sz = torch.tensor([ne, npairs], dtype=torch.int64, device=self.dev)
+        all_sz = torch.empty((world, 2), dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(all_sz, sz, group=group)
+        sizes = [(int(a), int(b)) for a, b in all_sz.tolist()]
+        total_pairs = sum(b for _, b in sizes)
+        self.mode = mode if mode != "auto" else ("gather" if total_pairs <= gather_limit_pairs else "reduce")
+        if self.mode == "gather":
+            self._gather(db, sizes, qsize, world, rank)
+        else:
+            self._reduce(_abi.KJ_VEC_SCORES, "sum")
+            self._reduce(_abi.KJ_VEC_FIRST_ORD, "min")
+            self._reduce(_abi.KJ_VEC_FIRST_IDX, "min")
+        self.m.set_query_size(qsize)
         self.m.commit()
+        self._gathered = None
         if self.m.hits == 0:
             raise NoHitsError("No hits were found!")
+
+    def _gather(self, db, sizes, qsize, world, rank):
+        import contextlib
+        import torch
+        import torch.distributed as dist
+        max_e = max(max(a for a, _ in sizes), 1)
+        max_p = max(max(b for _, b in sizes), 1)
+        seg_bytes = max_e * 32 + ((max_p * 4 + 15) // 16) * 16          # {entries | template ids}, one payload
+        mine = torch.empty(seg_bytes, dtype=torch.uint8, device=self.dev)
+        allb = torch.empty((world, seg_bytes), dtype=torch.uint8, device=self.dev)
+        ordered = torch.cuda.stream(self.torch_stream) if self.torch_stream is not None else contextlib.nullcontext()
+        with ordered:
+            self.local.export_matched(mine.data_ptr(), max_e, mine.data_ptr() + max_e * 32, max_p)
+            if self.torch_stream is None:
+                torch.cuda.synchronize(self.dev)
+            dist.all_gather_into_tensor(allb, mine, group=self.group)
+            if self.torch_stream is None:
+                torch.cuda.synchronize(self.dev)
+            segs = [(allb[r].data_ptr(), sizes[r][0], allb[r].data_ptr() + max_e * 32, sizes[r][1])
+                    for r in range(world)]
+            self.m = Match.from_matched(self.local.ctx, db, segs, qsize, part=rank, n_parts=world)
+        self._gathered = (mine, allb)       # alive until commit() has synchronised
 
     def _reduce(self, which: int, op: str):
         import torch
@@ -218,6 +263,12 @@ class DistMatch:
 
     def rows(self, max_hits: int = 100):
         self.m.set_max_hits(max_hits)
+        if self.mode == "gather":
+            while True:
+                row = self.m.next_row()
+                if row is None:
+                    return
+                yield row
         self.m.defer_rows(True)
         while True:
             state, row = self.m.next_row_begin()
@@ -231,4 +282,6 @@ class DistMatch:
             yield row
 
     def free(self):
-        self.m.free()
+        if self.m is not self.local:
+            self.m.free()
+        self.local.free()

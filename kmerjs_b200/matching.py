@@ -45,7 +45,35 @@ class Match:
         self.handle = h
         self.last_row = None
 
+    @classmethod
+    def from_matched(cls, ctx, db: TemplateDB, segments, query_size: int, *, part: int = 0, n_parts: int = 1):
+        """A match over the matched entries of all ranks (kj_match_from_matched).  segments: one
+        (entries_dev_ptr, n_entries, tmpl_dev_ptr, n_pairs) per rank, as written by export_matched."""
+        self = cls.__new__(cls)
+        self.counts, self.db, self.ctx = None, db, ctx
+        self._L = _abi.lib()
+        self._dbh = db.device(ctx, part, n_parts)
+        n = len(segments)
+        arr = lambda i: (C.c_uint64 * max(n, 1))(*[int(s[i]) for s in segments])
+        h = C.c_void_p()
+        _abi.check(self._L.kj_match_from_matched(ctx.handle, self._dbh.handle, n, arr(0), arr(1), arr(2), arr(3),
+                                                 int(query_size), C.byref(h)), ctx.handle)
+        self.handle = h
+        self.last_row = None
+        return self
+
     # -- distributed protocol ---------------------------------------------------------------------
+    def matched_size(self):
+        """(entries that hit the DB, sum of their template-list lengths) on this rank."""
+        ne, np_ = C.c_uint64(), C.c_uint64()
+        _abi.check(self._L.kj_match_matched_size(self.handle, C.byref(ne), C.byref(np_)), self.ctx.handle)
+        return int(ne.value), int(np_.value)
+
+    def export_matched(self, entries_ptr: int, cap_entries: int, tmpl_ptr: int, cap_pairs: int):
+        """Stream-ordered on the context's stream (kj_match_export_matched)."""
+        _abi.check(self._L.kj_match_export_matched(self.handle, C.c_void_p(entries_ptr), cap_entries,
+                                                   C.c_void_p(tmpl_ptr), cap_pairs), self.ctx.handle)
+
     def vec_len(self, which: int) -> int:
         return int(self._L.kj_match_vec_len(self.handle, which))
 

@@ -1,6 +1,7 @@
 """The multi-GPU path over real NCCL (needs >= 2 GPUs; skipped otherwise): reads sharded over ranks,
-owner all-to-all, sharded DB, all-reduced score vectors, replicated WTA -- every rank must produce the rows
-of the single-GPU run over all the reads, in both the synchronous and the stream-ordered reduction mode."""
+owner all-to-all, sharded DB, all-reduced score vectors or the all-gathered matched set, replicated WTA -- every rank must produce the
+rows of the single-GPU run over all the reads, in both scoring modes ("reduce", "gather"), each synchronous
+and stream-ordered."""
 import os
 import socket
 
@@ -36,10 +37,12 @@ def _worker(rank, world, port, q):
         w = synth.Workload(n_reads=n_reads, genome_len=1_000_000, seed=5, first_read=rank * n_reads, ctx=ctx)
         tdb = synth.template_db_from_genome(w.genome_host(), 8, b"ATGAC", 16)
         out = {}
-        for mode, ts in (("sync", None), ("stream", stream)):
+        for mode, ts, how in (("sync", None, "reduce"), ("stream", stream, "reduce"),
+                              ("gather-sync", None, "gather"), ("gather-stream", stream, "auto")):
             owned = kdist.count_sharded(w.fastq_ptr, w.n_bytes, w.n_bytes, prefix=b"ATGAC", k=16, step=1, final=True,
                                         base_line=rank * n_reads * 4, ctx=ctx)
-            dm = kdist.DistMatch(owned, tdb, torch_stream=ts)
+            dm = kdist.DistMatch(owned, tdb, torch_stream=ts, mode=how)
+            assert dm.mode == ("gather" if how == "auto" else how)
             rows, err = [], None
             try:
                 for r in dm.rows():
@@ -92,7 +95,7 @@ def test_two_ranks_equal_single_gpu():
     assert len(single["rows"]) >= 1
     merged = {}
     for rank in range(world):
-        for mode in ("sync", "stream"):
+        for mode in ("sync", "stream", "gather-sync", "gather-stream"):
             o = res[rank][mode]
             for f in ("size", "lines", "hits", "order", "rows", "err"):
                 assert o[f] == single[f], (rank, mode, f)

@@ -158,3 +158,82 @@ def test_sharded_scoring_equals_single_device():
         m.free()
     for oc in owned:
         oc.free()
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_gathered_match_equals_single_device(world):
+    """kj_match_matched_size / export_matched / from_matched: the matched entries of every (emulated) rank,
+    gathered, give the rows, hits and first-encounter order of the single-device run -- and of the oracle."""
+    golden_reads = read_golden("test_long.kmer.fastq")
+    exp_counts, _ = ko_c.count_fastq(golden_reads)
+    rng = random.Random(2718)
+    lists, attrs, summary = synthetic_db(list(exp_counts.keys()), rng, n_templates=20, decoys=80, share=0.7)
+    tdb = TemplateDB.from_lists(lists, attrs, summary)
+    db = ko.TemplateDB(lists, attrs, summary)
+    q = OrderedDict(exp_counts)
+    templates, hits = ko.first_match(q, db)
+    e_rows, e_err = [], None
+    try:
+        for r in ko.find_matches(templates, summary, q, len(exp_counts)):
+            e_rows.append(r)
+    except RuntimeError as exc:
+        e_err = str(exc)
+    owned, totals, _keep = sharded_counts(golden_reads, world)
+    qsize = sum(oc.size for oc in owned)
+    ms = [Match(oc, tdb, local_only=True, part=r, n_parts=world) for r, oc in enumerate(owned)]
+    sizes = [m.matched_size() for m in ms]
+    assert sum(p for _, p in sizes) == hits
+    segs, keep = [], []
+    for m, (ne, npairs) in zip(ms, sizes):
+        pe, ke, back_e = dev_u64(np.zeros(max(4 * ne, 4), dtype=np.uint64))
+        pt, kt, back_t = dev_u64(np.zeros(max((npairs + 1) // 2, 1), dtype=np.uint64))
+        m.export_matched(pe, ne, pt, npairs)
+        assert m.matched_size() == (ne, npairs)                 # sizing is repeatable (and synchronises)
+        ent = back_e()[:4 * ne].reshape(-1, 4)
+        # every entry's list lies inside the rank's template array and the lists tile it exactly
+        spans = sorted((int(o), int(o + l)) for _, _, o, l in ent)
+        pos = 0
+        for lo, hi in spans:
+            assert lo == pos
+            pos = hi
+        assert pos == npairs
+        tm = back_t().view(np.uint32)[:npairs]
+        assert tm.size == 0 or int(tm.max()) < tdb.n_templates
+        segs.append((pe, ne, pt, npairs))
+        keep += [ke, kt]
+    g = Match.from_matched(ms[0].ctx, tdb, segs, qsize, part=0, n_parts=world)
+    g.commit()
+    assert g.hits == hits and list(g.templates().keys()) == list(templates.keys())
+    assert {n: (t["uScore"], t["tScore"]) for n, t in g.templates().items()} == \
+        {n: (t["uScore"], t["tScore"]) for n, t in templates.items()}
+    with pytest.raises(_abi.KjError):
+        g.template_kmers(0)
+    g_rows, g_err = [], None
+    try:
+        while True:
+            r = g.next_row()
+            if r is None:
+                break
+            g_rows.append(r)
+    except NoHitsError as exc:
+        g_err = str(exc)
+    assert [r["template"] for r in g_rows] == [r["template"] for r in e_rows]
+    for a, e in zip(g_rows, e_rows):
+        for f in ko.ROW_KEYS:
+            if f == "probability":
+                assert a[f] == pytest.approx(e[f], rel=1e-9)
+            else:
+                assert a[f] == e[f], f
+    assert g_err == e_err
+    # a record pointing outside its segment is refused
+    if sizes[0][0]:
+        bad = np.zeros(4, dtype=np.uint64)
+        bad[2], bad[3] = 0, sizes[0][1] + 1
+        pb, kb, _ = dev_u64(bad)
+        with pytest.raises(_abi.KjError):
+            Match.from_matched(ms[0].ctx, tdb, [(pb, 1, segs[0][2], sizes[0][1])], qsize)
+    g.free()
+    for m in ms:
+        m.free()
+    for oc in owned:
+        oc.free()

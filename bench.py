@@ -239,7 +239,7 @@ def run_b200(args):
             t = time.perf_counter()
             owned = kdist.count_sharded(w.fastq_ptr, w.n_bytes, w.n_bytes, prefix=PREFIX, k=K, step=STEP, final=True,
                                         base_line=rank * n_reads * 4, capacity_hint=hint, flags=state.get("flags", 0),
-                                        ctx=ctx)
+                                        ctx=ctx, trace=state.get("fine_trace"))
             t = tick("count+exchange", t)
             dm = kdist.DistMatch(owned, tdb, torch_stream=stream, mode=args.score_mode)
             t = tick("first_match+reduce", t)
@@ -286,6 +286,15 @@ def run_b200(args):
     if args.trace:            # every rank runs the step (it contains collectives); rank 0 prints
         trace.clear()
         step_device()
+        coarse = dict(trace)
+        trace.clear()
+        state["fine_trace"] = trace         # synchronising marks inside count_sharded: a second, slower step
+        step_device()
+        state["fine_trace"] = None
+        fine = {k: round(v, 3) for k, v in trace.items() if k[:2] in ("c.", "x.")}
+        trace.clear(); trace.update(coarse)
+        if rank == 0 and fine:
+            print("trace (ms, count+exchange phases, synchronised):", json.dumps(fine), file=sys.stderr)
         if rank == 0:
             print("trace (ms, one device-resident step):", json.dumps({k: round(v, 3) for k, v in trace.items()}), file=sys.stderr)
     ctx.enable_timers(True)

@@ -92,13 +92,46 @@ class _CudaView:
                                          "version": 2, "strides": None}
 
 
-def exchange_counts(local: Counts, group=None) -> Counts:
+_IRR_INLINE = 1024 * 56        # bytes of irregular records that ride in the totals all-gather
+_STAGE = {}
+
+
+def _pinned_stage(device: int):
+    import torch
+    t = _STAGE.get(device)
+    if t is None:
+        t = torch.zeros(40 + _IRR_INLINE + 24, dtype=torch.uint8).pin_memory()
+        _STAGE[device] = t
+    return t
+
+
+class _Trace:
+    """Optional phase timing (a dict the caller passes): synchronises at every mark, so only for diagnosis."""
+
+    def __init__(self, sink, dev):
+        import time
+        self.sink, self.dev, self.t = sink, dev, time.perf_counter()
+
+    def mark(self, name):
+        if self.sink is None:
+            return
+        import time
+        import torch
+        torch.cuda.synchronize(self.dev)
+        now = time.perf_counter()
+        self.sink[name] = self.sink.get(name, 0.0) + (now - self.t) * 1e3
+        self.t = now
+
+
+def exchange_counts(local: Counts, group=None, trace=None) -> Counts:
     """Local table -> the table of the k-mers this rank owns (collective)."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = torch.device(f"cuda:{local.ctx.device}")
+    tr = _Trace(trace, dev)
     ptr, sizes = local.partition(world)
+    tr.mark("x.partition")
     n = sum(sizes)
     if n:
         send = torch.as_tensor(_CudaView(ptr, 3 * n), device=dev).reshape(-1, 3)
@@ -106,20 +139,30 @@ def exchange_counts(local: Counts, group=None) -> Counts:
         send = torch.empty((0, 3), dtype=torch.int64, device=dev)
     recv = exchange_records(send, sizes, group)
     torch.cuda.synchronize(dev)
+    tr.mark("x.all_to_all")
     owned = Counts(local.prefix, local.k, local.step, flags=local.flags & ~(_abi.KJ_F_FORWARD_ONLY),
                    capacity_hint=max(int(recv.shape[0]), 1024), ctx=local.ctx)
     if recv.shape[0]:
         owned.merge_records(recv.data_ptr(), int(recv.shape[0]))
-    # one small all-gather carries everything the ranks need from each other besides the records:
-    # irregular-record bytes (rare k-mers, gathered on rank 0), line / base / occurrence / byte totals
+    tr.mark("x.merge")
+    # one small all-gather carries everything the ranks need from each other besides the records: line /
+    # base / occurrence / byte totals and -- while they fit _IRR_INLINE bytes, the usual case: k-mers with
+    # N or other non-ACGT bytes are rare -- the irregular records themselves (gathered on rank 0)
     irr = local.irregular_records()
-    mine_v = torch.tensor([irr.size, local.lines, local.bases, local.occurrences, local.bytes_read],
-                          dtype=torch.int64, device=dev)
-    all_v = torch.empty((world, 5), dtype=torch.int64, device=dev)
+    head = np.array([irr.size, local.lines, local.bases, local.occurrences, local.bytes_read], dtype=np.int64)
+    stage = _pinned_stage(local.ctx.device)
+    stage[:40] = torch.from_numpy(head.view(np.uint8))
+    n_inline = min(int(irr.size), _IRR_INLINE)
+    if n_inline:
+        stage[40:40 + n_inline] = torch.from_numpy(irr[:n_inline])
+    mine_v = stage.to(dev, non_blocking=True)
+    all_v = torch.empty((world, stage.numel()), dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(all_v, mine_v, group=group)
-    rows = all_v.tolist()
+    host_v = all_v.cpu().numpy()
+    rows = [host_v[r, :40].view(np.int64).tolist() for r in range(world)]
     sizes_irr = [int(r[0]) for r in rows]
-    if max(sizes_irr) > 0:
+    tr.mark("x.totals_allgather")
+    if max(sizes_irr) > _IRR_INLINE:
         pad = max(sizes_irr)
         mine = torch.zeros(pad, dtype=torch.uint8, device=dev)
         if irr.size:
@@ -128,24 +171,36 @@ def exchange_counts(local: Counts, group=None) -> Counts:
         dist.all_gather_into_tensor(parts, mine, group=group)
         if rank == 0:
             host = parts.cpu().numpy()
-            for rr, sz in enumerate(sizes_irr):
-                if sz:
-                    owned.merge_irregular(host[rr, :sz])
+            owned.merge_irregular(np.concatenate([host[rr, :sz] for rr, sz in enumerate(sizes_irr)]))
+    elif rank == 0 and max(sizes_irr) > 0:
+        owned.merge_irregular(np.concatenate([host_v[rr, 40:40 + sz] for rr, sz in enumerate(sizes_irr)]))
+    tr.mark("x.irregular")
     owned.finish()
+    tr.mark("x.finish_owned")
     # a rank's line count already includes the lines before its range (base_line): the last rank's is the file's
     lines = max(int(r[1]) for r in rows)
     bases, occ, nbytes = (sum(int(r[i]) for r in rows) for i in (2, 3, 4))
-    qs = torch.tensor([owned.size], dtype=torch.int64, device=dev)
-    dist.all_reduce(qs, group=group)
-    qsize = int(qs.item())
     owned.set_totals(lines, bases, occ, nbytes)
-    owned.global_size = qsize
+    owned.global_size = None        # kmerMap.size over all ranks: global_size() / DistMatch fill it in
+    tr.mark("x.set_totals")
     return owned
+
+
+def global_size(owned: Counts, group=None) -> int:
+    """kmerMap.size of the whole query = sum of the owners' table sizes (collective; cached on the handle).
+    DistMatch folds this sum into its own first all-gather, so the scoring path never calls it."""
+    import torch
+    import torch.distributed as dist
+    if getattr(owned, "global_size", None) is None:
+        qs = torch.tensor([owned.size], dtype=torch.int64, device=torch.device(f"cuda:{owned.ctx.device}"))
+        dist.all_reduce(qs, group=group)
+        owned.global_size = int(qs.item())
+    return owned.global_size
 
 
 def count_sharded(dev_ptr: int, n_own: int, n_read: int, *, prefix=b"ATGAC", k=16, step=1, final: bool,
                   base_line: int | None = None, base_col: int = 0, capacity_hint: int = 0, flags: int = 0,
-                  group=None, ctx=None) -> Counts:
+                  group=None, ctx=None, trace=None) -> Counts:
     """Count this rank's byte range and exchange.  With base_line None the ranks agree on the record
     phase first (newline counts of the owned ranges, allgathered)."""
     import torch
@@ -160,12 +215,18 @@ def count_sharded(dev_ptr: int, n_own: int, n_read: int, *, prefix=b"ATGAC", k=1
         rows = [[int(x) for x in v.tolist()] for v in allv]
         bl, bc = phase_of_ranges([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows])
         base_line, base_col = bl[rank], bc[rank]
+    tr = _Trace(trace, torch.device(f"cuda:{(ctx.device if ctx else 0)}"))
     local = Counts(prefix, k, step, flags=flags, base_line=base_line, base_col=base_col,
                    capacity_hint=capacity_hint, ctx=ctx)
+    tr.mark("c.create")
     local.add_device(dev_ptr, n_read, own_n=n_own, final=final)
+    tr.mark("c.add_device")
     local.finish()
-    owned = exchange_counts(local, group)
+    tr.mark("c.finish_local")
+    owned = exchange_counts(local, group, trace)
+    tr.t = __import__("time").perf_counter()
     local.free()
+    tr.mark("c.free_local")
     return owned
 
 
@@ -194,12 +255,15 @@ class DistMatch:
         self.local = Match(owned, db, local_only=True, part=rank, n_parts=world)
         self.m = self.local
         self._buf = {}
-        qsize = int(getattr(owned, "global_size", owned.size))
         ne, npairs = self.local.matched_size()
-        sz = torch.tensor([ne, npairs], dtype=torch.int64, device=self.dev)
-        all_sz = torch.empty((world, 2), dtype=torch.int64, device=self.dev)
+        sz = torch.tensor([ne, npairs, owned.size], dtype=torch.int64, device=self.dev)
+        all_sz = torch.empty((world, 3), dtype=torch.int64, device=self.dev)
         dist.all_gather_into_tensor(all_sz, sz, group=group)
-        sizes = [(int(a), int(b)) for a, b in all_sz.tolist()]
+        gathered = all_sz.tolist()
+        sizes = [(int(a), int(b)) for a, b, _ in gathered]
+        qsize = sum(int(c) for _, _, c in gathered)           # kmerMap.size (lib/kmerFinderClient.js:242)
+        if getattr(owned, "global_size", None) is None:
+            owned.global_size = qsize
         total_pairs = sum(b for _, b in sizes)
         self.mode = mode if mode != "auto" else ("gather" if total_pairs <= gather_limit_pairs else "reduce")
         if self.mode == "gather":

@@ -38,7 +38,15 @@ KJ_HD uint32_t kj_pack4(uint32_t w) {
 
 // 16 bytes -> 32 bits: code of byte p at bits 2p..2p+1
 KJ_HD uint32_t kj_pack16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+#if defined(__CUDA_ARCH__)
+    // the multiply leaves the four codes of a word in its top byte: three byte permutes collect the top
+    // bytes of the four products (11 instructions instead of 17 with shifts and ORs)
+    const uint32_t p0 = (w0 & 0x06060606u) * 0x00820820u, p1 = (w1 & 0x06060606u) * 0x00820820u;
+    const uint32_t p2 = (w2 & 0x06060606u) * 0x00820820u, p3 = (w3 & 0x06060606u) * 0x00820820u;
+    return __byte_perm(__byte_perm(p0, p1, 0x0073u), __byte_perm(p2, p3, 0x0073u), 0x5410u);
+#else
     return kj_pack4(w0) | (kj_pack4(w1) << 8) | (kj_pack4(w2) << 16) | (kj_pack4(w3) << 24);
+#endif
 }
 
 // 4 bytes -> 4 bits: bit i set iff byte i == '\n'
@@ -49,8 +57,24 @@ KJ_HD uint32_t kj_nl4(uint32_t w) {
 }
 
 // 16 bytes -> 16 bits
+// msb of byte i set iff byte i == '\n'
+KJ_HD uint32_t kj_nl_flags4(uint32_t w) {
+    uint32_t t = ((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | w) & 0x80808080u;
+}
+
 KJ_HD uint32_t kj_nl16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+#if defined(__CUDA_ARCH__)
+    // the 4-way byte dot product gathers four flag bytes (0x80 or 0) in one instruction: weights 1,2,4,8
+    // for one word, 16..128 for the next, so two words leave 8 mask bits times 128 in the accumulator
+    uint32_t lo = __dp4a(kj_nl_flags4(w0), 0x08040201u, 0u);
+    lo = __dp4a(kj_nl_flags4(w1), 0x80402010u, lo);
+    uint32_t hi = __dp4a(kj_nl_flags4(w2), 0x08040201u, 0u);
+    hi = __dp4a(kj_nl_flags4(w3), 0x80402010u, hi);
+    return (lo >> 7) | ((hi << 1) & 0xFF00u);
+#else
     return kj_nl4(w0) | (kj_nl4(w1) << 4) | (kj_nl4(w2) << 8) | (kj_nl4(w3) << 12);
+#endif
 }
 
 // 4 bytes -> nonzero iff some byte is not one of 'A','C','G','T' (upper case).  The 2-bit code of

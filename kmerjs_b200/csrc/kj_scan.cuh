@@ -33,7 +33,11 @@
 #define KJ_STHREADS 224
 #define KJ_ETHREADS 64
 #define KJ_FTHREADS (KJ_CTHREADS + KJ_STHREADS + KJ_ETHREADS)
-#define KJ_FQCAP 256                                     // candidate queue entries per slot (~56 per tile)
+#define KJ_FQCAP 256                                     // candidate queue entries per slot (~55 chunks per tile hold one)
+// One queue entry per 16-byte chunk that holds a candidate: the lanes that passed the code-space filter
+// (bit 2p: forward window at chunk position p, bit 2p + 1: reverse-strand window) and the chunk index.
+// The stream warps only store the two words; the emit warps take the bits apart.
+struct KjCandQueue { uint32_t lanes[KJ_FQCAP]; uint16_t chunk[KJ_FQCAP]; };
 #define KJ_STAGE_BYTES (KJ_TILE_BYTES + 32)              // a tile and the 32 bytes its last windows reach into
 #define KJ_HALF_BYTES (KJ_TILE_BYTES / 2)                // the tile is copied and converted in two halves
 #define KJ_NO_TILE 0xFFFFFFFFu
@@ -117,7 +121,7 @@ __device__ __forceinline__ uint4 kj_load_chunk(const uint8_t *buf, uint64_t off,
 // next tile can be converted (and its aggregate published) before the current one is finished
 struct __align__(16) KjTileSmem {
     uint16_t nl[KJ_TILE_CHUNKS];          // '\n' mask of the chunk: together a bitmap of the tile, bit p = byte p
-    uint32_t row_pre[KJ_ROWS];            // row counts, then exclusive prefix over the tile
+    uint32_t row_pre[KJ_ROWS];            // exclusive prefix of the rows' newline counts over the tile (kj_tile_rowscan_warp)
     uint32_t q_n;                         // entries in the kernel's candidate / line queue
     uint32_t tile_count;                  // '\n' in the tile
     unsigned long long excl_count;        // '\n' before the tile (whole stream)
@@ -236,14 +240,10 @@ __device__ __forceinline__ void kj_nbar_arrive(uint32_t id, uint32_t count) {
 }
 #endif
 
-// one 16-byte chunk -> code word, newline mask, row count (warp = 32 consecutive chunks = one row)
-__device__ __forceinline__ void kj_p1_chunk(uint32_t *codes, KjTileSmem &s, uint32_t c, uint32_t row, const uint4 v,
-                                            uint32_t nl_keep) {
+// one 16-byte chunk -> code word and newline mask (the rows are counted by kj_tile_rowscan_warp)
+__device__ __forceinline__ void kj_p1_chunk(uint32_t *codes, KjTileSmem &s, uint32_t c, const uint4 v, uint32_t nl_keep) {
     codes[c] = kj_pack16(v.x, v.y, v.z, v.w);
-    const uint32_t nl = kj_nl16(v.x, v.y, v.z, v.w) & nl_keep;
-    s.nl[c] = (uint16_t)nl;
-    const uint32_t rc = __reduce_add_sync(0xFFFFFFFFu, __popc(nl));
-    if ((threadIdx.x & 31) == 0) s.row_pre[row] = rc;
+    s.nl[c] = (uint16_t)(kj_nl16(v.x, v.y, v.z, v.w) & nl_keep);
 }
 
 // P1 of one half of the staged tile (interior tiles: every byte owned, halo readable) by a group of
@@ -256,7 +256,7 @@ __device__ __forceinline__ void kj_tile_p1_stage(uint32_t *codes, KjTileSmem &s,
     for (int it = HALF * (CPT / 2); it < (HALF + 1) * (CPT / 2); ++it) {      // the first or the second half of the tile
         const uint32_t c = it * NT + t;
         const uint4 v = *reinterpret_cast<const uint4 *>(stage + c * 16u);
-        kj_p1_chunk(codes, s, c, c >> 5, v, 0xFFFFu);
+        kj_p1_chunk(codes, s, c, v, 0xFFFFu);
     }
     if (HALF == 1 && t < 2) {
         const uint4 h = *reinterpret_cast<const uint4 *>(stage + (KJ_TILE_CHUNKS + t) * 16u);
@@ -280,7 +280,7 @@ static __device__ __noinline__ void kj_tile_p1_global(const KjScanArgs &a, uint3
         uint32_t keep = 0xFFFFu;
         if (off >= a.own_n) keep = 0;
         else if (off + 16 > a.own_n) keep = (1u << (uint32_t)(a.own_n - off)) - 1u;
-        kj_p1_chunk(codes, s, c, c >> 5, v, keep);
+        kj_p1_chunk(codes, s, c, v, keep);
     }
     if (t < 2) {   // halo code words
         const uint64_t off = tile_off + (uint64_t)(KJ_TILE_CHUNKS + t) * 16u;
@@ -293,8 +293,19 @@ static __device__ __noinline__ void kj_tile_p1_global(const KjScanArgs &a, uint3
 __device__ __forceinline__ void kj_tile_rowscan_warp(const KjScanArgs &a, KjTileSmem &s, uint32_t tile) {
     const uint32_t lane = threadIdx.x & 31;
     static_assert(KJ_ROWS <= 64, "two rows per lane");
-    const uint32_t c0 = 2 * lane < KJ_ROWS ? s.row_pre[2 * lane] : 0u;
-    const uint32_t c1 = 2 * lane + 1 < KJ_ROWS ? s.row_pre[2 * lane + 1] : 0u;
+    static_assert(KJ_ROWS % 2 == 0, "a lane counts a pair of rows");
+    // newlines of rows 2 * lane and 2 * lane + 1, straight from the masks: a row is 32 masks = 16 words;
+    // the lanes start at different words of their rows so that a load touches 16 banks, not one
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(s.nl) + 32u * lane;
+    uint32_t c0 = 0, c1 = 0;
+    if (2 * lane < KJ_ROWS) {
+#pragma unroll
+        for (uint32_t j = 0; j < 16; ++j) {
+            const uint32_t i = (j + lane) & 15u;
+            c0 += __popc(w[i]);
+            c1 += __popc(w[16u + i]);
+        }
+    }
     const uint32_t sum = c0 + c1;
     uint32_t incl = sum;
 #pragma unroll
@@ -589,7 +600,7 @@ __device__ __forceinline__ void kj_chunk_filter(const KjScanArgs &a, const uint3
 
 // P2 of one tile by a group of NT threads: bit-parallel prefix search in code space; candidates -> queue
 template <int MP, int RC, int NT, bool FULL>
-__device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32_t *codes, KjTileSmem &s, uint16_t *queue,
+__device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32_t *codes, KjTileSmem &s, KjCandQueue &queue,
                                                uint32_t own_in_tile, uint32_t t) {
     constexpr int CPT = KJ_TILE_CHUNKS / NT;
 #pragma unroll 4
@@ -603,14 +614,9 @@ __device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32
             const uint32_t keep = (1u << (2u * (own_in_tile - pos0))) - 1u;
             zf &= keep; zr &= keep;
         }
-        while (zf | zr) {
-            const uint32_t strand = zf ? 0u : 1u;
-            uint32_t &z = zf ? zf : zr;
-            const uint32_t bit = __ffs(z) - 1;
-            z &= z - 1;
-            const uint32_t jt = pos0 + (bit >> 1);
+        if (zf | zr) {                                     // one chunk in 32
             const uint32_t q = atomicAdd(&s.q_n, 1u);
-            if (q < KJ_FQCAP) queue[q] = (uint16_t)((jt << 1) | strand);
+            if (q < KJ_FQCAP) { queue.lanes[q] = zf | (zr << 1); queue.chunk[q] = (uint16_t)c; }
         }
     }
 }
@@ -635,7 +641,7 @@ __global__ void __launch_bounds__(KJ_FTHREADS, 4)
 kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ uint32_t codes[KJ_TILE_CHUNKS + 2];              // +2 halo words: windows reach k-1 bytes past the tile
     __shared__ KjTileSmem meta[KJ_SLOTS];
-    __shared__ uint16_t queue[KJ_SLOTS][KJ_FQCAP];              // candidates: tile position << 1 | strand
+    __shared__ KjCandQueue queue[KJ_SLOTS];                     // chunks with candidate lanes
     __shared__ uint32_t tile_of[KJ_SLOTS];                      // tile in the slot (KJ_NO_TILE: no more work)
     __shared__ uint32_t tile_next;                              // ticket fetched ahead
     __shared__ KjCtlCmd ctl[2];
@@ -716,15 +722,20 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                 // the record buffer, in blocks of KJ_REC_BLOCK records reserved per warp (one global
                 // atomic per block, off the per-tile path).
                 for (uint32_t q0 = 0; q0 < qn; q0 += KJ_ETHREADS) {
-                    const uint32_t q = q0 + et;
+                  const uint32_t q = q0 + et;
+                  uint32_t lanes = 0, cpos = 0;
+                  if (q < qn) { lanes = queue[b].lanes[q]; cpos = 16u * queue[b].chunk[q]; }
+                  // one candidate of every lane's chunk per round (a chunk rarely holds two)
+                  while (__any_sync(0xFFFFFFFFu, lanes != 0u)) {
                     bool keep = false;
                     uint64_t ord = 0, rec = 0;
-                    uint32_t e = 0;
-                    if (q < qn) {
-                        e = queue[b][q];
-                        if (tile_off + (e >> 1) + a.k <= a.n)
-                            keep = kj_candidate_line(a, m, tile_off, tile_voff, e >> 1, e & 1u, ord);
-                        rec = (tile_off + (e >> 1)) | ((e & 1u) ? KJ_REC_STRAND : 0ull);
+                    if (lanes) {
+                        const uint32_t bit = __ffs(lanes) - 1;
+                        lanes &= lanes - 1;
+                        const uint32_t jt = cpos + (bit >> 1), strand = bit & 1u;
+                        if (tile_off + jt + a.k <= a.n)
+                            keep = kj_candidate_line(a, m, tile_off, tile_voff, jt, strand, ord);
+                        rec = (tile_off + jt) | (strand ? KJ_REC_STRAND : 0ull);
                     }
                     const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
                     const uint32_t need = __popc(kb);
@@ -754,6 +765,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                         kj_window_load(a, rec & ~KJ_REC_STRAND, v0, v1, v2);
                         kj_window_emit(a, rec & ~KJ_REC_STRAND, (uint32_t)(rec >> 63), ord, v0, v1, v2, n_emit);
                     }
+                  }
                 }
             } else {
                 // dense candidates (e.g. homopolymer input): the code words are gone by now, so every
@@ -927,7 +939,6 @@ kj_scan_dense_kernel(const __grid_constant__ KjScanArgs a) {
                 if ((int)lane >= d) incl += o;
             }
             ds.pre[c] = (uint16_t)(incl - cnt);
-            if (lane == 31) s.row_pre[c >> 5] = incl;
         }
         if (tid < 2) {   // halo
             const uint64_t off = tile_off + (uint64_t)(KJ_TILE_CHUNKS + tid) * 16u;

@@ -9,9 +9,11 @@
 // hits) and a double-precision z for the gate; the reported row is finished here so that the
 // rounded fields are identical to the reference's, not merely close.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 #include "kj_stats.hpp"
@@ -200,21 +202,41 @@ static void divmod(const Big &a, const Big &b, Big &q, Big &r) {
         r.d[i] = sh ? (u[i] >> sh) | ((uint64_t)u[i + 1] << (32 - sh)) : u[i];
     r.trim();
 }
-static Big pow10(unsigned e) {
+static Big pow10_slow(unsigned e) {
     Big r(1);
     while (e >= 9) { r = mul_small(r, 1000000000u); e -= 9; }
     static const uint32_t p[9] = {1, 10, 100, 1000, 10000, 100000, 1000000, 10000000, 100000000};
     if (e) r = mul_small(r, p[e]);
     return r;
 }
+// the exponents the rows use (<= 2 DP + a few) come from a table built once
+struct Pow10Table {
+    enum { N = 96 };
+    Big p[N];
+    Pow10Table() { for (unsigned e = 0; e < N; ++e) p[e] = pow10_slow(e); }
+};
+static const Big &pow10(unsigned e) {
+    static const Pow10Table t;
+    static thread_local Big big;
+    if (e < Pow10Table::N) return t.p[e];
+    big = pow10_slow(e);
+    return big;
+}
 // floor(sqrt(a)): Newton's iteration from above, x <- (x + a / x) / 2 until it stops decreasing
 static Big isqrt(const Big &a) {
     if (a.zero()) return Big();
-    const size_t nb = (bits(a) + 1) / 2;
-    Big x;                                     // 2^nb >= sqrt(a)
-    x.d.assign(nb / 32 + 1, 0);
-    x.d[nb / 32] = 1u << (nb % 32);
-    x.trim();
+    // start from above: the top 62 bits of a give sqrt(a) to ~30 bits (hardware sqrt, rounded up with
+    // a margin), so Newton's iteration needs 2-3 divisions instead of one per bit-doubling from 2^nb
+    const size_t na = bits(a);
+    size_t s = na > 62 ? na - 62 : 0;
+    s += s & 1;                                // even shift
+    uint64_t top = 0;
+    for (size_t i = 0; i < 64 && s + i < na; ++i)
+        if (bit(a, s + i)) top |= 1ull << i;
+    uint64_t r0 = (uint64_t)std::sqrt((double)top) + 2;      // >= floor(sqrt(top)) + 1 despite rounding
+    while (r0 * r0 <= top) ++r0;                              // r0 < 2^32 here, the product cannot wrap
+    Big x(r0);                                 // x = r0 << (s / 2) >= sqrt((top + 1) << s) > sqrt(a)
+    for (size_t i = 0; i < s / 2; ++i) shl1_or(x, false);
     for (;;) {
         Big qd, rd;
         divmod(a, x, qd, rd);
@@ -256,6 +278,7 @@ struct Dec {
     Dec(uint64_t v, unsigned e_) : n(v), e(e_) { norm(); }
     void norm() {
         while (e > 0 && !n.zero()) {
+            if (n.d[0] & 1u) break;            // odd: not a multiple of 10
             Big t = n;
             if (divmod_small(t, 10) != 0) break;
             n = t;
@@ -378,8 +401,22 @@ static std::string text(const Dec &a) {
     return (a.neg ? "-" : "") + s;
 }
 static double to_number(const Dec &a) {
-    std::string s = (a.neg ? "-" : "") + to_string(a.n) + "e-" + std::to_string(a.e);
-    return strtod(s.c_str(), nullptr);   // glibc strtod is correctly rounded
+    // digits into a stack buffer, then glibc strtod (correctly rounded)
+    char buf[Limbs::CAP * 10 + 32];
+    char *end = buf + sizeof(buf) - 16, *p = end;
+    Big t = a.n;
+    if (t.zero()) *--p = '0';
+    while (!t.zero()) {
+        uint32_t rem = divmod_small(t, 1000000000u);
+        for (int i = 0; i < 9; ++i) {
+            *--p = (char)('0' + rem % 10);
+            rem /= 10;
+            if (t.zero() && rem == 0) break;
+        }
+    }
+    if (a.neg) *--p = '-';
+    snprintf(end, 16, "e-%u", a.e);
+    return strtod(p, nullptr);
 }
 static bool parse(const char *s, Dec &out) {
     Dec r;

@@ -13,7 +13,7 @@ cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench_ref rc=$?" | tee -a gpurun_out/summary.txt
 cat gpurun_out/bench_ref.json
 if [ "$T" == "0" ] && [ "$B" == "0" ] && [ "${NCU:-1}" == "1" ]; then
-  SHORT="python bench.py --reads 2000000 --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline"
+  SHORT="python bench.py --reads ${READS:-10000000} --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline"
   $SHORT > gpurun_out/plain_short.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $SHORT > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches rc=$?" | tee -a gpurun_out/summary.txt

@@ -319,10 +319,16 @@ def run_b200(args):
 
     def step_e2e():
         if world == 1:
+            t = time.perf_counter()
             c = Counts(PREFIX, K, STEP, ctx=ctx)
-            c.add_host(pinned, final=True).finish()
+            c.add_host(pinned, final=True)
+            t = tick("e2e.add_host", t)
+            c.finish()
+            t = tick("e2e.finish", t)
             keys, lens, cnts = c.export_arrays()                     # the k-mer map, back on the host
+            t = tick("e2e.export", t)
             m = Match(c, tdb)
+            t = tick("e2e.first_match", t)
             rows = []
             try:
                 while True:
@@ -332,8 +338,10 @@ def run_b200(args):
                     rows.append(r)
             except NoHitsError:
                 pass
+            t = tick("e2e.wta_rows", t)
             d2h["bytes"] = keys.nbytes + lens.nbytes + cnts.nbytes + len(rows) * 136
             m.free(); c.free()
+            tick("e2e.free", t)
         else:
             with torch.cuda.stream(stream):
                 dev_in[: w.n_bytes].copy_(pinned, non_blocking=True)
@@ -352,6 +360,11 @@ def run_b200(args):
             dm.free(); owned.free()
 
     step_e2e()
+    if args.trace and rank == 0 and world == 1:
+        trace.clear()
+        step_e2e()
+        print("trace (ms, one end-to-end step):", json.dumps({k: round(v, 3) for k, v in trace.items() if k.startswith("e2e.")}),
+              file=sys.stderr)
     e2e_steps = max(1, args.e2e_steps)
     ms_e2e = timed(step_e2e, e2e_steps)
     e2e_value = bases_per_step * e2e_steps / (ms_e2e * 1e-3) / 1e9

@@ -102,6 +102,8 @@ struct kj_counts {
     uint64_t cap = 0;
     KjIrrTable irr{};
     uint64_t irr_cap = 0;
+    std::vector<uint64_t> tail_counts, tail_ords;   // host side of the special + irregular entries (kj_counts_finish)
+    uint64_t irr_bound = 0;          // upper bound of the side table's entries: last pull + merged since
     KjOverflow ovf{};
     KjCounters *ctr = nullptr;        // device
     KjCounters *h_ctr = nullptr;      // pinned mirror

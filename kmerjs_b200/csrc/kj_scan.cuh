@@ -44,9 +44,10 @@ struct KjCandQueue { uint32_t lanes[KJ_FQCAP]; uint16_t chunk[KJ_FQCAP]; };
 #define KJ_SLOTS 3                                       // stream -> emit hand-over slots
 #define KJ_REC_BLOCK 256u                                // candidate records reserved per emit warp at a time
 // named barriers of the filter kernel (0: __syncthreads, 1: stream warps)
-#define KJ_NB_CTL 2                                      // +0/+1: stream warp 0 -> control warp, alternating
-#define KJ_NB_FULL 4                                     // +slot: control warp -> emit warps
-#define KJ_NB_EMPTY 7                                    // +slot: emit warps -> stream warps
+#define KJ_NB_CTL 2                                      // +(seq mod KJ_SLOTS): stream warp 0 -> control warp
+#define KJ_NB_FULL (KJ_NB_CTL + KJ_SLOTS)                // +slot: control warp -> emit warps
+#define KJ_NB_EMPTY (KJ_NB_FULL + KJ_SLOTS)              // +slot: emit warps -> stream warps
+static_assert(KJ_NB_EMPTY + KJ_SLOTS <= 16, "16 named barriers per CTA");
 
 #define KJ_ST_AGG 1ull
 #define KJ_ST_INC 2ull
@@ -632,8 +633,10 @@ __device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32
 // tile before it is searched.  A tile is converted to code words and its newline aggregate is
 // published BEFORE the current one is finished, so the look-back of the tiles behind it does not
 // wait for this CTA.  Hand-over: KJ_SLOTS slots {KjTileSmem, candidate queue} with a full / empty
-// mbarrier pair each; stream -> control commands alternate between two mbarriers (at most two are
-// outstanding, because the stream warps cannot run further ahead of the emit warps than the slots allow).
+// named barrier pair each.  Stream -> control commands rotate over KJ_SLOTS buffers / barrier ids: a command
+// is known to be consumed only when the slot it handed over comes back free (the stream warps wait for
+// that before they refill the slot), so up to KJ_SLOTS commands can be outstanding -- at the start, before
+// any slot has gone round, and at the end, where the last command is sent without refilling a slot.
 struct KjCtlCmd { uint32_t lb_tile, lb_slot, scan_tile, scan_slot; };
 
 template <int MP, int RC>
@@ -644,7 +647,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ KjCandQueue queue[KJ_SLOTS];                     // chunks with candidate lanes
     __shared__ uint32_t tile_of[KJ_SLOTS];                      // tile in the slot (KJ_NO_TILE: no more work)
     __shared__ uint32_t tile_next;                              // ticket fetched ahead
-    __shared__ KjCtlCmd ctl[2];
+    __shared__ KjCtlCmd ctl[KJ_SLOTS];
     __shared__ __align__(8) uint64_t bar_load[2];               // completion of the two half-tile copies in flight
     KJ_DYN_SMEM(stage);                                         // KJ_STAGE_BYTES: raw bytes of the tile in flight
     const uint32_t tid = threadIdx.x;
@@ -683,7 +686,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
         // ------------------------------------------------------------------ control warp
         uint32_t seq = 0;
         for (;;) {
-            const uint32_t kk = seq & 1u;
+            const uint32_t kk = seq % KJ_SLOTS;
             kj_nbar_sync(KJ_NB_CTL + kk, 32 + KJ_CTHREADS);      // a command from stream warp 0
             ++seq;
             const KjCtlCmd cmd = ctl[kk];
@@ -825,7 +828,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
         }
     };
     auto send_cmd = [&](uint32_t lb_tile, uint32_t lb_slot, uint32_t scan_tile, uint32_t scan_slot) {   // stream warp 0
-        const uint32_t kk = cseq & 1u;
+        const uint32_t kk = cseq % KJ_SLOTS;
         if (st == 0) {
             ctl[kk].lb_tile = lb_tile; ctl[kk].lb_slot = lb_slot;
             ctl[kk].scan_tile = scan_tile; ctl[kk].scan_slot = scan_slot;

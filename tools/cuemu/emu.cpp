@@ -75,7 +75,8 @@ void emu_yield() {
 }
 
 static void spin_guard() {
-    if (++g_idle_spins > 200000000L) {
+    static const long limit = getenv("EMU_SPIN_LIMIT") ? atol(getenv("EMU_SPIN_LIMIT")) : 200000000L;
+    if (++g_idle_spins > limit) {
         fprintf(stderr, "cuemu: deadlock suspected (thread %u of block %u)\n", threadIdx.x, blockIdx.x);
         abort();
     }

@@ -222,15 +222,7 @@ def run_b200(args):
             t = tick("finish", t)
             m = Match(c, tdb)
             t = tick("first_match", t)
-            rows = []
-            try:
-                while True:
-                    r = m.next_row()
-                    if r is None:
-                        break
-                    rows.append(r)
-            except NoHitsError:
-                pass
+            rows, _end = m.all_rows()          # findMatches, the whole generator (kj_wta_all)
             t = tick("wta_rows", t)
             state.update(occ=c.occurrences, uniq=c.size, rows=rows, lines=c.lines, bases=c.bases)
             m.free(); c.free()
@@ -329,15 +321,7 @@ def run_b200(args):
             t = tick("e2e.export", t)
             m = Match(c, tdb)
             t = tick("e2e.first_match", t)
-            rows = []
-            try:
-                while True:
-                    r = m.next_row()
-                    if r is None:
-                        break
-                    rows.append(r)
-            except NoHitsError:
-                pass
+            rows, _end = m.all_rows()
             t = tick("e2e.wta_rows", t)
             d2h["bytes"] = keys.nbytes + lens.nbytes + cnts.nbytes + len(rows) * 136
             m.free(); c.free()
@@ -399,7 +383,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": w.n_bytes * world,
                     "d2h_bytes_per_step": d2h["bytes"], "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "api": "kj_counts_add_buffer(KJ_MEM_HOST, pinned) -> kj_counts_finish -> kj_counts_export -> "
-                           "kj_first_match -> kj_wta_next" if world == 1 else
+                           "kj_first_match -> kj_wta_all" if world == 1 else
                            "pinned H2D -> dist.count_sharded -> DistMatch.rows -> export"},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
             "result": {"unique_kmers": int(state["uniq"]), "occurrences": int(state["occ"]),

@@ -118,6 +118,7 @@ SIGNATURES = {
     "kj_match_set_max_hits": (C.c_int, [vp, C.c_uint32]),
     "kj_match_defer_rows": (C.c_int, [vp, C.c_int]),
     "kj_wta_row": (C.c_int, [vp, C.POINTER(kj_row)]),
+    "kj_wta_all": (C.c_int, [vp, C.POINTER(kj_row), C.c_uint32, u32p, C.POINTER(C.c_int)]),
     "kj_match_matched_size": (C.c_int, [vp, u64p, u64p]),
     "kj_match_export_matched": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64]),
     "kj_match_from_matched": (C.c_int, [vp, vp, C.c_uint32, u64p, u64p, u64p, u64p, C.c_uint64, C.POINTER(vp)]),

@@ -328,11 +328,8 @@ class DistMatch:
     def rows(self, max_hits: int = 100):
         self.m.set_max_hits(max_hits)
         if self.mode == "gather":
-            while True:
-                row = self.m.next_row()
-                if row is None:
-                    return
-                yield row
+            yield from self.m.rows(max_hits)       # one call: rounds back to back, rows finished by helper threads
+            return
         self.m.defer_rows(True)
         while True:
             state, row = self.m.next_row_begin()

@@ -147,6 +147,28 @@ class Match:
         self.last_row = r
         return row_to_dict(r, self.db) if rc == 1 else None
 
+    def all_rows(self, max_hits: int = 100):
+        """The whole findMatches generator in one call (kj_wta_all): (rows, error) where error is the
+        NoHitsError the generator would have raised after yielding the rows, or None."""
+        self.set_max_hits(max_hits)
+        buf = (_abi.kj_row * max(max_hits, 1))()
+        n, end = C.c_uint32(), C.c_int()
+        _abi.check(self._L.kj_wta_all(self.handle, buf, max(max_hits, 1), C.byref(n), C.byref(end)), self.ctx.handle)
+        rows = [row_to_dict(buf[i], self.db) for i in range(n.value)]
+        err = None
+        if end.value == _abi.KJ_E_NO_HITS:
+            err = NoHitsError("No hits were found! (nHits === 0)")
+        elif end.value == _abi.KJ_E_NO_WINNER:
+            err = NoHitsError("No hits were found! (kmerResults.length === 0)")
+        return rows, err
+
+    def rows(self, max_hits: int = 100):
+        """findMatches as a generator over all_rows(): the rows, then the error the reference throws (if any)."""
+        rows, err = self.all_rows(max_hits)
+        yield from rows
+        if err is not None:
+            raise err
+
     def defer_rows(self, on: bool = True):
         _abi.check(self._L.kj_match_defer_rows(self.handle, 1 if on else 0), self.ctx.handle)
 

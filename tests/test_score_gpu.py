@@ -222,6 +222,47 @@ def test_deferred_rows_equal_immediate_rows():
     m.free(); c.free()
 
 
+@pytest.mark.parametrize("seed,max_hits", [(123, 100), (7, 3), (31, 1)])
+def test_all_rows_equal_the_generator(seed, max_hits):
+    """kj_wta_all (rounds back to back, rows finished by helper threads) against the oracle's generator:
+    same rows, same terminal error, also when maxHits cuts the loop short."""
+    rng = random.Random(seed)
+    keys = [bytes(b"ATGAC") + bytes(rng.choice(b"ACGT") for _ in range(11)) for _ in range(600)]
+    qmap = OrderedDict((k, rng.randint(1, 5)) for k in dict.fromkeys(keys))
+    lists, attrs, summary = synthetic_db(list(qmap.keys()), rng, n_templates=16, decoys=20, share=0.8)
+    tdb = TemplateDB.from_lists(lists, attrs, summary)
+    c = counts_from_map({k.decode(): v for k, v in qmap.items()}, "ATGAC", 16, 1)
+    # the stepwise path on one handle, the one-call path on another
+    m1 = Match(c, tdb)
+    m1.set_max_hits(max_hits)
+    step_rows, step_err = [], None
+    try:
+        while True:
+            r = m1.next_row()
+            if r is None:
+                break
+            step_rows.append(r)
+    except NoHitsError as exc:
+        step_err = str(exc)
+    m1.free(); c.free()
+    c = counts_from_map({k.decode(): v for k, v in qmap.items()}, "ATGAC", 16, 1)
+    m2 = Match(c, tdb)
+    rows, err = m2.all_rows(max_hits)
+    assert rows == step_rows and (str(err) if err else None) == step_err
+    assert len(rows) <= max_hits
+    if max_hits == 100:
+        _, _, e_rows, e_err, _ = oracle_rows(qmap, lists, attrs, summary)
+        check_rows(rows, e_rows)
+        assert (str(err) if err else None) == e_err
+    with pytest.raises(_abi.KjError):       # a row buffer smaller than maxHits is refused
+        m2.set_max_hits(100)
+        buf = (_abi.kj_row * 2)()
+        import ctypes as C
+        n, end = C.c_uint32(), C.c_int()
+        _abi.check(_abi.lib().kj_wta_all(m2.handle, buf, 2, C.byref(n), C.byref(end)), m2.ctx.handle)
+    m2.free(); c.free()
+
+
 def test_standard_scoring():
     golden = json.loads(read_golden("test_long.json"))          # 6045-key sorted subset of the golden map
     qmap = OrderedDict((k.encode("latin-1"), v) for k, v in golden.items())

@@ -248,8 +248,7 @@ int kj_wta_next(kj_match *m, kj_row *out);
  * kj_wta_row, which finishes the row in exact-decimal arithmetic while the GPU works. */
 int kj_match_defer_rows(kj_match *m, int on);
 int kj_wta_row(kj_match *m, kj_row *out);
-/* The whole generator in one call: the rounds run back to back on the device while helper threads finish the
- * exact-decimal rows.  rows: capacity cap (>= maxHits); *n_rows rows were yielded; *end_status = 0 (normal end)
+/* The whole generator in one call (no trip through the host language per row).  rows: capacity cap (>= maxHits); *n_rows rows were yielded; *end_status = 0 (normal end)
  * or the KJ_E_NO_HITS / KJ_E_NO_WINNER the generator throws after them (text in kj_last_error). */
 int kj_wta_all(kj_match *m, kj_row *rows, uint32_t cap, uint32_t *n_rows, int *end_status);
 /* Gathered matches (multi-GPU): instead of a collective per winner-takes-all round, every rank exports the

@@ -17,8 +17,6 @@
 #include <cstring>
 #include <unordered_map>
 #include "kj_internal.hpp"
-#include <atomic>
-#include <thread>
 #include "kj_stats.hpp"
 
 #define KJ_NONE32 0xFFFFFFFFu
@@ -1117,81 +1115,33 @@ extern "C" int kj_wta_row(kj_match *m, kj_row *out) {
     return 1;
 }
 
-// The whole findMatches loop in one call.  The rounds run back to back on the device (the gate of a round is
-// taken from the double-precision evaluation of kj_argmax_kernel whenever it is away from every threshold,
-// exactly as in kj_wta_next), and the exact-decimal rows -- 15-25 us of host arithmetic each, more than a
-// round takes on the GPU -- are finished by two helper threads while the loop goes on.  rows[0 .. *n_rows) are
-// the rows the generator would have yielded; *end_status is 0 when it would have returned normally, or the
-// KJ_E_NO_HITS / KJ_E_NO_WINNER it would have thrown after them (text in kj_last_error).
+// The whole findMatches loop in one call: kj_wta_next until it ends, without a trip through the host
+// language per row.  Each round's exact-decimal row is finished while the device removes the winner's k-mers
+// and takes the next argmax (kj_wta_next launches both before it starts the arithmetic).  rows[0 .. *n_rows)
+// are the rows the generator would have yielded; *end_status is 0 when it would have returned normally, or
+// the KJ_E_NO_HITS / KJ_E_NO_WINNER it would have thrown after them (text in kj_last_error).
+// (Helper threads for the rows were tried and measured slower: starting them costs more than the ~20 us per
+// round the dependent chain argmax -> copy -> host -> removal takes anyway.)
 extern "C" int kj_wta_all(kj_match *m, kj_row *rows, uint32_t cap, uint32_t *n_rows, int *end_status) {
     if (!m || !rows || !n_rows || !end_status) return KJ_E_INVALID;
     kj_ctx *ctx = m->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (!m->committed) return kj_fail(ctx, KJ_E_STATE, "kj_match_commit has not run");
     if (cap < m->max_hits) return kj_fail(ctx, KJ_E_RANGE, "row buffer smaller than maxHits");
-    struct Job { KjWtaResult r; int accepted; bool ok, deferred; };
-    std::vector<Job> jobs(cap);
-    std::atomic<uint32_t> published{0}, taken{0};
-    std::atomic<bool> closed{false};
-    const int rm = ctx->rounding_mode;
-    auto finish_job = [&](uint32_t i) {
-        Job &j = jobs[i];
-        const uint32_t w = j.r.winner;
-        memset(&rows[i], 0, sizeof(kj_row));
-        j.ok = kj_exact_row(rm, j.r.u, j.r.tau, m->u0[w], m->t0[w], m->db->lengths[w], m->db->ulengths[w], j.r.hits,
-                            m->kmer_map_size, m->db->s_templates, m->db->s_unique_lens, &rows[i], &j.accepted);
-        rows[i].template_id = w;
-        rows[i].z_device = j.r.z;
-        rows[i].probability_device = j.r.p;
-    };
-    auto worker = [&]() {
-        for (;;) {
-            const uint32_t i = taken.load(std::memory_order_relaxed);
-            if (i < published.load(std::memory_order_acquire)) {
-                uint32_t want = i;
-                if (!taken.compare_exchange_weak(want, i + 1, std::memory_order_acq_rel)) continue;
-                if (jobs[i].deferred) finish_job(i);
-            } else if (closed.load(std::memory_order_acquire) && i >= published.load(std::memory_order_acquire)) {
-                return;
-            } else {
-                std::this_thread::yield();
-            }
-        }
-    };
     const bool was_deferring = m->defer_rows;
-    m->defer_rows = true;
-    std::thread helpers[2];
-    for (auto &t : helpers) t = std::thread(worker);
+    m->defer_rows = false;
     uint32_t n = 0;
     int status = 0, hard = KJ_OK;
-    while (n < cap) {
+    for (;;) {
         kj_row tmp;
         const int rc = kj_wta_next(m, &tmp);
-        if (rc == 2) {                          // accepted by the device gate, removal launched: row finished by a helper
-            jobs[n].r = m->pending;
-            jobs[n].deferred = true;
-            m->row_pending = false;
-        } else if (rc == 1) {                   // near a threshold: finished (and decided) in exact arithmetic already
-            rows[n] = tmp;
-            jobs[n].deferred = false; jobs[n].ok = true; jobs[n].accepted = 1;
-        } else {
-            if (rc == KJ_E_NO_HITS || rc == KJ_E_NO_WINNER) status = rc;
-            else if (rc < 0) hard = rc;
-            break;
-        }
-        ++n;
-        published.store(n, std::memory_order_release);
+        if (rc == 1 && n < cap) { rows[n++] = tmp; continue; }
+        if (rc == KJ_E_NO_HITS || rc == KJ_E_NO_WINNER) status = rc;
+        else if (rc != 0) hard = rc < 0 ? rc : KJ_E_STATE;
+        break;
     }
-    closed.store(true, std::memory_order_release);
-    worker();                                   // the calling thread helps with what is left
-    for (auto &t : helpers) t.join();
     m->defer_rows = was_deferring;
     if (hard != KJ_OK) return hard;
-    for (uint32_t i = 0; i < n; ++i) {
-        if (!jobs[i].ok) return kj_fail(ctx, KJ_E_INVALID, "template with zero length / ulength or zero Summary.uniqueLens");
-        if (!jobs[i].accepted)
-            return kj_fail(ctx, KJ_E_CUDA, "internal: device gate and exact-decimal gate disagree away from a threshold");
-    }
     *n_rows = n;
     *end_status = status;
     return KJ_OK;

@@ -328,7 +328,7 @@ class DistMatch:
     def rows(self, max_hits: int = 100):
         self.m.set_max_hits(max_hits)
         if self.mode == "gather":
-            yield from self.m.rows(max_hits)       # one call: rounds back to back, rows finished by helper threads
+            yield from self.m.rows(max_hits)       # the whole loop in one call
             return
         self.m.defer_rows(True)
         while True:

@@ -224,7 +224,7 @@ def test_deferred_rows_equal_immediate_rows():
 
 @pytest.mark.parametrize("seed,max_hits", [(123, 100), (7, 3), (31, 1)])
 def test_all_rows_equal_the_generator(seed, max_hits):
-    """kj_wta_all (rounds back to back, rows finished by helper threads) against the oracle's generator:
+    """kj_wta_all (the whole loop in one call) against the stepwise generator and the oracle:
     same rows, same terminal error, also when maxHits cuts the loop short."""
     rng = random.Random(seed)
     keys = [bytes(b"ATGAC") + bytes(rng.choice(b"ACGT") for _ in range(11)) for _ in range(600)]

@@ -144,10 +144,14 @@ int kj_counts_merge_host_records(kj_counts *c, const void *host_records, uint64_
 uint64_t kj_counts_irregular_size(const kj_counts *c);
 int kj_counts_irregular_export(kj_counts *c, void *host_records);
 int kj_counts_irregular_merge(kj_counts *c, const void *host_records, uint64_t n);
+/* the same, keeping only the records this part owns (owner = hash of the padded key bytes and the length, the
+ * rule kj_owner and kj_db_desc.part/n_parts use for byte-string k-mers): every rank can be handed all records */
+int kj_counts_irregular_merge_part(kj_counts *c, const void *host_records, uint64_t n, uint32_t part, uint32_t n_parts);
 /* totals of the whole job for a handle that holds only the k-mers one rank owns */
 int kj_counts_set_totals(kj_counts *c, uint64_t lines, uint64_t bases, uint64_t occurrences,
                          uint64_t bytes_read);
-/* owner hash of an ASCII k-mer (the same function the device uses) */
+/* owner of a k-mer given as ASCII (the same functions the device uses): full-length ACGT-only k-mers by their
+ * 2-bit key, every other k-mer (N, lower case, ...: the byte-string side table) by a hash of its padded bytes */
 uint32_t kj_owner(const uint8_t *kmer, uint32_t len, uint32_t n_parts);
 
 /* ---------------------------------------------------------------- template database

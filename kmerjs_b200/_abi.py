@@ -93,6 +93,7 @@ SIGNATURES = {
     "kj_counts_irregular_size": (C.c_uint64, [vp]),
     "kj_counts_irregular_export": (C.c_int, [vp, vp]),
     "kj_counts_irregular_merge": (C.c_int, [vp, vp, C.c_uint64]),
+    "kj_counts_irregular_merge_part": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]),
     "kj_counts_set_totals": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "kj_owner": (C.c_uint32, [C.c_char_p, C.c_uint32, C.c_uint32]),
     "kj_db_create": (C.c_int, [vp, C.POINTER(kj_db_desc), C.POINTER(vp)]),

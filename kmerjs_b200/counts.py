@@ -138,11 +138,13 @@ class Counts:
         _abi.check(self._L.kj_counts_irregular_export(self.handle, _ptr(rec)), self.ctx.handle)
         return rec[:n * 56]
 
-    def merge_irregular(self, records: np.ndarray):
+    def merge_irregular(self, records: np.ndarray, part: int = 0, n_parts: int = 1):
+        """Merge byte-string k-mer records; with n_parts > 1 only those this part owns."""
         n = records.size // 56
         if n:
             records = np.ascontiguousarray(records, dtype=np.uint8)
-            _abi.check(self._L.kj_counts_irregular_merge(self.handle, _ptr(records), n), self.ctx.handle)
+            _abi.check(self._L.kj_counts_irregular_merge_part(self.handle, _ptr(records), n, part, n_parts),
+                       self.ctx.handle)
             self.finished = False
 
     def set_totals(self, lines: int, bases: int, occurrences: int, bytes_read: int):

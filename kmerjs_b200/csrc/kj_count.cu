@@ -128,9 +128,11 @@ __global__ void kj_merge_records_kernel(KjTable t, KjCounters *ctr, const KjReco
             atomicOr(&ctr->error_flags, 0x80000000u);
 }
 
-__global__ void kj_merge_irr_kernel(KjIrrTable t, KjCounters *ctr, const KjIrrRecord *rec, uint64_t n) {
+__global__ void kj_merge_irr_kernel(KjIrrTable t, KjCounters *ctr, const KjIrrRecord *rec, uint64_t n, uint32_t part,
+                                    uint32_t n_parts) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
+        if (n_parts > 1 && kj_owner_bytes(rec[i].key, (uint32_t)rec[i].len, n_parts) != part) continue;   // not ours
         __align__(8) uint8_t key32[32];
         const uint64_t *src = reinterpret_cast<const uint64_t *>(rec[i].key);
         uint64_t *dst = reinterpret_cast<uint64_t *>(key32);
@@ -1147,7 +1149,13 @@ extern "C" int kj_counts_irregular_export(kj_counts *c, void *host_records) {
 }
 
 extern "C" int kj_counts_irregular_merge(kj_counts *c, const void *host_records, uint64_t n) {
+    return kj_counts_irregular_merge_part(c, host_records, n, 0, 1);
+}
+
+extern "C" int kj_counts_irregular_merge_part(kj_counts *c, const void *host_records, uint64_t n, uint32_t part,
+                                              uint32_t n_parts) {
     if (!c) return KJ_E_INVALID;
+    if (n_parts == 0 || part >= n_parts) return kj_fail(c->ctx, KJ_E_INVALID, "part / n_parts");
     kj_ctx *ctx = c->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (!n) return KJ_OK;
@@ -1160,7 +1168,7 @@ extern "C" int kj_counts_irregular_merge(kj_counts *c, const void *host_records,
     KJ_CUDA(ctx, kj_dmalloc(ctx, &d, n * sizeof(KjIrrRecord)));
     cudaError_t e = cudaMemcpyAsync(d, host_records, n * sizeof(KjIrrRecord), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
-        KJ_LAUNCH(kj_merge_irr_kernel, grid_for(ctx, n), 256, 0, ctx->stream, c->irr, c->ctr, d, n);
+        KJ_LAUNCH(kj_merge_irr_kernel, grid_for(ctx, n), 256, 0, ctx->stream, c->irr, c->ctr, d, n, part, n_parts);
         ctx->launches++;
         e = cudaGetLastError();
     }
@@ -1219,7 +1227,12 @@ static bool ascii_regular(const uint8_t *kmer, uint32_t len) {
 
 extern "C" uint32_t kj_owner(const uint8_t *kmer, uint32_t len, uint32_t n_parts) {
     if (!kmer || !n_parts) return 0;
-    if (!ascii_regular(kmer, len)) return 0;       // irregular k-mers are gathered on part 0
+    if (!ascii_regular(kmer, len)) {               // byte-string (side-table) k-mers: hash of the padded bytes
+        if (len > 32) return 0;
+        uint8_t pad[32] = {0};
+        memcpy(pad, kmer, len);
+        return kj_owner_bytes(pad, len, n_parts);
+    }
     uint64_t key = 0;
     for (uint32_t i = 0; i < len; ++i) key = (key << 2) | kj_code(kmer[i]);
     return kj_owner_key(key, n_parts);

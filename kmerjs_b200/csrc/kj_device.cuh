@@ -148,3 +148,13 @@ static __device__ __noinline__ bool kj_insert_irr(const KjIrrTable &t, KjCounter
 __host__ __device__ __forceinline__ uint32_t kj_owner_key(uint64_t key, uint32_t n_parts) {
     return (uint32_t)((kj_mix64(key ^ 0x9E3779B97F4A7C15ull) >> 32) % n_parts);
 }
+// owner of a byte-string (side-table) k-mer: hash of the zero-padded 32 key bytes and the length
+__host__ __device__ __forceinline__ uint32_t kj_owner_bytes(const uint8_t *key32, uint32_t len, uint32_t n_parts) {
+    uint64_t h = 0x243F6A8885A308D3ull ^ (uint64_t)len;
+    for (int i = 0; i < 4; ++i) {
+        uint64_t w = 0;
+        for (int j = 0; j < 8; ++j) w |= (uint64_t)key32[8 * i + j] << (8 * j);
+        h = kj_mix64(h ^ w);
+    }
+    return (uint32_t)((h >> 32) % n_parts);
+}

@@ -466,7 +466,9 @@ extern "C" int kj_db_create(kj_ctx *ctx, const kj_db_desc *d, kj_db **out) {
         boff += len;
         if (len > 32) { delete db; return kj_fail(ctx, KJ_E_RANGE, "DB k-mer longer than 32 bytes"); }
         const bool regular = db->k && len == db->k && all_acgt(kb, len);
-        const uint32_t owner = regular ? kj_owner_key(pack_key(kb, len), n_parts) : 0;
+        uint8_t pad[32] = {0};
+        memcpy(pad, kb, len);
+        const uint32_t owner = regular ? kj_owner_key(pack_key(kb, len), n_parts) : kj_owner_bytes(pad, len, n_parts);
         if (owner != d->part % n_parts) continue;
         const uint32_t id = next_id;
         if (regular) {

@@ -147,7 +147,7 @@ def exchange_counts(local: Counts, group=None, trace=None) -> Counts:
     tr.mark("x.merge")
     # one small all-gather carries everything the ranks need from each other besides the records: line /
     # base / occurrence / byte totals and -- while they fit _IRR_INLINE bytes, the usual case: k-mers with
-    # N or other non-ACGT bytes are rare -- the irregular records themselves (gathered on rank 0)
+    # N or other non-ACGT bytes are rare -- the irregular records themselves (owned by hash like the rest)
     irr = local.irregular_records()
     head = np.array([irr.size, local.lines, local.bases, local.occurrences, local.bytes_read], dtype=np.int64)
     stage = _pinned_stage(local.ctx.device)
@@ -169,11 +169,11 @@ def exchange_counts(local: Counts, group=None, trace=None) -> Counts:
             mine[:irr.size] = torch.from_numpy(irr.copy()).to(dev)
         parts = torch.empty((world, pad), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(parts, mine, group=group)
-        if rank == 0:
-            host = parts.cpu().numpy()
-            owned.merge_irregular(np.concatenate([host[rr, :sz] for rr, sz in enumerate(sizes_irr)]))
-    elif rank == 0 and max(sizes_irr) > 0:
-        owned.merge_irregular(np.concatenate([host_v[rr, 40:40 + sz] for rr, sz in enumerate(sizes_irr)]))
+        host = parts.cpu().numpy()
+        owned.merge_irregular(np.concatenate([host[rr, :sz] for rr, sz in enumerate(sizes_irr)]), rank, world)
+    elif max(sizes_irr) > 0:
+        # every rank holds all records after the all-gather and keeps the ones it owns
+        owned.merge_irregular(np.concatenate([host_v[rr, 40:40 + sz] for rr, sz in enumerate(sizes_irr)]), rank, world)
     tr.mark("x.irregular")
     owned.finish()
     tr.mark("x.finish_owned")

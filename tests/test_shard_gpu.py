@@ -58,9 +58,8 @@ def sharded_counts(data, world, prefix=b"ATGAC", k=16, step=1, halo=64):
             off = sum(sizes[:o])
             if sizes[o]:
                 oc.merge_records(ptr + 24 * off, sizes[o])
-        if o == 0:
-            for c in locals_:
-                oc.merge_irregular(c.irregular_records())
+        for c in locals_:                     # byte-string k-mers: every owner is shown all, keeps its own
+            oc.merge_irregular(c.irregular_records(), o, world)
         oc.finish()
         owned.append(oc)
     totals = (max(c.lines for c in locals_), sum(c.bases for c in locals_), sum(c.occurrences for c in locals_))

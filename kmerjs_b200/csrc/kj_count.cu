@@ -1158,6 +1158,16 @@ extern "C" int kj_counts_irregular_merge_part(kj_counts *c, const void *host_rec
     if (n_parts == 0 || part >= n_parts) return kj_fail(c->ctx, KJ_E_INVALID, "part / n_parts");
     kj_ctx *ctx = c->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    // the records this part owns are picked on the host: only they cross PCIe and size the table
+    std::vector<KjIrrRecord> mine;
+    if (n_parts > 1) {
+        const KjIrrRecord *all = reinterpret_cast<const KjIrrRecord *>(host_records);
+        for (uint64_t i = 0; i < n; ++i)
+            if (kj_owner_bytes(all[i].key, (uint32_t)all[i].len, n_parts) == part) mine.push_back(all[i]);
+        host_records = mine.data();
+        n = mine.size();
+        n_parts = 1;
+    }
     if (!n) return KJ_OK;
     KJ_CUDA(ctx, cudaSetDevice(ctx->device));
     // no round trip for the current size: every scan ends with the counters pulled, merges add at most n

@@ -461,7 +461,8 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
     if (c->use_filter) {
         // part B of the candidates: one thread per record, the whole GPU at once
         if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
-        KJ_LAUNCH(kj_verify_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);
+        if (c->k <= 16) KJ_LAUNCH((kj_verify_kernel<4>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
+        else KJ_LAUNCH((kj_verify_kernel<8>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
     }
     if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches++;

@@ -492,23 +492,27 @@ __device__ __forceinline__ void kj_window_load(const KjScanArgs &a, uint64_t j, 
 }
 
 // Part B: the window at buffer offset j, its chunks already loaded.  Straight-line SIMD-in-register code.
+// KW = 4-byte words of the window the code looks at: 8 covers every k <= 32; 4 (k <= 16, the KmerFinder
+// default) halves the work and never needs the third chunk (offset in the chunk + k <= 31).
+template <int KW = 8>
 __device__ __forceinline__ void kj_window_emit(const KjScanArgs &a, uint64_t j, uint32_t strand, uint64_t ord,
                                                const uint4 v0, const uint4 v1, const uint4 v2, uint32_t &n_emit) {
+    static_assert(KW == 4 || KW == 8, "window words");
     const uint32_t k = a.k;
     const uint32_t o = (uint32_t)(j & 15u);
     // window bytes 0..31 in X[0..7]: shift the 48 loaded bytes down by o
     const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
     const uint32_t q = o >> 2, r8 = (o & 3u) * 8u;
-    uint32_t X[8];
+    uint32_t X[KW];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < KW; ++i) {
         const uint32_t lo = q == 0 ? W[i] : q == 1 ? W[i + 1] : q == 2 ? W[i + 2] : W[i + 3];
         const uint32_t hi = q == 0 ? W[i + 1] : q == 1 ? W[i + 2] : q == 2 ? W[i + 3] : W[i + 4];
         X[i] = kj_funnel_r(lo, hi, r8);
     }
     uint32_t bad = 0, nl = 0, irr = 0, p_lo = 0, p_hi = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < KW; ++i) {
         if (4u * i < k) {
             const uint32_t bm = (4u * i + 4u <= k) ? 0xFFFFFFFFu : ((1u << (8u * (k - 4u * i))) - 1u);   // bytes of the window
             bad |= (X[i] ^ a.want[strand][i]) & a.wmask[strand][i];
@@ -550,6 +554,7 @@ static __device__ __noinline__ void kj_verify_candidate(const KjScanArgs &a, con
 }
 
 // Part B over the records of one launch.
+template <int KW>
 __global__ void __launch_bounds__(256) kj_verify_kernel(const __grid_constant__ KjScanArgs a) {
     const unsigned long long n_res = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;   // slots handed out
     uint32_t n_emit = 0;
@@ -561,14 +566,15 @@ __global__ void __launch_bounds__(256) kj_verify_kernel(const __grid_constant__ 
         const uint4 *rp = reinterpret_cast<const uint4 *>(a.cand + KJ_REC_WORDS * i);
         const uint4 *rq = reinterpret_cast<const uint4 *>(a.cand + KJ_REC_WORDS * (i2 < n_res ? i2 : i));
         const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(rp);
-        const uint4 v0 = rp[1], v1 = rp[2], v2 = rp[3];    // the window's chunks travel in the record
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        const uint4 v0 = rp[1], v1 = rp[2], v2 = KW > 4 ? rp[3] : zero;    // the window's chunks travel in the record
         ulonglong2 r2 = *reinterpret_cast<const ulonglong2 *>(rq);
-        const uint4 w0 = rq[1], w1 = rq[2], w2 = rq[3];
+        const uint4 w0 = rq[1], w1 = rq[2], w2 = KW > 4 ? rq[3] : zero;
         if (i2 >= n_res) r2.x = KJ_REC_NONE;
         if (r.x != KJ_REC_NONE)                            // KJ_REC_NONE: unused tail of a reserved block
-            kj_window_emit(a, r.x & ~KJ_REC_STRAND, (uint32_t)(r.x >> 63), r.y, v0, v1, v2, n_emit);
+            kj_window_emit<KW>(a, r.x & ~KJ_REC_STRAND, (uint32_t)(r.x >> 63), r.y, v0, v1, v2, n_emit);
         if (r2.x != KJ_REC_NONE)
-            kj_window_emit(a, r2.x & ~KJ_REC_STRAND, (uint32_t)(r2.x >> 63), r2.y, w0, w1, w2, n_emit);
+            kj_window_emit<KW>(a, r2.x & ~KJ_REC_STRAND, (uint32_t)(r2.x >> 63), r2.y, w0, w1, w2, n_emit);
     }
     for (int d = 16; d > 0; d >>= 1) n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
     if ((threadIdx.x & 31) == 0 && n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);
@@ -760,7 +766,8 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                             kj_window_load(a, rec & ~KJ_REC_STRAND, v0, v1, v2);
                             uint4 *rp = reinterpret_cast<uint4 *>(a.cand + KJ_REC_WORDS * at);
                             *reinterpret_cast<ulonglong2 *>(rp) = make_ulonglong2(rec, ord);
-                            rp[1] = v0; rp[2] = v1; rp[3] = v2;
+                            rp[1] = v0; rp[2] = v1;
+                            if (a.k > 16) rp[3] = v2;            // windows of <= 16 bytes never reach a third chunk
                         }
                         blk_used += need;
                     } else if (keep) {

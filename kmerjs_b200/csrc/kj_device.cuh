@@ -89,7 +89,10 @@ __device__ __forceinline__ bool kj_insert(const KjTable &t, KjCounters *ctr, uin
         if (cur == key) {
             // results unused: both become fire-and-forget reductions (RED), nothing waits on them
             atomicAdd((unsigned long long *)&t.counts[slot], (unsigned long long)add);
-            if (t.ords) atomicMin((unsigned long long *)&t.ords[slot], (unsigned long long)ord);
+            // the stream is read in order, so after a key's first occurrences its stored ordinal is already the
+            // smaller one: a plain read filters most of the 64-bit atomics out
+            if (t.ords && kj_ld_volatile(&t.ords[slot]) > ord)
+                atomicMin((unsigned long long *)&t.ords[slot], (unsigned long long)ord);
             return true;
         }
         slot = (slot + 1) & t.mask;

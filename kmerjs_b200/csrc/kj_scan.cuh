@@ -766,8 +766,7 @@ kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
                             kj_window_load(a, rec & ~KJ_REC_STRAND, v0, v1, v2);
                             uint4 *rp = reinterpret_cast<uint4 *>(a.cand + KJ_REC_WORDS * at);
                             *reinterpret_cast<ulonglong2 *>(rp) = make_ulonglong2(rec, ord);
-                            rp[1] = v0; rp[2] = v1;
-                            if (a.k > 16) rp[3] = v2;            // windows of <= 16 bytes never reach a third chunk
+                            rp[1] = v0; rp[2] = v1; rp[3] = v2;  // the whole 64-byte record: a partial sector write costs a DRAM read
                         }
                         blk_used += need;
                     } else if (keep) {

@@ -2,6 +2,7 @@
 compute is called), and the host logic around it (DB loaders, range planning, JSON helpers)."""
 import json
 import os
+import random
 import re
 
 import numpy as np
@@ -133,3 +134,42 @@ def test_plan_ranges_and_phase():
     # a range without any newline passes the column on
     bl, bc = kdist.phase_of_ranges([1, 0, 2], [5, 0, 9], [10, 7, 20])
     assert bl == [0, 1, 1] and bc == [0, 5, 12]
+
+
+def test_owner_function_matches_its_restatement():
+    """kj_owner (host-side; the device uses the same two functions): full-length ACGT k-mers by their 2-bit
+    key, byte-string k-mers (N, lower case, ...) by the padded bytes and the length.  Restated here so that a
+    change of either hash is a visible change of the exchange format."""
+    M = (1 << 64) - 1
+
+    def mix64(x):
+        x ^= x >> 30; x = (x * 0xBF58476D1CE4E5B9) & M
+        x ^= x >> 27; x = (x * 0x94D049BB133111EB) & M
+        x ^= x >> 31
+        return x
+
+    def owner(kmer: bytes, n_parts: int) -> int:
+        if all(b in b"ACGT" for b in kmer) and 1 <= len(kmer) <= 32:
+            key = 0
+            for b in kmer:
+                key = (key << 2) | ((b >> 1) & 3)
+            return (mix64(key ^ 0x9E3779B97F4A7C15) >> 32) % n_parts
+        pad = kmer + bytes(32 - len(kmer))
+        h = 0x243F6A8885A308D3 ^ len(kmer)
+        for i in range(4):
+            h = mix64(h ^ int.from_bytes(pad[8 * i:8 * i + 8], "little"))
+        return (h >> 32) % n_parts
+
+    L = _abi.lib()
+    rng = random.Random(77)
+    seen = set()
+    for _ in range(400):
+        n = rng.choice([1, 5, 16, 31, 32])
+        alphabet = rng.choice([b"ACGT", b"ACGTN", b"ACGTacgtN-"])
+        kmer = bytes(rng.choice(alphabet) for _ in range(n))
+        for parts in (1, 2, 3, 8):
+            got = L.kj_owner(kmer, len(kmer), parts)
+            assert got == owner(kmer, parts), (kmer, parts)
+            assert 0 <= got < parts
+        seen.add(L.kj_owner(kmer, len(kmer), 8))
+    assert seen == set(range(8))                       # both kinds of k-mer spread over the parts

@@ -241,7 +241,7 @@ class DistMatch:
     collective's latency.  "auto" picks "gather" up to gather_limit_pairs template-list entries."""
 
     def __init__(self, owned: Counts, db, group=None, torch_stream=None, mode: str = "auto",
-                 gather_limit_pairs: int = 1 << 28):
+                 gather_limit_pairs: int = 1 << 26):
         """torch_stream: the torch.cuda.Stream whose handle the Context was created on.  With it the
         collectives are stream-ordered (no host synchronisation between copy, collective and copy back)."""
         import torch

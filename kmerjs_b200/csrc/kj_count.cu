@@ -695,6 +695,9 @@ extern "C" int kj_counts_add_file(kj_counts *c, const char *path) {
     if (size == 0) rc = kj_counts_add_buffer(c, pin, 0, 0, KJ_MEM_HOST, 1);
     while (lo < size && rc == KJ_OK) {
         uint64_t hi = std::min(size, lo + chunk);
+        // a tail shorter than the 32-byte halo a non-final piece must bring belongs to this piece
+        // (the pinned buffer holds chunk + halo bytes)
+        if (size - hi < 32) hi = size;
         uint64_t rd_end = std::min(size, hi + halo);
         uint64_t got = 0;
         while (got < rd_end - lo) {

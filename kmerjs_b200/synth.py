@@ -128,3 +128,101 @@ def template_db_from_genome(genome: bytes, n_templates: int = 64, prefix: bytes 
     summary = {"templates": n_templates, "uniqueLens": int(sum(ulens)), "totalLen": int(sum(lengths))}
     return TemplateDB(kb.reshape(-1), np.full(uk.size, k, dtype=np.uint32), new_off, tm, names,
                       np.array(lengths, dtype=np.uint64), np.array(ulens, dtype=np.uint64), species, summary)
+
+
+def genus_template_db(sample_keys: np.ndarray, n_templates: int = 10_000, per_template: int = 10_000,
+                      genus_size: int = 20, identity: float = 0.7, overlap: float = 0.4,
+                      prefix: bytes = b"ATGAC", k: int = 16, seed: int = 11, relabel: bool = True):
+    """BASELINE config 4's database: ``n_templates`` templates of about ``per_template``
+    prefix-filtered k-mers each, in genera of ``genus_size`` templates that share a k-mer pool (a template
+    holds each k-mer of its genus pool with probability ``identity``, so two templates of a genus are
+    about ``identity`` alike); neighbouring genera overlap in a fraction ``overlap`` of their pools, so
+    k-mer lists mix genera.  Template 0 holds exactly ``sample_keys`` (2-bit packed keys, first base most
+    significant: the sample genome's own k-mers) and its genus the relatives of the sample.  Built in k-mer
+    space, deterministic in ``seed``.  ``relabel`` permutes the template ids so that list order (ascending
+    original id) is unrelated to the id.  Returns a TemplateDB."""
+    from .db import TemplateDB
+    rng = np.random.default_rng(seed)
+    m = len(prefix)
+    code = {65: 0, 67: 1, 84: 2, 71: 3}
+    pk = 0
+    for b in prefix:
+        pk = (pk << 2) | code[b]
+    sample_keys = np.unique(np.asarray(sample_keys, dtype=np.uint64))
+    n_genera = (n_templates + genus_size - 1) // genus_size
+    pool = max(int(round(per_template / identity)), int(sample_keys.size), 1)
+    stride = max(1, int(round(pool * (1.0 - overlap))))
+    sfx_bits = 2 * (k - m)
+    space = 1 << sfx_bits if sfx_bits < 62 else None
+    if space is not None and n_genera > 1 and stride * (n_genera - 1) + pool > space:
+        stride = max(1, (space - pool) // (n_genera - 1))           # the k-mer space is small: genera overlap more
+    n_pos = stride * (n_genera - 1) + pool                       # k-mers of the DB, in "position" order
+    # position -> key: the sample's k-mers first, then distinct random keys with the prefix
+    need = n_pos - sample_keys.size
+    if space is not None and space <= (1 << 26):
+        if need > space - sample_keys.size:
+            raise ValueError("the k-mer space is smaller than the database asked for")
+        allk = (np.uint64(pk) << np.uint64(sfx_bits)) | rng.permutation(space).astype(np.uint64)
+        rest = allk[~np.isin(allk, sample_keys)][:need]
+    else:
+        rest = np.zeros(0, dtype=np.uint64)
+        while rest.size < need:
+            cand = rng.integers(0, 1 << min(sfx_bits, 62), size=2 * (need - rest.size) + 16, dtype=np.uint64)
+            cand = (np.uint64(pk) << np.uint64(sfx_bits)) | cand
+            cand = cand[~np.isin(cand, sample_keys)]
+            rest = np.unique(np.concatenate([rest, cand]))
+        rest = rng.permutation(rest)[:need]
+    keys = np.concatenate([sample_keys, rest])
+    # per genus: membership matrix [template in genus, pool column]; column j of genus g is position g*stride + j
+    col_cnt = np.zeros((n_genera, pool), dtype=np.uint32)
+    members = []
+    per_t = np.zeros(n_templates, dtype=np.uint64)
+    for g in range(n_genera):
+        gs = min(genus_size, n_templates - g * genus_size)
+        M = rng.random((gs, pool)) < identity
+        if g == 0:
+            M[0, :] = np.arange(pool) < sample_keys.size           # the sample genome itself
+        cols, ts = np.nonzero(M.T)                                 # sorted by column, then template
+        members.append((cols.astype(np.int64), (ts + g * genus_size).astype(np.uint32)))
+        col_cnt[g] = M.sum(axis=0)
+        per_t[g * genus_size:g * genus_size + gs] = M.sum(axis=1)
+    # list length of every position = its column in the genus that starts at or before it + columns of
+    # earlier genera that still reach it
+    reach = (pool + stride - 1) // stride                          # genera covering one position (at most)
+    cnt = np.zeros(n_pos, dtype=np.uint64)
+    for g in range(n_genera):
+        cnt[g * stride:g * stride + pool] += col_cnt[g]
+    list_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+    tmpl = np.zeros(int(list_off[-1]), dtype=np.uint32)
+    fill = np.zeros(n_pos, dtype=np.uint64)                        # entries already written per position
+    for g in range(n_genera):                                      # ascending genus = ascending template id
+        cols, ts = members[g]
+        if cols.size == 0:
+            continue
+        pos = cols + g * stride
+        first = np.concatenate([[0], np.nonzero(np.diff(cols))[0] + 1])
+        start_of = np.repeat(first, np.diff(np.concatenate([first, [cols.size]])))
+        rank = np.arange(cols.size) - start_of                     # rank inside the column
+        tmpl[(list_off[pos] + fill[pos] + rank.astype(np.uint64)).astype(np.int64)] = ts
+        fill[g * stride:g * stride + pool] += col_cnt[g]
+    del members, reach
+    if relabel:
+        perm = rng.permutation(n_templates).astype(np.uint32)
+        perm[perm == 0], perm[0] = perm[0], 0                      # the sample genome stays template 0
+        tmpl = perm[tmpl]
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(n_templates, dtype=np.uint32)
+        per_t = per_t[inv]
+    letters = np.array([65, 67, 84, 71], dtype=np.uint8)
+    kb = np.zeros((n_pos, k), dtype=np.uint8)
+    for i in range(k):
+        kb[:, i] = letters[((keys >> np.uint64(2 * (k - 1 - i))) & np.uint64(3)).astype(np.int64)]
+    ulens = per_t + rng.integers(1, 50, size=n_templates).astype(np.uint64)
+    lengths = np.uint64(1000) + np.uint64(50) * per_t
+    names = [f"SYN_{t:05d}" for t in range(n_templates)]
+    species = ["Synthetic sample genome" if t == 0 else f"synthetic template {t}" for t in range(n_templates)]
+    summary = {"templates": n_templates, "uniqueLens": int(ulens.sum()), "totalLen": int(lengths.sum())}
+    db = TemplateDB(kb.reshape(-1), np.full(n_pos, k, dtype=np.uint32), list_off, tmpl, names, lengths, ulens,
+                    species, summary)
+    db.keys_u64 = keys                                             # position -> 2-bit key (tests)
+    return db

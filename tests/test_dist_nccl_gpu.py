@@ -69,6 +69,18 @@ def _worker(rank, world, port, q):
             except NoHitsError as exc:
                 err = str(exc)
             out["single"] = dict(size=c.size, lines=c.lines, hits=hits, order=order, rows=rows, err=err, counts=counts)
+            # and the CPU oracle over the same reads: map (keys, counts, Map order), first match, rows
+            import sys
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+            import ko as ko_c
+            import kmer_oracle as ko_py
+            from collections import OrderedDict
+            o_counts, o_lines = ko_c.count_fastq(w2.host_bytes(), b"ATGAC", 16, 1)
+            lists, attrs = tdb.to_lists()
+            o_first, o_hits, o_rows, o_err = ko_c.find_matches_fast(OrderedDict(o_counts),
+                                                                     ko_py.TemplateDB(lists, attrs, tdb.summary))
+            out["oracle"] = dict(counts=[(k.decode("latin-1"), v) for k, v in o_counts.items()], lines=o_lines,
+                                 hits=o_hits, order=list(o_first), rows=[dict(r) for r in o_rows], err=o_err)
         q.put((rank, out))
         dist.barrier()
     finally:
@@ -102,3 +114,15 @@ def test_two_ranks_equal_single_gpu():
         assert not (set(res[rank]["sync"]["counts"]) & set(merged))       # every k-mer has one owner
         merged.update(res[rank]["sync"]["counts"])
     assert merged == single["counts"]
+    # the oracle: the merged map of the two ranks key for key, the single-GPU map in Map order, and the rows
+    oracle = res[0]["oracle"]
+    assert merged == dict(oracle["counts"])
+    assert list(single["counts"].items()) == oracle["counts"] and single["lines"] == oracle["lines"]
+    assert (single["hits"], single["order"], single["err"]) == (oracle["hits"], oracle["order"], oracle["err"])
+    assert [r["template"] for r in single["rows"]] == [r["template"] for r in oracle["rows"]]
+    for g, e in zip(single["rows"], oracle["rows"]):
+        for f in e:
+            if f == "probability":
+                assert g[f] == pytest.approx(e[f], rel=1e-9)
+            else:
+                assert g[f] == e[f], (g["template"], f)

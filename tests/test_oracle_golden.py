@@ -144,3 +144,46 @@ def test_wta_oracle_small():
             rows.append(r)
     assert [r["template"] for r in rows] == ["T1", "T2"]
     assert rows[1]["score"] == 1 and rows[1]["total-frac-d"] == 100.0 and rows[1]["frac-d"] == 50.0
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_c_wta_equals_python_oracle(seed):
+    """oracle/kmer_oracle.c ko_wta (integer loop in C, exact-decimal gate + rows in Python) against the
+    readable restatement kmer_oracle.first_match + find_matches: first-encounter order, first scores, hits,
+    every row, the terminating error; seeded DBs with ties, dead templates, maxHits cuts."""
+    from collections import OrderedDict
+    from util import synthetic_db
+    rng = random.Random(400 + seed)
+    n_q = rng.choice([30, 200, 1200])
+    qmap = OrderedDict()
+    while len(qmap) < n_q:
+        qmap[bytes(rng.choice(b"ACGT") for _ in range(16))] = rng.randint(1, 9)
+    lists, attrs, summary = synthetic_db(list(qmap.keys()), rng, n_templates=rng.choice([3, 17, 90]), decoys=50,
+                                         share=rng.choice([0.1, 0.35, 0.9]))
+    if seed == 5:
+        # the query is no richer in any template than the DB as a whole: the gate rejects the first winner
+        summary = dict(summary, uniqueLens=sum(len(lists.get(q, ())) for q in qmap) + 1)
+    for max_hits in (100, 2):
+        db = ko_py.TemplateDB(lists, attrs, summary)
+        exp_rows, exp_err = [], None
+        try:
+            templates, hits = ko_py.first_match(OrderedDict(qmap), db)
+            first = OrderedDict((n, {"uScore": t["uScore"], "tScore": t["tScore"]}) for n, t in templates.items())
+            try:
+                for r in ko_py.find_matches(templates, summary, OrderedDict(qmap), len(qmap), max_hits):
+                    exp_rows.append(r)
+            except RuntimeError as exc:
+                exp_err = str(exc)
+        except RuntimeError as exc:
+            first, hits, exp_err = OrderedDict(), 0, str(exc)
+        g_first, g_hits, g_rows, g_err = ko_c.find_matches_fast(OrderedDict(qmap), db, max_hits)
+        assert g_hits == hits and list(g_first.items()) == list(first.items())
+        assert g_rows == exp_rows and g_err == exp_err, (seed, max_hits)
+
+
+def test_c_wta_no_hits():
+    from collections import OrderedDict
+    db = ko_py.TemplateDB({b"AAAA": ["T1"]}, {"T1": {"lengths": 10, "ulength": 1, "species": "s"}},
+                          {"templates": 1, "uniqueLens": 10, "totalLen": 10})
+    first, hits, rows, err = ko_c.find_matches_fast(OrderedDict([(b"CCCC", 1)]), db)
+    assert (hits, rows, err) == (0, [], "No hits were found!")

@@ -11,7 +11,7 @@ import pytest
 
 import kmer_oracle as ko
 from conftest import read_golden
-from util import random_fastq, synthetic_db
+from util import random_fastq, synthetic_db, emulated as util_emulated
 
 import kmerjs_b200
 from kmerjs_b200 import _abi
@@ -322,3 +322,60 @@ def test_exact_decimal_host_functions():
         finally:
             ko.BNConfig.rounding_mode = 4
             kmerjs_b200.stats.set_rounding_mode(4)
+
+
+@pytest.mark.parametrize("max_hits", [100, 7])
+def test_ten_thousand_templates_vs_oracle(max_hits):
+    """BASELINE config 4's shape at a size the oracle follows in seconds: 10 000 templates in genera that
+    share k-mers, > 1e6 (k-mer, template) pairs, a query that hits 3 000 of them.  T > 8192 takes the
+    global-atomic walk (kj_walk_kernel<ACCUM, false>); the loop is cut by maxHits; uScore ties are decided by
+    first-encounter order.  Oracle: the reference's full recount per round (oracle/kmer_oracle.c ko_wta,
+    pinned to the Python restatement in test_oracle_golden.py) with the exact-decimal gate and rows."""
+    import ko as ko_c
+    from kmerjs_b200 import synth
+    T = 10_000 if not util_emulated() else 600
+    rng = np.random.default_rng(4242)
+    pk = 0b0010110001                                                   # ATGAC
+    sample = (np.uint64(pk) << np.uint64(22)) | rng.integers(0, 1 << 22, 150, dtype=np.uint64)
+    tdb = synth.genus_template_db(sample, T, 135, seed=3)
+    assert T < 10_000 or (tdb.tmpl_ids.size > 1_000_000 and tdb.n_templates > 8192)
+    # the query: 70 % of the k-mers of the first 30 % of the genera (enriched in them, like a sample is in its
+    # relatives) plus k-mers the DB does not hold, in random (Map) order
+    n_db = tdb.n_kmers
+    pick = np.nonzero(rng.random(int(0.3 * n_db)) < 0.7)[0]
+    miss = (np.uint64(pk) << np.uint64(22)) | rng.integers(0, 1 << 22, 5000, dtype=np.uint64)
+    miss = miss[~np.isin(miss, tdb.keys_u64)]
+    qkeys = np.concatenate([tdb.keys_u64[pick], np.unique(miss)])
+    qidx = np.concatenate([pick, np.full(qkeys.size - pick.size, -1)])
+    order = rng.permutation(qkeys.size)
+    qkeys, qidx = qkeys[order], qidx[order]
+    qcount = rng.integers(1, 40, qkeys.size).astype(np.uint64)
+    rec = np.stack([qkeys, qcount, np.arange(qkeys.size, dtype=np.uint64)], axis=1)
+    c = Counts(b"ATGAC", 16, 1)
+    c.merge_host_records(rec)
+    c.finish()
+    assert c.size == qkeys.size
+    # oracle arrays: every query entry with its DB list (DB order)
+    off = tdb.list_off.astype(np.int64)
+    lens = np.where(qidx >= 0, off[np.maximum(qidx, 0) + 1] - off[np.maximum(qidx, 0)], 0)
+    qoff = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    starts = np.repeat(off[np.maximum(qidx, 0)], lens)
+    within = np.arange(int(lens.sum())) - np.repeat(qoff[:-1].astype(np.int64), lens)
+    qt = tdb.tmpl_ids[starts + within]
+    attrs = {n: {"lengths": int(tdb.lengths[i]), "ulength": int(tdb.ulengths[i]), "species": tdb.species[i]}
+             for i, n in enumerate(tdb.names)}
+    e_first, e_hits, e_rows, e_err = ko_c.wta_arrays(qcount, qoff, qt, tdb.names, attrs, tdb.summary,
+                                                     int(qkeys.size), max_hits)
+    m = Match(c, tdb)
+    g_first = m.templates()
+    assert m.hits == e_hits == int(lens.sum())
+    assert list(g_first.keys()) == list(e_first.keys())                       # first-encounter order, 10 k templates
+    assert all((g_first[n]["uScore"], g_first[n]["tScore"]) == (e_first[n]["uScore"], e_first[n]["tScore"])
+               for n in e_first)
+    rows, err = m.all_rows(max_hits)
+    assert T < 10_000 or len(e_rows) == max_hits                              # the loop is cut by maxHits
+    check_rows(rows, e_rows)
+    assert (str(err) if err else None) == e_err
+    us = [r["score"] for r in e_rows]
+    assert T < 10_000 or max_hits < 100 or len(set(us)) < len(us)             # ties took part
+    m.free(); c.free()

@@ -1,22 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- Gbases/s of the kmerjs hot path (FASTQ -> k-mer counts + template scores) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c3|c4|c5]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One step = one pass of the whole path over one batch of synthetic reads: count (scan + extract +
-hash count), first match against the template DB resident in HBM, winner-takes-all rows.
-Workload (BASELINE.json configs[2]): 10 M x 150 bp Illumina-shaped reads per GPU, prefix ATGAC,
-k = 16, step = 1, sampled from a 5 Mbp random genome; template DB = that genome, mutated relatives
-and decoys.  With N > 1 every rank takes its own 10 M reads (weak scaling), k-mers travel to
-their owner GPU in one NCCL all-to-all, per-template vectors are all-reduced.
+One step = one pass of the whole path over one batch of synthetic reads: count (scan + extract + hash
+count), first match against the template DB resident in HBM, winner-takes-all rows.
+
+--config (BASELINE.json `configs`):
+  c3 (default; the configuration the metric is quoted on at N = 1)  10 M x 150 bp Illumina-shaped reads per
+      GPU, prefix ATGAC, k = 16, step = 1, sampled from a 5 Mbp genome; DB of 10 000 templates in genera
+      that share k-mers (template 0 = the genome).  N > 1: every rank brings its own 10 M reads (weak).
+  c4  100 M reads in total, split over the ranks (strong), against 10 000 templates / ~1e8 (k-mer, template)
+      pairs, DB sharded by k-mer owner.
+  c5  empty prefix, k = 31: every window is an emission (hash-table bound); 1/10 of BASELINE's size: 100 M reads
+      in total over the ranks, count + owner exchange, no DB.
 
 `value`      device-resident throughput (inputs already in HBM when the timed region starts)
-`e2e`        the same path through the C ABI with HOST buffers: pinned FASTQ bytes in, H2D staging,
-             k-mer map arrays and rows back out, all inside the timed region
-`roofline`   the scan kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-`cpu_baseline` / --impl reference: the CPU restatement of the reference algorithm (oracle/, one
-             thread -- the reference is a single Node.js event loop) on a bounded sample.
+`e2e`        the same path through the C ABI with HOST buffers: pinned FASTQ bytes in, H2D staging, k-mer map
+             arrays and rows back out, all inside the timed region; `e2e.file` is the entry point a user calls,
+             kmerjs(path, ...) on a tmpfs file (kj_counts_add_file: reader threads, two pinned buffers)
+`roofline`   extraction + count kernels against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+`parity_checked`  outside the timed region: the GPU path on the first reads of the workload against the CPU
+             oracle (map keys, counts, Map order, rows)
+`cpu_baseline` / --impl reference: the CPU restatement of the reference algorithm (oracle/, one thread -- the
+             reference is a single Node.js event loop) on a bounded sample.
 """
 from __future__ import annotations
 
@@ -34,11 +42,17 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Gbases/s FASTQ->k-mer counts+template scores"
 UNIT = "Gbases/s"
-PREFIX, K, STEP = b"ATGAC", 16, 1
-GENOME_LEN = 5_000_000
-N_TEMPLATES = 32
 SEED = 0x6B6D6572
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
+
+CONFIGS = {
+    "c3": dict(name="BASELINE configs[2]", reads_per_gpu=10_000_000, genome_len=5_000_000, prefix=b"ATGAC", k=16,
+               step=1, templates=10_000, per_template=0, scaling="weak", sub_rate=0.005, cpu_reads=1_000_000),
+    "c4": dict(name="BASELINE configs[3]", total_reads=100_000_000, genome_len=5_000_000, prefix=b"ATGAC", k=16,
+               step=1, templates=10_000, per_template=10_000, scaling="strong", sub_rate=0.005, cpu_reads=1_000_000),
+    "c5": dict(name="BASELINE configs[4] at 1/10 scale", total_reads=100_000_000, genome_len=50_000_000, prefix=b"",
+               k=31, step=1, templates=0, per_template=0, scaling="strong", sub_rate=0.001, cpu_reads=50_000),
+}
 
 
 def parse_args():
@@ -47,81 +61,168 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU (150 bp)")
-    ap.add_argument("--cpu-reads", type=int, default=1_000_000, help="reads in the CPU-baseline sample")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--reads", type=int, default=0, help="override: reads per GPU (c3) / in total (c4, c5)")
+    ap.add_argument("--templates", type=int, default=-1, help="override the number of DB templates")
+    ap.add_argument("--cpu-reads", type=int, default=0, help="reads in the CPU-baseline / parity sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-file-leg", action="store_true")
     ap.add_argument("--score-mode", default="auto", choices=["auto", "gather", "reduce"],
                     help="N>1: all-gather the matched set once (gather) or all-reduce the score vector every round (reduce)")
     ap.add_argument("--trace", action="store_true", help="print host-side phase timings of one device step to stderr")
     return ap.parse_args()
 
 
-def workload_config(args, world):
-    return {"workload": f"synthetic {args.reads // 1_000_000 if args.reads >= 1_000_000 else args.reads / 1e6:g}M x 150bp "
-                        f"Illumina-shaped reads per GPU, prefix ATGAC, k=16, step=1 (BASELINE configs[2]); "
-                        f"template DB of {N_TEMPLATES} synthetic templates over a {GENOME_LEN // 1_000_000} Mbp genome",
-            "reads_per_gpu": args.reads, "read_len": 150, "prefix": "ATGAC", "k": K, "step": STEP,
-            "templates": N_TEMPLATES, "l2": "inputs larger than L2 (3.46 GB FASTQ per GPU vs 126 MB)",
-            "sharding": ("whole records per rank; owner all-to-all of counted k-mers; scoring: " +
+def resolve_config(args, world):
+    cfg = dict(CONFIGS[args.config])
+    if cfg["scaling"] == "weak":
+        cfg["reads_per_gpu"] = args.reads or cfg["reads_per_gpu"]
+        cfg["total_reads"] = cfg["reads_per_gpu"] * world
+    else:
+        cfg["total_reads"] = args.reads or cfg["total_reads"]
+        cfg["reads_per_gpu"] = (cfg["total_reads"] + world - 1) // world
+    if args.templates >= 0:
+        cfg["templates"] = args.templates
+    cfg["cpu_reads"] = min(args.cpu_reads or cfg["cpu_reads"], cfg["reads_per_gpu"])
+    return cfg
+
+
+def workload_config(args, cfg, world):
+    reads = cfg["reads_per_gpu"]
+    db = (f"template DB of {cfg['templates']} synthetic templates in genera of 20 sharing k-mers (template 0 = the "
+          f"{cfg['genome_len'] // 1_000_000} Mbp sample genome)" if cfg["templates"] else "no template DB (count + exchange only)")
+    return {"workload": f"synthetic {reads / 1e6:g}M x 150bp Illumina-shaped reads per GPU ({cfg['total_reads'] / 1e6:g}M in total), "
+                        f"prefix {cfg['prefix'].decode() or '(empty)'}, k={cfg['k']}, step={cfg['step']} ({cfg['name']}); {db}",
+            "config": args.config, "reads_per_gpu": reads, "total_reads": cfg["total_reads"], "read_len": 150,
+            "prefix": cfg["prefix"].decode(), "k": cfg["k"], "step": cfg["step"], "templates": cfg["templates"],
+            "l2": f"inputs larger than L2 ({reads * 346 / 1e9:.2f} GB FASTQ per GPU vs 126 MB)",
+            "sharding": ("whole records per rank; owner all-to-all of counted k-mers" + ("; scoring: " +
                          ("per-round all-reduce of the template sums" if args.score_mode == "reduce" else
-                          "one all-gather of the matched entries, winner-takes-all replicated")) if world > 1 else "single GPU"}
+                          "one all-gather of the matched entries, winner-takes-all replicated") if cfg["templates"] else ""))
+            if world > 1 else "single GPU"}
+
+
+# ---------------------------------------------------------------------------------------------- workload pieces
+
+def sample_keys_of(genome, prefix: bytes, k: int):
+    """2-bit keys of the prefix-filtered k-mers of the genome's forward strand (a template's k-mer set)."""
+    import numpy as np
+    g = np.frombuffer(genome, dtype=np.uint8) if not hasattr(genome, "dtype") else genome
+    code = np.zeros(256, dtype=np.uint64)
+    for ch, v in ((65, 0), (67, 1), (84, 2), (71, 3)):
+        code[ch] = v
+    c = code[g]
+    n = c.size - k + 1
+    key = np.zeros(n, dtype=np.uint64)
+    for i in range(k):
+        key = (key << np.uint64(2)) | c[i:i + n]
+    pk = 0
+    for b in prefix:
+        pk = (pk << 2) | int(code[b])
+    sel = (key >> np.uint64(2 * (k - len(prefix)))) == np.uint64(pk)
+    return np.unique(key[sel])
+
+
+def build_db(cfg, genome):
+    from kmerjs_b200 import synth
+    if not cfg["templates"]:
+        return None
+    keys = sample_keys_of(genome, cfg["prefix"], cfg["k"])
+    return synth.genus_template_db(keys, cfg["templates"], cfg["per_template"] or int(keys.size), prefix=cfg["prefix"],
+                                   k=cfg["k"], seed=11)
 
 
 # ---------------------------------------------------------------------------------------------- CPU leg
 
-def cpu_reference_sample(sample: bytes, tdb_lists, attrs, summary, n_reads: int):
-    """Time the CPU restatement (oracle/) on `sample`: C count, Python scoring.  Returns
-    (Gbases/s, seconds, n_unique, n_rows)."""
+def oracle_query_arrays(counts, tdb):
+    """The oracle's k-mer map against the DB as arrays: (qcount, qoff, qt) for oracle/ko.wta_arrays."""
+    import numpy as np
+    k = int(tdb.kmer_len[0])
+    keys = list(counts.keys())
+    qcount = np.fromiter(counts.values(), dtype=np.uint64, count=len(keys))
+    code = np.full(256, 255, dtype=np.uint8)
+    for ch, v in ((65, 0), (67, 1), (84, 2), (71, 3)):
+        code[ch] = v
+    regular = np.array([len(x) == k for x in keys], dtype=bool)
+    raw = np.frombuffer(b"".join(x if len(x) == k else b"N" * k for x in keys), dtype=np.uint8).reshape(-1, k)
+    cs = code[raw]
+    regular &= (cs != 255).all(axis=1)
+    key = np.zeros(len(keys), dtype=np.uint64)
+    for i in range(k):
+        key = (key << np.uint64(2)) | (cs[:, i] & 3).astype(np.uint64)
+    order = np.argsort(tdb.keys_u64)
+    sk = tdb.keys_u64[order]
+    at = np.searchsorted(sk, key)
+    at = np.minimum(at, sk.size - 1)
+    hit = regular & (sk[at] == key)
+    pos = np.where(hit, order[at], 0)
+    off = tdb.list_off.astype(np.int64)
+    lens = np.where(hit, off[pos + 1] - off[pos], 0)
+    qoff = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    starts = np.repeat(off[pos], lens)
+    within = np.arange(int(lens.sum())) - np.repeat(qoff[:-1].astype(np.int64), lens)
+    qt = tdb.tmpl_ids[starts + within] if lens.sum() else np.zeros(1, dtype=np.uint32)
+    return qcount, qoff, qt
+
+
+def cpu_reference_sample(sample, cfg, tdb, n_reads: int):
+    """The CPU restatement (oracle/) on `sample`: C count; scoring = the reference's full recount per round in C
+    with the exact-decimal gate and rows in Python.  Returns (Gbases/s, seconds, counts, rows, error text)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import kmer_oracle as ko_py
     import ko as ko_c
     t0 = time.perf_counter()
-    counts, _ = ko_c.count_fastq(sample, PREFIX, K, STEP)
-    rows = 0
-    try:
-        db = ko_py.TemplateDB(tdb_lists, attrs, summary)
-        templates, _ = ko_py.first_match(counts, db)
-        for _ in ko_py.find_matches(templates, summary, counts, len(counts)):
-            rows += 1
-    except RuntimeError:
-        pass
+    counts, lines = ko_c.count_fastq(sample, cfg["prefix"], cfg["k"], cfg["step"])
+    rows, err = [], None
+    if tdb is not None:
+        qcount, qoff, qt = oracle_query_arrays(counts, tdb)
+        attrs = cpu_reference_sample.attrs.get(id(tdb))
+        if attrs is None:
+            attrs = {n: {"lengths": int(tdb.lengths[i]), "ulength": int(tdb.ulengths[i]), "species": tdb.species[i]}
+                     for i, n in enumerate(tdb.names)}
+            cpu_reference_sample.attrs[id(tdb)] = attrs
+        _first, _hits, rows, err = ko_c.wta_arrays(qcount, qoff, qt, tdb.names, attrs, tdb.summary, len(counts))
     dt = time.perf_counter() - t0
-    return n_reads * 150 / dt / 1e9, dt, len(counts), rows
+    return n_reads * 150 / dt / 1e9, dt, counts, rows, err, lines
+
+
+cpu_reference_sample.attrs = {}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm (restated in oracle/; the reference is
-    JavaScript and there is no Node.js here or on the GPU box) on the host cores, one thread."""
+    """--impl reference: the reference's own CPU algorithm (restated in oracle/; the reference is JavaScript and
+    there is no Node.js here or on the GPU box) on the host cores, one thread.  Nothing of the GPU library is
+    loaded: the sample comes from the numpy restatement of the generator (oracle/synth_ref.py)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    from kmerjs_b200 import synth
-    n_reads = args.cpu_reads
-    # the same generator as the GPU arm; it needs the GPU only to produce the bytes
-    w = synth.Workload(n_reads=n_reads, genome_len=GENOME_LEN, seed=SEED)
-    sample = w.host_bytes()
-    tdb = synth.template_db_from_genome(w.genome_host(), N_TEMPLATES, PREFIX, K)
-    lists, attrs = tdb.to_lists()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import synth_ref
+    cfg = resolve_config(args, 1)
+    n_reads = cfg["cpu_reads"]
+    genome = synth_ref.genome(SEED, cfg["genome_len"])
+    sample = synth_ref.fastq(SEED, n_reads, genome, sub_rate=cfg["sub_rate"])
+    tdb = build_db(cfg, genome)
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_sample(sample[: len(sample) // 8], lists, attrs, tdb.summary, n_reads // 8)
-    vals, secs = [], []
+        cpu_reference_sample(sample[: (n_reads // 8) * 346], cfg, tdb, n_reads // 8)
+    secs = []
     for _ in range(args.steps):
-        v, dt, nuniq, nrows = cpu_reference_sample(sample, lists, attrs, tdb.summary, n_reads)
-        vals.append(v)
+        _v, dt, counts, rows, _err, _lines = cpu_reference_sample(sample, cfg, tdb, n_reads)
         secs.append(dt)
     total = sum(secs)
     value = args.steps * n_reads * 150 / total / 1e9
+    conf = workload_config(args, cfg, 1)
+    conf["sample"] = f"every step counts and scores the first {n_reads} reads of the workload (a rate: comparable with the GPU arm's)"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "impl": "reference",
-            "config": workload_config(args, 1),
+            "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "u8", "data": "synthetic", "impl": "reference",
+            "config": conf,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": f"{n_reads} reads of the same workload per step (C count + Python "
-                                       f"scoring of oracle/; the reference is single-threaded Node.js)"},
+                             "sample": f"{n_reads} reads of the same workload per step (C count + C recount loop + Python "
+                                       f"exact-decimal rows of oracle/; the reference is single-threaded Node.js)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "host_cores": os.cpu_count()}
+            "gpu_launches": 0, "host_cores": os.cpu_count(),
+            "result": {"unique_kmers": len(counts), "rows": len(rows)}}
     print(json.dumps(line), flush=True)
 
 
@@ -198,13 +299,22 @@ def run_b200(args):
     stream = torch.cuda.Stream(device=dev)
     ctx = Context(local_rank, stream=stream.cuda_stream)
 
-    n_reads = args.reads
-    w = synth.Workload(n_reads=n_reads, genome_len=GENOME_LEN, seed=SEED, first_read=rank * n_reads, ctx=ctx)
-    tdb = synth.template_db_from_genome(w.genome_host(), N_TEMPLATES, PREFIX, K)
-    dbh = tdb.device(ctx, rank, world)          # DB resident in HBM before the timed region (the reference's Redis is up)
-    hint = 1 << 20
+    cfg = resolve_config(args, world)
+    PREFIX, K, STEP = cfg["prefix"], cfg["k"], cfg["step"]
+    n_reads = cfg["reads_per_gpu"]
+    first_read = rank * n_reads
+    if cfg["scaling"] == "strong":
+        n_reads = max(0, min(n_reads, cfg["total_reads"] - first_read))
+    w = synth.Workload(n_reads=n_reads, genome_len=cfg["genome_len"], seed=SEED, first_read=first_read,
+                       sub_rate=cfg["sub_rate"], ctx=ctx)
+    genome = w.genome_host()
+    tdb = build_db(cfg, genome)
+    if tdb is not None:
+        tdb.device(ctx, rank, world)            # DB resident in HBM before the timed region (the reference's Redis is up)
+    scoring = tdb is not None
+    # distinct k-mers one GPU meets: error variants dominate (c3: 175 k from 2.6 M occurrences)
+    hint = (1 << 20) * max(1, n_reads // 10_000_000) if PREFIX else 0
     state = {}
-
     trace = {}
 
     def tick(name, t0):
@@ -220,31 +330,38 @@ def run_b200(args):
             t = tick("add_device", t)
             c.finish()
             t = tick("finish", t)
-            m = Match(c, tdb)
-            t = tick("first_match", t)
-            rows, _end = m.all_rows()          # findMatches, the whole generator (kj_wta_all)
-            t = tick("wta_rows", t)
+            rows = []
+            if scoring:
+                m = Match(c, tdb)
+                t = tick("first_match", t)
+                rows, _end = m.all_rows()          # findMatches, the whole generator (kj_wta_all)
+                t = tick("wta_rows", t)
+                m.free()
             state.update(occ=c.occurrences, uniq=c.size, rows=rows, lines=c.lines, bases=c.bases)
-            m.free(); c.free()
+            c.free()
             t = tick("free", t)
         else:
             t = time.perf_counter()
             owned = kdist.count_sharded(w.fastq_ptr, w.n_bytes, w.n_bytes, prefix=PREFIX, k=K, step=STEP, final=True,
-                                        base_line=rank * n_reads * 4, capacity_hint=hint, flags=state.get("flags", 0),
+                                        base_line=first_read * 4, capacity_hint=hint, flags=state.get("flags", 0),
                                         ctx=ctx, trace=state.get("fine_trace"))
             t = tick("count+exchange", t)
-            dm = kdist.DistMatch(owned, tdb, torch_stream=stream, mode=args.score_mode)
-            t = tick("first_match+reduce", t)
             rows = []
-            try:
-                for r in dm.rows():      # the generator may end by throwing (query exhausted): keep what it yielded
-                    rows.append(r)
-            except NoHitsError:
-                pass
-            t = tick("wta_rows", t)
-            state.update(occ=owned.occurrences, uniq=getattr(owned, "global_size", owned.size), rows=rows,
-                         lines=owned.lines, bases=owned.bases)
-            dm.free(); owned.free()
+            if scoring:
+                dm = kdist.DistMatch(owned, tdb, torch_stream=stream, mode=args.score_mode)
+                t = tick("first_match+reduce", t)
+                try:
+                    for r in dm.rows():      # the generator may end by throwing (query exhausted): keep what it yielded
+                        rows.append(r)
+                except NoHitsError:
+                    pass
+                t = tick("wta_rows", t)
+                dm.free()
+            uniq = getattr(owned, "global_size", None)
+            if uniq is None:
+                uniq = kdist.global_size(owned)
+            state.update(occ=owned.occurrences, uniq=uniq, rows=rows, lines=owned.lines, bases=owned.bases)
+            owned.free()
 
     def sync_all():
         if world > 1:
@@ -271,7 +388,8 @@ def run_b200(args):
     # the bases the throughput is quoted on are checked against what the kernel saw
     state["flags"] = _abi.KJ_F_COUNT_BASES
     step_device()
-    assert state["bases"] == n_reads * 150 * world and state["lines"] == 4 * n_reads * world, state
+    total_reads = cfg["total_reads"]
+    assert state["bases"] == total_reads * 150 and state["lines"] == 4 * total_reads, state
     state["flags"] = 0
     for _ in range(max(args.warmup, 3) - 1):
         step_device()
@@ -297,13 +415,13 @@ def run_b200(args):
     scan_ms, scan_n, scan_bytes = ctx.scan_kernel_stats()
     verify_ms = ctx.verify_kernel_ms()
     ctx.enable_timers(False)
-    bases_per_step = n_reads * 150 * world
-    assert state["lines"] == 4 * n_reads * world, state
+    bases_per_step = total_reads * 150
+    assert state["lines"] == 4 * total_reads, state
     value = bases_per_step * args.steps / (ms_total * 1e-3) / 1e9
 
     # ---- end to end through the C ABI with host buffers --------------------------------------
-    pinned = torch.empty(w.n_bytes, dtype=torch.uint8, pin_memory=True)
-    pinned.copy_(w.fastq._t[: w.n_bytes])
+    pinned = torch.empty(max(w.n_bytes, 16), dtype=torch.uint8, pin_memory=True)
+    pinned[: w.n_bytes].copy_(w.fastq._t[: w.n_bytes])
     torch.cuda.synchronize(dev)
     d2h = {"bytes": 0}
     dev_in = torch.empty(w.n_bytes + 64, dtype=torch.uint8, device=dev) if world > 1 else None
@@ -312,94 +430,145 @@ def run_b200(args):
         if world == 1:
             t = time.perf_counter()
             c = Counts(PREFIX, K, STEP, ctx=ctx)
-            c.add_host(pinned, final=True)
+            c.add_host(pinned[: w.n_bytes], final=True)
             t = tick("e2e.add_host", t)
             c.finish()
             t = tick("e2e.finish", t)
             keys, lens, cnts = c.export_arrays()                     # the k-mer map, back on the host
             t = tick("e2e.export", t)
-            m = Match(c, tdb)
-            t = tick("e2e.first_match", t)
-            rows, _end = m.all_rows()
-            t = tick("e2e.wta_rows", t)
+            rows = []
+            if scoring:
+                m = Match(c, tdb)
+                t = tick("e2e.first_match", t)
+                rows, _end = m.all_rows()
+                t = tick("e2e.wta_rows", t)
+                m.free()
             d2h["bytes"] = keys.nbytes + lens.nbytes + cnts.nbytes + len(rows) * 136
-            m.free(); c.free()
+            c.free()
             tick("e2e.free", t)
         else:
             with torch.cuda.stream(stream):
-                dev_in[: w.n_bytes].copy_(pinned, non_blocking=True)
+                dev_in[: w.n_bytes].copy_(pinned[: w.n_bytes], non_blocking=True)
             stream.synchronize()
             owned = kdist.count_sharded(dev_in.data_ptr(), w.n_bytes, w.n_bytes, prefix=PREFIX, k=K, step=STEP,
-                                        final=True, base_line=rank * n_reads * 4, ctx=ctx)
-            dm = kdist.DistMatch(owned, tdb, torch_stream=stream, mode=args.score_mode)
+                                        final=True, base_line=first_read * 4, ctx=ctx)
             rows = []
-            try:
-                for r in dm.rows():
-                    rows.append(r)
-            except NoHitsError:
-                pass
+            if scoring:
+                dm = kdist.DistMatch(owned, tdb, torch_stream=stream, mode=args.score_mode)
+                try:
+                    for r in dm.rows():
+                        rows.append(r)
+                except NoHitsError:
+                    pass
+                dm.free()
             keys, lens, cnts = owned.export_arrays()
             d2h["bytes"] = keys.nbytes + lens.nbytes + cnts.nbytes + len(rows) * 136
-            dm.free(); owned.free()
+            owned.free()
 
-    step_e2e()
-    if args.trace and rank == 0 and world == 1:
-        trace.clear()
+    e2e = None
+    if args.config != "c5":         # c5's map (10^8 .. 10^9 keys) is not exported key by key
         step_e2e()
-        print("trace (ms, one end-to-end step):", json.dumps({k: round(v, 3) for k, v in trace.items() if k.startswith("e2e.")}),
-              file=sys.stderr)
-    e2e_steps = max(1, args.e2e_steps)
-    ms_e2e = timed(step_e2e, e2e_steps)
+        if args.trace and rank == 0 and world == 1:
+            trace.clear()
+            step_e2e()
+            print("trace (ms, one end-to-end step):", json.dumps({k: round(v, 3) for k, v in trace.items() if k.startswith("e2e.")}),
+                  file=sys.stderr)
+        e2e_steps = max(1, args.e2e_steps)
+        ms_e2e = timed(step_e2e, e2e_steps)
+        e2e = {"value": bases_per_step * e2e_steps / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": w.n_bytes * world, "d2h_bytes_per_step": d2h["bytes"], "steps": e2e_steps,
+               "ms_per_step": ms_e2e / e2e_steps,
+               "api": "kj_counts_add_buffer(KJ_MEM_HOST, pinned) -> kj_counts_finish -> kj_counts_export -> "
+                      "kj_first_match -> kj_wta_all" if world == 1 else
+                      "pinned H2D -> dist.count_sharded -> DistMatch.rows -> export"}
+        # the entry point a user calls: kmerjs(path, prefix, k, step) on a file (tmpfs, so the disk is not what is timed)
+        if world == 1 and not args.no_file_leg and os.path.isdir("/dev/shm"):
+            import kmerjs_b200
+            path = f"/dev/shm/kmerjs_b200_bench_{os.getpid()}.fastq"
+            try:
+                free = os.statvfs("/dev/shm")
+                if free.f_bavail * free.f_frsize > w.n_bytes + (1 << 28):
+                    with open(path, "wb") as f:
+                        f.write(memoryview(pinned[: w.n_bytes].numpy()))
+                    kmerjs_b200.kmerjs(path, PREFIX.decode(), K, STEP).result(timeout=600)      # warm-up (page cache, pinned buffers)
+                    torch.cuda.synchronize(dev)
+                    t0 = time.perf_counter()
+                    m = kmerjs_b200.kmerjs(path, PREFIX.decode(), K, STEP).result(timeout=600)
+                    dt = time.perf_counter() - t0
+                    e2e["file"] = {"value": bases_per_step / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3,
+                                   "keys": len(m), "api": "kmerjs(path, prefix, k, step) -> kj_counts_add_file (two pinned "
+                                                          "buffers, reader threads) -> finish -> export -> Map", "timer": "host wall clock"}
+            finally:
+                if os.path.exists(path):
+                    os.unlink(path)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_value = bases_per_step * e2e_steps / (ms_e2e * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (scan: newline phase + extract + count) ----------------
+    # ---- roofline of the dominant kernels (scan + resolve: extraction + count) ----------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
     per_rank_occ = state["occ"] / world
-    per_rank_uniq = state["uniq"] / world
     alg_bytes = scan_bytes / max(scan_n, 1) + 32.0 * per_rank_occ          # F + 32 * N_occ per launch
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     # DRAM bytes per launch from the committed `ncu --set full` capture of this workload (profiles/), scaled to
     # the bytes of this launch when the capture was taken at another size
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.config != "c5":
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_per_input_byte"] * (scan_bytes / max(scan_n, 1))
+    kname = ("kj_scan_dense_kernel (extraction + count)" if not PREFIX else
+             "kj_warp_filter_kernel<5,0> + tile scan + kj_resolve_kernel<4> (extraction + count)")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "kj_scan_filter_kernel<5,0> + kj_verify_kernel (extraction + count)",
-                "kernel_ms": scan_ms, "scan_kernel_ms": scan_ms - verify_ms, "verify_kernel_ms": verify_ms,
+                "traffic": traffic, "kernel": kname,
+                "kernel_ms": scan_ms, "scan_kernel_ms": scan_ms - verify_ms, "resolve_kernel_ms": verify_ms,
                 "launches_averaged": scan_n, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": scan_ms * scan_n / max(ms_total, 1e-9)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, world),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": w.n_bytes * world,
-                    "d2h_bytes_per_step": d2h["bytes"], "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                    "api": "kj_counts_add_buffer(KJ_MEM_HOST, pinned) -> kj_counts_finish -> kj_counts_export -> "
-                           "kj_first_match -> kj_wta_all" if world == 1 else
-                           "pinned H2D -> dist.count_sharded -> DistMatch.rows -> export"},
-            "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+            "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, cfg, world),
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
             "result": {"unique_kmers": int(state["uniq"]), "occurrences": int(state["occ"]),
                        "rows": len(state["rows"]), "winner": state["rows"][0]["template"] if state["rows"] else None},
             "fastq_bytes_per_gpu": w.n_bytes}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
+    # ---- parity at benchmark inputs + CPU baseline beside it (rank 0, N = 1 only) ---------------
     if world == 1 and not args.no_cpu_baseline:
-        n_cpu = min(args.cpu_reads, n_reads)
+        n_cpu = cfg["cpu_reads"]
         sample = w.host_bytes(n_cpu)
-        lists, attrs = tdb.to_lists()
-        v, dt, nuniq, nrows = cpu_reference_sample(sample, lists, attrs, tdb.summary, n_cpu)
+        v, dt, o_counts, o_rows, o_err, o_lines = cpu_reference_sample(sample, cfg, tdb, n_cpu)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
                                 "host_cores": os.cpu_count(),
-                                "sample": f"first {n_cpu} reads of the same workload (C count + Python scoring of "
-                                          f"oracle/, one thread: the reference is a single Node.js event loop)"}
+                                "sample": f"first {n_cpu} reads of the same workload (C count + C recount loop + Python "
+                                          f"exact-decimal rows of oracle/, one thread: the reference is a single Node.js event loop)"}
+        # the same reads through the GPU path, outside every timed region: map (keys, counts, Map order), lines, rows
+        c = Counts(PREFIX, K, STEP, capacity_hint=hint, ctx=ctx)
+        c.add_device(w.fastq_ptr, n_cpu * w.record_bytes, final=True).finish()
+        keys, lens, cnts = c.export_arrays()
+        raw = keys.tobytes()
+        g_items = [(raw[32 * i:32 * i + int(lens[i])], int(cnts[i])) for i in range(len(lens))]
+        assert c.lines == o_lines, (c.lines, o_lines)
+        assert g_items == list(o_counts.items()), "k-mer map differs from the oracle's (keys, counts or Map order)"
+        g_rows, g_err = [], None
+        if scoring:
+            m = Match(c, tdb)
+            g_rows, g_err = m.all_rows()
+            m.free()
+            assert [r["template"] for r in g_rows] == [r["template"] for r in o_rows], "winner order differs from the oracle's"
+            for g, e in zip(g_rows, o_rows):
+                for f in e:
+                    if f == "probability":
+                        assert abs(g[f] - e[f]) <= 1e-9 * abs(e[f]), (g["template"], f)
+                    else:
+                        assert g[f] == e[f], (g["template"], f, g[f], e[f])
+            assert (str(g_err) if g_err else None) == o_err
+        c.free()
+        line["parity_checked"] = {"reads": n_cpu, "keys": len(g_items), "occurrences": int(sum(v for _, v in g_items)),
+                                  "rows": len(g_rows), "against": "oracle/ (bit-exact map and Map order, rows exact, probability 1e-9)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -79,6 +79,9 @@ double kj_scan_kernel_ms(const kj_ctx *ctx, uint64_t *n_launches);
 double kj_verify_kernel_ms(const kj_ctx *ctx);
 /* input bytes those launches owned (the F term of the algorithmic-bytes model) */
 uint64_t kj_scan_kernel_bytes(const kj_ctx *ctx);
+/* size of the chunks in which host buffers and files are staged into device memory (two pinned + two device buffers of
+ * this size per context; default 64 MiB, or KJ_STAGE_CHUNK_MB from the environment at first use) */
+int kj_set_stage_chunk(kj_ctx *ctx, uint64_t bytes);
 void kj_reset_timers(kj_ctx *ctx);
 void kj_enable_timers(kj_ctx *ctx, int on);
 

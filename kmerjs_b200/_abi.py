@@ -73,6 +73,7 @@ SIGNATURES = {
     "kj_verify_kernel_ms": (C.c_double, [vp]),
     "kj_scan_kernel_bytes": (C.c_uint64, [vp]),
     "kj_reset_timers": (None, [vp]),
+    "kj_set_stage_chunk": (C.c_int, [vp, C.c_uint64]),
     "kj_enable_timers": (None, [vp, C.c_int]),
     "kj_counts_create": (C.c_int, [vp, C.POINTER(kj_count_params), C.POINTER(vp)]),
     "kj_counts_add_buffer": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int]),

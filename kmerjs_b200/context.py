@@ -36,6 +36,10 @@ class Context:
     def enable_timers(self, on: bool = True):
         self._L.kj_enable_timers(self.handle, 1 if on else 0)
 
+    def set_stage_chunk(self, nbytes: int):
+        """Size of the host -> device staging chunks of add_host / add_file."""
+        _abi.check(self._L.kj_set_stage_chunk(self.handle, int(nbytes)), self.handle)
+
     def reset_timers(self):
         self._L.kj_reset_timers(self.handle)
 

@@ -1,16 +1,27 @@
 // kj_count.cu -- host side of the extraction + count path (kj_counts_* of include/kmerjs_b200.h)
 // and the small maintenance kernels around the table (rehash, replay, compaction, exchange).
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
+#include <future>
+#include <thread>
 #include <cstring>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include "kj_internal.hpp"
-#include "kj_scan.cuh"
+#include "kj_scan_warp.cuh"
 #ifndef KJ_CPU_EMU
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #endif
+
+// the filter-path piece in flight
+struct KjPiece {
+    KjScanArgs args;
+    KjTensorMap tmap;
+    bool timed = false;
+};
 
 // ------------------------------------------------------------------------------------ kernels
 
@@ -337,64 +348,12 @@ static double expected_emissions(const kj_counts *c, uint64_t bytes) {
     return e;
 }
 
-// One kernel launch over a device-resident piece.  Synchronises, handles spills and growth.
-static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t own_n, int final_) {
-    kj_ctx *ctx = c->ctx;
-    if (own_n == 0) return KJ_OK;
+// kernel arguments of one piece (everything but the table pointers, which are filled in at launch time)
+static KjScanArgs make_args(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t own_n, int final_) {
     const uint32_t m = (uint32_t)c->prefix.size();
-    const uint64_t n_tiles64 = (own_n + KJ_TILE_BYTES - 1) / KJ_TILE_BYTES;
-    if (n_tiles64 > 0xFFFFFFF0ull) return kj_fail(ctx, KJ_E_RANGE, "piece too large");
-    const uint32_t n_tiles = (uint32_t)n_tiles64;
-
-    // table capacity: the caller's hint, else what this piece is expected to add (it grows by
-    // rehash between pieces, and emissions that find no slot are spilled and replayed)
-    const uint64_t hard_bound = 2 * own_n + 16;                 // emissions this launch can produce
-    uint64_t expect = c->use_filter ? (uint64_t)(4.0 * expected_emissions(c, own_n)) + 65536 : hard_bound;
-    expect = std::min(expect, hard_bound);
-    uint64_t known = c->h_ctr->n_unique;
-    uint64_t want = c->capacity_hint ? std::max<uint64_t>(2 * c->capacity_hint, 2 * known)
-                                     : std::min<uint64_t>(2 * (known + expect), std::max<uint64_t>(1ull << 24, 4 * known));
-    int rc = grow_table(c, want);
-    if (rc) return rc;
-    // irregular k-mers (an N in the window, short windows of step > 1): a small share of the emissions
-    // for the filter kernel, potentially all of them for the line kernel
-    rc = grow_irr(c, std::max<uint64_t>(std::max<uint64_t>(1ull << 12, 4 * c->h_ctr->n_irr_unique),
-                                        c->use_filter ? expect / 32 : std::min<uint64_t>(expect, 1ull << 22)));
-    if (rc) return rc;
-    // spill lists: the table is sized for the expected load, so spills are the exception; the line
-    // kernel (every window is an emission) gets the worst case of its 4 MiB pieces
-    rc = ensure_overflow(c, (c->use_filter || c->use_dense) ? std::min<uint64_t>(hard_bound, 1ull << 20) : hard_bound,
-                         c->use_filter ? std::min<uint64_t>(hard_bound, 1ull << 16)
-                                       : (c->use_dense ? std::min<uint64_t>(hard_bound, 1ull << 20) : hard_bound));
-    if (rc) return rc;
-
-    // tile state
-    if (n_tiles > c->tile_cap) {
-        kj_dfree(ctx, c->tile_mem);
-        c->tile_mem = nullptr; c->tile_cap = 0;
-        uint64_t tc = std::max<uint64_t>(n_tiles, 4096);
-        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->tile_mem, tc * 8));
-        c->tile_cap = tc;
-    }
-    KJ_CUDA(ctx, cudaMemsetAsync(c->tile_mem, 0, (uint64_t)n_tiles * 8, ctx->stream));  // status only
-    if (c->use_filter) {
-        // candidate records: code-space matches in sequence lines, about 0.9 * 4^-m of the bytes for
-        // FASTQ of random bases; whatever does not fit is verified in place by the scan kernel
-        uint64_t want_rec = std::min<uint64_t>(hard_bound, (uint64_t)(2.0 * expected_emissions(c, own_n)) + (1ull << 18));
-        want_rec = (want_rec + KJ_REC_BLOCK - 1) / KJ_REC_BLOCK * KJ_REC_BLOCK;
-        if (want_rec > c->cand_cap) {
-            kj_dfree(ctx, c->cand);
-            c->cand = nullptr; c->cand_cap = 0;
-            KJ_CUDA(ctx, kj_dmalloc(ctx, &c->cand, want_rec * 8 * KJ_REC_WORDS));
-            c->cand_cap = want_rec;
-        }
-        KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_cand, 0, sizeof(unsigned long long), ctx->stream));
-    }
-    KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->ticket, 0, sizeof(unsigned int), ctx->stream));
-
     KjScanArgs a{};
     a.buf = dbuf; a.n = n; a.own_n = own_n; a.voff = c->voff;
-    a.n_tiles = n_tiles; a.parity = c->parity; a.final_ = final_ ? 1u : 0u;
+    a.parity = c->parity; a.final_ = final_ ? 1u : 0u;
     a.k = c->k; a.step = c->step; a.m = m; a.order = c->order ? 1u : 0u;
     a.n_strands = (c->flags & KJ_F_FORWARD_ONLY) ? 1u : 2u;
     a.line_gate = (c->flags & KJ_F_NO_LINE_GATE) ? 0u : 1u;
@@ -410,7 +369,7 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
         memcpy(a.prefix, c->prefix.data(), std::min<size_t>(32, m));
         memcpy(a.rprefix, c->rprefix.data(), std::min<size_t>(32, m));
     }
-    {   // byte-exact window check of the filter kernel: wanted bytes and their mask, per strand
+    {   // byte-exact window check of the filter path: wanted bytes and their mask, per strand
         uint8_t want[2][32], mask[2][32];
         memset(want, 0, sizeof(want)); memset(mask, 0, sizeof(mask));
         if (m <= c->k && c->k <= 32) {
@@ -422,65 +381,302 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
         memcpy(a.want, want, sizeof(want));
         memcpy(a.wmask, mask, sizeof(mask));
     }
-    a.tab = c->tab; a.irr = c->irr; a.ovf = c->ovf; a.ctr = c->ctr;
-    a.status = c->tile_mem;
-    a.cand = c->cand;
-    a.cand_cap = c->cand_cap;
+    a.ctr = c->ctr;
+    return a;
+}
 
-    void (*fn)(const KjScanArgs) = c->use_dense ? kj_scan_dense_kernel : kj_scan_lines_kernel;
-    if (c->use_filter) {
-        // where the filter symbols of complement(prefix) sit relative to the window start
-        const uint32_t d_lo = a.rc_shift, d_hi = a.rc_shift + a.mp - 1;
-        const int rc = d_hi < 16 ? KJ_RC_LOW : (d_lo >= 16 ? KJ_RC_HIGH : KJ_RC_MIXED);
+static int account_scan_time(kj_counts *c, uint64_t own_n, bool has_verify) {
+    kj_ctx *ctx = c->ctx;
+    float ms = 0.f;
+    KJ_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->scan_ms += ms;
+    if (has_verify) {
+        float vms = 0.f;
+        KJ_CUDA(ctx, cudaEventElapsedTime(&vms, ctx->ev2, ctx->ev1));
+        ctx->verify_ms += vms;
+    }
+    ctx->scan_launches++;
+    ctx->scan_bytes += own_n;
+    return KJ_OK;
+}
+
+// keep the load factor at or below one half between launches
+static int keep_load_factor(kj_counts *c) {
+    int rc = KJ_OK;
+    if (c->h_ctr->n_unique * 2 > c->cap) rc = grow_table(c, c->cap * 4);
+    if (rc == KJ_OK && c->h_ctr->n_irr_unique * 2 > c->irr_cap) rc = grow_irr(c, c->irr_cap * 4);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------ filter path
+
+#ifndef KJ_CPU_EMU
+typedef CUresult (*KjEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+#endif
+
+// the input as a 2-D tensor of rows of 128 bytes (whole rows only), boxes of 32 rows, 128-byte swizzle
+static int make_tensor_map(kj_ctx *ctx, const uint8_t *dbuf, uint64_t n, KjTensorMap *tm) {
+    const uint64_t rows = n / 128;
+#ifdef KJ_CPU_EMU
+    tm->base = dbuf; tm->rows = rows;
+#else
+    static KjEncodeTiled encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        KJ_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn) return kj_fail(ctx, KJ_E_CUDA, "the driver has no cuTensorMapEncodeTiled");
+        encode = (KjEncodeTiled)fn;
+    }
+    memset(tm, 0, sizeof(*tm));
+    if (rows == 0) return KJ_OK;                       // no whole row: every tile takes the bounds-checked path
+    const cuuint64_t gdim[2] = {128, rows};
+    const cuuint64_t gstr[1] = {128};
+    const cuuint32_t box[2] = {128, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(dbuf), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return kj_fail(ctx, KJ_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+#endif
+    return KJ_OK;
+}
+
+typedef void (*KjFilterFn)(const KjTensorMap, const KjScanArgs);
+static KjFilterFn pick_filter_kernel(const KjScanArgs &a) {
+    // where the filter symbols of complement(prefix) sit relative to the window start
+    const uint32_t d_lo = a.rc_shift, d_hi = a.rc_shift + a.mp - 1;
+    const int rc = d_hi < 16 ? KJ_RC_LOW : (d_lo >= 16 ? KJ_RC_HIGH : KJ_RC_MIXED);
 #define KJ_PICK(MP)                                                                          \
     case MP:                                                                                 \
-        fn = rc == KJ_RC_LOW ? kj_scan_filter_kernel<MP, KJ_RC_LOW>                          \
-                             : rc == KJ_RC_HIGH ? kj_scan_filter_kernel<MP, KJ_RC_HIGH>      \
-                                                : kj_scan_filter_kernel<MP, KJ_RC_MIXED>;    \
-        break;
-        switch (a.mp) {
-            KJ_PICK(1) KJ_PICK(2) KJ_PICK(3) KJ_PICK(4) KJ_PICK(5) KJ_PICK(6) KJ_PICK(7)
-            default: fn = rc == KJ_RC_LOW ? kj_scan_filter_kernel<8, KJ_RC_LOW>
-                                          : rc == KJ_RC_HIGH ? kj_scan_filter_kernel<8, KJ_RC_HIGH>
-                                                             : kj_scan_filter_kernel<8, KJ_RC_MIXED>;
-        }
-#undef KJ_PICK
+        return rc == KJ_RC_LOW ? kj_warp_filter_kernel<MP, KJ_RC_LOW>                        \
+                               : rc == KJ_RC_HIGH ? kj_warp_filter_kernel<MP, KJ_RC_HIGH>    \
+                                                  : kj_warp_filter_kernel<MP, KJ_RC_MIXED>;
+    switch (a.mp) {
+        KJ_PICK(1) KJ_PICK(2) KJ_PICK(3) KJ_PICK(4) KJ_PICK(5) KJ_PICK(6) KJ_PICK(7)
+        default: break;
     }
-    // the filter kernel stages the tile in flight in dynamic shared memory (TMA bulk copy target)
-    const size_t dyn_smem = c->use_filter ? (size_t)KJ_STAGE_BYTES : 0;
-    if (dyn_smem) KJ_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    return rc == KJ_RC_LOW ? kj_warp_filter_kernel<8, KJ_RC_LOW>
+                           : rc == KJ_RC_HIGH ? kj_warp_filter_kernel<8, KJ_RC_HIGH> : kj_warp_filter_kernel<8, KJ_RC_MIXED>;
+#undef KJ_PICK
+}
+
+// scan -> exclusive scan of the tile counts -> resolve, all stream-ordered
+static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only) {
+    kj_ctx *ctx = c->ctx;
+    KjScanArgs &a = pc.args;
+    a.tab = c->tab; a.irr = c->irr; a.ovf = c->ovf;
+    a.cand = c->cand; a.cand_cap = c->cand_cap;
+    a.tile_cnt = c->tile_cnt; a.tile_excl = c->tile_mem;
+    a.resolve_retry = retry_only ? 1u : 0u;
+    // the failure counters of this pass (n_overflow, n_irr_overflow) and, for a full pass, the entry counter
+    KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_overflow, 0, (retry_only ? 2 : 3) * sizeof(unsigned long long), ctx->stream));
+    const bool timed = ctx->timers_on && !retry_only;
+    if (timed) KJ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (!retry_only) {
+        KjFilterFn fn = pick_filter_kernel(a);
+        KJ_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KJ_WT_SMEM_BYTES));
+        int occ = 0;
+        KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KJ_WT_THREADS, KJ_WT_SMEM_BYTES));
+        const uint64_t want_ctas = ((uint64_t)a.n_tiles + KJ_WT_WARPS - 1) / KJ_WT_WARPS;
+        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want_ctas, (uint64_t)ctx->sm_count * std::max(occ, 1)));
+        KJ_LAUNCH(fn, grid, KJ_WT_THREADS, KJ_WT_SMEM_BYTES, ctx->stream, pc.tmap, a);
+        ctx->launches++;
+        if (timed) KJ_CUDA(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+#ifdef KJ_CPU_EMU
+        {
+            uint64_t run = 0;
+            for (uint32_t t = 0; t < a.n_tiles; ++t) { a.tile_excl[t] = run; run += a.tile_cnt[t]; }
+        }
+#else
+        {
+            size_t tmp = c->scan_tmp_bytes;
+            KJ_CUDA(ctx, cub::DeviceScan::ExclusiveSum(c->scan_tmp, tmp, a.tile_cnt, a.tile_excl, (int)a.n_tiles, ctx->stream));
+            ctx->launches += 2;
+        }
+#endif
+    }
+    if (c->k <= 16) KJ_LAUNCH((kj_resolve_kernel<4>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
+    else KJ_LAUNCH((kj_resolve_kernel<8>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
+    ctx->launches++;
+    if (a.count_bases && !retry_only) {
+        KJ_LAUNCH(kj_bases_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);
+        ctx->launches++;
+    }
+    if (timed) KJ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    KJ_CUDA(ctx, cudaGetLastError());
+    pc.timed = timed;
+    return KJ_OK;
+}
+
+// entry buffer and tile arrays for a piece of n_tiles tiles expecting `want_ent` entries
+static int ensure_filter_buffers(kj_counts *c, uint32_t n_tiles, uint64_t want_ent) {
+    kj_ctx *ctx = c->ctx;
+    if (n_tiles > c->tile_cap) {
+        kj_dfree(ctx, c->tile_mem); kj_dfree(ctx, c->tile_cnt); kj_dfree(ctx, c->scan_tmp);
+        c->tile_mem = nullptr; c->tile_cnt = nullptr; c->scan_tmp = nullptr; c->tile_cap = 0;
+        const uint64_t tc = std::max<uint64_t>(n_tiles, 4096);
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->tile_mem, tc * 8));
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->tile_cnt, tc * 8));
+        size_t tmp = 0;
+#ifndef KJ_CPU_EMU
+        KJ_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->tile_cnt, c->tile_mem, (int)tc, ctx->stream));
+#endif
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->scan_tmp, std::max<size_t>(tmp, 16)));
+        c->scan_tmp_bytes = tmp;
+        c->tile_cap = tc;
+    }
+    if (want_ent > c->cand_cap) {
+        kj_dfree(ctx, c->cand);
+        c->cand = nullptr; c->cand_cap = 0;
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->cand, want_ent * 16));
+        c->cand_cap = want_ent;
+    }
+    return KJ_OK;
+}
+
+// Wait for the piece in flight and deal with what the device reports: an entry buffer that was too small (the
+// launch touched nothing: repeat it with a larger one), emissions that found no table slot (grow, run the
+// retry pass over the marked entries), error flags.  Nothing is ever dropped.
+static int settle_filter(kj_counts *c) {
+    kj_ctx *ctx = c->ctx;
+    if (!c->pending) return KJ_OK;
+    KjPiece &pc = *c->piece;
+    int rc = pull_counters(c);
+    if (rc) return rc;
+    if (pc.timed) { rc = account_scan_time(c, pc.args.own_n, true); if (rc) return rc; }
+    for (int round = 0; round < 4 && c->h_ctr->n_cand > c->cand_cap; ++round) {
+        rc = ensure_filter_buffers(c, pc.args.n_tiles, c->h_ctr->n_cand + (c->h_ctr->n_cand >> 3) + 1024);
+        if (rc) return rc;
+        rc = launch_filter(c, pc, false);
+        if (rc) return rc;
+        rc = pull_counters(c);
+        if (rc) return rc;
+    }
+    if (c->h_ctr->n_cand > c->cand_cap) return kj_fail(ctx, KJ_E_CUDA, "internal: candidate entries exceed their own count");
+    rc = check_device_errors(c);
+    if (rc) return rc;
+    for (int round = 0; c->h_ctr->n_overflow; ++round) {
+        if (round >= 40) return kj_fail(ctx, KJ_E_TABLE_FULL, "k-mer table cannot take the emissions of this piece (device memory?)");
+        // entries with lanes left over: the tables are too small or too crowded for them.  Their number bounds the
+        // emissions still to come from below; every round at least doubles both tables.
+        const uint64_t left = c->h_ctr->n_overflow;
+        rc = grow_table(c, std::max<uint64_t>(c->cap * 4, 4 * (c->h_ctr->n_unique + left)));
+        if (rc) return rc;
+        rc = grow_irr(c, std::max<uint64_t>(c->irr_cap * 4, 4 * (c->h_ctr->n_irr_unique + left)));
+        if (rc) return rc;
+        rc = launch_filter(c, pc, true);
+        if (rc) return rc;
+        rc = pull_counters(c);
+        if (rc) return rc;
+        rc = check_device_errors(c);
+        if (rc) return rc;
+    }
+    c->pending = false;
+    return keep_load_factor(c);
+}
+
+// One piece through the filter path.  With a capacity hint on a device-resident buffer the host does not wait:
+// the piece is settled by the next call that needs its results (kj_counts_finish, or another add).
+static int scan_piece_filter(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t own_n, int final_, bool may_defer) {
+    kj_ctx *ctx = c->ctx;
+    int rc = settle_filter(c);                      // one piece in flight per handle
+    if (rc) return rc;
+    const uint32_t m = (uint32_t)c->prefix.size();
+    const uint64_t n_tiles64 = (own_n + KJ_WT_BYTES - 1) / KJ_WT_BYTES;
+    if (n_tiles64 > 0x7FFFFFF0ull / KJ_WT_OWN_ROWS) return kj_fail(ctx, KJ_E_RANGE, "piece too large");
+    // table capacity: the caller's hint, else what this piece is expected to add (it grows by rehash between
+    // pieces; emissions that find no slot wait for the retry pass)
+    const uint64_t hard_bound = 2 * own_n + 16;
+    uint64_t expect = std::min<uint64_t>((uint64_t)(4.0 * expected_emissions(c, own_n)) + 65536, hard_bound);
+    const uint64_t known = c->h_ctr->n_unique;
+    const uint64_t want = c->capacity_hint ? std::max<uint64_t>(2 * c->capacity_hint, 2 * known)
+                                           : std::min<uint64_t>(2 * (known + expect), std::max<uint64_t>(1ull << 24, 4 * known));
+    rc = grow_table(c, want);
+    if (rc) return rc;
+    rc = grow_irr(c, std::max<uint64_t>(std::max<uint64_t>(1ull << 12, 4 * c->h_ctr->n_irr_unique), expect / 32));
+    if (rc) return rc;
+    // entries: one per 16-byte chunk that holds a code-space match, 2 * 16 * 4^-mp of them for random bytes
+    const uint64_t chunks = own_n / 16 + 1;
+    double share = 48.0;
+    for (uint32_t i = 0; i < std::min<uint32_t>(m, KJ_MAX_MP); ++i) share *= 0.25;
+    const uint64_t want_ent = std::min<uint64_t>(chunks, (uint64_t)(std::min(1.0, share) * (double)chunks) + (1ull << 16));
+    rc = ensure_filter_buffers(c, (uint32_t)n_tiles64, want_ent);
+    if (rc) return rc;
+
+    KjPiece &pc = *c->piece;
+    pc.args = make_args(c, dbuf, n, own_n, final_);
+    pc.args.n_tiles = (uint32_t)n_tiles64;
+    const uint64_t rows = n / 128;
+    const uint64_t fast_rows = rows >= 32 ? (rows - 32) / KJ_WT_OWN_ROWS + 1 : 0;       // rows [31 t, 31 t + 32) exist
+    pc.args.n_fast = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(fast_rows, own_n / KJ_WT_BYTES), n_tiles64);
+    rc = make_tensor_map(ctx, dbuf, n, &pc.tmap);
+    if (rc) return rc;
+    rc = launch_filter(c, pc, false);
+    if (rc) return rc;
+    c->pending = true;
+    c->voff += own_n;
+    c->consumed += own_n;
+    c->parity ^= 1u;
+    if (may_defer && c->capacity_hint) return KJ_OK;
+    return settle_filter(c);
+}
+
+// ------------------------------------------------------------------------------------ dense and line kernels
+
+// One kernel launch over a device-resident piece.  Synchronises, handles spills and growth.
+static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t own_n, int final_, bool may_defer) {
+    kj_ctx *ctx = c->ctx;
+    if (own_n == 0) return KJ_OK;
+    if (c->use_filter) return scan_piece_filter(c, dbuf, n, own_n, final_, may_defer);
+    const uint64_t n_tiles64 = (own_n + KJ_TILE_BYTES - 1) / KJ_TILE_BYTES;
+    if (n_tiles64 > 0xFFFFFFF0ull) return kj_fail(ctx, KJ_E_RANGE, "piece too large");
+    const uint32_t n_tiles = (uint32_t)n_tiles64;
+
+    // every window can be an emission: the spill lists take the worst case of a piece, so nothing is ever dropped
+    const uint64_t hard_bound = 2 * own_n + 16;
+    uint64_t known = c->h_ctr->n_unique;
+    uint64_t want = c->capacity_hint ? std::max<uint64_t>(2 * c->capacity_hint, 2 * known)
+                                     : std::min<uint64_t>(2 * (known + hard_bound), std::max<uint64_t>(1ull << 24, 4 * known));
+    int rc = grow_table(c, want);
+    if (rc) return rc;
+    rc = grow_irr(c, std::max<uint64_t>(std::max<uint64_t>(1ull << 12, 4 * c->h_ctr->n_irr_unique), std::min<uint64_t>(hard_bound, 1ull << 22)));
+    if (rc) return rc;
+    rc = ensure_overflow(c, hard_bound, hard_bound);
+    if (rc) return rc;
+
+    // tile state
+    if (n_tiles > c->tile_cap) {
+        kj_dfree(ctx, c->tile_mem);
+        c->tile_mem = nullptr; c->tile_cap = 0;
+        uint64_t tc = std::max<uint64_t>(n_tiles, 4096);
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->tile_mem, tc * 8));
+        c->tile_cap = tc;
+    }
+    KJ_CUDA(ctx, cudaMemsetAsync(c->tile_mem, 0, (uint64_t)n_tiles * 8, ctx->stream));  // status only
+    KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->ticket, 0, sizeof(unsigned int), ctx->stream));
+
+    KjScanArgs a = make_args(c, dbuf, n, own_n, final_);
+    a.n_tiles = n_tiles;
+    a.tab = c->tab; a.irr = c->irr; a.ovf = c->ovf;
+    a.status = c->tile_mem;
+
+    void (*fn)(const KjScanArgs) = c->use_dense ? kj_scan_dense_kernel : kj_scan_lines_kernel;
     int occ = 0;
-    const int threads = c->use_filter ? KJ_FTHREADS : KJ_THREADS;   // filter kernel: 8 stream + 2 emit warps
-    KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, dyn_smem));
+    KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KJ_THREADS, 0));
     // persistent CTAs: a whole number of CTAs per SM, all resident (tiles are handed out by ticket and
     // a tile waits for the aggregates of the tiles before it)
     const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * std::max(occ, 1));
     if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    KJ_LAUNCH(fn, grid, threads, dyn_smem, ctx->stream, a);
+    KJ_LAUNCH(fn, grid, KJ_THREADS, 0, ctx->stream, a);
     ctx->launches++;
-    if (c->use_filter) {
-        // part B of the candidates: one thread per record, the whole GPU at once
-        if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
-        if (c->k <= 16) KJ_LAUNCH((kj_verify_kernel<4>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
-        else KJ_LAUNCH((kj_verify_kernel<8>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
-    }
     if (ctx->timers_on) KJ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->launches++;
     KJ_CUDA(ctx, cudaGetLastError());
     rc = pull_counters(c);
     if (rc) return rc;
-    if (ctx->timers_on) {
-        float ms = 0.f;
-        KJ_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        ctx->scan_ms += ms;
-        if (c->use_filter) {
-            float vms = 0.f;
-            KJ_CUDA(ctx, cudaEventElapsedTime(&vms, ctx->ev2, ctx->ev1));
-            ctx->verify_ms += vms;
-        }
-        ctx->scan_launches++;
-        ctx->scan_bytes += own_n;
-    }
+    if (ctx->timers_on) { rc = account_scan_time(c, own_n, false); if (rc) return rc; }
     rc = check_device_errors(c);
     if (rc) return rc;
 
@@ -488,10 +684,7 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
     for (int round = 0; round < 8 && (c->h_ctr->n_overflow || c->h_ctr->n_irr_overflow); ++round) {
         uint64_t nov = c->h_ctr->n_overflow, niov = c->h_ctr->n_irr_overflow;
         if (nov > c->ovf.cap || niov > c->ovf.irr_cap)
-            return kj_fail(ctx, KJ_E_TABLE_FULL,
-                           "k-mer table overflowed beyond the spill buffer (" + std::to_string(nov) +
-                               " regular, " + std::to_string(niov) +
-                               " irregular spills); raise capacity_hint");
+            return kj_fail(ctx, KJ_E_TABLE_FULL, "internal: more spills than a piece can emit");
         if (nov) { rc = grow_table(c, std::max<uint64_t>(c->cap * 4, 4 * (c->h_ctr->n_unique + nov))); if (rc) return rc; }
         if (niov) { rc = grow_irr(c, std::max<uint64_t>(c->irr_cap * 4, 4 * (c->h_ctr->n_irr_unique + niov))); if (rc) return rc; }
         KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_overflow, 0, 2 * sizeof(unsigned long long), ctx->stream));
@@ -511,9 +704,8 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
         rc = check_device_errors(c);
         if (rc) return rc;
     }
-    // keep the load factor at or below one half between launches
-    if (c->h_ctr->n_unique * 2 > c->cap) { rc = grow_table(c, c->cap * 4); if (rc) return rc; }
-    if (c->h_ctr->n_irr_unique * 2 > c->irr_cap) { rc = grow_irr(c, c->irr_cap * 4); if (rc) return rc; }
+    rc = keep_load_factor(c);
+    if (rc) return rc;
 
     c->voff += own_n;
     c->consumed += own_n;
@@ -524,13 +716,14 @@ static int scan_piece(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t ow
 // device-resident buffer.  The filter kernel takes it in one launch when the caller sized the
 // table (capacity_hint), else in 512 MiB pieces so the table can grow in between; the line
 // kernel (whose spill lists are sized for the worst case) in 4 MiB pieces.
-static int scan_device(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t own_n, int final_) {
-    const uint64_t piece = c->use_filter ? (c->capacity_hint ? (1ull << 40) : (512ull << 20))
-                                         : (c->use_dense ? (16ull << 20) : (4ull << 20));
+static int scan_device(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint64_t own_n, int final_, bool may_defer = false) {
+    // pieces are multiples of the filter path's tile, so that every piece but the last ends on a tile boundary
+    const uint64_t piece = c->use_filter ? (c->capacity_hint ? (1ull << 40) : (uint64_t)KJ_WT_BYTES * 16 * 8192)
+                                         : (c->use_dense ? (8ull << 20) : (4ull << 20));
     uint64_t lo = 0;
     while (lo < own_n) {
         uint64_t len = std::min(piece, own_n - lo);
-        int rc = scan_piece(c, dbuf + lo, n - lo, len, (final_ && lo + len == own_n) ? 1 : 0);
+        int rc = scan_piece(c, dbuf + lo, n - lo, len, (final_ && lo + len == own_n) ? 1 : 0, may_defer && len == own_n);
         if (rc) return rc;
         lo += len;
     }
@@ -548,6 +741,7 @@ extern "C" int kj_counts_create(kj_ctx *ctx, const kj_count_params *p, kj_counts
     KJ_CUDA(ctx, cudaSetDevice(ctx->device));
     kj_counts *c = new kj_counts();
     c->ctx = ctx;
+    c->piece = new KjPiece();
     c->prefix.assign(p->prefix, p->prefix + p->prefix_len);
     c->rprefix.resize(p->prefix_len);
     for (uint32_t i = 0; i < p->prefix_len; ++i)
@@ -583,25 +777,41 @@ extern "C" int kj_counts_create(kj_ctx *ctx, const kj_count_params *p, kj_counts
     return KJ_OK;
 }
 
-// host -> device staging chunk.  KJ_STAGE_CHUNK_MB overrides it (tuning aid; read once).
-static uint64_t kj_stage_chunk() {
-    static uint64_t v = 0;
-    if (!v) {
+// host -> device staging chunk of the context: kj_set_stage_chunk, else KJ_STAGE_CHUNK_MB, else 64 MiB
+static uint64_t kj_stage_chunk(kj_ctx *ctx) {
+    if (!ctx->stage_chunk) {
         const char *e = getenv("KJ_STAGE_CHUNK_MB");
         long mb = e ? atol(e) : 0;
-        v = (mb >= 1 && mb <= 4096) ? ((uint64_t)mb << 20) : (64ull << 20);
+        ctx->stage_chunk = (mb >= 1 && mb <= 4096) ? ((uint64_t)mb << 20) : (64ull << 20);
     }
-    return v;
+    return ctx->stage_chunk;
 }
-#define KJ_STAGE_CHUNK kj_stage_chunk()
+#define KJ_STAGE_CHUNK kj_stage_chunk(ctx)
 static const uint64_t KJ_STAGE_HALO_LINES = 1ull << 20;   // line kernel: longest line it can finish
+
+extern "C" int kj_set_stage_chunk(kj_ctx *ctx, uint64_t bytes) {
+    if (!ctx) return KJ_E_INVALID;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (bytes < 4096 || bytes > (4096ull << 20)) return kj_fail(ctx, KJ_E_INVALID, "staging chunk must be 4 KiB .. 4 GiB");
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    for (int i = 0; i < 2; ++i) {              // reallocated at the next use
+        cudaFree(ctx->d_stage[i]); ctx->d_stage[i] = nullptr;
+        if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
+        ctx->h_stage[i] = nullptr;
+    }
+    ctx->stage_chunk = (bytes + 15) / 16 * 16;
+    ctx->stage_cap = 0;
+    return KJ_OK;
+}
 
 static int ensure_staging(kj_ctx *ctx, bool need_host) {
     const uint64_t cap = KJ_STAGE_CHUNK + KJ_STAGE_HALO_LINES;
     if (!ctx->d_stage[0]) {
         for (int i = 0; i < 2; ++i) {
             KJ_CUDA(ctx, cudaMalloc(&ctx->d_stage[i], cap + 64));
-            KJ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+            if (!ctx->ev_copy[i]) KJ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
         }
         ctx->stage_cap = cap;
     }
@@ -664,7 +874,7 @@ extern "C" int kj_counts_add_buffer(kj_counts *c, const uint8_t *buf, uint64_t n
     int rc;
     if (mem_kind == KJ_MEM_DEVICE) {
         if ((uintptr_t)buf & 15) return kj_fail(ctx, KJ_E_INVALID, "device buffers must be 16-byte aligned");
-        rc = scan_device(c, buf, n, own_n, final_);
+        rc = scan_device(c, buf, n, own_n, final_, true);
     } else if (mem_kind == KJ_MEM_HOST) {
         rc = add_host(c, buf, n, own_n, final_);
     } else {
@@ -675,10 +885,32 @@ extern "C" int kj_counts_add_buffer(kj_counts *c, const uint8_t *buf, uint64_t n
     return KJ_OK;
 }
 
+// pread of [off, off + len) by up to four threads (page-cache / tmpfs copies scale with threads)
+static bool read_range(int fd, uint8_t *dst, uint64_t off, uint64_t len) {
+    const unsigned nt = len >= (8u << 20) ? 4u : 1u;
+    std::atomic<bool> ok(true);
+    auto part = [&](unsigned i) {
+        uint64_t lo = len * i / nt, hi = len * (i + 1) / nt;
+        while (lo < hi) {
+            ssize_t r = pread(fd, dst + lo, hi - lo, (off_t)(off + lo));
+            if (r <= 0) { ok = false; return; }
+            lo += (uint64_t)r;
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned i = 1; i < nt; ++i) th.emplace_back(part, i);
+    part(0);
+    for (auto &t : th) t.join();
+    return ok;
+}
+
+// KmerJS#readFile (lib/kmers.js:106-185): the file in staging chunks through two pinned buffers of the context; a
+// reader thread fills one while the other is copied to the device and counted.
 extern "C" int kj_counts_add_file(kj_counts *c, const char *path) {
     if (!c || !path) return KJ_E_INVALID;
     kj_ctx *ctx = c->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (c->finished || c->saw_final) return kj_fail(ctx, KJ_E_STATE, "kj_counts_add_file after the final buffer / finish");
     int fd = open(path, O_RDONLY);
     if (fd < 0) return kj_fail(ctx, KJ_E_IO, std::string("cannot open ") + path);
     struct stat st;
@@ -686,33 +918,42 @@ extern "C" int kj_counts_add_file(kj_counts *c, const char *path) {
     const uint64_t size = (uint64_t)st.st_size;
     const uint64_t halo = (c->use_filter || c->use_dense) ? 64 : KJ_STAGE_HALO_LINES;
     const uint64_t chunk = KJ_STAGE_CHUNK;
-    // read each piece (chunk + halo) into pinned memory and hand it over as a host buffer;
-    // the halo bytes are read again by the next piece
-    uint8_t *pin = nullptr;
-    if (cudaMallocHost(&pin, chunk + halo) != cudaSuccess) { close(fd); return kj_fail(ctx, KJ_E_NOMEM, "pinned staging"); }
     int rc = KJ_OK;
-    uint64_t lo = 0;
-    if (size == 0) rc = kj_counts_add_buffer(c, pin, 0, 0, KJ_MEM_HOST, 1);
-    while (lo < size && rc == KJ_OK) {
+    if (cudaSetDevice(ctx->device) != cudaSuccess) rc = kj_fail(ctx, KJ_E_CUDA, "cudaSetDevice");
+    if (rc == KJ_OK) rc = ensure_staging(ctx, true);
+    // piece boundaries: a tail shorter than the 32-byte halo a non-final piece must bring belongs to the piece before it
+    std::vector<uint64_t> cuts;
+    for (uint64_t lo = 0; lo < size;) {
         uint64_t hi = std::min(size, lo + chunk);
-        // a tail shorter than the 32-byte halo a non-final piece must bring belongs to this piece
-        // (the pinned buffer holds chunk + halo bytes)
         if (size - hi < 32) hi = size;
-        uint64_t rd_end = std::min(size, hi + halo);
-        uint64_t got = 0;
-        while (got < rd_end - lo) {
-            ssize_t r = pread(fd, pin + got, rd_end - lo - got, (off_t)(lo + got));
-            if (r <= 0) { rc = kj_fail(ctx, KJ_E_IO, std::string("read error on ") + path); break; }
-            got += (uint64_t)r;
-        }
-        if (rc) break;
-        int fin = hi == size;
-        rc = kj_counts_add_buffer(c, pin, fin ? hi - lo : rd_end - lo, hi - lo, KJ_MEM_HOST, fin);
+        cuts.push_back(hi);
         lo = hi;
     }
-    cudaFreeHost(pin);
+    const size_t np = cuts.size();
+    auto lo_of = [&](size_t i) { return i ? cuts[i - 1] : 0; };
+    auto rd_of = [&](size_t i) { return std::min(size, cuts[i] + halo) - lo_of(i); };      // bytes the piece reads (with halo)
+    std::future<bool> fut;
+    if (rc == KJ_OK && np) fut = std::async(std::launch::async, [&, fd]() { return read_range(fd, ctx->h_stage[0], 0, rd_of(0)); });
+    for (size_t i = 0; i < np && rc == KJ_OK; ++i) {
+        const int s = (int)(i & 1);
+        if (!fut.get()) { rc = kj_fail(ctx, KJ_E_IO, std::string("read error on ") + path); break; }
+        if (i + 1 < np) {
+            // the other pinned buffer was the source of the copy of piece i - 1
+            if (i >= 1 && cudaEventSynchronize(ctx->ev_copy[s ^ 1]) != cudaSuccess) { rc = kj_fail(ctx, KJ_E_CUDA, "cudaEventSynchronize"); break; }
+            const size_t nx = i + 1;
+            fut = std::async(std::launch::async, [&, fd, nx, s]() { return read_range(fd, ctx->h_stage[s ^ 1], lo_of(nx), rd_of(nx)); });
+        }
+        const uint64_t lo = lo_of(i), hi = cuts[i], rd = rd_of(i);
+        // device slot s was read by the scan of piece i - 2, which has been settled (host-staged pieces are not deferred)
+        cudaError_t e = cudaMemcpyAsync(ctx->d_stage[s], ctx->h_stage[s], rd, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copy[s], ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[s], 0);
+        if (e != cudaSuccess) { rc = kj_fail(ctx, KJ_E_CUDA, std::string("kj_counts_add_file: ") + cudaGetErrorString(e)); break; }
+        rc = scan_device(c, ctx->d_stage[s], rd, hi - lo, hi == size ? 1 : 0);
+    }
+    if (fut.valid()) fut.wait();
     close(fd);
-    if (rc == KJ_OK) c->bytes_read = size;
+    if (rc == KJ_OK) { c->bytes_read = size; c->saw_final = true; }
     return rc;
 }
 
@@ -730,7 +971,9 @@ extern "C" int kj_counts_finish(kj_counts *c) {
     kj_ctx *ctx = c->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     KJ_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = pull_counters(c);
+    int rc = settle_filter(c);         // a piece launched without waiting (capacity hint, device buffer)
+    if (rc) return rc;
+    rc = pull_counters(c);
     if (rc) return rc;
     rc = check_device_errors(c);
     if (rc) return rc;
@@ -1049,16 +1292,18 @@ extern "C" void kj_counts_free(kj_counts *c) {
     if (ctx) {
         std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         cudaSetDevice(ctx->device);
+        if (c->pending) cudaStreamSynchronize(ctx->stream);     // a kernel may still be reading the caller's buffer
         free_table(ctx, c->tab);
         free_irr(ctx, c->irr);
         kj_dfree(ctx, c->ovf.rec); kj_dfree(ctx, c->ovf.irr_rec);
         kj_dfree(ctx, c->ctr);
         kj_pinned_put(ctx, c->h_ctr);
-        kj_dfree(ctx, c->tile_mem);
+        kj_dfree(ctx, c->tile_mem); kj_dfree(ctx, c->tile_cnt); kj_dfree(ctx, c->scan_tmp);
         kj_dfree(ctx, c->cand);
         drop_compact(c);
         kj_dfree(ctx, c->part_rec);
     }
+    delete c->piece;
     delete c;
 }
 
@@ -1116,7 +1361,9 @@ extern "C" int kj_counts_merge_records(kj_counts *c, const void *dev_records, ui
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (!n) return KJ_OK;
     KJ_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = pull_counters(c);
+    int rc = settle_filter(c);
+    if (rc) return rc;
+    rc = pull_counters(c);
     if (rc) return rc;
     rc = grow_table(c, std::max<uint64_t>(2 * (c->h_ctr->n_unique + n), c->capacity_hint * 2));
     if (rc) return rc;
@@ -1174,7 +1421,9 @@ extern "C" int kj_counts_irregular_merge_part(kj_counts *c, const void *host_rec
     }
     if (!n) return KJ_OK;
     KJ_CUDA(ctx, cudaSetDevice(ctx->device));
-    // no round trip for the current size: every scan ends with the counters pulled, merges add at most n
+    int rc0 = settle_filter(c);
+    if (rc0) return rc0;
+    // no round trip for the current size: every settled scan ends with the counters pulled, merges add at most n
     c->irr_bound += n;
     int rc = grow_irr(c, 2 * c->irr_bound);
     if (rc) return rc;

@@ -96,6 +96,7 @@ extern "C" void kj_destroy(kj_ctx *ctx) {
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
     }
     if (ctx->pin_slab) cudaFreeHost(ctx->pin_slab);
+    if (ctx->h_wta) cudaFreeHost(ctx->h_wta);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);

@@ -29,6 +29,7 @@ struct kj_ctx {
     int rounding_mode = 4;              // bignumber.js ROUND_HALF_UP
     // scan-kernel timing (CUDA events on `stream`)
     bool timers_on = false;
+    uint64_t stage_chunk = 0;           // host -> device staging chunk (0: KJ_STAGE_CHUNK_MB or 64 MiB at first use)
     double scan_ms = 0.0;
     uint64_t scan_launches = 0;
     uint64_t scan_bytes = 0;
@@ -42,6 +43,7 @@ struct kj_ctx {
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     // small pinned blocks (device counters mirrored to the host, WTA results): cudaMallocHost costs
     // milliseconds, so handles borrow 1024-byte blocks from a slab owned by the context
+    void *h_wta = nullptr;              // pinned: the records of one kj_wta_loop_kernel launch
     uint8_t *pin_slab = nullptr;
     std::vector<void *> pin_free;
 };
@@ -107,10 +109,15 @@ struct kj_counts {
     KjOverflow ovf{};
     KjCounters *ctr = nullptr;        // device
     KjCounters *h_ctr = nullptr;      // pinned mirror
-    uint64_t *tile_mem = nullptr;     // tile_cap u64 (look-back status words)
+    uint64_t *tile_mem = nullptr;     // tile_cap u64: look-back status words (dense / line kernels), tile_excl (filter path)
     uint64_t tile_cap = 0;
-    uint64_t *cand = nullptr;         // candidate records of the launch in flight (filter kernel), 64 bytes each
+    uint64_t *tile_cnt = nullptr;     // filter path: '\n' per tile
+    void *scan_tmp = nullptr;         // filter path: temporary storage of the exclusive scan over the tiles
+    size_t scan_tmp_bytes = 0;
+    uint64_t *cand = nullptr;         // candidate entries of the piece in flight (filter path), 16 bytes each
     uint64_t cand_cap = 0;
+    struct KjPiece *piece = nullptr;  // filter path: the piece in flight (kernel arguments + tensor map), kj_count.cu
+    bool pending = false;             // the piece has been launched and not settled yet
     // results
     KjCompact reg{};
     // irregular entries, host side after finish: 56-byte records

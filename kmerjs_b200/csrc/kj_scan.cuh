@@ -1,21 +1,14 @@
-// kj_scan.cuh -- the extraction kernels (K1+K2+K3 of SURVEY.md appendix B) for sm_100a.
+// kj_scan.cuh -- shared pieces of the extraction kernels (K1+K2+K3 of SURVEY.md appendix B) for sm_100a, and the two
+// kernels that are not the hot one:
 //
-// One persistent single-pass kernel reads every FASTQ byte exactly once from HBM:
+//   kj_scan_dense_kernel   empty prefix, step 1, k >= 2 (BASELINE config 5): every window is an emission
+//   kj_scan_lines_kernel   everything else (step > 1, k = 1 with the empty prefix) and the independent second
+//                          implementation the tests compare with (KJ_F_FORCE_GENERIC)
 //
-//   P1  coalesced 16-byte loads -> per 16-byte chunk: a 32-bit word of 2-bit base codes and a
-//       16-bit newline mask, both kept in shared memory (the raw bytes are never staged);
-//       newline counts per 512-byte row (one warp-wide load) and per tile.
-//   LB  decoupled look-back over tiles (dynamic tile tickets) gives every tile the number of
-//       '\n' before it -- the reference's record FSM is "line index mod 4" (lib/kmers.js:151-163),
-//       which is global state.
-//   P2  (filter kernel) bit-parallel search of the prefix and of complement(prefix) in code
-//       space, 16 window positions per 32-bit operation.  Codes are a function of the byte, so
-//       this is an exact superset filter; candidates go to a shared-memory queue.
-//   P3  candidates (about 2/4^m of the positions) are verified on the bytes with the exact rules
-//       of lib/kmers.js:88-100,151-155 and inserted into the HBM hash table.
-//
-// The line-oriented kernel (P2'/P3') handles what the filter cannot: step > 1 (short windows),
-// the empty prefix, and is kept as an independent implementation for the tests.
+// Both read every FASTQ byte once, in tiles handed out by an atomic ticket: per 16-byte chunk a word of 2-bit base codes
+// and a newline mask; a decoupled look-back over the tiles gives every tile the number of '\n' before it -- the
+// reference's record FSM is "line index mod 4" (lib/kmers.js:151-163), which is global state.  The filter path
+// (step 1, 1 <= |prefix| <= k) lives in kj_scan_warp.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,28 +20,7 @@
 #define KJ_THREADS 256                                   // line kernel
 #define KJ_QCAP 1536                                     // line queue entries (line kernel: <= 1024 per round)
 #define KJ_MAX_MP 8                                      // filter symbols used in code space
-// filter kernel: warp 0 = control (aggregates, look-back, hand-over), warps 1-7 = stream (convert +
-// search), warps 8-9 = emit (verify + count)
-#define KJ_CTHREADS 32
-#define KJ_STHREADS 224
-#define KJ_ETHREADS 64
-#define KJ_FTHREADS (KJ_CTHREADS + KJ_STHREADS + KJ_ETHREADS)
-#define KJ_FQCAP 256                                     // candidate queue entries per slot (~55 chunks per tile hold one)
-// One queue entry per 16-byte chunk that holds a candidate: the lanes that passed the code-space filter
-// (bit 2p: forward window at chunk position p, bit 2p + 1: reverse-strand window) and the chunk index.
-// The stream warps only store the two words; the emit warps take the bits apart.
-struct KjCandQueue { uint32_t lanes[KJ_FQCAP]; uint16_t chunk[KJ_FQCAP]; };
-#define KJ_STAGE_BYTES (KJ_TILE_BYTES + 32)              // a tile and the 32 bytes its last windows reach into
-#define KJ_HALF_BYTES (KJ_TILE_BYTES / 2)                // the tile is copied and converted in two halves
 #define KJ_NO_TILE 0xFFFFFFFFu
-#define KJ_SLOTS 3                                       // stream -> emit hand-over slots
-#define KJ_REC_BLOCK 256u                                // candidate records reserved per emit warp at a time
-// named barriers of the filter kernel (0: __syncthreads, 1: stream warps)
-#define KJ_NB_CTL 2                                      // +(seq mod KJ_SLOTS): stream warp 0 -> control warp
-#define KJ_NB_FULL (KJ_NB_CTL + KJ_SLOTS)                // +slot: control warp -> emit warps
-#define KJ_NB_EMPTY (KJ_NB_FULL + KJ_SLOTS)              // +slot: emit warps -> stream warps
-static_assert(KJ_NB_EMPTY + KJ_SLOTS <= 16, "16 named barriers per CTA");
-
 #define KJ_ST_AGG 1ull
 #define KJ_ST_INC 2ull
 #define KJ_ST_MASK 0x3FFFFFFFFFFFFFFFull
@@ -85,8 +57,12 @@ struct KjScanArgs {
     KjIrrTable irr;
     KjOverflow ovf;
     uint64_t *status;     // per tile: flag << 62 | newline count; zeroed before every launch
-    uint64_t *cand;       // candidate records (KJ_REC_WORDS u64 each) of this launch (filter kernel)
-    uint64_t cand_cap;    // in records
+    uint64_t *cand;       // filter path: candidate entries of this launch, 16 bytes each (kj_scan_warp.cuh)
+    uint64_t cand_cap;    // in entries
+    uint64_t *tile_cnt;   // filter path: '\n' per tile
+    uint64_t *tile_excl;  // filter path: '\n' before the tile inside the launch (exclusive scan of tile_cnt)
+    uint32_t n_fast;      // filter path: leading tiles that are whole, owned and readable through the tensor map
+    uint32_t resolve_retry;   // kj_resolve_kernel: only the entries an earlier pass marked
     KjCounters *ctr;
 };
 
@@ -175,17 +151,9 @@ __device__ __forceinline__ void kj_bar_arrive(uint64_t *bar) {
     if (pending == 0) { pending = count; phase ^= 1u; }
     *bar = (uint64_t)pending | ((uint64_t)count << 16) | ((uint64_t)phase << 32);
 }
-__device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    memcpy(dst, src, bytes);
-    kj_bar_arrive(bar);
-}
 __device__ __forceinline__ void kj_bar_wait(uint64_t *bar, uint32_t parity) {
     while ((uint32_t)(*reinterpret_cast<volatile uint64_t *>(bar) >> 32) == parity) emu_yield();
 }
-#define kj_bar_wait_idle kj_bar_wait
-__device__ __forceinline__ void kj_sync_stream() { emu_named_barrier(1, KJ_STHREADS); }
-__device__ __forceinline__ void kj_nbar_sync(uint32_t id, uint32_t count) { emu_named_barrier((int)id, (int)count); }
-__device__ __forceinline__ void kj_nbar_arrive(uint32_t id, uint32_t count) { emu_named_arrive((int)id, (int)count); }
 #else
 __device__ __forceinline__ uint32_t kj_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void kj_bar_init(uint64_t *bar, uint32_t count) {
@@ -193,12 +161,6 @@ __device__ __forceinline__ void kj_bar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void kj_bar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(kj_smem_u32(bar)) : "memory");
-}
-// one thread: announce `bytes` on the barrier, then start the copy (src, dst 16-byte aligned, bytes % 16 == 0)
-__device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(kj_smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(kj_smem_u32(dst)), "l"(src), "r"(bytes), "r"(kj_smem_u32(bar)) : "memory");
 }
 // returns once the phase with parity `parity` has completed.  try_wait suspends the warp in hardware
 // for up to the hinted time, so waiting warps do not eat issue slots.  (A macro, so that profiles
@@ -213,32 +175,6 @@ __device__ __forceinline__ void kj_bulk_g2s(void *dst, const void *src, uint32_t
                          "selp.u32 %0, 1, 0, p;\n\t}"                                                         \
                          : "=r"(ok__) : "r"(addr__), "r"(par__), "r"(20000u) : "memory");                     \
     } while (0)
-// the same for warps that are off the critical path (control, emit): sleep between polls, an idle
-// warp must not compete for issue slots with the stream warps
-#define kj_bar_wait_idle(bar, parity)                                                                         \
-    do {                                                                                                      \
-        uint32_t ok__ = 0;                                                                                    \
-        const uint32_t addr__ = kj_smem_u32(bar);                                                             \
-        const uint32_t par__ = (parity);                                                                      \
-        for (;;) {                                                                                            \
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"    \
-                         "selp.u32 %0, 1, 0, p;\n\t}"                                                         \
-                         : "=r"(ok__) : "r"(addr__), "r"(par__) : "memory");                                  \
-            if (ok__) break;                                                                                  \
-            __nanosleep(256);                                                                                 \
-        }                                                                                                     \
-    } while (0)
-// barrier of the 7 stream warps of the filter kernel (control and emit warps do not take part)
-__device__ __forceinline__ void kj_sync_stream() { asm volatile("bar.sync 1, %0;" ::"n"(KJ_STHREADS) : "memory"); }
-// producer / consumer hand-over between warp groups on a hardware named barrier: the producer group
-// arrives and goes on, the consumer group blocks (no polling, no issue slots) until `count` threads
-// of both groups have arrived.  One hand-over may be outstanding per barrier id.
-__device__ __forceinline__ void kj_nbar_sync(uint32_t id, uint32_t count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void kj_nbar_arrive(uint32_t id, uint32_t count) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
 #endif
 
 // one 16-byte chunk -> code word and newline mask (the rows are counted by kj_tile_rowscan_warp)
@@ -247,25 +183,7 @@ __device__ __forceinline__ void kj_p1_chunk(uint32_t *codes, KjTileSmem &s, uint
     s.nl[c] = (uint16_t)(kj_nl16(v.x, v.y, v.z, v.w) & nl_keep);
 }
 
-// P1 of one half of the staged tile (interior tiles: every byte owned, halo readable) by a group of
-// NT threads, t = index in the group.  The caller synchronises.
-template <int NT, int HALF>
-__device__ __forceinline__ void kj_tile_p1_stage(uint32_t *codes, KjTileSmem &s, const uint8_t *stage, uint32_t t) {
-    constexpr int CPT = KJ_TILE_CHUNKS / NT;
-    static_assert(CPT * NT == KJ_TILE_CHUNKS && NT % 32 == 0 && CPT % 2 == 0, "tile must split evenly into warp rows, twice");
-#pragma unroll 4
-    for (int it = HALF * (CPT / 2); it < (HALF + 1) * (CPT / 2); ++it) {      // the first or the second half of the tile
-        const uint32_t c = it * NT + t;
-        const uint4 v = *reinterpret_cast<const uint4 *>(stage + c * 16u);
-        kj_p1_chunk(codes, s, c, v, 0xFFFFu);
-    }
-    if (HALF == 1 && t < 2) {
-        const uint4 h = *reinterpret_cast<const uint4 *>(stage + (KJ_TILE_CHUNKS + t) * 16u);
-        codes[KJ_TILE_CHUNKS + t] = kj_pack16(h.x, h.y, h.z, h.w);
-    }
-}
-
-// P1 straight from global memory (edge tiles of the filter kernel, every tile of the line kernel).
+// P1 straight from global memory (line kernel).
 // Newlines are counted only inside the owned range.  The caller synchronises.
 template <int NT>
 static __device__ __noinline__ void kj_tile_p1_global(const KjScanArgs &a, uint32_t *codes, KjTileSmem &s, uint32_t tile,
@@ -418,69 +336,6 @@ static __device__ __noinline__ void kj_emit_irregular(const KjScanArgs &a, uint6
     if (!kj_insert_irr(a.irr, a.ctr, key32, len, ord, 1)) kj_spill_irr(a, off, len, strand, ord);
 }
 
-// The 512-bit newline bitmap of the row (32 chunks) that holds tile position jt, as 16 words.
-struct KjRowBits { uint32_t w[16]; };
-__device__ __forceinline__ KjRowBits kj_row_bits(const KjTileSmem &s, uint32_t jt) {
-    const uint4 *rp = reinterpret_cast<const uint4 *>(&s.nl[(jt >> 9) * 32u]);
-    KjRowBits r;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint4 v = rp[i];
-        r.w[4 * i] = v.x; r.w[4 * i + 1] = v.y; r.w[4 * i + 2] = v.z; r.w[4 * i + 3] = v.w;
-    }
-    return r;
-}
-
-// A candidate of the filter kernel (window start at tile-relative jt; step == 1, 1 <= m <= k) is
-// handled in two parts.
-//
-// Part A, from the tile's newline bitmap in shared memory (emit warps of the scan kernel): is the
-// line a sequence line (index 1 mod 4, lib/kmers.js:151) and, if first-seen order is tracked, the
-// ordinal (read index, strand, column).  Survivors become 64-byte records {position | strand << 63,
-// ordinal, the three 16-byte chunks that hold the window} in global memory: the chunks are L2 hits
-// for the emit warps (the tile was streamed in a moment ago) and part B never touches the input again.
-//
-// Part B, from the window's bytes (kj_verify_kernel, one thread per record, the whole GPU at once):
-// exact prefix / newline / alphabet check and the hash-table update.  It is a chain of L2 round
-// trips per candidate; run per tile inside the scan kernel it set the pace of the whole pipeline,
-// as a separate wide kernel its latency disappears behind parallelism.
-#define KJ_REC_STRAND (1ull << 63)
-#define KJ_REC_NONE 0xFFFFFFFFFFFFFFFFull
-#define KJ_REC_WORDS 8      // u64 words per record: position | strand, ordinal, 48 bytes of the window's chunks
-
-// Part A.  false: not in a sequence line (or an error was flagged).
-__device__ __forceinline__ bool kj_candidate_line(const KjScanArgs &a, const KjTileSmem &s, uint64_t tile_off,
-                                                  uint64_t tile_voff, uint32_t jt, uint32_t strand, uint64_t &ord) {
-    // newlines of the tile before jt: prefix of the row + bitmap words of the row below jt
-    const KjRowBits rb = kj_row_bits(s, jt);
-    const uint32_t p = jt & 511u, pw = p >> 5;
-    const uint32_t part = (1u << (p & 31u)) - 1u;
-    uint32_t before = s.row_pre[jt >> 9];
-    uint32_t last_w = 0, last_i = 0;                      // highest bitmap word with a '\n' below jt
-#pragma unroll
-    for (uint32_t i = 0; i < 16; ++i) {
-        const uint32_t x = rb.w[i] & (i < pw ? 0xFFFFFFFFu : (i == pw ? part : 0u));
-        before += __popc(x);
-        if (x) { last_w = x; last_i = i; }
-    }
-    const uint64_t line = s.excl_count + before;
-    if ((line & 3ull) != 1ull) return false;              // lib/kmers.js:151  i === 1
-    ord = 0;
-    if (a.order || a.k == 1) {
-        // first byte of the line: the last '\n' below jt in this row, else further back
-        unsigned long long start;
-        if (last_w) start = tile_voff + (jt & ~511u) + last_i * 32u + (31u - __clz(last_w)) + 1ull;
-        else start = kj_line_start(a, s, jt & ~511u, tile_off, tile_voff);
-        const uint64_t col = tile_voff + jt - start;
-        if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); return false; }
-        const uint64_t read_idx = line >> 2;
-        if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); return false; }
-        // forward emissions in ascending column, then reverse emissions in descending column
-        ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
-    }
-    return true;
-}
-
 // the window's bytes: the (at most) three aligned 16-byte chunks that hold buf[j, j + k), requested together
 __device__ __forceinline__ void kj_window_load(const KjScanArgs &a, uint64_t j, uint4 &v0, uint4 &v1, uint4 &v2) {
     const uint64_t base = j & ~15ull;
@@ -491,96 +346,7 @@ __device__ __forceinline__ void kj_window_load(const KjScanArgs &a, uint64_t j, 
     if (base + 32u < j + a.k) v2 = kj_load_chunk(a.buf, base + 32u, a.n);
 }
 
-// Part B: the window at buffer offset j, its chunks already loaded.  Straight-line SIMD-in-register code.
-// KW = 4-byte words of the window the code looks at: 8 covers every k <= 32; 4 (k <= 16, the KmerFinder
-// default) halves the work and never needs the third chunk (offset in the chunk + k <= 31).
-template <int KW = 8>
-__device__ __forceinline__ void kj_window_emit(const KjScanArgs &a, uint64_t j, uint32_t strand, uint64_t ord,
-                                               const uint4 v0, const uint4 v1, const uint4 v2, uint32_t &n_emit) {
-    static_assert(KW == 4 || KW == 8, "window words");
-    const uint32_t k = a.k;
-    const uint32_t o = (uint32_t)(j & 15u);
-    // window bytes 0..31 in X[0..7]: shift the 48 loaded bytes down by o
-    const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-    const uint32_t q = o >> 2, r8 = (o & 3u) * 8u;
-    uint32_t X[KW];
-#pragma unroll
-    for (int i = 0; i < KW; ++i) {
-        const uint32_t lo = q == 0 ? W[i] : q == 1 ? W[i + 1] : q == 2 ? W[i + 2] : W[i + 3];
-        const uint32_t hi = q == 0 ? W[i + 1] : q == 1 ? W[i + 2] : q == 2 ? W[i + 3] : W[i + 4];
-        X[i] = kj_funnel_r(lo, hi, r8);
-    }
-    uint32_t bad = 0, nl = 0, irr = 0, p_lo = 0, p_hi = 0;
-#pragma unroll
-    for (int i = 0; i < KW; ++i) {
-        if (4u * i < k) {
-            const uint32_t bm = (4u * i + 4u <= k) ? 0xFFFFFFFFu : ((1u << (8u * (k - 4u * i))) - 1u);   // bytes of the window
-            bad |= (X[i] ^ a.want[strand][i]) & a.wmask[strand][i];
-            nl |= kj_nl_msb4(X[i]) & bm;
-            irr |= kj_not_acgt4(X[i]) & bm;
-            const uint32_t c8 = kj_pack4(X[i] & bm);
-            if (i < 4) p_lo |= c8 << (8 * i); else p_hi |= c8 << (8 * (i - 4));
-        }
-    }
-    if (nl | bad) return;                                 // crosses the end of the line / prefix bytes differ
-    if (k == 1 && a.line_gate) {                          // lib/kmers.js:151  line.length > 1: a lone byte is not processed
-        const bool first = j == 0 ? (a.ctr->carry_last[a.parity] == a.voff) : (a.buf[j - 1] == '\n');
-        const bool more = (j + 1 < a.n) && a.buf[j + 1] != '\n';
-        if (first && !more) return;
-    }
-    const uint64_t P = ((uint64_t)p_hi << 32) | p_lo;     // code of window byte i at bits 2i
-    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
-    ++n_emit;
-    if (!irr) {
-        // forward key: first base most significant; reverse key: complement codes, last base first
-        const uint64_t key = strand ? ((P ^ 0xAAAAAAAAAAAAAAAAull) & kmask) : (kj_pairrev64(P) >> (64u - 2u * k));
-        if (!kj_insert(a.tab, a.ctr, key, ord, 1)) kj_spill(a, key, ord);
-    } else {
-        kj_emit_irregular(a, j, k, strand, ord);
-    }
-}
-
-// both parts in place: the scan kernel's fallback when the record buffer is full, and dense inputs
-static __device__ __noinline__ void kj_verify_candidate(const KjScanArgs &a, const KjTileSmem &s,
-                                                        uint64_t tile_off, uint64_t tile_voff,
-                                                        uint32_t jt, uint32_t strand, uint32_t &n_emit) {
-    uint64_t ord;
-    if (tile_off + jt + a.k > a.n) return;                // window must lie inside the stream
-    if (kj_candidate_line(a, s, tile_off, tile_voff, jt, strand, ord)) {
-        uint4 v0, v1, v2;
-        kj_window_load(a, tile_off + jt, v0, v1, v2);
-        kj_window_emit(a, tile_off + jt, strand, ord, v0, v1, v2, n_emit);
-    }
-}
-
-// Part B over the records of one launch.
-template <int KW>
-__global__ void __launch_bounds__(256) kj_verify_kernel(const __grid_constant__ KjScanArgs a) {
-    const unsigned long long n_res = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;   // slots handed out
-    uint32_t n_emit = 0;
-    // two records in flight per thread: the kernel is a chain of round trips (record, key slot), so
-    // its pace is set by how many of them overlap
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_res; i += 2 * stride) {
-        const unsigned long long i2 = i + stride;
-        const uint4 *rp = reinterpret_cast<const uint4 *>(a.cand + KJ_REC_WORDS * i);
-        const uint4 *rq = reinterpret_cast<const uint4 *>(a.cand + KJ_REC_WORDS * (i2 < n_res ? i2 : i));
-        const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(rp);
-        const uint4 zero = make_uint4(0, 0, 0, 0);
-        const uint4 v0 = rp[1], v1 = rp[2], v2 = KW > 4 ? rp[3] : zero;    // the window's chunks travel in the record
-        ulonglong2 r2 = *reinterpret_cast<const ulonglong2 *>(rq);
-        const uint4 w0 = rq[1], w1 = rq[2], w2 = KW > 4 ? rq[3] : zero;
-        if (i2 >= n_res) r2.x = KJ_REC_NONE;
-        if (r.x != KJ_REC_NONE)                            // KJ_REC_NONE: unused tail of a reserved block
-            kj_window_emit<KW>(a, r.x & ~KJ_REC_STRAND, (uint32_t)(r.x >> 63), r.y, v0, v1, v2, n_emit);
-        if (r2.x != KJ_REC_NONE)
-            kj_window_emit<KW>(a, r2.x & ~KJ_REC_STRAND, (uint32_t)(r2.x >> 63), r2.y, w0, w1, w2, n_emit);
-    }
-    for (int d = 16; d > 0; d >>= 1) n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
-    if ((threadIdx.x & 31) == 0 && n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);
-}
-
-// ----------------------------------------------------------------------------- filter kernel
+// ----------------------------------------------------------------------------- code-space filter
 
 // 16 code lanes holding symbol i of complement(prefix) for the 16 windows of a chunk
 template <int RC>
@@ -588,304 +354,6 @@ __device__ __forceinline__ uint32_t kj_rc_lanes(uint32_t c0, uint32_t c1, uint32
     if (RC == KJ_RC_LOW) return kj_funnel_r(c0, c1, 2u * d);
     if (RC == KJ_RC_HIGH) return kj_funnel_r(c1, c2, 2u * (d - 16u));
     return kj_lanes(c0, c1, c2, d);
-}
-
-// candidate lanes (bit 2p set: window at chunk position p passes the code-space filter)
-template <int MP, int RC>
-__device__ __forceinline__ void kj_chunk_filter(const KjScanArgs &a, const uint32_t *codes, uint32_t c,
-                                                uint32_t &zf, uint32_t &zr) {
-    const uint32_t c0 = codes[c], c1 = codes[c + 1], c2 = codes[c + 2];
-    uint32_t accf = 0, accr = 0;
-#pragma unroll
-    for (int i = 0; i < MP; ++i) {
-        accf |= kj_funnel_r(c0, c1, 2u * i) ^ a.pat_f[i];
-        accr |= kj_rc_lanes<RC>(c0, c1, c2, a.rc_shift + i) ^ a.pat_r[i];
-    }
-    zf = kj_zero_lanes(accf);
-    zr = a.n_strands > 1 ? kj_zero_lanes(accr) : 0u;
-}
-
-// P2 of one tile by a group of NT threads: bit-parallel prefix search in code space; candidates -> queue
-template <int MP, int RC, int NT, bool FULL>
-__device__ __forceinline__ void kj_tile_search(const KjScanArgs &a, const uint32_t *codes, KjTileSmem &s, KjCandQueue &queue,
-                                               uint32_t own_in_tile, uint32_t t) {
-    constexpr int CPT = KJ_TILE_CHUNKS / NT;
-#pragma unroll 4
-    for (int it = 0; it < CPT; ++it) {
-        const uint32_t c = it * NT + t;
-        const uint32_t pos0 = c * 16u;
-        if (!FULL && pos0 >= own_in_tile) continue;        // FULL: every position of the tile is owned
-        uint32_t zf, zr;
-        kj_chunk_filter<MP, RC>(a, codes, c, zf, zr);
-        if (!FULL && own_in_tile - pos0 < 16u) {
-            const uint32_t keep = (1u << (2u * (own_in_tile - pos0))) - 1u;
-            zf &= keep; zr &= keep;
-        }
-        if (zf | zr) {                                     // one chunk in 32
-            const uint32_t q = atomicAdd(&s.q_n, 1u);
-            if (q < KJ_FQCAP) { queue.lanes[q] = zf | (zr << 1); queue.chunk[q] = (uint16_t)c; }
-        }
-    }
-}
-
-// The filter kernel: warp-specialised and software-pipelined over tiles.
-//
-//   warps 1-7  stream   search(cur) | convert(nxt) | take ticket, start copy(nxt+1), tell control
-//   warp  0    control  aggregate(nxt) -> published for the tiles behind; look-back(cur); hand cur to emit
-//   warps 8-9  emit     verify + count the candidates of the tiles handed over (latency bound: L2 round
-//                       trips of the byte check and of the hash table), up to KJ_SLOTS - 1 tiles behind
-//
-// The bytes of a tile arrive in `stage` through the TMA engine (cp.async.bulk + mbarrier) while the
-// tile before it is searched.  A tile is converted to code words and its newline aggregate is
-// published BEFORE the current one is finished, so the look-back of the tiles behind it does not
-// wait for this CTA.  Hand-over: KJ_SLOTS slots {KjTileSmem, candidate queue} with a full / empty
-// named barrier pair each.  Stream -> control commands rotate over KJ_SLOTS buffers / barrier ids: a command
-// is known to be consumed only when the slot it handed over comes back free (the stream warps wait for
-// that before they refill the slot), so up to KJ_SLOTS commands can be outstanding -- at the start, before
-// any slot has gone round, and at the end, where the last command is sent without refilling a slot.
-struct KjCtlCmd { uint32_t lb_tile, lb_slot, scan_tile, scan_slot; };
-
-template <int MP, int RC>
-__global__ void __launch_bounds__(KJ_FTHREADS, 4)
-kj_scan_filter_kernel(const __grid_constant__ KjScanArgs a) {
-    __shared__ uint32_t codes[KJ_TILE_CHUNKS + 2];              // +2 halo words: windows reach k-1 bytes past the tile
-    __shared__ KjTileSmem meta[KJ_SLOTS];
-    __shared__ KjCandQueue queue[KJ_SLOTS];                     // chunks with candidate lanes
-    __shared__ uint32_t tile_of[KJ_SLOTS];                      // tile in the slot (KJ_NO_TILE: no more work)
-    __shared__ uint32_t tile_next;                              // ticket fetched ahead
-    __shared__ KjCtlCmd ctl[KJ_SLOTS];
-    __shared__ __align__(8) uint64_t bar_load[2];               // completion of the two half-tile copies in flight
-    KJ_DYN_SMEM(stage);                                         // KJ_STAGE_BYTES: raw bytes of the tile in flight
-    const uint32_t tid = threadIdx.x;
-    // a tile travels through `stage` when it and the 32 bytes behind it are owned and readable
-    const bool any_staged = a.own_n >= KJ_STAGE_BYTES;
-    const uint64_t staged_end = any_staged ? a.own_n - KJ_STAGE_BYTES : 0;      // staged iff tile_off <= staged_end
-
-    // The tile in flight is copied in two halves, each re-armed as soon as the stream warps have
-    // converted that half of the tile before it: with one staging buffer a copy can only run while
-    // its target is not being read, and half-tile granularity keeps a copy in flight most of the time.
-    auto start_half = [&](uint32_t t, int half) {   // one thread
-        const uint64_t off = (uint64_t)t * KJ_TILE_BYTES;
-        if (t < a.n_tiles && any_staged && off <= staged_end)
-            kj_bulk_g2s(stage + half * KJ_HALF_BYTES, a.buf + off + half * KJ_HALF_BYTES,
-                        half ? KJ_STAGE_BYTES - KJ_HALF_BYTES : KJ_HALF_BYTES, &bar_load[half]);
-    };
-    auto take_ticket = [&]() {          // one thread: next tile + start of the copy of its first half
-        const uint32_t t = atomicAdd(&a.ctr->ticket, 1u);
-        tile_next = t;
-        start_half(t, 0);
-    };
-
-    if (tid == 0) {
-        kj_bar_init(&bar_load[0], 1);
-        kj_bar_init(&bar_load[1], 1);
-#if defined(__CUDA_ARCH__)
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-        take_ticket();
-        start_half(tile_next, 1);
-    }
-    __syncthreads();
-
-    if (tid < KJ_CTHREADS) {
-        // ------------------------------------------------------------------ control warp
-        uint32_t seq = 0;
-        for (;;) {
-            const uint32_t kk = seq % KJ_SLOTS;
-            kj_nbar_sync(KJ_NB_CTL + kk, 32 + KJ_CTHREADS);      // a command from stream warp 0
-            ++seq;
-            const KjCtlCmd cmd = ctl[kk];
-            if (cmd.scan_tile != KJ_NO_TILE) kj_tile_rowscan_warp(a, meta[cmd.scan_slot], cmd.scan_tile);
-            if (cmd.lb_tile != KJ_NO_TILE) {
-                kj_lookback(a, meta[cmd.lb_slot], cmd.lb_tile);
-                if (tid == 0) tile_of[cmd.lb_slot] = cmd.lb_tile;
-                __syncwarp();
-                kj_nbar_arrive(KJ_NB_FULL + cmd.lb_slot, KJ_CTHREADS + KJ_ETHREADS);
-            }
-            if (cmd.scan_tile == KJ_NO_TILE) break;          // nothing behind it
-        }
-        return;
-    }
-
-    if (tid >= KJ_CTHREADS + KJ_STHREADS) {
-        // ------------------------------------------------------------------ emit warps
-        const uint32_t et = tid - (KJ_CTHREADS + KJ_STHREADS);
-        uint32_t n_emit = 0, b = 0;
-        long long n_bases = 0;
-        unsigned long long blk_base = KJ_REC_NONE;      // this warp's block of record slots
-        uint32_t blk_used = KJ_REC_BLOCK;
-        for (;;) {
-            kj_nbar_sync(KJ_NB_FULL + b, KJ_CTHREADS + KJ_ETHREADS);   // slot b handed over (by the control warp, or the stop mark)
-            const uint32_t tile = tile_of[b];
-            if (tile == KJ_NO_TILE) break;
-            const KjTileSmem &m = meta[b];
-            const uint64_t tile_off = (uint64_t)tile * KJ_TILE_BYTES;
-            const uint64_t tile_voff = a.voff + tile_off;
-            const uint32_t own_in_tile =
-                (a.own_n - tile_off < KJ_TILE_BYTES) ? (uint32_t)(a.own_n - tile_off) : KJ_TILE_BYTES;
-            if (a.count_bases) n_bases += kj_tile_bases(m, tile_voff, et, KJ_ETHREADS);
-            const uint32_t qn = m.q_n;
-            if (qn <= KJ_FQCAP) {
-                // candidates sit densely in the lanes.  Survivors of the line check are appended to
-                // the record buffer, in blocks of KJ_REC_BLOCK records reserved per warp (one global
-                // atomic per block, off the per-tile path).
-                for (uint32_t q0 = 0; q0 < qn; q0 += KJ_ETHREADS) {
-                  const uint32_t q = q0 + et;
-                  uint32_t lanes = 0, cpos = 0;
-                  if (q < qn) { lanes = queue[b].lanes[q]; cpos = 16u * queue[b].chunk[q]; }
-                  // one candidate of every lane's chunk per round (a chunk rarely holds two)
-                  while (__any_sync(0xFFFFFFFFu, lanes != 0u)) {
-                    bool keep = false;
-                    uint64_t ord = 0, rec = 0;
-                    if (lanes) {
-                        const uint32_t bit = __ffs(lanes) - 1;
-                        lanes &= lanes - 1;
-                        const uint32_t jt = cpos + (bit >> 1), strand = bit & 1u;
-                        if (tile_off + jt + a.k <= a.n)
-                            keep = kj_candidate_line(a, m, tile_off, tile_voff, jt, strand, ord);
-                        rec = (tile_off + jt) | (strand ? KJ_REC_STRAND : 0ull);
-                    }
-                    const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
-                    const uint32_t need = __popc(kb);
-                    if (need == 0) continue;
-                    if (blk_used + need > KJ_REC_BLOCK) {
-                        // retire the block (mark its unused tail), reserve a new one
-                        if (blk_base != KJ_REC_NONE)
-                            for (uint32_t i = blk_used + (tid & 31); i < KJ_REC_BLOCK; i += 32) a.cand[KJ_REC_WORDS * (blk_base + i)] = KJ_REC_NONE;
-                        unsigned long long nb_ = 0;
-                        if ((tid & 31) == 0) nb_ = atomicAdd(&a.ctr->n_cand, (unsigned long long)KJ_REC_BLOCK);
-                        nb_ = __shfl_sync(0xFFFFFFFFu, nb_, 0);
-                        blk_base = nb_ + KJ_REC_BLOCK <= a.cand_cap ? nb_ : KJ_REC_NONE;     // NONE: buffer full
-                        blk_used = blk_base == KJ_REC_NONE ? KJ_REC_BLOCK : 0;              // stay "full"
-                    }
-                    if (blk_base != KJ_REC_NONE) {
-                        if (keep) {
-                            const unsigned long long at = blk_base + blk_used + __popc(kb & ((1u << (tid & 31)) - 1u));
-                            uint4 v0, v1, v2;
-                            kj_window_load(a, rec & ~KJ_REC_STRAND, v0, v1, v2);
-                            uint4 *rp = reinterpret_cast<uint4 *>(a.cand + KJ_REC_WORDS * at);
-                            *reinterpret_cast<ulonglong2 *>(rp) = make_ulonglong2(rec, ord);
-                            rp[1] = v0; rp[2] = v1; rp[3] = v2;  // the whole 64-byte record: a partial sector write costs a DRAM read
-                        }
-                        blk_used += need;
-                    } else if (keep) {
-                        uint4 v0, v1, v2;                   // buffer full: in place
-                        kj_window_load(a, rec & ~KJ_REC_STRAND, v0, v1, v2);
-                        kj_window_emit(a, rec & ~KJ_REC_STRAND, (uint32_t)(rec >> 63), ord, v0, v1, v2, n_emit);
-                    }
-                  }
-                }
-            } else {
-                // dense candidates (e.g. homopolymer input): the code words are gone by now, so every
-                // owned position takes the exact check, in place
-                for (uint32_t jt = et; jt < own_in_tile; jt += KJ_ETHREADS) {
-                    kj_verify_candidate(a, m, tile_off, tile_voff, jt, 0u, n_emit);
-                    if (a.n_strands > 1) kj_verify_candidate(a, m, tile_off, tile_voff, jt, 1u, n_emit);
-                }
-            }
-            kj_nbar_arrive(KJ_NB_EMPTY + b, KJ_ETHREADS + KJ_STHREADS);
-            b = (b + 1u == KJ_SLOTS) ? 0u : b + 1u;
-        }
-        if (blk_base != KJ_REC_NONE)               // unused tail of the last block
-            for (uint32_t i = blk_used + (tid & 31); i < KJ_REC_BLOCK; i += 32) a.cand[KJ_REC_WORDS * (blk_base + i)] = KJ_REC_NONE;
-        for (int d = 16; d > 0; d >>= 1) {       // one atomic per warp
-            n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
-            n_bases += __shfl_xor_sync(0xFFFFFFFFu, n_bases, d);
-        }
-        if ((tid & 31) == 0) {
-            if (n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);
-            if (n_bases) atomicAdd(&a.ctr->n_bases, (unsigned long long)n_bases);
-        }
-        return;
-    }
-
-    // ---------------------------------------------------------------------- stream warps
-    const uint32_t st = tid - KJ_CTHREADS;
-    uint32_t ph_load = 0;                           // phase parity of the copy in flight
-    uint32_t handed = 0;                            // bit s: slot s has been handed over and not waited for yet
-    uint32_t cseq = 0;                              // commands sent to the control warp
-    auto wait_slot_free = [&](uint32_t sl) {
-        if (handed & (1u << sl)) {
-            kj_nbar_sync(KJ_NB_EMPTY + sl, KJ_ETHREADS + KJ_STHREADS);
-            handed &= ~(1u << sl);
-        }
-    };
-    auto next_slot = [](uint32_t sl) { return (sl + 1u == KJ_SLOTS) ? 0u : sl + 1u; };
-    // P1 of `tile` into codes / m; publishes the ticket taken ahead (t_ahead, thread st == 0) and
-    // re-arms the copies.  Ends synchronised.
-    auto convert = [&](uint32_t tile, KjTileSmem &m, uint32_t t_ahead) {
-        if (st == 0) m.q_n = 0;
-        const uint64_t off = (uint64_t)tile * KJ_TILE_BYTES;
-        if (any_staged && off <= staged_end) {
-            kj_bar_wait(&bar_load[0], ph_load);
-            kj_tile_p1_stage<KJ_STHREADS, 0>(codes, m, stage, st);
-            kj_sync_stream();                              // first half of `stage` is free
-            if (st == 0) { tile_next = t_ahead; start_half(t_ahead, 0); }
-            kj_bar_wait(&bar_load[1], ph_load);
-            ph_load ^= 1u;
-            kj_tile_p1_stage<KJ_STHREADS, 1>(codes, m, stage, st);
-            kj_sync_stream();                              // second half is free
-            if (st == 0) start_half(t_ahead, 1);
-        } else {
-            kj_tile_p1_global<KJ_STHREADS>(a, codes, m, tile, st);
-            kj_sync_stream();
-            if (st == 0) { tile_next = t_ahead; start_half(t_ahead, 0); start_half(t_ahead, 1); }
-        }
-    };
-    auto send_cmd = [&](uint32_t lb_tile, uint32_t lb_slot, uint32_t scan_tile, uint32_t scan_slot) {   // stream warp 0
-        const uint32_t kk = cseq % KJ_SLOTS;
-        if (st == 0) {
-            ctl[kk].lb_tile = lb_tile; ctl[kk].lb_slot = lb_slot;
-            ctl[kk].scan_tile = scan_tile; ctl[kk].scan_slot = scan_slot;
-        }
-        __syncwarp();
-        kj_nbar_arrive(KJ_NB_CTL + kk, 32 + KJ_CTHREADS);
-    };
-
-    uint32_t cur = tile_next, b = 0;
-    if (cur < a.n_tiles) {
-        {
-            uint32_t t_ahead = 0;
-            if (st == 0) t_ahead = atomicAdd(&a.ctr->ticket, 1u);
-            convert(cur, meta[0], t_ahead);
-        }
-        if (st < 32) send_cmd(KJ_NO_TILE, 0, cur, 0);
-        ++cseq;
-        for (;;) {
-            // the ticket after the next one is requested now: the round trip of the atomic hides behind the
-            // search instead of holding up the barrier in convert()
-            uint32_t t_ahead = 0;
-            if (st == 0) t_ahead = atomicAdd(&a.ctr->ticket, 1u);
-            const uint64_t tile_off = (uint64_t)cur * KJ_TILE_BYTES;
-            const uint32_t own_in_tile =
-                (a.own_n - tile_off < KJ_TILE_BYTES) ? (uint32_t)(a.own_n - tile_off) : KJ_TILE_BYTES;
-            if (own_in_tile == KJ_TILE_BYTES) kj_tile_search<MP, RC, KJ_STHREADS, true>(a, codes, meta[b], queue[b], own_in_tile, st);
-            else kj_tile_search<MP, RC, KJ_STHREADS, false>(a, codes, meta[b], queue[b], own_in_tile, st);
-            kj_sync_stream();                              // code words of cur no longer needed; queue complete; ticket visible
-            const uint32_t nxt = tile_next;
-            const uint32_t nb = next_slot(b);
-            if (nxt < a.n_tiles) {
-                wait_slot_free(nb);                        // the emit warps may lag KJ_SLOTS - 1 tiles behind
-                convert(nxt, meta[nb], t_ahead);
-            }
-            if (st < 32) send_cmd(cur, b, nxt < a.n_tiles ? nxt : KJ_NO_TILE, nb);
-            ++cseq;
-            handed |= 1u << b;
-            if (nxt >= a.n_tiles) break;
-            cur = nxt;
-            b = nb;
-        }
-        b = next_slot(b);                                  // the slot after the last tile carries the stop mark
-    } else {
-        if (st < 32) send_cmd(KJ_NO_TILE, 0, KJ_NO_TILE, 0);
-    }
-    wait_slot_free(b);
-    if (st < 32) {       // stop mark for the emit warps, by the warp that would otherwise be the control warp's producer
-        if (st == 0) tile_of[b] = KJ_NO_TILE;
-        __syncwarp();
-        kj_nbar_arrive(KJ_NB_FULL + b, KJ_CTHREADS + KJ_ETHREADS);
-    }
 }
 
 // ----------------------------------------------------------------------------- dense kernel

@@ -1,0 +1,490 @@
+// kj_scan_warp.cuh -- the filter path (step = 1, 1 <= |prefix| <= k): the hot kernels of the library.
+//
+//   kj_warp_filter_kernel   every warp is its own pipeline, no warp ever waits for another one.  A warp
+//                           streams tiles of 31 rows x 128 bytes; the TMA engine brings 32 rows at a time
+//                           (one 2-D tensor-map copy with the 128-byte swizzle, SASS UTMALDG.2D) into the
+//                           warp's private ring of stages, so that every lane reads ITS OWN contiguous 128
+//                           bytes (8 chunks of 16) without bank conflicts: the code words of a lane's
+//                           neighbours in the stream are its own registers, and only the two words behind
+//                           its last chunk come from the next lane (two shuffles per 8 chunks; lane 31
+//                           converts the row behind the tile for lane 30 and owns nothing).
+//                           Per chunk: 2-bit code word, newline mask, bit-parallel search of the prefix and
+//                           of complement(prefix) in code space (lib/kmers.js:88-100,151-155 as an exact
+//                           superset filter).  Chunks with a candidate are queued in shared memory and
+//                           drained by the whole warp every few tiles as 16-byte entries
+//                           {chunk, '\n' before it in the tile, its '\n' mask, distance back to the last '\n',
+//                           candidate lanes}.  The tile's newline count goes to tile_cnt[]; nothing in this
+//                           kernel needs the number of lines before the tile.
+//   (exclusive scan of tile_cnt -> tile_excl, cub::DeviceScan; the record FSM of lib/kmers.js:151-163 is
+//    "line index mod 4" over the whole stream)
+//   kj_resolve_kernel       one thread per entry, the whole GPU: line index of every candidate = lines before
+//                           the launch + tile_excl + in-tile count -> keep iff 1 mod 4; first-seen ordinal;
+//                           exact check of the window's bytes and the hash-table update (kj_window_emit).
+//                           An emission that finds no slot marks its entry for a retry pass after the host
+//                           has grown the table: nothing is ever dropped, whatever the input looks like.
+#pragma once
+#include "kj_scan.cuh"
+
+#define KJ_WT_OWN_ROWS 31u
+#define KJ_WT_BYTES (KJ_WT_OWN_ROWS * 128u)      // 3968 bytes = 248 chunks owned by a tile
+#define KJ_WT_CHUNKS (KJ_WT_BYTES / 16u)
+#define KJ_WT_STAGE_BYTES 4096u                  // what one TMA copy brings: the tile and the row behind it
+#define KJ_WT_STAGES 2
+#define KJ_WT_RING 4u                            // tiles whose newline bitmaps stay in shared memory
+#define KJ_WT_QCAP 320u                          // queue entries per warp; a tile adds at most 256
+#define KJ_WT_WARPS 8
+#define KJ_WT_THREADS (KJ_WT_WARPS * 32)
+#define KJ_ENT_RETRY (1ull << 63)
+#define KJ_ENT_NODIST 0xFFFFu
+
+struct __align__(16) KjWarpSmem {
+    uint4 bitmap[KJ_WT_RING][32];                // lane l: the '\n' masks of its 8 chunks, 16 bits each, in stream order
+    uint32_t lanepre[KJ_WT_RING][32];            // '\n' of the tile before lane l's first byte
+    uint32_t qz[KJ_WT_QCAP];                     // candidate lanes of a chunk (bit 2p: forward window at byte p, 2p + 1: reverse)
+    uint16_t qloc[KJ_WT_QCAP];                   // ring slot << 8 | lane << 3 | chunk of the lane
+    uint32_t qn;
+    uint32_t pad_[3];
+};
+#define KJ_WT_SMEM_BYTES (KJ_WT_WARPS * KJ_WT_STAGES * KJ_WT_STAGE_BYTES + KJ_WT_WARPS * KJ_WT_STAGES * 8 + \
+                          KJ_WT_WARPS * sizeof(KjWarpSmem) + 1024)
+
+// ----------------------------------------------------------------------------- TMA tensor copy
+#ifdef KJ_CPU_EMU
+struct KjTensorMap { const uint8_t *base; uint64_t rows; };      // tools/cuemu: rows of 128 readable bytes
+__device__ __forceinline__ void kj_tma_tile(void *dst, const KjTensorMap *tm, uint32_t row, uint64_t *bar) {
+    uint8_t *d = reinterpret_cast<uint8_t *>(dst);
+    for (uint32_t r = 0; r < 32; ++r)
+        for (uint32_t c = 0; c < 8; ++c) {
+            uint8_t *to = d + r * 128u + ((c ^ (r & 7u)) << 4);            // the 128-byte swizzle
+            if ((uint64_t)row + r < tm->rows) memcpy(to, tm->base + ((uint64_t)row + r) * 128u + c * 16u, 16);
+            else memset(to, 0, 16);                                          // out of bounds reads as zero
+        }
+    kj_bar_arrive(bar);
+}
+__device__ __forceinline__ uint4 kj_lds128(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+typedef const uint8_t *kj_saddr;
+__device__ __forceinline__ kj_saddr kj_saddr_of(const void *p) { return reinterpret_cast<const uint8_t *>(p); }
+__device__ __forceinline__ uint32_t kj_atoms_inc(uint32_t *p) { return atomicAdd(p, 1u); }
+#else
+#include <cuda.h>
+typedef CUtensorMap KjTensorMap;
+// one thread: announce the bytes on the barrier, start the copy of rows [row, row + 32) of the tensor
+__device__ __forceinline__ void kj_tma_tile(void *dst, const KjTensorMap *tm, uint32_t row, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(kj_smem_u32(bar)), "r"(KJ_WT_STAGE_BYTES) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(kj_smem_u32(dst)), "l"(tm), "r"(0), "r"(row), "r"(kj_smem_u32(bar)) : "memory");
+}
+typedef uint32_t kj_saddr;
+__device__ __forceinline__ kj_saddr kj_saddr_of(const void *p) { return kj_smem_u32(p); }
+__device__ __forceinline__ uint4 kj_lds128(kj_saddr a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+// plain ATOMS: the compiler's warp-aggregated form of atomicAdd costs more than it saves with one or two active lanes
+__device__ __forceinline__ uint32_t kj_atoms_inc(uint32_t *p) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(kj_smem_u32(p)) : "memory");
+    return old;
+}
+#endif
+
+// newline mask of 16 bytes with the two constants of the zero-byte test held in registers: (w ^ a) & b is
+// then ONE LOP3 (with immediates the compiler needs two, an immediate operand being 32 bits per instruction)
+__device__ __forceinline__ uint32_t kj_nl_flags_r(uint32_t w, uint32_t c0a, uint32_t c7f) {
+    const uint32_t t = ((w ^ c0a) & c7f) + c7f;
+    return ~(t | w) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t kj_nl16_r(const uint4 v, uint32_t c0a, uint32_t c7f) {
+#if defined(__CUDA_ARCH__)
+    uint32_t lo = __dp4a(kj_nl_flags_r(v.x, c0a, c7f), 0x08040201u, 0u);
+    lo = __dp4a(kj_nl_flags_r(v.y, c0a, c7f), 0x80402010u, lo);
+    uint32_t hi = __dp4a(kj_nl_flags_r(v.z, c0a, c7f), 0x08040201u, 0u);
+    hi = __dp4a(kj_nl_flags_r(v.w, c0a, c7f), 0x80402010u, hi);
+    return (lo >> 7) | ((hi << 1) & 0xFF00u);
+#else
+    (void)c0a; (void)c7f;
+    return kj_nl16(v.x, v.y, v.z, v.w);
+#endif
+}
+
+// candidate lanes of one chunk from its code word and the two behind it
+template <int MP, int RC>
+__device__ __forceinline__ uint32_t kj_chunk_lanes(const KjScanArgs &a, uint32_t c0, uint32_t c1, uint32_t c2) {
+    uint32_t accf = 0, accr = 0;
+#pragma unroll
+    for (int i = 0; i < MP; ++i) {
+        accf |= kj_funnel_r(c0, c1, 2u * i) ^ a.pat_f[i];
+        accr |= kj_rc_lanes<RC>(c0, c1, c2, a.rc_shift + i) ^ a.pat_r[i];
+    }
+    const uint32_t zf = kj_zero_lanes(accf);
+    const uint32_t zr = a.n_strands > 1 ? kj_zero_lanes(accr) : 0u;
+    return zf | (zr << 1);
+}
+
+// ----------------------------------------------------------------------------- drain
+
+// The whole warp turns its queue into entries in global memory, one entry per lane and round.
+static __device__ __noinline__ void kj_wt_drain(const KjScanArgs &a, KjWarpSmem &ws, uint32_t t_cur, uint32_t slot_cur,
+                                                uint32_t G) {
+    const uint32_t lane = threadIdx.x & 31;
+    __syncwarp();
+    const uint32_t n = ws.qn < KJ_WT_QCAP ? ws.qn : KJ_WT_QCAP;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t e = base + lane;
+        bool keep = false;
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (e < n) {
+            const uint32_t z = ws.qz[e], loc = ws.qloc[e];
+            const uint32_t slot = loc >> 8, src = (loc >> 3) & 31u, i = loc & 7u;
+            if (src != 31u) {                                       // lane 31 converts the row behind the tile: not owned
+                keep = true;
+                const uint32_t age = (slot_cur - slot) & (KJ_WT_RING - 1u);
+                const uint32_t tile = t_cur - age * G;
+                const uint4 bm = ws.bitmap[slot][src];
+                const uint32_t w[4] = {bm.x, bm.y, bm.z, bm.w};
+                // bits of the lane's 128 below chunk i
+                uint32_t before = 0, hi_w = 0, hi_j = 0;
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j) {
+                    const uint32_t lim = i * 16u;
+                    const uint32_t m = (j * 32u + 32u <= lim) ? 0xFFFFFFFFu : ((j * 32u < lim) ? 0xFFFFu : 0u);
+                    const uint32_t x = w[j] & m;
+                    before += __popc(x);
+                    if (x) { hi_w = x; hi_j = j; }
+                }
+                uint32_t dist = KJ_ENT_NODIST;
+                if (hi_w) {
+                    dist = i * 16u - (hi_j * 32u + (31u - __clz(hi_w)) + 1u);
+                } else {
+                    for (int l = (int)src - 1; l >= 0; --l) {       // the lanes before it, nearest first
+                        const uint4 b2 = ws.bitmap[slot][l];
+                        const uint32_t v[4] = {b2.x, b2.y, b2.z, b2.w};
+                        int jj = -1;
+                        for (int j = 3; j >= 0; --j) if (v[j]) { jj = j; break; }
+                        if (jj >= 0) {
+                            dist = (src - (uint32_t)l) * 128u + i * 16u - ((uint32_t)jj * 32u + (31u - __clz(v[jj])) + 1u);
+                            break;
+                        }
+                    }
+                }
+                const uint32_t nlmask = (w[i >> 1] >> ((i & 1u) * 16u)) & 0xFFFFu;
+                const uint64_t chunk = (uint64_t)tile * KJ_WT_CHUNKS + src * 8u + i;
+                const uint64_t word = chunk | ((uint64_t)(ws.lanepre[slot][src] + before) << 40);
+                rec = make_uint4((uint32_t)word, (uint32_t)(word >> 32), z, nlmask | (dist << 16));
+            }
+        }
+        const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
+        if (kb) {
+            unsigned long long at = 0;
+            if (lane == 0) at = atomicAdd(&a.ctr->n_cand, (unsigned long long)__popc(kb));
+            at = __shfl_sync(0xFFFFFFFFu, at, 0);
+            at += __popc(kb & ((1u << lane) - 1u));
+            if (keep && at < a.cand_cap) reinterpret_cast<uint4 *>(a.cand)[at] = rec;    // beyond the buffer: the host sees n_cand and repeats the piece
+        }
+    }
+    __syncwarp();
+    if (lane == 0) ws.qn = 0;
+    __syncwarp();
+}
+
+// ----------------------------------------------------------------------------- scan kernel
+
+template <int MP, int RC>
+__global__ void __launch_bounds__(KJ_WT_THREADS, 2)
+kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_constant__ KjScanArgs a) {
+    KJ_DYN_SMEM(dyn);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // [stages of all warps, 1024-byte aligned: the swizzle is a function of the shared-memory address][barriers][per-warp state]
+    uint8_t *base = dyn + ((1024u - (uint32_t)(reinterpret_cast<uintptr_t>(dyn) & 1023u)) & 1023u);
+    uint8_t *stage = base + (size_t)warp * KJ_WT_STAGES * KJ_WT_STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)KJ_WT_WARPS * KJ_WT_STAGES * KJ_WT_STAGE_BYTES) + warp * KJ_WT_STAGES;
+    KjWarpSmem &ws = *(reinterpret_cast<KjWarpSmem *>(base + (size_t)KJ_WT_WARPS * KJ_WT_STAGES * (KJ_WT_STAGE_BYTES + 8)) + warp);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < KJ_WT_STAGES; ++s) kj_bar_init(&bars[s], 1);
+#if defined(__CUDA_ARCH__)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+        ws.qn = 0;
+    }
+    __syncwarp();
+    const uint32_t G = gridDim.x * KJ_WT_WARPS, g = blockIdx.x * KJ_WT_WARPS + warp;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < KJ_WT_STAGES; ++s) {
+            const uint64_t t = (uint64_t)g + (uint64_t)s * G;
+            if (t < a.n_fast) kj_tma_tile(stage + s * KJ_WT_STAGE_BYTES, &tmap, (uint32_t)t * KJ_WT_OWN_ROWS, &bars[s]);
+        }
+    }
+    // a lane reads chunk i of its row at (i ^ (row & 7)): what the 128-byte swizzle made of it
+    kj_saddr off[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) off[i] = kj_saddr_of(stage) + lane * 128u + (((uint32_t)i << 4) ^ ((lane & 7u) << 4));
+    uint32_t c0a = 0x0A0A0A0Au, c7f = 0x7F7F7F7Fu;
+#if defined(__CUDA_ARCH__)
+    asm volatile("mov.u32 %0, 0x0A0A0A0A;" : "=r"(c0a));             // opaque to the optimiser: stays a register operand
+    asm volatile("mov.u32 %0, 0x7F7F7F7F;" : "=r"(c7f));
+#endif
+    uint32_t phase = 0, it = 0;
+    uint64_t t = g;
+    while (t < a.n_tiles) {
+#pragma unroll
+        for (int s = 0; s < KJ_WT_STAGES; ++s) {
+            if (t >= a.n_tiles) break;
+            const uint32_t slot = it & (KJ_WT_RING - 1u);
+            // room for everything this tile can add (256 entries)
+            if (ws.qn + 256u > KJ_WT_QCAP) kj_wt_drain(a, ws, (uint32_t)t - G, (slot - 1u) & (KJ_WT_RING - 1u), G);
+            uint32_t cw[10], nlp[4];
+            const bool fast = t < a.n_fast;
+            if (fast) {
+                kj_bar_wait(&bars[s], (phase >> s) & 1u);
+                phase ^= 1u << s;
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    const uint4 v0 = kj_lds128(off[i] + s * KJ_WT_STAGE_BYTES), v1 = kj_lds128(off[i + 1] + s * KJ_WT_STAGE_BYTES);
+                    cw[i] = kj_pack16(v0.x, v0.y, v0.z, v0.w);
+                    cw[i + 1] = kj_pack16(v1.x, v1.y, v1.z, v1.w);
+                    nlp[i >> 1] = kj_nl16_r(v0, c0a, c7f) | (kj_nl16_r(v1, c0a, c7f) << 16);
+                }
+                __syncwarp();                                        // every lane has read the stage
+                if (lane == 0) {
+                    const uint64_t tn = t + (uint64_t)KJ_WT_STAGES * G;
+                    if (tn < a.n_fast) kj_tma_tile(stage + s * KJ_WT_STAGE_BYTES, &tmap, (uint32_t)tn * KJ_WT_OWN_ROWS, &bars[s]);
+                }
+                cw[8] = __shfl_down_sync(0xFFFFFFFFu, cw[0], 1);
+                cw[9] = __shfl_down_sync(0xFFFFFFFFu, cw[1], 1);
+            } else {
+                // edge tiles (the last one or two of a launch): bounds-checked loads straight from global memory,
+                // newlines and window starts clipped to the owned range
+                const uint64_t lo = t * KJ_WT_BYTES + lane * 128u;
+#pragma unroll 1
+                for (int i = 0; i < 10; ++i) {
+                    const uint64_t o = lo + (uint32_t)i * 16u;
+                    const uint4 v = (o < a.n) ? kj_load_chunk(a.buf, o, a.n) : make_uint4(0, 0, 0, 0);
+                    const uint32_t c = kj_pack16(v.x, v.y, v.z, v.w);
+                    uint32_t m = kj_nl16(v.x, v.y, v.z, v.w);
+                    if (o >= a.own_n) m = 0;
+                    else if (o + 16 > a.own_n) m &= (1u << (uint32_t)(a.own_n - o)) - 1u;
+                    // (dynamic register indexing would spill: a select chain keeps the arrays in registers)
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) if (j == i) cw[j] = c;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (i == 2 * j) nlp[j] = m;
+                        if (i == 2 * j + 1) nlp[j] |= m << 16;
+                    }
+                }
+            }
+            // newline bookkeeping: the lane's masks, '\n' before the lane inside the tile, the tile's count
+            ws.bitmap[slot][lane] = make_uint4(nlp[0], nlp[1], nlp[2], nlp[3]);
+            const uint32_t cnt = __popc(nlp[0]) + __popc(nlp[1]) + __popc(nlp[2]) + __popc(nlp[3]);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if ((int)lane >= d) incl += o;
+            }
+            ws.lanepre[slot][lane] = incl - cnt;
+            if (lane == KJ_WT_OWN_ROWS - 1u) a.tile_cnt[t] = incl;     // the 31 owned rows
+            // search
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t z = kj_chunk_lanes<MP, RC>(a, cw[i], cw[i + 1], cw[i + 2]);
+                if (!fast) {
+                    const uint64_t o = t * KJ_WT_BYTES + lane * 128u + (uint32_t)i * 16u;
+                    if (o >= a.own_n) z = 0;
+                    else if (o + 16 > a.own_n) z &= (1u << (2u * (uint32_t)(a.own_n - o))) - 1u;
+                }
+                if (z) {
+                    const uint32_t q = kj_atoms_inc(&ws.qn);
+                    if (q < KJ_WT_QCAP) { ws.qz[q] = z; ws.qloc[q] = (uint16_t)((slot << 8) | (lane << 3) | (uint32_t)i); }
+                }
+            }
+            __syncwarp();
+            // the ring keeps KJ_WT_RING tiles: drain when it is full (and at the end)
+            if (slot == KJ_WT_RING - 1u || t + G >= a.n_tiles) kj_wt_drain(a, ws, (uint32_t)t, slot, G);
+            t += G;
+            ++it;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- resolve kernel
+
+// status of one candidate window
+#define KJ_EMIT_NONE 0       // not an emission (prefix bytes differ, crosses the end of the line, ...)
+#define KJ_EMIT_OK 1
+#define KJ_EMIT_FULL 2       // the table has no slot within the probe limit: retry after the host has grown it
+
+template <int KW>
+__device__ __forceinline__ int kj_window_try(const KjScanArgs &a, uint64_t j, uint32_t strand, uint64_t ord,
+                                             const uint4 v0, const uint4 v1, const uint4 v2) {
+    const uint32_t k = a.k;
+    const uint32_t o = (uint32_t)(j & 15u);
+    const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+    const uint32_t q = o >> 2, r8 = (o & 3u) * 8u;
+    uint32_t X[KW];
+#pragma unroll
+    for (int i = 0; i < KW; ++i) {
+        const uint32_t lo = q == 0 ? W[i] : q == 1 ? W[i + 1] : q == 2 ? W[i + 2] : W[i + 3];
+        const uint32_t hi = q == 0 ? W[i + 1] : q == 1 ? W[i + 2] : q == 2 ? W[i + 3] : W[i + 4];
+        X[i] = kj_funnel_r(lo, hi, r8);
+    }
+    uint32_t bad = 0, nl = 0, irr = 0, p_lo = 0, p_hi = 0;
+#pragma unroll
+    for (int i = 0; i < KW; ++i) {
+        if (4u * i < k) {
+            const uint32_t bm = (4u * i + 4u <= k) ? 0xFFFFFFFFu : ((1u << (8u * (k - 4u * i))) - 1u);   // bytes of the window
+            bad |= (X[i] ^ a.want[strand][i]) & a.wmask[strand][i];
+            nl |= kj_nl_msb4(X[i]) & bm;
+            irr |= kj_not_acgt4(X[i]) & bm;
+            const uint32_t c8 = kj_pack4(X[i] & bm);
+            if (i < 4) p_lo |= c8 << (8 * i); else p_hi |= c8 << (8 * (i - 4));
+        }
+    }
+    if (nl | bad) return KJ_EMIT_NONE;                    // crosses the end of the line / prefix bytes differ
+    if (k == 1 && a.line_gate) {                          // lib/kmers.js:151  line.length > 1: a lone byte is not processed
+        const bool first = j == 0 ? (a.ctr->carry_last[a.parity] == a.voff) : (a.buf[j - 1] == '\n');
+        const bool more = (j + 1 < a.n) && a.buf[j + 1] != '\n';
+        if (first && !more) return KJ_EMIT_NONE;
+    }
+    const uint64_t P = ((uint64_t)p_hi << 32) | p_lo;     // code of window byte i at bits 2i
+    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    if (!irr) {
+        // forward key: first base most significant; reverse key: complement codes, last base first
+        const uint64_t key = strand ? ((P ^ 0xAAAAAAAAAAAAAAAAull) & kmask) : (kj_pairrev64(P) >> (64u - 2u * k));
+        return kj_insert(a.tab, a.ctr, key, ord, 1) ? KJ_EMIT_OK : KJ_EMIT_FULL;
+    }
+    __align__(8) uint8_t key32[32];
+    kj_window_bytes(a.buf, j, k, strand, key32);
+    return kj_insert_irr(a.irr, a.ctr, key32, k, ord, 1) ? KJ_EMIT_OK : KJ_EMIT_FULL;
+}
+
+// every candidate of one entry; returns the lanes that found no table slot
+template <int KW>
+__device__ __forceinline__ uint32_t kj_resolve_entry(const KjScanArgs &a, const uint4 rec, uint64_t base_lines, uint32_t &n_emit) {
+    const uint64_t word = ((uint64_t)rec.y << 32) | rec.x;
+    const uint64_t chunk = word & ((1ull << 40) - 1ull);
+    const uint32_t nlb = (uint32_t)(word >> 40) & 0x1FFFu;
+    const uint32_t nlmask = rec.w & 0xFFFFu, dist = rec.w >> 16;
+    const uint64_t tile = chunk / KJ_WT_CHUNKS;
+    const uint64_t line0 = base_lines + a.tile_excl[tile] + nlb;
+    uint32_t lanes = rec.z, failed = 0;
+    while (lanes) {
+        const uint32_t bit = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
+        const uint32_t p = bit >> 1, strand = bit & 1u;
+        const uint64_t j = chunk * 16u + p;
+        if (j + a.k > a.n) continue;                          // the window must lie inside the stream
+        const uint32_t below = nlmask & ((1u << p) - 1u);
+        const uint64_t line = line0 + __popc(below);
+        if ((line & 3ull) != 1ull) continue;                  // lib/kmers.js:151  i === 1
+        uint64_t ord = 0;
+        if (a.order || a.k == 1) {
+            unsigned long long start;                         // first byte of the line (virtual offset)
+            if (below) start = a.voff + chunk * 16u + (31u - __clz(below)) + 1ull;
+            else if (dist != KJ_ENT_NODIST) start = a.voff + chunk * 16u - dist;
+            else start = kj_line_start_global(a, tile * KJ_WT_BYTES);
+            const uint64_t col = a.voff + j - start;
+            if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); continue; }
+            const uint64_t read_idx = line >> 2;
+            if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); continue; }
+            // forward emissions in ascending column, then reverse emissions in descending column
+            ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
+        }
+        uint4 v0, v1, v2;
+        kj_window_load(a, j, v0, v1, v2);
+        const int st = kj_window_try<KW>(a, j, strand, ord, v0, v1, v2);
+        if (st == KJ_EMIT_OK) ++n_emit;
+        else if (st == KJ_EMIT_FULL) failed |= 1u << bit;
+    }
+    return failed;
+}
+
+// a.resolve_retry == 0: every entry; != 0: the entries an earlier pass marked (their z holds the lanes left over).
+// Block 0 also closes the stream state of the launch (lines and last '\n' so far) for the next one.
+template <int KW>
+__global__ void __launch_bounds__(256) kj_resolve_kernel(const __grid_constant__ KjScanArgs a) {
+    const unsigned long long n_ent = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;
+    const uint64_t base_lines = a.ctr->carry_lines[a.parity];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !a.resolve_retry && a.n_tiles) {
+        a.ctr->carry_lines[a.parity ^ 1] = base_lines + a.tile_excl[a.n_tiles - 1] + a.tile_cnt[a.n_tiles - 1];
+        a.ctr->carry_last[a.parity ^ 1] = kj_line_start_global(a, a.own_n);
+    }
+    if (a.ctr->n_cand > a.cand_cap) return;                   // the entry buffer was too small: nothing is touched, the host repeats the piece
+    uint32_t n_emit = 0, n_fail = 0;
+    uint4 *ent = reinterpret_cast<uint4 *>(a.cand);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_ent; i += stride) {
+        uint4 rec = ent[i];
+        const bool marked = (rec.y >> 31) != 0;
+        if (a.resolve_retry && !marked) continue;
+        rec.y &= 0x7FFFFFFFu;
+        const uint32_t failed = kj_resolve_entry<KW>(a, rec, base_lines, n_emit);
+        if (failed) {
+            ++n_fail;
+            ent[i] = make_uint4(rec.x, rec.y | 0x80000000u, failed, rec.w);
+        } else if (marked) {
+            ent[i] = make_uint4(rec.x, rec.y, 0u, rec.w);
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);
+        n_fail += __shfl_xor_sync(0xFFFFFFFFu, n_fail, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_emit) atomicAdd(&a.ctr->n_occ, (unsigned long long)n_emit);
+        if (n_fail) atomicAdd(&a.ctr->n_overflow, (unsigned long long)n_fail);
+    }
+}
+
+// ----------------------------------------------------------------------------- KJ_F_COUNT_BASES
+
+// Sum of the lengths of the sequence lines (index 1 mod 4): a '\n' that ends such a line adds its offset, one
+// that ends the line before it subtracts offset + 1; the sums telescope over tiles and launches and the host
+// closes the two ends of the stream (kj_counts_finish).  A second pass over the input, one warp per tile: the
+// statistic is not part of the reference and off by default.
+__global__ void __launch_bounds__(256) kj_bases_kernel(const __grid_constant__ KjScanArgs a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t base_lines = a.ctr->carry_lines[a.parity];
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    long long sum = 0;
+    for (uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < a.n_tiles; t += warps) {
+        uint32_t m[8], cnt = 0;
+        const uint64_t lo = t * KJ_WT_BYTES + lane * 128u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint64_t o = lo + (uint32_t)i * 16u;
+            m[i] = 0;
+            if (lane < KJ_WT_OWN_ROWS && o < a.own_n) {
+                const uint4 v = kj_load_chunk(a.buf, o, a.n);
+                m[i] = kj_nl16(v.x, v.y, v.z, v.w);
+                if (o + 16 > a.own_n) m[i] &= (1u << (uint32_t)(a.own_n - o)) - 1u;
+            }
+            cnt += __popc(m[i]);
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((int)lane >= d) incl += o;
+        }
+        uint64_t line = base_lines + a.tile_excl[t] + (incl - cnt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t mk = m[i];
+            const long long at = (long long)(a.voff + lo + (uint32_t)i * 16u);
+            while (mk) {
+                const uint32_t bit = __ffs(mk) - 1; mk &= mk - 1;
+                const uint32_t ph = (uint32_t)line & 3u;
+                if (ph == 1u) sum += at + bit;
+                else if (ph == 0u) sum -= at + bit + 1;
+                ++line;
+            }
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if (lane == 0 && sum) atomicAdd(&a.ctr->n_bases, (unsigned long long)sum);
+}

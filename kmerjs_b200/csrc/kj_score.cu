@@ -80,6 +80,7 @@ struct kj_match {
     unsigned long long *d_tcur = nullptr;
     uint32_t *d_tq = nullptr;
     KjWtaResult *d_res = nullptr, *h_res = nullptr;
+    void *d_loop = nullptr;          // kj_wta_loop_kernel: {records, status} + one KjWtaResult per round
     bool committed = false;
     bool distributed = false;        // d_glob is separate and maintained by the host layer
     std::vector<uint64_t> u0, t0;    // first-round scores (lib/kmerFinderClient.js:44-46)
@@ -400,6 +401,133 @@ __global__ void kj_remove_kernel(KjDbDev d, const uint32_t *tq, uint64_t lo, uin
     if (lane == 0 && gone) atomicAdd((unsigned long long *)&part[2 * (uint64_t)T], 0ull - gone);
 }
 
+// The whole findMatches loop (lib/kmerFinderClient.js:273-286) on the device: one CTA runs argmax -> gate ->
+// removal round after round and appends {winner, u, tau, H, z, p} per round to `res`; the host waits once and
+// finishes the rows in exact decimal arithmetic.  The gate is the double-precision one of kj_argmax_kernel: the
+// loop stops BEFORE the removal at the first round whose z is within 1e-6 of a fastp threshold (or whose
+// p * templates is within 1e-9 of the evalue) -- the exact arithmetic decides that round on the host and the
+// loop is resumed.  Scores are changed by atomics (L2) and read back with volatile loads.
+struct KjWtaLoopArgs {
+    KjDbDev d;
+    uint64_t *glob;               // u[T], tau[T], H  (== part on one GPU / in a gathered match)
+    const uint32_t *rank;
+    const uint64_t *ulen;
+    const uint64_t *toff;
+    const uint32_t *tq, *qkmer;
+    const uint64_t *qcount;
+    uint8_t *alive;
+    uint32_t T;
+    uint32_t max_rounds;          // rounds this launch may accept
+    double unique_lens, n_templates;
+    KjWtaResult *res;             // max_rounds + 1 records
+    uint32_t *head;               // {records written, status}
+};
+enum { KJ_LOOP_MORE = 0,          // max_rounds accepted: the caller decides whether maxHits is reached
+       KJ_LOOP_NO_HITS = 1,       // nHits === 0 / no template left (last record is not a row)
+       KJ_LOOP_REJECTED = 2,      // the gate rejected the winner away from every threshold (last record is not a row)
+       KJ_LOOP_UNDECIDED = 3 };   // the last record's winner has NOT been removed: exact arithmetic decides
+
+__device__ __forceinline__ bool kj_gate_decisive(double z, double p) {
+    const double thr[27] = {10.7016, 10.4862, 10.2663, 10.0416, 9.81197, 9.5769, 9.33604, 9.08895, 8.83511,
+                            8.57394, 8.30479, 8.02686, 7.73926, 7.4409,  7.13051, 6.8065,  6.46695, 6.10941,
+                            5.73073, 5.32672, 4.89164, 4.41717, 3.89059, 3.29053, 2.57583, 1.95996, 1.64485};
+    if (!(z == z)) return false;
+    for (int i = 0; i < 27; ++i) if (fabs(z - thr[i]) <= 1e-6) return false;
+    if (fabs(p - 0.05) <= 1e-9) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(1024) kj_wta_loop_kernel(const KjWtaLoopArgs a) {
+    __shared__ unsigned long long s_best[32];
+    __shared__ uint32_t s_who[32];
+    __shared__ uint32_t s_winner, s_go;
+    __shared__ unsigned long long s_gone[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t n_rec = 0, status = KJ_LOOP_MORE;
+    for (uint32_t round = 0; round < a.max_rounds; ++round) {
+        // winner = argmax over (uScore desc, first-encounter rank asc)
+        unsigned long long best = 0;
+        uint32_t who = KJ_NONE32;
+        for (uint32_t t = threadIdx.x; t < a.T; t += blockDim.x) {
+            const uint64_t u = kj_ld_volatile(&a.glob[t]);
+            if (!u) continue;
+            const unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(~a.rank[t]);
+            if (key > best) { best = key; who = t; }
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
+            const uint32_t ow = __shfl_xor_sync(0xFFFFFFFFu, who, d);
+            if (ob > best) { best = ob; who = ow; }
+        }
+        if (lane == 0) { s_best[warp] = best; s_who[warp] = who; }
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < nw ? s_best[lane] : 0ull;
+            who = lane < nw ? s_who[lane] : KJ_NONE32;
+            for (int d = 16; d > 0; d >>= 1) {
+                const unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
+                const uint32_t ow = __shfl_xor_sync(0xFFFFFFFFu, who, d);
+                if (ob > best) { best = ob; who = ow; }
+            }
+            if (lane == 0) {
+                KjWtaResult r;
+                r.winner = who; r.pad = 0;
+                r.hits = kj_ld_volatile(&a.glob[2 * (uint64_t)a.T]);
+                r.u = 0; r.tau = 0; r.z = 0.0; r.p = 1.0;
+                uint32_t go = 0;
+                if (who == KJ_NONE32 || r.hits == 0) {
+                    status = KJ_LOOP_NO_HITS;
+                } else {
+                    r.u = kj_ld_volatile(&a.glob[who]);
+                    r.tau = kj_ld_volatile(&a.glob[(uint64_t)a.T + who]);
+                    r.z = kj_zscore_f64((double)r.u, (double)a.ulen[who], (double)r.hits, a.unique_lens);
+                    r.p = kj_fastp_f64(r.z) * a.n_templates;
+                    if (!kj_gate_decisive(r.z, r.p)) status = KJ_LOOP_UNDECIDED;
+                    else if (r.u > 0 && r.p <= 0.05) go = 1;
+                    else status = KJ_LOOP_REJECTED;
+                }
+                a.res[n_rec] = r;
+                s_winner = who;
+                s_go = go;
+            }
+        }
+        __syncthreads();
+        ++n_rec;
+        if (!s_go) break;
+        // removeWinnerKmers (lib/kmerFinderClient.js:220-230): one warp per matched entry of the winner
+        const uint32_t w = s_winner;
+        const uint64_t lo = a.toff[w], hi = a.toff[w + 1];
+        unsigned long long gone = 0;
+        for (uint64_t i = lo + warp; i < hi; i += nw) {
+            const uint32_t q = a.tq[i];
+            const uint8_t was = *reinterpret_cast<volatile uint8_t *>(&a.alive[q]);
+            __syncwarp();
+            if (!was) continue;
+            if (lane == 0) a.alive[q] = 0;
+            const uint32_t kid = a.qkmer[q];
+            const unsigned long long c = a.qcount[q];
+            const uint64_t l0 = a.d.list_off[kid], l1 = a.d.list_off[kid + 1];
+            if (lane == 0) gone += l1 - l0;
+            for (uint64_t j = l0 + lane; j < l1; j += 32) {
+                const uint32_t t = a.d.tmpl[j];
+                atomicAdd((unsigned long long *)&a.glob[t], ~0ull);                       // u[t] -= 1
+                atomicAdd((unsigned long long *)&a.glob[(uint64_t)a.T + t], 0ull - c);    // tau[t] -= count
+            }
+        }
+        if (lane == 0) s_gone[warp] = gone;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long g = 0;
+            for (uint32_t i = 0; i < nw; ++i) g += s_gone[i];
+            if (g) atomicAdd((unsigned long long *)&a.glob[2 * (uint64_t)a.T], 0ull - g);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { a.head[0] = n_rec; a.head[1] = status; }
+}
+
 // ------------------------------------------------------------------------------------ database
 
 static bool all_acgt(const uint8_t *p, uint32_t n) {
@@ -554,6 +682,7 @@ extern "C" void kj_match_free(kj_match *m) {
         kj_dfree(ctx, m->d_part);
         kj_dfree(ctx, m->d_first_ord); kj_dfree(ctx, m->d_first_idx); kj_dfree(ctx, m->d_rank);
         kj_dfree(ctx, m->d_toff); kj_dfree(ctx, m->d_tcur); kj_dfree(ctx, m->d_tq); kj_dfree(ctx, m->d_res);
+        kj_dfree(ctx, m->d_loop);
         kj_pinned_put(ctx, m->h_res);
     }
     delete m;
@@ -988,6 +1117,21 @@ extern "C" int kj_match_set_max_hits(kj_match *m, uint32_t max_hits) {
 
 // ------------------------------------------------------------------------------------ winner takes all
 
+// removeWinnerKmers (lib/kmerFinderClient.js:220-230) on this rank's share of K_w
+static int wta_launch_remove(kj_match *m, uint32_t w) {
+    kj_ctx *ctx = m->ctx;
+    const uint64_t range[2] = {m->toff_h[w], m->toff_h[w + 1]};
+    if (range[1] > range[0]) {
+        const uint64_t n = range[1] - range[0];
+        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8));
+        KJ_LAUNCH(kj_remove_kernel, grid, 256, 0, ctx->stream, m->d, m->d_tq, range[0], range[1], m->d_qkmer,
+                  m->qcount, m->alive, m->d_part, m->T);
+        ctx->launches++;
+        KJ_CUDA(ctx, cudaGetLastError());
+    }
+    return KJ_OK;
+}
+
 extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
     if (!m || !out) return KJ_E_INVALID;
     kj_ctx *ctx = m->ctx;
@@ -1009,19 +1153,7 @@ extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
         KJ_CUDA(ctx, cudaMemcpyAsync(m->h_res, m->d_res, sizeof(KjWtaResult), cudaMemcpyDeviceToHost, ctx->stream));
         return KJ_OK;
     };
-    // removeWinnerKmers (lib/kmerFinderClient.js:220-230) on this rank's share of K_w
-    auto launch_remove = [&](uint32_t w) -> int {
-        const uint64_t range[2] = {m->toff_h[w], m->toff_h[w + 1]};
-        if (range[1] > range[0]) {
-            const uint64_t n = range[1] - range[0];
-            const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8));
-            KJ_LAUNCH(kj_remove_kernel, grid, 256, 0, ctx->stream, m->d, m->d_tq, range[0], range[1], m->d_qkmer,
-                      m->qcount, m->alive, m->d_part, m->T);
-            ctx->launches++;
-            KJ_CUDA(ctx, cudaGetLastError());
-        }
-        return KJ_OK;
-    };
+    auto launch_remove = [&](uint32_t w) -> int { return wta_launch_remove(m, w); };
     int rc;
     if (!m->inflight) { rc = launch_argmax(); if (rc) return rc; }
     m->inflight = false;
@@ -1117,6 +1249,91 @@ extern "C" int kj_wta_row(kj_match *m, kj_row *out) {
     return 1;
 }
 
+// kj_wta_all on one GPU (or on a gathered match): the rounds run in kj_wta_loop_kernel, the host waits once per
+// launch and finishes the rows in exact decimal arithmetic; it steps in only for a round the double-precision
+// gate could not decide.
+static int wta_all_device(kj_match *m, kj_row *rows, uint32_t cap, uint32_t *n_rows, int *end_status) {
+    kj_ctx *ctx = m->ctx;
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t per_launch = 300;
+    const size_t res_bytes = (size_t)(per_launch + 1) * sizeof(KjWtaResult) + 16;
+    if (!ctx->h_wta) KJ_CUDA(ctx, cudaMallocHost(&ctx->h_wta, res_bytes));
+    if (!m->d_loop) KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_loop, res_bytes));
+    uint32_t *h_head = reinterpret_cast<uint32_t *>(ctx->h_wta);
+    const KjWtaResult *h_res = reinterpret_cast<const KjWtaResult *>(reinterpret_cast<uint8_t *>(ctx->h_wta) + 16);
+    uint32_t n = 0;
+    int status = 0;
+    auto exact = [&](const KjWtaResult &r, kj_row *out, int *accepted) -> int {
+        const uint32_t w = r.winner;
+        memset(out, 0, sizeof(*out));
+        if (!kj_exact_row(ctx->rounding_mode, r.u, r.tau, m->u0[w], m->t0[w], m->db->lengths[w], m->db->ulengths[w],
+                          r.hits, m->kmer_map_size, m->db->s_templates, m->db->s_unique_lens, out, accepted))
+            return kj_fail(ctx, KJ_E_INVALID, "template with zero length / ulength or zero Summary.uniqueLens");
+        out->template_id = w;
+        out->z_device = r.z;
+        out->probability_device = r.p;
+        return KJ_OK;
+    };
+    for (;;) {
+        // while (notFound && hitCounter < maxHits)   lib/kmerFinderClient.js:274
+        if (m->hit_counter >= m->max_hits) { m->ended = true; break; }
+        const uint32_t rounds = std::min<uint32_t>(per_launch, m->max_hits - m->hit_counter);
+        KjWtaLoopArgs a{};
+        a.d = m->d; a.glob = m->d_glob; a.rank = m->d_rank; a.ulen = m->db->d_ulen; a.toff = m->d_toff;
+        a.tq = m->d_tq; a.qkmer = m->d_qkmer; a.qcount = m->qcount; a.alive = m->alive;
+        a.T = m->T; a.max_rounds = rounds;
+        a.unique_lens = (double)m->db->s_unique_lens; a.n_templates = (double)m->db->s_templates;
+        a.head = reinterpret_cast<uint32_t *>(m->d_loop);
+        a.res = reinterpret_cast<KjWtaResult *>(reinterpret_cast<uint8_t *>(m->d_loop) + 16);
+        KJ_LAUNCH(kj_wta_loop_kernel, 1, 1024, 0, ctx->stream, a);
+        ctx->launches++;
+        KJ_CUDA(ctx, cudaGetLastError());
+        KJ_CUDA(ctx, cudaMemcpyAsync(ctx->h_wta, m->d_loop, 16 + (size_t)(rounds + 1) * sizeof(KjWtaResult),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const uint32_t n_rec = h_head[0], st = h_head[1];
+        const uint32_t n_acc = st == KJ_LOOP_MORE ? n_rec : n_rec - 1;
+        for (uint32_t i = 0; i < n_acc; ++i) {
+            int accepted = 0;
+            int rc = exact(h_res[i], &rows[n], &accepted);
+            if (rc) return rc;
+            if (!accepted)
+                return kj_fail(ctx, KJ_E_CUDA, "internal: device gate and exact-decimal gate disagree away from a threshold");
+            ++n;
+            m->hit_counter++;
+        }
+        if (st == KJ_LOOP_MORE) continue;
+        const KjWtaResult &last = h_res[n_rec - 1];
+        if (st == KJ_LOOP_NO_HITS) {
+            // getMatches: nHits === 0 throws (lib/kmerFinderClient.js:264-266), also after earlier winners
+            m->ended = true;
+            status = kj_fail(ctx, KJ_E_NO_HITS, "No hits were found! (nHits === 0)");
+            break;
+        }
+        kj_row tmp;
+        int accepted = 0;
+        int rc = exact(last, &tmp, &accepted);
+        if (rc) return rc;
+        if (st == KJ_LOOP_REJECTED && accepted)
+            return kj_fail(ctx, KJ_E_CUDA, "internal: device gate and exact-decimal gate disagree away from a threshold");
+        if (accepted) {                         // undecided on the device, accepted by the exact arithmetic
+            rows[n++] = tmp;
+            m->hit_counter++;
+            rc = wta_launch_remove(m, last.winner);
+            if (rc) return rc;
+            continue;
+        }
+        // findWinner returned undefined: notFound = false (lib/kmerFinderClient.js:214-217)
+        m->ended = true;
+        if (m->hit_counter == 0) status = kj_fail(ctx, KJ_E_NO_WINNER, "No hits were found! (kmerResults.length === 0)");
+        break;
+    }
+    (void)cap;
+    *n_rows = n;
+    *end_status = status;
+    return KJ_OK;
+}
+
 // The whole findMatches loop in one call: kj_wta_next until it ends, without a trip through the host
 // language per row.  Each round's exact-decimal row is finished while the device removes the winner's k-mers
 // and takes the next argmax (kj_wta_next launches both before it starts the arithmetic).  rows[0 .. *n_rows)
@@ -1130,6 +1347,8 @@ extern "C" int kj_wta_all(kj_match *m, kj_row *rows, uint32_t cap, uint32_t *n_r
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (!m->committed) return kj_fail(ctx, KJ_E_STATE, "kj_match_commit has not run");
     if (cap < m->max_hits) return kj_fail(ctx, KJ_E_RANGE, "row buffer smaller than maxHits");
+    if (!m->distributed && !m->inflight && !m->row_pending && !m->ended)
+        return wta_all_device(m, rows, cap, n_rows, end_status);
     const bool was_deferring = m->defer_rows;
     m->defer_rows = false;
     uint32_t n = 0;

@@ -132,13 +132,15 @@ def template_db_from_genome(genome: bytes, n_templates: int = 64, prefix: bytes 
 
 def genus_template_db(sample_keys: np.ndarray, n_templates: int = 10_000, per_template: int = 10_000,
                       genus_size: int = 20, identity: float = 0.7, overlap: float = 0.4,
-                      prefix: bytes = b"ATGAC", k: int = 16, seed: int = 11, relabel: bool = True):
+                      prefix: bytes = b"ATGAC", k: int = 16, seed: int = 11, relabel: bool = True,
+                      sample_share: float = 0.9):
     """BASELINE config 4's database: ``n_templates`` templates of about ``per_template``
     prefix-filtered k-mers each, in genera of ``genus_size`` templates that share a k-mer pool (a template
     holds each k-mer of its genus pool with probability ``identity``, so two templates of a genus are
     about ``identity`` alike); neighbouring genera overlap in a fraction ``overlap`` of their pools, so
-    k-mer lists mix genera.  Template 0 holds exactly ``sample_keys`` (2-bit packed keys, first base most
-    significant: the sample genome's own k-mers) and its genus the relatives of the sample.  Built in k-mer
+    k-mer lists mix genera.  Template 0 holds ``sample_share`` of ``sample_keys`` (2-bit packed keys, first base most
+    significant: the sample genome's own k-mers -- the sample is a strain of template 0, not template 0 itself, so
+    the winner-takes-all loop goes on to the relatives) and its genus the relatives of the sample.  Built in k-mer
     space, deterministic in ``seed``.  ``relabel`` permutes the template ids so that list order (ascending
     original id) is unrelated to the id.  Returns a TemplateDB."""
     from .db import TemplateDB
@@ -181,7 +183,7 @@ def genus_template_db(sample_keys: np.ndarray, n_templates: int = 10_000, per_te
         gs = min(genus_size, n_templates - g * genus_size)
         M = rng.random((gs, pool)) < identity
         if g == 0:
-            M[0, :] = np.arange(pool) < sample_keys.size           # the sample genome itself
+            M[0, :] = (np.arange(pool) < sample_keys.size) & (rng.random(pool) < sample_share)   # the sample's closest template
         cols, ts = np.nonzero(M.T)                                 # sorted by column, then template
         members.append((cols.astype(np.int64), (ts + g * genus_size).astype(np.uint32)))
         col_cnt[g] = M.sum(axis=0)

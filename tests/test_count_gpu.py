@@ -285,3 +285,50 @@ def test_size_independent_properties():
     cs = Counts(b"ATGAC", 16, 1)
     cs.add_host(sample).finish()
     assert (list(cs.to_dict().items()), cs.lines) == exp
+
+
+def test_n_dense_input_is_counted_without_limit():
+    """Reads over the alphabet ACGTN (20 % N): most prefix-passing k-mers are irregular (byte-string keys), far more
+    than any fixed side-table or spill-list size.  The reference counts them without a limit; so does every kernel
+    here, whatever the capacity hint (the filter path retries marked entries after growing the tables, the dense
+    and line kernels keep a piece's worst case of spills)."""
+    from util import emulated
+    rng = random.Random(77)
+    data = random_fastq(rng, 120 if emulated() else 3400, min_len=150, max_len=150, alphabet=b"ACGTN", plant=None, p_n=0.0)
+    for prefix, k in [(b"A", 20), (b"AT", 16)]:
+        exp = oracle(data, prefix, k, 1)
+        assert emulated() or len(exp[0]) > (60000 if prefix == b"A" else 15000)
+        for kw in (dict(), dict(capacity_hint=1 << 22), dict(device=True, capacity_hint=1 << 10)):
+            got, (occ, _, _) = gpu(data, prefix, k, 1, **kw)
+            assert got == exp, (prefix, k, kw)
+            assert occ == sum(v for _, v in exp[0])
+    exp = oracle(data, b"", 31, 1)
+    assert gpu(data, b"", 31, 1, capacity_hint=1 << 10)[0] == exp                               # dense kernel
+    assert gpu(data, b"A", 20, 1, flags=_abi.KJ_F_FORCE_GENERIC, capacity_hint=1 << 10)[0] == oracle(data, b"A", 20, 1)
+
+
+@pytest.mark.parametrize("extra", [1, 31, 32, 33, 100])
+def test_file_tail_shorter_than_the_halo(tmp_path, ctx, extra):
+    """readFile() on a file whose last bytes fall just past a staging-chunk boundary: a tail shorter than the
+    32-byte halo belongs to the piece before it (1 MiB staging chunks, file = 2 chunks + extra bytes)."""
+    from util import emulated
+    chunk = (1 << 18) if emulated() else (1 << 20)
+    ctx.set_stage_chunk(chunk)
+    try:
+        rng = random.Random(5000 + extra)
+        size = 2 * chunk + extra
+        data = random_fastq(rng, size // 250 + 50, min_len=100, max_len=140)[:size]
+        assert len(data) == size
+        path = tmp_path / "tail.fastq"
+        path.write_bytes(data)
+        c = Counts(b"ATGAC", 16, 1)
+        c.add_file(str(path)).finish()
+        assert (list(c.to_dict().items()), c.lines) == oracle(data)
+        assert c.bytes_read == size
+        c.free()
+        c = Counts(b"ATGAC", 16, 1)                  # the same bytes as a pageable host buffer
+        c.add_host(data).finish()
+        assert (list(c.to_dict().items()), c.lines) == oracle(data)
+        c.free()
+    finally:
+        ctx.set_stage_chunk(64 << 20)

@@ -342,14 +342,14 @@ def run_b200(args):
             t = tick("free", t)
         else:
             t = time.perf_counter()
-            owned = kdist.count_sharded(w.fastq_ptr, w.n_bytes, w.n_bytes, prefix=PREFIX, k=K, step=STEP, final=True,
-                                        base_line=first_read * 4, capacity_hint=hint, flags=state.get("flags", 0),
-                                        ctx=ctx, trace=state.get("fine_trace"))
-            t = tick("count+exchange", t)
+            kw = dict(prefix=PREFIX, k=K, step=STEP, final=True, base_line=first_read * 4, capacity_hint=hint,
+                      flags=state.get("flags", 0), ctx=ctx, trace=state.get("fine_trace"))
             rows = []
             if scoring:
-                dm = kdist.DistMatch(owned, tdb, torch_stream=stream, mode=args.score_mode)
-                t = tick("first_match+reduce", t)
+                # count, owner exchange, matched gather; after the first job of a kind the exchanges have fixed capacities
+                owned, dm = kdist.count_and_match(w.fastq_ptr, w.n_bytes, w.n_bytes, tdb, torch_stream=stream,
+                                                  mode=args.score_mode, **kw)
+                t = tick("count+exchange+first_match", t)
                 try:
                     for r in dm.rows():      # the generator may end by throwing (query exhausted): keep what it yielded
                         rows.append(r)
@@ -357,10 +357,15 @@ def run_b200(args):
                     pass
                 t = tick("wta_rows", t)
                 dm.free()
+            else:
+                owned = kdist.count_sharded(w.fastq_ptr, w.n_bytes, w.n_bytes, fixed=False, **kw)
+                t = tick("count+exchange", t)
             uniq = getattr(owned, "global_size", None)
             if uniq is None:
                 uniq = kdist.global_size(owned)
             state.update(occ=owned.occurrences, uniq=uniq, rows=rows, lines=owned.lines, bases=owned.bases)
+            if getattr(owned, "_local", None) is not None:
+                owned._local.free()
             owned.free()
 
     def sync_all():
@@ -450,19 +455,23 @@ def run_b200(args):
             with torch.cuda.stream(stream):
                 dev_in[: w.n_bytes].copy_(pinned[: w.n_bytes], non_blocking=True)
             stream.synchronize()
-            owned = kdist.count_sharded(dev_in.data_ptr(), w.n_bytes, w.n_bytes, prefix=PREFIX, k=K, step=STEP,
-                                        final=True, base_line=first_read * 4, ctx=ctx)
+            kw = dict(prefix=PREFIX, k=K, step=STEP, final=True, base_line=first_read * 4, capacity_hint=hint, ctx=ctx)
             rows = []
             if scoring:
-                dm = kdist.DistMatch(owned, tdb, torch_stream=stream, mode=args.score_mode)
+                owned, dm = kdist.count_and_match(dev_in.data_ptr(), w.n_bytes, w.n_bytes, tdb, torch_stream=stream,
+                                                  mode=args.score_mode, **kw)
                 try:
                     for r in dm.rows():
                         rows.append(r)
                 except NoHitsError:
                     pass
                 dm.free()
+            else:
+                owned = kdist.count_sharded(dev_in.data_ptr(), w.n_bytes, w.n_bytes, fixed=False, **kw)
             keys, lens, cnts = owned.export_arrays()
             d2h["bytes"] = keys.nbytes + lens.nbytes + cnts.nbytes + len(rows) * 136
+            if getattr(owned, "_local", None) is not None:
+                owned._local.free()
             owned.free()
 
     e2e = None

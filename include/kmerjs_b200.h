@@ -150,6 +150,17 @@ int kj_counts_irregular_merge(kj_counts *c, const void *host_records, uint64_t n
 /* the same, keeping only the records this part owns (owner = hash of the padded key bytes and the length, the
  * rule kj_owner and kj_db_desc.part/n_parts use for byte-string k-mers): every rank can be handed all records */
 int kj_counts_irregular_merge_part(kj_counts *c, const void *host_records, uint64_t n, uint32_t part, uint32_t n_parts);
+/* Fixed-capacity exchange: the same redistribution without a size round trip and without a host wait.  The sender
+ * scatters its table (as it stands after the adds: no kj_counts_finish needed) by owner into n_parts segments of
+ * kj_segment_bytes(cap_reg, cap_irr) bytes each -- {header: record counts and the sender's line / base / occurrence /
+ * byte totals | regular records[cap_reg] | irregular records[cap_irr]} -- the ranks exchange them with ONE equal-split
+ * all-to-all, and the owner merges the n_parts segments it received; record counts are read on the device.  A
+ * segment that would have needed more than its capacity, or a sender whose count was not complete, makes the
+ * owner's kj_counts_finish fail with KJ_E_RANGE: the caller then falls back to kj_counts_partition.  After
+ * kj_counts_merge_segments + kj_counts_finish the handle's lines / bases / occurrences / bytes_read are the job's. */
+uint64_t kj_segment_bytes(uint32_t cap_reg, uint32_t cap_irr);
+int kj_counts_partition_segments(kj_counts *c, uint32_t n_parts, void *dev_segments, uint32_t cap_reg, uint32_t cap_irr);
+int kj_counts_merge_segments(kj_counts *c, const void *dev_segments, uint32_t n_parts, uint32_t cap_reg, uint32_t cap_irr);
 /* totals of the whole job for a handle that holds only the k-mers one rank owns */
 int kj_counts_set_totals(kj_counts *c, uint64_t lines, uint64_t bases, uint64_t occurrences,
                          uint64_t bytes_read);
@@ -273,6 +284,19 @@ int kj_match_export_matched(kj_match *m, void *dev_entries, uint64_t cap_entries
 int kj_match_from_matched(kj_ctx *ctx, const kj_db *db, uint32_t n_segments, const uint64_t *seg_entries,
                           const uint64_t *seg_n_entries, const uint64_t *seg_tmpl, const uint64_t *seg_n_pairs,
                           uint64_t kmer_map_size, kj_match **out);
+/* The same with fixed capacities (no size round trip, no host wait before the collective): every rank writes ONE
+ * segment of kj_matched_segment_bytes(cap_entries, cap_pairs) bytes -- {entries, pairs, query size, flags | entries |
+ * template ids} --, the ranks all-gather the segments, and kj_match_from_segments builds the match over the gathered
+ * buffer (which must stay valid until kj_match_free: the template lists are used in place).  Sizes are read on the
+ * device; kj_match_commit fails with KJ_E_RANGE when a segment overflowed or a rank passed flags != 0, and sets the
+ * query size to the sum of the ranks' (kj_match_query_size). */
+uint64_t kj_matched_segment_bytes(uint32_t cap_entries, uint32_t cap_pairs);
+int kj_match_export_segment(kj_match *m, void *dev_segment, uint32_t cap_entries, uint32_t cap_pairs,
+                            uint64_t query_size, uint64_t flags);
+int kj_match_from_segments(kj_ctx *ctx, const kj_db *db, uint32_t n_segments, const void *dev_segments,
+                           uint32_t cap_entries, uint32_t cap_pairs, kj_match **out);
+uint64_t kj_match_query_size(const kj_match *m);
+int kj_match_segment_sizes(const kj_match *m, uint64_t *n_entries, uint64_t *n_pairs);   /* summed over the ranks */
 /* maxHits (lib/kmerFinderClient.js:123), default 100 */
 int kj_match_set_max_hits(kj_match *m, uint32_t max_hits);
 /* standardScoring (lib/kmerFinderServer.js:857-874): one row per matched template from the first

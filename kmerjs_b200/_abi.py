@@ -95,6 +95,9 @@ SIGNATURES = {
     "kj_counts_irregular_export": (C.c_int, [vp, vp]),
     "kj_counts_irregular_merge": (C.c_int, [vp, vp, C.c_uint64]),
     "kj_counts_irregular_merge_part": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]),
+    "kj_segment_bytes": (C.c_uint64, [C.c_uint32, C.c_uint32]),
+    "kj_counts_partition_segments": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32]),
+    "kj_counts_merge_segments": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]),
     "kj_counts_set_totals": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "kj_owner": (C.c_uint32, [C.c_char_p, C.c_uint32, C.c_uint32]),
     "kj_db_create": (C.c_int, [vp, C.POINTER(kj_db_desc), C.POINTER(vp)]),
@@ -124,6 +127,11 @@ SIGNATURES = {
     "kj_match_matched_size": (C.c_int, [vp, u64p, u64p]),
     "kj_match_export_matched": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64]),
     "kj_match_from_matched": (C.c_int, [vp, vp, C.c_uint32, u64p, u64p, u64p, u64p, C.c_uint64, C.POINTER(vp)]),
+    "kj_matched_segment_bytes": (C.c_uint64, [C.c_uint32, C.c_uint32]),
+    "kj_match_export_segment": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64]),
+    "kj_match_from_segments": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "kj_match_query_size": (C.c_uint64, [vp]),
+    "kj_match_segment_sizes": (C.c_int, [vp, u64p, u64p]),
     "kj_standard_scoring": (C.c_int, [vp, C.POINTER(kj_row), C.c_uint32, u32p]),
     "kj_set_rounding_mode": (C.c_int, [vp, C.c_int]),
     "kj_stats_zscore": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, f64p,

@@ -147,6 +147,18 @@ class Counts:
                        self.ctx.handle)
             self.finished = False
 
+    def partition_segments(self, n_parts: int, dev_ptr: int, cap_reg: int, cap_irr: int):
+        """Fixed-capacity exchange, sender side (stream-ordered, no finish() needed): n_parts segments of
+        segment_bytes(cap_reg, cap_irr) bytes at dev_ptr."""
+        _abi.check(self._L.kj_counts_partition_segments(self.handle, n_parts, C.c_void_p(dev_ptr), cap_reg, cap_irr),
+                   self.ctx.handle)
+
+    def merge_segments(self, dev_ptr: int, n_parts: int, cap_reg: int, cap_irr: int):
+        """Receiver side: merge the n_parts segments this rank got; totals and overflow surface in finish()."""
+        _abi.check(self._L.kj_counts_merge_segments(self.handle, C.c_void_p(dev_ptr), n_parts, cap_reg, cap_irr),
+                   self.ctx.handle)
+        self.finished = False
+
     def set_totals(self, lines: int, bases: int, occurrences: int, bytes_read: int):
         _abi.check(self._L.kj_counts_set_totals(self.handle, lines, bases, occurrences, bytes_read),
                    self.ctx.handle)
@@ -161,6 +173,10 @@ class Counts:
             self.free()
         except Exception:
             pass
+
+
+def segment_bytes(cap_reg: int, cap_irr: int) -> int:
+    return int(_abi.lib().kj_segment_bytes(cap_reg, cap_irr))
 
 
 def _host_pointer(data):

@@ -201,6 +201,124 @@ __global__ void kj_part_scatter_kernel(const uint64_t *keys, const uint64_t *cou
     }
 }
 
+// ---- fixed-capacity exchange (no size round trip, no host synchronisation) ---------------------------------------
+// A segment = {KjSegHeader, KjRecord[cap_reg], KjIrrRecord[cap_irr]}, one per destination rank.
+struct KjSegHeader {
+    unsigned long long n_reg, n_irr;               // records the sender had for this owner (may exceed the capacity: overflow)
+    unsigned long long lines, bases, occ, bytes;   // the sender's totals (the same in all of its segments)
+    unsigned long long flags, pad_;
+};
+static_assert(sizeof(KjSegHeader) == 64, "segment header");
+struct KjSegArgs {
+    uint8_t *seg;            // n_parts segments
+    uint64_t seg_bytes;
+    uint32_t n_parts, cap_reg, cap_irr;
+    uint32_t parity;
+    uint64_t voff, consumed;           // stream position of the sender (host knowledge)
+    long long bases_fix;               // closes the telescoping sum of KJ_F_COUNT_BASES at the start of the range
+    uint32_t count_bases, bases_tail;  // bases_tail: the range may end inside a sequence line (adds voff)
+    uint64_t cand_cap;
+};
+__device__ __forceinline__ KjSegHeader *kj_seg_hdr(const KjSegArgs &a, uint32_t p) {
+    return reinterpret_cast<KjSegHeader *>(a.seg + (uint64_t)p * a.seg_bytes);
+}
+
+// the sender's totals into every header (the counters are final: this runs after the count kernels in stream order)
+__global__ void kj_seg_totals_kernel(const KjSegArgs a, const KjCounters *ctr) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_parts) return;
+    KjSegHeader *h = kj_seg_hdr(a, p);
+    unsigned long long lines = ctr->carry_lines[a.parity];
+    long long bases = (long long)ctr->n_bases;
+    if (a.count_bases == 1 && a.consumed) {       // filter / dense kernels: close the telescoping sum at both ends
+        bases += a.bases_fix;
+        if (a.bases_tail && (lines & 3ull) == 1ull) bases += (long long)a.voff;
+    }
+    // a non-empty unterminated tail is one more line (lib/kmers.js:130-136)
+    if (a.consumed && ctr->carry_last[a.parity] != a.voff) lines += 1;
+    h->lines = lines;
+    h->bases = a.count_bases ? (unsigned long long)bases : 0ull;
+    h->occ = ctr->n_occ;
+    h->bytes = a.consumed;
+    h->flags = (ctr->n_overflow || ctr->n_irr_overflow || ctr->n_cand > a.cand_cap || ctr->error_flags) ? 1ull : 0ull;
+    h->pad_ = 0;
+}
+
+__global__ void kj_seg_scatter_kernel(const KjSegArgs a, KjTable t, uint64_t cap, KjIrrTable it, uint64_t irr_cap,
+                                      const KjCounters *ctr) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint64_t i = i0; i < cap; i += stride) {
+        const uint64_t key = t.keys[i];
+        if (key == KJ_EMPTY) continue;
+        const uint32_t p = kj_owner_key(key, a.n_parts);
+        KjSegHeader *h = kj_seg_hdr(a, p);
+        const unsigned long long o = atomicAdd(&h->n_reg, 1ull);
+        if (o < a.cap_reg) {
+            KjRecord *r = reinterpret_cast<KjRecord *>(reinterpret_cast<uint8_t *>(h) + sizeof(KjSegHeader)) + o;
+            r->key = key; r->count = t.counts[i]; r->ord = t.ords ? t.ords[i] : ~0ull;
+        }
+    }
+    if (i0 == 0 && ctr->special_count) {          // the one key equal to KJ_EMPTY (k = 32, all 'G')
+        const uint32_t p = kj_owner_key(KJ_EMPTY, a.n_parts);
+        KjSegHeader *h = kj_seg_hdr(a, p);
+        const unsigned long long o = atomicAdd(&h->n_reg, 1ull);
+        if (o < a.cap_reg) {
+            KjRecord *r = reinterpret_cast<KjRecord *>(reinterpret_cast<uint8_t *>(h) + sizeof(KjSegHeader)) + o;
+            r->key = KJ_EMPTY; r->count = ctr->special_count; r->ord = ctr->special_ord;
+        }
+    }
+    for (uint64_t i = i0; i < irr_cap; i += stride) {
+        const uint32_t st = it.state[i];
+        if (st < 2) continue;
+        const uint32_t p = kj_owner_bytes(it.keys + i * 32, st - 2, a.n_parts);
+        KjSegHeader *h = kj_seg_hdr(a, p);
+        const unsigned long long o = atomicAdd(&h->n_irr, 1ull);
+        if (o < a.cap_irr) {
+            KjIrrRecord *r = reinterpret_cast<KjIrrRecord *>(reinterpret_cast<uint8_t *>(h) + sizeof(KjSegHeader) +
+                                                             (uint64_t)a.cap_reg * sizeof(KjRecord)) + o;
+            const uint64_t *src = reinterpret_cast<const uint64_t *>(it.keys + i * 32);
+            uint64_t *dst = reinterpret_cast<uint64_t *>(r->key);
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+            r->len = st - 2; r->count = it.counts[i]; r->ord = it.ords[i];
+        }
+    }
+}
+
+// the receiver: every record of every segment into the owner's tables, the totals into the counters
+__global__ void kj_seg_merge_kernel(const KjSegArgs a, KjTable t, KjIrrTable it, KjCounters *ctr) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint64_t i = i0; i < (uint64_t)a.n_parts * a.cap_reg; i += stride) {
+        const uint32_t p = (uint32_t)(i / a.cap_reg), j = (uint32_t)(i % a.cap_reg);
+        const KjSegHeader *h = kj_seg_hdr(a, p);
+        if (j >= h->n_reg) continue;
+        const KjRecord *r = reinterpret_cast<const KjRecord *>(reinterpret_cast<const uint8_t *>(h) + sizeof(KjSegHeader)) + j;
+        if (!kj_insert(t, ctr, r->key, r->ord, r->count)) atomicOr(&ctr->error_flags, 0x80000000u);
+    }
+    for (uint64_t i = i0; i < (uint64_t)a.n_parts * a.cap_irr; i += stride) {
+        const uint32_t p = (uint32_t)(i / a.cap_irr), j = (uint32_t)(i % a.cap_irr);
+        const KjSegHeader *h = kj_seg_hdr(a, p);
+        if (j >= h->n_irr) continue;
+        const KjIrrRecord *r = reinterpret_cast<const KjIrrRecord *>(reinterpret_cast<const uint8_t *>(h) + sizeof(KjSegHeader) +
+                                                                     (uint64_t)a.cap_reg * sizeof(KjRecord)) + j;
+        __align__(8) uint8_t key32[32];
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(r->key);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(key32);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        if (!kj_insert_irr(it, ctr, key32, (uint32_t)r->len, r->ord, r->count)) atomicOr(&ctr->error_flags, 0x80000000u);
+    }
+    if (i0 < a.n_parts) {
+        const KjSegHeader *h = kj_seg_hdr(a, (uint32_t)i0);
+        atomicMax(&ctr->x_lines, h->lines);       // a rank's line count includes the lines before its range: the last rank's is the file's
+        atomicAdd(&ctr->x_bases, h->bases);
+        atomicAdd(&ctr->x_occ, h->occ);
+        atomicAdd(&ctr->x_bytes, h->bytes);
+        if (h->n_reg > a.cap_reg || h->n_irr > a.cap_irr) atomicOr(&ctr->error_flags, KJ_DEV_E_XCHG_OVERFLOW);
+        if (h->flags) atomicOr(&ctr->error_flags, KJ_DEV_E_XCHG_INCOMPLETE);
+    }
+}
+
 // ------------------------------------------------------------------------------------ helpers
 
 static uint64_t next_pow2(uint64_t x) {
@@ -334,6 +452,10 @@ static int check_device_errors(kj_counts *c) {
         return kj_fail(c->ctx, KJ_E_RANGE, "a sequence line extends beyond the halo of its buffer (the line-oriented kernel needs whole lines; give a larger halo)");
     if (f & KJ_DEV_E_LINE_TOO_LONG)
         return kj_fail(c->ctx, KJ_E_RANGE, "a sequence line is longer than 2^27 bytes (first-seen position field); use KJ_F_NO_ORDER");
+    if (f & (KJ_DEV_E_XCHG_OVERFLOW | KJ_DEV_E_XCHG_INCOMPLETE))
+        return kj_fail(c->ctx, KJ_E_RANGE, (f & KJ_DEV_E_XCHG_OVERFLOW)
+                           ? "fixed-capacity exchange: a segment overflowed (use larger capacities or the two-phase exchange)"
+                           : "fixed-capacity exchange: a sender's count was incomplete (use the two-phase exchange)");
     if (f & KJ_DEV_E_READS_OVERFLOW)
         return kj_fail(c->ctx, KJ_E_RANGE, "more than 2^36 reads (first-seen read field); use KJ_F_NO_ORDER");
     return kj_fail(c->ctx, KJ_E_CUDA, "unknown device error flag");
@@ -382,6 +504,7 @@ static KjScanArgs make_args(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint6
         memcpy(a.wmask, mask, sizeof(mask));
     }
     a.ctr = c->ctr;
+    a.c0a = 0x0A0A0A0Au; a.c7f = 0x7F7F7F7Fu;
     return a;
 }
 
@@ -446,36 +569,34 @@ static int make_tensor_map(kj_ctx *ctx, const uint8_t *dbuf, uint64_t n, KjTenso
 
 typedef void (*KjFilterFn)(const KjTensorMap, const KjScanArgs);
 static KjFilterFn pick_filter_kernel(const KjScanArgs &a) {
-    // where the filter symbols of complement(prefix) sit relative to the window start
-    const uint32_t d_lo = a.rc_shift, d_hi = a.rc_shift + a.mp - 1;
-    const int rc = d_hi < 16 ? KJ_RC_LOW : (d_lo >= 16 ? KJ_RC_HIGH : KJ_RC_MIXED);
-#define KJ_PICK(MP)                                                                          \
-    case MP:                                                                                 \
-        return rc == KJ_RC_LOW ? kj_warp_filter_kernel<MP, KJ_RC_LOW>                        \
-                               : rc == KJ_RC_HIGH ? kj_warp_filter_kernel<MP, KJ_RC_HIGH>    \
-                                                  : kj_warp_filter_kernel<MP, KJ_RC_MIXED>;
     switch (a.mp) {
-        KJ_PICK(1) KJ_PICK(2) KJ_PICK(3) KJ_PICK(4) KJ_PICK(5) KJ_PICK(6) KJ_PICK(7)
-        default: break;
+        case 1: return kj_warp_filter_kernel<1>;
+        case 2: return kj_warp_filter_kernel<2>;
+        case 3: return kj_warp_filter_kernel<3>;
+        case 4: return kj_warp_filter_kernel<4>;
+        case 5: return kj_warp_filter_kernel<5>;
+        case 6: return kj_warp_filter_kernel<6>;
+        case 7: return kj_warp_filter_kernel<7>;
+        default: return kj_warp_filter_kernel<8>;
     }
-    return rc == KJ_RC_LOW ? kj_warp_filter_kernel<8, KJ_RC_LOW>
-                           : rc == KJ_RC_HIGH ? kj_warp_filter_kernel<8, KJ_RC_HIGH> : kj_warp_filter_kernel<8, KJ_RC_MIXED>;
-#undef KJ_PICK
 }
 
-// scan -> exclusive scan of the tile counts -> resolve, all stream-ordered
-static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only) {
+// scan -> exclusive scan of the tile counts -> filter (entries -> items) -> emit (items -> table), all stream-ordered;
+// retry_only: the emit pass over the marked items; items_only: from the filter on (the item buffer was too small)
+static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only, bool items_only = false) {
     kj_ctx *ctx = c->ctx;
     KjScanArgs &a = pc.args;
     a.tab = c->tab; a.irr = c->irr; a.ovf = c->ovf;
     a.cand = c->cand; a.cand_cap = c->cand_cap;
+    a.items = c->items; a.item_cap = c->item_cap;
     a.tile_cnt = c->tile_cnt; a.tile_excl = c->tile_mem;
     a.resolve_retry = retry_only ? 1u : 0u;
-    // the failure counters of this pass (n_overflow, n_irr_overflow) and, for a full pass, the entry counter
-    KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_overflow, 0, (retry_only ? 2 : 3) * sizeof(unsigned long long), ctx->stream));
-    const bool timed = ctx->timers_on && !retry_only;
+    // the failure counters of this pass (n_overflow, n_irr_overflow) and, for a full pass, the entry and item counters
+    KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_overflow, 0, (retry_only ? 2 : 4) * sizeof(unsigned long long), ctx->stream));
+    if (items_only) KJ_CUDA(ctx, cudaMemcpyAsync(&c->ctr->n_cand, &c->h_ctr->n_cand, sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    const bool timed = ctx->timers_on && !retry_only && !items_only;
     if (timed) KJ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (!retry_only) {
+    if (!retry_only && !items_only) {
         KjFilterFn fn = pick_filter_kernel(a);
         KJ_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KJ_WT_SMEM_BYTES));
         int occ = 0;
@@ -498,10 +619,14 @@ static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only) {
         }
 #endif
     }
-    if (c->k <= 16) KJ_LAUNCH((kj_resolve_kernel<4>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
-    else KJ_LAUNCH((kj_resolve_kernel<8>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
+    if (!retry_only) {
+        KJ_LAUNCH(kj_resolve_filter_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);
+        ctx->launches++;
+    }
+    if (c->k <= 16) KJ_LAUNCH((kj_resolve_emit_kernel<4>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
+    else KJ_LAUNCH((kj_resolve_emit_kernel<8>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
     ctx->launches++;
-    if (a.count_bases && !retry_only) {
+    if (a.count_bases && !retry_only && !items_only) {
         KJ_LAUNCH(kj_bases_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);
         ctx->launches++;
     }
@@ -511,8 +636,8 @@ static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only) {
     return KJ_OK;
 }
 
-// entry buffer and tile arrays for a piece of n_tiles tiles expecting `want_ent` entries
-static int ensure_filter_buffers(kj_counts *c, uint32_t n_tiles, uint64_t want_ent) {
+// entry / item buffers and tile arrays for a piece of n_tiles tiles expecting `want_ent` entries and `want_items` items
+static int ensure_filter_buffers(kj_counts *c, uint32_t n_tiles, uint64_t want_ent, uint64_t want_items) {
     kj_ctx *ctx = c->ctx;
     if (n_tiles > c->tile_cap) {
         kj_dfree(ctx, c->tile_mem); kj_dfree(ctx, c->tile_cnt); kj_dfree(ctx, c->scan_tmp);
@@ -534,6 +659,12 @@ static int ensure_filter_buffers(kj_counts *c, uint32_t n_tiles, uint64_t want_e
         KJ_CUDA(ctx, kj_dmalloc(ctx, &c->cand, want_ent * 16));
         c->cand_cap = want_ent;
     }
+    if (want_items > c->item_cap) {
+        kj_dfree(ctx, c->items);
+        c->items = nullptr; c->item_cap = 0;
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->items, want_items * 16));
+        c->item_cap = want_items;
+    }
     return KJ_OK;
 }
 
@@ -548,7 +679,7 @@ static int settle_filter(kj_counts *c) {
     if (rc) return rc;
     if (pc.timed) { rc = account_scan_time(c, pc.args.own_n, true); if (rc) return rc; }
     for (int round = 0; round < 4 && c->h_ctr->n_cand > c->cand_cap; ++round) {
-        rc = ensure_filter_buffers(c, pc.args.n_tiles, c->h_ctr->n_cand + (c->h_ctr->n_cand >> 3) + 1024);
+        rc = ensure_filter_buffers(c, pc.args.n_tiles, c->h_ctr->n_cand + (c->h_ctr->n_cand >> 3) + 1024, 0);
         if (rc) return rc;
         rc = launch_filter(c, pc, false);
         if (rc) return rc;
@@ -556,6 +687,15 @@ static int settle_filter(kj_counts *c) {
         if (rc) return rc;
     }
     if (c->h_ctr->n_cand > c->cand_cap) return kj_fail(ctx, KJ_E_CUDA, "internal: candidate entries exceed their own count");
+    if (c->h_ctr->n_items > c->item_cap) {          // the entries are fine, the items did not fit: from the filter on
+        rc = ensure_filter_buffers(c, pc.args.n_tiles, 0, c->h_ctr->n_items + 1024);
+        if (rc) return rc;
+        rc = launch_filter(c, pc, false, true);
+        if (rc) return rc;
+        rc = pull_counters(c);
+        if (rc) return rc;
+        if (c->h_ctr->n_items > c->item_cap) return kj_fail(ctx, KJ_E_CUDA, "internal: items exceed their own count");
+    }
     rc = check_device_errors(c);
     if (rc) return rc;
     for (int round = 0; c->h_ctr->n_overflow; ++round) {
@@ -585,7 +725,10 @@ static int scan_piece_filter(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint
     int rc = settle_filter(c);                      // one piece in flight per handle
     if (rc) return rc;
     const uint32_t m = (uint32_t)c->prefix.size();
-    const uint64_t n_tiles64 = (own_n + KJ_WT_BYTES - 1) / KJ_WT_BYTES;
+    // complement(prefix) is searched where it starts: rc_shift = k - m bytes behind the start of its window, so the tiles
+    // reach that far past the owned range
+    const uint64_t reach = (c->flags & KJ_F_FORWARD_ONLY) ? 0 : (uint64_t)(c->k - m);
+    const uint64_t n_tiles64 = (own_n + reach + KJ_WT_BYTES - 1) / KJ_WT_BYTES;
     if (n_tiles64 > 0x7FFFFFF0ull / KJ_WT_OWN_ROWS) return kj_fail(ctx, KJ_E_RANGE, "piece too large");
     // table capacity: the caller's hint, else what this piece is expected to add (it grows by rehash between
     // pieces; emissions that find no slot wait for the retry pass)
@@ -602,8 +745,11 @@ static int scan_piece_filter(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint
     const uint64_t chunks = own_n / 16 + 1;
     double share = 48.0;
     for (uint32_t i = 0; i < std::min<uint32_t>(m, KJ_MAX_MP); ++i) share *= 0.25;
-    const uint64_t want_ent = std::min<uint64_t>(chunks, (uint64_t)(std::min(1.0, share) * (double)chunks) + (1ull << 16));
-    rc = ensure_filter_buffers(c, (uint32_t)n_tiles64, want_ent);
+    // entry slots are reserved in blocks of KJ_WT_BLOCK per warp, so a buffer holds at least a few blocks for every warp
+    const uint64_t want_ent = std::min<uint64_t>(chunks + (1ull << 20), (uint64_t)(std::min(1.0, share) * (double)chunks) + (1ull << 20));
+    // items: the candidates that sit in sequence lines (for FASTQ of reads: less than half of them)
+    const uint64_t want_items = std::min<uint64_t>(hard_bound, (uint64_t)(std::min(1.0, share) * (double)chunks) + (1ull << 16));
+    rc = ensure_filter_buffers(c, (uint32_t)n_tiles64, want_ent, want_items);
     if (rc) return rc;
 
     KjPiece &pc = *c->piece;
@@ -1080,6 +1226,10 @@ extern "C" int kj_counts_finish(kj_counts *c) {
     // a non-empty unterminated tail is one more line (lib/kmers.js:130-136)
     if (c->consumed && c->h_ctr->carry_last[c->parity] != c->voff) c->lines += 1;
     c->occurrences = c->h_ctr->n_occ;
+    if (c->exchange_totals) {     // this handle holds the k-mers one rank owns: the totals are the whole job's
+        c->lines = c->h_ctr->x_lines; c->bases = c->h_ctr->x_bases;
+        c->occurrences = c->h_ctr->x_occ; c->bytes_read = c->h_ctr->x_bytes;
+    }
     c->finished = true;
     return KJ_OK;
 }
@@ -1299,7 +1449,7 @@ extern "C" void kj_counts_free(kj_counts *c) {
         kj_dfree(ctx, c->ctr);
         kj_pinned_put(ctx, c->h_ctr);
         kj_dfree(ctx, c->tile_mem); kj_dfree(ctx, c->tile_cnt); kj_dfree(ctx, c->scan_tmp);
-        kj_dfree(ctx, c->cand);
+        kj_dfree(ctx, c->cand); kj_dfree(ctx, c->items);
         drop_compact(c);
         kj_dfree(ctx, c->part_rec);
     }
@@ -1352,6 +1502,70 @@ extern "C" int kj_counts_partition(kj_counts *c, uint32_t n_parts, const void **
     kj_dfree(ctx, d_hist);
     if (e != cudaSuccess) return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e));
     *dev_records = c->part_rec;
+    return KJ_OK;
+}
+
+extern "C" uint64_t kj_segment_bytes(uint32_t cap_reg, uint32_t cap_irr) {
+    const uint64_t b = sizeof(KjSegHeader) + (uint64_t)cap_reg * sizeof(KjRecord) + (uint64_t)cap_irr * sizeof(KjIrrRecord);
+    return (b + 255) / 256 * 256;
+}
+
+// Fixed-capacity exchange, sender side: the table as it stands after the adds (no kj_counts_finish, no host wait) is
+// scattered by owner into n_parts segments of kj_segment_bytes(cap_reg, cap_irr) bytes each.  Whatever does not fit --
+// or a count that is not complete -- shows in the headers and makes the receivers' kj_counts_finish fail with
+// KJ_E_RANGE, so that the caller can fall back to the two-phase exchange (kj_counts_partition).
+extern "C" int kj_counts_partition_segments(kj_counts *c, uint32_t n_parts, void *dev_segments, uint32_t cap_reg,
+                                            uint32_t cap_irr) {
+    if (!c || !dev_segments || !n_parts || n_parts > 1024 || !cap_reg) return KJ_E_INVALID;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    KjSegArgs a{};
+    a.seg = reinterpret_cast<uint8_t *>(dev_segments);
+    a.seg_bytes = kj_segment_bytes(cap_reg, cap_irr);
+    a.n_parts = n_parts; a.cap_reg = cap_reg; a.cap_irr = cap_irr;
+    a.parity = c->parity; a.voff = c->voff; a.consumed = c->consumed;
+    a.count_bases = ((c->flags & KJ_F_COUNT_BASES) && (c->use_filter || c->use_dense)) ? 1u : 0u;
+    a.bases_fix = ((c->base_line & 3ull) == 1ull) ? -(long long)c->base_col : 0;
+    a.bases_tail = 1;
+    if ((c->flags & KJ_F_COUNT_BASES) && !a.count_bases) a.count_bases = 2;     // line kernel: n_bases is already the sum
+    a.cand_cap = c->use_filter ? c->cand_cap : ~0ull;
+    for (uint32_t p = 0; p < n_parts; ++p)
+        KJ_CUDA(ctx, cudaMemsetAsync(a.seg + (uint64_t)p * a.seg_bytes, 0, sizeof(KjSegHeader), ctx->stream));
+    KJ_LAUNCH(kj_seg_totals_kernel, (n_parts + 127) / 128, 128, 0, ctx->stream, a, c->ctr);
+    if (c->cap || c->irr_cap)
+        KJ_LAUNCH(kj_seg_scatter_kernel, grid_for(ctx, std::max(c->cap, c->irr_cap)), 256, 0, ctx->stream, a, c->tab, c->cap,
+                  c->irr, c->irr_cap, c->ctr);
+    ctx->launches += 2;
+    KJ_CUDA(ctx, cudaGetLastError());
+    return KJ_OK;
+}
+
+// receiver side: merge n_parts segments into this (fresh) handle; stream-ordered, the totals and the overflow flags
+// surface in kj_counts_finish
+extern "C" int kj_counts_merge_segments(kj_counts *c, const void *dev_segments, uint32_t n_parts, uint32_t cap_reg,
+                                        uint32_t cap_irr) {
+    if (!c || !dev_segments || !n_parts || n_parts > 1024 || !cap_reg) return KJ_E_INVALID;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = settle_filter(c);
+    if (rc) return rc;
+    const uint64_t bound = (uint64_t)n_parts * cap_reg;
+    rc = grow_table(c, 2 * (c->h_ctr->n_unique + (c->capacity_hint ? std::min<uint64_t>(c->capacity_hint, bound) : bound)));
+    if (rc) return rc;
+    c->irr_bound += (uint64_t)n_parts * cap_irr;
+    rc = grow_irr(c, 2 * c->irr_bound);
+    if (rc) return rc;
+    KjSegArgs a{};
+    a.seg = reinterpret_cast<uint8_t *>(const_cast<void *>(dev_segments));
+    a.seg_bytes = kj_segment_bytes(cap_reg, cap_irr);
+    a.n_parts = n_parts; a.cap_reg = cap_reg; a.cap_irr = cap_irr;
+    KJ_LAUNCH(kj_seg_merge_kernel, grid_for(ctx, std::max<uint64_t>(bound, n_parts)), 256, 0, ctx->stream, a, c->tab, c->irr, c->ctr);
+    ctx->launches++;
+    KJ_CUDA(ctx, cudaGetLastError());
+    c->finished = false;
+    c->exchange_totals = true;
     return KJ_OK;
 }
 

@@ -12,6 +12,8 @@
 #define KJ_DEV_E_LINE_TOO_LONG 1u      // position does not fit KJ_POS_BITS
 #define KJ_DEV_E_LINE_EXCEEDS_HALO 2u  // line-oriented kernel: line end not inside the readable bytes
 #define KJ_DEV_E_READS_OVERFLOW 4u     // read index does not fit 36 bits
+#define KJ_DEV_E_XCHG_OVERFLOW 8u      // fixed-capacity exchange: a segment held more records than its capacity
+#define KJ_DEV_E_XCHG_INCOMPLETE 16u   // fixed-capacity exchange: a sender's count had emissions or entries left over
 
 // regular table: ACGT-only, full-length k-mers as 2k-bit integers (first base most significant).
 // SoA: three arrays of cap entries (8+8+8 bytes per slot; ords may be null with KJ_F_NO_ORDER).
@@ -44,7 +46,8 @@ struct KjCounters {
     unsigned long long n_irr_unique;
     unsigned long long n_overflow;
     unsigned long long n_irr_overflow;
-    unsigned long long n_cand;         // candidate record slots handed out in the current launch (filter kernel)
+    unsigned long long n_cand;         // filter path: entry slots handed out in the current launch
+    unsigned long long n_items;        // filter path: items (candidates in sequence lines) of the current launch
     unsigned long long n_occ;          // emitted occurrences (regular + irregular)
     unsigned long long n_bases;        // sum of processed sequence-line lengths
     unsigned long long special_count;  // the one key equal to KJ_EMPTY (k = 32, all 'G')
@@ -58,6 +61,8 @@ struct KjCounters {
     unsigned long long n_unique_part[64];
     unsigned long long n_compact;      // compaction cursors
     unsigned long long n_irr_compact;
+    // totals of the whole job, summed from the segment headers of a fixed-capacity exchange (kj_counts_merge_segments)
+    unsigned long long x_lines, x_bases, x_occ, x_bytes;
 };
 
 __device__ __forceinline__ uint64_t kj_ld_volatile(const uint64_t *p) {

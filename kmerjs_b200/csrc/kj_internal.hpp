@@ -116,8 +116,11 @@ struct kj_counts {
     size_t scan_tmp_bytes = 0;
     uint64_t *cand = nullptr;         // candidate entries of the piece in flight (filter path), 16 bytes each
     uint64_t cand_cap = 0;
+    uint64_t *items = nullptr;        // items of the piece in flight (filter path), 16 bytes each
+    uint64_t item_cap = 0;
     struct KjPiece *piece = nullptr;  // filter path: the piece in flight (kernel arguments + tensor map), kj_count.cu
     bool pending = false;             // the piece has been launched and not settled yet
+    bool exchange_totals = false;     // totals come from the segment headers of a fixed-capacity exchange
     // results
     KjCompact reg{};
     // irregular entries, host side after finish: 56-byte records

@@ -59,10 +59,13 @@ struct KjScanArgs {
     uint64_t *status;     // per tile: flag << 62 | newline count; zeroed before every launch
     uint64_t *cand;       // filter path: candidate entries of this launch, 16 bytes each (kj_scan_warp.cuh)
     uint64_t cand_cap;    // in entries
+    uint64_t *items;      // filter path: candidates that sit in sequence lines, 16 bytes each {window start | strand, ordinal}
+    uint64_t item_cap;
     uint64_t *tile_cnt;   // filter path: '\n' per tile
     uint64_t *tile_excl;  // filter path: '\n' before the tile inside the launch (exclusive scan of tile_cnt)
     uint32_t n_fast;      // filter path: leading tiles that are whole, owned and readable through the tensor map
     uint32_t resolve_retry;   // kj_resolve_kernel: only the entries an earlier pass marked
+    uint32_t c0a, c7f;    // 0x0A0A0A0A, 0x7F7F7F7F as kernel arguments: register operands of the newline test (kj_nl_flags_r)
     KjCounters *ctr;
 };
 

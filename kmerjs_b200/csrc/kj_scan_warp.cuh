@@ -5,23 +5,27 @@
 //                           (one 2-D tensor-map copy with the 128-byte swizzle, SASS UTMALDG.2D) into the
 //                           warp's private ring of stages, so that every lane reads ITS OWN contiguous 128
 //                           bytes (8 chunks of 16) without bank conflicts: the code words of a lane's
-//                           neighbours in the stream are its own registers, and only the two words behind
-//                           its last chunk come from the next lane (two shuffles per 8 chunks; lane 31
-//                           converts the row behind the tile for lane 30 and owns nothing).
-//                           Per chunk: 2-bit code word, newline mask, bit-parallel search of the prefix and
-//                           of complement(prefix) in code space (lib/kmers.js:88-100,151-155 as an exact
-//                           superset filter).  Chunks with a candidate are queued in shared memory and
-//                           drained by the whole warp every few tiles as 16-byte entries
-//                           {chunk, '\n' before it in the tile, its '\n' mask, distance back to the last '\n',
-//                           candidate lanes}.  The tile's newline count goes to tile_cnt[]; nothing in this
-//                           kernel needs the number of lines before the tile.
+//                           neighbours in the stream are its own registers, and only the word behind its
+//                           last chunk comes from the next lane (one shuffle per 8 chunks; lane 31 converts
+//                           the row behind the tile for lane 30 and owns nothing).
+//                           Per chunk: 2-bit code word, newline mask, and a bit-parallel search in code space,
+//                           16 positions per 32-bit operation, for the places where the prefix starts (forward
+//                           windows start there) and where complement(prefix) starts (reverse-strand windows
+//                           start k - |prefix| bytes before): lib/kmers.js:88-100,151-155 as an exact superset
+//                           filter.  Both strands share the shifted words.  Chunks with a candidate go to a queue
+//                           per lane (a predicated store, no atomic, no branch) and are drained by the whole
+//                           warp every few tiles as 16-byte entries {chunk, '\n' before it in the tile, its
+//                           '\n' mask, distance back to the last '\n', candidate lanes}.  The tile's newline
+//                           count goes to tile_cnt[]; nothing here needs the number of lines before the tile.
 //   (exclusive scan of tile_cnt -> tile_excl, cub::DeviceScan; the record FSM of lib/kmers.js:151-163 is
 //    "line index mod 4" over the whole stream)
-//   kj_resolve_kernel       one thread per entry, the whole GPU: line index of every candidate = lines before
-//                           the launch + tile_excl + in-tile count -> keep iff 1 mod 4; first-seen ordinal;
-//                           exact check of the window's bytes and the hash-table update (kj_window_emit).
-//                           An emission that finds no slot marks its entry for a retry pass after the host
-//                           has grown the table: nothing is ever dropped, whatever the input looks like.
+//   kj_resolve_filter_kernel  one thread per entry: line index of every candidate = lines before the launch +
+//                           tile_excl + in-tile count -> keep iff 1 mod 4; first-seen ordinal; survivors become
+//                           16-byte items {window start | strand, ordinal}, appended densely.
+//   kj_resolve_emit_kernel  one thread per item, all lanes busy: exact check of the window's bytes (prefix,
+//                           no '\n' inside, alphabet) and the hash-table update.  An emission that finds no slot
+//                           marks its item for a retry pass after the host has grown the table: nothing is ever
+//                           dropped, whatever the input looks like.
 #pragma once
 #include "kj_scan.cuh"
 
@@ -31,19 +35,19 @@
 #define KJ_WT_STAGE_BYTES 4096u                  // what one TMA copy brings: the tile and the row behind it
 #define KJ_WT_STAGES 2
 #define KJ_WT_RING 4u                            // tiles whose newline bitmaps stay in shared memory
-#define KJ_WT_QCAP 320u                          // queue entries per warp; a tile adds at most 256
+#define KJ_WT_PQCAP 12u                          // queue entries per LANE; a tile adds at most 8 to a lane
+#define KJ_WT_BLOCK 128u                         // entry slots a warp reserves at a time (one global atomic, taken ahead)
 #define KJ_WT_WARPS 8
 #define KJ_WT_THREADS (KJ_WT_WARPS * 32)
-#define KJ_ENT_RETRY (1ull << 63)
 #define KJ_ENT_NODIST 0xFFFFu
+#define KJ_ITEM_STRAND (1ull << 63)
+#define KJ_ITEM_RETRY (1ull << 62)
 
 struct __align__(16) KjWarpSmem {
     uint4 bitmap[KJ_WT_RING][32];                // lane l: the '\n' masks of its 8 chunks, 16 bits each, in stream order
     uint32_t lanepre[KJ_WT_RING][32];            // '\n' of the tile before lane l's first byte
-    uint32_t qz[KJ_WT_QCAP];                     // candidate lanes of a chunk (bit 2p: forward window at byte p, 2p + 1: reverse)
-    uint16_t qloc[KJ_WT_QCAP];                   // ring slot << 8 | lane << 3 | chunk of the lane
-    uint32_t qn;
-    uint32_t pad_[3];
+    uint2 pq[KJ_WT_PQCAP][32];                   // a queue per lane, entry j of lane l at pq[j][l]: {candidate lanes of a chunk
+                                                 // (bit 2p: forward window at byte p, 2p + 1: reverse), ring slot << 3 | chunk of the lane}
 };
 #define KJ_WT_SMEM_BYTES (KJ_WT_WARPS * KJ_WT_STAGES * KJ_WT_STAGE_BYTES + KJ_WT_WARPS * KJ_WT_STAGES * 8 + \
                           KJ_WT_WARPS * sizeof(KjWarpSmem) + 1024)
@@ -64,7 +68,6 @@ __device__ __forceinline__ void kj_tma_tile(void *dst, const KjTensorMap *tm, ui
 __device__ __forceinline__ uint4 kj_lds128(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
 typedef const uint8_t *kj_saddr;
 __device__ __forceinline__ kj_saddr kj_saddr_of(const void *p) { return reinterpret_cast<const uint8_t *>(p); }
-__device__ __forceinline__ uint32_t kj_atoms_inc(uint32_t *p) { return atomicAdd(p, 1u); }
 #else
 #include <cuda.h>
 typedef CUtensorMap KjTensorMap;
@@ -80,12 +83,6 @@ __device__ __forceinline__ uint4 kj_lds128(kj_saddr a) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
-}
-// plain ATOMS: the compiler's warp-aggregated form of atomicAdd costs more than it saves with one or two active lanes
-__device__ __forceinline__ uint32_t kj_atoms_inc(uint32_t *p) {
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(kj_smem_u32(p)) : "memory");
-    return old;
 }
 #endif
 
@@ -108,35 +105,145 @@ __device__ __forceinline__ uint32_t kj_nl16_r(const uint4 v, uint32_t c0a, uint3
 #endif
 }
 
-// candidate lanes of one chunk from its code word and the two behind it
-template <int MP, int RC>
-__device__ __forceinline__ uint32_t kj_chunk_lanes(const KjScanArgs &a, uint32_t c0, uint32_t c1, uint32_t c2) {
+// candidate lanes of one chunk from its code word and the two behind it: bit 2p = the forward window at byte p passes the
+// code-space filter, bit 2p + 1 = the reverse-strand window.  live = 0x55555555 with KJ_F_FORWARD_ONLY, else all ones.
+// Candidate lanes of one chunk from its code word and the one behind it.  Bit 2p: the prefix starts at byte p of the
+// chunk in code space (a forward window starts there); bit 2p + 1: complement(prefix) starts at byte p (a reverse-strand
+// window starts rc_shift = k - |prefix| bytes before p: complement() reverses, so the prefix of the reverse strand is the
+// END of the window).  Both strands look at the same shifted words.  live = 0x55555555 with KJ_F_FORWARD_ONLY.
+// (Doing the shifts as multiplications on the FMA pipe, which is half idle, was measured slower: 1.05 vs 0.84 ms.)
+template <int MP>
+__device__ __forceinline__ uint32_t kj_chunk_lanes(const KjScanArgs &a, uint32_t c0, uint32_t c1, uint32_t live) {
     uint32_t accf = 0, accr = 0;
 #pragma unroll
     for (int i = 0; i < MP; ++i) {
-        accf |= kj_funnel_r(c0, c1, 2u * i) ^ a.pat_f[i];
-        accr |= kj_rc_lanes<RC>(c0, c1, c2, a.rc_shift + i) ^ a.pat_r[i];
+        const uint32_t sh = kj_funnel_r(c0, c1, 2u * i);
+        accf |= sh ^ a.pat_f[i];
+        accr |= sh ^ a.pat_r[i];
     }
-    const uint32_t zf = kj_zero_lanes(accf);
-    const uint32_t zr = a.n_strands > 1 ? kj_zero_lanes(accr) : 0u;
-    return zf | (zr << 1);
+    const uint32_t nf = accf | (accf >> 1);               // bit 0 of a lane: some filter symbol differs from the prefix
+    const uint32_t nr = accr | (accr << 1);               // bit 1 of a lane: the same for complement(prefix)
+    const uint32_t any = (nf & 0x55555555u) | (nr & 0xAAAAAAAAu);
+    return ~any & live;
+}
+
+// append {z, loc} to the LANE's queue when z != 0: a predicated store and a predicated add, no atomic, no branch (a
+// divergent region costs a compare, a convergence barrier, a branch and a wait for every chunk whether it holds a
+// candidate or not; a shared-memory atomic with a result cannot be predicated at all).  qaddr: where the lane's next
+// entry goes (shared-memory address on the device, a pointer under tools/cuemu).
+#if defined(__CUDA_ARCH__)
+typedef uint32_t kj_qaddr;
+__device__ __forceinline__ void kj_wt_push(kj_qaddr &qaddr, uint32_t z, uint32_t loc) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.u32 p, %1, 0;\n\t"
+                 "@p st.shared.v2.u32 [%0], {%1, %2};\n\t"
+                 "@p add.u32 %0, %0, 256;\n\t}"
+                 : "+r"(qaddr) : "r"(z), "r"(loc) : "memory");
+}
+__device__ __forceinline__ kj_qaddr kj_qaddr_of(KjWarpSmem &ws, uint32_t lane) { return kj_smem_u32(&ws.pq[0][lane]); }
+__device__ __forceinline__ uint32_t kj_q_count(KjWarpSmem &ws, uint32_t lane, kj_qaddr qaddr) {
+    return (qaddr - kj_smem_u32(&ws.pq[0][lane])) >> 8;
+}
+#else
+typedef uint2 *kj_qaddr;
+__device__ __forceinline__ void kj_wt_push(kj_qaddr &qaddr, uint32_t z, uint32_t loc) {
+    if (z) { *qaddr = make_uint2(z, loc); qaddr += 32; }
+}
+__device__ __forceinline__ kj_qaddr kj_qaddr_of(KjWarpSmem &ws, uint32_t lane) { return &ws.pq[0][lane]; }
+__device__ __forceinline__ uint32_t kj_q_count(KjWarpSmem &ws, uint32_t lane, kj_qaddr qaddr) {
+    return (uint32_t)(qaddr - &ws.pq[0][lane]) / 32u;
+}
+#endif
+
+// per-warp state that lives in registers across tiles
+struct KjWarpRegs {
+    kj_qaddr qaddr;                    // per lane: where its next queue entry goes
+    unsigned long long blk_at;         // entry slots of the block in use: [blk_at, blk_at + blk_left)   (uniform over the lanes)
+    uint32_t blk_left;
+    unsigned long long next_at;        // the block reserved ahead (its atomic was issued a drain ago: nothing waits for it)
+};
+
+// What follows the conversion of a tile, for a lane with its code words (cw[8]: the one behind its last chunk) and its
+// packed newline masks: newline bookkeeping, the search, the queue.  MASKED: edge tiles clip the candidates to the positions
+// whose windows start inside the owned range.
+template <int MP, bool MASKED>
+__device__ __forceinline__ void kj_wt_finish_tile(const KjScanArgs &a, KjWarpSmem &ws, const uint32_t (&cw)[9],
+                                                  const uint32_t (&nlp)[4], uint64_t t, uint32_t slot, uint32_t lane,
+                                                  uint32_t live, kj_qaddr &qaddr) {
+    // the lane's masks, '\n' before the lane inside the tile, the tile's count
+    ws.bitmap[slot][lane] = make_uint4(nlp[0], nlp[1], nlp[2], nlp[3]);
+    const uint32_t cnt = __popc(nlp[0]) + __popc(nlp[1]) + __popc(nlp[2]) + __popc(nlp[3]);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += o;
+    }
+    ws.lanepre[slot][lane] = incl - cnt;
+    if (lane == KJ_WT_OWN_ROWS - 1u) a.tile_cnt[t] = incl;     // the 31 owned rows
+    const uint32_t locbase = slot << 3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t z = kj_chunk_lanes<MP>(a, cw[i], cw[i + 1], live);
+        if (MASKED) {
+            // forward candidates below own_n; reverse ones below own_n + rc_shift (their windows start rc_shift earlier)
+            const uint64_t o = t * KJ_WT_BYTES + lane * 128u + (uint32_t)i * 16u;
+            const uint64_t lim_f = a.own_n, lim_r = a.own_n + a.rc_shift;
+            uint32_t keep = 0;
+            if (o + 16 <= lim_f) keep |= 0x55555555u;
+            else if (o < lim_f) keep |= ((1u << (2u * (uint32_t)(lim_f - o))) - 1u) & 0x55555555u;
+            if (o + 16 <= lim_r) keep |= 0xAAAAAAAAu;
+            else if (o < lim_r) keep |= ((1u << (2u * (uint32_t)(lim_r - o))) - 1u) & 0xAAAAAAAAu;
+            z &= keep;
+        }
+        kj_wt_push(qaddr, z, locbase | (uint32_t)i);
+    }
+    __syncwarp();
 }
 
 // ----------------------------------------------------------------------------- drain
 
-// The whole warp turns its queue into entries in global memory, one entry per lane and round.
+// one thread: reserve the next block of entry slots
+__device__ __forceinline__ unsigned long long kj_wt_reserve(const KjScanArgs &a) {
+    return atomicAdd(&a.ctr->n_cand, (unsigned long long)KJ_WT_BLOCK);
+}
+// the unused slots [at, at + n) of a block become empty entries (no candidate lanes)
+__device__ __forceinline__ void kj_wt_blank(const KjScanArgs &a, unsigned long long at, uint32_t n, uint32_t lane) {
+    for (uint32_t i = lane; i < n; i += 32)
+        if (at + i < a.cand_cap) reinterpret_cast<uint4 *>(a.cand)[at + i] = make_uint4(0, 0, 0, 0);
+}
+
+// The whole warp turns the lanes' queues into entries in global memory: dense again, one entry per lane and round (entry e of
+// the concatenated queues belongs to the lane whose inclusive count is the first above e: five shuffle probes find it).
+// Entry slots come from blocks of KJ_WT_BLOCK the warp reserves one drain ahead, so that nothing waits for the atomic.
 static __device__ __noinline__ void kj_wt_drain(const KjScanArgs &a, KjWarpSmem &ws, uint32_t t_cur, uint32_t slot_cur,
-                                                uint32_t G) {
+                                                uint32_t G, KjWarpRegs &wr) {
     const uint32_t lane = threadIdx.x & 31;
     __syncwarp();
-    const uint32_t n = ws.qn < KJ_WT_QCAP ? ws.qn : KJ_WT_QCAP;
+    const uint32_t mine = kj_q_count(ws, lane, wr.qaddr);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += o;
+    }
+    const uint32_t n = __shfl_sync(0xFFFFFFFFu, incl, 31);
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t e = base + lane;
+        uint32_t src = 0;
+#pragma unroll
+        for (uint32_t st = 16; st > 0; st >>= 1) {
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, (src + st - 1u) & 31u);
+            if (v <= e) src += st;
+        }
+        src &= 31u;
+        const uint32_t first = __shfl_sync(0xFFFFFFFFu, incl - mine, src);     // entries of the lanes before src
         bool keep = false;
         uint4 rec = make_uint4(0, 0, 0, 0);
         if (e < n) {
-            const uint32_t z = ws.qz[e], loc = ws.qloc[e];
-            const uint32_t slot = loc >> 8, src = (loc >> 3) & 31u, i = loc & 7u;
+            const uint2 qe = ws.pq[e - first][src];
+            const uint32_t z = qe.x, loc = qe.y;
+            const uint32_t slot = loc >> 3, i = loc & 7u;
             if (src != 31u) {                                       // lane 31 converts the row behind the tile: not owned
                 keep = true;
                 const uint32_t age = (slot_cur - slot) & (KJ_WT_RING - 1u);
@@ -175,22 +282,53 @@ static __device__ __noinline__ void kj_wt_drain(const KjScanArgs &a, KjWarpSmem 
             }
         }
         const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
-        if (kb) {
-            unsigned long long at = 0;
-            if (lane == 0) at = atomicAdd(&a.ctr->n_cand, (unsigned long long)__popc(kb));
-            at = __shfl_sync(0xFFFFFFFFu, at, 0);
-            at += __popc(kb & ((1u << lane) - 1u));
-            if (keep && at < a.cand_cap) reinterpret_cast<uint4 *>(a.cand)[at] = rec;    // beyond the buffer: the host sees n_cand and repeats the piece
+        const uint32_t need = __popc(kb);
+        if (need > wr.blk_left) {
+            // the block is used up: blank its tail, go on in the one reserved ahead, reserve the one after
+            kj_wt_blank(a, wr.blk_at, wr.blk_left, lane);
+            wr.blk_at = wr.next_at;
+            wr.blk_left = KJ_WT_BLOCK;
+            unsigned long long nx = 0;
+            if (lane == 0) nx = kj_wt_reserve(a);
+            wr.next_at = __shfl_sync(0xFFFFFFFFu, nx, 0);
         }
+        if (keep) {
+            const unsigned long long at = wr.blk_at + __popc(kb & ((1u << lane) - 1u));
+            if (at < a.cand_cap) reinterpret_cast<uint4 *>(a.cand)[at] = rec;    // beyond the buffer: the host sees n_cand and repeats the piece
+        }
+        wr.blk_at += need;
+        wr.blk_left -= need;
     }
     __syncwarp();
-    if (lane == 0) ws.qn = 0;
-    __syncwarp();
+    wr.qaddr = kj_qaddr_of(ws, lane);
 }
 
 // ----------------------------------------------------------------------------- scan kernel
 
-template <int MP, int RC>
+// edge tiles (the last ones of a launch): bounds-checked loads straight from global memory, newlines clipped to the
+// owned range.  Out of line: it runs once or twice per launch and must not sit in the hot loop.
+template <int MP>
+static __device__ __noinline__ void kj_wt_edge_tile(const KjScanArgs &a, KjWarpSmem &ws, uint64_t t, uint32_t slot, uint32_t live,
+                                                    kj_qaddr &qaddr) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t cw[9], nlp[4] = {0, 0, 0, 0};
+    const uint64_t lo = t * KJ_WT_BYTES + lane * 128u;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const uint64_t o = lo + (uint32_t)i * 16u;
+        const uint4 v = (o < a.n) ? kj_load_chunk(a.buf, o, a.n) : make_uint4(0, 0, 0, 0);
+        cw[i] = kj_pack16(v.x, v.y, v.z, v.w);
+        if (i < 8) {
+            uint32_t m = kj_nl16(v.x, v.y, v.z, v.w);
+            if (o >= a.own_n) m = 0;
+            else if (o + 16 > a.own_n) m &= (1u << (uint32_t)(a.own_n - o)) - 1u;
+            nlp[i >> 1] |= m << (16 * (i & 1));
+        }
+    }
+    kj_wt_finish_tile<MP, true>(a, ws, cw, nlp, t, slot, lane, live, qaddr);
+}
+
+template <int MP>
 __global__ void __launch_bounds__(KJ_WT_THREADS, 2)
 kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_constant__ KjScanArgs a) {
     KJ_DYN_SMEM(dyn);
@@ -207,10 +345,19 @@ kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
-        ws.qn = 0;
     }
     __syncwarp();
     const uint32_t G = gridDim.x * KJ_WT_WARPS, g = blockIdx.x * KJ_WT_WARPS + warp;
+    if (g >= a.n_tiles) return;                          // a warp without a tile reserves nothing
+    KjWarpRegs wr;
+    wr.qaddr = kj_qaddr_of(ws, lane);
+    {
+        unsigned long long b0 = 0, b1 = 0;
+        if (lane == 0) { b0 = kj_wt_reserve(a); b1 = kj_wt_reserve(a); }
+        wr.blk_at = __shfl_sync(0xFFFFFFFFu, b0, 0);
+        wr.next_at = __shfl_sync(0xFFFFFFFFu, b1, 0);
+        wr.blk_left = KJ_WT_BLOCK;
+    }
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < KJ_WT_STAGES; ++s) {
@@ -222,96 +369,124 @@ kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_con
     kj_saddr off[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) off[i] = kj_saddr_of(stage) + lane * 128u + (((uint32_t)i << 4) ^ ((lane & 7u) << 4));
-    uint32_t c0a = 0x0A0A0A0Au, c7f = 0x7F7F7F7Fu;
-#if defined(__CUDA_ARCH__)
-    asm volatile("mov.u32 %0, 0x0A0A0A0A;" : "=r"(c0a));             // opaque to the optimiser: stays a register operand
-    asm volatile("mov.u32 %0, 0x7F7F7F7F;" : "=r"(c7f));
-#endif
-    uint32_t phase = 0, it = 0;
-    uint64_t t = g;
-    while (t < a.n_tiles) {
+    const uint32_t c0a = a.c0a, c7f = a.c7f;          // kernel arguments, so that they stay register operands (kj_nl_flags_r)
+    const uint32_t live = a.n_strands > 1 ? 0xFFFFFFFFu : 0x55555555u;
+    uint32_t it = 0;
+    uint32_t t = g;
+    // ---- whole tiles through the TMA ring.  One body for every stage (the stage offset is an add per load): unrolled over the
+    // stages the loop outgrows the instruction cache, which cost more than the adds.
+    for (; t < a.n_fast; t += G, ++it) {
+        const uint32_t s = it % KJ_WT_STAGES, slot = it & (KJ_WT_RING - 1u);
+        // room in every lane's queue for everything this tile can add to it (8 entries)
+        if (__any_sync(0xFFFFFFFFu, kj_q_count(ws, lane, wr.qaddr) + 8u > KJ_WT_PQCAP))
+            kj_wt_drain(a, ws, t - G, (slot - 1u) & (KJ_WT_RING - 1u), G, wr);
+        kj_bar_wait(&bars[s], (it / KJ_WT_STAGES) & 1u);
+        const uint32_t soff = s * KJ_WT_STAGE_BYTES;
+        uint32_t cw[9], nlp[4];
 #pragma unroll
-        for (int s = 0; s < KJ_WT_STAGES; ++s) {
-            if (t >= a.n_tiles) break;
-            const uint32_t slot = it & (KJ_WT_RING - 1u);
-            // room for everything this tile can add (256 entries)
-            if (ws.qn + 256u > KJ_WT_QCAP) kj_wt_drain(a, ws, (uint32_t)t - G, (slot - 1u) & (KJ_WT_RING - 1u), G);
-            uint32_t cw[10], nlp[4];
-            const bool fast = t < a.n_fast;
-            if (fast) {
-                kj_bar_wait(&bars[s], (phase >> s) & 1u);
-                phase ^= 1u << s;
-#pragma unroll
-                for (int i = 0; i < 8; i += 2) {
-                    const uint4 v0 = kj_lds128(off[i] + s * KJ_WT_STAGE_BYTES), v1 = kj_lds128(off[i + 1] + s * KJ_WT_STAGE_BYTES);
-                    cw[i] = kj_pack16(v0.x, v0.y, v0.z, v0.w);
-                    cw[i + 1] = kj_pack16(v1.x, v1.y, v1.z, v1.w);
-                    nlp[i >> 1] = kj_nl16_r(v0, c0a, c7f) | (kj_nl16_r(v1, c0a, c7f) << 16);
-                }
-                __syncwarp();                                        // every lane has read the stage
-                if (lane == 0) {
-                    const uint64_t tn = t + (uint64_t)KJ_WT_STAGES * G;
-                    if (tn < a.n_fast) kj_tma_tile(stage + s * KJ_WT_STAGE_BYTES, &tmap, (uint32_t)tn * KJ_WT_OWN_ROWS, &bars[s]);
-                }
-                cw[8] = __shfl_down_sync(0xFFFFFFFFu, cw[0], 1);
-                cw[9] = __shfl_down_sync(0xFFFFFFFFu, cw[1], 1);
-            } else {
-                // edge tiles (the last one or two of a launch): bounds-checked loads straight from global memory,
-                // newlines and window starts clipped to the owned range
-                const uint64_t lo = t * KJ_WT_BYTES + lane * 128u;
-#pragma unroll 1
-                for (int i = 0; i < 10; ++i) {
-                    const uint64_t o = lo + (uint32_t)i * 16u;
-                    const uint4 v = (o < a.n) ? kj_load_chunk(a.buf, o, a.n) : make_uint4(0, 0, 0, 0);
-                    const uint32_t c = kj_pack16(v.x, v.y, v.z, v.w);
-                    uint32_t m = kj_nl16(v.x, v.y, v.z, v.w);
-                    if (o >= a.own_n) m = 0;
-                    else if (o + 16 > a.own_n) m &= (1u << (uint32_t)(a.own_n - o)) - 1u;
-                    // (dynamic register indexing would spill: a select chain keeps the arrays in registers)
-#pragma unroll
-                    for (int j = 0; j < 10; ++j) if (j == i) cw[j] = c;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (i == 2 * j) nlp[j] = m;
-                        if (i == 2 * j + 1) nlp[j] |= m << 16;
-                    }
-                }
-            }
-            // newline bookkeeping: the lane's masks, '\n' before the lane inside the tile, the tile's count
-            ws.bitmap[slot][lane] = make_uint4(nlp[0], nlp[1], nlp[2], nlp[3]);
-            const uint32_t cnt = __popc(nlp[0]) + __popc(nlp[1]) + __popc(nlp[2]) + __popc(nlp[3]);
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if ((int)lane >= d) incl += o;
-            }
-            ws.lanepre[slot][lane] = incl - cnt;
-            if (lane == KJ_WT_OWN_ROWS - 1u) a.tile_cnt[t] = incl;     // the 31 owned rows
-            // search
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint32_t z = kj_chunk_lanes<MP, RC>(a, cw[i], cw[i + 1], cw[i + 2]);
-                if (!fast) {
-                    const uint64_t o = t * KJ_WT_BYTES + lane * 128u + (uint32_t)i * 16u;
-                    if (o >= a.own_n) z = 0;
-                    else if (o + 16 > a.own_n) z &= (1u << (2u * (uint32_t)(a.own_n - o))) - 1u;
-                }
-                if (z) {
-                    const uint32_t q = kj_atoms_inc(&ws.qn);
-                    if (q < KJ_WT_QCAP) { ws.qz[q] = z; ws.qloc[q] = (uint16_t)((slot << 8) | (lane << 3) | (uint32_t)i); }
-                }
-            }
-            __syncwarp();
-            // the ring keeps KJ_WT_RING tiles: drain when it is full (and at the end)
-            if (slot == KJ_WT_RING - 1u || t + G >= a.n_tiles) kj_wt_drain(a, ws, (uint32_t)t, slot, G);
-            t += G;
-            ++it;
+        for (int i = 0; i < 8; i += 2) {
+            const uint4 v0 = kj_lds128(off[i] + soff), v1 = kj_lds128(off[i + 1] + soff);
+            cw[i] = kj_pack16(v0.x, v0.y, v0.z, v0.w);
+            cw[i + 1] = kj_pack16(v1.x, v1.y, v1.z, v1.w);
+            nlp[i >> 1] = kj_nl16_r(v0, c0a, c7f) | (kj_nl16_r(v1, c0a, c7f) << 16);
         }
+        __syncwarp();                                        // every lane has read the stage
+        if (lane == 0) {
+            const uint64_t tn = (uint64_t)t + (uint64_t)KJ_WT_STAGES * G;
+            if (tn < a.n_fast) kj_tma_tile(stage + soff, &tmap, (uint32_t)tn * KJ_WT_OWN_ROWS, &bars[s]);
+        }
+        cw[8] = __shfl_down_sync(0xFFFFFFFFu, cw[0], 1);
+        kj_wt_finish_tile<MP, false>(a, ws, cw, nlp, t, slot, lane, live, wr.qaddr);
+        // the ring keeps KJ_WT_RING tiles: drain when it is full
+        if (slot == KJ_WT_RING - 1u) kj_wt_drain(a, ws, t, slot, G, wr);
     }
+    // ---- edge tiles
+    for (; t < a.n_tiles; t += G, ++it) {
+        const uint32_t slot = it & (KJ_WT_RING - 1u);
+        if (__any_sync(0xFFFFFFFFu, kj_q_count(ws, lane, wr.qaddr) + 8u > KJ_WT_PQCAP))
+            kj_wt_drain(a, ws, t - G, (slot - 1u) & (KJ_WT_RING - 1u), G, wr);
+        kj_wt_edge_tile<MP>(a, ws, t, slot, live, wr.qaddr);
+        if (slot == KJ_WT_RING - 1u) kj_wt_drain(a, ws, t, slot, G, wr);
+    }
+    // what is left in the queues (the ring slot of the last tile is (it - 1) mod ring), then the unused entry slots
+    kj_wt_drain(a, ws, t - G, (it - 1u) & (KJ_WT_RING - 1u), G, wr);
+    kj_wt_blank(a, wr.blk_at, wr.blk_left, lane);
+    kj_wt_blank(a, wr.next_at, KJ_WT_BLOCK, lane);
 }
 
 // ----------------------------------------------------------------------------- resolve kernel
+
+// Entries -> items.  For every candidate of an entry: the line index (lines before the launch + lines before the tile +
+// '\n' before the position inside the tile) must be 1 mod 4 (lib/kmers.js:151, i === 1); the window must start inside the
+// owned range; the first-seen ordinal = (read, strand, column).  Survivors are appended as {window start | strand << 63,
+// ordinal}, one warp-wide append per round.  Block 0 also closes the stream state of the launch for the next one.
+__global__ void __launch_bounds__(256) kj_resolve_filter_kernel(const __grid_constant__ KjScanArgs a) {
+    const unsigned long long n_ent = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;
+    const uint64_t base_lines = a.ctr->carry_lines[a.parity];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.n_tiles) {
+        a.ctr->carry_lines[a.parity ^ 1] = base_lines + a.tile_excl[a.n_tiles - 1] + a.tile_cnt[a.n_tiles - 1];
+        a.ctr->carry_last[a.parity ^ 1] = kj_line_start_global(a, a.own_n);
+    }
+    if (a.ctr->n_cand > a.cand_cap) return;                   // the entry buffer was too small: nothing is touched, the host repeats the piece
+    const uint4 *ent = reinterpret_cast<const uint4 *>(a.cand);
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long rounds = (n_ent + stride - 1) / stride;      // the same trip count for every thread (warp collectives inside)
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    for (unsigned long long r = 0; r < rounds; ++r, i += stride) {
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (i < n_ent) rec = ent[i];
+        const uint64_t word = ((uint64_t)rec.y << 32) | rec.x;
+        const uint64_t chunk = word & ((1ull << 40) - 1ull);
+        const uint32_t nlb = (uint32_t)(word >> 40) & 0x1FFFu;
+        const uint32_t nlmask = rec.w & 0xFFFFu, dist = rec.w >> 16;
+        const uint64_t tile = chunk / KJ_WT_CHUNKS;
+        uint32_t lanes = rec.z;
+        uint64_t line0 = 0;
+        if (lanes) line0 = base_lines + a.tile_excl[tile] + nlb;
+        while (__any_sync(0xFFFFFFFFu, lanes != 0u)) {
+            bool keep = false;
+            uint64_t item0 = 0, ord = 0;
+            if (lanes) {
+                const uint32_t bit = __ffs(lanes) - 1;
+                lanes &= lanes - 1;
+                const uint32_t p = bit >> 1, strand = bit & 1u;
+                const uint64_t pos = chunk * 16u + p;                      // where the prefix / complement(prefix) starts
+                const uint32_t back = strand ? a.rc_shift : 0u;            // the reverse-strand window starts k - m before
+                const uint32_t below = nlmask & ((1u << p) - 1u);
+                const uint64_t line = line0 + __popc(below);
+                if (pos >= back && pos - back < a.own_n && pos - back + a.k <= a.n && (line & 3ull) == 1ull) {
+                    const uint64_t j = pos - back;
+                    keep = true;
+                    if (a.order || a.k == 1) {
+                        unsigned long long start;                          // first byte of the line (virtual offset)
+                        if (below) start = a.voff + chunk * 16u + (31u - __clz(below)) + 1ull;
+                        else if (dist != KJ_ENT_NODIST) start = a.voff + chunk * 16u - dist;
+                        else start = kj_line_start_global(a, tile * KJ_WT_BYTES);
+                        if (a.voff + j < start) {
+                            keep = false;                                  // a '\n' between the window start and the prefix: not a window
+                        } else {
+                            const uint64_t col = a.voff + j - start;
+                            const uint64_t read_idx = line >> 2;
+                            if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); keep = false; }
+                            else if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); keep = false; }
+                            // forward emissions in ascending column, then reverse emissions in descending column
+                            else ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
+                        }
+                    }
+                    item0 = j | (strand ? KJ_ITEM_STRAND : 0ull);
+                }
+            }
+            const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
+            if (kb) {
+                unsigned long long at = 0;
+                if (lane == 0) at = atomicAdd(&a.ctr->n_items, (unsigned long long)__popc(kb));
+                at = __shfl_sync(0xFFFFFFFFu, at, 0) + __popc(kb & ((1u << lane) - 1u));
+                if (keep && at < a.item_cap) reinterpret_cast<ulonglong2 *>(a.items)[at] = make_ulonglong2(item0, ord);
+            }
+        }
+    }
+}
 
 // status of one candidate window
 #define KJ_EMIT_NONE 0       // not an emission (prefix bytes differ, crosses the end of the line, ...)
@@ -362,72 +537,29 @@ __device__ __forceinline__ int kj_window_try(const KjScanArgs &a, uint64_t j, ui
     return kj_insert_irr(a.irr, a.ctr, key32, k, ord, 1) ? KJ_EMIT_OK : KJ_EMIT_FULL;
 }
 
-// every candidate of one entry; returns the lanes that found no table slot
+// Items -> table.  a.resolve_retry == 0: every item; != 0: the items an earlier pass marked.
 template <int KW>
-__device__ __forceinline__ uint32_t kj_resolve_entry(const KjScanArgs &a, const uint4 rec, uint64_t base_lines, uint32_t &n_emit) {
-    const uint64_t word = ((uint64_t)rec.y << 32) | rec.x;
-    const uint64_t chunk = word & ((1ull << 40) - 1ull);
-    const uint32_t nlb = (uint32_t)(word >> 40) & 0x1FFFu;
-    const uint32_t nlmask = rec.w & 0xFFFFu, dist = rec.w >> 16;
-    const uint64_t tile = chunk / KJ_WT_CHUNKS;
-    const uint64_t line0 = base_lines + a.tile_excl[tile] + nlb;
-    uint32_t lanes = rec.z, failed = 0;
-    while (lanes) {
-        const uint32_t bit = __ffs(lanes) - 1;
-        lanes &= lanes - 1;
-        const uint32_t p = bit >> 1, strand = bit & 1u;
-        const uint64_t j = chunk * 16u + p;
-        if (j + a.k > a.n) continue;                          // the window must lie inside the stream
-        const uint32_t below = nlmask & ((1u << p) - 1u);
-        const uint64_t line = line0 + __popc(below);
-        if ((line & 3ull) != 1ull) continue;                  // lib/kmers.js:151  i === 1
-        uint64_t ord = 0;
-        if (a.order || a.k == 1) {
-            unsigned long long start;                         // first byte of the line (virtual offset)
-            if (below) start = a.voff + chunk * 16u + (31u - __clz(below)) + 1ull;
-            else if (dist != KJ_ENT_NODIST) start = a.voff + chunk * 16u - dist;
-            else start = kj_line_start_global(a, tile * KJ_WT_BYTES);
-            const uint64_t col = a.voff + j - start;
-            if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); continue; }
-            const uint64_t read_idx = line >> 2;
-            if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); continue; }
-            // forward emissions in ascending column, then reverse emissions in descending column
-            ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
-        }
+__global__ void __launch_bounds__(256) kj_resolve_emit_kernel(const __grid_constant__ KjScanArgs a) {
+    if (a.ctr->n_cand > a.cand_cap || a.ctr->n_items > a.item_cap) return;      // a buffer was too small: the host repeats
+    const unsigned long long n_items = a.ctr->n_items;
+    uint32_t n_emit = 0, n_fail = 0;
+    ulonglong2 *items = reinterpret_cast<ulonglong2 *>(a.items);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_items; i += stride) {
+        const ulonglong2 it = items[i];
+        const bool marked = (it.x & KJ_ITEM_RETRY) != 0;
+        if (a.resolve_retry && !marked) continue;
+        const uint64_t j = it.x & ~(KJ_ITEM_STRAND | KJ_ITEM_RETRY);
+        const uint32_t strand = (uint32_t)(it.x >> 63);
         uint4 v0, v1, v2;
         kj_window_load(a, j, v0, v1, v2);
-        const int st = kj_window_try<KW>(a, j, strand, ord, v0, v1, v2);
+        const int st = kj_window_try<KW>(a, j, strand, it.y, v0, v1, v2);
         if (st == KJ_EMIT_OK) ++n_emit;
-        else if (st == KJ_EMIT_FULL) failed |= 1u << bit;
-    }
-    return failed;
-}
-
-// a.resolve_retry == 0: every entry; != 0: the entries an earlier pass marked (their z holds the lanes left over).
-// Block 0 also closes the stream state of the launch (lines and last '\n' so far) for the next one.
-template <int KW>
-__global__ void __launch_bounds__(256) kj_resolve_kernel(const __grid_constant__ KjScanArgs a) {
-    const unsigned long long n_ent = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;
-    const uint64_t base_lines = a.ctr->carry_lines[a.parity];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && !a.resolve_retry && a.n_tiles) {
-        a.ctr->carry_lines[a.parity ^ 1] = base_lines + a.tile_excl[a.n_tiles - 1] + a.tile_cnt[a.n_tiles - 1];
-        a.ctr->carry_last[a.parity ^ 1] = kj_line_start_global(a, a.own_n);
-    }
-    if (a.ctr->n_cand > a.cand_cap) return;                   // the entry buffer was too small: nothing is touched, the host repeats the piece
-    uint32_t n_emit = 0, n_fail = 0;
-    uint4 *ent = reinterpret_cast<uint4 *>(a.cand);
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_ent; i += stride) {
-        uint4 rec = ent[i];
-        const bool marked = (rec.y >> 31) != 0;
-        if (a.resolve_retry && !marked) continue;
-        rec.y &= 0x7FFFFFFFu;
-        const uint32_t failed = kj_resolve_entry<KW>(a, rec, base_lines, n_emit);
-        if (failed) {
+        if (st == KJ_EMIT_FULL) {
             ++n_fail;
-            ent[i] = make_uint4(rec.x, rec.y | 0x80000000u, failed, rec.w);
+            if (!marked) items[i].x = it.x | KJ_ITEM_RETRY;
         } else if (marked) {
-            ent[i] = make_uint4(rec.x, rec.y, 0u, rec.w);
+            items[i].x = it.x & ~KJ_ITEM_RETRY;
         }
     }
     for (int d = 16; d > 0; d >>= 1) {

@@ -17,6 +17,9 @@
 #include <cstring>
 #include <unordered_map>
 #include "kj_internal.hpp"
+#ifndef KJ_CPU_EMU
+#include <cub/device/device_scan.cuh>
+#endif
 #include "kj_stats.hpp"
 
 #define KJ_NONE32 0xFFFFFFFFu
@@ -49,11 +52,12 @@ struct kj_db {
     KjDbDev dev() const { return KjDbDev{d_keys, d_vals, cap - 1, d_list_off, d_tmpl}; }
 };
 
-struct KjWtaResult {        // written by the argmax kernel, copied to the host every round
+struct KjWtaResult {        // written by the argmax / loop kernels, copied to the host
     uint32_t winner;        // template id, KJ_NONE32 when every uScore is zero
     uint32_t pad;
     uint64_t u, tau, hits;
     double z, p;            // double-precision zScore / fastp * templates (the device gate)
+    uint64_t u0, tau0;      // the winner's first-round scores (loop kernel only)
 };
 
 struct kj_match {
@@ -83,11 +87,16 @@ struct kj_match {
     void *d_loop = nullptr;          // kj_wta_loop_kernel: {records, status} + one KjWtaResult per round
     bool committed = false;
     bool distributed = false;        // d_glob is separate and maintained by the host layer
-    std::vector<uint64_t> u0, t0;    // first-round scores (lib/kmerFinderClient.js:44-46)
+    bool from_segments = false;      // kj_match_from_segments: sizes / query size / flags arrive with the commit
+    uint64_t *d_glob0 = nullptr;     // {u[T], tau[T]} as the first match left them (lib/kmerFinderClient.js:44-46)
+    unsigned int *d_sync = nullptr;  // kj_wta_loop_kernel: grid barrier counter + one control word per round
+    bool host_first = false;         // u0 / t0 / order / toff_h below have been fetched (on demand: the hot path never needs them)
+    std::vector<uint64_t> u0, t0;    // first-round scores
     std::vector<uint32_t> order;     // matched templates in first-encounter order
     std::vector<uint64_t> toff_h;    // host copy of toff (range of a winner's matched entries)
     uint64_t hits0 = 0;
     uint64_t kmer_map_size = 0;
+    uint64_t seg_entries = 0, seg_pairs = 0;   // kj_match_from_segments: what the ranks really sent
     uint32_t max_hits = 100, hit_counter = 0;
     bool ended = false;
     bool inflight = false;           // the argmax of the next round has been launched ahead
@@ -295,6 +304,52 @@ __global__ void kj_matched_import_kernel(const uint64_t *entries, uint64_t n, ui
     }
 }
 
+// Fixed-capacity variant (no size round trip): a segment = {n_entries, n_pairs, query size, flags | entries[cap_e] x 32 B |
+// template ids[cap_p]}; all segments of the all-gather are imported by one launch, sizes read on the device, and the
+// template lists stay where the collective put them (list offsets index the gathered buffer as u32).
+struct KjMSegHeader { unsigned long long n_entries, n_pairs, qsize, flags; };
+__global__ void kj_matched_header_kernel(KjMSegHeader *h, unsigned long long qsize, unsigned long long flags) {
+    h->n_entries = 0; h->n_pairs = 0; h->qsize = qsize; h->flags = flags;
+}
+__global__ void kj_matched_import_segments_kernel(const uint8_t *segs, uint64_t seg_bytes, uint32_t n_seg, uint32_t cap_e,
+                                                  uint32_t cap_p, uint64_t *count, uint64_t *ord, uint8_t *alive,
+                                                  uint32_t *qkmer, uint64_t *off, unsigned long long *info) {
+    const uint64_t total = (uint64_t)n_seg * cap_e;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t sgm = (uint32_t)(i / cap_e), j = (uint32_t)(i % cap_e);
+        const KjMSegHeader *h = reinterpret_cast<const KjMSegHeader *>(segs + (uint64_t)sgm * seg_bytes);
+        const uint64_t n_s = h->n_entries < cap_e ? h->n_entries : cap_e;
+        if (j >= n_s) continue;
+        uint64_t e0 = 0;
+        for (uint32_t q = 0; q < sgm; ++q) {
+            const KjMSegHeader *hq = reinterpret_cast<const KjMSegHeader *>(segs + (uint64_t)q * seg_bytes);
+            e0 += hq->n_entries < cap_e ? hq->n_entries : cap_e;
+        }
+        const uint64_t e = e0 + j;
+        const uint64_t *ent = reinterpret_cast<const uint64_t *>(segs + (uint64_t)sgm * seg_bytes + sizeof(KjMSegHeader)) + 4 * (uint64_t)j;
+        const uint64_t o = ent[2], l = ent[3];
+        const uint64_t tbase = ((uint64_t)sgm * seg_bytes + sizeof(KjMSegHeader) + (uint64_t)cap_e * 32u) / 4u;
+        count[e] = ent[0];
+        ord[e] = ent[1];
+        alive[e] = 1;
+        qkmer[e] = (uint32_t)(2 * e);
+        off[2 * e] = tbase + o;
+        off[2 * e + 1] = tbase + o + l;
+        if (o + l > cap_p || o + l < o) atomicOr(&info[3], 2ull);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long ne = 0, np = 0, qs = 0, fl = 0;
+        for (uint32_t q = 0; q < n_seg; ++q) {
+            const KjMSegHeader *hq = reinterpret_cast<const KjMSegHeader *>(segs + (uint64_t)q * seg_bytes);
+            ne += hq->n_entries; np += hq->n_pairs; qs += hq->qsize;
+            if (hq->n_entries > cap_e || hq->n_pairs > cap_p) fl |= 2ull;
+            if (hq->flags) fl |= 1ull;
+        }
+        info[0] = ne; info[1] = np; info[2] = qs;
+        if (fl) atomicOr(&info[3], fl);
+    }
+}
+
 // double-precision restatement of lib/stats.js:19-45 (the device gate; rows are finished exactly on the host)
 __device__ __forceinline__ double kj_zscore_f64(double r1, double n1, double r2, double n2) {
     const double eta = 1.0e-8;
@@ -401,15 +456,34 @@ __global__ void kj_remove_kernel(KjDbDev d, const uint32_t *tq, uint64_t lo, uin
     if (lane == 0 && gone) atomicAdd((unsigned long long *)&part[2 * (uint64_t)T], 0ull - gone);
 }
 
-// The whole findMatches loop (lib/kmerFinderClient.js:273-286) on the device: one CTA runs argmax -> gate ->
-// removal round after round and appends {winner, u, tau, H, z, p} per round to `res`; the host waits once and
-// finishes the rows in exact decimal arithmetic.  The gate is the double-precision one of kj_argmax_kernel: the
-// loop stops BEFORE the removal at the first round whose z is within 1e-6 of a fastp threshold (or whose
-// p * templates is within 1e-9 of the evalue) -- the exact arithmetic decides that round on the host and the
-// loop is resumed.  Scores are changed by atomics (L2) and read back with volatile loads.
+// First-encounter rank of every matched template: its position in ascending (first ordinal, list index, id) order
+// (lib/kmerFinderServer.js:180-201: query k-mers in Map order, each list in DB order).  Every thread counts the keys
+// below its own: T^2 compares, all threads reading the same key at the same time (10^4 templates: tens of microseconds).
+__global__ void kj_rank_kernel(const uint64_t *u, const uint64_t *ford, const uint64_t *fidx, uint32_t T, uint32_t *rank) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+        if (!u[t]) { rank[t] = KJ_NONE32 - 1; continue; }
+        const uint64_t fo = ford[t], fi = fidx[t];
+        uint32_t below = 0;
+        for (uint32_t q = 0; q < T; ++q) {
+            if (!u[q]) continue;
+            const uint64_t qo = ford[q], qi = fidx[q];
+            below += (qo < fo) || (qo == fo && (qi < fi || (qi == fi && q < t)));
+        }
+        rank[t] = below;
+    }
+}
+
+// The whole findMatches loop (lib/kmerFinderClient.js:273-286) on the device.  Block 0 takes the argmax and the gate of a
+// round and appends {winner, u, tau, H, z, p, u0, tau0} to `res`; every block then removes its share of the winner's
+// k-mers; a grid barrier closes the round.  The host waits once and finishes the rows in exact decimal arithmetic.  The
+// gate is the double-precision one: the loop stops BEFORE the removal at the first round whose z is within 1e-6 of a fastp
+// threshold (or whose p * templates is within 1e-9 of the evalue) -- the exact arithmetic decides that round on the host
+// and the loop is resumed.  Scores are changed by atomics (L2) and read back with volatile loads.  The blocks must be
+// co-resident (cooperative launch, grid <= what the device holds at once).
 struct KjWtaLoopArgs {
     KjDbDev d;
     uint64_t *glob;               // u[T], tau[T], H  (== part on one GPU / in a gathered match)
+    const uint64_t *glob0;        // u[T], tau[T] of the first match
     const uint32_t *rank;
     const uint64_t *ulen;
     const uint64_t *toff;
@@ -421,6 +495,7 @@ struct KjWtaLoopArgs {
     double unique_lens, n_templates;
     KjWtaResult *res;             // max_rounds + 1 records
     uint32_t *head;               // {records written, status}
+    unsigned int *sync;           // [0]: barrier counter, [1 + round]: control word of the round (0: not yet, 1: stop, 2 + w: remove w)
 };
 enum { KJ_LOOP_MORE = 0,          // max_rounds accepted: the caller decides whether maxHits is reached
        KJ_LOOP_NO_HITS = 1,       // nHits === 0 / no template left (last record is not a row)
@@ -437,68 +512,70 @@ __device__ __forceinline__ bool kj_gate_decisive(double z, double p) {
     return true;
 }
 
-__global__ void __launch_bounds__(1024) kj_wta_loop_kernel(const KjWtaLoopArgs a) {
-    __shared__ unsigned long long s_best[32];
-    __shared__ uint32_t s_who[32];
-    __shared__ uint32_t s_winner, s_go;
-    __shared__ unsigned long long s_gone[32];
+__global__ void __launch_bounds__(256) kj_wta_loop_kernel(const KjWtaLoopArgs a) {
+    __shared__ unsigned long long s_best[8];
+    __shared__ uint32_t s_who[8];
+    __shared__ uint32_t s_ctl;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    uint32_t n_rec = 0, status = KJ_LOOP_MORE;
+    const uint64_t gwarp = (uint64_t)blockIdx.x * nw + warp, gwarps = (uint64_t)gridDim.x * nw;
+    uint32_t n_rec = 0, status = KJ_LOOP_MORE, done_rounds = 0;
     for (uint32_t round = 0; round < a.max_rounds; ++round) {
-        // winner = argmax over (uScore desc, first-encounter rank asc)
-        unsigned long long best = 0;
-        uint32_t who = KJ_NONE32;
-        for (uint32_t t = threadIdx.x; t < a.T; t += blockDim.x) {
-            const uint64_t u = kj_ld_volatile(&a.glob[t]);
-            if (!u) continue;
-            const unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(~a.rank[t]);
-            if (key > best) { best = key; who = t; }
-        }
-        for (int d = 16; d > 0; d >>= 1) {
-            const unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
-            const uint32_t ow = __shfl_xor_sync(0xFFFFFFFFu, who, d);
-            if (ob > best) { best = ob; who = ow; }
-        }
-        if (lane == 0) { s_best[warp] = best; s_who[warp] = who; }
-        __syncthreads();
-        if (warp == 0) {
-            best = lane < nw ? s_best[lane] : 0ull;
-            who = lane < nw ? s_who[lane] : KJ_NONE32;
+        if (blockIdx.x == 0) {
+            // winner = argmax over (uScore desc, first-encounter rank asc)
+            unsigned long long best = 0;
+            uint32_t who = KJ_NONE32;
+            for (uint32_t t = threadIdx.x; t < a.T; t += blockDim.x) {
+                const uint64_t u = kj_ld_volatile(&a.glob[t]);
+                if (!u) continue;
+                const unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(~a.rank[t]);
+                if (key > best) { best = key; who = t; }
+            }
             for (int d = 16; d > 0; d >>= 1) {
                 const unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
                 const uint32_t ow = __shfl_xor_sync(0xFFFFFFFFu, who, d);
                 if (ob > best) { best = ob; who = ow; }
             }
-            if (lane == 0) {
+            if (lane == 0) { s_best[warp] = best; s_who[warp] = who; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (uint32_t i = 1; i < nw; ++i) if (s_best[i] > best) { best = s_best[i]; who = s_who[i]; }
                 KjWtaResult r;
                 r.winner = who; r.pad = 0;
                 r.hits = kj_ld_volatile(&a.glob[2 * (uint64_t)a.T]);
-                r.u = 0; r.tau = 0; r.z = 0.0; r.p = 1.0;
-                uint32_t go = 0;
+                r.u = 0; r.tau = 0; r.z = 0.0; r.p = 1.0; r.u0 = 0; r.tau0 = 0;
+                uint32_t ctl = 1;
                 if (who == KJ_NONE32 || r.hits == 0) {
                     status = KJ_LOOP_NO_HITS;
                 } else {
                     r.u = kj_ld_volatile(&a.glob[who]);
                     r.tau = kj_ld_volatile(&a.glob[(uint64_t)a.T + who]);
+                    r.u0 = a.glob0[who];
+                    r.tau0 = a.glob0[(uint64_t)a.T + who];
                     r.z = kj_zscore_f64((double)r.u, (double)a.ulen[who], (double)r.hits, a.unique_lens);
                     r.p = kj_fastp_f64(r.z) * a.n_templates;
                     if (!kj_gate_decisive(r.z, r.p)) status = KJ_LOOP_UNDECIDED;
-                    else if (r.u > 0 && r.p <= 0.05) go = 1;
+                    else if (r.u > 0 && r.p <= 0.05) ctl = 2u + who;
                     else status = KJ_LOOP_REJECTED;
                 }
                 a.res[n_rec] = r;
-                s_winner = who;
-                s_go = go;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned int *>(&a.sync[1 + round]) = ctl;
             }
         }
+        if (threadIdx.x == 0) {
+            unsigned int c;
+            do { c = kj_ld_volatile(&a.sync[1 + round]); } while (c == 0);
+            s_ctl = c;
+        }
         __syncthreads();
+        const uint32_t ctl = s_ctl;
         ++n_rec;
-        if (!s_go) break;
-        // removeWinnerKmers (lib/kmerFinderClient.js:220-230): one warp per matched entry of the winner
-        const uint32_t w = s_winner;
+        if (ctl < 2u) break;
+        // removeWinnerKmers (lib/kmerFinderClient.js:220-230): one warp per matched entry of the winner, the whole grid
+        const uint32_t w = ctl - 2u;
         const uint64_t lo = a.toff[w], hi = a.toff[w + 1];
         unsigned long long gone = 0;
-        for (uint64_t i = lo + warp; i < hi; i += nw) {
+        for (uint64_t i = lo + gwarp; i < hi; i += gwarps) {
             const uint32_t q = a.tq[i];
             const uint8_t was = *reinterpret_cast<volatile uint8_t *>(&a.alive[q]);
             __syncwarp();
@@ -514,18 +591,20 @@ __global__ void __launch_bounds__(1024) kj_wta_loop_kernel(const KjWtaLoopArgs a
                 atomicAdd((unsigned long long *)&a.glob[(uint64_t)a.T + t], 0ull - c);    // tau[t] -= count
             }
         }
-        if (lane == 0) s_gone[warp] = gone;
+        if (lane == 0 && gone) atomicAdd((unsigned long long *)&a.glob[2 * (uint64_t)a.T], 0ull - gone);
+        // grid barrier: every block's removals are in L2 before block 0 takes the next argmax
         __threadfence();
         __syncthreads();
+        ++done_rounds;
         if (threadIdx.x == 0) {
-            unsigned long long g = 0;
-            for (uint32_t i = 0; i < nw; ++i) g += s_gone[i];
-            if (g) atomicAdd((unsigned long long *)&a.glob[2 * (uint64_t)a.T], 0ull - g);
+            atomicAdd(&a.sync[0], 1u);
+            const unsigned int target = done_rounds * gridDim.x;
+            while (kj_ld_volatile(&a.sync[0]) < target) { }
             __threadfence();
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { a.head[0] = n_rec; a.head[1] = status; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.head[0] = n_rec; a.head[1] = status; }
 }
 
 // ------------------------------------------------------------------------------------ database
@@ -682,7 +761,7 @@ extern "C" void kj_match_free(kj_match *m) {
         kj_dfree(ctx, m->d_part);
         kj_dfree(ctx, m->d_first_ord); kj_dfree(ctx, m->d_first_idx); kj_dfree(ctx, m->d_rank);
         kj_dfree(ctx, m->d_toff); kj_dfree(ctx, m->d_tcur); kj_dfree(ctx, m->d_tq); kj_dfree(ctx, m->d_res);
-        kj_dfree(ctx, m->d_loop);
+        kj_dfree(ctx, m->d_loop); kj_dfree(ctx, m->d_glob0); kj_dfree(ctx, m->d_sync);
         kj_pinned_put(ctx, m->h_res);
     }
     delete m;
@@ -929,6 +1008,96 @@ extern "C" int kj_match_from_matched(kj_ctx *ctx, const kj_db *db, uint32_t n_se
     return KJ_OK;
 }
 
+extern "C" uint64_t kj_matched_segment_bytes(uint32_t cap_entries, uint32_t cap_pairs) {
+    const uint64_t b = sizeof(KjMSegHeader) + (uint64_t)cap_entries * 32u + (uint64_t)cap_pairs * 4u;
+    return (b + 255) / 256 * 256;
+}
+
+// the matched entries of this rank into one fixed-capacity segment (stream-ordered, no host wait); query_size = the
+// number of k-mers this rank owns, flags != 0 marks the rank's part of the job as unusable (the gathered match fails)
+extern "C" int kj_match_export_segment(kj_match *m, void *dev_segment, uint32_t cap_entries, uint32_t cap_pairs,
+                                       uint64_t query_size, uint64_t flags) {
+    if (!m || !dev_segment) return KJ_E_INVALID;
+    kj_ctx *ctx = m->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint8_t *seg = reinterpret_cast<uint8_t *>(dev_segment);
+    KJ_LAUNCH(kj_matched_header_kernel, 1, 1, 0, ctx->stream, reinterpret_cast<KjMSegHeader *>(seg),
+              (unsigned long long)query_size, (unsigned long long)flags);
+    ctx->launches++;
+    if (m->Q) {
+        const uint64_t groups = (m->Q + 31) / 32;
+        const int wpb = KJ_SCORE_THREADS / 32;
+        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((groups + wpb - 1) / wpb, (uint64_t)ctx->sm_count * 8));
+        KJ_LAUNCH((kj_matched_export_kernel<false>), grid, KJ_SCORE_THREADS, 0, ctx->stream, m->d, m->d_qkmer, m->qcount,
+                  m->qord, m->alive, m->Q, reinterpret_cast<uint64_t *>(seg + sizeof(KjMSegHeader)), (uint64_t)cap_entries,
+                  reinterpret_cast<uint32_t *>(seg + sizeof(KjMSegHeader) + (uint64_t)cap_entries * 32u), (uint64_t)cap_pairs,
+                  reinterpret_cast<unsigned long long *>(seg));
+        ctx->launches++;
+    }
+    KJ_CUDA(ctx, cudaGetLastError());
+    return KJ_OK;
+}
+
+// a match over the gathered segments of every rank; the buffer must stay valid until kj_match_free.  Sizes, the query
+// size and the flags are read on the device: they surface in kj_match_commit (KJ_E_RANGE when a segment overflowed or
+// a rank flagged its part).
+extern "C" int kj_match_from_segments(kj_ctx *ctx, const kj_db *db, uint32_t n_segments, const void *dev_segments,
+                                      uint32_t cap_entries, uint32_t cap_pairs, kj_match **out) {
+    if (!ctx || !db || !out || !dev_segments || !n_segments || !cap_entries)
+        return kj_fail(ctx, KJ_E_INVALID, "kj_match_from_segments: bad argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t Q = (uint64_t)n_segments * cap_entries;
+    const uint64_t seg_bytes = kj_matched_segment_bytes(cap_entries, cap_pairs);
+    if (2 * Q >= KJ_NONE32 || (uint64_t)n_segments * seg_bytes / 4 >= (1ull << 40))
+        return kj_fail(ctx, KJ_E_RANGE, "too many matched entries for a gathered match");
+    kj_match *m = new kj_match();
+    m->ctx = ctx; m->q = nullptr; m->db = db;
+    m->T = db->n_templates;
+    m->Q = Q;
+    m->from_segments = true;
+    const uint64_t T = m->T;
+    cudaError_t e = kj_dmalloc(ctx, &m->d_qkmer, Q * 4);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->own_count, Q * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->own_ord, Q * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->own_off, 2 * Q * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->own_alive, Q);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_msize, 32);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_part, (2 * T + 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_ord, std::max<uint64_t>(T, 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_idx, std::max<uint64_t>(T, 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_rank, std::max<uint64_t>(T, 1) * 4);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_toff, (T + 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_tcur, std::max<uint64_t>(T, 1) * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_res, sizeof(KjWtaResult));
+    if (e == cudaSuccess) {
+        m->h_res = (KjWtaResult *)kj_pinned_get(ctx);
+        if (!m->h_res) e = cudaErrorMemoryAllocation;
+    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_part, 0, (2 * T + 1) * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_first_ord, 0xFF, std::max<uint64_t>(T, 1) * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_first_idx, 0xFF, std::max<uint64_t>(T, 1) * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->own_alive, 0, Q, ctx->stream);                // the unused tail stays dead
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_qkmer, 0xFF, Q * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_msize, 0, 32, ctx->stream);
+    if (e != cudaSuccess) {
+        kj_match_free(m);
+        return kj_fail(ctx, KJ_E_CUDA, std::string("kj_match_from_segments: ") + cudaGetErrorString(e));
+    }
+    KJ_LAUNCH(kj_matched_import_segments_kernel, kj_grid_for(ctx, Q), 256, 0, ctx->stream,
+              reinterpret_cast<const uint8_t *>(dev_segments), seg_bytes, n_segments, cap_entries, cap_pairs, m->own_count,
+              m->own_ord, m->own_alive, m->d_qkmer, m->own_off, m->d_msize);
+    ctx->launches++;
+    m->d_glob = m->d_part;
+    m->qcount = m->own_count; m->qord = m->own_ord; m->alive = m->own_alive;
+    m->d = KjDbDev{nullptr, nullptr, 0, m->own_off, reinterpret_cast<const uint32_t *>(dev_segments)};
+    int rc = launch_walk<KJ_WALK_ACCUM>(m);
+    if (rc) { kj_match_free(m); return rc; }
+    *out = m;
+    return KJ_OK;
+}
+
 // vectors the host layer reduces over ranks (device memory, caller-provided buffers)
 static int vec_info(kj_match *m, int which, uint64_t **ptr, uint64_t *n) {
     switch (which) {
@@ -998,7 +1167,38 @@ extern "C" int kj_match_set_query_size(kj_match *m, uint64_t kmer_map_size) {
     return KJ_OK;
 }
 
-// first-encounter order, first-round scores, per-template lists of matched query entries
+// u0 / t0 / order / toff_h on the host: what the stepwise calls and the result accessors need.  The hot path
+// (kj_first_match -> kj_wta_all) never does.
+static int ensure_host_first(kj_match *m) {
+    if (m->host_first) return KJ_OK;
+    kj_ctx *ctx = m->ctx;
+    const uint64_t T = m->T;
+    std::vector<uint64_t> ford(T), fidx(T);
+    m->u0.assign(T, 0); m->t0.assign(T, 0); m->toff_h.assign(T + 1, 0);
+    if (T) {
+        KJ_CUDA(ctx, cudaMemcpyAsync(m->u0.data(), m->d_glob0, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KJ_CUDA(ctx, cudaMemcpyAsync(m->t0.data(), m->d_glob0 + T, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KJ_CUDA(ctx, cudaMemcpyAsync(ford.data(), m->d_first_ord, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KJ_CUDA(ctx, cudaMemcpyAsync(fidx.data(), m->d_first_idx, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    KJ_CUDA(ctx, cudaMemcpyAsync(m->toff_h.data(), m->d_toff, (T + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // templates in order of first encounter (lib/kmerFinderServer.js:180-201) = ascending (first ordinal, list index)
+    m->order.clear();
+    for (uint32_t t = 0; t < T; ++t) if (m->u0[t]) m->order.push_back(t);
+    std::sort(m->order.begin(), m->order.end(), [&](uint32_t a, uint32_t b) {
+        if (ford[a] != ford[b]) return ford[a] < ford[b];
+        if (fidx[a] != fidx[b]) return fidx[a] < fidx[b];
+        return a < b;
+    });
+    m->host_first = true;
+    return KJ_OK;
+}
+
+__global__ void kj_toff_first_kernel(uint64_t *toff) { toff[0] = 0; }
+
+// first-encounter rank, first-round scores, per-template lists of matched query entries: all on the device; the host
+// waits once, for the number of hits (it sizes the lists and decides 'No hits were found!')
 extern "C" int kj_match_commit(kj_match *m) {
     if (!m) return KJ_E_INVALID;
     kj_ctx *ctx = m->ctx;
@@ -1012,45 +1212,52 @@ extern "C" int kj_match_commit(kj_match *m) {
         rc = launch_walk<KJ_WALK_FIRST>(m);
         if (rc) return rc;
     }
-    std::vector<uint64_t> glob(2 * T + 1), part_u(T), ford(T), fidx(T);
-    KJ_CUDA(ctx, cudaMemcpyAsync(glob.data(), m->d_glob, (2 * T + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // {global hits, this rank's hits, gathered-segment info[4]} come back in one pinned block
+    unsigned long long *h = reinterpret_cast<unsigned long long *>(m->h_res);
+    KJ_CUDA(ctx, cudaMemcpyAsync(&h[0], m->d_glob + 2 * T, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    KJ_CUDA(ctx, cudaMemcpyAsync(&h[1], m->d_part + 2 * T, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    h[2] = h[3] = h[4] = h[5] = 0;
+    if (m->from_segments) KJ_CUDA(ctx, cudaMemcpyAsync(&h[2], m->d_msize, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    // meanwhile: the first-round scores aside, the first-encounter ranks, the offsets of the per-template lists
+    KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_glob0, std::max<uint64_t>(2 * T, 1) * 8));
     if (T) {
-        KJ_CUDA(ctx, cudaMemcpyAsync(part_u.data(), m->d_part, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        KJ_CUDA(ctx, cudaMemcpyAsync(ford.data(), m->d_first_ord, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        KJ_CUDA(ctx, cudaMemcpyAsync(fidx.data(), m->d_first_idx, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KJ_CUDA(ctx, cudaMemcpyAsync(m->d_glob0, m->d_glob, 2 * T * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        KJ_LAUNCH(kj_rank_kernel, kj_grid_for(ctx, T, 128), 128, 0, ctx->stream, m->d_glob, m->d_first_ord, m->d_first_idx,
+                  (uint32_t)T, m->d_rank);
+        ctx->launches++;
+        KJ_CUDA(ctx, cudaMemsetAsync(m->d_tcur, 0, T * 8, ctx->stream));
+    }
+    KJ_LAUNCH(kj_toff_first_kernel, 1, 1, 0, ctx->stream, m->d_toff);
+    if (T) {
+#ifdef KJ_CPU_EMU
+        for (uint64_t t = 0; t < T; ++t) m->d_toff[t + 1] = m->d_toff[t] + m->d_part[t];
+#else
+        size_t tmp_bytes = 0;
+        void *d_tmp = nullptr;
+        KJ_CUDA(ctx, cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, m->d_part, m->d_toff + 1, (int)T, ctx->stream));
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &d_tmp, std::max<size_t>(tmp_bytes, 16)));
+        cudaError_t e = cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, m->d_part, m->d_toff + 1, (int)T, ctx->stream);
+        kj_dfree(ctx, d_tmp);
+        if (e != cudaSuccess) return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e));
+        ctx->launches += 2;
+#endif
     }
     KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    m->u0.assign(glob.begin(), glob.begin() + T);
-    m->t0.assign(glob.begin() + T, glob.begin() + 2 * T);
-    m->hits0 = glob[2 * T];
-    // templates in order of first encounter (lib/kmerFinderServer.js:180-201: query k-mers in Map
-    // order, each list in DB order) = ascending (first ordinal, list index)
-    m->order.clear();
-    for (uint32_t t = 0; t < T; ++t) if (m->u0[t]) m->order.push_back(t);
-    std::sort(m->order.begin(), m->order.end(), [&](uint32_t a, uint32_t b) {
-        if (ford[a] != ford[b]) return ford[a] < ford[b];
-        if (fidx[a] != fidx[b]) return fidx[a] < fidx[b];
-        return a < b;
-    });
-    std::vector<uint32_t> rank(T, KJ_NONE32 - 1);
-    for (uint32_t i = 0; i < m->order.size(); ++i) rank[m->order[i]] = i;
-    // CSR of this rank's matched entries per template (sized by the partial uScores)
-    std::vector<uint64_t> toff(T + 1, 0);
-    for (uint64_t t = 0; t < T; ++t) toff[t + 1] = toff[t] + part_u[t];
-    const uint64_t local_pairs = toff[T];
-    m->toff_h = toff;
+    if (m->from_segments) {
+        if (h[5])
+            return kj_fail(ctx, KJ_E_RANGE, (h[5] & 2) ? "gathered match: a segment overflowed its capacity"
+                                                       : "gathered match: a rank flagged its part of the job");
+        m->kmer_map_size = h[4];
+        m->seg_entries = h[2]; m->seg_pairs = h[3];
+    }
+    m->hits0 = h[0];
+    const uint64_t local_pairs = h[1];
     if (local_pairs > 0xFFFFFFF0ull * 16) return kj_fail(ctx, KJ_E_RANGE, "too many matched pairs");
     kj_dfree(ctx, m->d_tq);
     m->d_tq = nullptr;
     KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_tq, std::max<uint64_t>(local_pairs, 1) * 4));
-    if (T) {
-        KJ_CUDA(ctx, cudaMemcpyAsync(m->d_rank, rank.data(), T * 4, cudaMemcpyHostToDevice, ctx->stream));
-        KJ_CUDA(ctx, cudaMemsetAsync(m->d_tcur, 0, T * 8, ctx->stream));
-    }
-    KJ_CUDA(ctx, cudaMemcpyAsync(m->d_toff, toff.data(), (T + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rc = launch_walk<KJ_WALK_FILL>(m);
+    rc = launch_walk<KJ_WALK_FILL>(m);        // stream-ordered: whoever reads the lists comes later on the same stream
     if (rc) return rc;
-    KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // rank/toff are host vectors
     m->committed = true;
     return KJ_OK;
 }
@@ -1071,11 +1278,21 @@ extern "C" int kj_first_match(kj_ctx *ctx, kj_counts *q, const kj_db *db, kj_mat
 }
 
 extern "C" uint64_t kj_match_hits(const kj_match *m) { return m ? m->hits0 : 0; }
-extern "C" uint32_t kj_match_n_matched(const kj_match *m) { return m ? (uint32_t)m->order.size() : 0; }
+extern "C" uint64_t kj_match_query_size(const kj_match *m) { return m ? m->kmer_map_size : 0; }
+extern "C" int kj_match_segment_sizes(const kj_match *m, uint64_t *n_entries, uint64_t *n_pairs) {
+    if (!m || !n_entries || !n_pairs) return KJ_E_INVALID;
+    *n_entries = m->seg_entries; *n_pairs = m->seg_pairs;
+    return KJ_OK;
+}
+extern "C" uint32_t kj_match_n_matched(const kj_match *m) {
+    if (!m || !m->committed || ensure_host_first(const_cast<kj_match *>(m))) return 0;
+    return (uint32_t)m->order.size();
+}
 
 extern "C" int kj_match_scores(kj_match *m, uint64_t *uscore, uint64_t *tscore, uint32_t *order) {
     if (!m) return KJ_E_INVALID;
     if (!m->committed) return kj_fail(m->ctx, KJ_E_STATE, "kj_match_commit has not run");
+    { int rc0 = ensure_host_first(m); if (rc0) return rc0; }
     if (uscore) memcpy(uscore, m->u0.data(), m->u0.size() * 8);
     if (tscore) memcpy(tscore, m->t0.data(), m->t0.size() * 8);
     if (order) memcpy(order, m->order.data(), m->order.size() * 4);
@@ -1094,6 +1311,7 @@ extern "C" int kj_match_template_kmers(kj_match *m, uint32_t template_id, uint64
     if (template_id >= m->T) return kj_fail(ctx, KJ_E_INVALID, "template id out of range");
     if (!m->q) return kj_fail(ctx, KJ_E_STATE, "a gathered match has no counts handle: ask the local match");
     KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    { int rc0 = ensure_host_first(m); if (rc0) return rc0; }
     const uint64_t lo = m->toff_h[template_id], hi = m->toff_h[template_id + 1];
     *n_out = hi - lo;
     if (!idx || hi == lo) return KJ_OK;
@@ -1120,6 +1338,7 @@ extern "C" int kj_match_set_max_hits(kj_match *m, uint32_t max_hits) {
 // removeWinnerKmers (lib/kmerFinderClient.js:220-230) on this rank's share of K_w
 static int wta_launch_remove(kj_match *m, uint32_t w) {
     kj_ctx *ctx = m->ctx;
+    { int rc0 = ensure_host_first(m); if (rc0) return rc0; }
     const uint64_t range[2] = {m->toff_h[w], m->toff_h[w + 1]};
     if (range[1] > range[0]) {
         const uint64_t n = range[1] - range[0];
@@ -1138,6 +1357,7 @@ extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (!m->committed) return kj_fail(ctx, KJ_E_STATE, "kj_match_commit has not run");
     KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    { int rc0 = ensure_host_first(m); if (rc0) return rc0; }
     memset(out, 0, sizeof(*out));
     // while (notFound && hitCounter < maxHits)   lib/kmerFinderClient.js:274
     if (m->ended || m->hit_counter >= m->max_hits) {
@@ -1266,7 +1486,7 @@ static int wta_all_device(kj_match *m, kj_row *rows, uint32_t cap, uint32_t *n_r
     auto exact = [&](const KjWtaResult &r, kj_row *out, int *accepted) -> int {
         const uint32_t w = r.winner;
         memset(out, 0, sizeof(*out));
-        if (!kj_exact_row(ctx->rounding_mode, r.u, r.tau, m->u0[w], m->t0[w], m->db->lengths[w], m->db->ulengths[w],
+        if (!kj_exact_row(ctx->rounding_mode, r.u, r.tau, r.u0, r.tau0, m->db->lengths[w], m->db->ulengths[w],
                           r.hits, m->kmer_map_size, m->db->s_templates, m->db->s_unique_lens, out, accepted))
             return kj_fail(ctx, KJ_E_INVALID, "template with zero length / ulength or zero Summary.uniqueLens");
         out->template_id = w;
@@ -1274,18 +1494,37 @@ static int wta_all_device(kj_match *m, kj_row *rows, uint32_t cap, uint32_t *n_r
         out->probability_device = r.p;
         return KJ_OK;
     };
+    // the loop kernel's blocks wait for each other: all of them must be resident at once
+    int loop_grid = 1;
+#ifndef KJ_CPU_EMU
+    {
+        int per_sm = 0;
+        KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_wta_loop_kernel, 256, 0));
+        loop_grid = std::max(1, std::min(ctx->sm_count, per_sm * ctx->sm_count));
+    }
+#endif
+    if (!m->d_sync) KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_sync, (size_t)(per_launch + 2) * 4));
     for (;;) {
         // while (notFound && hitCounter < maxHits)   lib/kmerFinderClient.js:274
         if (m->hit_counter >= m->max_hits) { m->ended = true; break; }
         const uint32_t rounds = std::min<uint32_t>(per_launch, m->max_hits - m->hit_counter);
         KjWtaLoopArgs a{};
-        a.d = m->d; a.glob = m->d_glob; a.rank = m->d_rank; a.ulen = m->db->d_ulen; a.toff = m->d_toff;
+        a.d = m->d; a.glob = m->d_glob; a.glob0 = m->d_glob0; a.rank = m->d_rank; a.ulen = m->db->d_ulen; a.toff = m->d_toff;
+        a.sync = m->d_sync;
         a.tq = m->d_tq; a.qkmer = m->d_qkmer; a.qcount = m->qcount; a.alive = m->alive;
         a.T = m->T; a.max_rounds = rounds;
         a.unique_lens = (double)m->db->s_unique_lens; a.n_templates = (double)m->db->s_templates;
         a.head = reinterpret_cast<uint32_t *>(m->d_loop);
         a.res = reinterpret_cast<KjWtaResult *>(reinterpret_cast<uint8_t *>(m->d_loop) + 16);
-        KJ_LAUNCH(kj_wta_loop_kernel, 1, 1024, 0, ctx->stream, a);
+        KJ_CUDA(ctx, cudaMemsetAsync(m->d_sync, 0, (size_t)(rounds + 2) * 4, ctx->stream));
+#ifdef KJ_CPU_EMU
+        KJ_LAUNCH(kj_wta_loop_kernel, 1, 256, 0, ctx->stream, a);
+#else
+        {
+            void *kargs[1] = {(void *)&a};
+            KJ_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kj_wta_loop_kernel, dim3(loop_grid), dim3(256), kargs, 0, ctx->stream));
+        }
+#endif
         ctx->launches++;
         KJ_CUDA(ctx, cudaGetLastError());
         KJ_CUDA(ctx, cudaMemcpyAsync(ctx->h_wta, m->d_loop, 16 + (size_t)(rounds + 1) * sizeof(KjWtaResult),
@@ -1319,7 +1558,7 @@ static int wta_all_device(kj_match *m, kj_row *rows, uint32_t cap, uint32_t *n_r
         if (accepted) {                         // undecided on the device, accepted by the exact arithmetic
             rows[n++] = tmp;
             m->hit_counter++;
-            rc = wta_launch_remove(m, last.winner);
+            rc = wta_launch_remove(m, last.winner);      // (fetches the host copy of the list offsets: a rare path)
             if (rc) return rc;
             continue;
         }
@@ -1375,6 +1614,7 @@ extern "C" int kj_standard_scoring(kj_match *m, kj_row *rows, uint32_t n_rows_ca
     if (!m || !n_rows) return KJ_E_INVALID;
     kj_ctx *ctx = m->ctx;
     if (!m->committed) return kj_fail(ctx, KJ_E_STATE, "kj_match_commit has not run");
+    { std::lock_guard<std::recursive_mutex> lk(ctx->mu); int rc0 = ensure_host_first(m); if (rc0) return rc0; }
     std::vector<kj_row> all;
     for (uint32_t t : m->order) {
         kj_row r;

@@ -140,6 +140,7 @@ def exchange_counts(local: Counts, group=None, trace=None) -> Counts:
     recv = exchange_records(send, sizes, group)
     torch.cuda.synchronize(dev)
     tr.mark("x.all_to_all")
+    x_seen = [max(sizes) if sizes else 0, 0]        # what the fixed-capacity exchange would have needed per peer
     owned = Counts(local.prefix, local.k, local.step, flags=local.flags & ~(_abi.KJ_F_FORWARD_ONLY),
                    capacity_hint=max(int(recv.shape[0]), 1024), ctx=local.ctx)
     if recv.shape[0]:
@@ -183,6 +184,11 @@ def exchange_counts(local: Counts, group=None, trace=None) -> Counts:
     owned.set_totals(lines, bases, occ, nbytes)
     owned.global_size = None        # kmerMap.size over all ranks: global_size() / DistMatch fill it in
     tr.mark("x.set_totals")
+    # learn the capacities of the fixed-capacity exchange from what all ranks saw (identical on every rank)
+    x_seen[1] = max(sizes_irr) // 56
+    mx = torch.tensor(x_seen, dtype=torch.int64, device=dev)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    owned._seen = [int(v) for v in mx.tolist()]
     return owned
 
 
@@ -198,11 +204,73 @@ def global_size(owned: Counts, group=None) -> int:
     return owned.global_size
 
 
+# Capacities of the fixed-capacity exchange, learned from the sizes the two-phase exchange saw for the same kind of
+# job: {(device, world, prefix, k, step): (records per peer, irregular records per peer, matched entries, matched pairs)}.
+# Every rank derives them from the same collective results, so all ranks take the same path.
+_CAPS = {}
+_XBUF = {}
+
+
+def _caps_key(ctx, world, prefix, k, step):
+    return (ctx.device if ctx else 0, world, bytes(prefix), int(k), int(step))
+
+
+def _round_cap(n: int, floor: int) -> int:
+    """1.5 x what was seen, rounded up to a multiple of 1024."""
+    return max(floor, (int(n * 1.5) + 1023) // 1024 * 1024)
+
+
+def _xbuf(dev, name: str, nbytes: int):
+    """Persistent device buffers of the exchange (allocated once per size)."""
+    import torch
+    key = (dev.index, name)
+    t = _XBUF.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _XBUF[key] = t
+    return t[:nbytes]
+
+
+def exchange_counts_fixed(local: Counts, caps, group=None, torch_stream=None) -> Counts:
+    """Local table -> the table of the k-mers this rank owns, with ONE equal-split all-to-all and no host wait before
+    it: the sender scatters its table into per-owner segments of fixed capacity (record counts and its totals in the
+    segment headers), the owner merges what it receives, counts read on the device.  Overflow surfaces as KjError in
+    the returned handle's finish(), which the caller has not called yet."""
+    import contextlib
+    import torch
+    import torch.distributed as dist
+    from .counts import segment_bytes
+    world = dist.get_world_size(group)
+    dev = torch.device(f"cuda:{local.ctx.device}")
+    cap_reg, cap_irr = caps[0], caps[1]
+    seg = segment_bytes(cap_reg, cap_irr)
+    send = _xbuf(dev, "send", world * seg)
+    recv = _xbuf(dev, "recv", world * seg)
+    ordered = torch.cuda.stream(torch_stream) if torch_stream is not None else contextlib.nullcontext()
+    with ordered:
+        local.partition_segments(world, send.data_ptr(), cap_reg, cap_irr)
+        if torch_stream is None:
+            torch.cuda.synchronize(dev)
+        dist.all_to_all_single(recv, send, group=group)
+        if torch_stream is None:
+            torch.cuda.synchronize(dev)
+        owned = Counts(local.prefix, local.k, local.step, flags=local.flags & ~(_abi.KJ_F_FORWARD_ONLY),
+                       capacity_hint=world * cap_reg, ctx=local.ctx)
+        owned.merge_segments(recv.data_ptr(), world, cap_reg, cap_irr)
+    owned.global_size = None
+    return owned
+
+
 def count_sharded(dev_ptr: int, n_own: int, n_read: int, *, prefix=b"ATGAC", k=16, step=1, final: bool,
                   base_line: int | None = None, base_col: int = 0, capacity_hint: int = 0, flags: int = 0,
-                  group=None, ctx=None, trace=None) -> Counts:
+                  group=None, ctx=None, trace=None, torch_stream=None, fixed: bool = True) -> Counts:
     """Count this rank's byte range and exchange.  With base_line None the ranks agree on the record
-    phase first (newline counts of the owned ranges, allgathered)."""
+    phase first (newline counts of the owned ranges, allgathered).
+
+    With a capacity hint, once a job of the same kind has gone through the two-phase exchange on these ranks, the
+    fixed-capacity exchange is used (`fixed`): nothing waits on the host between counting and the owner's finish().
+    If it overflows, finish() raises KjError(KJ_E_RANGE) on every affected rank and DistMatch / the caller falls back
+    (redo with fixed=False)."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -221,6 +289,12 @@ def count_sharded(dev_ptr: int, n_own: int, n_read: int, *, prefix=b"ATGAC", k=1
     tr.mark("c.create")
     local.add_device(dev_ptr, n_read, own_n=n_own, final=final)
     tr.mark("c.add_device")
+    caps = _CAPS.get(_caps_key(local.ctx, world, prefix, k, step))
+    if fixed and capacity_hint and caps is not None and trace is None:
+        owned = exchange_counts_fixed(local, caps, group, torch_stream)
+        owned._local = local            # its table backs nothing any more, but its buffers must outlive the queued kernels
+        owned._fixed_caps = caps
+        return owned
     local.finish()
     tr.mark("c.finish_local")
     owned = exchange_counts(local, group, trace)
@@ -228,6 +302,27 @@ def count_sharded(dev_ptr: int, n_own: int, n_read: int, *, prefix=b"ATGAC", k=1
     local.free()
     tr.mark("c.free_local")
     return owned
+
+
+class ExchangeRetry(RuntimeError):
+    """The fixed-capacity exchange did not fit (on some rank): every rank raises this at the same point; redo the job
+    with count_sharded(..., fixed=False).  count_and_match() does that by itself."""
+
+
+def count_and_match(dev_ptr: int, n_own: int, n_read: int, db, *, torch_stream=None, mode: str = "auto", group=None, **kw):
+    """count_sharded + DistMatch with the fall-back from the fixed-capacity exchange handled: (owned, dist_match)."""
+    if mode == "reduce":
+        kw["fixed"] = False                     # the per-round all-reduce keeps the matched set sharded: two-phase exchange
+    owned = count_sharded(dev_ptr, n_own, n_read, torch_stream=torch_stream, group=group, **kw)
+    try:
+        return owned, DistMatch(owned, db, group=group, torch_stream=torch_stream, mode=mode)
+    except ExchangeRetry:
+        _CAPS.pop(_caps_key(owned.ctx, __import__("torch").distributed.get_world_size(group), owned.prefix, owned.k, owned.step), None)
+        getattr(owned, "_local", owned).free()
+        owned.free()
+        kw["fixed"] = False
+        owned = count_sharded(dev_ptr, n_own, n_read, torch_stream=torch_stream, group=group, **kw)
+        return owned, DistMatch(owned, db, group=group, torch_stream=torch_stream, mode=mode)
 
 
 class DistMatch:
@@ -250,11 +345,19 @@ class DistMatch:
             raise ValueError(mode)
         self.group = group
         self.torch_stream = torch_stream
+        self.m = self.local = None
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         self.dev = torch.device(f"cuda:{owned.ctx.device}")
+        self._buf = {}
+        self._gathered = None
+        caps = getattr(owned, "_fixed_caps", None)
+        if caps is not None:
+            if mode == "reduce":
+                raise ValueError("a handle from the fixed-capacity exchange goes with the gathered match (mode 'auto' or 'gather')")
+            self._init_fixed(owned, db, caps, world, rank)
+            return
         self.local = Match(owned, db, local_only=True, part=rank, n_parts=world)
         self.m = self.local
-        self._buf = {}
         ne, npairs = self.local.matched_size()
         sz = torch.tensor([ne, npairs, owned.size], dtype=torch.int64, device=self.dev)
         all_sz = torch.empty((world, 3), dtype=torch.int64, device=self.dev)
@@ -275,6 +378,57 @@ class DistMatch:
         self.m.set_query_size(qsize)
         self.m.commit()
         self._gathered = None
+        seen = getattr(owned, "_seen", None)
+        if seen is not None and self.mode == "gather":
+            # what the fixed-capacity exchange of the next job of this kind will be sized for
+            _CAPS[_caps_key(owned.ctx, world, owned.prefix, owned.k, owned.step)] = (
+                _round_cap(seen[0], 4096), _round_cap(seen[1], 1024),
+                _round_cap(max(a for a, _ in sizes), 4096), _round_cap(max(b for _, b in sizes), 4096))
+        if self.m.hits == 0:
+            raise NoHitsError("No hits were found!")
+
+    def _init_fixed(self, owned, db, caps, world, rank):
+        """The lean path: owner tables merged from fixed-capacity segments (not finished yet), matched entries
+        gathered in fixed-capacity segments.  Three host waits in all: the owner's finish(), the commit, the rows."""
+        import contextlib
+        import torch
+        import torch.distributed as dist
+        from .matching import matched_segment_bytes
+        cap_e, cap_p = caps[2], caps[3]
+        seg = matched_segment_bytes(cap_e, cap_p)
+        mine = _xbuf(self.dev, "mseg", seg)
+        allb = _xbuf(self.dev, "mall", world * seg)
+        ok = True
+        try:
+            owned.finish()
+        except _abi.KjError as exc:
+            if exc.code != _abi.KJ_E_RANGE:
+                raise
+            ok = False                                  # this rank's exchange overflowed: tell everybody
+        ordered = torch.cuda.stream(self.torch_stream) if self.torch_stream is not None else contextlib.nullcontext()
+        self.local = None
+        with ordered:
+            if ok:
+                self.local = Match(owned, db, local_only=True, part=rank, n_parts=world)
+                self.local.export_segment(mine.data_ptr(), cap_e, cap_p, owned.size, 0)
+            else:
+                mine[:32].copy_(torch.tensor([0, 0, 0, 1], dtype=torch.int64).view(torch.uint8), non_blocking=False)
+            if self.torch_stream is None:
+                torch.cuda.synchronize(self.dev)
+            dist.all_gather_into_tensor(allb.view(world, seg), mine, group=self.group)
+            if self.torch_stream is None:
+                torch.cuda.synchronize(self.dev)
+            self.m = Match.from_segments(owned.ctx, db, world, allb.data_ptr(), cap_e, cap_p, part=rank, n_parts=world)
+        self._gathered = (mine, allb)                   # the template lists are used in place
+        self.mode = "gather"
+        try:
+            self.m.commit()
+        except _abi.KjError as exc:
+            if exc.code != _abi.KJ_E_RANGE:
+                raise
+            self.free()
+            raise ExchangeRetry(str(exc)) from exc
+        owned.global_size = self.m.query_size
         if self.m.hits == 0:
             raise NoHitsError("No hits were found!")
 
@@ -343,6 +497,8 @@ class DistMatch:
             yield row
 
     def free(self):
-        if self.m is not self.local:
+        if getattr(self, "m", None) is not None and self.m is not self.local:
             self.m.free()
-        self.local.free()
+        if getattr(self, "local", None) is not None:
+            self.local.free()
+        self.m = self.local = None

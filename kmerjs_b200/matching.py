@@ -18,6 +18,10 @@ class NoHitsError(RuntimeError):
     """'No hits were found!' family (lib/kmerFinderClient.js:161,265,284)."""
 
 
+def matched_segment_bytes(cap_entries: int, cap_pairs: int) -> int:
+    return int(_abi.lib().kj_matched_segment_bytes(cap_entries, cap_pairs))
+
+
 def row_to_dict(r: _abi.kj_row, db: TemplateDB) -> dict:
     def num(x):                      # JS numbers: 108 prints as 108, not 108.0
         return int(x) if float(x).is_integer() and abs(x) < 2 ** 53 else float(x)
@@ -61,6 +65,36 @@ class Match:
         self.handle = h
         self.last_row = None
         return self
+
+    @classmethod
+    def from_segments(cls, ctx, db: TemplateDB, n_segments: int, dev_ptr: int, cap_entries: int, cap_pairs: int, *,
+                      part: int = 0, n_parts: int = 1):
+        """A match over the fixed-capacity segments of all ranks (kj_match_from_segments): the gathered buffer at
+        dev_ptr must outlive the match.  Sizes and flags are checked by commit()."""
+        self = cls.__new__(cls)
+        self.counts, self.db, self.ctx = None, db, ctx
+        self._L = _abi.lib()
+        self._dbh = db.device(ctx, part, n_parts)
+        h = C.c_void_p()
+        _abi.check(self._L.kj_match_from_segments(ctx.handle, self._dbh.handle, n_segments, C.c_void_p(dev_ptr),
+                                                  cap_entries, cap_pairs, C.byref(h)), ctx.handle)
+        self.handle = h
+        self.last_row = None
+        return self
+
+    def export_segment(self, dev_ptr: int, cap_entries: int, cap_pairs: int, query_size: int, flags: int = 0):
+        """This rank's matched entries as one fixed-capacity segment (stream-ordered, kj_match_export_segment)."""
+        _abi.check(self._L.kj_match_export_segment(self.handle, C.c_void_p(dev_ptr), cap_entries, cap_pairs,
+                                                   int(query_size), int(flags)), self.ctx.handle)
+
+    @property
+    def query_size(self) -> int:
+        return int(self._L.kj_match_query_size(self.handle))
+
+    def segment_sizes(self):
+        ne, np_ = C.c_uint64(), C.c_uint64()
+        _abi.check(self._L.kj_match_segment_sizes(self.handle, C.byref(ne), C.byref(np_)), self.ctx.handle)
+        return int(ne.value), int(np_.value)
 
     # -- distributed protocol ---------------------------------------------------------------------
     def matched_size(self):

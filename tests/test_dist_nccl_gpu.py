@@ -52,6 +52,31 @@ def _worker(rank, world, port, q):
             out[mode] = dict(size=owned.global_size, lines=owned.lines, hits=dm.hits, order=list(dm.templates()),
                              rows=rows, err=err, counts=owned.to_dict())
             dm.free(); owned.free()
+        # the lean path: after the two-phase exchange above has been seen, the same kind of job goes through the
+        # fixed-capacity exchange (one all-to-all, one all-gather, no size round trips); then with capacities that are
+        # too small: every rank must fall back together and still get the same answer
+        for name, force in (("fixed", None), ("fixed-overflow", (256, 16, 256, 256))):
+            key = kdist._caps_key(ctx, world, b"ATGAC", 16, 1)
+            assert key in kdist._CAPS
+            if force:
+                kdist._CAPS[key] = force
+            owned, dm = kdist.count_and_match(w.fastq_ptr, w.n_bytes, w.n_bytes, tdb, torch_stream=stream, mode="auto",
+                                              prefix=b"ATGAC", k=16, step=1, final=True, base_line=rank * n_reads * 4,
+                                              capacity_hint=1 << 18, ctx=ctx)
+            took_fixed = getattr(owned, "_fixed_caps", None) is not None
+            assert took_fixed == (force is None), (name, took_fixed)
+            rows, err = [], None
+            try:
+                for r in dm.rows():
+                    rows.append(r)
+            except NoHitsError as exc:
+                err = str(exc)
+            out[name] = dict(size=owned.global_size, lines=owned.lines, hits=dm.hits, order=list(dm.templates()),
+                             rows=rows, err=err, counts=owned.to_dict())
+            dm.free()
+            if getattr(owned, "_local", None) is not None:
+                owned._local.free()
+            owned.free()
         if rank == 0:      # single-GPU truth over the reads of all ranks
             w2 = synth.Workload(n_reads=world * n_reads, genome_len=1_000_000, seed=5, first_read=0, ctx=ctx)
             c = Counts(b"ATGAC", 16, 1, ctx=ctx)
@@ -107,12 +132,14 @@ def test_two_ranks_equal_single_gpu():
     assert len(single["rows"]) >= 1
     merged = {}
     for rank in range(world):
-        for mode in ("sync", "stream", "gather-sync", "gather-stream"):
+        for mode in ("sync", "stream", "gather-sync", "gather-stream", "fixed", "fixed-overflow"):
             o = res[rank][mode]
             for f in ("size", "lines", "hits", "order", "rows", "err"):
                 assert o[f] == single[f], (rank, mode, f)
         assert not (set(res[rank]["sync"]["counts"]) & set(merged))       # every k-mer has one owner
         merged.update(res[rank]["sync"]["counts"])
+        assert res[rank]["fixed"]["counts"] == res[rank]["sync"]["counts"]
+        assert list(res[rank]["fixed"]["counts"]) == list(res[rank]["sync"]["counts"])      # Map order too
     assert merged == single["counts"]
     # the oracle: the merged map of the two ranks key for key, the single-GPU map in Map order, and the rows
     oracle = res[0]["oracle"]

@@ -313,7 +313,7 @@ def run_b200(args):
         tdb.device(ctx, rank, world)            # DB resident in HBM before the timed region (the reference's Redis is up)
     scoring = tdb is not None
     # distinct k-mers one GPU meets: error variants dominate (c3: 175 k from 2.6 M occurrences)
-    hint = (1 << 20) * max(1, n_reads // 10_000_000) if PREFIX else 0
+    hint = (1 << 18) * max(1, n_reads // 10_000_000) if PREFIX else 0
     state = {}
     trace = {}
 

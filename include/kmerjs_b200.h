@@ -188,6 +188,23 @@ typedef struct kj_db_desc {
 } kj_db_desc;
 
 int kj_db_create(kj_ctx *ctx, const kj_db_desc *d, kj_db **out);
+/* From disk (the step before the path): the reference's own JSON layouts and a versioned packed binary.
+ *   KJ_DB_KMER_DOCS       [{"kmer", "templates": [{"sequence","lengths","ulengths","species"}]}]  lib/kmerFinderServer.js:68-92,184-199
+ *   KJ_DB_TEMPLATE_DOCS   [{"sequence","lengths","ulenght","species","reads":[..]}]                src/kmerPyToMongo.py:35-42
+ *   KJ_DB_KMERFINDER_MAP  {kmer: "T1,T2,.."} + <path>.lengths.json / .ulengths.json / .descriptions.json   lib/index.js:184-192
+ *   KJ_DB_PACKED          written by kj_db_save_packed
+ *   KJ_DB_AUTO            decided from the content
+ * summary_path: a Summary record {"templates","uniqueLens","totalLen"} (lib/kmerFinderServer.js:716-724); NULL derives it
+ * from the templates (packed files carry their own).  part / n_parts as in kj_db_desc. */
+enum { KJ_DB_AUTO = 0, KJ_DB_KMER_DOCS = 1, KJ_DB_TEMPLATE_DOCS = 2, KJ_DB_KMERFINDER_MAP = 3, KJ_DB_PACKED = 4 };
+int kj_db_load(kj_ctx *ctx, const char *path, int format, const char *summary_path, uint32_t part, uint32_t n_parts,
+               kj_db **out);
+/* write a host description as the packed binary (names / species: n_templates C strings, may be NULL); needs no device */
+int kj_db_save_packed(const char *path, const kj_db_desc *d, const char *const *names, const char *const *species);
+/* template attributes (name / species are empty strings unless the database came through kj_db_load) and the Summary */
+int kj_db_template(const kj_db *db, uint32_t id, const char **name, const char **species, uint64_t *lengths,
+                   uint64_t *ulength);
+int kj_db_summary(const kj_db *db, uint64_t *templates, uint64_t *unique_lens, uint64_t *total_len);
 void kj_db_free(kj_db *db);
 uint64_t kj_db_n_kmers(const kj_db *db);
 uint64_t kj_db_n_pairs(const kj_db *db);            /* (k-mer, template) pairs held */

@@ -16,6 +16,7 @@ KJ_E_TABLE_FULL, KJ_E_NO_HITS, KJ_E_NO_WINNER, KJ_E_RANGE, KJ_E_STATE = -6, -7, 
 KJ_MEM_HOST, KJ_MEM_DEVICE = 0, 1
 KJ_F_NO_ORDER, KJ_F_FORCE_GENERIC, KJ_F_FORWARD_ONLY, KJ_F_NO_LINE_GATE, KJ_F_COUNT_BASES = 1, 2, 4, 8, 16
 KJ_VEC_SCORES, KJ_VEC_FIRST_ORD, KJ_VEC_FIRST_IDX = 0, 1, 2
+KJ_DB_AUTO, KJ_DB_KMER_DOCS, KJ_DB_TEMPLATE_DOCS, KJ_DB_KMERFINDER_MAP, KJ_DB_PACKED = 0, 1, 2, 3, 4
 KJ_ABI_VERSION = 1
 
 u8p = C.POINTER(C.c_uint8)
@@ -101,6 +102,10 @@ SIGNATURES = {
     "kj_counts_set_totals": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "kj_owner": (C.c_uint32, [C.c_char_p, C.c_uint32, C.c_uint32]),
     "kj_db_create": (C.c_int, [vp, C.POINTER(kj_db_desc), C.POINTER(vp)]),
+    "kj_db_load": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "kj_db_save_packed": (C.c_int, [C.c_char_p, C.POINTER(kj_db_desc), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]),
+    "kj_db_template": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), u64p, u64p]),
+    "kj_db_summary": (C.c_int, [vp, u64p, u64p, u64p]),
     "kj_db_free": (None, [vp]),
     "kj_db_n_kmers": (C.c_uint64, [vp]),
     "kj_db_n_pairs": (C.c_uint64, [vp]),

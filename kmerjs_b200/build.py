@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("KMERJS_B200_LIB") or os.path.join(HERE, "libkmerjs_b200.so")     # override: kernel variants side by side (tuning)
-SOURCES = ["kj_ctx.cu", "kj_count.cu", "kj_score.cu", "kj_synth.cu", "kj_stats.cpp"]
+SOURCES = ["kj_ctx.cu", "kj_count.cu", "kj_score.cu", "kj_dbio.cu", "kj_synth.cu", "kj_stats.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",

@@ -72,7 +72,7 @@ __global__ void kj_replay_irr_kernel(KjIrrTable t, KjCounters *ctr, const uint8_
 
 // one atomic per warp: ballot the occupied slots, lane 0 claims a run of output positions
 __global__ void kj_compact_kernel(KjTable t, uint64_t cap, KjCounters *ctr, uint64_t *keys,
-                                  uint64_t *counts, uint64_t *ords) {
+                                  uint64_t *counts, uint64_t *ords, uint64_t out_cap) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t rounds = (cap + stride - 1) / stride;       // same trip count for every thread
@@ -87,6 +87,7 @@ __global__ void kj_compact_kernel(KjTable t, uint64_t cap, KjCounters *ctr, uint
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (have) {
             uint64_t o = base + __popc(b & ((1u << lane) - 1u));
+            if (o >= out_cap) continue;                  // sized by a hint that was too small: the host sees n_compact and repeats
             keys[o] = key;
             counts[o] = t.counts[i];
             ords[o] = t.ords ? t.ords[i] : ~0ull;
@@ -95,12 +96,13 @@ __global__ void kj_compact_kernel(KjTable t, uint64_t cap, KjCounters *ctr, uint
 }
 
 __global__ void kj_compact_irr_kernel(KjIrrTable t, uint64_t cap, KjCounters *ctr,
-                                      KjIrrRecord *out) {
+                                      KjIrrRecord *out, uint64_t out_cap) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap;
          i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t st = t.state[i];
         if (st < 2) continue;
         unsigned long long o = atomicAdd(&ctr->n_irr_compact, 1ull);
+        if (o >= out_cap) continue;
         const uint64_t *src = reinterpret_cast<const uint64_t *>(t.keys + i * 32);
         uint64_t *dst = reinterpret_cast<uint64_t *>(out[o].key);
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
@@ -568,35 +570,37 @@ static int make_tensor_map(kj_ctx *ctx, const uint8_t *dbuf, uint64_t n, KjTenso
 }
 
 typedef void (*KjFilterFn)(const KjTensorMap, const KjScanArgs);
-static KjFilterFn pick_filter_kernel(const KjScanArgs &a) {
+template <int KW>
+static KjFilterFn pick_filter_kernel_kw(const KjScanArgs &a) {
     switch (a.mp) {
-        case 1: return kj_warp_filter_kernel<1>;
-        case 2: return kj_warp_filter_kernel<2>;
-        case 3: return kj_warp_filter_kernel<3>;
-        case 4: return kj_warp_filter_kernel<4>;
-        case 5: return kj_warp_filter_kernel<5>;
-        case 6: return kj_warp_filter_kernel<6>;
-        case 7: return kj_warp_filter_kernel<7>;
-        default: return kj_warp_filter_kernel<8>;
+        case 1: return kj_warp_filter_kernel<1, KW>;
+        case 2: return kj_warp_filter_kernel<2, KW>;
+        case 3: return kj_warp_filter_kernel<3, KW>;
+        case 4: return kj_warp_filter_kernel<4, KW>;
+        case 5: return kj_warp_filter_kernel<5, KW>;
+        case 6: return kj_warp_filter_kernel<6, KW>;
+        case 7: return kj_warp_filter_kernel<7, KW>;
+        default: return kj_warp_filter_kernel<8, KW>;
     }
 }
+static KjFilterFn pick_filter_kernel(const KjScanArgs &a) {
+    return a.k <= 16 ? pick_filter_kernel_kw<4>(a) : pick_filter_kernel_kw<8>(a);
+}
 
-// scan -> exclusive scan of the tile counts -> filter (entries -> items) -> emit (items -> table), all stream-ordered;
-// retry_only: the emit pass over the marked items; items_only: from the filter on (the item buffer was too small)
-static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only, bool items_only = false) {
+// scan (with the byte check of the candidates) -> exclusive scan of the tile counts -> resolve, all stream-ordered;
+// retry_only: the resolve pass over the marked entries
+static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only) {
     kj_ctx *ctx = c->ctx;
     KjScanArgs &a = pc.args;
     a.tab = c->tab; a.irr = c->irr; a.ovf = c->ovf;
     a.cand = c->cand; a.cand_cap = c->cand_cap;
-    a.items = c->items; a.item_cap = c->item_cap;
     a.tile_cnt = c->tile_cnt; a.tile_excl = c->tile_mem;
     a.resolve_retry = retry_only ? 1u : 0u;
-    // the failure counters of this pass (n_overflow, n_irr_overflow) and, for a full pass, the entry and item counters
-    KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_overflow, 0, (retry_only ? 2 : 4) * sizeof(unsigned long long), ctx->stream));
-    if (items_only) KJ_CUDA(ctx, cudaMemcpyAsync(&c->ctr->n_cand, &c->h_ctr->n_cand, sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-    const bool timed = ctx->timers_on && !retry_only && !items_only;
+    // the failure counters of this pass (n_overflow, n_irr_overflow) and, for a full pass, the entry counter
+    KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_overflow, 0, (retry_only ? 2 : 3) * sizeof(unsigned long long), ctx->stream));
+    const bool timed = ctx->timers_on && !retry_only;
     if (timed) KJ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (!retry_only && !items_only) {
+    if (!retry_only) {
         KjFilterFn fn = pick_filter_kernel(a);
         KJ_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KJ_WT_SMEM_BYTES));
         int occ = 0;
@@ -619,14 +623,9 @@ static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only, bool items_
         }
 #endif
     }
-    if (!retry_only) {
-        KJ_LAUNCH(kj_resolve_filter_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);
-        ctx->launches++;
-    }
-    if (c->k <= 16) KJ_LAUNCH((kj_resolve_emit_kernel<4>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
-    else KJ_LAUNCH((kj_resolve_emit_kernel<8>), ctx->sm_count * 8, 256, 0, ctx->stream, a);
+    KJ_LAUNCH(kj_resolve_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);
     ctx->launches++;
-    if (a.count_bases && !retry_only && !items_only) {
+    if (a.count_bases && !retry_only) {
         KJ_LAUNCH(kj_bases_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);
         ctx->launches++;
     }
@@ -636,8 +635,8 @@ static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only, bool items_
     return KJ_OK;
 }
 
-// entry / item buffers and tile arrays for a piece of n_tiles tiles expecting `want_ent` entries and `want_items` items
-static int ensure_filter_buffers(kj_counts *c, uint32_t n_tiles, uint64_t want_ent, uint64_t want_items) {
+// entry buffer and tile arrays for a piece of n_tiles tiles expecting `want_ent` entries
+static int ensure_filter_buffers(kj_counts *c, uint32_t n_tiles, uint64_t want_ent) {
     kj_ctx *ctx = c->ctx;
     if (n_tiles > c->tile_cap) {
         kj_dfree(ctx, c->tile_mem); kj_dfree(ctx, c->tile_cnt); kj_dfree(ctx, c->scan_tmp);
@@ -659,12 +658,6 @@ static int ensure_filter_buffers(kj_counts *c, uint32_t n_tiles, uint64_t want_e
         KJ_CUDA(ctx, kj_dmalloc(ctx, &c->cand, want_ent * 16));
         c->cand_cap = want_ent;
     }
-    if (want_items > c->item_cap) {
-        kj_dfree(ctx, c->items);
-        c->items = nullptr; c->item_cap = 0;
-        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->items, want_items * 16));
-        c->item_cap = want_items;
-    }
     return KJ_OK;
 }
 
@@ -677,9 +670,9 @@ static int settle_filter(kj_counts *c) {
     KjPiece &pc = *c->piece;
     int rc = pull_counters(c);
     if (rc) return rc;
-    if (pc.timed) { rc = account_scan_time(c, pc.args.own_n, true); if (rc) return rc; }
+    if (pc.timed) { rc = account_scan_time(c, pc.args.own_n, true); if (rc) return rc; pc.timed = false; }
     for (int round = 0; round < 4 && c->h_ctr->n_cand > c->cand_cap; ++round) {
-        rc = ensure_filter_buffers(c, pc.args.n_tiles, c->h_ctr->n_cand + (c->h_ctr->n_cand >> 3) + 1024, 0);
+        rc = ensure_filter_buffers(c, pc.args.n_tiles, c->h_ctr->n_cand + (c->h_ctr->n_cand >> 3) + 1024);
         if (rc) return rc;
         rc = launch_filter(c, pc, false);
         if (rc) return rc;
@@ -687,15 +680,6 @@ static int settle_filter(kj_counts *c) {
         if (rc) return rc;
     }
     if (c->h_ctr->n_cand > c->cand_cap) return kj_fail(ctx, KJ_E_CUDA, "internal: candidate entries exceed their own count");
-    if (c->h_ctr->n_items > c->item_cap) {          // the entries are fine, the items did not fit: from the filter on
-        rc = ensure_filter_buffers(c, pc.args.n_tiles, 0, c->h_ctr->n_items + 1024);
-        if (rc) return rc;
-        rc = launch_filter(c, pc, false, true);
-        if (rc) return rc;
-        rc = pull_counters(c);
-        if (rc) return rc;
-        if (c->h_ctr->n_items > c->item_cap) return kj_fail(ctx, KJ_E_CUDA, "internal: items exceed their own count");
-    }
     rc = check_device_errors(c);
     if (rc) return rc;
     for (int round = 0; c->h_ctr->n_overflow; ++round) {
@@ -745,11 +729,10 @@ static int scan_piece_filter(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint
     const uint64_t chunks = own_n / 16 + 1;
     double share = 48.0;
     for (uint32_t i = 0; i < std::min<uint32_t>(m, KJ_MAX_MP); ++i) share *= 0.25;
-    // entry slots are reserved in blocks of KJ_WT_BLOCK per warp, so a buffer holds at least a few blocks for every warp
-    const uint64_t want_ent = std::min<uint64_t>(chunks + (1ull << 20), (uint64_t)(std::min(1.0, share) * (double)chunks) + (1ull << 20));
-    // items: the candidates that sit in sequence lines (for FASTQ of reads: less than half of them)
-    const uint64_t want_items = std::min<uint64_t>(hard_bound, (uint64_t)(std::min(1.0, share) * (double)chunks) + (1ull << 16));
-    rc = ensure_filter_buffers(c, (uint32_t)n_tiles64, want_ent, want_items);
+    // entries: the candidates whose bytes pass the exact check -- about the emissions plus what header and quality lines
+    // happen to spell; slots are reserved in blocks of KJ_WT_BLOCK per warp, so the buffer holds a few blocks for every warp
+    const uint64_t want_ent = std::min<uint64_t>(hard_bound, (uint64_t)(std::min(1.0, share) * (double)chunks)) + (1ull << 20);
+    rc = ensure_filter_buffers(c, (uint32_t)n_tiles64, want_ent);
     if (rc) return rc;
 
     KjPiece &pc = *c->piece;
@@ -1117,47 +1100,71 @@ extern "C" int kj_counts_finish(kj_counts *c) {
     kj_ctx *ctx = c->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     KJ_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = settle_filter(c);         // a piece launched without waiting (capacity hint, device buffer)
-    if (rc) return rc;
-    rc = pull_counters(c);
-    if (rc) return rc;
-    rc = check_device_errors(c);
-    if (rc) return rc;
-    drop_compact(c);   // finish may be called again after merges
+    // Everything the device has to do is queued first -- compaction of the table, compaction and copy back of the irregular
+    // records, the counters -- and the host waits once.  With a capacity hint that holds even for a piece that is still in
+    // flight: the compaction is sized by the hint and queued behind the count kernels; should the device report a table
+    // or buffer that was too small, the piece is settled the long way and the compaction repeated with the exact sizes.
+    bool spec = c->pending && c->capacity_hint != 0;
+    int rc = KJ_OK;
+    for (;;) {
+        uint64_t cap_tab, cap_irr;
+        if (spec) {
+            cap_tab = c->capacity_hint;
+            cap_irr = std::min<uint64_t>(c->irr_cap, 4096);
+        } else {
+            rc = settle_filter(c);
+            if (rc) return rc;
+            rc = pull_counters(c);
+            if (rc) return rc;
+            rc = check_device_errors(c);
+            if (rc) return rc;
+            cap_tab = c->h_ctr->n_unique;
+            cap_irr = c->h_ctr->n_irr_unique;
+        }
+        drop_compact(c);   // finish may be called again after merges
+        const uint64_t q_cap = cap_tab + 1 + cap_irr;
+        if (q_cap > 0xFFFFFFF0ull) return kj_fail(ctx, KJ_E_RANGE, "more than 2^32 distinct k-mers on one GPU");
+        KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_compact, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.keys, q_cap * 8));
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.counts, q_cap * 8));
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.ords, q_cap * 8));
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.alive, q_cap));
+        KJ_CUDA(ctx, cudaMemsetAsync(c->reg.alive, 1, q_cap, ctx->stream));
+        if (cap_tab && c->cap) {
+            KJ_LAUNCH(kj_compact_kernel, grid_for(ctx, c->cap), 256, 0, ctx->stream, c->tab, c->cap, c->ctr,
+                      c->reg.keys, c->reg.counts, c->reg.ords, cap_tab);
+            ctx->launches++;
+        }
+        KjIrrRecord *d_irr = nullptr;
+        if (cap_irr && c->irr_cap) {
+            KJ_CUDA(ctx, kj_dmalloc(ctx, &d_irr, cap_irr * sizeof(KjIrrRecord)));
+            KJ_LAUNCH(kj_compact_irr_kernel, grid_for(ctx, c->irr_cap), 256, 0, ctx->stream, c->irr, c->irr_cap,
+                      c->ctr, d_irr, cap_irr);
+            ctx->launches++;
+            c->irr_host.resize(cap_irr * sizeof(KjIrrRecord));
+            cudaError_t e = cudaMemcpyAsync(c->irr_host.data(), d_irr, cap_irr * sizeof(KjIrrRecord),
+                                            cudaMemcpyDeviceToHost, ctx->stream);
+            if (e != cudaSuccess) { kj_dfree(ctx, d_irr); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
+        }
+        rc = pull_counters(c);           // the one wait: n_compact and the irregular records are back with it
+        kj_dfree(ctx, d_irr);
+        if (rc) return rc;
+        if (!spec) break;
+        const KjCounters &h = *c->h_ctr;
+        const bool fits = !h.n_overflow && !h.n_irr_overflow && !h.error_flags && h.n_cand <= c->cand_cap &&
+                          h.n_unique <= cap_tab && h.n_irr_unique <= cap_irr && h.n_unique * 2 <= c->cap;
+        if (fits) {
+            if (c->piece->timed) { rc = account_scan_time(c, c->piece->args.own_n, true); if (rc) return rc; c->piece->timed = false; }
+            c->pending = false;
+            break;
+        }
+        spec = false;                    // the long way: settle (retries, growth), then compact with the exact sizes
+    }
     const uint64_t n_tab = c->h_ctr->n_unique;
     const uint64_t n_reg = n_tab + (c->h_ctr->special_count ? 1 : 0);
     const uint64_t n_irr = c->h_ctr->n_irr_unique;
     const uint64_t q = n_reg + n_irr;
-    if (q > 0xFFFFFFF0ull) return kj_fail(ctx, KJ_E_RANGE, "more than 2^32 distinct k-mers on one GPU");
-    KJ_CUDA(ctx, cudaMemsetAsync(&c->ctr->n_compact, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    // Everything the device has to do is queued first -- compaction of the table, compaction and copy back of
-    // the irregular records, the counters -- and the host waits once.
-    if (q) {
-        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.keys, q * 8));
-        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.counts, q * 8));
-        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.ords, q * 8));
-        KJ_CUDA(ctx, kj_dmalloc(ctx, &c->reg.alive, q));
-        KJ_CUDA(ctx, cudaMemsetAsync(c->reg.alive, 1, q, ctx->stream));
-        if (n_tab) {
-            KJ_LAUNCH(kj_compact_kernel, grid_for(ctx, c->cap), 256, 0, ctx->stream, c->tab, c->cap, c->ctr,
-                      c->reg.keys, c->reg.counts, c->reg.ords);
-            ctx->launches++;
-        }
-    }
-    KjIrrRecord *d_irr = nullptr;
-    if (n_irr) {
-        KJ_CUDA(ctx, kj_dmalloc(ctx, &d_irr, n_irr * sizeof(KjIrrRecord)));
-        KJ_LAUNCH(kj_compact_irr_kernel, grid_for(ctx, c->irr_cap), 256, 0, ctx->stream, c->irr, c->irr_cap,
-                  c->ctr, d_irr);
-        ctx->launches++;
-        c->irr_host.resize(n_irr * sizeof(KjIrrRecord));
-        cudaError_t e = cudaMemcpyAsync(c->irr_host.data(), d_irr, n_irr * sizeof(KjIrrRecord),
-                                        cudaMemcpyDeviceToHost, ctx->stream);
-        if (e != cudaSuccess) { kj_dfree(ctx, d_irr); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
-    }
-    rc = pull_counters(c);           // the one wait: n_compact and the irregular records are back with it
-    kj_dfree(ctx, d_irr);
-    if (rc) return rc;
+    c->irr_host.resize(n_irr * sizeof(KjIrrRecord));
     std::vector<uint64_t> &tail_counts = c->tail_counts, &tail_ords = c->tail_ords;   // special + irregular entries
     tail_counts.clear(); tail_ords.clear();
     if (c->h_ctr->special_count) {
@@ -1449,7 +1456,7 @@ extern "C" void kj_counts_free(kj_counts *c) {
         kj_dfree(ctx, c->ctr);
         kj_pinned_put(ctx, c->h_ctr);
         kj_dfree(ctx, c->tile_mem); kj_dfree(ctx, c->tile_cnt); kj_dfree(ctx, c->scan_tmp);
-        kj_dfree(ctx, c->cand); kj_dfree(ctx, c->items);
+        kj_dfree(ctx, c->cand);
         drop_compact(c);
         kj_dfree(ctx, c->part_rec);
     }

@@ -47,7 +47,6 @@ struct KjCounters {
     unsigned long long n_overflow;
     unsigned long long n_irr_overflow;
     unsigned long long n_cand;         // filter path: entry slots handed out in the current launch
-    unsigned long long n_items;        // filter path: items (candidates in sequence lines) of the current launch
     unsigned long long n_occ;          // emitted occurrences (regular + irregular)
     unsigned long long n_bases;        // sum of processed sequence-line lengths
     unsigned long long special_count;  // the one key equal to KJ_EMPTY (k = 32, all 'G')

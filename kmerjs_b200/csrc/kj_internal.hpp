@@ -116,8 +116,6 @@ struct kj_counts {
     size_t scan_tmp_bytes = 0;
     uint64_t *cand = nullptr;         // candidate entries of the piece in flight (filter path), 16 bytes each
     uint64_t cand_cap = 0;
-    uint64_t *items = nullptr;        // items of the piece in flight (filter path), 16 bytes each
-    uint64_t item_cap = 0;
     struct KjPiece *piece = nullptr;  // filter path: the piece in flight (kernel arguments + tensor map), kj_count.cu
     bool pending = false;             // the piece has been launched and not settled yet
     bool exchange_totals = false;     // totals come from the segment headers of a fixed-capacity exchange
@@ -136,6 +134,37 @@ struct kj_counts {
     uint64_t *part_rec = nullptr;
     uint64_t part_cap = 0;
 };
+
+// the template database in HBM (kj_score.cu) and what the loaders keep beside it (kj_dbio.cu)
+#include <unordered_map>
+#define KJ_NONE32 0xFFFFFFFFu
+struct KjDbDev {
+    const uint64_t *keys;
+    const uint32_t *vals;
+    uint64_t mask;
+    const uint64_t *list_off;
+    const uint32_t *tmpl;
+};
+
+struct kj_db {
+    kj_ctx *ctx = nullptr;
+    uint32_t k = 0;                 // length of the regular (ACGT-only) k-mers in the device index
+    uint64_t n_kmers = 0, n_pairs = 0;
+    uint32_t n_templates = 0;
+    uint64_t *d_keys = nullptr;
+    uint32_t *d_vals = nullptr;
+    uint64_t cap = 0;
+    uint64_t *d_list_off = nullptr;
+    uint32_t *d_tmpl = nullptr;
+    uint64_t *d_ulen = nullptr;
+    std::vector<uint64_t> lengths, ulengths;
+    std::unordered_map<std::string, uint32_t> other;   // k-mers that are not regular: bytes -> k-mer id
+    uint32_t special_id = KJ_NONE32;                   // k-mer whose key equals KJ_EMPTY (k = 32, all G)
+    uint64_t s_templates = 0, s_unique_lens = 0, s_total_len = 0;
+    std::vector<std::string> names, species;           // per template, when the DB came through kj_db_load (else empty)
+    KjDbDev dev() const { return KjDbDev{d_keys, d_vals, cap - 1, d_list_off, d_tmpl}; }
+};
+
 
 // records used by the exchange and by export: {key, count, ord}
 struct KjRecord { uint64_t key, count, ord; };

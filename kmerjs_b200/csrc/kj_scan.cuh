@@ -59,8 +59,6 @@ struct KjScanArgs {
     uint64_t *status;     // per tile: flag << 62 | newline count; zeroed before every launch
     uint64_t *cand;       // filter path: candidate entries of this launch, 16 bytes each (kj_scan_warp.cuh)
     uint64_t cand_cap;    // in entries
-    uint64_t *items;      // filter path: candidates that sit in sequence lines, 16 bytes each {window start | strand, ordinal}
-    uint64_t item_cap;
     uint64_t *tile_cnt;   // filter path: '\n' per tile
     uint64_t *tile_excl;  // filter path: '\n' before the tile inside the launch (exclusive scan of tile_cnt)
     uint32_t n_fast;      // filter path: leading tiles that are whole, owned and readable through the tensor map

@@ -14,18 +14,19 @@
 //                           start k - |prefix| bytes before): lib/kmers.js:88-100,151-155 as an exact superset
 //                           filter.  Both strands share the shifted words.  Chunks with a candidate go to a queue
 //                           per lane (a predicated store, no atomic, no branch) and are drained by the whole
-//                           warp every few tiles as 16-byte entries {chunk, '\n' before it in the tile, its
-//                           '\n' mask, distance back to the last '\n', candidate lanes}.  The tile's newline
+//                           warp every few tiles: exact check of the window's bytes, then one 16-byte entry per
+//                           surviving window {key | tile, '\n' before it in the tile, column}.  The tile's newline
 //                           count goes to tile_cnt[]; nothing here needs the number of lines before the tile.
 //   (exclusive scan of tile_cnt -> tile_excl, cub::DeviceScan; the record FSM of lib/kmers.js:151-163 is
 //    "line index mod 4" over the whole stream)
-//   kj_resolve_filter_kernel  one thread per entry: line index of every candidate = lines before the launch +
-//                           tile_excl + in-tile count -> keep iff 1 mod 4; first-seen ordinal; survivors become
-//                           16-byte items {window start | strand, ordinal}, appended densely.
-//   kj_resolve_emit_kernel  one thread per item, all lanes busy: exact check of the window's bytes (prefix,
-//                           no '\n' inside, alphabet) and the hash-table update.  An emission that finds no slot
-//                           marks its item for a retry pass after the host has grown the table: nothing is ever
-//                           dropped, whatever the input looks like.
+//   kj_resolve_kernel       one thread per entry, the whole GPU: line index of the candidate = lines before the launch +
+//                           tile_excl + in-tile count -> keep iff 1 mod 4 (the reference's i === 1); first-seen ordinal;
+//                           hash-table update.  An emission that finds no slot marks its entry for a retry pass after the
+//                           host has grown the table: nothing is ever dropped, whatever the input looks like.
+// The window's bytes are checked (prefix, no '\n' inside, alphabet) and turned into the 2k-bit key by the DRAIN of the scan
+// kernel, a few tiles after the tile went by: the bytes are still in L2 then.  Fetching them in the resolve kernel cost
+// 0.19 ms of random DRAM reads per 10 M reads; the byte check also rejects nearly every candidate that sits in a header or
+// quality line, so 2.7 M entries reach the resolve kernel instead of 6.8 M.
 #pragma once
 #include "kj_scan.cuh"
 
@@ -40,8 +41,14 @@
 #define KJ_WT_WARPS 8
 #define KJ_WT_THREADS (KJ_WT_WARPS * 32)
 #define KJ_ENT_NODIST 0xFFFFu
-#define KJ_ITEM_STRAND (1ull << 63)
-#define KJ_ITEM_RETRY (1ull << 62)
+// entry = {word0, meta}.  word0: the 2k-bit key, or for an irregular window (a byte that is not A/C/G/T) its start j.
+// meta: tile (28 bits) | '\n' of the tile before the candidate (13) << 28 | column, or with NOCOL the window start relative
+// to the tile + 32 (12) << 41 | NOCOL << 53 (the line starts before the tile) | strand << 54 | irregular << 55 | retry << 63.
+// A blank entry (unused slot of a reserved block) is all ones.
+#define KJ_ENT_NOCOL (1ull << 53)
+#define KJ_ENT_STRAND (1ull << 54)
+#define KJ_ENT_IRR (1ull << 55)
+#define KJ_ENT_RETRY (1ull << 63)
 
 struct __align__(16) KjWarpSmem {
     uint4 bitmap[KJ_WT_RING][32];                // lane l: the '\n' masks of its 8 chunks, 16 bits each, in stream order
@@ -201,21 +208,69 @@ __device__ __forceinline__ void kj_wt_finish_tile(const KjScanArgs &a, KjWarpSme
     __syncwarp();
 }
 
+// The window at buffer offset j, its chunks loaded: exact check and key.  Straight-line SIMD-in-register code.  KW = 4-byte
+// words of the window the code looks at: 8 covers every k <= 32; 4 (k <= 16, the KmerFinder default) halves the work.
+// Returns 0: not an emission (prefix bytes differ, crosses the end of the line, ...); 1: key holds the 2k-bit key;
+// 2: irregular (some byte is not A/C/G/T): the byte string is the key.
+template <int KW>
+__device__ __forceinline__ int kj_window_key(const KjScanArgs &a, uint64_t j, uint32_t strand, const uint4 v0, const uint4 v1,
+                                             const uint4 v2, uint64_t &key) {
+    const uint32_t k = a.k;
+    const uint32_t o = (uint32_t)(j & 15u);
+    const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+    const uint32_t q = o >> 2, r8 = (o & 3u) * 8u;
+    uint32_t X[KW];
+#pragma unroll
+    for (int i = 0; i < KW; ++i) {
+        const uint32_t lo = q == 0 ? W[i] : q == 1 ? W[i + 1] : q == 2 ? W[i + 2] : W[i + 3];
+        const uint32_t hi = q == 0 ? W[i + 1] : q == 1 ? W[i + 2] : q == 2 ? W[i + 3] : W[i + 4];
+        X[i] = kj_funnel_r(lo, hi, r8);
+    }
+    uint32_t bad = 0, nl = 0, irr = 0, p_lo = 0, p_hi = 0;
+#pragma unroll
+    for (int i = 0; i < KW; ++i) {
+        if (4u * i < k) {
+            const uint32_t bm = (4u * i + 4u <= k) ? 0xFFFFFFFFu : ((1u << (8u * (k - 4u * i))) - 1u);   // bytes of the window
+            bad |= (X[i] ^ a.want[strand][i]) & a.wmask[strand][i];
+            nl |= kj_nl_msb4(X[i]) & bm;
+            irr |= kj_not_acgt4(X[i]) & bm;
+            const uint32_t c8 = kj_pack4(X[i] & bm);
+            if (i < 4) p_lo |= c8 << (8 * i); else p_hi |= c8 << (8 * (i - 4));
+        }
+    }
+    if (nl | bad) return 0;                               // crosses the end of the line / prefix bytes differ
+    if (k == 1 && a.line_gate) {                          // lib/kmers.js:151  line.length > 1: a lone byte is not processed
+        const bool first = j == 0 ? (a.ctr->carry_last[a.parity] == a.voff) : (a.buf[j - 1] == '\n');
+        const bool more = (j + 1 < a.n) && a.buf[j + 1] != '\n';
+        if (first && !more) return 0;
+    }
+    if (irr) return 2;
+    const uint64_t P = ((uint64_t)p_hi << 32) | p_lo;     // code of window byte i at bits 2i
+    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    // forward key: first base most significant; reverse key: complement codes, last base first
+    key = strand ? ((P ^ 0xAAAAAAAAAAAAAAAAull) & kmask) : (kj_pairrev64(P) >> (64u - 2u * k));
+    return 1;
+}
+
 // ----------------------------------------------------------------------------- drain
 
 // one thread: reserve the next block of entry slots
 __device__ __forceinline__ unsigned long long kj_wt_reserve(const KjScanArgs &a) {
     return atomicAdd(&a.ctr->n_cand, (unsigned long long)KJ_WT_BLOCK);
 }
-// the unused slots [at, at + n) of a block become empty entries (no candidate lanes)
+// the unused slots [at, at + n) of a block become blank entries
 __device__ __forceinline__ void kj_wt_blank(const KjScanArgs &a, unsigned long long at, uint32_t n, uint32_t lane) {
     for (uint32_t i = lane; i < n; i += 32)
-        if (at + i < a.cand_cap) reinterpret_cast<uint4 *>(a.cand)[at + i] = make_uint4(0, 0, 0, 0);
+        if (at + i < a.cand_cap) reinterpret_cast<ulonglong2 *>(a.cand)[at + i] = make_ulonglong2(~0ull, ~0ull);
 }
 
-// The whole warp turns the lanes' queues into entries in global memory: dense again, one entry per lane and round (entry e of
-// the concatenated queues belongs to the lane whose inclusive count is the first above e: five shuffle probes find it).
-// Entry slots come from blocks of KJ_WT_BLOCK the warp reserves one drain ahead, so that nothing waits for the atomic.
+// The whole warp turns the lanes' queues into entries in global memory.  The queue entries (chunks with candidate lanes) are
+// made dense again, one per lane and round (entry e of the concatenated queues belongs to the lane whose inclusive count is
+// the first above e: five shuffle probes find it); every candidate of the chunk then takes the exact check of its window's
+// bytes -- read from global memory, where the tile went by a few microseconds ago: L2 hits -- and the survivors are
+// appended as {key, tile | '\n' before | column}.  Entry slots come from blocks of KJ_WT_BLOCK the warp reserves one drain
+// ahead, so that nothing waits for the atomic.
+template <int KW>
 static __device__ __noinline__ void kj_wt_drain(const KjScanArgs &a, KjWarpSmem &ws, uint32_t t_cur, uint32_t slot_cur,
                                                 uint32_t G, KjWarpRegs &wr) {
     const uint32_t lane = threadIdx.x & 31;
@@ -238,16 +293,16 @@ static __device__ __noinline__ void kj_wt_drain(const KjScanArgs &a, KjWarpSmem 
         }
         src &= 31u;
         const uint32_t first = __shfl_sync(0xFFFFFFFFu, incl - mine, src);     // entries of the lanes before src
-        bool keep = false;
-        uint4 rec = make_uint4(0, 0, 0, 0);
+        // this lane's chunk: its candidate lanes and what the tile's newline bitmap says about it
+        uint32_t lanes = 0, nlmask = 0, nlb = 0, dist = KJ_ENT_NODIST, tile = 0;
+        uint64_t chunk = 0;
         if (e < n) {
             const uint2 qe = ws.pq[e - first][src];
-            const uint32_t z = qe.x, loc = qe.y;
-            const uint32_t slot = loc >> 3, i = loc & 7u;
+            const uint32_t slot = qe.y >> 3, i = qe.y & 7u;
             if (src != 31u) {                                       // lane 31 converts the row behind the tile: not owned
-                keep = true;
+                lanes = qe.x;
                 const uint32_t age = (slot_cur - slot) & (KJ_WT_RING - 1u);
-                const uint32_t tile = t_cur - age * G;
+                tile = t_cur - age * G;
                 const uint4 bm = ws.bitmap[slot][src];
                 const uint32_t w[4] = {bm.x, bm.y, bm.z, bm.w};
                 // bits of the lane's 128 below chunk i
@@ -260,7 +315,6 @@ static __device__ __noinline__ void kj_wt_drain(const KjScanArgs &a, KjWarpSmem 
                     before += __popc(x);
                     if (x) { hi_w = x; hi_j = j; }
                 }
-                uint32_t dist = KJ_ENT_NODIST;
                 if (hi_w) {
                     dist = i * 16u - (hi_j * 32u + (31u - __clz(hi_w)) + 1u);
                 } else {
@@ -275,29 +329,64 @@ static __device__ __noinline__ void kj_wt_drain(const KjScanArgs &a, KjWarpSmem 
                         }
                     }
                 }
-                const uint32_t nlmask = (w[i >> 1] >> ((i & 1u) * 16u)) & 0xFFFFu;
-                const uint64_t chunk = (uint64_t)tile * KJ_WT_CHUNKS + src * 8u + i;
-                const uint64_t word = chunk | ((uint64_t)(ws.lanepre[slot][src] + before) << 40);
-                rec = make_uint4((uint32_t)word, (uint32_t)(word >> 32), z, nlmask | (dist << 16));
+                nlmask = (w[i >> 1] >> ((i & 1u) * 16u)) & 0xFFFFu;
+                nlb = ws.lanepre[slot][src] + before;
+                chunk = (uint64_t)tile * KJ_WT_CHUNKS + src * 8u + i;
             }
         }
-        const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
-        const uint32_t need = __popc(kb);
-        if (need > wr.blk_left) {
-            // the block is used up: blank its tail, go on in the one reserved ahead, reserve the one after
-            kj_wt_blank(a, wr.blk_at, wr.blk_left, lane);
-            wr.blk_at = wr.next_at;
-            wr.blk_left = KJ_WT_BLOCK;
-            unsigned long long nx = 0;
-            if (lane == 0) nx = kj_wt_reserve(a);
-            wr.next_at = __shfl_sync(0xFFFFFFFFu, nx, 0);
+        // one candidate of every lane's chunk per round (a chunk rarely holds two)
+        while (__any_sync(0xFFFFFFFFu, lanes != 0u)) {
+            bool keep = false;
+            unsigned long long w0 = 0, meta = 0;
+            if (lanes) {
+                const uint32_t bit = __ffs(lanes) - 1;
+                lanes &= lanes - 1;
+                const uint32_t p = bit >> 1, strand = bit & 1u;
+                const uint64_t pos = chunk * 16u + p;                      // where the prefix / complement(prefix) starts
+                const uint32_t back = strand ? a.rc_shift : 0u;            // the reverse-strand window starts k - m before
+                if (pos >= back && pos - back < a.own_n && pos - back + a.k <= a.n) {
+                    const uint64_t j = pos - back;
+                    const uint32_t below = nlmask & ((1u << p) - 1u);
+                    // first byte of the line, when it lies in this tile
+                    bool have_ls = true;
+                    uint64_t ls = 0;
+                    if (below) ls = chunk * 16u + (31u - __clz(below)) + 1u;
+                    else if (dist != KJ_ENT_NODIST) ls = chunk * 16u - dist;
+                    else have_ls = false;
+                    if (!have_ls || j >= ls) {                             // else: a '\n' between the window start and the prefix
+                        uint4 v0, v1, v2;
+                        kj_window_load(a, j, v0, v1, v2);
+                        uint64_t key = 0;
+                        const int st = kj_window_key<KW>(a, j, strand, v0, v1, v2, key);
+                        if (st) {
+                            keep = true;
+                            const uint64_t tile_start = (uint64_t)tile * KJ_WT_BYTES;
+                            const uint64_t colf = have_ls ? (j - ls) : (j + 32u - tile_start);
+                            w0 = st == 1 ? key : j;
+                            meta = (unsigned long long)tile | ((unsigned long long)(nlb + __popc(below)) << 28) | (colf << 41) |
+                                   (have_ls ? 0ull : KJ_ENT_NOCOL) | (strand ? KJ_ENT_STRAND : 0ull) | (st == 2 ? KJ_ENT_IRR : 0ull);
+                        }
+                    }
+                }
+            }
+            const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
+            const uint32_t need = __popc(kb);
+            if (need > wr.blk_left) {
+                // the block is used up: blank its tail, go on in the one reserved ahead, reserve the one after
+                kj_wt_blank(a, wr.blk_at, wr.blk_left, lane);
+                wr.blk_at = wr.next_at;
+                wr.blk_left = KJ_WT_BLOCK;
+                unsigned long long nx = 0;
+                if (lane == 0) nx = kj_wt_reserve(a);
+                wr.next_at = __shfl_sync(0xFFFFFFFFu, nx, 0);
+            }
+            if (keep) {
+                const unsigned long long at = wr.blk_at + __popc(kb & ((1u << lane) - 1u));
+                if (at < a.cand_cap) reinterpret_cast<ulonglong2 *>(a.cand)[at] = make_ulonglong2(w0, meta);   // beyond: the host repeats the piece
+            }
+            wr.blk_at += need;
+            wr.blk_left -= need;
         }
-        if (keep) {
-            const unsigned long long at = wr.blk_at + __popc(kb & ((1u << lane) - 1u));
-            if (at < a.cand_cap) reinterpret_cast<uint4 *>(a.cand)[at] = rec;    // beyond the buffer: the host sees n_cand and repeats the piece
-        }
-        wr.blk_at += need;
-        wr.blk_left -= need;
     }
     __syncwarp();
     wr.qaddr = kj_qaddr_of(ws, lane);
@@ -328,7 +417,7 @@ static __device__ __noinline__ void kj_wt_edge_tile(const KjScanArgs &a, KjWarpS
     kj_wt_finish_tile<MP, true>(a, ws, cw, nlp, t, slot, lane, live, qaddr);
 }
 
-template <int MP>
+template <int MP, int KW>
 __global__ void __launch_bounds__(KJ_WT_THREADS, 2)
 kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_constant__ KjScanArgs a) {
     KJ_DYN_SMEM(dyn);
@@ -379,7 +468,7 @@ kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_con
         const uint32_t s = it % KJ_WT_STAGES, slot = it & (KJ_WT_RING - 1u);
         // room in every lane's queue for everything this tile can add to it (8 entries)
         if (__any_sync(0xFFFFFFFFu, kj_q_count(ws, lane, wr.qaddr) + 8u > KJ_WT_PQCAP))
-            kj_wt_drain(a, ws, t - G, (slot - 1u) & (KJ_WT_RING - 1u), G, wr);
+            kj_wt_drain<KW>(a, ws, t - G, (slot - 1u) & (KJ_WT_RING - 1u), G, wr);
         kj_bar_wait(&bars[s], (it / KJ_WT_STAGES) & 1u);
         const uint32_t soff = s * KJ_WT_STAGE_BYTES;
         uint32_t cw[9], nlp[4];
@@ -398,168 +487,74 @@ kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_con
         cw[8] = __shfl_down_sync(0xFFFFFFFFu, cw[0], 1);
         kj_wt_finish_tile<MP, false>(a, ws, cw, nlp, t, slot, lane, live, wr.qaddr);
         // the ring keeps KJ_WT_RING tiles: drain when it is full
-        if (slot == KJ_WT_RING - 1u) kj_wt_drain(a, ws, t, slot, G, wr);
+        if (slot == KJ_WT_RING - 1u) kj_wt_drain<KW>(a, ws, t, slot, G, wr);
     }
     // ---- edge tiles
     for (; t < a.n_tiles; t += G, ++it) {
         const uint32_t slot = it & (KJ_WT_RING - 1u);
         if (__any_sync(0xFFFFFFFFu, kj_q_count(ws, lane, wr.qaddr) + 8u > KJ_WT_PQCAP))
-            kj_wt_drain(a, ws, t - G, (slot - 1u) & (KJ_WT_RING - 1u), G, wr);
+            kj_wt_drain<KW>(a, ws, t - G, (slot - 1u) & (KJ_WT_RING - 1u), G, wr);
         kj_wt_edge_tile<MP>(a, ws, t, slot, live, wr.qaddr);
-        if (slot == KJ_WT_RING - 1u) kj_wt_drain(a, ws, t, slot, G, wr);
+        if (slot == KJ_WT_RING - 1u) kj_wt_drain<KW>(a, ws, t, slot, G, wr);
     }
     // what is left in the queues (the ring slot of the last tile is (it - 1) mod ring), then the unused entry slots
-    kj_wt_drain(a, ws, t - G, (it - 1u) & (KJ_WT_RING - 1u), G, wr);
+    kj_wt_drain<KW>(a, ws, t - G, (it - 1u) & (KJ_WT_RING - 1u), G, wr);
     kj_wt_blank(a, wr.blk_at, wr.blk_left, lane);
     kj_wt_blank(a, wr.next_at, KJ_WT_BLOCK, lane);
 }
 
 // ----------------------------------------------------------------------------- resolve kernel
 
-// Entries -> items.  For every candidate of an entry: the line index (lines before the launch + lines before the tile +
-// '\n' before the position inside the tile) must be 1 mod 4 (lib/kmers.js:151, i === 1); the window must start inside the
-// owned range; the first-seen ordinal = (read, strand, column).  Survivors are appended as {window start | strand << 63,
-// ordinal}, one warp-wide append per round.  Block 0 also closes the stream state of the launch for the next one.
-__global__ void __launch_bounds__(256) kj_resolve_filter_kernel(const __grid_constant__ KjScanArgs a) {
+// Entries -> table.  a.resolve_retry == 0: every entry; != 0: the entries an earlier pass marked.
+// Block 0 also closes the stream state of the launch (lines and last '\n' so far) for the next one.
+__global__ void __launch_bounds__(256) kj_resolve_kernel(const __grid_constant__ KjScanArgs a) {
     const unsigned long long n_ent = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;
     const uint64_t base_lines = a.ctr->carry_lines[a.parity];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && a.n_tiles) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !a.resolve_retry && a.n_tiles) {
         a.ctr->carry_lines[a.parity ^ 1] = base_lines + a.tile_excl[a.n_tiles - 1] + a.tile_cnt[a.n_tiles - 1];
         a.ctr->carry_last[a.parity ^ 1] = kj_line_start_global(a, a.own_n);
     }
     if (a.ctr->n_cand > a.cand_cap) return;                   // the entry buffer was too small: nothing is touched, the host repeats the piece
-    const uint4 *ent = reinterpret_cast<const uint4 *>(a.cand);
-    const uint32_t lane = threadIdx.x & 31;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long rounds = (n_ent + stride - 1) / stride;      // the same trip count for every thread (warp collectives inside)
-    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    for (unsigned long long r = 0; r < rounds; ++r, i += stride) {
-        uint4 rec = make_uint4(0, 0, 0, 0);
-        if (i < n_ent) rec = ent[i];
-        const uint64_t word = ((uint64_t)rec.y << 32) | rec.x;
-        const uint64_t chunk = word & ((1ull << 40) - 1ull);
-        const uint32_t nlb = (uint32_t)(word >> 40) & 0x1FFFu;
-        const uint32_t nlmask = rec.w & 0xFFFFu, dist = rec.w >> 16;
-        const uint64_t tile = chunk / KJ_WT_CHUNKS;
-        uint32_t lanes = rec.z;
-        uint64_t line0 = 0;
-        if (lanes) line0 = base_lines + a.tile_excl[tile] + nlb;
-        while (__any_sync(0xFFFFFFFFu, lanes != 0u)) {
-            bool keep = false;
-            uint64_t item0 = 0, ord = 0;
-            if (lanes) {
-                const uint32_t bit = __ffs(lanes) - 1;
-                lanes &= lanes - 1;
-                const uint32_t p = bit >> 1, strand = bit & 1u;
-                const uint64_t pos = chunk * 16u + p;                      // where the prefix / complement(prefix) starts
-                const uint32_t back = strand ? a.rc_shift : 0u;            // the reverse-strand window starts k - m before
-                const uint32_t below = nlmask & ((1u << p) - 1u);
-                const uint64_t line = line0 + __popc(below);
-                if (pos >= back && pos - back < a.own_n && pos - back + a.k <= a.n && (line & 3ull) == 1ull) {
-                    const uint64_t j = pos - back;
-                    keep = true;
-                    if (a.order || a.k == 1) {
-                        unsigned long long start;                          // first byte of the line (virtual offset)
-                        if (below) start = a.voff + chunk * 16u + (31u - __clz(below)) + 1ull;
-                        else if (dist != KJ_ENT_NODIST) start = a.voff + chunk * 16u - dist;
-                        else start = kj_line_start_global(a, tile * KJ_WT_BYTES);
-                        if (a.voff + j < start) {
-                            keep = false;                                  // a '\n' between the window start and the prefix: not a window
-                        } else {
-                            const uint64_t col = a.voff + j - start;
-                            const uint64_t read_idx = line >> 2;
-                            if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); keep = false; }
-                            else if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); keep = false; }
-                            // forward emissions in ascending column, then reverse emissions in descending column
-                            else ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
-                        }
-                    }
-                    item0 = j | (strand ? KJ_ITEM_STRAND : 0ull);
-                }
-            }
-            const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
-            if (kb) {
-                unsigned long long at = 0;
-                if (lane == 0) at = atomicAdd(&a.ctr->n_items, (unsigned long long)__popc(kb));
-                at = __shfl_sync(0xFFFFFFFFu, at, 0) + __popc(kb & ((1u << lane) - 1u));
-                if (keep && at < a.item_cap) reinterpret_cast<ulonglong2 *>(a.items)[at] = make_ulonglong2(item0, ord);
-            }
-        }
-    }
-}
-
-// status of one candidate window
-#define KJ_EMIT_NONE 0       // not an emission (prefix bytes differ, crosses the end of the line, ...)
-#define KJ_EMIT_OK 1
-#define KJ_EMIT_FULL 2       // the table has no slot within the probe limit: retry after the host has grown it
-
-template <int KW>
-__device__ __forceinline__ int kj_window_try(const KjScanArgs &a, uint64_t j, uint32_t strand, uint64_t ord,
-                                             const uint4 v0, const uint4 v1, const uint4 v2) {
-    const uint32_t k = a.k;
-    const uint32_t o = (uint32_t)(j & 15u);
-    const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-    const uint32_t q = o >> 2, r8 = (o & 3u) * 8u;
-    uint32_t X[KW];
-#pragma unroll
-    for (int i = 0; i < KW; ++i) {
-        const uint32_t lo = q == 0 ? W[i] : q == 1 ? W[i + 1] : q == 2 ? W[i + 2] : W[i + 3];
-        const uint32_t hi = q == 0 ? W[i + 1] : q == 1 ? W[i + 2] : q == 2 ? W[i + 3] : W[i + 4];
-        X[i] = kj_funnel_r(lo, hi, r8);
-    }
-    uint32_t bad = 0, nl = 0, irr = 0, p_lo = 0, p_hi = 0;
-#pragma unroll
-    for (int i = 0; i < KW; ++i) {
-        if (4u * i < k) {
-            const uint32_t bm = (4u * i + 4u <= k) ? 0xFFFFFFFFu : ((1u << (8u * (k - 4u * i))) - 1u);   // bytes of the window
-            bad |= (X[i] ^ a.want[strand][i]) & a.wmask[strand][i];
-            nl |= kj_nl_msb4(X[i]) & bm;
-            irr |= kj_not_acgt4(X[i]) & bm;
-            const uint32_t c8 = kj_pack4(X[i] & bm);
-            if (i < 4) p_lo |= c8 << (8 * i); else p_hi |= c8 << (8 * (i - 4));
-        }
-    }
-    if (nl | bad) return KJ_EMIT_NONE;                    // crosses the end of the line / prefix bytes differ
-    if (k == 1 && a.line_gate) {                          // lib/kmers.js:151  line.length > 1: a lone byte is not processed
-        const bool first = j == 0 ? (a.ctr->carry_last[a.parity] == a.voff) : (a.buf[j - 1] == '\n');
-        const bool more = (j + 1 < a.n) && a.buf[j + 1] != '\n';
-        if (first && !more) return KJ_EMIT_NONE;
-    }
-    const uint64_t P = ((uint64_t)p_hi << 32) | p_lo;     // code of window byte i at bits 2i
-    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
-    if (!irr) {
-        // forward key: first base most significant; reverse key: complement codes, last base first
-        const uint64_t key = strand ? ((P ^ 0xAAAAAAAAAAAAAAAAull) & kmask) : (kj_pairrev64(P) >> (64u - 2u * k));
-        return kj_insert(a.tab, a.ctr, key, ord, 1) ? KJ_EMIT_OK : KJ_EMIT_FULL;
-    }
-    __align__(8) uint8_t key32[32];
-    kj_window_bytes(a.buf, j, k, strand, key32);
-    return kj_insert_irr(a.irr, a.ctr, key32, k, ord, 1) ? KJ_EMIT_OK : KJ_EMIT_FULL;
-}
-
-// Items -> table.  a.resolve_retry == 0: every item; != 0: the items an earlier pass marked.
-template <int KW>
-__global__ void __launch_bounds__(256) kj_resolve_emit_kernel(const __grid_constant__ KjScanArgs a) {
-    if (a.ctr->n_cand > a.cand_cap || a.ctr->n_items > a.item_cap) return;      // a buffer was too small: the host repeats
-    const unsigned long long n_items = a.ctr->n_items;
     uint32_t n_emit = 0, n_fail = 0;
-    ulonglong2 *items = reinterpret_cast<ulonglong2 *>(a.items);
+    ulonglong2 *ent = reinterpret_cast<ulonglong2 *>(a.cand);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_items; i += stride) {
-        const ulonglong2 it = items[i];
-        const bool marked = (it.x & KJ_ITEM_RETRY) != 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_ent; i += stride) {
+        const ulonglong2 e = ent[i];
+        if (e.y == ~0ull) continue;                           // blank
+        const bool marked = (e.y & KJ_ENT_RETRY) != 0;
         if (a.resolve_retry && !marked) continue;
-        const uint64_t j = it.x & ~(KJ_ITEM_STRAND | KJ_ITEM_RETRY);
-        const uint32_t strand = (uint32_t)(it.x >> 63);
-        uint4 v0, v1, v2;
-        kj_window_load(a, j, v0, v1, v2);
-        const int st = kj_window_try<KW>(a, j, strand, it.y, v0, v1, v2);
-        if (st == KJ_EMIT_OK) ++n_emit;
-        if (st == KJ_EMIT_FULL) {
-            ++n_fail;
-            if (!marked) items[i].x = it.x | KJ_ITEM_RETRY;
-        } else if (marked) {
-            items[i].x = it.x & ~KJ_ITEM_RETRY;
+        const uint64_t tile = e.y & 0xFFFFFFFull;
+        const uint32_t nlq = (uint32_t)(e.y >> 28) & 0x1FFFu, colf = (uint32_t)(e.y >> 41) & 0xFFFu;
+        const uint32_t strand = (e.y & KJ_ENT_STRAND) ? 1u : 0u;
+        const uint64_t line = base_lines + a.tile_excl[tile] + nlq;
+        if ((line & 3ull) != 1ull) continue;                  // lib/kmers.js:151  i === 1
+        uint64_t ord = 0;
+        if (a.order || a.k == 1) {
+            uint64_t col = colf;
+            if (e.y & KJ_ENT_NOCOL) {                         // the line starts before the tile: search backwards from the tile
+                const uint64_t j = tile * KJ_WT_BYTES + colf - 32u;
+                col = a.voff + j - kj_line_start_global(a, tile * KJ_WT_BYTES);
+            }
+            if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); continue; }
+            const uint64_t read_idx = line >> 2;
+            if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); continue; }
+            // forward emissions in ascending column, then reverse emissions in descending column
+            ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
+        }
+        bool ok;
+        if (!(e.y & KJ_ENT_IRR)) {
+            ok = kj_insert(a.tab, a.ctr, e.x, ord, 1);
+        } else {
+            __align__(8) uint8_t key32[32];
+            kj_window_bytes(a.buf, e.x, a.k, strand, key32);
+            ok = kj_insert_irr(a.irr, a.ctr, key32, a.k, ord, 1);
+        }
+        if (ok) {
+            ++n_emit;
+            if (marked) ent[i].y = e.y & ~KJ_ENT_RETRY;
+        } else {
+            ++n_fail;                                          // no slot within the probe limit: retry after the host has grown the table
+            if (!marked) ent[i].y = e.y | KJ_ENT_RETRY;
         }
     }
     for (int d = 16; d > 0; d >>= 1) {

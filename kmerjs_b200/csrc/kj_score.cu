@@ -22,35 +22,8 @@
 #endif
 #include "kj_stats.hpp"
 
-#define KJ_NONE32 0xFFFFFFFFu
 #define KJ_SCORE_THREADS 256
 #define KJ_SMEM_T_MAX 8192u     // templates whose u (u32) and tau (u64) are privatised in shared memory
-
-struct KjDbDev {
-    const uint64_t *keys;
-    const uint32_t *vals;
-    uint64_t mask;
-    const uint64_t *list_off;
-    const uint32_t *tmpl;
-};
-
-struct kj_db {
-    kj_ctx *ctx = nullptr;
-    uint32_t k = 0;                 // length of the regular (ACGT-only) k-mers in the device index
-    uint64_t n_kmers = 0, n_pairs = 0;
-    uint32_t n_templates = 0;
-    uint64_t *d_keys = nullptr;
-    uint32_t *d_vals = nullptr;
-    uint64_t cap = 0;
-    uint64_t *d_list_off = nullptr;
-    uint32_t *d_tmpl = nullptr;
-    uint64_t *d_ulen = nullptr;
-    std::vector<uint64_t> lengths, ulengths;
-    std::unordered_map<std::string, uint32_t> other;   // k-mers that are not regular: bytes -> k-mer id
-    uint32_t special_id = KJ_NONE32;                   // k-mer whose key equals KJ_EMPTY (k = 32, all G)
-    uint64_t s_templates = 0, s_unique_lens = 0, s_total_len = 0;
-    KjDbDev dev() const { return KjDbDev{d_keys, d_vals, cap - 1, d_list_off, d_tmpl}; }
-};
 
 struct KjWtaResult {        // written by the argmax / loop kernels, copied to the host
     uint32_t winner;        // template id, KJ_NONE32 when every uScore is zero
@@ -457,20 +430,37 @@ __global__ void kj_remove_kernel(KjDbDev d, const uint32_t *tq, uint64_t lo, uin
 }
 
 // First-encounter rank of every matched template: its position in ascending (first ordinal, list index, id) order
-// (lib/kmerFinderServer.js:180-201: query k-mers in Map order, each list in DB order).  Every thread counts the keys
-// below its own: T^2 compares, all threads reading the same key at the same time (10^4 templates: tens of microseconds).
-__global__ void kj_rank_kernel(const uint64_t *u, const uint64_t *ford, const uint64_t *fidx, uint32_t T, uint32_t *rank) {
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
-        if (!u[t]) { rank[t] = KJ_NONE32 - 1; continue; }
-        const uint64_t fo = ford[t], fi = fidx[t];
-        uint32_t below = 0;
-        for (uint32_t q = 0; q < T; ++q) {
-            if (!u[q]) continue;
-            const uint64_t qo = ford[q], qi = fidx[q];
-            below += (qo < fo) || (qo == fo && (qi < fi || (qi == fi && q < t)));
+// (lib/kmerFinderServer.js:180-201: query k-mers in Map order, each list in DB order).  Every thread counts the keys below
+// its own in one slice of the templates (grid.y slices, keys staged through shared memory) and adds the count to rank[t],
+// which starts at zero; unmatched templates (first ordinal still all ones) get KJ_NONE32 - 1.  T^2 compares: 10^4
+// templates take some ten microseconds.
+#define KJ_RANK_THREADS 128
+#define KJ_RANK_TILE 256
+__global__ void __launch_bounds__(KJ_RANK_THREADS) kj_rank_kernel(const uint64_t *u, const uint64_t *ford, const uint64_t *fidx,
+                                                                   uint32_t T, uint32_t *rank) {
+    __shared__ uint64_t s_o[KJ_RANK_TILE], s_i[KJ_RANK_TILE];
+    const uint32_t t = blockIdx.x * KJ_RANK_THREADS + threadIdx.x;
+    const bool live = t < T && u[t] != 0;
+    const uint64_t fo = t < T ? ford[t] : 0, fi = t < T ? fidx[t] : 0;
+    const uint32_t slice = (T + gridDim.y - 1) / gridDim.y;
+    const uint32_t q0 = blockIdx.y * slice, q1 = min(T, q0 + slice);
+    uint32_t below = 0;
+    for (uint32_t base = q0; base < q1; base += KJ_RANK_TILE) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < KJ_RANK_TILE; i += KJ_RANK_THREADS) {
+            const uint32_t q = base + i;
+            s_o[i] = q < q1 ? ford[q] : ~0ull;            // unmatched templates keep all ones: never below anything matched
+            s_i[i] = q < q1 ? fidx[q] : ~0ull;
         }
-        rank[t] = below;
+        __syncthreads();
+        const uint32_t n = min((uint32_t)KJ_RANK_TILE, q1 - base);
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint64_t qo = s_o[i], qi = s_i[i];
+            below += (qo < fo) || (qo == fo && (qi < fi || (qi == fi && base + i < t)));
+        }
     }
+    if (live) { if (below) atomicAdd(&rank[t], below); }
+    else if (t < T && blockIdx.y == 0) rank[t] = KJ_NONE32 - 1;
 }
 
 // The whole findMatches loop (lib/kmerFinderClient.js:273-286) on the device.  Block 0 takes the argmax and the gate of a
@@ -1222,8 +1212,9 @@ extern "C" int kj_match_commit(kj_match *m) {
     KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_glob0, std::max<uint64_t>(2 * T, 1) * 8));
     if (T) {
         KJ_CUDA(ctx, cudaMemcpyAsync(m->d_glob0, m->d_glob, 2 * T * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        KJ_LAUNCH(kj_rank_kernel, kj_grid_for(ctx, T, 128), 128, 0, ctx->stream, m->d_glob, m->d_first_ord, m->d_first_idx,
-                  (uint32_t)T, m->d_rank);
+        KJ_CUDA(ctx, cudaMemsetAsync(m->d_rank, 0, T * 4, ctx->stream));
+        KJ_LAUNCH(kj_rank_kernel, dim3((unsigned)((T + KJ_RANK_THREADS - 1) / KJ_RANK_THREADS), (unsigned)std::min<uint64_t>(16, (T + 1023) / 1024)),
+                  KJ_RANK_THREADS, 0, ctx->stream, m->d_glob, m->d_first_ord, m->d_first_idx, (uint32_t)T, m->d_rank);
         ctx->launches++;
         KJ_CUDA(ctx, cudaMemsetAsync(m->d_tcur, 0, T * 8, ctx->stream));
     }

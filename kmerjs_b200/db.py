@@ -9,7 +9,10 @@ On-disk formats accepted by :func:`load` (all defined by the reference, SURVEY.m
     (src/kmerPyToMongo.py:35-42 -- the field really is spelled ``ulenght``)
   * the original KmerFinder map {K: "T1,T2,.."} with side tables for lengths / ulengths /
     descriptions (lib/index.js:184-192, src/kmerPyToMongo.py:15-24)
-  * ``.npz`` written by :meth:`TemplateDB.save` (packed arrays; the fast path)
+  * ``.kjdb`` written by :meth:`TemplateDB.save` / kj_db_save_packed: a versioned binary of plain arrays (the fast path;
+    nothing in it is executable -- no pickle); ``.npz`` of the same arrays is still read and written (allow_pickle=False)
+:func:`load` parses on the host (numpy arrays, e.g. to hand the DB to the CPU oracle in tests); :func:`load_native` goes
+through the C ABI (kj_db_load): file -> GPU without Python touching the records.
 The Summary record {"templates","uniqueLens","totalLen"} (lib/kmerFinderServer.js:716-724,
 test_data/summary.json) travels with the DB."""
 from __future__ import annotations
@@ -115,11 +118,26 @@ class TemplateDB:
                        "totalLen": sum(int(a["lengths"]) for a in attrs.values())}
         return cls.from_lists(lists, attrs, summary)
 
+    def _desc(self, part: int = 0, n_parts: int = 1):
+        return _abi.kj_db_desc(self.n_kmers, self.kmer_bytes.ctypes.data, self.kmer_len.ctypes.data,
+                               self.list_off.ctypes.data, self.tmpl_ids.ctypes.data, self.n_templates,
+                               self.lengths.ctypes.data, self.ulengths.ctypes.data,
+                               self.summary["templates"], self.summary["uniqueLens"],
+                               self.summary["totalLen"], part, n_parts)
+
     def save(self, path: str):
-        np.savez(path, kmer_bytes=self.kmer_bytes, kmer_len=self.kmer_len, list_off=self.list_off,
-                 tmpl_ids=self.tmpl_ids, lengths=self.lengths, ulengths=self.ulengths,
-                 names=np.array(self.names, dtype=object), species=np.array(self.species, dtype=object),
-                 summary=np.array(json.dumps(self.summary)), allow_pickle=True)
+        """``.npz``: numpy archive of plain arrays; anything else: the versioned packed binary (kj_db_save_packed)."""
+        if str(path).endswith(".npz"):
+            np.savez(path, kmer_bytes=self.kmer_bytes, kmer_len=self.kmer_len, list_off=self.list_off,
+                     tmpl_ids=self.tmpl_ids, lengths=self.lengths, ulengths=self.ulengths,
+                     names=np.array(self.names, dtype=np.str_), species=np.array(self.species, dtype=np.str_),
+                     summary=np.array(json.dumps(self.summary)))
+            return
+        d = self._desc()
+        T = self.n_templates
+        names = (C.c_char_p * max(T, 1))(*[n.encode("utf-8") for n in self.names])
+        species = (C.c_char_p * max(T, 1))(*[s.encode("utf-8") for s in self.species])
+        _abi.check(_abi.lib().kj_db_save_packed(str(path).encode(), C.byref(d), names, species))
 
     # ------------------------------------------------------------------ views
     @property
@@ -152,11 +170,7 @@ class TemplateDB:
         h = self._dev.get(key)
         if h is None:
             L = _abi.lib()
-            d = _abi.kj_db_desc(self.n_kmers, self.kmer_bytes.ctypes.data, self.kmer_len.ctypes.data,
-                                self.list_off.ctypes.data, self.tmpl_ids.ctypes.data, self.n_templates,
-                                self.lengths.ctypes.data, self.ulengths.ctypes.data,
-                                self.summary["templates"], self.summary["uniqueLens"],
-                                self.summary["totalLen"], part, n_parts)
+            d = self._desc(part, n_parts)
             out = C.c_void_p()
             _abi.check(L.kj_db_create(ctx.handle, C.byref(d), C.byref(out)), ctx.handle)
             h = _DbHandle(out, ctx)
@@ -196,9 +210,13 @@ def load(path: str, summary=None, **side) -> TemplateDB:
         return x
 
     if str(path).endswith(".npz"):
-        z = np.load(path, allow_pickle=True)
-        return TemplateDB(z["kmer_bytes"], z["kmer_len"], z["list_off"], z["tmpl_ids"], list(z["names"]),
-                          z["lengths"], z["ulengths"], list(z["species"]), json.loads(str(z["summary"])))
+        z = np.load(path, allow_pickle=False)
+        return TemplateDB(z["kmer_bytes"], z["kmer_len"], z["list_off"], z["tmpl_ids"], [str(x) for x in z["names"]],
+                          z["lengths"], z["ulengths"], [str(x) for x in z["species"]], json.loads(str(z["summary"])))
+    with open(path, "rb") as f:
+        magic = f.read(8)
+    if magic[:4] == b"KJDB":
+        return _load_packed(path)
     doc = _json(path)
     summary = _json(summary) if summary is not None else None
     if isinstance(doc, dict):
@@ -209,3 +227,68 @@ def load(path: str, summary=None, **side) -> TemplateDB:
     if summary is None:
         raise ValueError("per-k-mer documents need a Summary record")
     return TemplateDB.from_kmer_docs(doc, summary)
+
+
+def _load_packed(path: str) -> TemplateDB:
+    """The packed binary (kj_dbio.cu PackedHeader) read with numpy: header of 8 + 9 * 8 bytes, then plain arrays."""
+    with open(path, "rb") as f:
+        if f.read(8) != b"KJDBv001":
+            raise ValueError(f"{path}: not a kmerjs_b200 packed database (magic / version)")
+        n_kmers, kbytes, n_pairs, T, nb, sb, s_t, s_u, s_l = np.fromfile(f, dtype=np.uint64, count=9).tolist()
+        kmer_len = np.fromfile(f, dtype=np.uint32, count=n_kmers)
+        kmer_bytes = np.fromfile(f, dtype=np.uint8, count=kbytes)
+        list_off = np.fromfile(f, dtype=np.uint64, count=n_kmers + 1)
+        tmpl_ids = np.fromfile(f, dtype=np.uint32, count=n_pairs)
+        lengths = np.fromfile(f, dtype=np.uint64, count=T)
+        ulengths = np.fromfile(f, dtype=np.uint64, count=T)
+        names = f.read(nb).split(b"\0")[:T]
+        species = f.read(sb).split(b"\0")[:T]
+    return TemplateDB(kmer_bytes, kmer_len, list_off, tmpl_ids, [x.decode("utf-8") for x in names], lengths, ulengths,
+                      [x.decode("utf-8") for x in species], {"templates": s_t, "uniqueLens": s_u, "totalLen": s_l})
+
+
+class NativeTemplateDB:
+    """A template DB loaded by the library itself (kj_db_load): file -> host arrays -> HBM inside the C ABI.  Same
+    surface as TemplateDB for scoring (names, species, lengths, ulengths, summary, device())."""
+
+    def __init__(self, path: str, summary: str | None = None, fmt: int = _abi.KJ_DB_AUTO, ctx: Context | None = None,
+                 part: int = 0, n_parts: int = 1):
+        self.ctx = ctx or default_context()
+        L = _abi.lib()
+        out = C.c_void_p()
+        _abi.check(L.kj_db_load(self.ctx.handle, str(path).encode(), fmt, summary.encode() if summary else None,
+                                part, n_parts, C.byref(out)), self.ctx.handle)
+        self._h = _DbHandle(out, self.ctx)
+        self._key = (part, n_parts)
+        T = int(L.kj_db_n_templates(out))
+        self.names, self.species = [], []
+        self.lengths = np.zeros(T, dtype=np.uint64)
+        self.ulengths = np.zeros(T, dtype=np.uint64)
+        nm, sp, ln, ul = C.c_char_p(), C.c_char_p(), C.c_uint64(), C.c_uint64()
+        for t in range(T):
+            _abi.check(L.kj_db_template(out, t, C.byref(nm), C.byref(sp), C.byref(ln), C.byref(ul)))
+            self.names.append((nm.value or b"").decode("utf-8"))
+            self.species.append((sp.value or b"").decode("utf-8"))
+            self.lengths[t], self.ulengths[t] = ln.value, ul.value
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _abi.check(L.kj_db_summary(out, C.byref(a), C.byref(b), C.byref(c)))
+        self.summary = {"templates": int(a.value), "uniqueLens": int(b.value), "totalLen": int(c.value)}
+
+    @property
+    def n_templates(self) -> int:
+        return len(self.names)
+
+    @property
+    def n_kmers(self) -> int:
+        return self._h.n_kmers
+
+    def device(self, ctx: Context | None = None, part: int = 0, n_parts: int = 1):
+        if (part, n_parts) != self._key or (ctx is not None and ctx is not self.ctx):
+            raise ValueError("a natively loaded DB lives on the context / part it was loaded for")
+        return self._h
+
+
+def load_native(path: str, summary: str | None = None, fmt: int = _abi.KJ_DB_AUTO, ctx: Context | None = None,
+                part: int = 0, n_parts: int = 1) -> NativeTemplateDB:
+    """kj_db_load: any of the reference's JSON layouts or the packed binary, straight into GPU memory."""
+    return NativeTemplateDB(path, summary, fmt, ctx, part, n_parts)

@@ -16,6 +16,37 @@ from .db import TemplateDB, load as load_db
 from .kmers import KmerJS, KmerMap, Promise, mapToJSON  # noqa: F401  (mapToJSON re-exported like the JS module)
 from .matching import Match, NoHitsError
 
+def js_number(x) -> str:
+    """Number#toString of JavaScript: what a template string prints (lib/kmerFinderClient.js:195-208).  Shortest digits
+    that round-trip; positional notation for 1e-7 <= |x| < 1e21, exponent form outside (3e-05 prints as 0.00003, 5.0 as 5)."""
+    from decimal import Decimal
+    if isinstance(x, bool) or not isinstance(x, (int, float)):
+        return str(x)
+    if isinstance(x, int):
+        return str(x)
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Infinity" if x > 0 else "-Infinity"
+    if x == 0:
+        return "0"
+    sign, digits, exp = Decimal(repr(float(x))).as_tuple()
+    ds = "".join(map(str, digits)).lstrip("0") or "0"
+    trail = len(ds) - len(ds.rstrip("0"))
+    ds, exp = ds.rstrip("0") or "0", exp + trail
+    k, n = len(ds), len(ds) + exp                     # value = 0.ds x 10^n
+    if k <= n <= 21:
+        body = ds + "0" * (n - k)
+    elif 0 < n <= 21:
+        body = ds[:n] + "." + ds[n:]
+    elif -6 < n <= 0:
+        body = "0." + "0" * (-n) + ds
+    else:
+        e = n - 1
+        body = (ds[0] + ("." + ds[1:] if k > 1 else "")) + "e" + ("+" if e >= 0 else "-") + str(abs(e))
+    return ("-" if sign else "") + body
+
+
 TSV_HEADER = ("Template\tScore\tExpected\tz\tp_value\tquery\tcoverage [%]\ttemplate coverage [%]"
               "\tdepth\tKmers in Template\tDescription\n")      # lib/kmerFinderClient.js:185
 
@@ -132,7 +163,7 @@ class KmerFinderClient(KmerJS):
                     if self.progress:
                         print(TSV_HEADER, end="")
                 if self.progress:                                              # :195-208
-                    print("\t".join(str(row[k]) for k in ("template", "score", "expected", "z", "probability",
+                    print("\t".join(js_number(row[k]) for k in ("template", "score", "expected", "z", "probability",
                                                           "frac-q", "frac-d", "depth", "kmers-template",
                                                           "species")))
                 # removeWinnerKmers on the caller's map (:220-230)

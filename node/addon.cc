@@ -121,15 +121,9 @@ static napi_value CountsExport(napi_env env, napi_callback_info info) {
     return out;
 }
 
-static napi_value WtaNext(napi_env env, napi_callback_info info) {
-    size_t argc = 1; napi_value argv[1];
-    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-    kj_match *m = unwrap<kj_match>(env, argv[0]);
-    kj_row r;
-    int rc = kj_wta_next(m, &r);
-    if (rc < 0) return throw_kj(env, nullptr, rc);       // the two 'No hits were found! (...)' texts
+// kj_row -> the numeric fields of a result row (lib/kmerFinderClient.js:75-89); template / species are resolved in index.js
+static napi_value row_to_js(napi_env env, const kj_row &r) {
     napi_value out, v;
-    if (rc == 0) { napi_get_null(env, &out); return out; }
     napi_create_object(env, &out);
 #define SETD(name, val) napi_create_double(env, (double)(val), &v); napi_set_named_property(env, out, name, v)
     SETD("templateId", r.template_id); SETD("score", r.score); SETD("expected", r.expected); SETD("z", r.z);
@@ -138,6 +132,17 @@ static napi_value WtaNext(napi_env env, napi_callback_info info) {
     SETD("total-frac-d", r.total_frac_d); SETD("total-temp-cover", r.total_temp_cover);
 #undef SETD
     return out;
+}
+
+static napi_value WtaNext(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value argv[1];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    kj_match *m = unwrap<kj_match>(env, argv[0]);
+    kj_row r;
+    int rc = kj_wta_next(m, &r);
+    if (rc < 0) return throw_kj(env, nullptr, rc);       // the two 'No hits were found! (...)' texts
+    if (rc == 0) { napi_value out; napi_get_null(env, &out); return out; }
+    return row_to_js(env, r);
 }
 
 // ---- helpers for array arguments ---------------------------------------------------------------
@@ -302,6 +307,119 @@ static napi_value CountsAlive(napi_env env, napi_callback_info info) {
     return out;
 }
 
+
+// countLine(ctx, line, prefix, k, step) -> {keys: string[], counts: number[]}
+// KmerJS#kmersInLine (lib/kmers.js:88-100): the windows of one line, this strand only, no length gate: the
+// byte stream API with KJ_F_FORWARD_ONLY | KJ_F_NO_LINE_GATE and base_line = 1 (the buffer IS a sequence line).
+static napi_value CountLine(napi_env env, napi_callback_info info) {
+    size_t argc = 5; napi_value argv[5];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    kj_ctx *ctx = unwrap<kj_ctx>(env, argv[0]);
+    std::string line = get_string(env, argv[1]), prefix = get_string(env, argv[2]);
+    uint32_t k = 16, step = 1;
+    napi_get_value_uint32(env, argv[3], &k); napi_get_value_uint32(env, argv[4], &step);
+    kj_count_params p{};
+    p.prefix = (const uint8_t *)prefix.data(); p.prefix_len = (uint32_t)prefix.size();
+    p.k = k; p.step = step; p.flags = KJ_F_FORWARD_ONLY | KJ_F_NO_LINE_GATE; p.base_line = 1;
+    kj_counts *c = nullptr;
+    int rc = kj_counts_create(ctx, &p, &c);
+    if (rc == KJ_OK) rc = kj_counts_add_buffer(c, (const uint8_t *)line.data(), line.size(), line.size(), KJ_MEM_HOST, 1);
+    if (rc == KJ_OK) rc = kj_counts_finish(c);
+    if (rc) { kj_counts_free(c); return throw_kj(env, ctx, rc); }
+    const uint64_t n = kj_counts_size(c);
+    std::vector<uint8_t> keys(32 * (n + 1)); std::vector<uint32_t> len(n + 1); std::vector<uint64_t> cnt(n + 1);
+    rc = kj_counts_export(c, keys.data(), len.data(), cnt.data());
+    kj_counts_free(c);
+    if (rc) return throw_kj(env, ctx, rc);
+    napi_value out, ks, cs, v;
+    NAPI_OK(napi_create_object(env, &out));
+    NAPI_OK(napi_create_array_with_length(env, n, &ks));
+    NAPI_OK(napi_create_array_with_length(env, n, &cs));
+    for (uint64_t i = 0; i < n; ++i) {
+        napi_create_string_latin1(env, (const char *)keys.data() + 32 * i, len[i], &v); napi_set_element(env, ks, (uint32_t)i, v);
+        napi_create_double(env, (double)cnt[i], &v); napi_set_element(env, cs, (uint32_t)i, v);
+    }
+    napi_set_named_property(env, out, "keys", ks);
+    napi_set_named_property(env, out, "counts", cs);
+    return out;
+}
+
+// dbLoad(ctx, path, summaryPath | null) -> {handle, names, species, lengths, ulengths, summary}   (kj_db_load, any layout)
+static napi_value DbLoad(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value argv[3];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    kj_ctx *ctx = unwrap<kj_ctx>(env, argv[0]);
+    std::string path = get_string(env, argv[1]);
+    napi_valuetype ty; napi_typeof(env, argv[2], &ty);
+    std::string spath = ty == napi_string ? get_string(env, argv[2]) : std::string();
+    kj_db *db = nullptr;
+    int rc = kj_db_load(ctx, path.c_str(), KJ_DB_AUTO, spath.empty() ? nullptr : spath.c_str(), 0, 1, &db);
+    if (rc) return throw_kj(env, ctx, rc);
+    napi_value out, ext, names, species, lengths, ulengths, summary, v;
+    NAPI_OK(napi_create_object(env, &out));
+    NAPI_OK(napi_create_external(env, db, [](napi_env, void *q, void *) { kj_db_free((kj_db *)q); }, nullptr, &ext));
+    const uint32_t T = kj_db_n_templates(db);
+    napi_create_array_with_length(env, T, &names); napi_create_array_with_length(env, T, &species);
+    napi_create_array_with_length(env, T, &lengths); napi_create_array_with_length(env, T, &ulengths);
+    for (uint32_t t = 0; t < T; ++t) {
+        const char *nm = "", *sp = ""; uint64_t ln = 0, ul = 0;
+        kj_db_template(db, t, &nm, &sp, &ln, &ul);
+        napi_create_string_utf8(env, nm, NAPI_AUTO_LENGTH, &v); napi_set_element(env, names, t, v);
+        napi_create_string_utf8(env, sp, NAPI_AUTO_LENGTH, &v); napi_set_element(env, species, t, v);
+        napi_create_double(env, (double)ln, &v); napi_set_element(env, lengths, t, v);
+        napi_create_double(env, (double)ul, &v); napi_set_element(env, ulengths, t, v);
+    }
+    uint64_t st = 0, su = 0, sl = 0;
+    kj_db_summary(db, &st, &su, &sl);
+    napi_create_object(env, &summary);
+    napi_create_double(env, (double)st, &v); napi_set_named_property(env, summary, "templates", v);
+    napi_create_double(env, (double)su, &v); napi_set_named_property(env, summary, "uniqueLens", v);
+    napi_create_double(env, (double)sl, &v); napi_set_named_property(env, summary, "totalLen", v);
+    napi_set_named_property(env, out, "_handle", ext);
+    napi_set_named_property(env, out, "names", names); napi_set_named_property(env, out, "species", species);
+    napi_set_named_property(env, out, "lengths", lengths); napi_set_named_property(env, out, "ulengths", ulengths);
+    napi_set_named_property(env, out, "summary", summary);
+    return out;
+}
+
+// zScore(roundingMode, r1, n1, r2, n2) -> decimal string (lib/stats.js:19-45, exact, 20 places)
+static napi_value ZScore(napi_env env, napi_callback_info info) {
+    size_t argc = 5; napi_value argv[5];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    double a[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 5; ++i) napi_get_value_double(env, argv[i], &a[i]);
+    double z = 0; char text[256];
+    int rc = kj_stats_zscore((int)a[0], (uint64_t)a[1], (uint64_t)a[2], (uint64_t)a[3], (uint64_t)a[4], &z, text, sizeof(text));
+    if (rc) return throw_kj(env, nullptr, rc);
+    napi_value out; NAPI_OK(napi_create_string_utf8(env, text, NAPI_AUTO_LENGTH, &out));
+    return out;
+}
+
+// fastp(zText) -> number (lib/stats.js:52-115, exact compare against the thresholds)
+static napi_value Fastp(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value argv[1];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    double p = 1.0;
+    int rc = kj_stats_fastp_text(get_string(env, argv[0]).c_str(), &p);
+    if (rc) return throw_kj(env, nullptr, rc);
+    napi_value out; NAPI_OK(napi_create_double(env, p, &out));
+    return out;
+}
+
+// standardScoring(match, nTemplates) -> row[]   (lib/kmerFinderServer.js:857-874)
+static napi_value StandardScoring(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value argv[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    kj_match *m = unwrap<kj_match>(env, argv[0]);
+    uint32_t T = 0; napi_get_value_uint32(env, argv[1], &T);
+    std::vector<kj_row> rows(T + 1);
+    uint32_t n = 0;
+    if (int rc = kj_standard_scoring(m, rows.data(), T + 1, &n)) return throw_kj(env, nullptr, rc);
+    napi_value out; NAPI_OK(napi_create_array_with_length(env, n, &out));
+    for (uint32_t i = 0; i < n; ++i) napi_set_element(env, out, i, row_to_js(env, rows[i]));
+    return out;
+}
+
 static napi_value ModuleInit(napi_env env, napi_value exports) {
     napi_property_descriptor props[] = {
         {"init", nullptr, Init, nullptr, nullptr, nullptr, napi_default, nullptr},
@@ -314,6 +432,11 @@ static napi_value ModuleInit(napi_env env, napi_value exports) {
         {"matchScores", nullptr, MatchScores, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"templateKmers", nullptr, TemplateKmers, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"countsAlive", nullptr, CountsAlive, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"countLine", nullptr, CountLine, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"dbLoad", nullptr, DbLoad, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"zScore", nullptr, ZScore, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"fastp", nullptr, Fastp, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"standardScoring", nullptr, StandardScoring, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
     return exports;

@@ -13,13 +13,41 @@ const complementMap = new Map([['A', 'T'], ['T', 'A'], ['G', 'C'], ['C', 'G']]);
 function complement(s) {                                                            // lib/kmers.js:31-38
   return s.replace(/[ATGC]/g, (m) => complementMap.get(m)).split('').reverse().join('');
 }
-function mapToJSON(m) { const o = Object.create(null); for (const [k, v] of m) o[k] = v; return o; }
-function objectToMap(o) { return new Map(Object.entries(o)); }
+function mapToJSON(m) { const o = Object.create(null); for (const [k, v] of m) o[k] = v; return o; }      // lib/kmers.js:46-54
+function objToStrMap(o) { return new Map(Object.entries(o)); }                                             // lib/kmers.js:19-25
+function jsonToStrMap(o) { return objToStrMap(o); }                          // lib/kmers.js:27-29 (takes an object, despite the name)
+function stringToMap(s) { return objToStrMap(JSON.parse(s)); }               // lib/kmers.js:40-42
+function objectToMap(o) { return objToStrMap(o); }                           // lib/kmers.js:43-45
+
+// lib/stats.js: etta, zScore, fastp.  The reference returns bignumber.js objects; these return the exact decimal as a string
+// (zScore) and a number (fastp) -- wrap them in `new BN(..)` where the caller does bignumber arithmetic on them.
+const etta = '1e-8';                                                                                 // lib/stats.js:6
+let roundingMode = 4;                                          // bignumber.js default; lib/kmerFinderServer.js:7 configures 2
+function setRoundingMode(m) { roundingMode = m; }
+function zScore(r1, n1, r2, n2) { return native.zScore(roundingMode, r1, n1, r2, n2); }              // lib/stats.js:19-45
+function fastp(z) { return native.fastp(String(z)); }                                                // lib/stats.js:52-115
 
 class KmerJS {                                                                      // lib/kmers.js:56-186
   constructor(fastq = '', preffix = 'ATGAC', length = 16, step = 1, coverage = 1, progress = true, env = 'node') {
     Object.assign(this, { fastq, preffix, kmerLength: length, step, coverage, progress, env });
     this.kmerMap = new Map(); this.kmerMapSize = 0; this.lines = 0; this.bytesRead = 0;
+  }
+  kmersInLine(line) {                                                               // lib/kmers.js:88-100
+    // a JS string may hold '\n' as an ordinary character (test/kmers.js:14-15 does); the byte stream API splits on it,
+    // so it travels as a byte that occurs nowhere else
+    let prefix = this.preffix, sentinel = null;
+    if (line.includes('\n') || prefix.includes('\n')) {
+      for (let i = 1; i < 256 && sentinel === null; i++) {
+        const ch = String.fromCharCode(i);
+        if (!'ATGC\n'.includes(ch) && !line.includes(ch) && !prefix.includes(ch)) sentinel = ch;
+      }
+      line = line.split('\n').join(sentinel); prefix = prefix.split('\n').join(sentinel);
+    }
+    const r = native.countLine(context(), line, prefix, this.kmerLength, this.step);
+    for (let i = 0; i < r.keys.length; i++) {
+      const k = sentinel === null ? r.keys[i] : r.keys[i].split(sentinel).join('\n');
+      this.kmerMap.set(k, (this.kmerMap.get(k) || 0) + r.counts[i]);
+    }
   }
   readFile() {
     const event = new EventEmitter();
@@ -56,12 +84,15 @@ class KmerFinderClient extends KmerJS {
   constructor(fastq, env, preffix = 'ATGAC', length = 16, step = 1, coverage = 1, out = true, db = 'server',
     url = 'http://localhost:3000/kmers', summary, collection = 'genomes', dbName = 'Kmers') {
     super(fastq, preffix, length, step, coverage, out, env);
-    Object.assign(this, { dbLocation: db, dbURL: url, collection, dbName, maxHits: 100 });
+    Object.assign(this, { dbLocation: db, dbURL: url, collection, dbName, maxHits: 100,
+      summaryPath: typeof summary === 'string' ? summary : null });
   }
   findKmers() { return this.readFile(); }
   findFirstMatch(kmerQuery) {
     return new Promise((resolve, reject) => {
       try {
+        // a path: any of the reference's DB layouts or the packed binary, file -> GPU inside the library (kj_db_load)
+        if (typeof this.dbLocation === 'string') this.dbLocation = native.dbLoad(context(), this.dbLocation, this.summaryPath || null);
         const db = this.dbLocation;
         if (!db._handle) db._handle = native.dbCreate(context(), db);
         kmerQuery.set('db', this.dbName); kmerQuery.set('collection', this.collection);   // :132-133
@@ -106,6 +137,19 @@ class KmerFinderClient extends KmerJS {
       yield row;
     }
   }
+
+  // standardScoring (lib/kmerFinderServer.js:857-874): one row per matched template of the first match, by score.
+  // Templates the evalue gate rejects produce no row (the reference leaves `undefined` entries in their place).
+  standardScoring() {
+    const db = this.dbLocation;
+    return native.standardScoring(this._match, db.names.length).map((r) => {
+      const row = {};
+      for (const k of ROW_KEYS) row[k] = k === 'template' ? db.names[r.templateId] : k === 'species' ? db.species[r.templateId] : r[k];
+      return row;
+    });
+  }
+  close() { this._match = null; }          // the native handles are released by their finalizers
 }
 
-module.exports = { kmerjs, default: kmerjs, KmerJS, KmerFinderClient, complement, complementMap, mapToJSON, objectToMap };
+module.exports = { kmerjs, default: kmerjs, KmerJS, KmerFinderClient, complement, complementMap, mapToJSON, objToStrMap,
+  jsonToStrMap, stringToMap, objectToMap, zScore, fastp, etta, setRoundingMode };

@@ -104,7 +104,11 @@ def test_db_loaders_agree(tmp_path):
     p3 = tmp_path / "map.json"; p3.write_text(json.dumps(csv_map))
     ps = tmp_path / "summary.json"; ps.write_text(json.dumps(summary))
     p4 = tmp_path / "packed.npz"; a.save(str(p4))
-    dbs = [load_db(str(p1), str(ps)), load_db(str(p2), summary), load_db(str(p4)),
+    p5 = tmp_path / "packed.kjdb"; a.save(str(p5))              # the versioned binary (kj_db_save_packed): no pickle anywhere
+    assert p5.read_bytes()[:8] == b"KJDBv001"
+    import numpy as np
+    assert not any(v.dtype == object for v in np.load(str(p4), allow_pickle=False).values())
+    dbs = [load_db(str(p1), str(ps)), load_db(str(p2), summary), load_db(str(p4)), load_db(str(p5)),
            load_db(str(p3), summary, lengths={t: v["lengths"] for t, v in attrs.items()},
                    ulengths={t: v["ulength"] for t, v in attrs.items()},
                    descriptions={t: v["species"] for t, v in attrs.items()})]

@@ -379,3 +379,53 @@ def test_ten_thousand_templates_vs_oracle(max_hits):
     us = [r["score"] for r in e_rows]
     assert T < 10_000 or max_hits < 100 or len(set(us)) < len(us)             # ties took part
     m.free(); c.free()
+
+
+@pytest.mark.parametrize("fmt", ["kmer_docs", "redis_strings", "template_docs", "kmerfinder_map", "packed"])
+def test_native_db_load_scores_like_the_oracle(fmt, tmp_path):
+    """kj_db_load (C ABI): each on-disk layout of the reference (lib/kmerFinderServer.js:68-92,184-199,
+    src/kmerPyToMongo.py:35-42, lib/index.js:184-192) and the packed binary, file -> GPU, scored against the oracle
+    fed with the same database."""
+    from kmerjs_b200.db import load as load_db, load_native
+    golden = json.loads(read_golden("test_long.json"))
+    qmap = OrderedDict((k.encode("latin-1"), v) for k, v in golden.items())
+    rng = random.Random(31)
+    lists, attrs, summary = synthetic_db(list(qmap.keys()), rng, n_templates=20, decoys=60)
+    names = list(attrs)
+    spath = tmp_path / "summary.json"
+    spath.write_text(json.dumps(summary))
+    path = tmp_path / ("db." + ("kjdb" if fmt == "packed" else "json"))
+    if fmt in ("kmer_docs", "redis_strings"):
+        rec = lambda t: {"sequence": t, "lengths": attrs[t]["lengths"], "ulengths": attrs[t]["ulength"], "species": attrs[t]["species"]}
+        docs = [{"kmer": k.decode("latin-1"), "templates": [json.dumps(rec(t)) if fmt == "redis_strings" else rec(t) for t in lst]}
+                for k, lst in lists.items()]
+        path.write_text(json.dumps(docs))
+        host = load_db(str(path), str(spath))
+    elif fmt == "template_docs":
+        docs = [{"sequence": t, "lengths": attrs[t]["lengths"], "ulenght": attrs[t]["ulength"], "species": attrs[t]["species"],
+                 "reads": [k.decode("latin-1") for k, lst in lists.items() if t in lst]} for t in names]
+        path.write_text(json.dumps(docs))
+        host = load_db(str(path), str(spath))
+    elif fmt == "kmerfinder_map":
+        path.write_text(json.dumps({k.decode("latin-1"): ",".join(lst) for k, lst in lists.items()}))
+        side = {"lengths": {t: attrs[t]["lengths"] for t in names}, "ulengths": {t: attrs[t]["ulength"] for t in names},
+                "descriptions": {t: attrs[t]["species"] for t in names}}
+        for suffix, d in side.items():
+            (tmp_path / f"db.json.{suffix}.json").write_text(json.dumps(d))
+        host = load_db(str(path), str(spath), **side)
+    else:
+        TemplateDB.from_lists(lists, attrs, summary).save(str(path))
+        host = load_db(str(path))
+    native = load_native(str(path), None if fmt == "packed" else str(spath))
+    assert native.summary == summary and native.n_templates == host.n_templates
+    assert sorted(native.names) == sorted(host.names)
+    o_lists, o_attrs = host.to_lists()                       # the oracle sees what the host loader read from the same file
+    e_first, e_hits, e_rows, e_err, _ = oracle_rows(qmap, o_lists, o_attrs, summary)
+    counts = counts_from_map(golden, "ATGAC", 16, 1)
+    g_first, g_hits, g_rows, g_err, m = gpu_rows(counts, native)
+    assert g_hits == e_hits and list(g_first.keys()) == list(e_first.keys())
+    assert all((g_first[n]["uScore"], g_first[n]["tScore"]) == (e_first[n]["uScore"], e_first[n]["tScore"]) for n in e_first)
+    assert len(e_rows) >= 2
+    check_rows(g_rows, e_rows)
+    assert g_err == e_err
+    m.free(); counts.free()

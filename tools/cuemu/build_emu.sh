@@ -9,7 +9,7 @@ SAN=${SAN:--fsanitize=address,undefined -fno-sanitize-recover=undefined}
 OPT=${OPT:--O1}
 FLAGS="-std=c++17 $OPT -g -fPIC -DKJ_CPU_EMU -I tools/cuemu -Wall -Wno-unused-function -Wno-unknown-pragmas -Wno-unused-variable $SAN"
 pids=()
-for f in kj_ctx.cu kj_count.cu kj_score.cu kj_synth.cu kj_stats.cpp; do
+for f in kj_ctx.cu kj_count.cu kj_score.cu kj_dbio.cu kj_synth.cu kj_stats.cpp; do
   g++ $FLAGS -x c++ -c kmerjs_b200/csrc/$f -o build/emu/${f%.*}.o &
   pids+=($!)
 done

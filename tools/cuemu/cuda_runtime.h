@@ -47,6 +47,8 @@ static inline uint2 make_uint2(uint32_t a, uint32_t b) { return uint2{a, b}; }
 struct __attribute__((aligned(16))) ulonglong2 { unsigned long long x, y; };
 static inline ulonglong2 make_ulonglong2(unsigned long long a, unsigned long long b) { return ulonglong2{a, b}; }
 
+using std::min;
+using std::max;
 extern uint3 threadIdx, blockIdx;
 extern dim3 blockDim, gridDim;
 

@@ -570,24 +570,23 @@ static int make_tensor_map(kj_ctx *ctx, const uint8_t *dbuf, uint64_t n, KjTenso
 }
 
 typedef void (*KjFilterFn)(const KjTensorMap, const KjScanArgs);
-template <int KW>
-static KjFilterFn pick_filter_kernel_kw(const KjScanArgs &a) {
+static KjFilterFn pick_filter_kernel(const KjScanArgs &a) {
     switch (a.mp) {
-        case 1: return kj_warp_filter_kernel<1, KW>;
-        case 2: return kj_warp_filter_kernel<2, KW>;
-        case 3: return kj_warp_filter_kernel<3, KW>;
-        case 4: return kj_warp_filter_kernel<4, KW>;
-        case 5: return kj_warp_filter_kernel<5, KW>;
-        case 6: return kj_warp_filter_kernel<6, KW>;
-        case 7: return kj_warp_filter_kernel<7, KW>;
-        default: return kj_warp_filter_kernel<8, KW>;
+        case 1: return kj_warp_filter_kernel<1>;
+        case 2: return kj_warp_filter_kernel<2>;
+        case 3: return kj_warp_filter_kernel<3>;
+        case 4: return kj_warp_filter_kernel<4>;
+        case 5: return kj_warp_filter_kernel<5>;
+        case 6: return kj_warp_filter_kernel<6>;
+        case 7: return kj_warp_filter_kernel<7>;
+        default: return kj_warp_filter_kernel<8>;
     }
 }
-static KjFilterFn pick_filter_kernel(const KjScanArgs &a) {
-    return a.k <= 16 ? pick_filter_kernel_kw<4>(a) : pick_filter_kernel_kw<8>(a);
-}
+typedef void (*KjResolveFn)(const KjScanArgs);
+// the byte check looks at 4 words of the window when k <= 16 (the KmerFinder default), at 8 otherwise
+static KjResolveFn pick_resolve_kernel(const KjScanArgs &a) { return a.k <= 16 ? kj_resolve_kernel<4> : kj_resolve_kernel<8>; }
 
-// scan (with the byte check of the candidates) -> exclusive scan of the tile counts -> resolve, all stream-ordered;
+// scan -> exclusive scan of the tile counts -> resolve, all stream-ordered;
 // retry_only: the resolve pass over the marked entries
 static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only) {
     kj_ctx *ctx = c->ctx;
@@ -623,7 +622,7 @@ static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only) {
         }
 #endif
     }
-    KJ_LAUNCH(kj_resolve_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);
+    KJ_LAUNCH(pick_resolve_kernel(a), ctx->sm_count * 8, 256, 0, ctx->stream, a);
     ctx->launches++;
     if (a.count_bases && !retry_only) {
         KJ_LAUNCH(kj_bases_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);
@@ -729,8 +728,8 @@ static int scan_piece_filter(kj_counts *c, const uint8_t *dbuf, uint64_t n, uint
     const uint64_t chunks = own_n / 16 + 1;
     double share = 48.0;
     for (uint32_t i = 0; i < std::min<uint32_t>(m, KJ_MAX_MP); ++i) share *= 0.25;
-    // entries: the candidates whose bytes pass the exact check -- about the emissions plus what header and quality lines
-    // happen to spell; slots are reserved in blocks of KJ_WT_BLOCK per warp, so the buffer holds a few blocks for every warp
+    // (with slack: 48 instead of 32); slots are reserved in blocks of KJ_WT_BLOCK per warp, so the buffer also holds a few
+    // blocks for every warp
     const uint64_t want_ent = std::min<uint64_t>(hard_bound, (uint64_t)(std::min(1.0, share) * (double)chunks)) + (1ull << 20);
     rc = ensure_filter_buffers(c, (uint32_t)n_tiles64, want_ent);
     if (rc) return rc;

@@ -14,19 +14,21 @@
 //                           start k - |prefix| bytes before): lib/kmers.js:88-100,151-155 as an exact superset
 //                           filter.  Both strands share the shifted words.  Chunks with a candidate go to a queue
 //                           per lane (a predicated store, no atomic, no branch) and are drained by the whole
-//                           warp every few tiles: exact check of the window's bytes, then one 16-byte entry per
-//                           surviving window {key | tile, '\n' before it in the tile, column}.  The tile's newline
-//                           count goes to tile_cnt[]; nothing here needs the number of lines before the tile.
+//                           warp every few tiles into 16-byte entries {chunk, candidate lanes, '\n' before it in the
+//                           tile, its own '\n' mask, distance back to the line start}.  The tile's newline count goes to
+//                           tile_cnt[]; nothing here needs the number of lines before the tile.
 //   (exclusive scan of tile_cnt -> tile_excl, cub::DeviceScan; the record FSM of lib/kmers.js:151-163 is
 //    "line index mod 4" over the whole stream)
 //   kj_resolve_kernel       one thread per entry, the whole GPU: line index of the candidate = lines before the launch +
-//                           tile_excl + in-tile count -> keep iff 1 mod 4 (the reference's i === 1); first-seen ordinal;
-//                           hash-table update.  An emission that finds no slot marks its entry for a retry pass after the
-//                           host has grown the table: nothing is ever dropped, whatever the input looks like.
-// The window's bytes are checked (prefix, no '\n' inside, alphabet) and turned into the 2k-bit key by the DRAIN of the scan
-// kernel, a few tiles after the tile went by: the bytes are still in L2 then.  Fetching them in the resolve kernel cost
-// 0.19 ms of random DRAM reads per 10 M reads; the byte check also rejects nearly every candidate that sits in a header or
-// quality line, so 2.7 M entries reach the resolve kernel instead of 6.8 M.
+//                           tile_excl + in-tile count -> keep iff 1 mod 4 (the reference's i === 1); the window's bytes
+//                           (prefix, no '\n' inside, alphabet) -> 2k-bit key; first-seen ordinal; hash-table update.  An
+//                           emission that finds no slot marks its entry for a retry pass after the host has grown the
+//                           table: nothing is ever dropped, whatever the input looks like.
+// Where the byte check lives was measured three ways on 10 M reads (3.46 GB): in the resolve kernel (this file: the windows
+// come back from DRAM, 1-2 sectors each, but 64 warps per SM hide it); split into a compacting filter kernel and a dense
+// emit kernel (0.22 + 0.19 ms: the append counter and the second pass cost more than the divergence they removed); inside the
+// drain of the scan kernel, where the bytes are still in L2 (scan 0.77 -> 1.20 ms: 16 warps per SM cannot hide the L2
+// latency, and the key extraction competes with the search for the ALU pipe the scan is bound by).
 #pragma once
 #include "kj_scan.cuh"
 
@@ -41,14 +43,11 @@
 #define KJ_WT_WARPS 8
 #define KJ_WT_THREADS (KJ_WT_WARPS * 32)
 #define KJ_ENT_NODIST 0xFFFFu
-// entry = {word0, meta}.  word0: the 2k-bit key, or for an irregular window (a byte that is not A/C/G/T) its start j.
-// meta: tile (28 bits) | '\n' of the tile before the candidate (13) << 28 | column, or with NOCOL the window start relative
-// to the tile + 32 (12) << 41 | NOCOL << 53 (the line starts before the tile) | strand << 54 | irregular << 55 | retry << 63.
-// A blank entry (unused slot of a reserved block) is all ones.
-#define KJ_ENT_NOCOL (1ull << 53)
-#define KJ_ENT_STRAND (1ull << 54)
-#define KJ_ENT_IRR (1ull << 55)
-#define KJ_ENT_RETRY (1ull << 63)
+// entry (16 bytes, one per chunk with candidates) = {chunk index in the launch (40 bits) | '\n' of the tile before the chunk
+// (13) << 40 | retry << 63, candidate lanes (bit 2p: forward window at byte p of the chunk, 2p + 1: reverse),
+// the chunk's own '\n' mask (16) | distance from the chunk back to the byte after the last '\n' of the tile << 16
+// (KJ_ENT_NODIST: the line starts before the tile)}.  A blank entry (unused slot of a reserved block) has no candidate lanes.
+#define KJ_ENT_RETRY32 0x80000000u               // in the entry's second 32-bit word
 
 struct __align__(16) KjWarpSmem {
     uint4 bitmap[KJ_WT_RING][32];                // lane l: the '\n' masks of its 8 chunks, 16 bits each, in stream order
@@ -208,69 +207,21 @@ __device__ __forceinline__ void kj_wt_finish_tile(const KjScanArgs &a, KjWarpSme
     __syncwarp();
 }
 
-// The window at buffer offset j, its chunks loaded: exact check and key.  Straight-line SIMD-in-register code.  KW = 4-byte
-// words of the window the code looks at: 8 covers every k <= 32; 4 (k <= 16, the KmerFinder default) halves the work.
-// Returns 0: not an emission (prefix bytes differ, crosses the end of the line, ...); 1: key holds the 2k-bit key;
-// 2: irregular (some byte is not A/C/G/T): the byte string is the key.
-template <int KW>
-__device__ __forceinline__ int kj_window_key(const KjScanArgs &a, uint64_t j, uint32_t strand, const uint4 v0, const uint4 v1,
-                                             const uint4 v2, uint64_t &key) {
-    const uint32_t k = a.k;
-    const uint32_t o = (uint32_t)(j & 15u);
-    const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-    const uint32_t q = o >> 2, r8 = (o & 3u) * 8u;
-    uint32_t X[KW];
-#pragma unroll
-    for (int i = 0; i < KW; ++i) {
-        const uint32_t lo = q == 0 ? W[i] : q == 1 ? W[i + 1] : q == 2 ? W[i + 2] : W[i + 3];
-        const uint32_t hi = q == 0 ? W[i + 1] : q == 1 ? W[i + 2] : q == 2 ? W[i + 3] : W[i + 4];
-        X[i] = kj_funnel_r(lo, hi, r8);
-    }
-    uint32_t bad = 0, nl = 0, irr = 0, p_lo = 0, p_hi = 0;
-#pragma unroll
-    for (int i = 0; i < KW; ++i) {
-        if (4u * i < k) {
-            const uint32_t bm = (4u * i + 4u <= k) ? 0xFFFFFFFFu : ((1u << (8u * (k - 4u * i))) - 1u);   // bytes of the window
-            bad |= (X[i] ^ a.want[strand][i]) & a.wmask[strand][i];
-            nl |= kj_nl_msb4(X[i]) & bm;
-            irr |= kj_not_acgt4(X[i]) & bm;
-            const uint32_t c8 = kj_pack4(X[i] & bm);
-            if (i < 4) p_lo |= c8 << (8 * i); else p_hi |= c8 << (8 * (i - 4));
-        }
-    }
-    if (nl | bad) return 0;                               // crosses the end of the line / prefix bytes differ
-    if (k == 1 && a.line_gate) {                          // lib/kmers.js:151  line.length > 1: a lone byte is not processed
-        const bool first = j == 0 ? (a.ctr->carry_last[a.parity] == a.voff) : (a.buf[j - 1] == '\n');
-        const bool more = (j + 1 < a.n) && a.buf[j + 1] != '\n';
-        if (first && !more) return 0;
-    }
-    if (irr) return 2;
-    const uint64_t P = ((uint64_t)p_hi << 32) | p_lo;     // code of window byte i at bits 2i
-    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
-    // forward key: first base most significant; reverse key: complement codes, last base first
-    key = strand ? ((P ^ 0xAAAAAAAAAAAAAAAAull) & kmask) : (kj_pairrev64(P) >> (64u - 2u * k));
-    return 1;
-}
-
 // ----------------------------------------------------------------------------- drain
 
 // one thread: reserve the next block of entry slots
 __device__ __forceinline__ unsigned long long kj_wt_reserve(const KjScanArgs &a) {
     return atomicAdd(&a.ctr->n_cand, (unsigned long long)KJ_WT_BLOCK);
 }
-// the unused slots [at, at + n) of a block become blank entries
+// the unused slots [at, at + n) of a block become empty entries (no candidate lanes)
 __device__ __forceinline__ void kj_wt_blank(const KjScanArgs &a, unsigned long long at, uint32_t n, uint32_t lane) {
     for (uint32_t i = lane; i < n; i += 32)
-        if (at + i < a.cand_cap) reinterpret_cast<ulonglong2 *>(a.cand)[at + i] = make_ulonglong2(~0ull, ~0ull);
+        if (at + i < a.cand_cap) reinterpret_cast<uint4 *>(a.cand)[at + i] = make_uint4(0, 0, 0, 0);
 }
 
-// The whole warp turns the lanes' queues into entries in global memory.  The queue entries (chunks with candidate lanes) are
-// made dense again, one per lane and round (entry e of the concatenated queues belongs to the lane whose inclusive count is
-// the first above e: five shuffle probes find it); every candidate of the chunk then takes the exact check of its window's
-// bytes -- read from global memory, where the tile went by a few microseconds ago: L2 hits -- and the survivors are
-// appended as {key, tile | '\n' before | column}.  Entry slots come from blocks of KJ_WT_BLOCK the warp reserves one drain
-// ahead, so that nothing waits for the atomic.
-template <int KW>
+// The whole warp turns the lanes' queues into entries in global memory: dense again, one entry per lane and round (entry e of
+// the concatenated queues belongs to the lane whose inclusive count is the first above e: five shuffle probes find it).
+// Entry slots come from blocks of KJ_WT_BLOCK the warp reserves one drain ahead, so that nothing waits for the atomic.
 static __device__ __noinline__ void kj_wt_drain(const KjScanArgs &a, KjWarpSmem &ws, uint32_t t_cur, uint32_t slot_cur,
                                                 uint32_t G, KjWarpRegs &wr) {
     const uint32_t lane = threadIdx.x & 31;
@@ -293,16 +244,16 @@ static __device__ __noinline__ void kj_wt_drain(const KjScanArgs &a, KjWarpSmem 
         }
         src &= 31u;
         const uint32_t first = __shfl_sync(0xFFFFFFFFu, incl - mine, src);     // entries of the lanes before src
-        // this lane's chunk: its candidate lanes and what the tile's newline bitmap says about it
-        uint32_t lanes = 0, nlmask = 0, nlb = 0, dist = KJ_ENT_NODIST, tile = 0;
-        uint64_t chunk = 0;
+        bool keep = false;
+        uint4 rec = make_uint4(0, 0, 0, 0);
         if (e < n) {
             const uint2 qe = ws.pq[e - first][src];
-            const uint32_t slot = qe.y >> 3, i = qe.y & 7u;
+            const uint32_t z = qe.x, loc = qe.y;
+            const uint32_t slot = loc >> 3, i = loc & 7u;
             if (src != 31u) {                                       // lane 31 converts the row behind the tile: not owned
-                lanes = qe.x;
+                keep = true;
                 const uint32_t age = (slot_cur - slot) & (KJ_WT_RING - 1u);
-                tile = t_cur - age * G;
+                const uint32_t tile = t_cur - age * G;
                 const uint4 bm = ws.bitmap[slot][src];
                 const uint32_t w[4] = {bm.x, bm.y, bm.z, bm.w};
                 // bits of the lane's 128 below chunk i
@@ -315,6 +266,7 @@ static __device__ __noinline__ void kj_wt_drain(const KjScanArgs &a, KjWarpSmem 
                     before += __popc(x);
                     if (x) { hi_w = x; hi_j = j; }
                 }
+                uint32_t dist = KJ_ENT_NODIST;
                 if (hi_w) {
                     dist = i * 16u - (hi_j * 32u + (31u - __clz(hi_w)) + 1u);
                 } else {
@@ -329,64 +281,29 @@ static __device__ __noinline__ void kj_wt_drain(const KjScanArgs &a, KjWarpSmem 
                         }
                     }
                 }
-                nlmask = (w[i >> 1] >> ((i & 1u) * 16u)) & 0xFFFFu;
-                nlb = ws.lanepre[slot][src] + before;
-                chunk = (uint64_t)tile * KJ_WT_CHUNKS + src * 8u + i;
+                const uint32_t nlmask = (w[i >> 1] >> ((i & 1u) * 16u)) & 0xFFFFu;
+                const uint64_t chunk = (uint64_t)tile * KJ_WT_CHUNKS + src * 8u + i;
+                const uint64_t word = chunk | ((uint64_t)(ws.lanepre[slot][src] + before) << 40);
+                rec = make_uint4((uint32_t)word, (uint32_t)(word >> 32), z, nlmask | (dist << 16));
             }
         }
-        // one candidate of every lane's chunk per round (a chunk rarely holds two)
-        while (__any_sync(0xFFFFFFFFu, lanes != 0u)) {
-            bool keep = false;
-            unsigned long long w0 = 0, meta = 0;
-            if (lanes) {
-                const uint32_t bit = __ffs(lanes) - 1;
-                lanes &= lanes - 1;
-                const uint32_t p = bit >> 1, strand = bit & 1u;
-                const uint64_t pos = chunk * 16u + p;                      // where the prefix / complement(prefix) starts
-                const uint32_t back = strand ? a.rc_shift : 0u;            // the reverse-strand window starts k - m before
-                if (pos >= back && pos - back < a.own_n && pos - back + a.k <= a.n) {
-                    const uint64_t j = pos - back;
-                    const uint32_t below = nlmask & ((1u << p) - 1u);
-                    // first byte of the line, when it lies in this tile
-                    bool have_ls = true;
-                    uint64_t ls = 0;
-                    if (below) ls = chunk * 16u + (31u - __clz(below)) + 1u;
-                    else if (dist != KJ_ENT_NODIST) ls = chunk * 16u - dist;
-                    else have_ls = false;
-                    if (!have_ls || j >= ls) {                             // else: a '\n' between the window start and the prefix
-                        uint4 v0, v1, v2;
-                        kj_window_load(a, j, v0, v1, v2);
-                        uint64_t key = 0;
-                        const int st = kj_window_key<KW>(a, j, strand, v0, v1, v2, key);
-                        if (st) {
-                            keep = true;
-                            const uint64_t tile_start = (uint64_t)tile * KJ_WT_BYTES;
-                            const uint64_t colf = have_ls ? (j - ls) : (j + 32u - tile_start);
-                            w0 = st == 1 ? key : j;
-                            meta = (unsigned long long)tile | ((unsigned long long)(nlb + __popc(below)) << 28) | (colf << 41) |
-                                   (have_ls ? 0ull : KJ_ENT_NOCOL) | (strand ? KJ_ENT_STRAND : 0ull) | (st == 2 ? KJ_ENT_IRR : 0ull);
-                        }
-                    }
-                }
-            }
-            const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
-            const uint32_t need = __popc(kb);
-            if (need > wr.blk_left) {
-                // the block is used up: blank its tail, go on in the one reserved ahead, reserve the one after
-                kj_wt_blank(a, wr.blk_at, wr.blk_left, lane);
-                wr.blk_at = wr.next_at;
-                wr.blk_left = KJ_WT_BLOCK;
-                unsigned long long nx = 0;
-                if (lane == 0) nx = kj_wt_reserve(a);
-                wr.next_at = __shfl_sync(0xFFFFFFFFu, nx, 0);
-            }
-            if (keep) {
-                const unsigned long long at = wr.blk_at + __popc(kb & ((1u << lane) - 1u));
-                if (at < a.cand_cap) reinterpret_cast<ulonglong2 *>(a.cand)[at] = make_ulonglong2(w0, meta);   // beyond: the host repeats the piece
-            }
-            wr.blk_at += need;
-            wr.blk_left -= need;
+        const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
+        const uint32_t need = __popc(kb);
+        if (need > wr.blk_left) {
+            // the block is used up: blank its tail, go on in the one reserved ahead, reserve the one after
+            kj_wt_blank(a, wr.blk_at, wr.blk_left, lane);
+            wr.blk_at = wr.next_at;
+            wr.blk_left = KJ_WT_BLOCK;
+            unsigned long long nx = 0;
+            if (lane == 0) nx = kj_wt_reserve(a);
+            wr.next_at = __shfl_sync(0xFFFFFFFFu, nx, 0);
         }
+        if (keep) {
+            const unsigned long long at = wr.blk_at + __popc(kb & ((1u << lane) - 1u));
+            if (at < a.cand_cap) reinterpret_cast<uint4 *>(a.cand)[at] = rec;    // beyond the buffer: the host sees n_cand and repeats the piece
+        }
+        wr.blk_at += need;
+        wr.blk_left -= need;
     }
     __syncwarp();
     wr.qaddr = kj_qaddr_of(ws, lane);
@@ -417,7 +334,7 @@ static __device__ __noinline__ void kj_wt_edge_tile(const KjScanArgs &a, KjWarpS
     kj_wt_finish_tile<MP, true>(a, ws, cw, nlp, t, slot, lane, live, qaddr);
 }
 
-template <int MP, int KW>
+template <int MP>
 __global__ void __launch_bounds__(KJ_WT_THREADS, 2)
 kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_constant__ KjScanArgs a) {
     KJ_DYN_SMEM(dyn);
@@ -468,7 +385,7 @@ kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_con
         const uint32_t s = it % KJ_WT_STAGES, slot = it & (KJ_WT_RING - 1u);
         // room in every lane's queue for everything this tile can add to it (8 entries)
         if (__any_sync(0xFFFFFFFFu, kj_q_count(ws, lane, wr.qaddr) + 8u > KJ_WT_PQCAP))
-            kj_wt_drain<KW>(a, ws, t - G, (slot - 1u) & (KJ_WT_RING - 1u), G, wr);
+            kj_wt_drain(a, ws, t - G, (slot - 1u) & (KJ_WT_RING - 1u), G, wr);
         kj_bar_wait(&bars[s], (it / KJ_WT_STAGES) & 1u);
         const uint32_t soff = s * KJ_WT_STAGE_BYTES;
         uint32_t cw[9], nlp[4];
@@ -487,26 +404,78 @@ kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_con
         cw[8] = __shfl_down_sync(0xFFFFFFFFu, cw[0], 1);
         kj_wt_finish_tile<MP, false>(a, ws, cw, nlp, t, slot, lane, live, wr.qaddr);
         // the ring keeps KJ_WT_RING tiles: drain when it is full
-        if (slot == KJ_WT_RING - 1u) kj_wt_drain<KW>(a, ws, t, slot, G, wr);
+        if (slot == KJ_WT_RING - 1u) kj_wt_drain(a, ws, t, slot, G, wr);
     }
     // ---- edge tiles
     for (; t < a.n_tiles; t += G, ++it) {
         const uint32_t slot = it & (KJ_WT_RING - 1u);
         if (__any_sync(0xFFFFFFFFu, kj_q_count(ws, lane, wr.qaddr) + 8u > KJ_WT_PQCAP))
-            kj_wt_drain<KW>(a, ws, t - G, (slot - 1u) & (KJ_WT_RING - 1u), G, wr);
+            kj_wt_drain(a, ws, t - G, (slot - 1u) & (KJ_WT_RING - 1u), G, wr);
         kj_wt_edge_tile<MP>(a, ws, t, slot, live, wr.qaddr);
-        if (slot == KJ_WT_RING - 1u) kj_wt_drain<KW>(a, ws, t, slot, G, wr);
+        if (slot == KJ_WT_RING - 1u) kj_wt_drain(a, ws, t, slot, G, wr);
     }
     // what is left in the queues (the ring slot of the last tile is (it - 1) mod ring), then the unused entry slots
-    kj_wt_drain<KW>(a, ws, t - G, (it - 1u) & (KJ_WT_RING - 1u), G, wr);
+    kj_wt_drain(a, ws, t - G, (it - 1u) & (KJ_WT_RING - 1u), G, wr);
     kj_wt_blank(a, wr.blk_at, wr.blk_left, lane);
     kj_wt_blank(a, wr.next_at, KJ_WT_BLOCK, lane);
 }
 
 // ----------------------------------------------------------------------------- resolve kernel
 
-// Entries -> table.  a.resolve_retry == 0: every entry; != 0: the entries an earlier pass marked.
+// The window at buffer offset j, its chunks loaded: exact check and key.  Straight-line SIMD-in-register code.  KW = 4-byte
+// words of the window the code looks at: 8 covers every k <= 32; 4 (k <= 16, the KmerFinder default) halves the work.
+// Returns 0: not an emission (prefix bytes differ, crosses the end of the line, ...); 1: key holds the 2k-bit key;
+// 2: irregular (some byte is not A/C/G/T): the byte string is the key.
+template <int KW>
+__device__ __forceinline__ int kj_window_key(const KjScanArgs &a, uint64_t j, uint32_t strand, const uint4 v0, const uint4 v1,
+                                             const uint4 v2, uint64_t &key) {
+    const uint32_t k = a.k;
+    const uint32_t o = (uint32_t)(j & 15u);
+    const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+    const uint32_t q = o >> 2, r8 = (o & 3u) * 8u;
+    uint32_t X[KW];
+#pragma unroll
+    for (int i = 0; i < KW; ++i) {
+        const uint32_t lo = q == 0 ? W[i] : q == 1 ? W[i + 1] : q == 2 ? W[i + 2] : W[i + 3];
+        const uint32_t hi = q == 0 ? W[i + 1] : q == 1 ? W[i + 2] : q == 2 ? W[i + 3] : W[i + 4];
+        X[i] = kj_funnel_r(lo, hi, r8);
+    }
+    uint32_t bad = 0, nl = 0, irr = 0, p_lo = 0, p_hi = 0;
+#pragma unroll
+    for (int i = 0; i < KW; ++i) {
+        if (4u * i < k) {
+            const uint32_t bm = (4u * i + 4u <= k) ? 0xFFFFFFFFu : ((1u << (8u * (k - 4u * i))) - 1u);   // bytes of the window
+            bad |= (X[i] ^ a.want[strand][i]) & a.wmask[strand][i];
+            nl |= kj_nl_msb4(X[i]) & bm;
+            irr |= kj_not_acgt4(X[i]) & bm;
+            const uint32_t c8 = kj_pack4(X[i] & bm);
+            if (i < 4) p_lo |= c8 << (8 * i); else p_hi |= c8 << (8 * (i - 4));
+        }
+    }
+    if (nl | bad) return 0;                               // crosses the end of the line / prefix bytes differ
+    if (k == 1 && a.line_gate) {                          // lib/kmers.js:151  line.length > 1: a lone byte is not processed
+        const bool first = j == 0 ? (a.ctr->carry_last[a.parity] == a.voff) : (a.buf[j - 1] == '\n');
+        const bool more = (j + 1 < a.n) && a.buf[j + 1] != '\n';
+        if (first && !more) return 0;
+    }
+    if (irr) return 2;
+    const uint64_t P = ((uint64_t)p_hi << 32) | p_lo;     // code of window byte i at bits 2i
+    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    // forward key: first base most significant; reverse key: complement codes, last base first
+    key = strand ? ((P ^ 0xAAAAAAAAAAAAAAAAull) & kmask) : (kj_pairrev64(P) >> (64u - 2u * k));
+    return 1;
+}
+
+// Entries -> table, one thread per entry (a chunk with candidate positions), the whole GPU at full occupancy.  For every
+// candidate: the line index (lines before the launch + lines before the tile + '\n' before the position inside the tile) must
+// be 1 mod 4 (lib/kmers.js:151, i === 1) -- that drops every candidate of a header or quality line before anything is
+// fetched; then the window's bytes (one or two 32-byte sectors from DRAM: the kernel lives on memory-level parallelism),
+// the exact check, the key, the first-seen ordinal = (read, strand, column), the hash-table update.
+// a.resolve_retry == 0: every entry; != 0: the entries an earlier pass marked.  A candidate that finds no slot within the
+// probe limit stays in the entry (its bit of the lane mask is kept, the others are cleared) and the entry is marked: the
+// host grows the table and runs the retry pass; nothing is ever dropped, whatever the input looks like.
 // Block 0 also closes the stream state of the launch (lines and last '\n' so far) for the next one.
+template <int KW>
 __global__ void __launch_bounds__(256) kj_resolve_kernel(const __grid_constant__ KjScanArgs a) {
     const unsigned long long n_ent = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;
     const uint64_t base_lines = a.ctr->carry_lines[a.parity];
@@ -516,45 +485,67 @@ __global__ void __launch_bounds__(256) kj_resolve_kernel(const __grid_constant__
     }
     if (a.ctr->n_cand > a.cand_cap) return;                   // the entry buffer was too small: nothing is touched, the host repeats the piece
     uint32_t n_emit = 0, n_fail = 0;
-    ulonglong2 *ent = reinterpret_cast<ulonglong2 *>(a.cand);
+    uint4 *ent = reinterpret_cast<uint4 *>(a.cand);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_ent; i += stride) {
-        const ulonglong2 e = ent[i];
-        if (e.y == ~0ull) continue;                           // blank
-        const bool marked = (e.y & KJ_ENT_RETRY) != 0;
+        const uint4 rec = ent[i];
+        uint32_t lanes = rec.z;
+        if (!lanes) continue;                                 // blank, or everything it held is in the table
+        const bool marked = (rec.y & KJ_ENT_RETRY32) != 0;
         if (a.resolve_retry && !marked) continue;
-        const uint64_t tile = e.y & 0xFFFFFFFull;
-        const uint32_t nlq = (uint32_t)(e.y >> 28) & 0x1FFFu, colf = (uint32_t)(e.y >> 41) & 0xFFFu;
-        const uint32_t strand = (e.y & KJ_ENT_STRAND) ? 1u : 0u;
-        const uint64_t line = base_lines + a.tile_excl[tile] + nlq;
-        if ((line & 3ull) != 1ull) continue;                  // lib/kmers.js:151  i === 1
-        uint64_t ord = 0;
-        if (a.order || a.k == 1) {
-            uint64_t col = colf;
-            if (e.y & KJ_ENT_NOCOL) {                         // the line starts before the tile: search backwards from the tile
-                const uint64_t j = tile * KJ_WT_BYTES + colf - 32u;
-                col = a.voff + j - kj_line_start_global(a, tile * KJ_WT_BYTES);
+        const uint64_t word = ((uint64_t)(rec.y & ~KJ_ENT_RETRY32) << 32) | rec.x;
+        const uint64_t chunk = word & ((1ull << 40) - 1ull);
+        const uint32_t nlb = (uint32_t)(word >> 40) & 0x1FFFu;
+        const uint32_t nlmask = rec.w & 0xFFFFu, dist = rec.w >> 16;
+        const uint64_t tile = chunk / KJ_WT_CHUNKS;
+        const uint64_t line0 = base_lines + a.tile_excl[tile] + nlb;
+        uint32_t failed = 0;
+        while (lanes) {
+            const uint32_t bit = __ffs(lanes) - 1;
+            lanes &= lanes - 1;
+            const uint32_t p = bit >> 1, strand = bit & 1u;
+            const uint64_t pos = chunk * 16u + p;                      // where the prefix / complement(prefix) starts
+            const uint32_t back = strand ? a.rc_shift : 0u;            // the reverse-strand window starts k - m before
+            const uint32_t below = nlmask & ((1u << p) - 1u);
+            const uint64_t line = line0 + __popc(below);
+            if ((line & 3ull) != 1ull) continue;
+            if (!(pos >= back && pos - back < a.own_n && pos - back + a.k <= a.n)) continue;
+            const uint64_t j = pos - back;
+            uint4 v0, v1, v2;
+            kj_window_load(a, j, v0, v1, v2);
+            uint64_t key = 0;
+            const int st = kj_window_key<KW>(a, j, strand, v0, v1, v2, key);   // a '\n' between window start and prefix fails here too
+            if (!st) continue;
+            uint64_t ord = 0;
+            if (a.order || a.k == 1) {
+                unsigned long long start;                              // first byte of the line (virtual offset)
+                if (below) start = a.voff + chunk * 16u + (31u - __clz(below)) + 1ull;
+                else if (dist != KJ_ENT_NODIST) start = a.voff + chunk * 16u - dist;
+                else start = kj_line_start_global(a, tile * KJ_WT_BYTES);
+                const uint64_t col = a.voff + j - start;
+                const uint64_t read_idx = line >> 2;
+                if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); continue; }
+                if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); continue; }
+                // forward emissions in ascending column, then reverse emissions in descending column
+                ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
             }
-            if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); continue; }
-            const uint64_t read_idx = line >> 2;
-            if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); continue; }
-            // forward emissions in ascending column, then reverse emissions in descending column
-            ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
+            bool ok;
+            if (st == 1) {
+                ok = kj_insert(a.tab, a.ctr, key, ord, 1);
+            } else {
+                __align__(8) uint8_t key32[32];
+                kj_window_bytes(a.buf, j, a.k, strand, key32);
+                ok = kj_insert_irr(a.irr, a.ctr, key32, a.k, ord, 1);
+            }
+            if (ok) ++n_emit;
+            else { ++n_fail; failed |= 1u << bit; }
         }
-        bool ok;
-        if (!(e.y & KJ_ENT_IRR)) {
-            ok = kj_insert(a.tab, a.ctr, e.x, ord, 1);
-        } else {
-            __align__(8) uint8_t key32[32];
-            kj_window_bytes(a.buf, e.x, a.k, strand, key32);
-            ok = kj_insert_irr(a.irr, a.ctr, key32, a.k, ord, 1);
-        }
-        if (ok) {
-            ++n_emit;
-            if (marked) ent[i].y = e.y & ~KJ_ENT_RETRY;
-        } else {
-            ++n_fail;                                          // no slot within the probe limit: retry after the host has grown the table
-            if (!marked) ent[i].y = e.y | KJ_ENT_RETRY;
+        if (failed) {
+            ent[i].z = failed;
+            if (!marked) ent[i].y = rec.y | KJ_ENT_RETRY32;
+        } else if (marked) {
+            ent[i].z = 0u;
+            ent[i].y = rec.y & ~KJ_ENT_RETRY32;
         }
     }
     for (int d = 16; d > 0; d >>= 1) {

@@ -82,6 +82,9 @@ __device__ __forceinline__ bool kj_insert(const KjTable &t, KjCounters *ctr, uin
     uint64_t slot = kj_mix64(key) & t.mask;
     for (int probe = 0; probe < KJ_MAX_PROBE; ++probe) {
         uint64_t cur = kj_ld_volatile(&t.keys[slot]);
+        // the slot's ordinal is requested with its key, not after the comparison: one round trip instead of two.  It may be
+        // stale by the time it is looked at, but ordinals only go down, so "stale <= ord" still proves "current <= ord".
+        const uint64_t seen = t.ords ? kj_ld_volatile(&t.ords[slot]) : 0ull;
         if (cur == KJ_EMPTY) {
             cur = atomicCAS((unsigned long long *)&t.keys[slot], (unsigned long long)KJ_EMPTY,
                             (unsigned long long)key);
@@ -95,7 +98,7 @@ __device__ __forceinline__ bool kj_insert(const KjTable &t, KjCounters *ctr, uin
             atomicAdd((unsigned long long *)&t.counts[slot], (unsigned long long)add);
             // the stream is read in order, so after a key's first occurrences its stored ordinal is already the
             // smaller one: a plain read filters most of the 64-bit atomics out
-            if (t.ords && kj_ld_volatile(&t.ords[slot]) > ord)
+            if (t.ords && seen > ord)
                 atomicMin((unsigned long long *)&t.ords[slot], (unsigned long long)ord);
             return true;
         }

@@ -422,33 +422,40 @@ kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_con
 
 // ----------------------------------------------------------------------------- resolve kernel
 
-// The window at buffer offset j, its chunks loaded: exact check and key.  Straight-line SIMD-in-register code.  KW = 4-byte
-// words of the window the code looks at: 8 covers every k <= 32; 4 (k <= 16, the KmerFinder default) halves the work.
-// Returns 0: not an emission (prefix bytes differ, crosses the end of the line, ...); 1: key holds the 2k-bit key;
-// 2: irregular (some byte is not A/C/G/T): the byte string is the key.
+// The window at buffer offset j: its bytes as the KW + 1 aligned 4-byte words from j & ~3 on (the buffer is 16-byte aligned),
+// requested together.  KW = 4-byte words of the window the check looks at: 8 covers every k <= 32; 4 (k <= 16, the
+// KmerFinder default) halves the work.
+__device__ __forceinline__ uint32_t kj_load_word(const uint8_t *buf, uint64_t off, uint64_t limit) {
+    if (off + 4 <= limit) return __ldg(reinterpret_cast<const uint32_t *>(buf + off));
+    uint32_t w = 0;
+    for (uint32_t i = 0; i < 4; ++i)
+        if (off + i < limit) w |= (uint32_t)buf[off + i] << (8 * i);
+    return w;
+}
 template <int KW>
-__device__ __forceinline__ int kj_window_key(const KjScanArgs &a, uint64_t j, uint32_t strand, const uint4 v0, const uint4 v1,
-                                             const uint4 v2, uint64_t &key) {
-    const uint32_t k = a.k;
-    const uint32_t o = (uint32_t)(j & 15u);
-    const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-    const uint32_t q = o >> 2, r8 = (o & 3u) * 8u;
-    uint32_t X[KW];
+__device__ __forceinline__ void kj_window_words(const KjScanArgs &a, uint64_t j, uint32_t (&w)[KW + 1]) {
+    const uint64_t base = j & ~3ull;
+    const uint32_t need = (uint32_t)(j & 3u) + a.k;          // bytes from base to the end of the window
 #pragma unroll
-    for (int i = 0; i < KW; ++i) {
-        const uint32_t lo = q == 0 ? W[i] : q == 1 ? W[i + 1] : q == 2 ? W[i + 2] : W[i + 3];
-        const uint32_t hi = q == 0 ? W[i + 1] : q == 1 ? W[i + 2] : q == 2 ? W[i + 3] : W[i + 4];
-        X[i] = kj_funnel_r(lo, hi, r8);
-    }
+    for (int i = 0; i <= KW; ++i) w[i] = (4u * i < need) ? kj_load_word(a.buf, base + 4u * i, a.n) : 0u;
+}
+// Exact check and key, straight-line SIMD-in-register code.  Returns 0: not an emission (prefix bytes differ, crosses the end
+// of the line, ...); 1: key holds the 2k-bit key; 2: irregular (some byte is not A/C/G/T): the byte string is the key.
+template <int KW>
+__device__ __forceinline__ int kj_window_key(const KjScanArgs &a, uint64_t j, uint32_t strand, const uint32_t (&w)[KW + 1],
+                                             uint64_t &key) {
+    const uint32_t k = a.k;
+    const uint32_t r8 = ((uint32_t)j & 3u) * 8u;
     uint32_t bad = 0, nl = 0, irr = 0, p_lo = 0, p_hi = 0;
 #pragma unroll
     for (int i = 0; i < KW; ++i) {
         if (4u * i < k) {
+            const uint32_t x = kj_funnel_r(w[i], w[i + 1], r8);
             const uint32_t bm = (4u * i + 4u <= k) ? 0xFFFFFFFFu : ((1u << (8u * (k - 4u * i))) - 1u);   // bytes of the window
-            bad |= (X[i] ^ a.want[strand][i]) & a.wmask[strand][i];
-            nl |= kj_nl_msb4(X[i]) & bm;
-            irr |= kj_not_acgt4(X[i]) & bm;
-            const uint32_t c8 = kj_pack4(X[i] & bm);
+            bad |= (x ^ a.want[strand][i]) & a.wmask[strand][i];
+            nl |= kj_nl_msb4(x) & bm;
+            irr |= kj_not_acgt4(x) & bm;
+            const uint32_t c8 = kj_pack4(x & bm);
             if (i < 4) p_lo |= c8 << (8 * i); else p_hi |= c8 << (8 * (i - 4));
         }
     }
@@ -464,6 +471,14 @@ __device__ __forceinline__ int kj_window_key(const KjScanArgs &a, uint64_t j, ui
     // forward key: first base most significant; reverse key: complement codes, last base first
     key = strand ? ((P ^ 0xAAAAAAAAAAAAAAAAull) & kmask) : (kj_pairrev64(P) >> (64u - 2u * k));
     return 1;
+}
+
+__device__ __forceinline__ void kj_prefetch_l2(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
 }
 
 // Entries -> table, one thread per entry (a chunk with candidate positions), the whole GPU at full occupancy.  For every
@@ -487,65 +502,85 @@ __global__ void __launch_bounds__(256) kj_resolve_kernel(const __grid_constant__
     uint32_t n_emit = 0, n_fail = 0;
     uint4 *ent = reinterpret_cast<uint4 *>(a.cand);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_ent; i += stride) {
-        const uint4 rec = ent[i];
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    uint4 rec_next = make_uint4(0, 0, 0, 0);
+    if (i < n_ent) rec_next = ent[i];
+    for (; i < n_ent; i += stride) {
+        const uint4 rec = rec_next;
+        // The entry of the next round is requested now, and at the end of this round the two places it will read (the tile's
+        // line count, the first candidate's window) are prefetched into L2: the chain entry -> line count -> window -> table
+        // slot of a round is then one DRAM latency shorter at every link but the last.
+        rec_next = make_uint4(0, 0, 0, 0);
+        if (i + stride < n_ent) rec_next = ent[i + stride];
         uint32_t lanes = rec.z;
-        if (!lanes) continue;                                 // blank, or everything it held is in the table
         const bool marked = (rec.y & KJ_ENT_RETRY32) != 0;
-        if (a.resolve_retry && !marked) continue;
-        const uint64_t word = ((uint64_t)(rec.y & ~KJ_ENT_RETRY32) << 32) | rec.x;
-        const uint64_t chunk = word & ((1ull << 40) - 1ull);
-        const uint32_t nlb = (uint32_t)(word >> 40) & 0x1FFFu;
-        const uint32_t nlmask = rec.w & 0xFFFFu, dist = rec.w >> 16;
-        const uint64_t tile = chunk / KJ_WT_CHUNKS;
-        const uint64_t line0 = base_lines + a.tile_excl[tile] + nlb;
+        if (a.resolve_retry && !marked) lanes = 0;
         uint32_t failed = 0;
-        while (lanes) {
-            const uint32_t bit = __ffs(lanes) - 1;
-            lanes &= lanes - 1;
-            const uint32_t p = bit >> 1, strand = bit & 1u;
-            const uint64_t pos = chunk * 16u + p;                      // where the prefix / complement(prefix) starts
-            const uint32_t back = strand ? a.rc_shift : 0u;            // the reverse-strand window starts k - m before
-            const uint32_t below = nlmask & ((1u << p) - 1u);
-            const uint64_t line = line0 + __popc(below);
-            if ((line & 3ull) != 1ull) continue;
-            if (!(pos >= back && pos - back < a.own_n && pos - back + a.k <= a.n)) continue;
-            const uint64_t j = pos - back;
-            uint4 v0, v1, v2;
-            kj_window_load(a, j, v0, v1, v2);
-            uint64_t key = 0;
-            const int st = kj_window_key<KW>(a, j, strand, v0, v1, v2, key);   // a '\n' between window start and prefix fails here too
-            if (!st) continue;
-            uint64_t ord = 0;
-            if (a.order || a.k == 1) {
-                unsigned long long start;                              // first byte of the line (virtual offset)
-                if (below) start = a.voff + chunk * 16u + (31u - __clz(below)) + 1ull;
-                else if (dist != KJ_ENT_NODIST) start = a.voff + chunk * 16u - dist;
-                else start = kj_line_start_global(a, tile * KJ_WT_BYTES);
-                const uint64_t col = a.voff + j - start;
-                const uint64_t read_idx = line >> 2;
-                if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); continue; }
-                if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); continue; }
-                // forward emissions in ascending column, then reverse emissions in descending column
-                ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
+        if (lanes) {                                          // else: blank, or everything it held is in the table
+            const uint64_t word = ((uint64_t)(rec.y & ~KJ_ENT_RETRY32) << 32) | rec.x;
+            const uint64_t chunk = word & ((1ull << 40) - 1ull);
+            const uint32_t nlb = (uint32_t)(word >> 40) & 0x1FFFu;
+            const uint32_t nlmask = rec.w & 0xFFFFu, dist = rec.w >> 16;
+            const uint64_t tile = chunk / KJ_WT_CHUNKS;
+            const uint64_t line0 = base_lines + a.tile_excl[tile] + nlb;
+            while (lanes) {
+                const uint32_t bit = __ffs(lanes) - 1;
+                lanes &= lanes - 1;
+                const uint32_t p = bit >> 1, strand = bit & 1u;
+                const uint64_t pos = chunk * 16u + p;                      // where the prefix / complement(prefix) starts
+                const uint32_t back = strand ? a.rc_shift : 0u;            // the reverse-strand window starts k - m before
+                if (!(pos >= back && pos - back < a.own_n && pos - back + a.k <= a.n)) continue;
+                const uint64_t j = pos - back;
+                uint32_t w[KW + 1];
+                kj_window_words<KW>(a, j, w);                              // requested before the line count is looked at
+                const uint32_t below = nlmask & ((1u << p) - 1u);
+                const uint64_t line = line0 + __popc(below);
+                if ((line & 3ull) != 1ull) continue;
+                uint64_t key = 0;
+                const int st = kj_window_key<KW>(a, j, strand, w, key);    // a '\n' between window start and prefix fails here too
+                if (!st) continue;
+                uint64_t ord = 0;
+                if (a.order || a.k == 1) {
+                    unsigned long long start;                              // first byte of the line (virtual offset)
+                    if (below) start = a.voff + chunk * 16u + (31u - __clz(below)) + 1ull;
+                    else if (dist != KJ_ENT_NODIST) start = a.voff + chunk * 16u - dist;
+                    else start = kj_line_start_global(a, tile * KJ_WT_BYTES);
+                    const uint64_t col = a.voff + j - start;
+                    const uint64_t read_idx = line >> 2;
+                    if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); continue; }
+                    if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); continue; }
+                    // forward emissions in ascending column, then reverse emissions in descending column
+                    ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
+                }
+                bool ok;
+                if (st == 1) {
+                    ok = kj_insert(a.tab, a.ctr, key, ord, 1);
+                } else {
+                    __align__(8) uint8_t key32[32];
+                    kj_window_bytes(a.buf, j, a.k, strand, key32);
+                    ok = kj_insert_irr(a.irr, a.ctr, key32, a.k, ord, 1);
+                }
+                if (ok) ++n_emit;
+                else { ++n_fail; failed |= 1u << bit; }
             }
-            bool ok;
-            if (st == 1) {
-                ok = kj_insert(a.tab, a.ctr, key, ord, 1);
-            } else {
-                __align__(8) uint8_t key32[32];
-                kj_window_bytes(a.buf, j, a.k, strand, key32);
-                ok = kj_insert_irr(a.irr, a.ctr, key32, a.k, ord, 1);
-            }
-            if (ok) ++n_emit;
-            else { ++n_fail; failed |= 1u << bit; }
         }
         if (failed) {
             ent[i].z = failed;
             if (!marked) ent[i].y = rec.y | KJ_ENT_RETRY32;
-        } else if (marked) {
+        } else if (marked && a.resolve_retry) {
             ent[i].z = 0u;
             ent[i].y = rec.y & ~KJ_ENT_RETRY32;
+        }
+        if (rec_next.z && !(a.resolve_retry && !(rec_next.y & KJ_ENT_RETRY32))) {
+            const uint64_t chunk = (((uint64_t)(rec_next.y & ~KJ_ENT_RETRY32) << 32) | rec_next.x) & ((1ull << 40) - 1ull);
+            kj_prefetch_l2(&a.tile_excl[chunk / KJ_WT_CHUNKS]);
+            const uint32_t bit = __ffs(rec_next.z) - 1;
+            const uint64_t pos = chunk * 16u + (bit >> 1);
+            const uint64_t j = (bit & 1u) ? (pos >= a.rc_shift ? pos - a.rc_shift : 0) : pos;
+            if (j < a.n) {
+                kj_prefetch_l2(a.buf + (j & ~31ull));
+                if ((j & 31u) + a.k > 32u && (j | 31ull) + 1 < a.n) kj_prefetch_l2(a.buf + (j | 31ull) + 1);
+            }
         }
     }
     for (int d = 16; d > 0; d >>= 1) {

@@ -622,7 +622,13 @@ static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only) {
         }
 #endif
     }
-    KJ_LAUNCH(pick_resolve_kernel(a), ctx->sm_count * 8, 256, 0, ctx->stream, a);
+    {
+        // exactly the blocks that are resident together: every thread then runs its software pipeline over many rounds
+        KjResolveFn rf = pick_resolve_kernel(a);
+        int occ = 0;
+        KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rf, 256, 0));
+        KJ_LAUNCH(rf, ctx->sm_count * std::max(occ, 1), 256, 0, ctx->stream, a);
+    }
     ctx->launches++;
     if (a.count_bases && !retry_only) {
         KJ_LAUNCH(kj_bases_kernel, ctx->sm_count * 8, 256, 0, ctx->stream, a);

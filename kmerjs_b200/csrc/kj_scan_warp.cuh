@@ -422,22 +422,18 @@ kj_warp_filter_kernel(const __grid_constant__ KjTensorMap tmap, const __grid_con
 
 // ----------------------------------------------------------------------------- resolve kernel
 
-// The window at buffer offset j: its bytes as the KW + 1 aligned 4-byte words from j & ~3 on (the buffer is 16-byte aligned),
-// requested together.  KW = 4-byte words of the window the check looks at: 8 covers every k <= 32; 4 (k <= 16, the
-// KmerFinder default) halves the work.
-__device__ __forceinline__ uint32_t kj_load_word(const uint8_t *buf, uint64_t off, uint64_t limit) {
-    if (off + 4 <= limit) return __ldg(reinterpret_cast<const uint32_t *>(buf + off));
-    uint32_t w = 0;
-    for (uint32_t i = 0; i < 4; ++i)
-        if (off + i < limit) w |= (uint32_t)buf[off + i] << (8 * i);
-    return w;
-}
+// The window at buffer offset j: the KW + 1 aligned 4-byte words from j & ~3 on, out of the (at most) three aligned 16-byte
+// chunks that hold buf[j, j + k) (kj_window_load).  KW = 4-byte words of the window the check looks at: 8 covers every
+// k <= 32; 4 (k <= 16, the KmerFinder default) halves the work.  The word offset is taken in two binary steps (by 2, by 1).
 template <int KW>
-__device__ __forceinline__ void kj_window_words(const KjScanArgs &a, uint64_t j, uint32_t (&w)[KW + 1]) {
-    const uint64_t base = j & ~3ull;
-    const uint32_t need = (uint32_t)(j & 3u) + a.k;          // bytes from base to the end of the window
+__device__ __forceinline__ void kj_window_words(uint64_t j, const uint4 v0, const uint4 v1, const uint4 v2, uint32_t (&w)[KW + 1]) {
+    const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+    const bool by2 = (j & 8u) != 0, by1 = (j & 4u) != 0;
+    uint32_t A[KW + 2];
 #pragma unroll
-    for (int i = 0; i <= KW; ++i) w[i] = (4u * i < need) ? kj_load_word(a.buf, base + 4u * i, a.n) : 0u;
+    for (int i = 0; i < KW + 2; ++i) A[i] = by2 ? W[i + 2 < 12 ? i + 2 : 11] : W[i];
+#pragma unroll
+    for (int i = 0; i <= KW; ++i) w[i] = by1 ? A[i + 1] : A[i];
 }
 // Exact check and key, straight-line SIMD-in-register code.  Returns 0: not an emission (prefix bytes differ, crosses the end
 // of the line, ...); 1: key holds the 2k-bit key; 2: irregular (some byte is not A/C/G/T): the byte string is the key.
@@ -481,6 +477,23 @@ __device__ __forceinline__ void kj_prefetch_l2(const void *p) {
 #endif
 }
 
+// fields of an entry
+__device__ __forceinline__ uint64_t kj_ent_chunk(const uint4 rec) { return ((uint64_t)(rec.y & 0xFFu) << 32) | rec.x; }
+// the candidate lanes of an entry whose line index is 1 mod 4 (lib/kmers.js:151, i === 1); lines0 = lines before the tile
+__device__ __forceinline__ uint32_t kj_ent_line_filter(const uint4 rec, uint64_t lines0) {
+    if (!rec.z) return 0u;
+    const uint32_t nlmask = rec.w & 0xFFFFu;
+    const uint32_t l0 = (uint32_t)lines0 + ((rec.y >> 8) & 0x1FFFu);       // mod 4 is all that matters
+    if (!nlmask) return (l0 & 3u) == 1u ? rec.z : 0u;                       // no '\n' inside the chunk: one line for all
+    uint32_t keep = 0, lanes = rec.z;
+    while (lanes) {
+        const uint32_t bit = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
+        if (((l0 + __popc(nlmask & ((1u << (bit >> 1)) - 1u))) & 3u) == 1u) keep |= 1u << bit;
+    }
+    return keep;
+}
+
 // Entries -> table, one thread per entry (a chunk with candidate positions), the whole GPU at full occupancy.  For every
 // candidate: the line index (lines before the launch + lines before the tile + '\n' before the position inside the tile) must
 // be 1 mod 4 (lib/kmers.js:151, i === 1) -- that drops every candidate of a header or quality line before anything is
@@ -491,7 +504,7 @@ __device__ __forceinline__ void kj_prefetch_l2(const void *p) {
 // host grows the table and runs the retry pass; nothing is ever dropped, whatever the input looks like.
 // Block 0 also closes the stream state of the launch (lines and last '\n' so far) for the next one.
 template <int KW>
-__global__ void __launch_bounds__(256) kj_resolve_kernel(const __grid_constant__ KjScanArgs a) {
+__global__ void __launch_bounds__(256, 4) kj_resolve_kernel(const __grid_constant__ KjScanArgs a) {
     const unsigned long long n_ent = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;
     const uint64_t base_lines = a.ctr->carry_lines[a.parity];
     if (blockIdx.x == 0 && threadIdx.x == 0 && !a.resolve_retry && a.n_tiles) {
@@ -502,27 +515,44 @@ __global__ void __launch_bounds__(256) kj_resolve_kernel(const __grid_constant__
     uint32_t n_emit = 0, n_fail = 0;
     uint4 *ent = reinterpret_cast<uint4 *>(a.cand);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    // A software pipeline over the thread's entries, one per round: the round that inserts entry r has the line count of
+    // r + 1 in registers and uses it to prefetch (L2) the window of r + 1's first candidate that sits in a sequence line -- so
+    // no window of a header or quality line is ever fetched --, requests the line count of r + 2 and the entry r + 3.  What
+    // a round waits for is then an L2 hit at every link of entry -> line count -> window -> table slot.
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    uint4 rec_next = make_uint4(0, 0, 0, 0);
-    if (i < n_ent) rec_next = ent[i];
+    const uint4 none = make_uint4(0, 0, 0, 0);
+    uint4 rec0 = i < n_ent ? ent[i] : none, rec1 = i + stride < n_ent ? ent[i + stride] : none;
+    uint4 rec2 = i + 2 * stride < n_ent ? ent[i + 2 * stride] : none;
+    if (a.resolve_retry) {
+        if (!(rec0.y & KJ_ENT_RETRY32)) rec0.z = 0;
+        if (!(rec1.y & KJ_ENT_RETRY32)) rec1.z = 0;
+        if (!(rec2.y & KJ_ENT_RETRY32)) rec2.z = 0;
+    }
+    uint64_t excl0 = rec0.z ? a.tile_excl[kj_ent_chunk(rec0) / KJ_WT_CHUNKS] : 0;
+    uint64_t excl1 = rec1.z ? a.tile_excl[kj_ent_chunk(rec1) / KJ_WT_CHUNKS] : 0;
+    rec0.z = kj_ent_line_filter(rec0, base_lines + excl0);
     for (; i < n_ent; i += stride) {
-        const uint4 rec = rec_next;
-        // The entry of the next round is requested now, and at the end of this round the two places it will read (the tile's
-        // line count, the first candidate's window) are prefetched into L2: the chain entry -> line count -> window -> table
-        // slot of a round is then one DRAM latency shorter at every link but the last.
-        rec_next = make_uint4(0, 0, 0, 0);
-        if (i + stride < n_ent) rec_next = ent[i + stride];
-        uint32_t lanes = rec.z;
-        const bool marked = (rec.y & KJ_ENT_RETRY32) != 0;
-        if (a.resolve_retry && !marked) lanes = 0;
-        uint32_t failed = 0;
-        if (lanes) {                                          // else: blank, or everything it held is in the table
-            const uint64_t word = ((uint64_t)(rec.y & ~KJ_ENT_RETRY32) << 32) | rec.x;
-            const uint64_t chunk = word & ((1ull << 40) - 1ull);
-            const uint32_t nlb = (uint32_t)(word >> 40) & 0x1FFFu;
-            const uint32_t nlmask = rec.w & 0xFFFFu, dist = rec.w >> 16;
+        uint4 rec3 = i + 3 * stride < n_ent ? ent[i + 3 * stride] : none;
+        const uint64_t excl2 = rec2.z ? a.tile_excl[kj_ent_chunk(rec2) / KJ_WT_CHUNKS] : 0;
+        rec1.z = kj_ent_line_filter(rec1, base_lines + excl1);
+        if (rec1.z) {
+            const uint32_t bit = __ffs(rec1.z) - 1;
+            const uint64_t pos = kj_ent_chunk(rec1) * 16u + (bit >> 1);
+            const uint64_t j = (bit & 1u) ? (pos >= a.rc_shift ? pos - a.rc_shift : 0) : pos;
+            if (j < a.n) {
+                kj_prefetch_l2(a.buf + (j & ~31ull));
+                if ((j & 31u) + a.k > 32u && (j | 31ull) + 1 < a.n) kj_prefetch_l2(a.buf + (j | 31ull) + 1);
+            }
+        }
+        // ---- entry r: rec0 holds the candidate lanes that passed the line filter
+        uint32_t lanes = rec0.z, failed = 0;
+        const bool marked = (rec0.y & KJ_ENT_RETRY32) != 0;
+        if (lanes) {
+            const uint64_t chunk = kj_ent_chunk(rec0);
+            const uint32_t nlb = (rec0.y >> 8) & 0x1FFFu;
+            const uint32_t nlmask = rec0.w & 0xFFFFu, dist = rec0.w >> 16;
             const uint64_t tile = chunk / KJ_WT_CHUNKS;
-            const uint64_t line0 = base_lines + a.tile_excl[tile] + nlb;
+            const uint64_t line0 = base_lines + excl0 + nlb;
             while (lanes) {
                 const uint32_t bit = __ffs(lanes) - 1;
                 lanes &= lanes - 1;
@@ -531,16 +561,17 @@ __global__ void __launch_bounds__(256) kj_resolve_kernel(const __grid_constant__
                 const uint32_t back = strand ? a.rc_shift : 0u;            // the reverse-strand window starts k - m before
                 if (!(pos >= back && pos - back < a.own_n && pos - back + a.k <= a.n)) continue;
                 const uint64_t j = pos - back;
+                uint4 v0, v1, v2;
+                kj_window_load(a, j, v0, v1, v2);
                 uint32_t w[KW + 1];
-                kj_window_words<KW>(a, j, w);                              // requested before the line count is looked at
-                const uint32_t below = nlmask & ((1u << p) - 1u);
-                const uint64_t line = line0 + __popc(below);
-                if ((line & 3ull) != 1ull) continue;
+                kj_window_words<KW>(j, v0, v1, v2, w);
                 uint64_t key = 0;
                 const int st = kj_window_key<KW>(a, j, strand, w, key);    // a '\n' between window start and prefix fails here too
                 if (!st) continue;
                 uint64_t ord = 0;
                 if (a.order || a.k == 1) {
+                    const uint32_t below = nlmask & ((1u << p) - 1u);
+                    const uint64_t line = line0 + __popc(below);
                     unsigned long long start;                              // first byte of the line (virtual offset)
                     if (below) start = a.voff + chunk * 16u + (31u - __clz(below)) + 1ull;
                     else if (dist != KJ_ENT_NODIST) start = a.voff + chunk * 16u - dist;
@@ -566,22 +597,15 @@ __global__ void __launch_bounds__(256) kj_resolve_kernel(const __grid_constant__
         }
         if (failed) {
             ent[i].z = failed;
-            if (!marked) ent[i].y = rec.y | KJ_ENT_RETRY32;
+            if (!marked) ent[i].y = rec0.y | KJ_ENT_RETRY32;
         } else if (marked && a.resolve_retry) {
             ent[i].z = 0u;
-            ent[i].y = rec.y & ~KJ_ENT_RETRY32;
+            ent[i].y = rec0.y & ~KJ_ENT_RETRY32;
         }
-        if (rec_next.z && !(a.resolve_retry && !(rec_next.y & KJ_ENT_RETRY32))) {
-            const uint64_t chunk = (((uint64_t)(rec_next.y & ~KJ_ENT_RETRY32) << 32) | rec_next.x) & ((1ull << 40) - 1ull);
-            kj_prefetch_l2(&a.tile_excl[chunk / KJ_WT_CHUNKS]);
-            const uint32_t bit = __ffs(rec_next.z) - 1;
-            const uint64_t pos = chunk * 16u + (bit >> 1);
-            const uint64_t j = (bit & 1u) ? (pos >= a.rc_shift ? pos - a.rc_shift : 0) : pos;
-            if (j < a.n) {
-                kj_prefetch_l2(a.buf + (j & ~31ull));
-                if ((j & 31u) + a.k > 32u && (j | 31ull) + 1 < a.n) kj_prefetch_l2(a.buf + (j | 31ull) + 1);
-            }
-        }
+        if (a.resolve_retry && !(rec3.y & KJ_ENT_RETRY32)) rec3.z = 0;
+        rec0 = rec1; excl0 = excl1;
+        rec1 = rec2; excl1 = excl2;
+        rec2 = rec3;
     }
     for (int d = 16; d > 0; d >>= 1) {
         n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);

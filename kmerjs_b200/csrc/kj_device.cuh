@@ -72,6 +72,10 @@ __device__ __forceinline__ uint32_t kj_ld_volatile(const uint32_t *p) {
 }
 
 // count[key] += add ; ord[key] = min(ord[key], ord).  false = probe limit hit (caller spills).
+// READ_ORD: look at the stored ordinal before the atomic min.  The stream is read in order, so after a key's first occurrences
+// its stored ordinal is already the smaller one and the plain read filters most of the 64-bit atomics out: that pays where the
+// atomics are the bound (dense emission, BASELINE config 5), and costs a round trip where they are not (filter path).
+template <bool READ_ORD = true>
 __device__ __forceinline__ bool kj_insert(const KjTable &t, KjCounters *ctr, uint64_t key,
                                           uint64_t ord, uint64_t add) {
     if (key == KJ_EMPTY) {
@@ -84,7 +88,7 @@ __device__ __forceinline__ bool kj_insert(const KjTable &t, KjCounters *ctr, uin
         uint64_t cur = kj_ld_volatile(&t.keys[slot]);
         // the slot's ordinal is requested with its key, not after the comparison: one round trip instead of two.  It may be
         // stale by the time it is looked at, but ordinals only go down, so "stale <= ord" still proves "current <= ord".
-        const uint64_t seen = t.ords ? kj_ld_volatile(&t.ords[slot]) : 0ull;
+        const uint64_t seen = (READ_ORD && t.ords) ? kj_ld_volatile(&t.ords[slot]) : ~0ull;
         if (cur == KJ_EMPTY) {
             cur = atomicCAS((unsigned long long *)&t.keys[slot], (unsigned long long)KJ_EMPTY,
                             (unsigned long long)key);

@@ -494,17 +494,89 @@ __device__ __forceinline__ uint32_t kj_ent_line_filter(const uint4 rec, uint64_t
     return keep;
 }
 
-// Entries -> table, one thread per entry (a chunk with candidate positions), the whole GPU at full occupancy.  For every
-// candidate: the line index (lines before the launch + lines before the tile + '\n' before the position inside the tile) must
-// be 1 mod 4 (lib/kmers.js:151, i === 1) -- that drops every candidate of a header or quality line before anything is
-// fetched; then the window's bytes (one or two 32-byte sectors from DRAM: the kernel lives on memory-level parallelism),
-// the exact check, the key, the first-seen ordinal = (read, strand, column), the hash-table update.
-// a.resolve_retry == 0: every entry; != 0: the entries an earlier pass marked.  A candidate that finds no slot within the
-// probe limit stays in the entry (its bit of the lane mask is kept, the others are cleared) and the entry is marked: the
-// host grows the table and runs the retry pass; nothing is ever dropped, whatever the input looks like.
+// One entry whose candidate lanes passed the line filter (rec.z; lines0 = lines before its tile): for every candidate the
+// window's bytes, the exact check, the key, the first-seen ordinal = (read, strand, column), the hash-table update.  A
+// candidate that finds no slot within the probe limit stays in the entry (its bit of the lane mask is kept, the others are
+// cleared) and the entry is marked for the retry pass.
+template <int KW>
+__device__ __forceinline__ void kj_resolve_entry(const KjScanArgs &a, const uint4 rec, uint64_t lines0, unsigned long long idx,
+                                                 uint32_t &n_emit, uint32_t &n_fail) {
+    uint32_t lanes = rec.z, failed = 0;
+    const uint64_t chunk = kj_ent_chunk(rec);
+    const uint32_t nlmask = rec.w & 0xFFFFu, dist = rec.w >> 16;
+    const uint64_t tile = chunk / KJ_WT_CHUNKS;
+    const uint64_t line0 = lines0 + ((rec.y >> 8) & 0x1FFFu);
+    while (lanes) {
+        const uint32_t bit = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
+        const uint32_t p = bit >> 1, strand = bit & 1u;
+        const uint64_t pos = chunk * 16u + p;                      // where the prefix / complement(prefix) starts
+        const uint32_t back = strand ? a.rc_shift : 0u;            // the reverse-strand window starts k - m before
+        if (!(pos >= back && pos - back < a.own_n && pos - back + a.k <= a.n)) continue;
+        const uint64_t j = pos - back;
+        uint4 v0, v1, v2;
+        kj_window_load(a, j, v0, v1, v2);
+        uint32_t w[KW + 1];
+        kj_window_words<KW>(j, v0, v1, v2, w);
+        uint64_t key = 0;
+        const int st = kj_window_key<KW>(a, j, strand, w, key);    // a '\n' between window start and prefix fails here too
+        if (!st) continue;
+        uint64_t ord = 0;
+        if (a.order || a.k == 1) {
+            const uint32_t below = nlmask & ((1u << p) - 1u);
+            const uint64_t line = line0 + __popc(below);
+            unsigned long long start;                              // first byte of the line (virtual offset)
+            if (below) start = a.voff + chunk * 16u + (31u - __clz(below)) + 1ull;
+            else if (dist != KJ_ENT_NODIST) start = a.voff + chunk * 16u - dist;
+            else start = kj_line_start_global(a, tile * KJ_WT_BYTES);
+            const uint64_t col = a.voff + j - start;
+            const uint64_t read_idx = line >> 2;
+            if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); continue; }
+            if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); continue; }
+            // forward emissions in ascending column, then reverse emissions in descending column
+            ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
+        }
+        bool ok;
+        if (st == 1) {
+            ok = kj_insert<false>(a.tab, a.ctr, key, ord, 1);
+        } else {
+            __align__(8) uint8_t key32[32];
+            kj_window_bytes(a.buf, j, a.k, strand, key32);
+            ok = kj_insert_irr(a.irr, a.ctr, key32, a.k, ord, 1);
+        }
+        if (ok) ++n_emit;
+        else { ++n_fail; failed |= 1u << bit; }
+    }
+    uint4 *ent = reinterpret_cast<uint4 *>(a.cand);
+    const bool marked = (rec.y & KJ_ENT_RETRY32) != 0;
+    if (failed) {
+        ent[idx].z = failed;
+        if (!marked) ent[idx].y = rec.y | KJ_ENT_RETRY32;
+    } else if (marked) {
+        ent[idx].z = 0u;
+        ent[idx].y = rec.y & ~KJ_ENT_RETRY32;
+    }
+}
+
+#define KJ_RS_QUEUE 64u            // ring of entries per warp: at most 31 left over + 32 new ones
+struct KjResolveSmem {
+    uint4 rec[8][KJ_RS_QUEUE];
+    uint64_t lines0[8][KJ_RS_QUEUE];
+    unsigned long long idx[8][KJ_RS_QUEUE];
+};
+
+// Entries -> table.  Every round a warp reads 32 entries (a chunk with candidate positions each), looks up the lines before
+// their tiles and keeps the candidates whose line index (lines before the launch + lines before the tile + '\n' before the
+// position inside the tile) is 1 mod 4 (lib/kmers.js:151, i === 1): that drops every candidate of a header or quality line,
+// more than half of them, before anything is fetched.  The entries that are left go to a ring in shared memory and their
+// first window is prefetched into L2; whenever the ring holds 32, every lane takes one (kj_resolve_entry): the expensive part
+// runs with full warps and finds its window in L2.
+// a.resolve_retry == 0: every entry; != 0: the entries an earlier pass marked (the host has grown the table in between);
+// nothing is ever dropped, whatever the input looks like.
 // Block 0 also closes the stream state of the launch (lines and last '\n' so far) for the next one.
 template <int KW>
 __global__ void __launch_bounds__(256, 4) kj_resolve_kernel(const __grid_constant__ KjScanArgs a) {
+    __shared__ KjResolveSmem sm;
     const unsigned long long n_ent = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;
     const uint64_t base_lines = a.ctr->carry_lines[a.parity];
     if (blockIdx.x == 0 && threadIdx.x == 0 && !a.resolve_retry && a.n_tiles) {
@@ -513,99 +585,50 @@ __global__ void __launch_bounds__(256, 4) kj_resolve_kernel(const __grid_constan
     }
     if (a.ctr->n_cand > a.cand_cap) return;                   // the entry buffer was too small: nothing is touched, the host repeats the piece
     uint32_t n_emit = 0, n_fail = 0;
-    uint4 *ent = reinterpret_cast<uint4 *>(a.cand);
+    const uint4 *ent = reinterpret_cast<const uint4 *>(a.cand);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    // A software pipeline over the thread's entries, one per round: the round that inserts entry r has the line count of
-    // r + 1 in registers and uses it to prefetch (L2) the window of r + 1's first candidate that sits in a sequence line -- so
-    // no window of a header or quality line is ever fetched --, requests the line count of r + 2 and the entry r + 3.  What
-    // a round waits for is then an L2 hit at every link of entry -> line count -> window -> table slot.
+    const unsigned long long rounds = (n_ent + stride - 1) / stride;      // the same trip count for every thread (warp collectives inside)
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const uint4 none = make_uint4(0, 0, 0, 0);
-    uint4 rec0 = i < n_ent ? ent[i] : none, rec1 = i + stride < n_ent ? ent[i + stride] : none;
-    uint4 rec2 = i + 2 * stride < n_ent ? ent[i + 2 * stride] : none;
-    if (a.resolve_retry) {
-        if (!(rec0.y & KJ_ENT_RETRY32)) rec0.z = 0;
-        if (!(rec1.y & KJ_ENT_RETRY32)) rec1.z = 0;
-        if (!(rec2.y & KJ_ENT_RETRY32)) rec2.z = 0;
-    }
-    uint64_t excl0 = rec0.z ? a.tile_excl[kj_ent_chunk(rec0) / KJ_WT_CHUNKS] : 0;
-    uint64_t excl1 = rec1.z ? a.tile_excl[kj_ent_chunk(rec1) / KJ_WT_CHUNKS] : 0;
-    rec0.z = kj_ent_line_filter(rec0, base_lines + excl0);
-    for (; i < n_ent; i += stride) {
-        uint4 rec3 = i + 3 * stride < n_ent ? ent[i + 3 * stride] : none;
-        const uint64_t excl2 = rec2.z ? a.tile_excl[kj_ent_chunk(rec2) / KJ_WT_CHUNKS] : 0;
-        rec1.z = kj_ent_line_filter(rec1, base_lines + excl1);
-        if (rec1.z) {
-            const uint32_t bit = __ffs(rec1.z) - 1;
-            const uint64_t pos = kj_ent_chunk(rec1) * 16u + (bit >> 1);
+    uint4 rec_next = i < n_ent ? ent[i] : none;
+    uint32_t q_head = 0, q_n = 0;
+    for (unsigned long long r = 0; r < rounds; ++r, i += stride) {
+        uint4 rec = rec_next;
+        rec_next = i + stride < n_ent ? ent[i + stride] : none;           // in flight while this round works
+        if (a.resolve_retry && !(rec.y & KJ_ENT_RETRY32)) rec.z = 0;
+        uint64_t lines0 = 0;
+        if (rec.z) {
+            lines0 = base_lines + a.tile_excl[kj_ent_chunk(rec) / KJ_WT_CHUNKS];
+            rec.z = kj_ent_line_filter(rec, lines0);
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, rec.z != 0u);
+        if (rec.z) {
+            const uint32_t at = (q_head + q_n + __popc(m & ((1u << lane) - 1u))) & (KJ_RS_QUEUE - 1u);
+            sm.rec[warp][at] = rec;
+            sm.lines0[warp][at] = lines0;
+            sm.idx[warp][at] = i;
+            const uint32_t bit = __ffs(rec.z) - 1;
+            const uint64_t pos = kj_ent_chunk(rec) * 16u + (bit >> 1);
             const uint64_t j = (bit & 1u) ? (pos >= a.rc_shift ? pos - a.rc_shift : 0) : pos;
             if (j < a.n) {
                 kj_prefetch_l2(a.buf + (j & ~31ull));
                 if ((j & 31u) + a.k > 32u && (j | 31ull) + 1 < a.n) kj_prefetch_l2(a.buf + (j | 31ull) + 1);
             }
         }
-        // ---- entry r: rec0 holds the candidate lanes that passed the line filter
-        uint32_t lanes = rec0.z, failed = 0;
-        const bool marked = (rec0.y & KJ_ENT_RETRY32) != 0;
-        if (lanes) {
-            const uint64_t chunk = kj_ent_chunk(rec0);
-            const uint32_t nlb = (rec0.y >> 8) & 0x1FFFu;
-            const uint32_t nlmask = rec0.w & 0xFFFFu, dist = rec0.w >> 16;
-            const uint64_t tile = chunk / KJ_WT_CHUNKS;
-            const uint64_t line0 = base_lines + excl0 + nlb;
-            while (lanes) {
-                const uint32_t bit = __ffs(lanes) - 1;
-                lanes &= lanes - 1;
-                const uint32_t p = bit >> 1, strand = bit & 1u;
-                const uint64_t pos = chunk * 16u + p;                      // where the prefix / complement(prefix) starts
-                const uint32_t back = strand ? a.rc_shift : 0u;            // the reverse-strand window starts k - m before
-                if (!(pos >= back && pos - back < a.own_n && pos - back + a.k <= a.n)) continue;
-                const uint64_t j = pos - back;
-                uint4 v0, v1, v2;
-                kj_window_load(a, j, v0, v1, v2);
-                uint32_t w[KW + 1];
-                kj_window_words<KW>(j, v0, v1, v2, w);
-                uint64_t key = 0;
-                const int st = kj_window_key<KW>(a, j, strand, w, key);    // a '\n' between window start and prefix fails here too
-                if (!st) continue;
-                uint64_t ord = 0;
-                if (a.order || a.k == 1) {
-                    const uint32_t below = nlmask & ((1u << p) - 1u);
-                    const uint64_t line = line0 + __popc(below);
-                    unsigned long long start;                              // first byte of the line (virtual offset)
-                    if (below) start = a.voff + chunk * 16u + (31u - __clz(below)) + 1ull;
-                    else if (dist != KJ_ENT_NODIST) start = a.voff + chunk * 16u - dist;
-                    else start = kj_line_start_global(a, tile * KJ_WT_BYTES);
-                    const uint64_t col = a.voff + j - start;
-                    const uint64_t read_idx = line >> 2;
-                    if (col > KJ_POS_MAX) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_LINE_TOO_LONG); continue; }
-                    if (read_idx >> 36) { atomicOr(&a.ctr->error_flags, KJ_DEV_E_READS_OVERFLOW); continue; }
-                    // forward emissions in ascending column, then reverse emissions in descending column
-                    ord = kj_ordinal(read_idx, strand, strand ? KJ_POS_MAX - col : col);
-                }
-                bool ok;
-                if (st == 1) {
-                    ok = kj_insert(a.tab, a.ctr, key, ord, 1);
-                } else {
-                    __align__(8) uint8_t key32[32];
-                    kj_window_bytes(a.buf, j, a.k, strand, key32);
-                    ok = kj_insert_irr(a.irr, a.ctr, key32, a.k, ord, 1);
-                }
-                if (ok) ++n_emit;
-                else { ++n_fail; failed |= 1u << bit; }
-            }
+        q_n += __popc(m);
+        __syncwarp();
+        if (q_n >= 32u) {
+            const uint32_t at = (q_head + lane) & (KJ_RS_QUEUE - 1u);
+            kj_resolve_entry<KW>(a, sm.rec[warp][at], sm.lines0[warp][at], sm.idx[warp][at], n_emit, n_fail);
+            q_head = (q_head + 32u) & (KJ_RS_QUEUE - 1u);
+            q_n -= 32u;
+            __syncwarp();
         }
-        if (failed) {
-            ent[i].z = failed;
-            if (!marked) ent[i].y = rec0.y | KJ_ENT_RETRY32;
-        } else if (marked && a.resolve_retry) {
-            ent[i].z = 0u;
-            ent[i].y = rec0.y & ~KJ_ENT_RETRY32;
-        }
-        if (a.resolve_retry && !(rec3.y & KJ_ENT_RETRY32)) rec3.z = 0;
-        rec0 = rec1; excl0 = excl1;
-        rec1 = rec2; excl1 = excl2;
-        rec2 = rec3;
+    }
+    if (lane < q_n) {
+        const uint32_t at = (q_head + lane) & (KJ_RS_QUEUE - 1u);
+        kj_resolve_entry<KW>(a, sm.rec[warp][at], sm.lines0[warp][at], sm.idx[warp][at], n_emit, n_fail);
     }
     for (int d = 16; d > 0; d >>= 1) {
         n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);

@@ -558,7 +558,16 @@ __device__ __forceinline__ void kj_resolve_entry(const KjScanArgs &a, const uint
     }
 }
 
-#define KJ_RS_QUEUE 64u            // ring of entries per warp: at most 31 left over + 32 new ones
+#ifndef KJ_RS_LAG
+#define KJ_RS_LAG 0u               // entries a warp keeps waiting beyond a full batch (their window prefetches get a round more)
+#endif
+#ifndef KJ_RS_MINB
+#define KJ_RS_MINB 4
+#endif
+#ifndef KJ_RS_AHEAD
+#define KJ_RS_AHEAD 1              // the lines-before-the-tile lookup of a round is requested a round ahead
+#endif
+#define KJ_RS_QUEUE 128u           // ring of entries per warp: at most 31 + KJ_RS_LAG left over + 32 new ones
 struct KjResolveSmem {
     uint4 rec[8][KJ_RS_QUEUE];
     uint64_t lines0[8][KJ_RS_QUEUE];
@@ -575,7 +584,7 @@ struct KjResolveSmem {
 // nothing is ever dropped, whatever the input looks like.
 // Block 0 also closes the stream state of the launch (lines and last '\n' so far) for the next one.
 template <int KW>
-__global__ void __launch_bounds__(256, 4) kj_resolve_kernel(const __grid_constant__ KjScanArgs a) {
+__global__ void __launch_bounds__(256, KJ_RS_MINB) kj_resolve_kernel(const __grid_constant__ KjScanArgs a) {
     __shared__ KjResolveSmem sm;
     const unsigned long long n_ent = a.ctr->n_cand < a.cand_cap ? a.ctr->n_cand : a.cand_cap;
     const uint64_t base_lines = a.ctr->carry_lines[a.parity];
@@ -591,8 +600,22 @@ __global__ void __launch_bounds__(256, 4) kj_resolve_kernel(const __grid_constan
     const unsigned long long rounds = (n_ent + stride - 1) / stride;      // the same trip count for every thread (warp collectives inside)
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const uint4 none = make_uint4(0, 0, 0, 0);
-    uint4 rec_next = i < n_ent ? ent[i] : none;
     uint32_t q_head = 0, q_n = 0;
+#if KJ_RS_AHEAD
+    // entry r + 2 and the line count of entry r + 1 are in flight while round r works
+    uint4 rec1 = i < n_ent ? ent[i] : none, rec2 = i + stride < n_ent ? ent[i + stride] : none;
+    if (a.resolve_retry && !(rec1.y & KJ_ENT_RETRY32)) rec1.z = 0;
+    uint64_t excl1 = rec1.z ? a.tile_excl[kj_ent_chunk(rec1) / KJ_WT_CHUNKS] : 0;
+    for (unsigned long long r = 0; r < rounds; ++r, i += stride) {
+        uint4 rec = rec1;
+        const uint64_t lines0 = base_lines + excl1;
+        rec1 = rec2;
+        if (a.resolve_retry && !(rec1.y & KJ_ENT_RETRY32)) rec1.z = 0;
+        excl1 = rec1.z ? a.tile_excl[kj_ent_chunk(rec1) / KJ_WT_CHUNKS] : 0;
+        rec2 = i + 2 * stride < n_ent ? ent[i + 2 * stride] : none;
+        rec.z = kj_ent_line_filter(rec, lines0);
+#else
+    uint4 rec_next = i < n_ent ? ent[i] : none;
     for (unsigned long long r = 0; r < rounds; ++r, i += stride) {
         uint4 rec = rec_next;
         rec_next = i + stride < n_ent ? ent[i + stride] : none;           // in flight while this round works
@@ -602,6 +625,7 @@ __global__ void __launch_bounds__(256, 4) kj_resolve_kernel(const __grid_constan
             lines0 = base_lines + a.tile_excl[kj_ent_chunk(rec) / KJ_WT_CHUNKS];
             rec.z = kj_ent_line_filter(rec, lines0);
         }
+#endif
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, rec.z != 0u);
         if (rec.z) {
             const uint32_t at = (q_head + q_n + __popc(m & ((1u << lane) - 1u))) & (KJ_RS_QUEUE - 1u);
@@ -618,7 +642,7 @@ __global__ void __launch_bounds__(256, 4) kj_resolve_kernel(const __grid_constan
         }
         q_n += __popc(m);
         __syncwarp();
-        if (q_n >= 32u) {
+        if (q_n >= 32u + KJ_RS_LAG) {
             const uint32_t at = (q_head + lane) & (KJ_RS_QUEUE - 1u);
             kj_resolve_entry<KW>(a, sm.rec[warp][at], sm.lines0[warp][at], sm.idx[warp][at], n_emit, n_fail);
             q_head = (q_head + 32u) & (KJ_RS_QUEUE - 1u);
@@ -626,9 +650,11 @@ __global__ void __launch_bounds__(256, 4) kj_resolve_kernel(const __grid_constan
             __syncwarp();
         }
     }
-    if (lane < q_n) {
-        const uint32_t at = (q_head + lane) & (KJ_RS_QUEUE - 1u);
-        kj_resolve_entry<KW>(a, sm.rec[warp][at], sm.lines0[warp][at], sm.idx[warp][at], n_emit, n_fail);
+    for (; q_n; q_n -= min(q_n, 32u), q_head = (q_head + 32u) & (KJ_RS_QUEUE - 1u)) {
+        if (lane < q_n) {
+            const uint32_t at = (q_head + lane) & (KJ_RS_QUEUE - 1u);
+            kj_resolve_entry<KW>(a, sm.rec[warp][at], sm.lines0[warp][at], sm.idx[warp][at], n_emit, n_fail);
+        }
     }
     for (int d = 16; d > 0; d >>= 1) {
         n_emit += __shfl_xor_sync(0xFFFFFFFFu, n_emit, d);

@@ -156,16 +156,34 @@ __global__ void __launch_bounds__(KJ_SCORE_THREADS) kj_walk_kernel(const KjWalkA
             id = a.qkmer[q];
             if (id != KJ_NONE32) { cnt = a.qcount[q]; ord = a.qord[q]; }
         }
-        uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, id != KJ_NONE32);
-        while (hitmask) {
-            const int src = __ffs(hitmask) - 1;
-            hitmask &= hitmask - 1;
-            const uint32_t kid = __shfl_sync(0xFFFFFFFFu, id, src);
+        // the 32 template lists as one sequence of (entry, position) items, 32 items per round: every lane has work whatever
+        // the list lengths are, and no round waits for a list header (they were all requested at once)
+        uint64_t lo = 0;
+        uint32_t len = 0;
+        if (id != KJ_NONE32) { lo = a.d.list_off[id]; len = (uint32_t)(a.d.list_off[id + 1] - lo); }
+        uint32_t incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((int)lane >= d) incl += o;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (MODE == KJ_WALK_ACCUM && lane == 0) my_hits += total;
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t item = base + lane;
+            uint32_t src = 0;
+#pragma unroll
+            for (uint32_t st = 16; st > 0; st >>= 1) {
+                const uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, (src + st - 1u) & 31u);
+                if (v <= item) src += st;
+            }
+            src &= 31u;                                        // lanes beyond the total read lane 0's values and do nothing
+            const uint32_t first = __shfl_sync(0xFFFFFFFFu, incl - len, src);
+            const uint64_t slo = __shfl_sync(0xFFFFFFFFu, lo, src);
             const uint64_t c = __shfl_sync(0xFFFFFFFFu, cnt, src);
             const uint64_t o = __shfl_sync(0xFFFFFFFFu, ord, src);
-            const uint64_t lo = a.d.list_off[kid], hi = a.d.list_off[kid + 1];
-            if (MODE == KJ_WALK_ACCUM && lane == 0) my_hits += hi - lo;
-            for (uint64_t i = lo + lane; i < hi; i += 32) {
+            if (item < total) {
+                const uint64_t i = slo + (item - first);
                 const uint32_t t = a.d.tmpl[i];
                 if (MODE == KJ_WALK_ACCUM) {
                     if (SMEM) {
@@ -178,7 +196,7 @@ __global__ void __launch_bounds__(KJ_SCORE_THREADS) kj_walk_kernel(const KjWalkA
                     if (a.first_ord[t] > o) atomicMin((unsigned long long *)&a.first_ord[t], (unsigned long long)o);
                 } else if (MODE == KJ_WALK_FIRST) {
                     if (a.first_ord[t] == o)
-                        atomicMin((unsigned long long *)&a.first_idx[t], (unsigned long long)(i - lo));
+                        atomicMin((unsigned long long *)&a.first_idx[t], (unsigned long long)(item - first));
                 } else {
                     unsigned long long pos = atomicAdd(&a.tcur[t], 1ull);
                     a.tq[a.toff[t] + pos] = (uint32_t)(g * 32 + src);
@@ -403,29 +421,64 @@ __global__ void __launch_bounds__(1024) kj_argmax_kernel(const uint64_t *glob, c
     }
 }
 
+// 32 matched entries [i0, i0 + 32) of a winner's list, one per lane: mark them dead and take their contribution out of
+// every template that shares them.  The lanes fetch their entry's count and list header side by side, then the 32 template
+// lists are walked as one sequence of (entry, position) items, 32 per round.  Returns (lane 0) the list entries removed.
+__device__ __forceinline__ unsigned long long kj_remove_group(const KjDbDev &d, const uint32_t *tq, uint64_t i0, uint64_t hi,
+                                                              const uint32_t *qkmer, const uint64_t *qcount, uint8_t *alive,
+                                                              uint64_t *part, uint32_t T, uint32_t lane) {
+    const uint64_t i = i0 + lane;
+    uint64_t lo = 0;
+    uint32_t len = 0;
+    unsigned long long c = 0;
+    if (i < hi) {
+        const uint32_t q = tq[i];
+        // each q occurs once in a template's list (DB lists are deduplicated): no other lane or warp looks at alive[q] now
+        if (*reinterpret_cast<volatile uint8_t *>(&alive[q])) {
+            alive[q] = 0;
+            const uint32_t kid = qkmer[q];
+            c = qcount[q];
+            lo = d.list_off[kid];
+            len = (uint32_t)(d.list_off[kid + 1] - lo);
+        }
+    }
+    uint32_t incl = len;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, s);
+        if ((int)lane >= s) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t item = base + lane;
+        uint32_t src = 0;
+#pragma unroll
+        for (uint32_t st = 16; st > 0; st >>= 1) {
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, (src + st - 1u) & 31u);
+            if (v <= item) src += st;
+        }
+        src &= 31u;
+        const uint32_t first = __shfl_sync(0xFFFFFFFFu, incl - len, src);
+        const uint64_t slo = __shfl_sync(0xFFFFFFFFu, lo, src);
+        const unsigned long long sc = __shfl_sync(0xFFFFFFFFu, c, src);
+        if (item < total) {
+            const uint32_t t = d.tmpl[slo + (item - first)];
+            atomicAdd((unsigned long long *)&part[t], ~0ull);                     // u[t] -= 1
+            atomicAdd((unsigned long long *)&part[(uint64_t)T + t], 0ull - sc);   // tau[t] -= count
+        }
+    }
+    return total;
+}
+
 // Remove the winner's k-mers from the query (kmerMap.delete, lib/kmerFinderClient.js:220-230) and
-// take their contribution out of every template that shares them.  One warp per matched entry.
+// take their contribution out of every template that shares them.  One warp per 32 matched entries.
 __global__ void kj_remove_kernel(KjDbDev d, const uint32_t *tq, uint64_t lo, uint64_t hi, const uint32_t *qkmer,
                                  const uint64_t *qcount, uint8_t *alive, uint64_t *part, uint32_t T) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long gone = 0;
-    for (uint64_t i = lo + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < hi; i += warps) {
-        const uint32_t q = tq[i];
-        const uint8_t was = alive[q];          // each q occurs once in a template's list (DB lists are deduplicated)
-        __syncwarp();
-        if (!was) continue;
-        if (lane == 0) alive[q] = 0;
-        const uint32_t kid = qkmer[q];
-        const unsigned long long c = qcount[q];
-        const uint64_t l0 = d.list_off[kid], l1 = d.list_off[kid + 1];
-        if (lane == 0) gone += l1 - l0;
-        for (uint64_t j = l0 + lane; j < l1; j += 32) {
-            const uint32_t t = d.tmpl[j];
-            atomicAdd((unsigned long long *)&part[t], ~0ull);                    // u[t] -= 1
-            atomicAdd((unsigned long long *)&part[(uint64_t)T + t], 0ull - c);    // tau[t] -= count
-        }
-    }
+    for (uint64_t i = lo + 32 * (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < hi; i += 32 * warps)
+        gone += kj_remove_group(d, tq, i, hi, qkmer, qcount, alive, part, T, lane);
     if (lane == 0 && gone) atomicAdd((unsigned long long *)&part[2 * (uint64_t)T], 0ull - gone);
 }
 
@@ -561,26 +614,12 @@ __global__ void __launch_bounds__(256) kj_wta_loop_kernel(const KjWtaLoopArgs a)
         const uint32_t ctl = s_ctl;
         ++n_rec;
         if (ctl < 2u) break;
-        // removeWinnerKmers (lib/kmerFinderClient.js:220-230): one warp per matched entry of the winner, the whole grid
+        // removeWinnerKmers (lib/kmerFinderClient.js:220-230): a warp per 32 matched entries of the winner, the whole grid
         const uint32_t w = ctl - 2u;
         const uint64_t lo = a.toff[w], hi = a.toff[w + 1];
         unsigned long long gone = 0;
-        for (uint64_t i = lo + gwarp; i < hi; i += gwarps) {
-            const uint32_t q = a.tq[i];
-            const uint8_t was = *reinterpret_cast<volatile uint8_t *>(&a.alive[q]);
-            __syncwarp();
-            if (!was) continue;
-            if (lane == 0) a.alive[q] = 0;
-            const uint32_t kid = a.qkmer[q];
-            const unsigned long long c = a.qcount[q];
-            const uint64_t l0 = a.d.list_off[kid], l1 = a.d.list_off[kid + 1];
-            if (lane == 0) gone += l1 - l0;
-            for (uint64_t j = l0 + lane; j < l1; j += 32) {
-                const uint32_t t = a.d.tmpl[j];
-                atomicAdd((unsigned long long *)&a.glob[t], ~0ull);                       // u[t] -= 1
-                atomicAdd((unsigned long long *)&a.glob[(uint64_t)a.T + t], 0ull - c);    // tau[t] -= count
-            }
-        }
+        for (uint64_t i = lo + 32 * gwarp; i < hi; i += 32 * gwarps)
+            gone += kj_remove_group(a.d, a.tq, i, hi, a.qkmer, a.qcount, a.alive, a.glob, a.T, lane);
         if (lane == 0 && gone) atomicAdd((unsigned long long *)&a.glob[2 * (uint64_t)a.T], 0ull - gone);
         // grid barrier: every block's removals are in L2 before block 0 takes the next argmax
         __threadfence();
@@ -1333,7 +1372,7 @@ static int wta_launch_remove(kj_match *m, uint32_t w) {
     const uint64_t range[2] = {m->toff_h[w], m->toff_h[w + 1]};
     if (range[1] > range[0]) {
         const uint64_t n = range[1] - range[0];
-        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8));
+        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((n + 31) / 32 + 7) / 8, (uint64_t)ctx->sm_count * 8));
         KJ_LAUNCH(kj_remove_kernel, grid, 256, 0, ctx->stream, m->d, m->d_tq, range[0], range[1], m->d_qkmer,
                   m->qcount, m->alive, m->d_part, m->T);
         ctx->launches++;

@@ -10,7 +10,7 @@
 // Layout in HBM.  DB: keys[cap] u64 + vals[cap] u32 (open addressing, linear probing), list_off
 // [n_kmers+1] u64, tmpl[pairs] u32 (DB list order), ulen[T] u64.  Match: score vector
 // S = {u[T], tau[T], H} u64 (partial sums of this rank) and G (global sums; G == S on one GPU),
-// first-encounter keys first_ord[T], first_idx[T] u64, rank[T] u32, the per-template CSR of
+// first-encounter keys first_ord[T], first_idx[T] u64, the per-template CSR of
 // matched query entries toff[T+1] u64 / tq[hits] u32, qkmer[Q] u32 (DB k-mer id per query entry).
 #include <algorithm>
 #include <cmath>
@@ -52,7 +52,6 @@ struct kj_match {
     uint64_t *d_part = nullptr;      // {u[T], tau[T], H}: this rank's sums
     uint64_t *d_glob = nullptr;      // global sums (== d_part unless the host layer reduces over ranks)
     uint64_t *d_first_ord = nullptr, *d_first_idx = nullptr;
-    uint32_t *d_rank = nullptr;
     uint64_t *d_toff = nullptr;
     unsigned long long *d_tcur = nullptr;
     uint32_t *d_tq = nullptr;
@@ -372,40 +371,63 @@ __global__ void kj_stats_kernel(uint64_t n, const uint64_t *r1, const uint64_t *
     }
 }
 
-// winner = argmax over (uScore desc, first-encounter rank asc)  (lib/kmerFinderClient.js:100-109,181;
-// the stable-sort tie rule of SURVEY.md 7.5).  One block.
-__global__ void __launch_bounds__(1024) kj_argmax_kernel(const uint64_t *glob, const uint32_t *rank, uint32_t T,
-                                                         const uint64_t *ulen, double unique_lens,
-                                                         double n_templates, KjWtaResult *res) {
-    __shared__ unsigned long long s_best[32];
-    __shared__ uint32_t s_who[32];
-    // key = u << 32 | ~rank  (u < 2^32: a template has fewer than 2^32 k-mers in one query)
-    unsigned long long best = 0;
+// winner = argmax over (uScore desc, first-encounter order asc)  (lib/kmerFinderClient.js:100-109,181; the stable-sort tie
+// rule of SURVEY.md 7.5).  First-encounter order = ascending (first ordinal, list index, id) (lib/kmerFinderServer.js:
+// 180-201: query k-mers in Map order, each list in DB order); it is only ever needed between templates that tie on the
+// score, so the block compares (score, order key) directly -- no rank of all templates against all templates is
+// computed.  Every thread returns the winner (KJ_NONE32: none).
+__device__ __forceinline__ bool kj_order_less(unsigned long long o, unsigned long long x, uint32_t t,
+                                              unsigned long long fo, unsigned long long fi, uint32_t who) {
+    return o < fo || (o == fo && (x < fi || (x == fi && t < who)));
+}
+__device__ __forceinline__ uint32_t kj_block_winner(const uint64_t *glob, const uint64_t *ford, const uint64_t *fidx, uint32_t T) {
+    __shared__ unsigned long long s_u[32], s_a[32], s_b[32];
+    __shared__ uint32_t s_w[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    unsigned long long bu = 0, fo = ~0ull, fi = ~0ull;
     uint32_t who = KJ_NONE32;
-    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
-        uint64_t u = glob[t];
-        if (!u) continue;
-        unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(~rank[t]);
-        if (key > best) { best = key; who = t; }
+    // eight scores in flight per thread (the scores sit in L2: a thread that waited for each would spend the whole round here);
+    // the order key of a template is only fetched when its score reaches the thread's best so far
+    for (uint32_t t0 = threadIdx.x; t0 < T; t0 += blockDim.x * 8u) {
+        unsigned long long u8[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+            const uint32_t t = t0 + j * blockDim.x;
+            u8[j] = t < T ? kj_ld_volatile(&glob[t]) : 0ull;
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+            const uint32_t t = t0 + j * blockDim.x;
+            if (u8[j] == 0ull || u8[j] < bu) continue;
+            const unsigned long long o = ford[t], x = fidx[t];
+            if (u8[j] > bu || kj_order_less(o, x, t, fo, fi, who)) { bu = u8[j]; fo = o; fi = x; who = t; }
+        }
     }
     for (int d = 16; d > 0; d >>= 1) {
-        unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
-        uint32_t ow = __shfl_xor_sync(0xFFFFFFFFu, who, d);
-        if (ob > best) { best = ob; who = ow; }
+        const unsigned long long u = __shfl_xor_sync(0xFFFFFFFFu, bu, d);
+        const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, fo, d), x = __shfl_xor_sync(0xFFFFFFFFu, fi, d);
+        const uint32_t w = __shfl_xor_sync(0xFFFFFFFFu, who, d);
+        if (u > bu || (u == bu && kj_order_less(o, x, w, fo, fi, who))) { bu = u; fo = o; fi = x; who = w; }
     }
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { s_best[warp] = best; s_who[warp] = who; }
+    __syncthreads();                                   // the arrays may still be read by a previous call
+    if (lane == 0) { s_u[warp] = bu; s_a[warp] = fo; s_b[warp] = fi; s_w[warp] = who; }
     __syncthreads();
-    if (warp == 0) {
-        const uint32_t nw = (blockDim.x + 31) >> 5;
-        best = lane < nw ? s_best[lane] : 0ull;
-        who = lane < nw ? s_who[lane] : KJ_NONE32;
-        for (int d = 16; d > 0; d >>= 1) {
-            unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
-            uint32_t ow = __shfl_xor_sync(0xFFFFFFFFu, who, d);
-            if (ob > best) { best = ob; who = ow; }
-        }
-        if (lane == 0) {
+    bu = s_u[0]; fo = s_a[0]; fi = s_b[0]; who = s_w[0];
+    for (uint32_t i = 1; i < nw; ++i) {
+        const unsigned long long u = s_u[i], o = s_a[i], x = s_b[i];
+        const uint32_t w = s_w[i];
+        if (u > bu || (u == bu && kj_order_less(o, x, w, fo, fi, who))) { bu = u; fo = o; fi = x; who = w; }
+    }
+    return bu ? who : KJ_NONE32;
+}
+
+// One block.
+__global__ void __launch_bounds__(1024) kj_argmax_kernel(const uint64_t *glob, const uint64_t *ford, const uint64_t *fidx, uint32_t T,
+                                                         const uint64_t *ulen, double unique_lens,
+                                                         double n_templates, KjWtaResult *res) {
+    const uint32_t who = kj_block_winner(glob, ford, fidx, T);
+    {
+        if (threadIdx.x == 0) {
             KjWtaResult r;
             r.winner = who; r.pad = 0;
             r.hits = glob[2 * (uint64_t)T];
@@ -482,40 +504,6 @@ __global__ void kj_remove_kernel(KjDbDev d, const uint32_t *tq, uint64_t lo, uin
     if (lane == 0 && gone) atomicAdd((unsigned long long *)&part[2 * (uint64_t)T], 0ull - gone);
 }
 
-// First-encounter rank of every matched template: its position in ascending (first ordinal, list index, id) order
-// (lib/kmerFinderServer.js:180-201: query k-mers in Map order, each list in DB order).  Every thread counts the keys below
-// its own in one slice of the templates (grid.y slices, keys staged through shared memory) and adds the count to rank[t],
-// which starts at zero; unmatched templates (first ordinal still all ones) get KJ_NONE32 - 1.  T^2 compares: 10^4
-// templates take some ten microseconds.
-#define KJ_RANK_THREADS 128
-#define KJ_RANK_TILE 256
-__global__ void __launch_bounds__(KJ_RANK_THREADS) kj_rank_kernel(const uint64_t *u, const uint64_t *ford, const uint64_t *fidx,
-                                                                   uint32_t T, uint32_t *rank) {
-    __shared__ uint64_t s_o[KJ_RANK_TILE], s_i[KJ_RANK_TILE];
-    const uint32_t t = blockIdx.x * KJ_RANK_THREADS + threadIdx.x;
-    const bool live = t < T && u[t] != 0;
-    const uint64_t fo = t < T ? ford[t] : 0, fi = t < T ? fidx[t] : 0;
-    const uint32_t slice = (T + gridDim.y - 1) / gridDim.y;
-    const uint32_t q0 = blockIdx.y * slice, q1 = min(T, q0 + slice);
-    uint32_t below = 0;
-    for (uint32_t base = q0; base < q1; base += KJ_RANK_TILE) {
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < KJ_RANK_TILE; i += KJ_RANK_THREADS) {
-            const uint32_t q = base + i;
-            s_o[i] = q < q1 ? ford[q] : ~0ull;            // unmatched templates keep all ones: never below anything matched
-            s_i[i] = q < q1 ? fidx[q] : ~0ull;
-        }
-        __syncthreads();
-        const uint32_t n = min((uint32_t)KJ_RANK_TILE, q1 - base);
-        for (uint32_t i = 0; i < n; ++i) {
-            const uint64_t qo = s_o[i], qi = s_i[i];
-            below += (qo < fo) || (qo == fo && (qi < fi || (qi == fi && base + i < t)));
-        }
-    }
-    if (live) { if (below) atomicAdd(&rank[t], below); }
-    else if (t < T && blockIdx.y == 0) rank[t] = KJ_NONE32 - 1;
-}
-
 // The whole findMatches loop (lib/kmerFinderClient.js:273-286) on the device.  Block 0 takes the argmax and the gate of a
 // round and appends {winner, u, tau, H, z, p, u0, tau0} to `res`; every block then removes its share of the winner's
 // k-mers; a grid barrier closes the round.  The host waits once and finishes the rows in exact decimal arithmetic.  The
@@ -527,7 +515,7 @@ struct KjWtaLoopArgs {
     KjDbDev d;
     uint64_t *glob;               // u[T], tau[T], H  (== part on one GPU / in a gathered match)
     const uint64_t *glob0;        // u[T], tau[T] of the first match
-    const uint32_t *rank;
+    const uint64_t *ford, *fidx;  // first-encounter keys (ties of the score)
     const uint64_t *ulen;
     const uint64_t *toff;
     const uint32_t *tq, *qkmer;
@@ -556,32 +544,14 @@ __device__ __forceinline__ bool kj_gate_decisive(double z, double p) {
 }
 
 __global__ void __launch_bounds__(256) kj_wta_loop_kernel(const KjWtaLoopArgs a) {
-    __shared__ unsigned long long s_best[8];
-    __shared__ uint32_t s_who[8];
     __shared__ uint32_t s_ctl;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const uint64_t gwarp = (uint64_t)blockIdx.x * nw + warp, gwarps = (uint64_t)gridDim.x * nw;
     uint32_t n_rec = 0, status = KJ_LOOP_MORE, done_rounds = 0;
     for (uint32_t round = 0; round < a.max_rounds; ++round) {
         if (blockIdx.x == 0) {
-            // winner = argmax over (uScore desc, first-encounter rank asc)
-            unsigned long long best = 0;
-            uint32_t who = KJ_NONE32;
-            for (uint32_t t = threadIdx.x; t < a.T; t += blockDim.x) {
-                const uint64_t u = kj_ld_volatile(&a.glob[t]);
-                if (!u) continue;
-                const unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(~a.rank[t]);
-                if (key > best) { best = key; who = t; }
-            }
-            for (int d = 16; d > 0; d >>= 1) {
-                const unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
-                const uint32_t ow = __shfl_xor_sync(0xFFFFFFFFu, who, d);
-                if (ob > best) { best = ob; who = ow; }
-            }
-            if (lane == 0) { s_best[warp] = best; s_who[warp] = who; }
-            __syncthreads();
+            const uint32_t who = kj_block_winner(a.glob, a.ford, a.fidx, a.T);
             if (threadIdx.x == 0) {
-                for (uint32_t i = 1; i < nw; ++i) if (s_best[i] > best) { best = s_best[i]; who = s_who[i]; }
                 KjWtaResult r;
                 r.winner = who; r.pad = 0;
                 r.hits = kj_ld_volatile(&a.glob[2 * (uint64_t)a.T]);
@@ -788,7 +758,7 @@ extern "C" void kj_match_free(kj_match *m) {
         kj_dfree(ctx, m->own_alive); kj_dfree(ctx, m->own_tmpl);
         if (m->d_glob != m->d_part) kj_dfree(ctx, m->d_glob);
         kj_dfree(ctx, m->d_part);
-        kj_dfree(ctx, m->d_first_ord); kj_dfree(ctx, m->d_first_idx); kj_dfree(ctx, m->d_rank);
+        kj_dfree(ctx, m->d_first_ord); kj_dfree(ctx, m->d_first_idx);
         kj_dfree(ctx, m->d_toff); kj_dfree(ctx, m->d_tcur); kj_dfree(ctx, m->d_tq); kj_dfree(ctx, m->d_res);
         kj_dfree(ctx, m->d_loop); kj_dfree(ctx, m->d_glob0); kj_dfree(ctx, m->d_sync);
         kj_pinned_put(ctx, m->h_res);
@@ -857,7 +827,6 @@ extern "C" int kj_first_match_local(kj_ctx *ctx, kj_counts *q, const kj_db *db, 
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_part, (2 * T + 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_ord, std::max<uint64_t>(T, 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_idx, std::max<uint64_t>(T, 1) * 8);
-    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_rank, std::max<uint64_t>(T, 1) * 4);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_toff, (T + 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_tcur, std::max<uint64_t>(T, 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_res, sizeof(KjWtaResult));
@@ -993,7 +962,6 @@ extern "C" int kj_match_from_matched(kj_ctx *ctx, const kj_db *db, uint32_t n_se
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_part, (2 * T + 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_ord, std::max<uint64_t>(T, 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_idx, std::max<uint64_t>(T, 1) * 8);
-    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_rank, std::max<uint64_t>(T, 1) * 4);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_toff, (T + 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_tcur, std::max<uint64_t>(T, 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_res, sizeof(KjWtaResult));
@@ -1096,7 +1064,6 @@ extern "C" int kj_match_from_segments(kj_ctx *ctx, const kj_db *db, uint32_t n_s
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_part, (2 * T + 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_ord, std::max<uint64_t>(T, 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_first_idx, std::max<uint64_t>(T, 1) * 8);
-    if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_rank, std::max<uint64_t>(T, 1) * 4);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_toff, (T + 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_tcur, std::max<uint64_t>(T, 1) * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_res, sizeof(KjWtaResult));
@@ -1247,14 +1214,10 @@ extern "C" int kj_match_commit(kj_match *m) {
     KJ_CUDA(ctx, cudaMemcpyAsync(&h[1], m->d_part + 2 * T, 8, cudaMemcpyDeviceToHost, ctx->stream));
     h[2] = h[3] = h[4] = h[5] = 0;
     if (m->from_segments) KJ_CUDA(ctx, cudaMemcpyAsync(&h[2], m->d_msize, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    // meanwhile: the first-round scores aside, the first-encounter ranks, the offsets of the per-template lists
+    // meanwhile: the first-round scores aside, the offsets of the per-template lists
     KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_glob0, std::max<uint64_t>(2 * T, 1) * 8));
     if (T) {
         KJ_CUDA(ctx, cudaMemcpyAsync(m->d_glob0, m->d_glob, 2 * T * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        KJ_CUDA(ctx, cudaMemsetAsync(m->d_rank, 0, T * 4, ctx->stream));
-        KJ_LAUNCH(kj_rank_kernel, dim3((unsigned)((T + KJ_RANK_THREADS - 1) / KJ_RANK_THREADS), (unsigned)std::min<uint64_t>(16, (T + 1023) / 1024)),
-                  KJ_RANK_THREADS, 0, ctx->stream, m->d_glob, m->d_first_ord, m->d_first_idx, (uint32_t)T, m->d_rank);
-        ctx->launches++;
         KJ_CUDA(ctx, cudaMemsetAsync(m->d_tcur, 0, T * 8, ctx->stream));
     }
     KJ_LAUNCH(kj_toff_first_kernel, 1, 1, 0, ctx->stream, m->d_toff);
@@ -1397,7 +1360,7 @@ extern "C" int kj_wta_next(kj_match *m, kj_row *out) {
         return 0;
     }
     auto launch_argmax = [&]() -> int {
-        KJ_LAUNCH(kj_argmax_kernel, 1, 1024, 0, ctx->stream, m->d_glob, m->d_rank, m->T, m->db->d_ulen,
+        KJ_LAUNCH(kj_argmax_kernel, 1, 1024, 0, ctx->stream, m->d_glob, m->d_first_ord, m->d_first_idx, m->T, m->db->d_ulen,
                   (double)m->db->s_unique_lens, (double)m->db->s_templates, m->d_res);
         ctx->launches++;
         KJ_CUDA(ctx, cudaMemcpyAsync(m->h_res, m->d_res, sizeof(KjWtaResult), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1539,7 +1502,7 @@ static int wta_all_device(kj_match *m, kj_row *rows, uint32_t cap, uint32_t *n_r
         if (m->hit_counter >= m->max_hits) { m->ended = true; break; }
         const uint32_t rounds = std::min<uint32_t>(per_launch, m->max_hits - m->hit_counter);
         KjWtaLoopArgs a{};
-        a.d = m->d; a.glob = m->d_glob; a.glob0 = m->d_glob0; a.rank = m->d_rank; a.ulen = m->db->d_ulen; a.toff = m->d_toff;
+        a.d = m->d; a.glob = m->d_glob; a.glob0 = m->d_glob0; a.ford = m->d_first_ord; a.fidx = m->d_first_idx; a.ulen = m->db->d_ulen; a.toff = m->d_toff;
         a.sync = m->d_sync;
         a.tq = m->d_tq; a.qkmer = m->d_qkmer; a.qcount = m->qcount; a.alive = m->alive;
         a.T = m->T; a.max_rounds = rounds;

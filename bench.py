@@ -294,7 +294,13 @@ def run_b200(args):
         raise SystemExit("bench.py needs a B200: kmerjs_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    stdout_fd = None
     if world > 1:
+        # NCCL prints its version banner on the process's stdout when the first communicator comes up: the one JSON line is
+        # the only thing this program may write there, so file descriptor 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
     ctx = Context(local_rank, stream=stream.cuda_stream)
@@ -578,6 +584,10 @@ def run_b200(args):
         c.free()
         line["parity_checked"] = {"reads": n_cpu, "keys": len(g_items), "occurrences": int(sum(v for _, v in g_items)),
                                   "rows": len(g_rows), "against": "oracle/ (bit-exact map and Map order, rows exact, probability 1e-9)"}
+    if stdout_fd is not None:
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        os.close(stdout_fd)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

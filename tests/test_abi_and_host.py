@@ -177,3 +177,22 @@ def test_owner_function_matches_its_restatement():
             assert 0 <= got < parts
         seen.add(L.kj_owner(kmer, len(kmer), 8))
     assert seen == set(range(8))                       # both kinds of k-mer spread over the parts
+
+
+def test_wire_host_side_shapes():
+    """The parts of the findFirstMatch exchange that need no device (lib/kmerFinderClient.js:132-161)."""
+    import json
+    from kmerjs_b200 import wire
+    from kmerjs_b200.matching import NoHitsError
+    body = wire.first_match_request({"ATGACAAAAAAAAAAA": 3, "ATGACCCCCCCCCCCC": 1}, "Kmers", "genomes")
+    doc = json.loads(body)
+    assert list(doc) == ["ATGACAAAAAAAAAAA", "ATGACCCCCCCCCCCC", "db", "collection"]
+    assert wire._query_of(body) == {"ATGACAAAAAAAAAAA": 3, "ATGACCCCCCCCCCCC": 1}
+    with pytest.raises(NoHitsError, match="No hits were found!"):
+        wire.parse_first_match_reply(204, b"")
+    with pytest.raises(RuntimeError):
+        wire.parse_first_match_reply(500, b"")
+    reply = json.dumps({"templates": {"T1": {"tScore": 4, "uScore": 2, "kmers": ["a", "b", "a"]}}, "hits": 2, "summary": {}})
+    w = wire.parse_first_match_reply(200, reply.encode())
+    assert list(w["templates"]["T1"]["kmers"]) == ["a", "b"] and w["hits"] == 2
+    assert wire.post_kmers(b"", None)[0] == 400

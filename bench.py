@@ -535,7 +535,7 @@ def run_b200(args):
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_per_input_byte"] * (scan_bytes / max(scan_n, 1))
     kname = ("kj_scan_dense_kernel (extraction + count)" if not PREFIX else
-             "kj_warp_filter_kernel<5,0> + tile scan + kj_resolve_kernel<4> (extraction + count)")
+             "kj_warp_filter_kernel<5> + cub tile scan + kj_resolve_kernel<4> (extraction + count)")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": kname,
                 "kernel_ms": scan_ms, "scan_kernel_ms": scan_ms - verify_ms, "resolve_kernel_ms": verify_ms,

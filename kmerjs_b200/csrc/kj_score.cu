@@ -126,7 +126,7 @@ struct KjWalkArgs {
     uint32_t *tq;
 };
 
-enum { KJ_WALK_ACCUM = 0, KJ_WALK_FIRST = 1, KJ_WALK_FILL = 2 };
+enum { KJ_WALK_ACCUM = 0, KJ_WALK_FIRST = 1, KJ_WALK_FILL = 2, KJ_WALK_FIRST_FILL = 3 };   // 3: both in one pass
 
 // Every warp takes 32 consecutive query entries; entries that hit the DB are walked one after the
 // other by the whole warp (lanes stride over the template list: coalesced reads of tmpl[]).
@@ -193,12 +193,15 @@ __global__ void __launch_bounds__(KJ_SCORE_THREADS) kj_walk_kernel(const KjWalkA
                         atomicAdd((unsigned long long *)&a.part[a.T + t], (unsigned long long)c);
                     }
                     if (a.first_ord[t] > o) atomicMin((unsigned long long *)&a.first_ord[t], (unsigned long long)o);
-                } else if (MODE == KJ_WALK_FIRST) {
-                    if (a.first_ord[t] == o)
-                        atomicMin((unsigned long long *)&a.first_idx[t], (unsigned long long)(item - first));
                 } else {
-                    unsigned long long pos = atomicAdd(&a.tcur[t], 1ull);
-                    a.tq[a.toff[t] + pos] = (uint32_t)(g * 32 + src);
+                    if (MODE == KJ_WALK_FIRST || MODE == KJ_WALK_FIRST_FILL) {
+                        if (a.first_ord[t] == o)
+                            atomicMin((unsigned long long *)&a.first_idx[t], (unsigned long long)(item - first));
+                    }
+                    if (MODE == KJ_WALK_FILL || MODE == KJ_WALK_FIRST_FILL) {
+                        unsigned long long pos = atomicAdd(&a.tcur[t], 1ull);
+                        a.tq[a.toff[t] + pos] = (uint32_t)(g * 32 + src);
+                    }
                 }
             }
         }
@@ -1203,11 +1206,6 @@ extern "C" int kj_match_commit(kj_match *m) {
     if (m->committed) return kj_fail(ctx, KJ_E_STATE, "kj_match_commit called twice");
     const uint64_t T = m->T;
     int rc;
-    if (!m->distributed) {
-        // single GPU: first_ord is already global; compute the list indices now
-        rc = launch_walk<KJ_WALK_FIRST>(m);
-        if (rc) return rc;
-    }
     // {global hits, this rank's hits, gathered-segment info[4]} come back in one pinned block
     unsigned long long *h = reinterpret_cast<unsigned long long *>(m->h_res);
     KJ_CUDA(ctx, cudaMemcpyAsync(&h[0], m->d_glob + 2 * T, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1249,7 +1247,9 @@ extern "C" int kj_match_commit(kj_match *m) {
     kj_dfree(ctx, m->d_tq);
     m->d_tq = nullptr;
     KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_tq, std::max<uint64_t>(local_pairs, 1) * 4));
-    rc = launch_walk<KJ_WALK_FILL>(m);        // stream-ordered: whoever reads the lists comes later on the same stream
+    // stream-ordered: whoever reads the lists comes later on the same stream.  On a single GPU first_ord is already global:
+    // the list indices of the first k-mers (the tie order) are taken by the same pass
+    rc = m->distributed ? launch_walk<KJ_WALK_FILL>(m) : launch_walk<KJ_WALK_FIRST_FILL>(m);
     if (rc) return rc;
     m->committed = true;
     return KJ_OK;

@@ -10,7 +10,7 @@ import shutil
 import subprocess
 import sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 G, P = "gpurun_out", "profiles"
 
 
@@ -43,8 +43,8 @@ def launches():
         # share of the extraction kernels inside one step = the kernels a step launches
         step = [n for n in tot if not any(x in n for x in ("synth", "genome", "db_build"))]
         st = sum(tot[n] for n in step)
-        ext = sum(tot[n] for n in step if "kj_scan" in n or "kj_verify" in n)
-        f.write(f"# extraction (kj_scan* + kj_verify) share of the step kernels: {100 * ext / st:.1f}%\n")
+        ext = sum(tot[n] for n in step if any(x in n for x in ("kj_warp_filter", "kj_resolve", "kj_scan", "DeviceScan")))
+        f.write(f"# extraction (kj_warp_filter + tile scan + kj_resolve; includes the small scans of the scoring path) share of the step kernels: {100 * ext / st:.1f}%\n")
 
 
 def full():
@@ -72,10 +72,15 @@ def full():
                      f"dram_write_MB {wr / 1e6:.1f} regs {col(r, 'launch__registers_per_thread'):.0f} grid "
                      f"{col(r, 'launch__grid_size'):.0f} block {col(r, 'launch__block_size'):.0f}")
         per[name.split("(")[0]].append(rd + wr)
-    plain = json.loads(open(os.path.join(G, "plain_short.json")).read().strip().splitlines()[-1])
+    plain = None
+    for cand in ("bench.json", "bench_quick.json", "plain_short.json"):
+        q = os.path.join(G, cand)
+        if os.path.exists(q) and os.path.getsize(q):
+            plain = json.loads([l for l in open(q).read().strip().splitlines() if l.startswith("{")][-1])
+            break
     nbytes = plain["fastq_bytes_per_gpu"]
     with open(os.path.join(P, f"{tag}_ncu_full_kernels.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:kj_scan|kj_verify, python bench.py --reads "
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:kj_warp_filter|kj_resolve, python bench.py --reads "
                 f"{plain['config']['reads_per_gpu']} --steps 2 --warmup 3 ({nbytes / 1e6:.0f} MB FASTQ per launch); per launch\n")
         f.write("\n".join(lines) + "\n")
     traffic = sum(sum(v) / len(v) for v in per.values())
@@ -93,7 +98,7 @@ def bench():
                      ("bench_2gpu.json", f"{tag}_bench_n2.json")):
         p = os.path.join(G, src)
         if os.path.exists(p) and os.path.getsize(p):
-            line = open(p).read().strip().splitlines()[-1]
+            line = [l for l in open(p).read().strip().splitlines() if l.startswith("{")][-1]
             json.loads(line)
             open(os.path.join(P, dst), "w").write(line + "\n")
 

@@ -525,7 +525,10 @@ def run_b200(args):
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
     per_rank_occ = state["occ"] / world
-    alg_bytes = scan_bytes / max(scan_n, 1) + 32.0 * per_rank_occ          # F + 32 * N_occ per launch
+    # F + 32 * N_occ per launch: a step may take several launches (config 5 counts in 8 MiB pieces), the
+    # occurrences of a step are spread over them
+    launches_per_step = max(scan_n, 1) / max(args.steps, 1)
+    alg_bytes = scan_bytes / max(scan_n, 1) + 32.0 * per_rank_occ / max(launches_per_step, 1.0)
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     # DRAM bytes per launch from the committed `ncu --set full` capture of this workload (profiles/), scaled to
     # the bytes of this launch when the capture was taken at another size

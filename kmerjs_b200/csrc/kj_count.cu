@@ -1102,6 +1102,85 @@ static void drop_compact(kj_counts *c) {
     c->export_rank.clear();
 }
 
+// Large irregular sets (dense emission over reads with N: BASELINE config 5 has some 10^8 of them) are put into
+// first-seen order on the device: sort keys out, cub radix sort of (ordinal, index), one gather that also writes the
+// count / ordinal columns of the compact arrays.  The host gets the records already sorted.
+__global__ void kj_irr_sortkeys_kernel(const KjIrrRecord *rec, uint64_t n, uint64_t *ord, uint32_t *idx) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        ord[i] = rec[i].ord;
+        idx[i] = (uint32_t)i;
+    }
+}
+__global__ void kj_irr_gather_kernel(const KjIrrRecord *rec, const uint32_t *perm, uint64_t n, KjIrrRecord *sorted,
+                                     uint64_t *counts, uint64_t *ords) {
+    // a record is 56 bytes = 7 words of 8: seven threads per record keep the copies coalesced
+    const uint64_t total = n * 7;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = w / 7, part = w % 7;
+        const uint64_t src = perm ? perm[i] : i;
+        const uint64_t v = reinterpret_cast<const uint64_t *>(rec + src)[part];
+        reinterpret_cast<uint64_t *>(sorted + i)[part] = v;
+        if (part == 5) counts[i] = v;          // {key[32], len, count, ord}
+        if (part == 6) ords[i] = v;
+    }
+}
+// below this many records the host sorts them while it waits anyway (test hook: environment KJ_IRR_DEVICE_SORT_MIN)
+static uint64_t irr_device_sort_min() {
+    const char *e = getenv("KJ_IRR_DEVICE_SORT_MIN");
+    return e && *e ? strtoull(e, nullptr, 10) : 65536ull;
+}
+
+// d_irr: the n_irr compacted records in slot order.  Leaves them sorted in c->irr_host and writes the key (unused: all ones),
+// count and ordinal columns of the compact arrays from entry n_reg on.
+static int irregular_sorted_on_device(kj_counts *c, const KjIrrRecord *d_irr, uint64_t n_irr, uint64_t n_reg) {
+    kj_ctx *ctx = c->ctx;
+    c->irr_host.resize(n_irr * sizeof(KjIrrRecord));
+    if (!n_irr) return KJ_OK;
+    KjIrrRecord *d_sorted = nullptr;
+    uint64_t *d_ord = nullptr, *d_ord2 = nullptr;
+    uint32_t *d_idx = nullptr, *d_perm = nullptr;
+    void *d_tmp = nullptr;
+    const bool sort = c->order && n_irr > 1;
+    cudaError_t e = kj_dmalloc(ctx, &d_sorted, n_irr * sizeof(KjIrrRecord));
+    if (sort) {
+        if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_ord, n_irr * 8);
+        if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_ord2, n_irr * 8);
+        if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_idx, n_irr * 4);
+        if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_perm, n_irr * 4);
+        if (e == cudaSuccess) {
+            KJ_LAUNCH(kj_irr_sortkeys_kernel, grid_for(ctx, n_irr), 256, 0, ctx->stream, d_irr, n_irr, d_ord, d_idx);
+            ctx->launches++;
+#ifndef KJ_CPU_EMU
+            size_t tmp_bytes = 0;
+            e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_ord, d_ord2, d_idx, d_perm, (int)n_irr, 0, 64, ctx->stream);
+            if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_tmp, std::max<size_t>(tmp_bytes, 16));
+            if (e == cudaSuccess)
+                e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_ord, d_ord2, d_idx, d_perm, (int)n_irr, 0, 64, ctx->stream);
+            ctx->launches += 4;
+#else
+            {   // tools/cuemu: "device" memory is host memory
+                std::vector<uint32_t> p(n_irr);
+                for (uint64_t i = 0; i < n_irr; ++i) p[i] = (uint32_t)i;
+                std::stable_sort(p.begin(), p.end(), [&](uint32_t x, uint32_t y) { return d_irr[x].ord < d_irr[y].ord; });
+                memcpy(d_perm, p.data(), n_irr * 4);
+            }
+#endif
+        }
+    }
+    if (e == cudaSuccess) {
+        KJ_LAUNCH(kj_irr_gather_kernel, grid_for(ctx, n_irr * 7), 256, 0, ctx->stream, d_irr, sort ? d_perm : nullptr, n_irr,
+                  d_sorted, c->reg.counts + n_reg, c->reg.ords + n_reg);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->reg.keys + n_reg, 0xFF, n_irr * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->irr_host.data(), d_sorted, n_irr * sizeof(KjIrrRecord), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    kj_dfree(ctx, d_sorted); kj_dfree(ctx, d_ord); kj_dfree(ctx, d_ord2); kj_dfree(ctx, d_idx); kj_dfree(ctx, d_perm); kj_dfree(ctx, d_tmp);
+    if (e != cudaSuccess) return kj_fail(ctx, KJ_E_CUDA, std::string("kj_counts_finish (irregular k-mers): ") + cudaGetErrorString(e));
+    return KJ_OK;
+}
+
 extern "C" int kj_counts_finish(kj_counts *c) {
     if (!c) return KJ_E_INVALID;
     kj_ctx *ctx = c->ctx;
@@ -1111,6 +1190,7 @@ extern "C" int kj_counts_finish(kj_counts *c) {
     // records, the counters -- and the host waits once.  With a capacity hint that holds even for a piece that is still in
     // flight: the compaction is sized by the hint and queued behind the count kernels; should the device report a table
     // or buffer that was too small, the piece is settled the long way and the compaction repeated with the exact sizes.
+    bool irr_on_device = false;      // the irregular records came back sorted, their columns are written
     bool spec = c->pending && c->capacity_hint != 0;
     int rc = KJ_OK;
     for (;;) {
@@ -1148,12 +1228,18 @@ extern "C" int kj_counts_finish(kj_counts *c) {
             KJ_LAUNCH(kj_compact_irr_kernel, grid_for(ctx, c->irr_cap), 256, 0, ctx->stream, c->irr, c->irr_cap,
                       c->ctr, d_irr, cap_irr);
             ctx->launches++;
-            c->irr_host.resize(cap_irr * sizeof(KjIrrRecord));
-            cudaError_t e = cudaMemcpyAsync(c->irr_host.data(), d_irr, cap_irr * sizeof(KjIrrRecord),
-                                            cudaMemcpyDeviceToHost, ctx->stream);
-            if (e != cudaSuccess) { kj_dfree(ctx, d_irr); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
+            if (cap_irr <= irr_device_sort_min() || cap_irr >= 0x7FFFFFFFull || spec) {
+                c->irr_host.resize(cap_irr * sizeof(KjIrrRecord));
+                cudaError_t e = cudaMemcpyAsync(c->irr_host.data(), d_irr, cap_irr * sizeof(KjIrrRecord),
+                                                cudaMemcpyDeviceToHost, ctx->stream);
+                if (e != cudaSuccess) { kj_dfree(ctx, d_irr); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
+            }
         }
-        rc = pull_counters(c);           // the one wait: n_compact and the irregular records are back with it
+        rc = pull_counters(c);           // the one wait: n_compact and (a small set of) irregular records are back with it
+        if (rc == KJ_OK && cap_irr > irr_device_sort_min() && cap_irr < 0x7FFFFFFFull && !spec) {
+            rc = irregular_sorted_on_device(c, d_irr, c->h_ctr->n_irr_unique, c->h_ctr->n_unique + (c->h_ctr->special_count ? 1 : 0));
+            irr_on_device = (rc == KJ_OK);
+        }
         kj_dfree(ctx, d_irr);
         if (rc) return rc;
         if (!spec) break;
@@ -1178,7 +1264,9 @@ extern "C" int kj_counts_finish(kj_counts *c) {
         tail_counts.push_back(c->h_ctr->special_count);
         tail_ords.push_back(c->h_ctr->special_ord);
     }
-    if (n_irr) {
+    if (n_irr && irr_on_device) {
+        // sorted on the device, count / ordinal columns written there: only the special key is left for the host
+    } else if (n_irr) {
         // order of the irregular entries: by first-seen ordinal (distinct per entry), so that it does not
         // depend on the table size.  LSD radix sort of (ordinal, index), then one permutation pass: the
         // stress configs have ~10^6 of these.  Without ordinals (KJ_F_NO_ORDER) they stay in slot order.

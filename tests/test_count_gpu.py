@@ -307,6 +307,19 @@ def test_n_dense_input_is_counted_without_limit():
     assert gpu(data, b"A", 20, 1, flags=_abi.KJ_F_FORCE_GENERIC, capacity_hint=1 << 10)[0] == oracle(data, b"A", 20, 1)
 
 
+def test_irregular_kmers_sorted_on_the_device(monkeypatch):
+    """Large irregular sets are put into first-seen order by a device radix sort in kj_counts_finish (config 5 has some
+    10^8 of them); the threshold is lowered so that the small case takes that path: same map, same Map order."""
+    from util import emulated
+    rng = random.Random(78)
+    data = random_fastq(rng, 60 if emulated() else 600, min_len=150, max_len=150, alphabet=b"ACGTN", plant=None, p_n=0.0)
+    exp_dense, exp_filter = oracle(data, b"", 31, 1), oracle(data, b"A", 20, 1)
+    monkeypatch.setenv("KJ_IRR_DEVICE_SORT_MIN", "8")
+    assert gpu(data, b"", 31, 1)[0] == exp_dense
+    assert gpu(data, b"A", 20, 1)[0] == exp_filter
+    assert gpu(data, b"A", 20, 1, flags=_abi.KJ_F_FORCE_GENERIC)[0] == exp_filter
+
+
 @pytest.mark.parametrize("extra", [1, 31, 32, 33, 100])
 def test_file_tail_shorter_than_the_halo(tmp_path, ctx, extra):
     """readFile() on a file whose last bytes fall just past a staging-chunk boundary: a tail shorter than the

@@ -601,9 +601,13 @@ static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only) {
     if (timed) KJ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (!retry_only) {
         KjFilterFn fn = pick_filter_kernel(a);
-        KJ_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KJ_WT_SMEM_BYTES));
-        int occ = 0;
-        KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KJ_WT_THREADS, KJ_WT_SMEM_BYTES));
+        // attribute and occupancy of a kernel are asked once per context (the host work in front of the launch is GPU idle time)
+        int &occ = ctx->occ_cache[(const void *)fn];
+        if (occ == 0) {
+            KJ_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KJ_WT_SMEM_BYTES));
+            KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KJ_WT_THREADS, KJ_WT_SMEM_BYTES));
+            occ = std::max(occ, 1);
+        }
         const uint64_t want_ctas = ((uint64_t)a.n_tiles + KJ_WT_WARPS - 1) / KJ_WT_WARPS;
         const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want_ctas, (uint64_t)ctx->sm_count * std::max(occ, 1)));
         KJ_LAUNCH(fn, grid, KJ_WT_THREADS, KJ_WT_SMEM_BYTES, ctx->stream, pc.tmap, a);
@@ -625,9 +629,12 @@ static int launch_filter(kj_counts *c, KjPiece &pc, bool retry_only) {
     {
         // exactly the blocks that are resident together: every thread then runs its software pipeline over many rounds
         KjResolveFn rf = pick_resolve_kernel(a);
-        int occ = 0;
-        KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rf, 256, 0));
-        KJ_LAUNCH(rf, ctx->sm_count * std::max(occ, 1), 256, 0, ctx->stream, a);
+        int &occ = ctx->occ_cache[(const void *)rf];
+        if (occ == 0) {
+            KJ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rf, 256, 0));
+            occ = std::max(occ, 1);
+        }
+        KJ_LAUNCH(rf, ctx->sm_count * occ, 256, 0, ctx->stream, a);
     }
     ctx->launches++;
     if (a.count_bases && !retry_only) {

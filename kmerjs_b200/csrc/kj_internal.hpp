@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <mutex>
 #include <string>
+#include <map>
 #include <vector>
 #include "../../include/kmerjs_b200.h"
 #include "kj_device.cuh"
@@ -18,6 +19,7 @@
 #endif
 
 struct kj_ctx {
+    std::map<const void *, int> occ_cache;   // kernel -> resident CTAs per SM (asked once)
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;      // launch stream

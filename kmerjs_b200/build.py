@@ -42,6 +42,17 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
+    # one builder at a time: the ranks of a multi-GPU job may all find the library older than its sources
+    import fcntl
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    with open(os.path.join(ROOT, "build", ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return LIB                     # another process built it while this one waited
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objdir = os.path.join(ROOT, "build", "obj")
     os.makedirs(objdir, exist_ok=True)

@@ -1551,7 +1551,12 @@ extern "C" void kj_counts_free(kj_counts *c) {
     if (ctx) {
         std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         cudaSetDevice(ctx->device);
-        if (c->pending) cudaStreamSynchronize(ctx->stream);     // a kernel may still be reading the caller's buffer
+        if (c->pending) {
+            cudaStreamSynchronize(ctx->stream);                 // a kernel may still be reading the caller's buffer
+            // a piece nobody settled (the fixed-capacity exchange partitions straight from the table): its kernel times
+            // are still in the context's events
+            if (c->piece && c->piece->timed && ctx->timers_on) { account_scan_time(c, c->piece->args.own_n, true); c->piece->timed = false; }
+        }
         free_table(ctx, c->tab);
         free_irr(ctx, c->irr);
         kj_dfree(ctx, c->ovf.rec); kj_dfree(ctx, c->ovf.irr_rec);

@@ -364,7 +364,8 @@ def run_b200(args):
                 t = tick("wta_rows", t)
                 dm.free()
             else:
-                owned = kdist.count_sharded(w.fastq_ptr, w.n_bytes, w.n_bytes, fixed=False, **kw)
+                # count + owner exchange; after the first job of a kind the exchange has fixed capacities
+                owned = kdist.count_only(w.fastq_ptr, w.n_bytes, w.n_bytes, torch_stream=stream, **kw)
                 t = tick("count+exchange", t)
             uniq = getattr(owned, "global_size", None)
             if uniq is None:

@@ -185,7 +185,8 @@ def exchange_counts(local: Counts, group=None, trace=None) -> Counts:
     owned.global_size = None        # kmerMap.size over all ranks: global_size() / DistMatch fill it in
     tr.mark("x.set_totals")
     # learn the capacities of the fixed-capacity exchange from what all ranks saw (identical on every rank)
-    x_seen[1] = max(sizes_irr) // 56
+    # (irregular records are owned by hash like the rest: a peer gets about 1/world of a rank's; generous slack)
+    x_seen[1] = (max(sizes_irr) // 56 + world - 1) // world * 2 + 2048
     mx = torch.tensor(x_seen, dtype=torch.int64, device=dev)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
     owned._seen = [int(v) for v in mx.tolist()]
@@ -302,6 +303,38 @@ def count_sharded(dev_ptr: int, n_own: int, n_read: int, *, prefix=b"ATGAC", k=1
     local.free()
     tr.mark("c.free_local")
     return owned
+
+
+def count_only(dev_ptr: int, n_own: int, n_read: int, *, group=None, torch_stream=None, **kw) -> Counts:
+    """count_sharded for jobs without scoring (collective), finished: the first job of a kind goes through the two-phase
+    exchange and leaves the capacities for the fixed-capacity exchange of the next ones; whether that one fitted is agreed by
+    all ranks (one small all-reduce), and if it did not the job is redone the robust way."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    owned = count_sharded(dev_ptr, n_own, n_read, group=group, torch_stream=torch_stream, **kw)
+    key = _caps_key(owned.ctx, world, owned.prefix, owned.k, owned.step)
+    if getattr(owned, "_fixed_caps", None) is None:
+        seen = getattr(owned, "_seen", None)
+        if seen is not None and kw.get("capacity_hint"):
+            _CAPS[key] = (_round_cap(seen[0], 4096), _round_cap(seen[1], 1024), 4096, 4096)
+        return owned
+    bad = 0
+    try:
+        owned.finish()
+    except _abi.KjError as exc:
+        if exc.code != _abi.KJ_E_RANGE:
+            raise
+        bad = 1
+    flag = torch.tensor([bad], dtype=torch.int64, device=torch.device(f"cuda:{owned.ctx.device}"))
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if int(flag.item()) == 0:
+        return owned
+    _CAPS.pop(key, None)
+    getattr(owned, "_local", owned).free()
+    owned.free()
+    kw["fixed"] = False
+    return count_only(dev_ptr, n_own, n_read, group=group, torch_stream=torch_stream, **kw)
 
 
 class ExchangeRetry(RuntimeError):

@@ -77,6 +77,29 @@ def _worker(rank, world, port, q):
             if getattr(owned, "_local", None) is not None:
                 owned._local.free()
             owned.free()
+        # count-only jobs (BASELINE config 5 shape: empty prefix, k = 31, reads with N -> byte-string k-mers travel too):
+        # two-phase exchange first, then the fixed-capacity one, then one that is forced to overflow and must fall back
+        n_dense = 4000
+        wd = synth.Workload(n_reads=n_dense, genome_len=200_000, seed=9, first_read=rank * n_dense, ctx=ctx)
+        dkey = kdist._caps_key(ctx, world, b"", 31, 1)
+        for name in ("dense-two-phase", "dense-fixed", "dense-overflow"):
+            if name == "dense-overflow":
+                kdist._CAPS[dkey] = (1024, 16, 4096, 4096)
+            owned = kdist.count_only(wd.fastq_ptr, wd.n_bytes, wd.n_bytes, torch_stream=stream, prefix=b"", k=31, step=1,
+                                     final=True, base_line=rank * n_dense * 4, capacity_hint=1 << 20, ctx=ctx)
+            took_fixed = getattr(owned, "_fixed_caps", None) is not None
+            assert took_fixed == (name == "dense-fixed"), (name, took_fixed)
+            assert dkey in kdist._CAPS
+            out[name] = dict(size=kdist.global_size(owned), lines=owned.lines, occ=owned.occurrences, counts=owned.to_dict())
+            if getattr(owned, "_local", None) is not None:
+                owned._local.free()
+            owned.free()
+        if rank == 0:
+            wd2 = synth.Workload(n_reads=world * n_dense, genome_len=200_000, seed=9, first_read=0, ctx=ctx)
+            cd = Counts(b"", 31, 1, ctx=ctx)
+            cd.add_device(wd2.fastq_ptr, wd2.n_bytes, final=True).finish()
+            out["dense-single"] = dict(size=cd.size, lines=cd.lines, occ=cd.occurrences, counts=cd.to_dict())
+            cd.free()
         if rank == 0:      # single-GPU truth over the reads of all ranks
             w2 = synth.Workload(n_reads=world * n_reads, genome_len=1_000_000, seed=5, first_read=0, ctx=ctx)
             c = Counts(b"ATGAC", 16, 1, ctx=ctx)
@@ -144,6 +167,15 @@ def test_two_ranks_equal_single_gpu():
         for p in procs:                         # a rank left waiting in a collective for a peer that is gone
             if p.is_alive():
                 p.terminate()
+    dsingle = res[0]["dense-single"]
+    for name in ("dense-two-phase", "dense-fixed", "dense-overflow"):
+        merged_d = {}
+        for rank in range(world):
+            o = res[rank][name]
+            assert (o["size"], o["lines"], o["occ"]) == (dsingle["size"], dsingle["lines"], dsingle["occ"]), (name, rank)
+            assert not (set(o["counts"]) & set(merged_d))                  # every k-mer has one owner
+            merged_d.update(o["counts"])
+        assert merged_d == dsingle["counts"], name
     single = res[0]["single"]
     assert len(single["rows"]) >= 1
     merged = {}

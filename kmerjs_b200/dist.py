@@ -291,7 +291,8 @@ def count_sharded(dev_ptr: int, n_own: int, n_read: int, *, prefix=b"ATGAC", k=1
     local.add_device(dev_ptr, n_read, own_n=n_own, final=final)
     tr.mark("c.add_device")
     caps = _CAPS.get(_caps_key(local.ctx, world, prefix, k, step))
-    if fixed and capacity_hint and caps is not None and trace is None:
+    # (fixed == "always": count_only, which agrees on the outcome itself, also takes it without a capacity hint)
+    if fixed and (capacity_hint or fixed == "always") and caps is not None and trace is None:
         owned = exchange_counts_fixed(local, caps, group, torch_stream)
         owned._local = local            # its table backs nothing any more, but its buffers must outlive the queued kernels
         owned._fixed_caps = caps
@@ -312,11 +313,13 @@ def count_only(dev_ptr: int, n_own: int, n_read: int, *, group=None, torch_strea
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    if kw.get("fixed", True):
+        kw["fixed"] = "always"
     owned = count_sharded(dev_ptr, n_own, n_read, group=group, torch_stream=torch_stream, **kw)
     key = _caps_key(owned.ctx, world, owned.prefix, owned.k, owned.step)
     if getattr(owned, "_fixed_caps", None) is None:
         seen = getattr(owned, "_seen", None)
-        if seen is not None and kw.get("capacity_hint"):
+        if seen is not None:
             _CAPS[key] = (_round_cap(seen[0], 4096), _round_cap(seen[1], 1024), 4096, 4096)
         return owned
     bad = 0

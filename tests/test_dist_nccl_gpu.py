@@ -86,7 +86,7 @@ def _worker(rank, world, port, q):
             if name == "dense-overflow":
                 kdist._CAPS[dkey] = (1024, 16, 4096, 4096)
             owned = kdist.count_only(wd.fastq_ptr, wd.n_bytes, wd.n_bytes, torch_stream=stream, prefix=b"", k=31, step=1,
-                                     final=True, base_line=rank * n_dense * 4, capacity_hint=1 << 20, ctx=ctx)
+                                     final=True, base_line=rank * n_dense * 4, ctx=ctx)
             took_fixed = getattr(owned, "_fixed_caps", None) is not None
             assert took_fixed == (name == "dense-fixed"), (name, took_fixed)
             assert dkey in kdist._CAPS

@@ -3,7 +3,7 @@
 N=${1:-2}; shift
 CONFIGS=${@:-c3}
 mkdir -p gpurun_out
-if [ "$N" == "2" ]; then
+if [ "$N" == "2" ] || [ "$N" == "4" ]; then
   timeout 900 python -m pytest tests/test_dist_nccl_gpu.py -m gpu -x -q -rs > gpurun_out/pytest_nccl.log 2>&1; echo "pytest nccl rc=$?"; tail -3 gpurun_out/pytest_nccl.log
 fi
 for c in $CONFIGS; do

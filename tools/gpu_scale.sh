@@ -10,7 +10,7 @@ for c in $CONFIGS; do
   extra=""
   if [ "$c" != "c3" ]; then extra="--no-file-leg --e2e-steps 1"; fi
   steps=10; if [ "$c" == "c5" ]; then steps=3; fi
-  timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --config $c --steps $steps --warmup 3 --trace $extra > gpurun_out/bench_${c}_n$N.json 2> gpurun_out/bench_${c}_n$N.err; echo "$c N=$N rc=$?"
+  timeout ${BENCH_TIMEOUT:-420} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --config $c --steps $steps --warmup 3 --trace $extra > gpurun_out/bench_${c}_n$N.json 2> gpurun_out/bench_${c}_n$N.err; echo "$c N=$N rc=$?"
   python -c "
 import json
 for l in open('gpurun_out/bench_${c}_n$N.json'):

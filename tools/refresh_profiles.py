@@ -35,7 +35,7 @@ def launches():
     log = os.path.join(G, "ncu_launches.log")
     whole = sum(tot.values())
     with open(os.path.join(P, f"{tag}_launch_shares.txt"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 400: {cmd} (10 M reads, 3.46 GB per launch)\n")
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 120: {cmd} --no-file-leg (10 M reads, 3.46 GB per launch)\n")
         f.write(f"# {sum(cnt.values())} launches captured (includes workload generation, warm-up and the first steps); "
                 "cold-cache, serialised: compare shares\n")
         for name, t in tot.most_common():

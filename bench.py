@@ -378,6 +378,7 @@ def run_b200(args):
             kw = dict(prefix=PREFIX, k=K, step=STEP, final=True, base_line=first_read * 4, capacity_hint=hint,
                       flags=state.get("flags", 0), ctx=ctx, trace=state.get("fine_trace"))
             rows = []
+            kdist._lean_mark(None, dev)
             if scoring:
                 # count, owner exchange, matched gather; after the first job of a kind the exchanges have fixed capacities
                 owned, dm = kdist.count_and_match(w.fastq_ptr, w.n_bytes, w.n_bytes, tdb, torch_stream=stream,
@@ -389,6 +390,7 @@ def run_b200(args):
                 except NoHitsError:
                     pass
                 t = tick("wta_rows", t)
+                kdist._lean_mark("l.rows", dev)
                 dm.free()
             else:
                 # count + owner exchange; after the first job of a kind the exchange has fixed capacities
@@ -446,6 +448,8 @@ def run_b200(args):
             print("trace (ms, count+exchange phases, synchronised):", json.dumps(fine), file=sys.stderr)
         if rank == 0:
             print("trace (ms, one device-resident step):", json.dumps({k: round(v, 3) for k, v in trace.items()}), file=sys.stderr)
+        if rank == 0 and kdist._LEAN["sink"]:
+            print("trace (ms, fixed-capacity path, every phase followed by a device wait):", json.dumps(kdist._LEAN["sink"]), file=sys.stderr)
     ctx.enable_timers(True)
     ctx.reset_timers()
     l0 = ctx.launches

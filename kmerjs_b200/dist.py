@@ -232,6 +232,23 @@ def _xbuf(dev, name: str, nbytes: int):
     return t[:nbytes]
 
 
+_LEAN = {"on": bool(__import__("os").environ.get("KJ_TRACE_LEAN")), "t": None, "sink": {}}
+
+
+def _lean_mark(name: str, dev=None):
+    """Developer trace of the fixed-capacity path (environment KJ_TRACE_LEAN=1): every mark waits for the device, so the
+    numbers are phase costs, not what the overlapped step pays.  name None: start."""
+    if not _LEAN["on"]:
+        return
+    import time
+    import torch
+    torch.cuda.synchronize(dev)
+    now = time.perf_counter()
+    if name is not None and _LEAN["t"] is not None:
+        _LEAN["sink"][name] = round((now - _LEAN["t"]) * 1e3, 3)
+    _LEAN["t"] = now
+
+
 def exchange_counts_fixed(local: Counts, caps, group=None, torch_stream=None) -> Counts:
     """Local table -> the table of the k-mers this rank owns, with ONE equal-split all-to-all and no host wait before
     it: the sender scatters its table into per-owner segments of fixed capacity (record counts and its totals in the
@@ -249,15 +266,19 @@ def exchange_counts_fixed(local: Counts, caps, group=None, torch_stream=None) ->
     recv = _xbuf(dev, "recv", world * seg)
     ordered = torch.cuda.stream(torch_stream) if torch_stream is not None else contextlib.nullcontext()
     with ordered:
+        _lean_mark("l.count", dev)
         local.partition_segments(world, send.data_ptr(), cap_reg, cap_irr)
         if torch_stream is None:
             torch.cuda.synchronize(dev)
+        _lean_mark("l.partition", dev)
         dist.all_to_all_single(recv, send, group=group)
         if torch_stream is None:
             torch.cuda.synchronize(dev)
+        _lean_mark("l.all_to_all", dev)
         owned = Counts(local.prefix, local.k, local.step, flags=local.flags & ~(_abi.KJ_F_FORWARD_ONLY),
                        capacity_hint=world * cap_reg, ctx=local.ctx)
         owned.merge_segments(recv.data_ptr(), world, cap_reg, cap_irr)
+        _lean_mark("l.merge", dev)
     owned.global_size = None
     return owned
 
@@ -441,12 +462,15 @@ class DistMatch:
             if exc.code != _abi.KJ_E_RANGE:
                 raise
             ok = False                                  # this rank's exchange overflowed: tell everybody
+        _lean_mark("l.finish_owned", self.dev)
         ordered = torch.cuda.stream(self.torch_stream) if self.torch_stream is not None else contextlib.nullcontext()
         self.local = None
         with ordered:
             if ok:
                 self.local = Match(owned, db, local_only=True, part=rank, n_parts=world)
+                _lean_mark("l.first_match_local", self.dev)
                 self.local.export_segment(mine.data_ptr(), cap_e, cap_p, owned.size, 0)
+                _lean_mark("l.export_segment", self.dev)
             else:
                 mine[:32].copy_(torch.tensor([0, 0, 0, 1], dtype=torch.int64).view(torch.uint8), non_blocking=False)
             if self.torch_stream is None:
@@ -454,7 +478,9 @@ class DistMatch:
             dist.all_gather_into_tensor(allb.view(world, seg), mine, group=self.group)
             if self.torch_stream is None:
                 torch.cuda.synchronize(self.dev)
+            _lean_mark("l.all_gather", self.dev)
             self.m = Match.from_segments(owned.ctx, db, world, allb.data_ptr(), cap_e, cap_p, part=rank, n_parts=world)
+            _lean_mark("l.from_segments", self.dev)
         self._gathered = (mine, allb)                   # the template lists are used in place
         self.mode = "gather"
         try:
@@ -464,6 +490,7 @@ class DistMatch:
                 raise
             self.free()
             raise ExchangeRetry(str(exc)) from exc
+        _lean_mark("l.commit", self.dev)
         owned.global_size = self.m.query_size
         if self.m.hits == 0:
             raise NoHitsError("No hits were found!")

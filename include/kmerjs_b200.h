@@ -310,6 +310,14 @@ int kj_match_from_matched(kj_ctx *ctx, const kj_db *db, uint32_t n_segments, con
 uint64_t kj_matched_segment_bytes(uint32_t cap_entries, uint32_t cap_pairs);
 int kj_match_export_segment(kj_match *m, void *dev_segment, uint32_t cap_entries, uint32_t cap_pairs,
                             uint64_t query_size, uint64_t flags);
+/* The segment of a rank straight from a handle's hash table, WITHOUT kj_counts_finish in between (the owner side of
+ * kj_counts_merge_segments: its finish then leaves the chain count -> exchange -> gather -> winner-takes-all).  Query size
+ * and the "this rank's exchange did not fit" flag come from the handle's device counters.  Returns 1 -- not an error --
+ * when the short cut does not apply (the DB holds byte-string k-mers or the all-G 32-mer, k differs, a piece is still in
+ * flight): finish the handle and use kj_first_match_local + kj_match_export_segment.
+ * Replaces nothing in the reference (lib/kmerFinderServer.js:171-226 queries one Redis for the whole map). */
+int kj_counts_export_matched_segment(kj_counts *c, const kj_db *db, void *dev_segment, uint32_t cap_entries,
+                                     uint32_t cap_pairs);
 int kj_match_from_segments(kj_ctx *ctx, const kj_db *db, uint32_t n_segments, const void *dev_segments,
                            uint32_t cap_entries, uint32_t cap_pairs, kj_match **out);
 uint64_t kj_match_query_size(const kj_match *m);

@@ -134,6 +134,7 @@ SIGNATURES = {
     "kj_match_from_matched": (C.c_int, [vp, vp, C.c_uint32, u64p, u64p, u64p, u64p, C.c_uint64, C.POINTER(vp)]),
     "kj_matched_segment_bytes": (C.c_uint64, [C.c_uint32, C.c_uint32]),
     "kj_match_export_segment": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64]),
+    "kj_counts_export_matched_segment": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32]),
     "kj_match_from_segments": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     "kj_match_query_size": (C.c_uint64, [vp]),
     "kj_match_segment_sizes": (C.c_int, [vp, u64p, u64p]),

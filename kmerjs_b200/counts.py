@@ -159,6 +159,16 @@ class Counts:
                    self.ctx.handle)
         self.finished = False
 
+    def export_matched_segment(self, dbh, dev_ptr: int, cap_entries: int, cap_pairs: int) -> bool:
+        """The matched entries of this (unfinished) handle against the device DB `dbh` (TemplateDB.device(...)) as one
+        fixed-capacity segment, straight from the hash table (kj_counts_export_matched_segment).  False: the short cut does
+        not apply, finish() first."""
+        rc = self._L.kj_counts_export_matched_segment(self.handle, dbh.handle, C.c_void_p(dev_ptr), cap_entries, cap_pairs)
+        if rc == 1:
+            return False
+        _abi.check(rc, self.ctx.handle)
+        return True
+
     def set_totals(self, lines: int, bases: int, occurrences: int, bytes_read: int):
         _abi.check(self._L.kj_counts_set_totals(self.handle, lines, bases, occurrences, bytes_read),
                    self.ctx.handle)

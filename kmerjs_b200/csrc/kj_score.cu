@@ -1039,6 +1039,57 @@ extern "C" int kj_match_export_segment(kj_match *m, void *dev_segment, uint32_t 
     return KJ_OK;
 }
 
+// The same segment straight from a handle's hash table, without kj_counts_finish in between (the owner of a fixed-capacity
+// exchange: its finish -- compaction, counters back, a host wait -- then leaves the chain count -> exchange -> gather ->
+// winner-takes-all and only has to be done before the k-mer map itself is read).  Table slots play the query entries.
+// Only regular k-mers can hit here, so the short cut applies when the DB holds nothing else (no byte-string k-mers, no
+// all-G 32-mer) and k matches; returns 1 (not an error) when it does not and the caller finishes first.  The query size and
+// the "this rank's exchange did not fit" flag are read from the handle's device counters.
+__global__ void kj_probe_table_kernel(KjDbDev d, const uint64_t *tkeys, uint64_t cap, uint32_t *qkmer, uint8_t *alive) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = tkeys[i];
+        qkmer[i] = key == KJ_EMPTY ? KJ_NONE32 : kj_db_lookup(d, key);
+        alive[i] = 1;
+    }
+}
+__global__ void kj_matched_header_counts_kernel(KjMSegHeader *h, const KjCounters *ctr) {
+    unsigned long long n = 0;
+    for (int i = 0; i < 64; ++i) n += ctr->n_unique_part[i];
+    h->n_entries = 0; h->n_pairs = 0;
+    h->qsize = n + ctr->n_irr_unique + (ctr->special_count ? 1ull : 0ull);
+    h->flags = (ctr->error_flags || ctr->n_overflow || ctr->n_irr_overflow) ? 1ull : 0ull;
+}
+extern "C" int kj_counts_export_matched_segment(kj_counts *c, const kj_db *db, void *dev_segment, uint32_t cap_entries,
+                                                uint32_t cap_pairs) {
+    if (!c || !db || !dev_segment) return KJ_E_INVALID;
+    kj_ctx *ctx = c->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (c->k != db->k || c->k >= 32 || !db->other.empty() || db->special_id != KJ_NONE32 || c->pending) return 1;
+    KJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint8_t *seg = reinterpret_cast<uint8_t *>(dev_segment);
+    KJ_LAUNCH(kj_matched_header_counts_kernel, 1, 1, 0, ctx->stream, reinterpret_cast<KjMSegHeader *>(seg), c->ctr);
+    ctx->launches++;
+    if (c->cap) {
+        uint32_t *d_qkmer = nullptr;
+        uint8_t *d_alive = nullptr;
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &d_qkmer, c->cap * 4));
+        cudaError_t e = kj_dmalloc(ctx, &d_alive, c->cap);
+        if (e != cudaSuccess) { kj_dfree(ctx, d_qkmer); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
+        KJ_LAUNCH(kj_probe_table_kernel, kj_grid_for(ctx, c->cap), 256, 0, ctx->stream, db->dev(), c->tab.keys, c->cap, d_qkmer, d_alive);
+        const uint64_t groups = (c->cap + 31) / 32;
+        const int wpb = KJ_SCORE_THREADS / 32;
+        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((groups + wpb - 1) / wpb, (uint64_t)ctx->sm_count * 8));
+        KJ_LAUNCH((kj_matched_export_kernel<false>), grid, KJ_SCORE_THREADS, 0, ctx->stream, db->dev(), d_qkmer, c->tab.counts,
+                  c->tab.ords, d_alive, c->cap, reinterpret_cast<uint64_t *>(seg + sizeof(KjMSegHeader)), (uint64_t)cap_entries,
+                  reinterpret_cast<uint32_t *>(seg + sizeof(KjMSegHeader) + (uint64_t)cap_entries * 32u), (uint64_t)cap_pairs,
+                  reinterpret_cast<unsigned long long *>(seg));
+        ctx->launches += 2;
+        kj_dfree(ctx, d_qkmer); kj_dfree(ctx, d_alive);       // stream-ordered: after the kernels
+    }
+    KJ_CUDA(ctx, cudaGetLastError());
+    return KJ_OK;
+}
+
 // a match over the gathered segments of every rank; the buffer must stay valid until kj_match_free.  Sizes, the query
 // size and the flags are read on the device: they surface in kj_match_commit (KJ_E_RANGE when a segment overflowed or
 // a rank flagged its part).

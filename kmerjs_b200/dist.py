@@ -455,18 +455,25 @@ class DistMatch:
         seg = matched_segment_bytes(cap_e, cap_p)
         mine = _xbuf(self.dev, "mseg", seg)
         allb = _xbuf(self.dev, "mall", world * seg)
-        ok = True
-        try:
-            owned.finish()
-        except _abi.KjError as exc:
-            if exc.code != _abi.KJ_E_RANGE:
-                raise
-            ok = False                                  # this rank's exchange overflowed: tell everybody
-        _lean_mark("l.finish_owned", self.dev)
         ordered = torch.cuda.stream(self.torch_stream) if self.torch_stream is not None else contextlib.nullcontext()
         self.local = None
+        # the short way: this rank's matched entries straight from the owner's hash table -- its finish() (compaction,
+        # counters back, a host wait) is queued behind the gather and no longer sits between the two collectives
         with ordered:
-            if ok:
+            fast = owned.export_matched_segment(db.device(owned.ctx, rank, world), mine.data_ptr(), cap_e, cap_p)
+        ok = True
+        if not fast:
+            try:
+                owned.finish()
+            except _abi.KjError as exc:
+                if exc.code != _abi.KJ_E_RANGE:
+                    raise
+                ok = False                                  # this rank's exchange overflowed: tell everybody
+            _lean_mark("l.finish_owned", self.dev)
+        with ordered:
+            if fast:
+                _lean_mark("l.export_from_table", self.dev)
+            elif ok:
                 self.local = Match(owned, db, local_only=True, part=rank, n_parts=world)
                 _lean_mark("l.first_match_local", self.dev)
                 self.local.export_segment(mine.data_ptr(), cap_e, cap_p, owned.size, 0)
@@ -481,6 +488,15 @@ class DistMatch:
             _lean_mark("l.all_gather", self.dev)
             self.m = Match.from_segments(owned.ctx, db, world, allb.data_ptr(), cap_e, cap_p, part=rank, n_parts=world)
             _lean_mark("l.from_segments", self.dev)
+        finish_failed = False
+        if fast:
+            try:
+                owned.finish()                          # its wait also covers the gather and the import
+            except _abi.KjError as exc:
+                if exc.code != _abi.KJ_E_RANGE:
+                    raise
+                finish_failed = True                    # the header of this rank's segment says so too: commit fails everywhere
+            _lean_mark("l.finish_owned", self.dev)
         self._gathered = (mine, allb)                   # the template lists are used in place
         self.mode = "gather"
         try:
@@ -491,6 +507,9 @@ class DistMatch:
             self.free()
             raise ExchangeRetry(str(exc)) from exc
         _lean_mark("l.commit", self.dev)
+        if finish_failed:
+            self.free()
+            raise ExchangeRetry("the owner's exchange overflowed")
         owned.global_size = self.m.query_size
         if self.m.hits == 0:
             raise NoHitsError("No hits were found!")

@@ -236,3 +236,69 @@ def test_gathered_match_equals_single_device(world):
         m.free()
     for oc in owned:
         oc.free()
+
+
+def test_matched_segment_straight_from_the_table():
+    """kj_counts_export_matched_segment: the matched entries of a handle that has NOT been finished, read from its hash
+    table, give the same gathered match (hits, first-encounter order, scores, rows) as the finished handle and the
+    oracle; the handle can still be finished afterwards.  A DB with byte-string k-mers does not take the short cut."""
+    from kmerjs_b200.context import default_context
+    from kmerjs_b200.matching import matched_segment_bytes
+    golden_reads = read_golden("test_long.kmer.fastq")
+    exp_counts, _ = ko_c.count_fastq(golden_reads)
+    rng = random.Random(1618)
+    regular = [k for k in exp_counts.keys() if set(k) <= set(b"ACGT") and len(k) == 16]
+    lists, attrs, summary = synthetic_db(regular, rng, n_templates=20, decoys=80, share=0.7)
+    assert all(set(k) <= set(b"ACGT") and len(k) == 16 for k in lists)
+    tdb = TemplateDB.from_lists(lists, attrs, summary)
+    db = ko.TemplateDB(lists, attrs, summary)
+    q = OrderedDict(exp_counts)
+    templates, hits = ko.first_match(q, db)
+    e_rows, e_err = [], None
+    try:
+        for r in ko.find_matches(templates, summary, q, len(exp_counts)):
+            e_rows.append(r)
+    except RuntimeError as exc:
+        e_err = str(exc)
+    ctx = default_context()
+    c = Counts(b"ATGAC", 16, 1)
+    c.add_host(golden_reads, final=True)                       # counted, not finished
+    cap_e, cap_p = 1024, 16384
+    p, keep, _back = dev_u64(np.zeros(matched_segment_bytes(cap_e, cap_p) // 8 + 1, dtype=np.uint64))
+    assert c.export_matched_segment(tdb.device(ctx, 0, 1), p, cap_e, cap_p)
+    g = Match.from_segments(ctx, tdb, 1, p, cap_e, cap_p)
+    g.commit()
+    assert g.query_size == len(exp_counts)
+    assert g.hits == hits and list(g.templates().keys()) == list(templates.keys())
+    assert {n: (t["uScore"], t["tScore"]) for n, t in g.templates().items()} == \
+        {n: (t["uScore"], t["tScore"]) for n, t in templates.items()}
+    g_rows, g_err = [], None
+    try:
+        while True:
+            r = g.next_row()
+            if r is None:
+                break
+            g_rows.append(r)
+    except NoHitsError as exc:
+        g_err = str(exc)
+    assert [r["template"] for r in g_rows] == [r["template"] for r in e_rows]
+    for a, e in zip(g_rows, e_rows):
+        for f in ko.ROW_KEYS:
+            if f == "probability":
+                assert a[f] == pytest.approx(e[f], rel=1e-9)
+            else:
+                assert a[f] == e[f], f
+    assert g_err == e_err
+    g.free()
+    c.finish()
+    assert c.size == len(exp_counts)
+    # a DB that holds a byte-string k-mer (here: one with N) must be matched the long way
+    lists_n = OrderedDict(lists)
+    lists_n[b"ATGACNNNNNNNNNNN"] = [next(iter(attrs))] if isinstance(attrs, dict) else ["T0000"]
+    tdb_n = TemplateDB.from_lists(lists_n, attrs, summary)
+    c2 = Counts(b"ATGAC", 16, 1)
+    c2.add_host(golden_reads, final=True)
+    assert not c2.export_matched_segment(tdb_n.device(ctx, 0, 1), p, cap_e, cap_p)
+    c2.free()
+    c.free()
+    del keep

@@ -326,9 +326,12 @@ __global__ void kj_matched_import_segments_kernel(const uint8_t *segs, uint64_t 
         ord[e] = ent[1];
         alive[e] = 1;
         qkmer[e] = (uint32_t)(2 * e);
-        off[2 * e] = tbase + o;
-        off[2 * e + 1] = tbase + o + l;
-        if (o + l > cap_p || o + l < o) atomicOr(&info[3], 2ull);
+        // a list that does not lie inside the segment (the segment overflowed) is flagged and left empty: the walk that is
+        // queued right behind this kernel must not follow it; kj_match_commit then fails with KJ_E_RANGE
+        const bool inside = o + l <= cap_p && o + l >= o;
+        off[2 * e] = tbase + (inside ? o : 0);
+        off[2 * e + 1] = tbase + (inside ? o + l : 0);
+        if (!inside) atomicOr(&info[3], 2ull);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long ne = 0, np = 0, qs = 0, fl = 0;

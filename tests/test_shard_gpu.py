@@ -292,6 +292,20 @@ def test_matched_segment_straight_from_the_table():
     g.free()
     c.finish()
     assert c.size == len(exp_counts)
+    # a segment that is too small: nothing may follow a list outside it (the walk is queued before the sizes are known to
+    # the host), and the commit refuses the match
+    c3 = Counts(b"ATGAC", 16, 1)
+    c3.add_host(golden_reads, final=True)
+    small_e, small_p = 64, 8
+    p2, keep2, _b2 = dev_u64(np.zeros(matched_segment_bytes(small_e, small_p) // 8 + 1, dtype=np.uint64))
+    assert c3.export_matched_segment(tdb.device(ctx, 0, 1), p2, small_e, small_p)
+    g2 = Match.from_segments(ctx, tdb, 1, p2, small_e, small_p)
+    with pytest.raises(_abi.KjError) as ei:
+        g2.commit()
+    assert ei.value.code == _abi.KJ_E_RANGE
+    g2.free()
+    c3.free()
+    del keep2
     # a DB that holds a byte-string k-mer (here: one with N) must be matched the long way
     lists_n = OrderedDict(lists)
     lists_n[b"ATGACNNNNNNNNNNN"] = [next(iter(attrs))] if isinstance(attrs, dict) else ["T0000"]

@@ -1198,7 +1198,9 @@ extern "C" int kj_counts_finish(kj_counts *c) {
     // flight: the compaction is sized by the hint and queued behind the count kernels; should the device report a table
     // or buffer that was too small, the piece is settled the long way and the compaction repeated with the exact sizes.
     bool irr_on_device = false;      // the irregular records came back sorted, their columns are written
-    bool spec = c->pending && c->capacity_hint != 0;
+    // (the owner side of a fixed-capacity exchange -- a handle that kj_counts_merge_segments filled -- is the same case: its
+    // capacity hint bounds what the segments can hold)
+    bool spec = (c->pending || c->exchange_totals) && c->capacity_hint != 0;
     int rc = KJ_OK;
     for (;;) {
         uint64_t cap_tab, cap_irr;

@@ -316,3 +316,66 @@ def test_matched_segment_straight_from_the_table():
     c2.free()
     c.free()
     del keep
+
+
+@pytest.mark.parametrize("prefix,k", [(b"ATGAC", 16), (b"", 31)])
+def test_fixed_capacity_exchange_emulated(prefix, k):
+    """kj_counts_partition_segments / kj_counts_merge_segments with the ranks emulated on one device: every rank scatters
+    its (unfinished) table into one fixed-capacity segment per owner, the owners merge what they are sent and finish; the
+    union of the owners' maps is the single-device map, totals included.  Reads with N: byte-string k-mers travel too.
+    Then with segments that are too small: an owner that was sent an overflowed segment must refuse in finish (KJ_E_RANGE),
+    never return a partial map."""
+    from kmerjs_b200.counts import segment_bytes
+    rng = random.Random(99)
+    n_reads = 60 if emulated() else 2000
+    data = random_fastq(rng, n_reads, min_len=60, max_len=150, p_n=0.02)
+    world = 3
+    single = Counts(prefix, k, 1)
+    single.add_host(data, final=True)
+    single.finish()
+    exp = single.to_dict()
+    for cap_reg, cap_irr, fits in ((1 << 15, 1 << 12, True), (8, 2, False)):
+        ranges = kdist.plan_ranges(len(data), world, halo=64)
+        whole = DevBuf(data)
+        stats = [count_newlines_device(whole.ptr + lo, own) for lo, own, _ in ranges]
+        bl, bc = kdist.phase_of_ranges([s_[0] for s_ in stats], [s_[1] for s_ in stats], [r[1] for r in ranges])
+        seg = segment_bytes(cap_reg, cap_irr)
+        sent, locals_, keep = [], [], []
+        for r, (lo, own, rd) in enumerate(ranges):
+            c = Counts(prefix, k, 1, base_line=bl[r], base_col=bc[r])
+            c.add_device(whole.ptr + lo, rd, own_n=own, final=(r == world - 1))      # not finished
+            p, kp, back = dev_u64(np.zeros(world * seg // 8, dtype=np.uint64))
+            c.partition_segments(world, p, cap_reg, cap_irr)
+            c.finish()                                                               # (waits for the scatter)
+            sent.append(back().view(np.uint8).reshape(world, seg))
+            locals_.append(c)
+            keep.append(kp)
+        merged, failed = {}, 0
+        lines = occ = 0
+        for o in range(world):
+            recv = np.concatenate([sent[r][o] for r in range(world)])
+            p, kp, _ = dev_u64(recv.view(np.uint64))
+            oc = Counts(prefix, k, 1, capacity_hint=world * cap_reg)
+            oc.merge_segments(p, world, cap_reg, cap_irr)
+            try:
+                oc.finish()
+            except _abi.KjError as exc:
+                assert exc.code == _abi.KJ_E_RANGE
+                failed += 1
+                oc.free()
+                continue
+            d = oc.to_dict()
+            assert not (set(d) & set(merged))
+            merged.update(d)
+            lines, occ = oc.lines, oc.occurrences
+            oc.free()
+            del kp
+        if fits:
+            assert failed == 0 and merged == exp
+            assert (lines, occ) == (single.lines, single.occurrences)
+        else:
+            # an owner whose segments all fitted is complete for the k-mers it owns; the others refused
+            assert failed >= 1 and all(exp.get(key) == v for key, v in merged.items())
+        for c in locals_:
+            c.free()
+    single.free()

@@ -1026,12 +1026,13 @@ extern "C" int kj_counts_add_buffer(kj_counts *c, const uint8_t *buf, uint64_t n
     return KJ_OK;
 }
 
-// pread of [off, off + len) by up to sixteen threads (page-cache / tmpfs copies scale with threads: the read is what
-// bounds the file leg, 13 GB/s with four of them, 18.6 GB/s with eight); environment KJ_READ_THREADS overrides
+// pread of [off, off + len) by three threads per four cores, twelve at most (page-cache / tmpfs copies scale with threads
+// up to there on a 16-core host: 15.4 / 20.3 / 23.4 / 21.8 GB/s with 4 / 8 / 12 / 16, profiles/r02_file_leg_threads.txt: the
+// read is what bounds the file leg); environment KJ_READ_THREADS overrides
 static bool read_range(int fd, uint8_t *dst, uint64_t off, uint64_t len) {
     const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
     const char *env = getenv("KJ_READ_THREADS");
-    const unsigned want = env && *env ? (unsigned)std::max(1, atoi(env)) : std::min(16u, hw);
+    const unsigned want = env && *env ? (unsigned)std::max(1, atoi(env)) : std::max(1u, std::min(12u, hw * 3u / 4u));
     const unsigned nt = len >= (8u << 20) ? std::min(want, 64u) : 1u;
     std::atomic<bool> ok(true);
     auto part = [&](unsigned i) {

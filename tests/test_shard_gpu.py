@@ -334,7 +334,7 @@ def test_fixed_capacity_exchange_emulated(prefix, k):
     single.add_host(data, final=True)
     single.finish()
     exp = single.to_dict()
-    for cap_reg, cap_irr, fits in ((1 << 15, 1 << 12, True), (8, 2, False)):
+    for cap_reg, cap_irr, fits in ((1 << 17, 1 << 15, True), (8, 2, False)):     # 2000 dense reads: ~45 k records per segment
         ranges = kdist.plan_ranges(len(data), world, halo=64)
         whole = DevBuf(data)
         stats = [count_newlines_device(whole.ptr + lo, own) for lo, own, _ in ranges]

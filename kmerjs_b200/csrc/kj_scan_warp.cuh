@@ -564,8 +564,8 @@ __device__ __forceinline__ void kj_resolve_entry(const KjScanArgs &a, const uint
 #ifndef KJ_RS_MINB
 #define KJ_RS_MINB 4
 #endif
-#ifndef KJ_RS_AHEAD
-#define KJ_RS_AHEAD 1              // the lines-before-the-tile lookup of a round is requested a round ahead
+#ifndef KJ_RS_PER
+#define KJ_RS_PER 1                // entries per lane and round of the filter stage
 #endif
 #define KJ_RS_QUEUE 128u           // ring of entries per warp: at most 31 + KJ_RS_LAG left over + 32 new ones
 struct KjResolveSmem {
@@ -597,57 +597,55 @@ __global__ void __launch_bounds__(256, KJ_RS_MINB) kj_resolve_kernel(const __gri
     const uint4 *ent = reinterpret_cast<const uint4 *>(a.cand);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long rounds = (n_ent + stride - 1) / stride;      // the same trip count for every thread (warp collectives inside)
+    // KJ_RS_PER entries per lane and round: their loads (entry, then lines before the tile) are in flight together, and the
+    // fixed cost of a round is shared
+    const unsigned long long per_round = stride * KJ_RS_PER;
+    const unsigned long long rounds = (n_ent + per_round - 1) / per_round;    // the same trip count for every thread (warp collectives inside)
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const uint4 none = make_uint4(0, 0, 0, 0);
     uint32_t q_head = 0, q_n = 0;
-#if KJ_RS_AHEAD
-    // entry r + 2 and the line count of entry r + 1 are in flight while round r works
-    uint4 rec1 = i < n_ent ? ent[i] : none, rec2 = i + stride < n_ent ? ent[i + stride] : none;
-    if (a.resolve_retry && !(rec1.y & KJ_ENT_RETRY32)) rec1.z = 0;
-    uint64_t excl1 = rec1.z ? a.tile_excl[kj_ent_chunk(rec1) / KJ_WT_CHUNKS] : 0;
-    for (unsigned long long r = 0; r < rounds; ++r, i += stride) {
-        uint4 rec = rec1;
-        const uint64_t lines0 = base_lines + excl1;
-        rec1 = rec2;
-        if (a.resolve_retry && !(rec1.y & KJ_ENT_RETRY32)) rec1.z = 0;
-        excl1 = rec1.z ? a.tile_excl[kj_ent_chunk(rec1) / KJ_WT_CHUNKS] : 0;
-        rec2 = i + 2 * stride < n_ent ? ent[i + 2 * stride] : none;
-        rec.z = kj_ent_line_filter(rec, lines0);
-#else
-    uint4 rec_next = i < n_ent ? ent[i] : none;
-    for (unsigned long long r = 0; r < rounds; ++r, i += stride) {
-        uint4 rec = rec_next;
-        rec_next = i + stride < n_ent ? ent[i + stride] : none;           // in flight while this round works
-        if (a.resolve_retry && !(rec.y & KJ_ENT_RETRY32)) rec.z = 0;
-        uint64_t lines0 = 0;
-        if (rec.z) {
-            lines0 = base_lines + a.tile_excl[kj_ent_chunk(rec) / KJ_WT_CHUNKS];
-            rec.z = kj_ent_line_filter(rec, lines0);
+    uint4 rec_next[KJ_RS_PER];
+#pragma unroll
+    for (int j = 0; j < KJ_RS_PER; ++j) rec_next[j] = i + j * stride < n_ent ? ent[i + j * stride] : none;
+    for (unsigned long long r = 0; r < rounds; ++r, i += per_round) {
+        uint4 rec[KJ_RS_PER];
+        uint64_t lines0[KJ_RS_PER];
+#pragma unroll
+        for (int j = 0; j < KJ_RS_PER; ++j) {
+            rec[j] = rec_next[j];
+            const unsigned long long nx = i + per_round + j * stride;
+            rec_next[j] = nx < n_ent ? ent[nx] : none;                    // in flight while this round works
+            if (a.resolve_retry && !(rec[j].y & KJ_ENT_RETRY32)) rec[j].z = 0;
         }
-#endif
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, rec.z != 0u);
-        if (rec.z) {
-            const uint32_t at = (q_head + q_n + __popc(m & ((1u << lane) - 1u))) & (KJ_RS_QUEUE - 1u);
-            sm.rec[warp][at] = rec;
-            sm.lines0[warp][at] = lines0;
-            sm.idx[warp][at] = i;
-            const uint32_t bit = __ffs(rec.z) - 1;
-            const uint64_t pos = kj_ent_chunk(rec) * 16u + (bit >> 1);
-            const uint64_t j = (bit & 1u) ? (pos >= a.rc_shift ? pos - a.rc_shift : 0) : pos;
-            if (j < a.n) {
-                kj_prefetch_l2(a.buf + (j & ~31ull));
-                if ((j & 31u) + a.k > 32u && (j | 31ull) + 1 < a.n) kj_prefetch_l2(a.buf + (j | 31ull) + 1);
+#pragma unroll
+        for (int j = 0; j < KJ_RS_PER; ++j)
+            lines0[j] = rec[j].z ? base_lines + a.tile_excl[kj_ent_chunk(rec[j]) / KJ_WT_CHUNKS] : 0;
+#pragma unroll
+        for (int j = 0; j < KJ_RS_PER; ++j) {
+            rec[j].z = kj_ent_line_filter(rec[j], lines0[j]);
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, rec[j].z != 0u);
+            if (rec[j].z) {
+                const uint32_t at = (q_head + q_n + __popc(m & ((1u << lane) - 1u))) & (KJ_RS_QUEUE - 1u);
+                sm.rec[warp][at] = rec[j];
+                sm.lines0[warp][at] = lines0[j];
+                sm.idx[warp][at] = i + j * stride;
+                const uint32_t bit = __ffs(rec[j].z) - 1;
+                const uint64_t pos = kj_ent_chunk(rec[j]) * 16u + (bit >> 1);
+                const uint64_t jw = (bit & 1u) ? (pos >= a.rc_shift ? pos - a.rc_shift : 0) : pos;
+                if (jw < a.n) {
+                    kj_prefetch_l2(a.buf + (jw & ~31ull));
+                    if ((jw & 31u) + a.k > 32u && (jw | 31ull) + 1 < a.n) kj_prefetch_l2(a.buf + (jw | 31ull) + 1);
+                }
             }
-        }
-        q_n += __popc(m);
-        __syncwarp();
-        if (q_n >= 32u + KJ_RS_LAG) {
-            const uint32_t at = (q_head + lane) & (KJ_RS_QUEUE - 1u);
-            kj_resolve_entry<KW>(a, sm.rec[warp][at], sm.lines0[warp][at], sm.idx[warp][at], n_emit, n_fail);
-            q_head = (q_head + 32u) & (KJ_RS_QUEUE - 1u);
-            q_n -= 32u;
+            q_n += __popc(m);
             __syncwarp();
+            if (q_n >= 32u + KJ_RS_LAG) {
+                const uint32_t at = (q_head + lane) & (KJ_RS_QUEUE - 1u);
+                kj_resolve_entry<KW>(a, sm.rec[warp][at], sm.lines0[warp][at], sm.idx[warp][at], n_emit, n_fail);
+                q_head = (q_head + 32u) & (KJ_RS_QUEUE - 1u);
+                q_n -= 32u;
+                __syncwarp();
+            }
         }
     }
     for (; q_n; q_n -= min(q_n, 32u), q_head = (q_head + 32u) & (KJ_RS_QUEUE - 1u)) {

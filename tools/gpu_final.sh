@@ -10,7 +10,7 @@ import json; d=json.load(open('gpurun_out/bench.json')); r=d['roofline']
 print('N=1 value', round(d['value'],1), 'ms/step', round(d['ms_per_step'],3), 'scan', round(r['scan_kernel_ms'],3), 'resolve', round(r['resolve_kernel_ms'],3), 'frac', round(r['frac'],3), 'share', round(r['kernel_share_of_step'],3), 'e2e', round(d['e2e']['value'],2), 'file', d['e2e'].get('file',{}).get('value'), 'parity', d.get('parity_checked'))"
 tail -3 gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "reference rc=$?"; cut -c1-300 gpurun_out/bench_ref.json
-timeout 600 python tools/exp/file_leg.py > gpurun_out/file_leg.txt 2>&1; echo "file leg rc=$?"; cat gpurun_out/file_leg.txt | tail -14
+
 SHORT="python bench.py --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-file-leg"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv $SHORT > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 ncu --set full --clock-control none --import-source on -k "regex:kj_warp_filter|kj_resolve" -s 6 -c 2 -f -o gpurun_out/prof_scan $SHORT > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"

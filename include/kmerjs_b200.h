@@ -109,7 +109,10 @@ int kj_counts_create(kj_ctx *ctx, const kj_count_params *p, kj_counts **out);
  * KJ_MEM_HOST buffers are staged through pinned memory in chunks with copy/compute overlap. */
 int kj_counts_add_buffer(kj_counts *c, const uint8_t *buf, uint64_t n, uint64_t own_n,
                          int mem_kind, int final);
-/* Convenience: whole file (KmerJS#readFile, env='node', lib/kmers.js:138-139). */
+/* Whole file (KmerJS#readFile, env='node', lib/kmers.js:138-139): reader threads fill two pinned staging buffers of
+ * kj_set_stage_chunk bytes while the other one is copied to the device and counted.  A file that starts with the gzip
+ * magic (1f 8b; any number of members) is inflated by zlib on the reader thread into the same buffers -- an ingest format
+ * the reference does not have; kj_counts_bytes_read then counts the inflated bytes.  KJ_E_IO on read / stream errors. */
 int kj_counts_add_file(kj_counts *c, const char *path);
 /* Wait for the device, build the compact (key,count,ordinal) list.  After this the handle is
  * read-only for add_*; merge/score/export are allowed. */

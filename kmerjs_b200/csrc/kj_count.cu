@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <future>
 #include <thread>
+#include <zlib.h>
 #include <cstring>
 #include <fcntl.h>
 #include <sys/stat.h>
@@ -1050,6 +1051,68 @@ static bool read_range(int fd, uint8_t *dst, uint64_t off, uint64_t len) {
     return ok;
 }
 
+// gzip'd FASTQ (an ingest format the reference does not have: SURVEY.md 8f rank 4).  zlib inflates on the reader thread
+// straight into the pinned staging buffers; pieces, halos and the copy / count overlap are those of the plain file, except
+// that the length of the stream is only known at its end: a piece is final when the stream ended inside its halo.
+struct KjGzFill { uint64_t n; bool eof; bool ok; };
+static int add_file_gz(kj_counts *c, int fd, const char *path) {
+    kj_ctx *ctx = c->ctx;
+    const uint64_t halo = (c->use_filter || c->use_dense) ? 64 : KJ_STAGE_HALO_LINES;
+    const uint64_t chunk = KJ_STAGE_CHUNK;
+    int rc = KJ_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) rc = kj_fail(ctx, KJ_E_CUDA, "cudaSetDevice");
+    if (rc == KJ_OK) rc = ensure_staging(ctx, true);
+    gzFile gz = rc == KJ_OK ? gzdopen(fd, "rb") : nullptr;          // owns fd from here on
+    if (!gz) { close(fd); return rc ? rc : kj_fail(ctx, KJ_E_IO, std::string("cannot read ") + path); }
+    gzbuffer(gz, 1u << 20);
+    auto fill = [&, gz](int s, const uint8_t *carry, uint64_t carry_n) -> KjGzFill {
+        uint8_t *dst = ctx->h_stage[s];
+        if (carry_n) memcpy(dst, carry, carry_n);
+        uint64_t n = carry_n;
+        const uint64_t want = chunk + halo;
+        while (n < want) {
+            const int r = gzread(gz, dst + n, (unsigned)std::min<uint64_t>(want - n, 1u << 30));
+            if (r < 0) return {n, false, false};
+            if (r == 0) {
+                // end of the stream -- or of a truncated file: zlib reports that one only through gzerror
+                int zerr = Z_OK;
+                gzerror(gz, &zerr);
+                return {n, true, zerr == Z_OK || zerr == Z_STREAM_END};
+            }
+            n += (uint64_t)r;
+        }
+        return {n, false, true};
+    };
+    uint64_t total = 0;
+    std::future<KjGzFill> fut = std::async(std::launch::async, fill, 0, (const uint8_t *)nullptr, (uint64_t)0);
+    for (size_t i = 0; rc == KJ_OK; ++i) {
+        const int s = (int)(i & 1);
+        const KjGzFill f = fut.get();
+        if (!f.ok) { rc = kj_fail(ctx, KJ_E_IO, std::string("gzip stream error in ") + path); break; }
+        // the stream ended inside this piece's halo (or before): it owns everything it holds and is the last one
+        const bool final_ = f.eof && (f.n <= chunk || f.n - chunk < 32);
+        const uint64_t own = final_ ? f.n : chunk;
+        if (!final_) {
+            // the other pinned buffer was the source of the copy of piece i - 1
+            if (i >= 1 && cudaEventSynchronize(ctx->ev_copy[s ^ 1]) != cudaSuccess) { rc = kj_fail(ctx, KJ_E_CUDA, "cudaEventSynchronize"); break; }
+            fut = std::async(std::launch::async, fill, s ^ 1, (const uint8_t *)(ctx->h_stage[s] + own), f.n - own);
+        }
+        total += own;
+        if (f.n) {
+            cudaError_t e = cudaMemcpyAsync(ctx->d_stage[s], ctx->h_stage[s], f.n, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copy[s], ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[s], 0);
+            if (e != cudaSuccess) { rc = kj_fail(ctx, KJ_E_CUDA, std::string("kj_counts_add_file: ") + cudaGetErrorString(e)); break; }
+            rc = scan_device(c, ctx->d_stage[s], f.n, own, final_ ? 1 : 0);
+        }
+        if (final_) break;
+    }
+    if (fut.valid()) fut.wait();
+    gzclose(gz);
+    if (rc == KJ_OK) { c->bytes_read = total; c->saw_final = true; }
+    return rc;
+}
+
 // KmerJS#readFile (lib/kmers.js:106-185): the file in staging chunks through two pinned buffers of the context; a
 // reader thread fills one while the other is copied to the device and counted.
 extern "C" int kj_counts_add_file(kj_counts *c, const char *path) {
@@ -1061,6 +1124,10 @@ extern "C" int kj_counts_add_file(kj_counts *c, const char *path) {
     if (fd < 0) return kj_fail(ctx, KJ_E_IO, std::string("cannot open ") + path);
     struct stat st;
     if (fstat(fd, &st) != 0) { close(fd); return kj_fail(ctx, KJ_E_IO, std::string("cannot stat ") + path); }
+    {
+        uint8_t magic[2] = {0, 0};
+        if (pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1F && magic[1] == 0x8B) return add_file_gz(c, fd, path);
+    }
     const uint64_t size = (uint64_t)st.st_size;
     const uint64_t halo = (c->use_filter || c->use_dense) ? 64 : KJ_STAGE_HALO_LINES;
     const uint64_t chunk = KJ_STAGE_CHUNK;

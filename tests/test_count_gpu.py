@@ -345,3 +345,44 @@ def test_file_tail_shorter_than_the_halo(tmp_path, ctx, extra):
         c.free()
     finally:
         ctx.set_stage_chunk(64 << 20)
+
+
+@pytest.mark.parametrize("extra", [0, 1, 31, 33, 64, 65, 5000])
+def test_gzip_file_is_inflated_into_the_staging_buffers(tmp_path, ctx, extra):
+    """readFile() on a gzip'd FASTQ (kj_counts_add_file sees the magic and inflates on the reader thread): several staging
+    pieces, the end of the stream falling at / just behind / inside the halo of a piece boundary, two gzip members in one
+    file; the same map, Map order, line and byte counts as the oracle on the plain bytes.  A truncated stream is an error."""
+    import gzip
+    from util import emulated
+    chunk = (1 << 18) if emulated() else (1 << 20)
+    ctx.set_stage_chunk(chunk)
+    try:
+        rng = random.Random(7000 + extra)
+        size = 2 * chunk + extra
+        data = random_fastq(rng, size // 250 + 50, min_len=100, max_len=140)[:size]
+        assert len(data) == size
+        path = tmp_path / "reads.fastq.gz"
+        cut = size // 3
+        path.write_bytes(gzip.compress(data[:cut], 1) + gzip.compress(data[cut:], 6))       # two members
+        for prefix, k in ((b"ATGAC", 16), (b"", 31)) if extra in (0, 33) else ((b"ATGAC", 16),):
+            c = Counts(prefix, k, 1)
+            c.add_file(str(path)).finish()
+            assert (list(c.to_dict().items()), c.lines) == oracle(data, prefix, k, 1)
+            assert c.bytes_read == size
+            c.free()
+        if extra == 5000:
+            blob = path.read_bytes()
+            bad = tmp_path / "truncated.fastq.gz"
+            bad.write_bytes(blob[: len(blob) // 2])
+            c = Counts(b"ATGAC", 16, 1)
+            with pytest.raises(_abi.KjError):
+                c.add_file(str(bad))
+            c.free()
+            empty = tmp_path / "empty.fastq.gz"
+            empty.write_bytes(gzip.compress(b""))
+            c = Counts(b"ATGAC", 16, 1)
+            c.add_file(str(empty)).finish()
+            assert c.size == 0 and c.lines == 0
+            c.free()
+    finally:
+        ctx.set_stage_chunk(64 << 20)

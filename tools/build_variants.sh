@@ -11,7 +11,7 @@ while [ $# -ge 2 ]; do
   ( nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function $flags \
       -c kmerjs_b200/csrc/kj_count.cu -o build/var/$name.o &&
     nvcc -shared -o kmerjs_b200/variants/$name.so build/var/$name.o build/obj/kj_ctx.o build/obj/kj_score.o build/obj/kj_dbio.o \
-      build/obj/kj_synth.o build/obj/kj_stats.o -gencode arch=compute_100a,code=sm_100a && echo "built $name ($flags)" ) &
+      build/obj/kj_synth.o build/obj/kj_stats.o -gencode arch=compute_100a,code=sm_100a -lz && echo "built $name ($flags)" ) &
 done
 wait
 ls -la kmerjs_b200/variants/

@@ -16,5 +16,5 @@ done
 g++ $FLAGS -c tools/cuemu/emu.cpp -o build/emu/emu.o &
 pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
-g++ -shared $SAN -o build/emu/libkmerjs_b200_emu.so build/emu/*.o
+g++ -shared $SAN -o build/emu/libkmerjs_b200_emu.so build/emu/*.o -lz
 echo build/emu/libkmerjs_b200_emu.so

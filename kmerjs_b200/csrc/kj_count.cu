@@ -1273,10 +1273,12 @@ extern "C" int kj_counts_finish(kj_counts *c) {
     bool spec = (c->pending || c->exchange_totals) && c->capacity_hint != 0;
     int rc = KJ_OK;
     for (;;) {
-        uint64_t cap_tab, cap_irr;
+        uint64_t cap_tab, cap_irr, irr_copied = 0;
         if (spec) {
             cap_tab = c->capacity_hint;
-            cap_irr = std::min<uint64_t>(c->irr_cap, 4096);
+            // room for 65536 irregular k-mers in the compaction; the first 8192 come back with the counters, a larger set
+            // takes one more copy (10 M reads of the bench workload leave some 10^4 of them: reads with N)
+            cap_irr = std::min<uint64_t>(c->irr_cap, 65536);
         } else {
             rc = settle_filter(c);
             if (rc) return rc;
@@ -1308,13 +1310,21 @@ extern "C" int kj_counts_finish(kj_counts *c) {
                       c->ctr, d_irr, cap_irr);
             ctx->launches++;
             if (cap_irr <= irr_device_sort_min() || cap_irr >= 0x7FFFFFFFull || spec) {
+                irr_copied = spec ? std::min<uint64_t>(cap_irr, 8192) : cap_irr;
                 c->irr_host.resize(cap_irr * sizeof(KjIrrRecord));
-                cudaError_t e = cudaMemcpyAsync(c->irr_host.data(), d_irr, cap_irr * sizeof(KjIrrRecord),
+                cudaError_t e = cudaMemcpyAsync(c->irr_host.data(), d_irr, irr_copied * sizeof(KjIrrRecord),
                                                 cudaMemcpyDeviceToHost, ctx->stream);
                 if (e != cudaSuccess) { kj_dfree(ctx, d_irr); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
             }
         }
         rc = pull_counters(c);           // the one wait: n_compact and (a small set of) irregular records are back with it
+        if (rc == KJ_OK && spec && d_irr && c->h_ctr->n_irr_unique > irr_copied && c->h_ctr->n_irr_unique <= cap_irr) {
+            // more irregular k-mers than came back with the counters: the rest of the compacted records
+            cudaError_t e = cudaMemcpyAsync(c->irr_host.data() + irr_copied * sizeof(KjIrrRecord), d_irr + irr_copied,
+                                            (c->h_ctr->n_irr_unique - irr_copied) * sizeof(KjIrrRecord), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { kj_dfree(ctx, d_irr); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
+        }
         if (rc == KJ_OK && cap_irr > irr_device_sort_min() && cap_irr < 0x7FFFFFFFull && !spec) {
             rc = irregular_sorted_on_device(c, d_irr, c->h_ctr->n_irr_unique, c->h_ctr->n_unique + (c->h_ctr->special_count ? 1 : 0));
             irr_on_device = (rc == KJ_OK);

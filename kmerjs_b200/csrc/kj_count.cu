@@ -1207,6 +1207,73 @@ static uint64_t irr_device_sort_min() {
     return e && *e ? strtoull(e, nullptr, 10) : 65536ull;
 }
 
+// The single-wait finish does the same without knowing any count on the host: d_irr has `cap` slots (unused ones all
+// ones, so that they sort last), the numbers come from the device counters, and nothing waits.
+__global__ void kj_irr_gather_spec_kernel(const KjIrrRecord *rec, const uint32_t *perm, uint64_t cap, const KjCounters *ctr,
+                                          uint64_t cap_tab, KjIrrRecord *sorted, uint64_t *keys, uint64_t *counts, uint64_t *ords) {
+    unsigned long long n_tab = 0;
+    for (int i = 0; i < 64; ++i) n_tab += ctr->n_unique_part[i];
+    if (n_tab > cap_tab) return;                           // the compaction did not fit: the host takes the long way
+    const uint64_t n = ctr->n_irr_compact < cap ? ctr->n_irr_compact : cap;
+    const uint64_t base = n_tab + (ctr->special_count ? 1ull : 0ull);
+    const uint64_t total = n * 7;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = w / 7, part = w % 7;
+        const uint64_t v = reinterpret_cast<const uint64_t *>(rec + (perm ? perm[i] : i))[part];
+        reinterpret_cast<uint64_t *>(sorted + i)[part] = v;
+        if (part == 0) keys[base + i] = ~0ull;
+        if (part == 5) counts[base + i] = v;
+        if (part == 6) ords[base + i] = v;
+    }
+}
+struct KjIrrSpec { KjIrrRecord *sorted = nullptr; void *tmp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; };
+static void irregular_spec_free(kj_ctx *ctx, KjIrrSpec &q) {
+    kj_dfree(ctx, q.sorted);
+    for (void *p : q.tmp) kj_dfree(ctx, p);
+    q = KjIrrSpec{};
+}
+// queue: sort keys out of the `cap` slots of d_irr, radix sort, gather into q.sorted + the columns behind the table entries
+static int irregular_spec_queue(kj_counts *c, const KjIrrRecord *d_irr, uint64_t cap, uint64_t cap_tab, KjIrrSpec &q) {
+    kj_ctx *ctx = c->ctx;
+    uint64_t *d_ord = nullptr, *d_ord2 = nullptr;
+    uint32_t *d_idx = nullptr, *d_perm = nullptr;
+    void *d_tmp = nullptr;
+    cudaError_t e = kj_dmalloc(ctx, &q.sorted, cap * sizeof(KjIrrRecord));
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_ord, cap * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_ord2, cap * 8);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_idx, cap * 4);
+    if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_perm, cap * 4);
+    q.tmp[0] = d_ord; q.tmp[1] = d_ord2; q.tmp[2] = d_idx; q.tmp[3] = d_perm;
+    if (e == cudaSuccess) {
+        KJ_LAUNCH(kj_irr_sortkeys_kernel, grid_for(ctx, cap), 256, 0, ctx->stream, d_irr, cap, d_ord, d_idx);
+        ctx->launches++;
+#ifndef KJ_CPU_EMU
+        size_t tmp_bytes = 0;
+        e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_ord, d_ord2, d_idx, d_perm, (int)cap, 0, 64, ctx->stream);
+        if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_tmp, std::max<size_t>(tmp_bytes, 16));
+        q.tmp[4] = d_tmp;
+        if (e == cudaSuccess)
+            e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_ord, d_ord2, d_idx, d_perm, (int)cap, 0, 64, ctx->stream);
+        ctx->launches += 4;
+#else
+        {   // tools/cuemu: "device" memory is host memory
+            std::vector<uint32_t> p(cap);
+            for (uint64_t i = 0; i < cap; ++i) p[i] = (uint32_t)i;
+            std::stable_sort(p.begin(), p.end(), [&](uint32_t x, uint32_t y) { return d_irr[x].ord < d_irr[y].ord; });
+            memcpy(d_perm, p.data(), cap * 4);
+        }
+#endif
+    }
+    if (e == cudaSuccess) {
+        KJ_LAUNCH(kj_irr_gather_spec_kernel, grid_for(ctx, cap * 7), 256, 0, ctx->stream, d_irr, d_perm, cap, c->ctr, cap_tab,
+                  q.sorted, c->reg.keys, c->reg.counts, c->reg.ords);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { irregular_spec_free(ctx, q); return kj_fail(ctx, KJ_E_CUDA, std::string("kj_counts_finish (irregular k-mers): ") + cudaGetErrorString(e)); }
+    return KJ_OK;
+}
+
 // d_irr: the n_irr compacted records in slot order.  Leaves them sorted in c->irr_host and writes the key (unused: all ones),
 // count and ordinal columns of the compact arrays from entry n_reg on.
 static int irregular_sorted_on_device(kj_counts *c, const KjIrrRecord *d_irr, uint64_t n_irr, uint64_t n_reg) {
@@ -1304,27 +1371,38 @@ extern "C" int kj_counts_finish(kj_counts *c) {
             ctx->launches++;
         }
         KjIrrRecord *d_irr = nullptr;
+        KjIrrSpec irr_spec;
+        // single-wait path with first-seen order: the records are sorted and their columns written on the device, queued
+        // with everything else (the host sort of some 10^4 records was 0.15 ms between two kernels of the bench step)
+        const bool spec_sort = spec && c->order && cap_irr > 1;
         if (cap_irr && c->irr_cap) {
             KJ_CUDA(ctx, kj_dmalloc(ctx, &d_irr, cap_irr * sizeof(KjIrrRecord)));
+            if (spec_sort) KJ_CUDA(ctx, cudaMemsetAsync(d_irr, 0xFF, cap_irr * sizeof(KjIrrRecord), ctx->stream));
             KJ_LAUNCH(kj_compact_irr_kernel, grid_for(ctx, c->irr_cap), 256, 0, ctx->stream, c->irr, c->irr_cap,
                       c->ctr, d_irr, cap_irr);
             ctx->launches++;
+            if (spec_sort) {
+                rc = irregular_spec_queue(c, d_irr, cap_irr, cap_tab, irr_spec);
+                if (rc) { kj_dfree(ctx, d_irr); return rc; }
+            }
             if (cap_irr <= irr_device_sort_min() || cap_irr >= 0x7FFFFFFFull || spec) {
                 irr_copied = spec ? std::min<uint64_t>(cap_irr, 8192) : cap_irr;
                 c->irr_host.resize(cap_irr * sizeof(KjIrrRecord));
-                cudaError_t e = cudaMemcpyAsync(c->irr_host.data(), d_irr, irr_copied * sizeof(KjIrrRecord),
+                cudaError_t e = cudaMemcpyAsync(c->irr_host.data(), spec_sort ? irr_spec.sorted : d_irr, irr_copied * sizeof(KjIrrRecord),
                                                 cudaMemcpyDeviceToHost, ctx->stream);
-                if (e != cudaSuccess) { kj_dfree(ctx, d_irr); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
+                if (e != cudaSuccess) { kj_dfree(ctx, d_irr); irregular_spec_free(ctx, irr_spec); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
             }
         }
         rc = pull_counters(c);           // the one wait: n_compact and (a small set of) irregular records are back with it
         if (rc == KJ_OK && spec && d_irr && c->h_ctr->n_irr_unique > irr_copied && c->h_ctr->n_irr_unique <= cap_irr) {
             // more irregular k-mers than came back with the counters: the rest of the compacted records
-            cudaError_t e = cudaMemcpyAsync(c->irr_host.data() + irr_copied * sizeof(KjIrrRecord), d_irr + irr_copied,
+            cudaError_t e = cudaMemcpyAsync(c->irr_host.data() + irr_copied * sizeof(KjIrrRecord),
+                                            (spec_sort ? irr_spec.sorted : d_irr) + irr_copied,
                                             (c->h_ctr->n_irr_unique - irr_copied) * sizeof(KjIrrRecord), cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) { kj_dfree(ctx, d_irr); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
+            if (e != cudaSuccess) { kj_dfree(ctx, d_irr); irregular_spec_free(ctx, irr_spec); return kj_fail(ctx, KJ_E_CUDA, cudaGetErrorString(e)); }
         }
+        irregular_spec_free(ctx, irr_spec);
         if (rc == KJ_OK && cap_irr > irr_device_sort_min() && cap_irr < 0x7FFFFFFFull && !spec) {
             rc = irregular_sorted_on_device(c, d_irr, c->h_ctr->n_irr_unique, c->h_ctr->n_unique + (c->h_ctr->special_count ? 1 : 0));
             irr_on_device = (rc == KJ_OK);
@@ -1338,6 +1416,7 @@ extern "C" int kj_counts_finish(kj_counts *c) {
         if (fits) {
             if (c->piece->timed) { rc = account_scan_time(c, c->piece->args.own_n, true); if (rc) return rc; c->piece->timed = false; }
             c->pending = false;
+            irr_on_device = spec_sort && cap_irr && c->irr_cap;
             break;
         }
         spec = false;                    // the long way: settle (retries, growth), then compact with the exact sizes

@@ -1232,13 +1232,26 @@ static void irregular_spec_free(kj_ctx *ctx, KjIrrSpec &q) {
     for (void *p : q.tmp) kj_dfree(ctx, p);
     q = KjIrrSpec{};
 }
-// queue: sort keys out of the `cap` slots of d_irr, radix sort, gather into q.sorted + the columns behind the table entries
-static int irregular_spec_queue(kj_counts *c, const KjIrrRecord *d_irr, uint64_t cap, uint64_t cap_tab, KjIrrSpec &q) {
+// queue: (sort: sort keys out of the `cap` slots of d_irr, radix sort,) gather into q.sorted + the columns behind the table
+// entries.  Without the sort the records keep the order the compaction gave them: the order of the query entries inside a
+// handle is not observable (exports are sorted by first-seen ordinal on the device, matches go by key), and a radix sort of
+// a few thousand records is eight passes of launch latency (0.1 ms) between the kernels of a step.
+static int irregular_spec_queue(kj_counts *c, const KjIrrRecord *d_irr, uint64_t cap, uint64_t cap_tab, KjIrrSpec &q, bool sort) {
     kj_ctx *ctx = c->ctx;
     uint64_t *d_ord = nullptr, *d_ord2 = nullptr;
     uint32_t *d_idx = nullptr, *d_perm = nullptr;
     void *d_tmp = nullptr;
     cudaError_t e = kj_dmalloc(ctx, &q.sorted, cap * sizeof(KjIrrRecord));
+    if (!sort) {
+        if (e == cudaSuccess) {
+            KJ_LAUNCH(kj_irr_gather_spec_kernel, grid_for(ctx, cap * 7), 256, 0, ctx->stream, d_irr, (const uint32_t *)nullptr, cap, c->ctr,
+                      cap_tab, q.sorted, c->reg.keys, c->reg.counts, c->reg.ords);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) { irregular_spec_free(ctx, q); return kj_fail(ctx, KJ_E_CUDA, std::string("kj_counts_finish (irregular k-mers): ") + cudaGetErrorString(e)); }
+        return KJ_OK;
+    }
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_ord, cap * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_ord2, cap * 8);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &d_idx, cap * 4);
@@ -1374,15 +1387,16 @@ extern "C" int kj_counts_finish(kj_counts *c) {
         KjIrrSpec irr_spec;
         // single-wait path with first-seen order: the records are sorted and their columns written on the device, queued
         // with everything else (the host sort of some 10^4 records was 0.15 ms between two kernels of the bench step)
-        const bool spec_sort = spec && c->order && cap_irr > 1;
+        const bool spec_sort = spec && cap_irr > 1;
         if (cap_irr && c->irr_cap) {
             KJ_CUDA(ctx, kj_dmalloc(ctx, &d_irr, cap_irr * sizeof(KjIrrRecord)));
-            if (spec_sort) KJ_CUDA(ctx, cudaMemsetAsync(d_irr, 0xFF, cap_irr * sizeof(KjIrrRecord), ctx->stream));
+            const bool sort_on_device = getenv("KJ_SPEC_SORT_IRREGULAR") != nullptr;        // developer switch: keep first-seen order inside the handle
+            if (spec_sort && sort_on_device) KJ_CUDA(ctx, cudaMemsetAsync(d_irr, 0xFF, cap_irr * sizeof(KjIrrRecord), ctx->stream));
             KJ_LAUNCH(kj_compact_irr_kernel, grid_for(ctx, c->irr_cap), 256, 0, ctx->stream, c->irr, c->irr_cap,
                       c->ctr, d_irr, cap_irr);
             ctx->launches++;
             if (spec_sort) {
-                rc = irregular_spec_queue(c, d_irr, cap_irr, cap_tab, irr_spec);
+                rc = irregular_spec_queue(c, d_irr, cap_irr, cap_tab, irr_spec, sort_on_device);
                 if (rc) { kj_dfree(ctx, d_irr); return rc; }
             }
             if (cap_irr <= irr_device_sort_min() || cap_irr >= 0x7FFFFFFFull || spec) {

@@ -69,6 +69,7 @@ struct kj_match {
     uint64_t hits0 = 0;
     uint64_t kmer_map_size = 0;
     uint64_t seg_entries = 0, seg_pairs = 0;   // kj_match_from_segments: what the ranks really sent
+    uint64_t pair_bound = 0;         // upper bound of the matched template-list entries, known without asking the device (0: unknown)
     uint32_t max_hits = 100, hit_counter = 0;
     bool ended = false;
     bool inflight = false;           // the argmax of the next round has been launched ahead
@@ -828,6 +829,7 @@ extern "C" int kj_first_match_local(kj_ctx *ctx, kj_counts *q, const kj_db *db, 
     m->T = db->n_templates;
     m->Q = q->reg.n;
     m->kmer_map_size = q->reg.n;
+    m->pair_bound = db->n_pairs;                      // every matched list is one of the DB's
     const uint64_t T = m->T;
     cudaError_t e = kj_dmalloc(ctx, &m->d_qkmer, std::max<uint64_t>(m->Q, 1) * 4);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->d_part, (2 * T + 1) * 8);
@@ -1111,6 +1113,7 @@ extern "C" int kj_match_from_segments(kj_ctx *ctx, const kj_db *db, uint32_t n_s
     m->T = db->n_templates;
     m->Q = Q;
     m->from_segments = true;
+    m->pair_bound = (uint64_t)n_segments * cap_pairs;
     const uint64_t T = m->T;
     cudaError_t e = kj_dmalloc(ctx, &m->d_qkmer, Q * 4);
     if (e == cudaSuccess) e = kj_dmalloc(ctx, &m->own_count, Q * 8);
@@ -1287,6 +1290,16 @@ extern "C" int kj_match_commit(kj_match *m) {
         ctx->launches += 2;
 #endif
     }
+    // With a bound on the matched list entries the per-template lists are filled before the host knows the hit count: the
+    // one wait of the commit then has nothing queued behind it (without: wait, size the list array, fill)
+    const bool fill_ahead = m->pair_bound && m->pair_bound <= (1ull << 28);
+    if (fill_ahead) {
+        kj_dfree(ctx, m->d_tq);
+        m->d_tq = nullptr;
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_tq, std::max<uint64_t>(m->pair_bound, 1) * 4));
+        rc = m->distributed ? launch_walk<KJ_WALK_FILL>(m) : launch_walk<KJ_WALK_FIRST_FILL>(m);
+        if (rc) return rc;
+    }
     KJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (m->from_segments) {
         if (h[5])
@@ -1298,13 +1311,17 @@ extern "C" int kj_match_commit(kj_match *m) {
     m->hits0 = h[0];
     const uint64_t local_pairs = h[1];
     if (local_pairs > 0xFFFFFFF0ull * 16) return kj_fail(ctx, KJ_E_RANGE, "too many matched pairs");
-    kj_dfree(ctx, m->d_tq);
-    m->d_tq = nullptr;
-    KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_tq, std::max<uint64_t>(local_pairs, 1) * 4));
-    // stream-ordered: whoever reads the lists comes later on the same stream.  On a single GPU first_ord is already global:
-    // the list indices of the first k-mers (the tie order) are taken by the same pass
-    rc = m->distributed ? launch_walk<KJ_WALK_FILL>(m) : launch_walk<KJ_WALK_FIRST_FILL>(m);
-    if (rc) return rc;
+    if (!fill_ahead) {
+        kj_dfree(ctx, m->d_tq);
+        m->d_tq = nullptr;
+        KJ_CUDA(ctx, kj_dmalloc(ctx, &m->d_tq, std::max<uint64_t>(local_pairs, 1) * 4));
+        // stream-ordered: whoever reads the lists comes later on the same stream.  On a single GPU first_ord is already global:
+        // the list indices of the first k-mers (the tie order) are taken by the same pass
+        rc = m->distributed ? launch_walk<KJ_WALK_FILL>(m) : launch_walk<KJ_WALK_FIRST_FILL>(m);
+        if (rc) return rc;
+    } else if (local_pairs > m->pair_bound) {
+        return kj_fail(ctx, KJ_E_CUDA, "internal: matched list entries exceed their bound");
+    }
     m->committed = true;
     return KJ_OK;
 }

@@ -196,3 +196,17 @@ def test_wire_host_side_shapes():
     w = wire.parse_first_match_reply(200, reply.encode())
     assert list(w["templates"]["T1"]["kmers"]) == ["a", "b"] and w["hits"] == 2
     assert wire.post_kmers(b"", None)[0] == 400
+
+
+def test_js_number_prints_like_a_template_string():
+    """Number#toString of JavaScript, which lib/kmerFinderClient.js:195-208 uses for the TSV rows: shortest digits that
+    round-trip, positional notation for 1e-7 <= |x| < 1e21, exponent form outside."""
+    from kmerjs_b200.kmer_finder_client import js_number
+    cases = [(5.0, "5"), (5, "5"), (0.5, "0.5"), (3e-05, "0.00003"), (1e-6, "0.000001"), (1e-7, "1e-7"), (1.5e-7, "1.5e-7"),
+             (123456789.125, "123456789.125"), (1e21, "1e+21"), (1e20, "100000000000000000000"), (-2.5, "-2.5"),
+             (0.0, "0"), (100.0, "100"), (1234.5678, "1234.5678"), (2.220446049250313e-16, "2.220446049250313e-16"),
+             (float("nan"), "NaN"), (float("inf"), "Infinity"), (float("-inf"), "-Infinity"), (99.99, "99.99"),
+             (0.1 + 0.2, "0.30000000000000004"), (1e-10, "1e-10"), (12e22, "1.2e+23")]
+    for x, want in cases:
+        assert js_number(x) == want, (x, js_number(x), want)
+    assert js_number("NC_017625") == "NC_017625" and js_number(True) == "True"
